@@ -1,0 +1,167 @@
+/*
+ * rvio_b200.h -- C ABI of the B200-native R-VIO hot path (librvio_b200.so).
+ *
+ * Drop-in boundary for the two calls System::MonoVIO makes into the hot path
+ *   mpTracker->track(image, imuList)                      src/rvio/System.cc:258   (Tracker.h:50)
+ *   mpUpdater->update(xk1k, Pk1k, types, measurements)     src/rvio/System.cc:268   (Updater.h:43-44)
+ * and for the results the host reads back
+ *   Tracker::mvFeatTypesForUpdate / mvlFeatMeasForUpdate   Tracker.h:70,74
+ *   Updater::xk1k1 / Pk1k1                                 Updater.h:51-52, read at System.cc:270-271
+ *
+ * Conventions: POD only, opaque handles, int status returns (0 = RVIO_OK), no exceptions cross the
+ * boundary, one handle per stream, caller-thread-affine (the reference is single threaded:
+ * src/rvio_mono.cc:127).  All pointers are HOST pointers unless the name says `_dev`.
+ * Doubles at the boundary keep Eigen::VectorXd / MatrixXd (column-major) unchanged on the host.
+ * There is no CPU fallback: every entry point fails with RVIO_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RVIO_B200_H
+#define RVIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVIO_OK               0
+#define RVIO_FIRST_IMAGE      1   /* track(): first image equalised; caller must seed (Tracker.cc:204-234) */
+#define RVIO_NO_FEATURES      2   /* track(): nothing to track, state untouched (Tracker.cc:246-250) */
+#define RVIO_ERR_ARG         -1
+#define RVIO_ERR_CUDA        -2
+#define RVIO_ERR_STATE       -3
+#define RVIO_ERR_CAPACITY    -4
+
+/* ------------------------------------------------------------------------------------------------
+ * Tracker  (replaces class RVIO::Tracker, src/rvio/Tracker.h:43-127, and RVIO::Ransac, Ransac.h:61-131)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvio_tracker rvio_tracker;
+
+/* Every key the Tracker / Ransac constructors read (Tracker.cc:39-79, Ransac.cc:34-46). */
+typedef struct rvio_tracker_cfg {
+    int32_t width, height;            /* Camera.width / Camera.height */
+    float   fx, fy, cx, cy;           /* Camera.fx.. (read into float: Tracker.cc:39-42) */
+    float   k1, k2, p1, p2, k3;       /* Camera.k1.. ; k3 == 0 -> 4-coefficient model (Tracker.cc:56-61) */
+    int32_t is_rgb;                   /* Camera.RGB (channel order for 3/4-channel input, Tracker.cc:183-196) */
+    int32_t is_fisheye;               /* Camera.Fisheye: must be 0 (radtan); 1 -> RVIO_ERR_ARG (not implemented) */
+    int32_t enable_equalizer;         /* Tracker.EnableEqualizer */
+    int32_t n_features;               /* Tracker.nFeatures */
+    int32_t max_track_len;            /* Tracker.nMaxTrackingLength */
+    int32_t min_track_len;            /* Tracker.nMinTrackingLength */
+    int32_t use_sampson;              /* Tracker.UseSampson */
+    double  inlier_thr;               /* Tracker.nInlierThrd */
+    double  small_angle;              /* IMU.nSmallAngle */
+    double  T_BC0[16];                /* Camera.T_BC0, row-major 4x4 */
+} rvio_tracker_cfg;
+
+/* Tracker::Tracker(const cv::FileStorage&)  -- System.cc:97.  device = CUDA ordinal. */
+int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio_tracker** out);
+/* Tracker::~Tracker  -- System.cc:108 */
+void rvio_tracker_destroy(rvio_tracker* trk);
+
+/* Tracker::track(im, lImuData) minus the corner detector  -- Tracker.cc:179-342.
+ *   img: width x height x channels u8 (channels 1, 3 or 4), row stride in bytes.
+ *   imu: n_imu rows of 8 doubles {w[3], a[3], Timestamp, TimeInterval}  (struct ImuData, InputBuffer.h:35-51).
+ * Does gray -> CLAHE -> pyramids -> LK -> undistort -> RANSAC -> bookkeeping on the device.
+ * Returns RVIO_OK, RVIO_FIRST_IMAGE or RVIO_NO_FEATURES (see above).  After RVIO_OK / RVIO_FIRST_IMAGE the caller
+ * runs its detector if it wants to (rvio_tracker_get_image, rvio_tracker_get_tracked_px), hands new corners in with
+ * rvio_tracker_seed / rvio_tracker_refill, and finishes the frame with rvio_tracker_commit (Tracker.cc:389-395). */
+int rvio_tracker_track(rvio_tracker* trk, const uint8_t* img, int width, int height, int stride_bytes,
+                       int channels, const double* imu, int n_imu);
+/* Same, image already resident in device memory (single channel, pitch in bytes). */
+int rvio_tracker_track_dev(rvio_tracker* trk, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu);
+
+/* Equalised current image (what the reference's detector sees: Tracker.cc:207,350). out: width*height bytes. */
+int rvio_tracker_get_image(rvio_tracker* trk, uint8_t* out, int out_stride_bytes);
+/* mlFreeIndices.size() after bookkeeping (Tracker.cc:344) */
+int rvio_tracker_n_free(rvio_tracker* trk, int* n_free);
+/* mvFeatsToTrack after loop 2 (Tracker.cc:313-314): pixel coords of the surviving features. */
+int rvio_tracker_get_tracked_px(rvio_tracker* trk, float* xy /* 2*n_features */, int* n);
+/* First image: Tracker.cc:215-233.  px = detector output (float2 pixels). */
+int rvio_tracker_seed(rvio_tracker* trk, const float* px, int n);
+/* Refill: Tracker.cc:358-386.  px = corners that passed FeatureDetector::FindNewer.  *n_used = how many were taken. */
+int rvio_tracker_refill(rvio_tracker* trk, const float* px, int n, int* n_used);
+/* Tracker.cc:389-395: commit feature set, current image becomes mLastImage. */
+int rvio_tracker_commit(rvio_tracker* trk);
+
+/* Results == public members Tracker.h:70,74 in CSR form: feature f has type types[f] ('1' lost, '2' max length)
+ * and measurements xy[2*offsets[f] .. 2*offsets[f+1]) (normalized, undistorted float2, oldest first). */
+int rvio_tracker_get_update_count(rvio_tracker* trk, int* n_feat, int* n_meas);
+int rvio_tracker_get_update_lists(rvio_tracker* trk, uint8_t* types, int32_t* offsets /* n_feat+1 */, float* xy);
+
+/* Debug / parity observables of the last track() call (all sized n = features fed to LK). */
+int rvio_tracker_get_debug(rvio_tracker* trk, int* n, uint8_t* lk_status, uint8_t* inlier_flags,
+                           float* lk_px /* 2n */, float* undist /* 2n */, int32_t* slots /* n */);
+/* RANSAC internals of the last call: 32 sampled indices, 16 inlier counts, winner, candidates (Ransac.h:43-59). */
+int rvio_tracker_get_ransac_debug(rvio_tracker* trk, int32_t* two_points /* 32 */, int32_t* n_inliers /* 16 */,
+                                  int32_t* winner, int32_t* n_candidates, double* hypotheses /* 16*9 row-major */);
+/* Pyramid level l (0..3) of the current (0) or previous (1) image, for parity tests. out: lw*lh bytes. */
+int rvio_tracker_get_pyramid(rvio_tracker* trk, int which, int level, uint8_t* out, int* lw, int* lh);
+
+/* ------------------------------------------------------------------------------------------------
+ * Updater  (replaces class RVIO::Updater, src/rvio/Updater.h:36-71)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvio_updater rvio_updater;
+
+typedef struct rvio_updater_cfg {
+    float   sigma_px, sigma_py;       /* Camera.sigma_px / sigma_py (read into float: Updater.cc:42-44) */
+    double  T_BC0[16];                /* Camera.T_BC0, row-major 4x4 (Updater.cc:46-53) */
+    int32_t max_clones;               /* capacity: Tracker.nMaxTrackingLength - 1 (System.cc:71-72) */
+    int32_t max_features;             /* capacity: ceil(Tracker.nFeatures / 2) (Tracker.cc:74) */
+    int32_t max_track_len;            /* capacity: Tracker.nMaxTrackingLength */
+} rvio_updater_cfg;
+
+typedef struct rvio_update_info {
+    int32_t n_feat, n_good, rows_stacked, updated;
+    int32_t n_reject_init, n_reject_lm, n_reject_gate;
+} rvio_update_info;
+
+/* Updater::Updater(const cv::FileStorage&)  -- System.cc:98 */
+int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio_updater** out);
+void rvio_updater_destroy(rvio_updater* upd);
+
+/* Updater::update(xk1k, Pk1k, types, meas) + outputs xk1k1 / Pk1k1  -- Updater.cc:72-628.
+ *   x: xdim = 26+7N doubles (layout SURVEY Appendix B), P: d x d column-major, d = 24+6N.
+ *   types/offsets/xy: CSR feature lists as produced by rvio_tracker_get_update_lists.
+ *   x_out/P_out: same shapes.  info may be NULL. */
+int rvio_updater_update(rvio_updater* upd, const double* x, int xdim, const double* P, int d,
+                        const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat,
+                        double* x_out, double* P_out, rvio_update_info* info);
+
+/* Fused form: consume the feature lists of `trk`'s last track() directly from device memory
+ * (no D2H/H2D of the lists); both handles must live on the same device. */
+int rvio_updater_update_from_tracker(rvio_updater* upd, rvio_tracker* trk, const double* x, int xdim,
+                                     const double* P, int d, double* x_out, double* P_out, rvio_update_info* info);
+
+/* Per-feature parity observables of the last update: status (0 accepted, 1 init reject, 2 LM reject, 3 gate reject),
+ * inverse-depth estimate [phi psi rho], Mahalanobis distance, dof. */
+int rvio_updater_get_debug(rvio_updater* upd, int n_feat, uint8_t* status, double* pfinv /* 3n */,
+                           double* gamma, int32_t* dof);
+/* Compressed normal terms of the last update: G = H^T H (n x n, row-major), z = H^T r (n), n = 6N. */
+int rvio_updater_get_normal_terms(rvio_updater* upd, double* G, double* z, int n);
+
+/* Multi-GPU (feature-sharded) form: rank `rank` of `world` processes only the features f with
+ * f % world == rank and leaves its partial normal terms on the device; the host adaptor sums them across ranks
+ * (one ncclAllReduce over [G | z | counters], see r-vio_b200/host) between _begin and _finish. */
+int rvio_updater_update_begin(rvio_updater* upd, const double* x, int xdim, const double* P, int d,
+                              const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat,
+                              int rank, int world);
+/* Device pointer + element count of the contiguous fp64 reduce buffer [G (n*n) | z (n) | counters (8)]. */
+int rvio_updater_reduce_buffer(rvio_updater* upd, double** buf_dev, int* count);
+int rvio_updater_update_finish(rvio_updater* upd, double* x_out, double* P_out, rvio_update_info* info);
+
+/* ------------------------------------------------------------------------------------------------
+ * Misc
+ * ---------------------------------------------------------------------------------------------- */
+const char* rvio_b200_version(void);
+/* Last CUDA / argument error text for this thread. */
+const char* rvio_b200_last_error(void);
+/* Number of kernels launched by this library since load (for bench accounting), and a reset. */
+uint64_t rvio_b200_kernel_launches(void);
+/* Raw CUDA stream used by a handle (so a host can order its own work / events against it). */
+void* rvio_tracker_stream(rvio_tracker* trk);
+void* rvio_updater_stream(rvio_updater* upd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVIO_B200_H */

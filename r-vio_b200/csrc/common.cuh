@@ -1,0 +1,50 @@
+// common.cuh -- shared host/device helpers for librvio_b200.so (sm_100a only, no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/rvio_b200.h"
+
+namespace rvio {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<uint64_t> g_kernel_launches;
+
+inline void set_error(const char* where, const char* what)
+{
+    snprintf(g_last_error, sizeof g_last_error, "%s: %s", where, what);
+}
+
+#define RVIO_CUDA_TRY(expr)                                                             \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            rvio::set_error(#expr, cudaGetErrorString(_e));                             \
+            return RVIO_ERR_CUDA;                                                       \
+        }                                                                               \
+    } while (0)
+
+#define RVIO_ARG_CHECK(cond)                                                            \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            rvio::set_error("argument check failed", #cond);                            \
+            return RVIO_ERR_ARG;                                                        \
+        }                                                                               \
+    } while (0)
+
+// Counts every kernel this library launches (bench.py reports it as gpu_launches).
+#define RVIO_LAUNCH(kernel, grid, block, smem, stream, ...)                             \
+    do {                                                                                \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+        rvio::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                \
+    } while (0)
+
+// Verifies that `device` is a usable sm_100 part; the product has no other path.
+int require_b200(int device);
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace rvio

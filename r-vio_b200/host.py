@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's Tracker / Updater call surface on top of the C ABI.
+
+Same names, argument meaning and result members as src/rvio/Tracker.h:43-127 and src/rvio/Updater.h:36-71:
+    Tracker.track(im, lImuData)         -> mvFeatTypesForUpdate, mvlFeatMeasForUpdate (CSR here)
+    Updater.update(xk1k, Pk1k, types, meas) -> xk1k1, Pk1k1
+The corner detector stays on the host exactly as in the reference (FeatureDetector is not on the hot path):
+a `detector(img, n_corners, s) -> (k,2) float32` callable plays FeatureDetector::DetectWithSubPix and
+`find_newer` plays FeatureDetector::FindNewer (FeatureDetector.cc:97-150).
+The C++ twin of this file (what a reference maintainer would compile in) is r-vio_b200/host/rvio_host.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+
+
+def find_newer(cfg, corners, ref):
+    """FeatureDetector::ChessGrid + FindNewer (FeatureDetector.cc:78-150), host logic (float32/int semantics)."""
+    f32 = np.float32
+    min_dist = f32(cfg.min_dist)
+    bx, by = f32(cfg.block_x), f32(cfg.block_y)
+    W, H = cfg.width, cfg.height
+    gc, gr = int(math.floor(W / float(bx))), int(math.floor(H / float(by)))
+    nb = gc * gr
+    offx = int(.5 * (W - gc * float(bx)))
+    offy = int(.5 * (H - gr * float(by)))
+    max_per_block = int(f32(cfg.n_features) / f32(nb))
+    grid = [[] for _ in range(nb)]
+
+    def inside(p):
+        return not (p[0] <= offx or p[1] <= offy or p[0] >= (W - offx) or p[1] >= (H - offy))
+
+    for p in np.asarray(ref, f32).reshape(-1, 2):
+        if not inside(p):
+            continue
+        col = int(math.floor(f32(p[0] - f32(offx)) / bx))
+        row = int(math.floor(f32(p[1] - f32(offy)) / by))
+        grid[row * gc + col].append(p)
+    out = []
+    for p in np.asarray(corners, f32).reshape(-1, 2):
+        if not inside(p):
+            continue
+        col = int(math.floor(f32(p[0] - f32(offx)) / bx))
+        row = int(math.floor(f32(p[1] - f32(offy)) / by))
+        xl = f32(f32(col) * bx + f32(offx)); xr = f32(xl + bx)
+        yt = f32(f32(row) * by + f32(offy)); yb = f32(yt + by)
+        if (abs(float(f32(p[0] - xl))) < min_dist or abs(float(f32(p[0] - xr))) < min_dist or
+                abs(float(f32(p[1] - yt))) < min_dist or abs(float(f32(p[1] - yb))) < min_dist):
+            continue
+        cell = grid[row * gc + col]
+        if float(len(cell)) < .75 * max_per_block:
+            ok = True
+            for q in cell:
+                dx, dy = float(f32(p[0] - q[0])), float(f32(p[1] - q[1]))
+                if not math.sqrt(dx * dx + dy * dy) > float(min_dist):
+                    ok = False
+                    break
+            if ok:
+                out.append(p)
+                cell.append(p)
+    return np.array(out, f32).reshape(-1, 2)
+
+
+class Tracker:
+    """RVIO::Tracker drop-in (device side behind rvio_tracker_*)."""
+
+    def __init__(self, cfg, device: int = 0, detector=None):
+        self.cfg = cfg
+        self.L = capi.lib()
+        self._cfg_c = capi.tracker_cfg(cfg)
+        h = C.c_void_p()
+        capi.check(self.L.rvio_tracker_create(C.byref(self._cfg_c), device, C.byref(h)), "rvio_tracker_create")
+        self.h = h
+        self.detector = detector
+        self.mvFeatTypesForUpdate = np.zeros(0, np.uint8)
+        self.mvlFeatMeasForUpdate = (np.zeros(1, np.int32), np.zeros((0, 2), np.float32))   # (offsets, xy)
+        self._eq = np.empty((cfg.height, cfg.width), np.uint8)
+        self.fetch_lists = True
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rvio_tracker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- pieces -----------------------------------------------------------------------------
+    def equalized_image(self):
+        capi.check(self.L.rvio_tracker_get_image(self.h, self._eq, self._eq.strides[0]), "get_image")
+        return self._eq
+
+    def n_free(self):
+        n = C.c_int()
+        capi.check(self.L.rvio_tracker_n_free(self.h, C.byref(n)))
+        return n.value
+
+    def tracked_px(self):
+        buf = np.empty((self.cfg.n_features, 2), np.float32)
+        n = C.c_int()
+        capi.check(self.L.rvio_tracker_get_tracked_px(self.h, buf, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def update_lists(self):
+        nf, nm = C.c_int(), C.c_int()
+        capi.check(self.L.rvio_tracker_get_update_count(self.h, C.byref(nf), C.byref(nm)))
+        nf, nm = nf.value, nm.value
+        types = np.zeros(max(nf, 1), np.uint8)
+        off = np.zeros(nf + 1, np.int32)
+        xy = np.zeros((max(nm, 1), 2), np.float32)
+        capi.check(self.L.rvio_tracker_get_update_lists(self.h, types, off, xy))
+        return types[:nf], off, xy[:nm]
+
+    def debug(self):
+        F = self.cfg.n_features
+        n = C.c_int()
+        st = np.zeros(F, np.uint8); fl = np.zeros(F, np.uint8)
+        lk = np.zeros((F, 2), np.float32); un = np.zeros((F, 2), np.float32); sl = np.zeros(F, np.int32)
+        capi.check(self.L.rvio_tracker_get_debug(self.h, C.byref(n), st, fl, lk, un, sl))
+        m = n.value
+        return dict(n=m, status=st[:m], flags=fl[:m], lk=lk[:m], un=un[:m], slots=sl[:m])
+
+    def ransac_debug(self):
+        tp = np.zeros(32, np.int32); ni = np.zeros(16, np.int32); hy = np.zeros(144)
+        w, nc = C.c_int(), C.c_int()
+        capi.check(self.L.rvio_tracker_get_ransac_debug(self.h, tp, ni, C.byref(w), C.byref(nc), hy))
+        return dict(two_points=tp, n_inliers=ni, winner=w.value, n_cand=nc.value, hyp=hy.reshape(16, 3, 3))
+
+    def pyramid(self, which, level):
+        lw, lh = C.c_int(), C.c_int()
+        capi.check(self.L.rvio_tracker_get_pyramid(self.h, which, level, None, C.byref(lw), C.byref(lh)))
+        out = np.empty((lh.value, lw.value), np.uint8)
+        capi.check(self.L.rvio_tracker_get_pyramid(self.h, which, level, out.ctypes.data, C.byref(lw), C.byref(lh)))
+        return out
+
+    # -- Tracker::track ---------------------------------------------------------------------
+    def track(self, im, lImuData, detections=None):
+        """Tracker::track (Tracker.cc:179-396).  `detections`: optional pre-computed corner list that replaces the
+        detector call for this frame (seed list on the first image, FindNewer output afterwards)."""
+        im = np.ascontiguousarray(im, np.uint8)
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        imu = np.ascontiguousarray(lImuData, np.float64).reshape(-1, 8)
+        rc = capi.check(self.L.rvio_tracker_track(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
+                                                  imu.ctypes.data, len(imu)), "rvio_tracker_track")
+        if rc == capi.NO_FEATURES:
+            return rc
+        if rc == capi.FIRST_IMAGE:
+            pts = detections if detections is not None else self.detector(self.equalized_image(), self.cfg.n_features, 1)
+            pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+            capi.check(self.L.rvio_tracker_seed(self.h, pts if len(pts) else np.zeros((1, 2), np.float32), len(pts)))
+        else:
+            if self.fetch_lists:
+                t, o, xy = self.update_lists()
+                self.mvFeatTypesForUpdate, self.mvlFeatMeasForUpdate = t, (o, xy)
+            if self.n_free() > 0:
+                if detections is not None:
+                    newer = np.ascontiguousarray(detections, np.float32).reshape(-1, 2)
+                else:
+                    cand = self.detector(self.equalized_image(), self.cfg.n_features, 2)
+                    newer = find_newer(self.cfg, cand, self.tracked_px())
+                if len(newer):
+                    used = C.c_int()
+                    capi.check(self.L.rvio_tracker_refill(self.h, np.ascontiguousarray(newer), len(newer), C.byref(used)))
+        capi.check(self.L.rvio_tracker_commit(self.h), "rvio_tracker_commit")
+        return rc
+
+
+class Updater:
+    """RVIO::Updater drop-in (device side behind rvio_updater_*)."""
+
+    def __init__(self, cfg, device: int = 0):
+        self.cfg = cfg
+        self.L = capi.lib()
+        self._cfg_c = capi.updater_cfg(cfg)
+        h = C.c_void_p()
+        capi.check(self.L.rvio_updater_create(C.byref(self._cfg_c), device, C.byref(h)), "rvio_updater_create")
+        self.h = h
+        self.xk1k1 = np.zeros(26)
+        self.Pk1k1 = np.zeros((24, 24))
+        self.info = capi.UpdateInfo()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rvio_updater_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update(self, xk1k, Pk1k, vFeatTypesForUpdate, vlFeatMeasForUpdate):
+        """Updater::update (Updater.cc:72-628).  Pk1k: (d,d) array; measurements as (offsets, xy) CSR."""
+        off, xy = vlFeatMeasForUpdate
+        x = np.ascontiguousarray(xk1k, np.float64)
+        d = Pk1k.shape[0]
+        Pc = np.ascontiguousarray(np.asarray(Pk1k, np.float64).T)           # column-major bytes
+        types = np.ascontiguousarray(vFeatTypesForUpdate, np.uint8)
+        nf = len(types)
+        off = np.ascontiguousarray(off, np.int32)
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1)
+        xo = np.empty_like(x); Po = np.empty_like(Pc)
+        capi.check(self.L.rvio_updater_update(self.h, x, len(x), Pc, d, types if nf else np.zeros(1, np.uint8), off,
+                                              xy if xy.size else np.zeros(2, np.float32), nf, xo, Po, C.byref(self.info)),
+                   "rvio_updater_update")
+        self.xk1k1, self.Pk1k1 = xo, Po.T.copy()
+        return self.xk1k1, self.Pk1k1
+
+    def update_from_tracker(self, xk1k, Pk1k, tracker: Tracker):
+        x = np.ascontiguousarray(xk1k, np.float64)
+        d = Pk1k.shape[0]
+        Pc = np.ascontiguousarray(np.asarray(Pk1k, np.float64).T)
+        xo = np.empty_like(x); Po = np.empty_like(Pc)
+        capi.check(self.L.rvio_updater_update_from_tracker(self.h, tracker.h, x, len(x), Pc, d, xo, Po, C.byref(self.info)),
+                   "rvio_updater_update_from_tracker")
+        self.xk1k1, self.Pk1k1 = xo, Po.T.copy()
+        return self.xk1k1, self.Pk1k1
+
+    def debug(self, n_feat):
+        st = np.zeros(max(n_feat, 1), np.uint8); pf = np.zeros(3 * max(n_feat, 1)); gm = np.zeros(max(n_feat, 1))
+        dof = np.zeros(max(n_feat, 1), np.int32)
+        capi.check(self.L.rvio_updater_get_debug(self.h, n_feat, st, pf, gm, dof))
+        return dict(status=st[:n_feat], pfinv=pf[:3 * n_feat].reshape(-1, 3), gamma=gm[:n_feat], dof=dof[:n_feat])
+
+    def normal_terms(self, n):
+        G = np.zeros((n, n)); z = np.zeros(n)
+        capi.check(self.L.rvio_updater_get_normal_terms(self.h, G, z, n))
+        return G, z

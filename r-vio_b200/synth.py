@@ -163,11 +163,11 @@ def _texture(seed: int, size: int = 2048):
 class Stream:
     """frames[i] (u8 HxW), frame_t[i]; imu rows [w(3), a(3), t, dt] (dt = t - t_prev, 0 for the first: rvio_mono.cc:102-107)."""
 
-    def __init__(self, cfg: Config, n_frames: int, seed: int, tex_px_per_m: float = 150.0):
+    def __init__(self, cfg: Config, n_frames: int, seed: int, tex_px_per_m: float = 150.0, t_static: float = 2.0):
         if cv2 is None:
             raise RuntimeError("cv2 is required to render synthetic frames")
         self.cfg, self.seed, self.n_frames = cfg, seed, n_frames
-        self.traj = Trajectory(seed)
+        self.traj = Trajectory(seed, t_static)
         T = np.array(cfg.T_BC0, np.float64).reshape(4, 4)
         self.R_IC, self.p_IC = T[:3, :3], T[:3, 3]
         self.tex_wall = _texture(seed * 7 + 1)
