@@ -44,7 +44,7 @@ class ImuCfg(C.Structure):
 
 class UpdateInfo(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n_feat", "n_good", "rows_stacked", "rank", "compressed", "updated",
-                                        "n_reject_init", "n_reject_lm", "n_reject_gate")]
+                                        "n_reject_init", "n_reject_lm", "n_reject_gate", "rank_full")]
 
 
 class RandState(C.Structure):
@@ -110,6 +110,7 @@ def lib():
     L.orc_updater_cfg_init.argtypes = [C.POINTER(UpdaterCfg), C.c_float, C.c_float, f64]
     L.orc_updater_update.argtypes = [C.POINTER(UpdaterCfg), f64, ci, f64, u8, i32, f32, ci, f64, f64,
                                      C.POINTER(UpdateInfo), vp, vp, vp, vp, vp]
+    L.orc_updater_set_rank_rule.argtypes = [ci]
     L.orc_propagate.argtypes = [C.POINTER(ImuCfg), f64, ci, f64, f64, ci, f64, f64]
     L.orc_augment_compose.argtypes = [f64, f64, C.POINTER(ci), ci, ci, f64]
     L.orc_initialize.argtypes = [C.POINTER(ImuCfg), cd, f64, f64, ci, ci, f64, f64]

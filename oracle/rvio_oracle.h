@@ -142,7 +142,9 @@ typedef struct {
 typedef struct {
     int n_feat, n_good, rows_stacked, rank, compressed, updated;
     int n_reject_init, n_reject_lm, n_reject_gate;
+    int rank_full;           /* rows with norm >= 1e-4 anywhere (== rank unless the reference's first-small-row cut dropped rows) */
 } orc_update_info_t;
+void orc_updater_set_rank_rule(int full_info);
 
 void orc_updater_cfg_init(orc_updater_cfg_t* c, float sigma_px, float sigma_py, const double* T_BC0_rowmajor16);
 

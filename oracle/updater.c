@@ -16,6 +16,11 @@
 #include <stdlib.h>
 #include <float.h>
 
+static int g_full_info = 0;
+/* 0 (default): the reference's rule (rows up to the first row with norm < 1e-4, Updater.cc:515-524);
+ * 1: keep every row with norm >= 1e-4 (no information discarded) -- used to quantify the rule's effect. */
+void orc_updater_set_rank_rule(int full_info) { g_full_info = full_info; }
+
 double orc_chi2_95(int dof) { return (dof >= 1 && dof <= 500) ? ORC_CHI2_95[dof - 1] : NAN; }
 
 void orc_updater_cfg_init(orc_updater_cfg_t* c, float sx, float sy, const double* T)
@@ -453,13 +458,22 @@ void orc_updater_update(const orc_updater_cfg_t* cfg, const double* x, int xdim,
                     rot_rows(r + (m - 1), r + m, 1, c, s);
                 }
             rk = 0;
+            int rk_full = 0, stopped = 0;
             for (int i = 0; i < M; ++i) {
                 double s = 0;
                 for (int j = 0; j < n; ++j) s += Hx[(size_t)i * n + j] * Hx[(size_t)i * n + j];
-                if (sqrt(s) < 1e-4) break;
-                rk++;
+                if (sqrt(s) < 1e-4) { stopped = 1; continue; }
+                if (!stopped) rk++;
+                if (g_full_info && rk_full != i) {       /* compact informative rows to the top */
+                    memcpy(Hx + (size_t)rk_full * n, Hx + (size_t)i * n, sizeof(double) * (size_t)n);
+                    r[rk_full] = r[i];
+                }
+                rk_full++;
             }
-        }
+            inf.rank_full = rk_full;
+            if (g_full_info) rk = rk_full;
+        } else
+            inf.rank_full = nRowCount;
         inf.rank = rk;
         /* EKF update, Updater.cc:540-544.  Hn = [0 (rk x 24) | Hx(0:rk,:)] */
         double* PHt = (double*)malloc(sizeof(double) * (size_t)d * (size_t)(rk > 0 ? rk : 1));     /* d x rk */

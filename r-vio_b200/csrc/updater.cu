@@ -1,15 +1,1119 @@
-// TEMPORARY skeleton so the library links while the tracker is brought up on the GPU; replaced by the real updater.
+// updater.cu -- CUDA kernels + C ABI of the MSCKF update half of the hot path (see updater_kernels.cuh).
 #include "common.cuh"
+#include "tracker_kernels.cuh"
+#include "updater_kernels.cuh"
+#include "chi2_table.h"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace rvio {
+
+// tracker.cu accessors (same shared library) for the fused path
+const TrackerBuffers* tracker_buffers(const rvio_tracker* t);
+int tracker_update_counts(const rvio_tracker* t, int* n_meas);
+int tracker_device(const rvio_tracker* t);
+cudaStream_t tracker_stream(const rvio_tracker* t);
+
+// ================================================================================================
+// small fp64 device helpers (Numerics.h:30-167 restated)
+// ================================================================================================
+__device__ __forceinline__ void d_m3mul(const double* A, const double* B, double* C)
+{
+    double T[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = T[i];
+}
+__device__ __forceinline__ void d_m3v(const double* A, const double* v, double* o)
+{
+    const double t0 = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    const double t1 = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    const double t2 = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+    o[0] = t0; o[1] = t1; o[2] = t2;
+}
+__device__ __forceinline__ void d_quat_to_rot(const double* q, double* R)   // I - 2w[q x] + 2[q x]^2
+{
+    const double qx[9] = {0, -q[2], q[1], q[2], 0, -q[0], -q[1], q[0], 0};
+    double qx2[9];
+    d_m3mul(qx, qx, qx2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+        R[i] = I - 2 * q[3] * qx[i] + 2 * qx2[i];
+    }
+}
+__device__ __forceinline__ void d_quat_mul(const double* q1, const double* q2, double* out)
+{
+    double q[4];
+    q[0] = q1[3] * q2[0] + q1[2] * q2[1] - q1[1] * q2[2] + q1[0] * q2[3];
+    q[1] = -q1[2] * q2[0] + q1[3] * q2[1] + q1[0] * q2[2] + q1[1] * q2[3];
+    q[2] = q1[1] * q2[0] - q1[0] * q2[1] + q1[3] * q2[2] + q1[2] * q2[3];
+    q[3] = -q1[0] * q2[0] - q1[1] * q2[1] - q1[2] * q2[2] + q1[3] * q2[3];
+    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double sg = (q[3] / nrm < 0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = sg * (q[i] / nrm);
+}
+__device__ __forceinline__ void d_rot_to_quat(const double* R, double* q)   // Breckenridge, Numerics.h:126-167
+{
+    const double T = R[0] + R[4] + R[8];
+    if (R[0] > T && R[0] > R[4] && R[0] > R[8]) {
+        q[0] = sqrt((1 + 2 * R[0] - T) / 4);
+        const double s = 1 / (4 * q[0]);
+        q[1] = s * (R[1] + R[3]); q[2] = s * (R[2] + R[6]); q[3] = s * (R[5] - R[7]);
+    } else if (R[4] > T && R[4] > R[0] && R[4] > R[8]) {
+        q[1] = sqrt((1 + 2 * R[4] - T) / 4);
+        const double s = 1 / (4 * q[1]);
+        q[0] = s * (R[1] + R[3]); q[2] = s * (R[5] + R[7]); q[3] = s * (R[6] - R[2]);
+    } else if (R[8] > T && R[8] > R[0] && R[8] > R[4]) {
+        q[2] = sqrt((1 + 2 * R[8] - T) / 4);
+        const double s = 1 / (4 * q[2]);
+        q[0] = s * (R[2] + R[6]); q[1] = s * (R[5] + R[7]); q[3] = s * (R[1] - R[3]);
+    } else {
+        q[3] = sqrt((1 + T) / 4);
+        const double s = 1 / (4 * q[3]);
+        q[0] = s * (R[5] - R[7]); q[1] = s * (R[6] - R[2]); q[2] = s * (R[1] - R[3]);
+    }
+    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double sg = (q[3] / nrm < 0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = sg * (q[i] / nrm);
+}
+__device__ __forceinline__ void d_set_dir(double phi, double psi, double* e, double* J /* 3x2 */)
+{
+    double sp, cp, ss, cs;
+    sincos(phi, &sp, &cp);
+    sincos(psi, &ss, &cs);
+    e[0] = cp * ss; e[1] = sp; e[2] = cp * cs;
+    J[0] = -sp * ss; J[1] = cp * cs;
+    J[2] = cp; J[3] = 0;
+    J[4] = -sp * cs; J[5] = -cp * ss;
+}
+__device__ __forceinline__ void d_hproj(const double* h, double* Hp /* 2x3 */)
+{
+    const double iz = 1 / h[2], iz2 = 1 / (h[2] * h[2]);
+    Hp[0] = iz; Hp[1] = 0; Hp[2] = -h[0] * iz2;
+    Hp[3] = 0; Hp[4] = iz; Hp[5] = -h[1] * iz2;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return __shfl_sync(0xffffffffu, v, 0);       // identical bits in every lane
+}
+
+// 3x3 solve by Gaussian elimination with partial pivoting (LM normal equations, Updater.cc:239)
+__device__ __forceinline__ void d_solve3(const double* A_, const double* b_, double* x)
+{
+    double A[9], b[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = A_[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b[i] = b_[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double mx = fabs(A[3 * k + k]);
+        for (int i = k + 1; i < 3; ++i)
+            if (fabs(A[3 * i + k]) > mx) { mx = fabs(A[3 * i + k]); p = i; }
+        if (p != k) {
+            for (int j = 0; j < 3; ++j) { const double t = A[3 * k + j]; A[3 * k + j] = A[3 * p + j]; A[3 * p + j] = t; }
+            const double t = b[k]; b[k] = b[p]; b[p] = t;
+        }
+        const double piv = A[3 * k + k];
+        for (int i = k + 1; i < 3; ++i) {
+            const double f = A[3 * i + k] / piv;
+            for (int j = k; j < 3; ++j) A[3 * i + j] -= f * A[3 * k + j];
+            b[i] -= f * b[k];
+        }
+    }
+    x[2] = b[2] / A[8];
+    x[1] = (b[1] - A[5] * x[2]) / A[4];
+    x[0] = (b[0] - A[1] * x[1] - A[2] * x[2]) / A[0];
+}
+
+// ================================================================================================
+// k_feature: one CTA (128 threads) per feature
+// ================================================================================================
+constexpr int kFeatThreads = 128;
+
+__global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_pf[4];          // phi, psi, rho, (unused)
+    __shared__ int s_flag[4];           // [0] reject code, [1] Nc
+    __shared__ double s_hh[4];          // householder: beta, alpha
+
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (f % P.world != P.rank) return;   // feature sharding: this rank owns f % world == rank
+    const FeatLayout& Y = P.lay;
+    const UpdaterConsts& C = P.c;
+    double* relI = sm + Y.o_relI; double* RI = sm + Y.o_RI; double* RC = sm + Y.o_RC; double* tC = sm + Y.o_tC;
+    double* HRR = sm + Y.o_HRR; double* SUB = sm + Y.o_SUB; double* Hf = sm + Y.o_Hf; double* rr = sm + Y.o_r;
+    double* vv = sm + Y.o_v; double* Hx = sm + Y.o_Hx; double* S = sm + Y.o_S; double* Tc = sm + Y.o_T;
+    float2* meas = reinterpret_cast<float2*>(sm + Y.o_meas);
+
+    const int N = P.N, n = 6 * N;
+    const int off0 = P.offsets[f];
+    int L = P.offsets[f + 1] - off0;
+    const int type = P.types[f];
+    const int phases_full = L - 1;
+
+    if (tid == 0) {
+        P.f_status[f] = 0; P.f_dof[f] = 0; P.f_c0[f] = 0; P.f_wc[f] = 0;
+        P.f_gamma[f] = nan("");
+        P.f_pfinv[3 * f] = P.f_pfinv[3 * f + 1] = P.f_pfinv[3 * f + 2] = nan("");
+        s_flag[0] = 0;
+    }
+    // capacity / consistency guards (the reference would read out of bounds here)
+    if (L < 2 || L > Y.Lc || phases_full > N) {
+        if (tid == 0) P.f_status[f] = 1;
+        return;
+    }
+    for (int i = tid; i < L; i += kFeatThreads) meas[i] = P.xy[off0 + i];
+
+    // ---- relative-pose chain, Updater.cc:118-132 (serial in i)
+    const double* rel = (type == '1') ? (P.x + P.xdim - 7 * phases_full) : (P.x + 26);
+    if (tid == 0) {
+        double R0[9], t[3];
+        d_quat_to_rot(rel, R0);
+        d_m3v(R0, rel + 4, t);
+        for (int k = 0; k < 4; ++k) relI[k] = rel[k];
+        relI[4] = -t[0]; relI[5] = -t[1]; relI[6] = -t[2];
+        for (int i = 1; i < phases_full; ++i) {
+            double Ri[9], dv[3];
+            d_quat_mul(rel + 7 * i, relI + 7 * (i - 1), relI + 7 * i);
+            d_quat_to_rot(rel + 7 * i, Ri);
+            for (int k = 0; k < 3; ++k) dv[k] = relI[7 * (i - 1) + 4 + k] - rel[7 * i + 4 + k];
+            d_m3v(Ri, dv, relI + 7 * i + 4);
+        }
+    }
+    __syncthreads();
+    // ---- camera poses, Updater.cc:134-141 (parallel in i)
+    for (int i = tid; i < phases_full; i += kFeatThreads) {
+        double R[9], T[9], M[9], qC[4], a[3], b[3];
+        d_quat_to_rot(relI + 7 * i, R);
+        for (int k = 0; k < 9; ++k) RI[9 * i + k] = R[k];
+        d_m3mul(C.Rci, R, T);
+        d_m3mul(T, C.Ric, M);
+        d_rot_to_quat(M, qC);
+        d_quat_to_rot(qC, M);
+        for (int k = 0; k < 9; ++k) RC[9 * i + k] = M[k];
+        d_m3v(T, C.tic, a);
+        d_m3v(C.Rci, relI + 7 * i + 4, b);
+        for (int k = 0; k < 3; ++k) tC[3 * i + k] = a[k] + b[k] + C.tci[k];
+    }
+    __syncthreads();
+
+    // ---- inverse-depth initialisation + LM (warp 0), Updater.cc:143-269
+    if (warp == 0) {
+        const float2 m0 = meas[0];
+        double phi = atan2((double)m0.y, sqrt((double)m0.x * (double)m0.x + 1));
+        double psi = atan2((double)m0.x, 1.0);
+        double rho = 0.;
+        int reject = 0;
+        if (fabs(phi) > .5 * 3.14 || fabs(psi) > .5 * 3.14) reject = 1;
+        if (!reject) {
+            double e[3], J[6];
+            d_set_dir(phi, psi, e, J);
+            const double rinv = 1. / (C.sigma * C.sigma);
+            double lambda = 0.01, lastCost = INFINITY;
+            for (int it = 0; it < 10; ++it) {
+                double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
+                for (int i = lane; i < L; i += 32) {
+                    double h[3], Hp[6], Hm[6];
+                    if (i == 0) {
+                        h[0] = e[0]; h[1] = e[1]; h[2] = e[2];
+                        d_hproj(h, Hp);
+                        for (int a = 0; a < 2; ++a) {
+                            Hm[3 * a] = Hp[3 * a] * J[0] + Hp[3 * a + 1] * J[2] + Hp[3 * a + 2] * J[4];
+                            Hm[3 * a + 1] = Hp[3 * a] * J[1] + Hp[3 * a + 1] * J[3] + Hp[3 * a + 2] * J[5];
+                            Hm[3 * a + 2] = 0;
+                        }
+                    } else {
+                        const double* Rc = RC + 9 * (i - 1);
+                        const double* tc = tC + 3 * (i - 1);
+                        d_m3v(Rc, e, h);
+                        h[0] += rho * tc[0]; h[1] += rho * tc[1]; h[2] += rho * tc[2];
+                        d_hproj(h, Hp);
+                        double HR[6];
+                        for (int a = 0; a < 2; ++a)
+                            for (int b = 0; b < 3; ++b) HR[3 * a + b] = Hp[3 * a] * Rc[b] + Hp[3 * a + 1] * Rc[3 + b] + Hp[3 * a + 2] * Rc[6 + b];
+                        for (int a = 0; a < 2; ++a) {
+                            Hm[3 * a] = HR[3 * a] * J[0] + HR[3 * a + 1] * J[2] + HR[3 * a + 2] * J[4];
+                            Hm[3 * a + 1] = HR[3 * a] * J[1] + HR[3 * a + 1] * J[3] + HR[3 * a + 2] * J[5];
+                            Hm[3 * a + 2] = Hp[3 * a] * tc[0] + Hp[3 * a + 1] * tc[1] + Hp[3 * a + 2] * tc[2];
+                        }
+                    }
+                    const float ptx = (float)(h[0] / h[2]), pty = (float)(h[1] / h[2]);
+                    const float2 mi = meas[i];
+                    const double e0 = (double)(mi.x - ptx), e1 = (double)(mi.y - pty);    // float subtraction (cv::Point2f)
+                    cost += (e0 * rinv) * e0 + (e1 * rinv) * e1;
+                    const double h00 = Hm[0] * rinv, h01 = Hm[1] * rinv, h02 = Hm[2] * rinv;
+                    const double h10 = Hm[3] * rinv, h11 = Hm[4] * rinv, h12 = Hm[5] * rinv;
+                    a00 += h00 * Hm[0] + h10 * Hm[3]; a01 += h00 * Hm[1] + h10 * Hm[4]; a02 += h00 * Hm[2] + h10 * Hm[5];
+                    a11 += h01 * Hm[1] + h11 * Hm[4]; a12 += h01 * Hm[2] + h11 * Hm[5]; a22 += h02 * Hm[2] + h12 * Hm[5];
+                    g0 += h00 * e0 + h10 * e1; g1 += h01 * e0 + h11 * e1; g2 += h02 * e0 + h12 * e1;
+                }
+                a00 = warp_sum(a00); a01 = warp_sum(a01); a02 = warp_sum(a02); a11 = warp_sum(a11);
+                a12 = warp_sum(a12); a22 = warp_sum(a22); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+                cost = warp_sum(cost);
+                if (cost <= lastCost) {
+                    double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
+                    const double g[3] = {g0, g1, g2};
+                    A[0] += lambda * A[0]; A[4] += lambda * A[4]; A[8] += lambda * A[8];
+                    double dp[3];
+                    d_solve3(A, g, dp);
+                    phi += dp[0]; psi += dp[1]; rho += dp[2];
+                    d_set_dir(phi, psi, e, J);
+                    if (fabs(lastCost - cost) < 1e-6 && dp[2] < 1e-6) break;
+                    lambda *= .1;
+                    lastCost = cost;
+                } else {
+                    lambda *= 10;
+                    lastCost = cost;
+                }
+            }
+            if (fabs(phi) > .5 * 3.14 || fabs(psi) > .5 * 3.14 || isinf(rho) || rho < 0) reject = 2;
+        }
+        if (lane == 0) {
+            s_pf[0] = phi; s_pf[1] = psi; s_pf[2] = rho;
+            s_flag[0] = reject;
+            if (!(reject == 1)) { P.f_pfinv[3 * f] = phi; P.f_pfinv[3 * f + 1] = psi; P.f_pfinv[3 * f + 2] = rho; }
+            if (reject) P.f_status[f] = (uint8_t)reject;
+        }
+    }
+    __syncthreads();
+    if (s_flag[0]) return;
+
+    const double phi = s_pf[0], psi = s_pf[1], rho = s_pf[2];
+    double e[3], J[6];
+    d_set_dir(phi, psi, e, J);
+    if (type == '2') L = (L + 1) / 2;                 // Updater.cc:271-275
+    const int Mr = 2 * L;                             // rows of this feature's block
+    const int wc = 6 * (L - 1);                       // non-zero clone columns of the block
+    const int c0 = (type == '1') ? 6 * (N - phases_full) : 0;   // Updater.cc:288-293
+    const int ld = Y.Wc;
+
+    // ---- Jacobians, Updater.cc:281-368
+    for (int i = tid; i < Mr * ld; i += kFeatThreads) Hx[i] = 0.0;
+    double Rice[3];
+    d_m3v(C.Ric, e, Rice);
+    // per-row quantities (thread i <-> measurement i)
+    for (int i = tid; i < L; i += kFeatThreads) {
+        double h[3], Hp[6];
+        if (i == 0) {
+            h[0] = e[0]; h[1] = e[1]; h[2] = e[2];
+            d_hproj(h, Hp);
+            for (int a = 0; a < 2; ++a) {
+                Hf[3 * a] = Hp[3 * a] * J[0] + Hp[3 * a + 1] * J[2] + Hp[3 * a + 2] * J[4];
+                Hf[3 * a + 1] = Hp[3 * a] * J[1] + Hp[3 * a + 1] * J[3] + Hp[3 * a + 2] * J[5];
+                Hf[3 * a + 2] = 0;
+            }
+        } else {
+            const double* Rc = RC + 9 * (i - 1);
+            const double* tc = tC + 3 * (i - 1);
+            d_m3v(Rc, e, h);
+            h[0] += rho * tc[0]; h[1] += rho * tc[1]; h[2] += rho * tc[2];
+            d_hproj(h, Hp);
+            double HR[6], HRci[6];
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 3; ++b) {
+                    HR[3 * a + b] = Hp[3 * a] * Rc[b] + Hp[3 * a + 1] * Rc[3 + b] + Hp[3 * a + 2] * Rc[6 + b];
+                    HRci[3 * a + b] = Hp[3 * a] * C.Rci[b] + Hp[3 * a + 1] * C.Rci[3 + b] + Hp[3 * a + 2] * C.Rci[6 + b];
+                }
+            const double* R = RI + 9 * (i - 1);
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 3; ++b)
+                    HRR[6 * i + 3 * a + b] = HRci[3 * a] * R[b] + HRci[3 * a + 1] * R[3 + b] + HRci[3 * a + 2] * R[6 + b];
+            for (int a = 0; a < 2; ++a) {
+                Hf[3 * (2 * i + a)] = HR[3 * a] * J[0] + HR[3 * a + 1] * J[2] + HR[3 * a + 2] * J[4];
+                Hf[3 * (2 * i + a) + 1] = HR[3 * a] * J[1] + HR[3 * a + 1] * J[3] + HR[3 * a + 2] * J[5];
+                Hf[3 * (2 * i + a) + 2] = Hp[3 * a] * tc[0] + Hp[3 * a + 1] * tc[1] + Hp[3 * a + 2] * tc[2];
+            }
+        }
+        const float ptx = (float)(h[0] / h[2]), pty = (float)(h[1] / h[2]);
+        const float2 mi = meas[i];
+        rr[2 * i] = (double)(mi.x - ptx);
+        rr[2 * i + 1] = (double)(mi.y - pty);
+    }
+    // per-clone 3x6 factors: SUB_j = [ skew(Ric e + rho tic + rho Rj^T tj) Rj^T , -rho R_{j-1}^T ]  (j=0: -rho I)
+    for (int j = tid; j < L - 1; j += kFeatThreads) {
+        const double* Rj = RI + 9 * j;
+        const double* tj = relI + 7 * j + 4;
+        double RjT[9], tmp[3], v[3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) RjT[3 * a + b] = Rj[3 * b + a];
+        d_m3v(RjT, tj, tmp);
+        for (int k = 0; k < 3; ++k) v[k] = Rice[k] + rho * C.tic[k] + rho * tmp[k];
+        const double sk[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+        double blkL[9];
+        d_m3mul(sk, RjT, blkL);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                SUB[18 * j + 6 * a + b] = blkL[3 * a + b];
+                SUB[18 * j + 6 * a + 3 + b] = (j == 0) ? ((a == b) ? -rho : 0.0) : -rho * RI[9 * (j - 1) + 3 * b + a];
+            }
+    }
+    __syncthreads();
+    // 2x6 blocks (i, j<i): Hx[2i..2i+1, 6j..6j+5] = HRR_i * SUB_j
+    {
+        const int npairs = L * (L - 1) / 2;
+        for (int p = tid; p < npairs; p += kFeatThreads) {
+            // p -> (i, j), i in 1..L-1, j in 0..i-1 ; p = i(i-1)/2 + j
+            int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            const int j = p - i * (i - 1) / 2;
+            const double* A = HRR + 6 * i;
+            const double* B = SUB + 18 * j;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 6; ++b)
+                    Hx[(2 * i + a) * ld + 6 * j + b] = A[3 * a] * B[b] + A[3 * a + 1] * B[6 + b] + A[3 * a + 2] * B[12 + b];
+        }
+    }
+    __syncthreads();
+
+    // ---- left-nullspace projection (Updater.cc:370-402) by Householder reflections on H_f
+    if (tid == 0) {
+        double s = 0;
+        for (int i = 0; i < Mr; ++i) s += Hf[3 * i + 2] * Hf[3 * i + 2];
+        s_flag[1] = (sqrt(s) < 1e-4) ? 2 : 3;         // rank-deficient H_f: use two columns
+    }
+    __syncthreads();
+    const int Nc = s_flag[1];
+    for (int k = 0; k < Nc; ++k) {
+        if (warp == 0) {
+            double s = 0;
+            for (int i = k + lane; i < Mr; i += 32) s += Hf[3 * i + k] * Hf[3 * i + k];
+            s = warp_sum(s);
+            const double x0 = Hf[3 * k + k];
+            const double nrm = sqrt(s);
+            const double alpha = (x0 >= 0) ? -nrm : nrm;
+            for (int i = k + lane; i < Mr; i += 32) vv[i] = (i == k) ? (x0 - alpha) : Hf[3 * i + k];
+            const double vtv = s - x0 * x0 + (x0 - alpha) * (x0 - alpha);
+            if (lane == 0) s_hh[0] = (vtv > 0) ? 2.0 / vtv : 0.0;
+        }
+        __syncthreads();
+        const double beta = s_hh[0];
+        // columns: Hx (wc), then remaining Hf columns, then r
+        const int ncols = wc + (Nc - k) + 1;
+        for (int c = tid; c < ncols; c += kFeatThreads) {
+            double* col; int stride;
+            if (c < wc) { col = Hx + c; stride = ld; }
+            else if (c < wc + (Nc - k)) { col = Hf + k + (c - wc); stride = 3; }
+            else { col = rr; stride = 1; }
+            double w = 0;
+            for (int i = k; i < Mr; ++i) w += vv[i] * col[i * stride];
+            w *= beta;
+            for (int i = k; i < Mr; ++i) col[i * stride] -= w * vv[i];
+        }
+        __syncthreads();
+    }
+    const int dof = Mr - Nc;
+    const double* Hn = Hx + Nc * ld;       // projected block, dof x wc (row stride ld)
+    const double* rn = rr + Nc;
+
+    // ---- Mahalanobis gate, Updater.cc:404-422:  S = Hn Pcc Hn^T + s^2 I ; gamma = |r^T S^-1 r|
+    for (int i = tid; i < dof * dof; i += kFeatThreads) S[i] = 0.0;
+    __syncthreads();
+    for (int j0 = 0; j0 < wc; j0 += 32) {
+        const int jw = min(32, wc - j0);
+        // T[a][jj] = sum_k Hn[a][k] * Pcc[c0+k][c0+j0+jj]   (P symmetric: read the row-contiguous element)
+        for (int o = tid; o < dof * 32; o += kFeatThreads) {
+            const int a = o >> 5, jj = o & 31;
+            double acc = 0;
+            if (jj < jw) {
+                const double* prow = P.P + (size_t)(24 + c0) * P.d + (24 + c0 + j0 + jj);
+                const double* hrow = Hn + a * ld;
+                for (int k = 0; k < wc; ++k) acc += hrow[k] * prow[(size_t)k * P.d];
+            }
+            Tc[o] = acc;
+        }
+        __syncthreads();
+        for (int o = tid; o < dof * dof; o += kFeatThreads) {
+            const int a = o / dof, b = o - a * dof;
+            const double* trow = Tc + a * 32;
+            const double* hrow = Hn + b * ld + j0;
+            double acc = 0;
+            for (int jj = 0; jj < jw; ++jj) acc += trow[jj] * hrow[jj];
+            S[o] += acc;
+        }
+        __syncthreads();
+    }
+    // symmetrise + noise
+    for (int o = tid; o < dof * dof; o += kFeatThreads) {
+        const int a = o / dof, b = o - a * dof;
+        if (a <= b) {
+            double v = .5 * (S[a * dof + b] + S[b * dof + a]);
+            if (a == b) v = S[a * dof + a] + C.sig2;
+            S[a * dof + b] = v;
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < dof * dof; o += kFeatThreads) {
+        const int a = o / dof, b = o - a * dof;
+        if (a > b) S[a * dof + b] = S[b * dof + a];
+    }
+    __syncthreads();
+    // Cholesky S = L L^T (lower), all threads
+    for (int j = 0; j < dof; ++j) {
+        if (tid == 0) {
+            const double dj = S[j * dof + j];
+            s_hh[1] = (dj > 0) ? sqrt(dj) : nan("");
+        }
+        __syncthreads();
+        const double dj = s_hh[1];
+        for (int i = j + tid; i < dof; i += kFeatThreads) S[i * dof + j] = (i == j) ? dj : S[i * dof + j] / dj;
+        __syncthreads();
+        const int rem = dof - j - 1;
+        for (int o = tid; o < rem * rem; o += kFeatThreads) {
+            const int a = j + 1 + o / rem, b = j + 1 + o % rem;
+            if (b <= a) S[a * dof + b] -= S[a * dof + j] * S[b * dof + j];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // y = L^-1 r ; gamma = y^T y
+        double gamma = 0;
+        for (int i = 0; i < dof; ++i) {
+            double s = rn[i];
+            for (int k = 0; k < i; ++k) s -= S[i * dof + k] * vv[k];
+            const double y = s / S[i * dof + i];
+            vv[i] = y;
+            gamma += y * y;
+        }
+        gamma = fabs(gamma);
+        P.f_gamma[f] = gamma;
+        const bool ok = gamma < P.chi2[dof - 1];
+        s_flag[2] = ok ? 1 : 0;
+        if (!ok) P.f_status[f] = 3;
+        P.f_dof[f] = ok ? dof : 0;
+        P.f_c0[f] = c0; P.f_wc[f] = wc;
+    }
+    __syncthreads();
+    if (!s_flag[2]) return;
+    // ---- accepted: publish the projected block (full width n, zero outside [c0, c0+wc))
+    double* Hout = P.Hblk + (size_t)f * P.blk_rows * n;
+    double* rout = P.rblk + (size_t)f * P.blk_rows;
+    for (int o = tid; o < dof * n; o += kFeatThreads) {
+        const int a = o / n, c = o - a * n;
+        const int k = c - c0;
+        Hout[o] = (k >= 0 && k < wc) ? Hn[a * ld + k] : 0.0;
+    }
+    for (int a = tid; a < dof; a += kFeatThreads) rout[a] = rn[a];
+}
+
+// ================================================================================================
+// normal terms  G = sum_f Hn_f^T Hn_f ,  z = sum_f Hn_f^T rn_f   (deterministic two-stage reduction)
+// ================================================================================================
+struct GramParams {
+    const double* Hblk; const double* rblk; const int32_t* f_dof; const int32_t* f_c0; const int32_t* f_wc;
+    int n_feat, n, blk_rows, groups, nt;
+    double* Gpart;     // [groups][n][n]
+    double* zpart;     // [groups][n]
+};
+
+__global__ void __launch_bounds__(256) k_gram(GramParams P)
+{
+    __shared__ double sA[8][33], sB[8][33];
+    const int ti = blockIdx.x / P.nt, tj = blockIdx.x % P.nt, g = blockIdx.y;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int n = P.n;
+    const int i0 = ti * 32, j0 = tj * 32;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int f = g; f < P.n_feat; f += P.groups) {
+        const int dof = P.f_dof[f];
+        if (dof <= 0) continue;
+        const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
+        if (i0 >= c1 || i0 + 32 <= c0 || j0 >= c1 || j0 + 32 <= c0) continue;     // block is zero on this tile
+        const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+        for (int a0 = 0; a0 < dof; a0 += 8) {
+            {
+                const int r = threadIdx.x >> 5, c = threadIdx.x & 31;      // 8 rows x 32 cols
+                const int a = a0 + r;
+                sA[r][c] = (a < dof && i0 + c < n) ? H[(size_t)a * n + i0 + c] : 0.0;
+                sB[r][c] = (a < dof && j0 + c < n) ? H[(size_t)a * n + j0 + c] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double a0v = sA[r][2 * ty], a1v = sA[r][2 * ty + 1];
+                const double b0v = sB[r][2 * tx], b1v = sB[r][2 * tx + 1];
+                acc[0][0] += a0v * b0v; acc[0][1] += a0v * b1v; acc[1][0] += a1v * b0v; acc[1][1] += a1v * b1v;
+            }
+            __syncthreads();
+        }
+    }
+    double* G = P.Gpart + (size_t)g * n * n;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
+            if (i < n && j < n) G[(size_t)i * n + j] = acc[a][b];
+        }
+}
+
+__global__ void __launch_bounds__(256) k_gram_z(GramParams P)
+{
+    const int g = blockIdx.x, n = P.n;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double acc = 0;
+        for (int f = g; f < P.n_feat; f += P.groups) {
+            const int dof = P.f_dof[f];
+            if (dof <= 0) continue;
+            const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
+            if (i < c0 || i >= c1) continue;
+            const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+            const double* r = P.rblk + (size_t)f * P.blk_rows;
+            for (int a = 0; a < dof; ++a) acc += H[(size_t)a * n + i] * r[a];
+        }
+        P.zpart[(size_t)g * n + i] = acc;
+    }
+}
+
+// reduce buffer layout: [G (n*n) | z (n) | counters (8)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_feat_local
+__global__ void __launch_bounds__(256) k_gram_reduce(GramParams P, const uint8_t* f_status, int rank, int world, double* red)
+{
+    const int n = P.n;
+    const int total = n * n + n;
+    for (int o = blockIdx.x * 256 + threadIdx.x; o < total; o += gridDim.x * 256) {
+        double acc = 0;
+        if (o < n * n) for (int g = 0; g < P.groups; ++g) acc += P.Gpart[(size_t)g * n * n + o];
+        else for (int g = 0; g < P.groups; ++g) acc += P.zpart[(size_t)g * n + (o - n * n)];
+        red[o] = acc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
+        for (int f = rank; f < P.n_feat; f += world) {
+            loc++;
+            const int st = f_status[f];
+            if (st == 0) { good++; rows += P.f_dof[f]; }
+            else if (st == 1) r1++;
+            else if (st == 2) r2++;
+            else r3++;
+        }
+        double* c = red + total;
+        c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
+    }
+}
+
+// ================================================================================================
+// generic fp64 GEMM (strided operands), Gauss-Jordan solve, finalisation
+// ================================================================================================
+struct GemmParams {
+    int M, N, K;
+    const double* A; long long ars, acs;      // A(i,k) = A[i*ars + k*acs]
+    const double* B; long long brs, bcs;      // B(k,j)
+    const double* C0; long long c0rs, c0cs;   // optional addend
+    double* C; long long crs, ccs;
+    double alpha, beta, diag_add;
+};
+
+__global__ void __launch_bounds__(256) k_dgemm(GemmParams P)
+{
+    __shared__ double sA[16][33], sB[16][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = 0; k0 < P.K; k0 += 16) {
+        for (int o = threadIdx.x; o < 16 * 32; o += 256) {
+            const int kk = o >> 5, c = o & 31;
+            const int k = k0 + kk;
+            sA[kk][c] = (k < P.K && i0 + c < P.M) ? P.A[(long long)(i0 + c) * P.ars + (long long)k * P.acs] : 0.0;
+            sB[kk][c] = (k < P.K && j0 + c < P.N) ? P.B[(long long)k * P.brs + (long long)(j0 + c) * P.bcs] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const double a0 = sA[kk][2 * ty], a1 = sA[kk][2 * ty + 1];
+            const double b0 = sB[kk][2 * tx], b1 = sB[kk][2 * tx + 1];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+        __syncthreads();
+    }
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
+            if (i < P.M && j < P.N) {
+                double v = P.alpha * acc[a][b];
+                if (P.C0) v += P.beta * P.C0[(long long)i * P.c0rs + (long long)j * P.c0cs];
+                if (i == j) v += P.diag_add;
+                P.C[(long long)i * P.crs + (long long)j * P.ccs] = v;
+            }
+        }
+}
+
+// Solves M Y = R in place (Y overwrites R) by Gauss-Jordan elimination with partial pivoting.
+// M: n x n row-major, R: n x m row-major.  Single CTA of 1024 threads; operands stay in L2.
+__global__ void __launch_bounds__(1024) k_gauss_jordan(double* M, double* R, int n, int m, int* singular)
+{
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    __shared__ double s_pinv;
+    extern __shared__ double s_fac[];          // n multipliers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = 0; k < n; ++k) {
+        // pivot search over rows k..n-1 of column k
+        double best = -1.0; int bi = k;
+        for (int i = k + tid; i < n; i += 1024) {
+            const double v = fabs(M[(size_t)i * n + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            best = s_val[lane]; bi = s_idx[lane];
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) {
+                s_piv = bi;
+                if (!(best > 0)) { *singular = 1; s_pinv = 0.0; }
+                else s_pinv = 1.0 / M[(size_t)bi * n + k];
+            }
+        }
+        __syncthreads();
+        const int p = s_piv;
+        const double pinv = s_pinv;
+        // swap rows k,p and scale the pivot row (columns >= k of M, all of R)
+        for (int j = k + tid; j < n + m; j += 1024) {
+            double* rowk = (j < n) ? &M[(size_t)k * n + j] : &R[(size_t)k * m + (j - n)];
+            double* rowp = (j < n) ? &M[(size_t)p * n + j] : &R[(size_t)p * m + (j - n)];
+            const double vk = *rowk, vp = *rowp;
+            *rowp = vk;
+            *rowk = vp * pinv;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) s_fac[i] = (i == k) ? 0.0 : M[(size_t)i * n + k];
+        __syncthreads();
+        // eliminate column k from every other row
+        const int wj = n - (k + 1) + m;          // columns k+1..n-1 of M, then all of R
+        for (long long o = tid; o < (long long)n * wj; o += 1024) {
+            const int i = (int)(o / wj), jj = (int)(o - (long long)i * wj);
+            const double fct = s_fac[i];
+            if (fct == 0.0) continue;
+            if (jj < n - (k + 1)) {
+                const int j = k + 1 + jj;
+                M[(size_t)i * n + j] -= fct * M[(size_t)k * n + j];
+            } else {
+                const int j = jj - (n - (k + 1));
+                R[(size_t)i * m + j] -= fct * R[(size_t)k * m + j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct FinalizeParams {
+    const double* x; int xdim, N, d;
+    const double* dx;
+    const double* Pnew;      // column-major d x d (unsymmetrised)
+    double* x_out; double* P_out;
+};
+
+__device__ __forceinline__ void d_apply_dq(const double* dth, const double* q, double* out)
+{
+    double dq[4] = {.5 * dth[0], .5 * dth[1], .5 * dth[2], 0};
+    const double vn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+    if (vn < 1) dq[3] = sqrt(1 - vn * vn);
+    else {
+        const double sc = 1 / sqrt(1 + vn * vn);
+        dq[0] *= sc; dq[1] *= sc; dq[2] *= sc; dq[3] = sc;
+    }
+    d_quat_mul(dq, q, out);
+}
+
+// State correction (Updater.cc:546-613) + covariance symmetrisation (Updater.cc:619).
+__global__ void __launch_bounds__(256) k_finalize(FinalizeParams P)
+{
+    const int d = P.d;
+    for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < (long long)d * d; o += (long long)gridDim.x * 256) {
+        const int i = (int)(o % d), j = (int)(o / d);
+        P.P_out[o] = .5 * (P.Pnew[(size_t)j * d + i] + P.Pnew[(size_t)i * d + j]);
+    }
+    if (blockIdx.x == 0) {
+        const double* x = P.x; const double* dx = P.dx; double* xo = P.x_out;
+        for (int b = threadIdx.x; b < 2 + P.N; b += 256) {
+            int xq, eq;
+            if (b == 0) { xq = 0; eq = 0; }
+            else if (b == 1) { xq = 10; eq = 9; }
+            else { xq = 26 + 7 * (b - 2); eq = 24 + 6 * (b - 2); }
+            d_apply_dq(dx + eq, x + xq, xo + xq);
+            if (b >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
+        }
+        if (threadIdx.x == 0) {
+            double g[3];
+            for (int k = 0; k < 3; ++k) xo[4 + k] = dx[3 + k] + x[4 + k];
+            for (int k = 0; k < 3; ++k) g[k] = dx[6 + k] + x[7 + k];
+            const double nn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+            for (int k = 0; k < 3; ++k) xo[7 + k] = g[k] / nn;
+            for (int k = 0; k < 12; ++k) xo[14 + k] = dx[12 + k] + x[14 + k];
+        }
+    }
+}
+
+}  // namespace rvio
+
+// ================================================================================================
+// host side
+// ================================================================================================
 using namespace rvio;
-struct rvio_updater { int device; };
-#define NOTYET(name) { set_error(name, "updater not built yet"); return RVIO_ERR_STATE; }
-extern "C" int rvio_updater_create(const rvio_updater_cfg*, int, rvio_updater**) NOTYET("rvio_updater_create")
-extern "C" void rvio_updater_destroy(rvio_updater*) {}
-extern "C" int rvio_updater_update(rvio_updater*, const double*, int, const double*, int, const uint8_t*, const int32_t*, const float*, int, double*, double*, rvio_update_info*) NOTYET("rvio_updater_update")
-extern "C" int rvio_updater_update_from_tracker(rvio_updater*, rvio_tracker*, const double*, int, const double*, int, double*, double*, rvio_update_info*) NOTYET("x")
-extern "C" int rvio_updater_get_debug(rvio_updater*, int, uint8_t*, double*, double*, int32_t*) NOTYET("x")
-extern "C" int rvio_updater_get_normal_terms(rvio_updater*, double*, double*, int) NOTYET("x")
-extern "C" int rvio_updater_update_begin(rvio_updater*, const double*, int, const double*, int, const uint8_t*, const int32_t*, const float*, int, int, int) NOTYET("x")
-extern "C" int rvio_updater_reduce_buffer(rvio_updater*, double**, int*) NOTYET("x")
-extern "C" int rvio_updater_update_finish(rvio_updater*, double*, double*, rvio_update_info*) NOTYET("x")
-extern "C" void* rvio_updater_stream(rvio_updater*) { return nullptr; }
+
+struct rvio_updater {
+    rvio_updater_cfg cfg;
+    int device;
+    cudaStream_t stream;
+    int Nmax, Fmax, Lmax, nmax, dmax, xmax;
+    UpdaterConsts consts;
+    FeatLayout lay;
+    // device
+    double *d_x, *d_P, *d_xout, *d_Pout, *d_Pnew, *d_dx;
+    uint8_t* d_types; int32_t* d_off; float2* d_xy;
+    uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma; int32_t *d_fdof, *d_fc0, *d_fwc;
+    double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2;
+    int* d_sing;
+    int groups_cap;
+    // pinned
+    double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy;
+    // state of an open begin/finish pair
+    int cur_N, cur_xdim, cur_d, cur_nfeat, cur_rank, cur_world; bool open;
+    const uint8_t* cur_types_dev; const int32_t* cur_off_dev; const float2* cur_xy_dev;
+    std::vector<void*> allocs, hallocs;
+};
+
+namespace {
+
+template <typename T>
+int ualloc(rvio_updater* u, T** p, size_t count)
+{
+    void* q = nullptr;
+    RVIO_CUDA_TRY(cudaMalloc(&q, count * sizeof(T) + 16));
+    RVIO_CUDA_TRY(cudaMemsetAsync(q, 0, count * sizeof(T) + 16, u->stream));
+    u->allocs.push_back(q);
+    *p = (T*)q;
+    return RVIO_OK;
+}
+template <typename T>
+int uhalloc(rvio_updater* u, T** p, size_t count)
+{
+    void* q = nullptr;
+    RVIO_CUDA_TRY(cudaMallocHost(&q, count * sizeof(T) + 16));
+    u->hallocs.push_back(q);
+    *p = (T*)q;
+    return RVIO_OK;
+}
+
+FeatLayout make_layout(int Lc)
+{
+    FeatLayout y;
+    y.Lc = Lc; y.Pc = Lc - 1; y.Mc = 2 * Lc; y.Wc = 6 * (Lc - 1); y.Dc = 2 * Lc - 2;
+    int o = 0;
+    auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+    y.o_relI = take(7 * y.Pc); y.o_RI = take(9 * y.Pc); y.o_RC = take(9 * y.Pc); y.o_tC = take(3 * y.Pc);
+    y.o_HRR = take(6 * y.Lc); y.o_SUB = take(18 * y.Pc); y.o_Hf = take(3 * y.Mc); y.o_r = take(y.Mc);
+    y.o_v = take(y.Mc); y.o_Hx = take(y.Mc * y.Wc); y.o_S = take(y.Dc * y.Dc); y.o_T = take(y.Dc * 32);
+    y.o_meas = take(Lc);      // float2 == one double each
+    y.total_bytes = o * 8;
+    return y;
+}
+
+void launch_gemm(cudaStream_t s, const GemmParams& g)
+{
+    dim3 grid(div_up(g.N, 32), div_up(g.M, 32));
+    RVIO_LAUNCH(k_dgemm, grid, 256, 0, s, g);
+}
+
+}  // namespace
+
+extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio_updater** out)
+{
+    RVIO_ARG_CHECK(cfg && out);
+    RVIO_ARG_CHECK(cfg->max_clones >= 1 && cfg->max_features >= 1 && cfg->max_track_len >= 2);
+    int rc = require_b200(device);
+    if (rc != RVIO_OK) return rc;
+    rvio_updater* u = new (std::nothrow) rvio_updater();
+    if (!u) return RVIO_ERR_CUDA;
+    u->cfg = *cfg; u->device = device; u->open = false;
+    u->Nmax = cfg->max_clones; u->Fmax = cfg->max_features; u->Lmax = cfg->max_track_len;
+    u->nmax = 6 * u->Nmax; u->dmax = 24 + u->nmax; u->xmax = 26 + 7 * u->Nmax;
+    RVIO_CUDA_TRY(cudaSetDevice(device));
+    RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking));
+    UpdaterConsts& c = u->consts;
+    const float sx = cfg->sigma_px, sy = cfg->sigma_py;
+    c.sigma = (double)(sx > sy ? sx : sy);               // Updater.cc:42-44
+    c.sig2 = c.sigma * c.sigma;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) { c.Ric[3 * i + j] = cfg->T_BC0[4 * i + j]; c.Rci[3 * j + i] = cfg->T_BC0[4 * i + j]; }
+        c.tic[i] = cfg->T_BC0[4 * i + 3];
+    }
+    for (int i = 0; i < 3; ++i)
+        c.tci[i] = -(c.Rci[3 * i] * c.tic[0] + c.Rci[3 * i + 1] * c.tic[1] + c.Rci[3 * i + 2] * c.tic[2]);   // Updater.cc:53
+    u->lay = make_layout(u->Lmax);
+    if (u->lay.total_bytes > 200 * 1024) { set_error("rvio_updater_create", "max_track_len too large for shared memory"); return RVIO_ERR_CAPACITY; }
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
+    const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
+    u->groups_cap = 32;
+#define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
+    A(u->d_x, u->xmax); A(u->d_xout, u->xmax); A(u->d_P, d * d); A(u->d_Pout, d * d); A(u->d_Pnew, d * d); A(u->d_dx, d);
+    A(u->d_types, F + 1); A(u->d_off, F + 2); A(u->d_xy, F * u->Lmax + 1);
+    A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1);
+    A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
+    A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
+    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
+#undef A
+#define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
+    HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1));
+#undef HA
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_chi2, RVIO_CHI2_95_HOST, sizeof(double) * 500, cudaMemcpyHostToDevice, u->stream));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
+    *out = u;
+    return RVIO_OK;
+}
+
+extern "C" void rvio_updater_destroy(rvio_updater* u)
+{
+    if (!u) return;
+    cudaSetDevice(u->device);
+    cudaStreamSynchronize(u->stream);
+    for (void* p : u->allocs) cudaFree(p);
+    for (void* p : u->hallocs) cudaFreeHost(p);
+    cudaStreamDestroy(u->stream);
+    delete u;
+}
+
+// Uploads x,P; runs k_feature + normal terms for this rank's share.  Lists are already on the device.
+static int updater_begin_dev(rvio_updater* u, const double* x, int xdim, const double* P, int d,
+                             const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev, int n_feat,
+                             int rank, int world)
+{
+    RVIO_ARG_CHECK(x && P);
+    RVIO_ARG_CHECK(xdim >= 26 && (xdim - 26) % 7 == 0);
+    const int N = (xdim - 26) / 7;
+    RVIO_ARG_CHECK(d == 24 + 6 * N);
+    RVIO_ARG_CHECK(world >= 1 && rank >= 0 && rank < world);
+    if (N > u->Nmax || n_feat > u->Fmax) { set_error("rvio_updater_update", "exceeds capacity given at create"); return RVIO_ERR_CAPACITY; }
+    cudaStream_t s = u->stream;
+    memcpy(u->h_x, x, sizeof(double) * xdim);
+    memcpy(u->h_P, P, sizeof(double) * (size_t)d * d);
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_x, u->h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_P, u->h_P, sizeof(double) * (size_t)d * d, cudaMemcpyHostToDevice, s));
+    u->cur_N = N; u->cur_xdim = xdim; u->cur_d = d; u->cur_nfeat = n_feat; u->cur_rank = rank; u->cur_world = world;
+    u->open = true;
+    const int n = 6 * N;
+    if (n_feat > 0 && N > 0) {
+        FeatureParams fp;
+        fp.x = u->d_x; fp.xdim = xdim; fp.N = N; fp.P = u->d_P; fp.d = d;
+        fp.types = types_dev; fp.offsets = off_dev; fp.xy = xy_dev; fp.n_feat = n_feat;
+        fp.rank = rank; fp.world = world; fp.chi2 = u->d_chi2;
+        fp.f_status = u->d_fstatus; fp.f_pfinv = u->d_fpfinv; fp.f_gamma = u->d_fgamma; fp.f_dof = u->d_fdof;
+        fp.f_c0 = u->d_fc0; fp.f_wc = u->d_fwc; fp.Hblk = u->d_Hblk; fp.rblk = u->d_rblk; fp.blk_rows = u->lay.Mc;
+        fp.c = u->consts; fp.lay = u->lay;
+        if (world > 1) {
+            // features owned by other ranks must not leave stale status/dof behind
+            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat, s));
+            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat, s));
+        }
+        RVIO_LAUNCH(k_feature, n_feat, kFeatThreads, u->lay.total_bytes, s, fp);
+        GramParams gp;
+        gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc;
+        gp.n_feat = n_feat; gp.n = n; gp.blk_rows = u->lay.Mc;
+        gp.groups = n_feat < u->groups_cap ? n_feat : u->groups_cap;
+        gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
+        RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp);
+        RVIO_LAUNCH(k_gram_z, gp.groups, 256, 0, s, gp);
+        RVIO_LAUNCH(k_gram_reduce, div_up(n * n + n, 256), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red);
+    } else {
+        RVIO_CUDA_TRY(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
+    }
+    RVIO_CUDA_TRY(cudaGetLastError());
+    return RVIO_OK;
+}
+
+static int upload_lists(rvio_updater* u, const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat)
+{
+    RVIO_ARG_CHECK(n_feat >= 0 && (n_feat == 0 || (types && offsets && xy)));
+    if (n_feat > u->Fmax) { set_error("rvio_updater_update", "n_feat exceeds capacity"); return RVIO_ERR_CAPACITY; }
+    if (n_feat == 0) return RVIO_OK;
+    const int n_meas = offsets[n_feat] - offsets[0];
+    RVIO_ARG_CHECK(offsets[0] == 0 && n_meas >= 0);
+    if ((size_t)n_meas > (size_t)u->Fmax * u->Lmax) { set_error("rvio_updater_update", "too many measurements"); return RVIO_ERR_CAPACITY; }
+    cudaStream_t s = u->stream;
+    memcpy(u->h_types, types, n_feat);
+    memcpy(u->h_off, offsets, sizeof(int32_t) * (n_feat + 1));
+    memcpy(u->h_xy, xy, sizeof(float) * 2 * n_meas);
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_types, u->h_types, n_feat, cudaMemcpyHostToDevice, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_off, u->h_off, sizeof(int32_t) * (n_feat + 1), cudaMemcpyHostToDevice, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_xy, u->h_xy, sizeof(float) * 2 * n_meas, cudaMemcpyHostToDevice, s));
+    return RVIO_OK;
+}
+
+extern "C" int rvio_updater_update_begin(rvio_updater* u, const double* x, int xdim, const double* P, int d,
+                                         const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat,
+                                         int rank, int world)
+{
+    RVIO_ARG_CHECK(u);
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    int rc = upload_lists(u, types, offsets, xy, n_feat);
+    if (rc != RVIO_OK) return rc;
+    return updater_begin_dev(u, x, xdim, P, d, u->d_types, u->d_off, u->d_xy, n_feat, rank, world);
+}
+
+extern "C" int rvio_updater_reduce_buffer(rvio_updater* u, double** buf_dev, int* count)
+{
+    RVIO_ARG_CHECK(u && buf_dev && count);
+    if (!u->open) { set_error("rvio_updater_reduce_buffer", "no update in flight"); return RVIO_ERR_STATE; }
+    const int n = 6 * u->cur_N;
+    *buf_dev = u->d_red;
+    *count = n * n + n + 8;
+    return RVIO_OK;
+}
+
+extern "C" int rvio_updater_update_finish(rvio_updater* u, double* x_out, double* P_out, rvio_update_info* info)
+{
+    RVIO_ARG_CHECK(u && x_out && P_out);
+    if (!u->open) { set_error("rvio_updater_update_finish", "no update in flight"); return RVIO_ERR_STATE; }
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    u->open = false;
+    cudaStream_t s = u->stream;
+    const int N = u->cur_N, n = 6 * N, d = u->cur_d, xdim = u->cur_xdim;
+    // counters decide between update and pass-through (Updater.cc:460,621-627)
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_red, u->d_red + (size_t)n * n + n, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    const int n_good = (int)u->h_red[0];
+    rvio_update_info inf;
+    inf.n_feat = u->cur_nfeat; inf.n_good = n_good; inf.rows_stacked = (int)u->h_red[1];
+    inf.n_reject_init = (int)u->h_red[2]; inf.n_reject_lm = (int)u->h_red[3]; inf.n_reject_gate = (int)u->h_red[4];
+    inf.updated = n_good > 2 ? 1 : 0;
+    if (info) *info = inf;
+    if (!inf.updated) {
+        memcpy(x_out, u->h_x, sizeof(double) * xdim);
+        memcpy(P_out, u->h_P, sizeof(double) * (size_t)d * d);
+        return RVIO_OK;
+    }
+    const double* G = u->d_red;
+    const double* z = u->d_red + (size_t)n * n;
+    const int m = d + 1;
+    // M = G * Pcc + s^2 I
+    {
+        GemmParams g;
+        g.M = n; g.N = n; g.K = n;
+        g.A = G; g.ars = n; g.acs = 1;
+        g.B = u->d_P + (size_t)24 * d + 24; g.brs = 1; g.bcs = d;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_M; g.crs = n; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = u->consts.sig2;
+        launch_gemm(s, g);
+    }
+    // R = [ z | G * P[c,:] ]   (n x (1+d), row-major)
+    {
+        GemmParams g;
+        g.M = n; g.N = d; g.K = n;
+        g.A = G; g.ars = n; g.acs = 1;
+        g.B = u->d_P + 24; g.brs = 1; g.bcs = d;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_R + 1; g.crs = m; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = 0;
+        // diag_add applies where i == j of the OUTPUT indices: must be 0 here
+        launch_gemm(s, g);
+        RVIO_CUDA_TRY(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+    }
+    RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+    RVIO_LAUNCH(k_gauss_jordan, 1, 1024, sizeof(double) * (n + 2), s, u->d_M, u->d_R, n, m, u->d_sing);
+    // dx = P[:,c] * y_z
+    {
+        GemmParams g;
+        g.M = d; g.N = 1; g.K = n;
+        g.A = u->d_P + (size_t)24 * d; g.ars = 1; g.acs = d;
+        g.B = u->d_R; g.brs = m; g.bcs = 1;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_dx; g.crs = 1; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = 0;
+        launch_gemm(s, g);
+    }
+    // Pnew = P - P[:,c] * Y_W    (column-major d x d)
+    {
+        GemmParams g;
+        g.M = d; g.N = d; g.K = n;
+        g.A = u->d_P + (size_t)24 * d; g.ars = 1; g.acs = d;
+        g.B = u->d_R + 1; g.brs = m; g.bcs = 1;
+        g.C0 = u->d_P; g.c0rs = 1; g.c0cs = d; g.C = u->d_Pnew; g.crs = 1; g.ccs = d;
+        g.alpha = -1; g.beta = 1; g.diag_add = 0;
+        launch_gemm(s, g);
+    }
+    {
+        FinalizeParams fp;
+        fp.x = u->d_x; fp.xdim = xdim; fp.N = N; fp.d = d; fp.dx = u->d_dx; fp.Pnew = u->d_Pnew;
+        fp.x_out = u->d_xout; fp.P_out = u->d_Pout;
+        RVIO_LAUNCH(k_finalize, div_up(d * d, 256), 256, 0, s, fp);
+    }
+    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_x, u->d_xout, sizeof(double) * xdim, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_P, u->d_Pout, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(x_out, u->h_x, sizeof(double) * xdim);
+    memcpy(P_out, u->h_P, sizeof(double) * (size_t)d * d);
+    return RVIO_OK;
+}
+
+extern "C" int rvio_updater_update(rvio_updater* u, const double* x, int xdim, const double* P, int d,
+                                   const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat,
+                                   double* x_out, double* P_out, rvio_update_info* info)
+{
+    int rc = rvio_updater_update_begin(u, x, xdim, P, d, types, offsets, xy, n_feat, 0, 1);
+    if (rc != RVIO_OK) return rc;
+    return rvio_updater_update_finish(u, x_out, P_out, info);
+}
+
+extern "C" int rvio_updater_update_from_tracker(rvio_updater* u, rvio_tracker* trk, const double* x, int xdim,
+                                                const double* P, int d, double* x_out, double* P_out, rvio_update_info* info)
+{
+    RVIO_ARG_CHECK(u && trk);
+    if (tracker_device(trk) != u->device) { set_error("rvio_updater_update_from_tracker", "handles on different devices"); return RVIO_ERR_ARG; }
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    const TrackerBuffers* B = tracker_buffers(trk);
+    int n_meas = 0;
+    const int n_feat = tracker_update_counts(trk, &n_meas);
+    // the tracker finished its stream work before returning (it synchronises to publish its counters)
+    int rc = updater_begin_dev(u, x, xdim, P, d, B->up_types, B->up_off, B->up_xy, n_feat, 0, 1);
+    if (rc != RVIO_OK) return rc;
+    return rvio_updater_update_finish(u, x_out, P_out, info);
+}
+
+extern "C" int rvio_updater_get_debug(rvio_updater* u, int n_feat, uint8_t* status, double* pfinv, double* gamma, int32_t* dof)
+{
+    RVIO_ARG_CHECK(u && n_feat >= 0 && n_feat <= u->Fmax);
+    if (n_feat == 0) return RVIO_OK;
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    cudaStream_t s = u->stream;
+    if (status) RVIO_CUDA_TRY(cudaMemcpyAsync(status, u->d_fstatus, n_feat, cudaMemcpyDeviceToHost, s));
+    if (pfinv) RVIO_CUDA_TRY(cudaMemcpyAsync(pfinv, u->d_fpfinv, sizeof(double) * 3 * n_feat, cudaMemcpyDeviceToHost, s));
+    if (gamma) RVIO_CUDA_TRY(cudaMemcpyAsync(gamma, u->d_fgamma, sizeof(double) * n_feat, cudaMemcpyDeviceToHost, s));
+    if (dof) RVIO_CUDA_TRY(cudaMemcpyAsync(dof, u->d_fdof, sizeof(int32_t) * n_feat, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    return RVIO_OK;
+}
+
+extern "C" int rvio_updater_get_normal_terms(rvio_updater* u, double* G, double* z, int n)
+{
+    RVIO_ARG_CHECK(u && n == 6 * u->cur_N && n > 0);
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    cudaStream_t s = u->stream;
+    if (G) RVIO_CUDA_TRY(cudaMemcpyAsync(G, u->d_red, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, s));
+    if (z) RVIO_CUDA_TRY(cudaMemcpyAsync(z, u->d_red + (size_t)n * n, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    return RVIO_OK;
+}
+
+extern "C" void* rvio_updater_stream(rvio_updater* u) { return u ? (void*)u->stream : nullptr; }

@@ -1,2 +1,45 @@
-// updater_kernels.cuh -- (placeholder, filled in by updater.cu)
+// updater_kernels.cuh -- device side of the MSCKF measurement update (sm_100a), float64.
+//
+// Replaces Updater::update (reference src/rvio/Updater.cc:72-628):
+//   k_feature       one CTA per feature: relative-pose chain (:118-141), inverse-depth LM triangulation (:146-269),
+//                   Jacobian blocks (:271-368), left-nullspace projection (:370-402), chi^2 gate (:404-455)
+//   k_gram / k_gram_z / k_gram_reduce
+//                   compression of the stacked system to its normal terms G = H^T H, z = H^T r  (:460-536)
+//   k_dgemm, k_gauss_jordan, k_finalize
+//                   EKF gain / state correction / covariance (:540-619) in the algebraically identical form
+//                        dx = P[:,c] (G Pcc + s^2 I)^-1 z ,   P+ = P - P[:,c] (G Pcc + s^2 I)^-1 G P[c,:]
+// See DESIGN.md "Updater" for the equivalence argument and for the one deliberate deviation (the reference's
+// first-small-row rank cut, Updater.cc:515-524, can discard informative rows; the normal-term form never does).
 #pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvio {
+
+struct UpdaterConsts {
+    double sigma, sig2;
+    double Ric[9], tic[3], Rci[9], tci[3];
+};
+
+// shared-memory layout of k_feature (offsets in doubles), computed on the host from the capacities
+struct FeatLayout {
+    int Lc, Pc, Mc, Wc, Dc;          // capacities: track length, phases, rows, clone columns, dof
+    int o_relI, o_RI, o_RC, o_tC, o_HRR, o_SUB, o_Hf, o_r, o_v, o_Hx, o_S, o_T, o_meas;
+    int total_bytes;
+};
+
+struct FeatureParams {
+    const double* x; int xdim; int N;           // state, clone count
+    const double* P; int d;                     // covariance, column-major
+    const uint8_t* types; const int32_t* offsets; const float2* xy; int n_feat;
+    int rank, world;                            // feature sharding (f % world == rank)
+    const double* chi2;                         // 500-entry table
+    // outputs
+    uint8_t* f_status; double* f_pfinv; double* f_gamma; int32_t* f_dof; int32_t* f_c0; int32_t* f_wc;
+    double* Hblk; double* rblk;                 // per-feature projected blocks: [f][Mc][n], [f][Mc]
+    int blk_rows;                               // Mc
+    UpdaterConsts c;
+    FeatLayout lay;
+};
+
+}  // namespace rvio
