@@ -150,6 +150,48 @@ int rvio_updater_reduce_buffer(rvio_updater* upd, double** buf_dev, int* count);
 int rvio_updater_update_finish(rvio_updater* upd, double* x_out, double* P_out, rvio_update_info* info);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused per-frame pipeline (SURVEY 8b "optional fused form rvio_frame"): one call == one System::MonoVIO
+ * iteration (src/rvio/System.cc:173-365) with the filter state (x, P), the feature lists and the pyramids resident
+ * on the device; per frame only the image + IMU samples go up and the pose (7 doubles) comes back, with a single
+ * stream synchronisation.  The corner detector stays outside: its output for this frame is passed in.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvio_vio rvio_vio;
+
+typedef struct rvio_vio_cfg {
+    rvio_tracker_cfg tracker;
+    rvio_updater_cfg updater;
+    /* IMU.* (System.cc:60-67, PreIntegrator.cc:32-38) */
+    double imu_rate, sigma_g, sigma_wg, sigma_a, sigma_wa, gravity;
+    /* INI.* (System.cc:77-91) */
+    double thr_angle, thr_displ;
+    int32_t enable_alignment;
+    /* FeatureDetector grid filter (FeatureDetector.cc:31-46) */
+    float   min_dist;
+    int32_t block_x, block_y;
+} rvio_vio_cfg;
+
+int  rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** out);
+void rvio_vio_destroy(rvio_vio* vio);
+
+/* One frame.  cand_px: n_cand detector corners (float2 pixels) for THIS image: used as seeds on the first tracked
+ * image (Tracker.cc:204-234) and passed through FindNewer on the device afterwards (cand_filtered = 0), or taken as
+ * already FindNewer-filtered (cand_filtered = 1).  pose_out = [pGk(3), qkG(4)] (System.cc:369-374); *pose_valid = 0
+ * while the filter is still initialising (System.cc:183-249). */
+int rvio_vio_step(rvio_vio* vio, const uint8_t* img, int width, int height, int stride_bytes, int channels,
+                  const double* imu, int n_imu, const float* cand_px, int n_cand, int cand_filtered,
+                  double* pose_out, int* pose_valid);
+/* Same with the (single-channel) image and the candidate list already in device memory. */
+int rvio_vio_step_dev(rvio_vio* vio, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu,
+                      const float* cand_px_dev, int n_cand, int cand_filtered, double* pose_out, int* pose_valid);
+/* Filter state after the last step: x (26+7N), P (d x d column-major). */
+int rvio_vio_get_state(rvio_vio* vio, double* x, int* xdim, double* P, int* d);
+/* Update counters of the last step (n_feat = 0 when no update ran). */
+int rvio_vio_get_update_info(rvio_vio* vio, rvio_update_info* info);
+/* The tracker / updater handles the pipeline owns (for the debug getters above). */
+rvio_tracker* rvio_vio_tracker(rvio_vio* vio);
+rvio_updater* rvio_vio_updater(rvio_vio* vio);
+
+/* ------------------------------------------------------------------------------------------------
  * Misc
  * ---------------------------------------------------------------------------------------------- */
 const char* rvio_b200_version(void);

@@ -30,6 +30,13 @@ class UpdaterCfg(C.Structure):
                 ("max_clones", C.c_int32), ("max_features", C.c_int32), ("max_track_len", C.c_int32)]
 
 
+class VioCfg(C.Structure):
+    _fields_ = [("tracker", TrackerCfg), ("updater", UpdaterCfg),
+                ("imu_rate", C.c_double), ("sigma_g", C.c_double), ("sigma_wg", C.c_double), ("sigma_a", C.c_double),
+                ("sigma_wa", C.c_double), ("gravity", C.c_double), ("thr_angle", C.c_double), ("thr_displ", C.c_double),
+                ("enable_alignment", C.c_int32), ("min_dist", C.c_float), ("block_x", C.c_int32), ("block_y", C.c_int32)]
+
+
 class UpdateInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_feat", "n_good", "rows_stacked", "updated",
                                           "n_reject_init", "n_reject_lm", "n_reject_gate")]
@@ -44,6 +51,8 @@ SYMBOLS = [
     "rvio_updater_create", "rvio_updater_destroy", "rvio_updater_update", "rvio_updater_update_from_tracker",
     "rvio_updater_get_debug", "rvio_updater_get_normal_terms", "rvio_updater_update_begin",
     "rvio_updater_reduce_buffer", "rvio_updater_update_finish",
+    "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_get_state",
+    "rvio_vio_get_update_info", "rvio_vio_tracker", "rvio_vio_updater",
     "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
     "rvio_tracker_stream", "rvio_updater_stream",
 ]
@@ -91,6 +100,17 @@ def lib():
     L.rvio_updater_update_begin.argtypes = [vp, f64, ci, f64, ci, u8, i32, f32, ci, ci, ci]
     L.rvio_updater_reduce_buffer.argtypes = [vp, C.POINTER(vp), pi]
     L.rvio_updater_update_finish.argtypes = [vp, f64, f64, C.POINTER(UpdateInfo)]
+    L.rvio_vio_create.argtypes = [C.POINTER(VioCfg), ci, C.POINTER(vp)]
+    L.rvio_vio_destroy.argtypes = [vp]
+    L.rvio_vio_destroy.restype = None
+    L.rvio_vio_step.argtypes = [vp, u8, ci, ci, ci, ci, vp, ci, vp, ci, ci, f64, pi]
+    L.rvio_vio_step_dev.argtypes = [vp, vp, ci, vp, ci, vp, ci, ci, f64, pi]
+    L.rvio_vio_get_state.argtypes = [vp, vp, pi, vp, pi]
+    L.rvio_vio_get_update_info.argtypes = [vp, C.POINTER(UpdateInfo)]
+    L.rvio_vio_tracker.argtypes = [vp]
+    L.rvio_vio_tracker.restype = vp
+    L.rvio_vio_updater.argtypes = [vp]
+    L.rvio_vio_updater.restype = vp
     L.rvio_b200_version.restype = C.c_char_p
     L.rvio_b200_last_error.restype = C.c_char_p
     L.rvio_b200_kernel_launches.restype = C.c_uint64
@@ -132,3 +152,13 @@ def updater_cfg(cfg) -> UpdaterCfg:
     u.max_features = (cfg.n_features + 1) // 2
     u.max_track_len = cfg.max_track_len
     return u
+
+
+def vio_cfg(cfg) -> VioCfg:
+    v = VioCfg()
+    v.tracker = tracker_cfg(cfg)
+    v.updater = updater_cfg(cfg)
+    v.imu_rate, v.sigma_g, v.sigma_wg, v.sigma_a, v.sigma_wa = cfg.imu_rate, cfg.sigma_g, cfg.sigma_wg, cfg.sigma_a, cfg.sigma_wa
+    v.gravity, v.thr_angle, v.thr_displ, v.enable_alignment = cfg.gravity, cfg.thr_angle, cfg.thr_displ, cfg.enable_alignment
+    v.min_dist, v.block_x, v.block_y = float(np.float32(cfg.min_dist)), cfg.block_x, cfg.block_y
+    return v

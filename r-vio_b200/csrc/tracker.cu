@@ -2,6 +2,7 @@
 // Compiled for sm_100a with -fmad=false (bit-exact float32/float64 contract).
 #include "common.cuh"
 #include "tracker_kernels.cuh"
+#include "device_utils.cuh"
 
 #include <math.h>
 #include <new>
@@ -32,54 +33,6 @@ __device__ __forceinline__ void store_with_border(const PyrLevel& L, int x, int 
     if (y <= L.h - 2 && y >= L.h - 1 - kBorder) ys[ny++] = 2 * (L.h - 1) - y;
     for (int a = 0; a < ny; ++a)
         for (int b = 0; b < nx; ++b) L.base[(ptrdiff_t)ys[a] * L.pitch + xs[b]] = v;
-}
-
-__device__ __forceinline__ int block_reduce_sum(int v, int* sh /* >= 32 ints */)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[wid] = v;
-    __syncthreads();
-    const int nw = (blockDim.x + 31) >> 5;
-    int r = 0;
-    if (wid == 0) {
-        r = lane < nw ? sh[lane] : 0;
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-        if (lane == 0) sh[0] = r;
-    }
-    __syncthreads();
-    r = sh[0];
-    __syncthreads();
-    return r;
-}
-
-// Exclusive scan of one int per thread over the block; returns the exclusive prefix, *total = block sum.
-__device__ __forceinline__ int block_exscan(int v, int* sh /* >= 33 ints */, int* total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) sh[wid] = inc;
-    __syncthreads();
-    const int nw = (blockDim.x + 31) >> 5;
-    if (wid == 0) {
-        int w = lane < nw ? sh[lane] : 0;
-        int winc = w;
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        sh[lane] = winc - w;          // exclusive warp offsets
-        if (lane == 31) sh[32] = winc;
-    }
-    __syncthreads();
-    int res = sh[wid] + inc - v;
-    *total = sh[32];
-    __syncthreads();
-    return res;
 }
 
 // ================================================================================================
@@ -968,7 +921,7 @@ extern "C" void rvio_tracker_destroy(rvio_tracker* t)
     delete t;
 }
 
-static int tracker_run(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu)
+static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu)
 {
     RVIO_ARG_CHECK(n_imu >= 0 && n_imu <= t->imu_cap);
     cudaStream_t s = t->stream;
@@ -1008,7 +961,29 @@ static int tracker_run(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch,
     RVIO_LAUNCH(k_ransac, 1, 256, 0, s, rp);
     RVIO_LAUNCH(k_bookkeep, 1, 256, 0, s, t->B, n);
     RVIO_CUDA_TRY(cudaGetLastError());
+    return RVIO_OK;
+}
+
+static int tracker_run(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu)
+{
+    const int rc = tracker_enqueue(t, gray_dev, gray_pitch, imu, n_imu);
+    if (rc != RVIO_OK) return rc;
     return sync_scalars(t);
+}
+
+static int upload_image(rvio_tracker* t, const uint8_t* img, int width, int height, int stride_bytes, int channels)
+{
+    const size_t row = (size_t)width * channels;
+    for (int y = 0; y < height; ++y) memcpy(t->h_img + (size_t)y * row, img + (size_t)y * stride_bytes, row);
+    cudaStream_t s = t->stream;
+    if (channels == 1) {
+        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_gray, t->gray_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
+    } else {
+        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_in, t->in_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
+        RVIO_LAUNCH(k_gray, dim3(div_up(width, 256), height), 256, 0, s, t->d_in, (int)t->in_pitch, channels,
+                    t->cfg.is_rgb, t->d_gray, (int)t->gray_pitch, width, height);
+    }
+    return RVIO_OK;
 }
 
 extern "C" int rvio_tracker_track(rvio_tracker* t, const uint8_t* img, int width, int height, int stride_bytes,
@@ -1020,16 +995,8 @@ extern "C" int rvio_tracker_track(rvio_tracker* t, const uint8_t* img, int width
     RVIO_ARG_CHECK(stride_bytes >= width * channels);
     RVIO_ARG_CHECK(n_imu == 0 || imu);
     RVIO_CUDA_TRY(cudaSetDevice(t->device));
-    const size_t row = (size_t)width * channels;
-    for (int y = 0; y < height; ++y) memcpy(t->h_img + (size_t)y * row, img + (size_t)y * stride_bytes, row);
-    cudaStream_t s = t->stream;
-    if (channels == 1) {
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_gray, t->gray_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
-    } else {
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_in, t->in_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
-        RVIO_LAUNCH(k_gray, dim3(div_up(width, 256), height), 256, 0, s, t->d_in, (int)t->in_pitch, channels,
-                    t->cfg.is_rgb, t->d_gray, (int)t->gray_pitch, width, height);
-    }
+    const int rcu = upload_image(t, img, width, height, stride_bytes, channels);
+    if (rcu != RVIO_OK) return rcu;
     return tracker_run(t, t->d_gray, (int)t->gray_pitch, imu, n_imu);
 }
 
@@ -1195,8 +1162,32 @@ extern "C" int rvio_tracker_get_pyramid(rvio_tracker* t, int which, int level, u
 
 extern "C" void* rvio_tracker_stream(rvio_tracker* t) { return t ? (void*)t->stream : nullptr; }
 
-// accessors for the updater's fused path (same shared library)
+// accessors for the updater's fused path and for vio.cu (same shared library)
 namespace rvio {
+int tracker_enqueue_frame_host(rvio_tracker* t, const uint8_t* img, int w, int h, int stride, int ch, const double* imu, int n_imu)
+{
+    RVIO_ARG_CHECK(t && img && w == t->W && h == t->H && (ch == 1 || ch == 3 || ch == 4) && stride >= w * ch);
+    const int rc = upload_image(t, img, w, h, stride, ch);
+    if (rc != RVIO_OK) return rc;
+    return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu);
+}
+int tracker_enqueue_frame_dev(rvio_tracker* t, const uint8_t* img_dev, int pitch, const double* imu, int n_imu)
+{
+    return tracker_enqueue(t, img_dev, pitch, imu, n_imu);
+}
+int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n)
+{
+    if (n > t->F) n = t->F;
+    RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, px_dev, n, t->cam);
+    RVIO_CUDA_TRY(cudaGetLastError());
+    t->first = false;
+    return RVIO_OK;
+}
+int tracker_sync(rvio_tracker* t) { return sync_scalars(t); }
+bool tracker_is_first(const rvio_tracker* t) { return t->first; }
+const CamParams* tracker_cam(const rvio_tracker* t) { return &t->cam; }
+int tracker_n_track(const rvio_tracker* t) { return t->n_track; }
+const TrackerScalars* tracker_host_scalars(const rvio_tracker* t) { return t->h_sc; }
 const TrackerBuffers* tracker_buffers(const rvio_tracker* t) { return &t->B; }
 int tracker_update_counts(const rvio_tracker* t, int* n_meas) { if (n_meas) *n_meas = t->h_sc->n_meas; return t->h_sc->n_up; }
 int tracker_device(const rvio_tracker* t) { return t->device; }

@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+    if (f >= n_feat) return;
     if (f % P.world != P.rank) return;   // feature sharding: this rank owns f % world == rank
     const FeatLayout& Y = P.lay;
     const UpdaterConsts& C = P.c;
@@ -516,6 +518,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 struct GramParams {
     const double* Hblk; const double* rblk; const int32_t* f_dof; const int32_t* f_c0; const int32_t* f_wc;
     int n_feat, n, blk_rows, groups, nt;
+    const int* n_feat_dev;   // optional device-resident feature count (fused path)
     double* Gpart;     // [groups][n][n]
     double* zpart;     // [groups][n]
 };
@@ -528,7 +531,8 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P)
     const int n = P.n;
     const int i0 = ti * 32, j0 = tj * 32;
     double acc[2][2] = {{0, 0}, {0, 0}};
-    for (int f = g; f < P.n_feat; f += P.groups) {
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+    for (int f = g; f < n_feat; f += P.groups) {
         const int dof = P.f_dof[f];
         if (dof <= 0) continue;
         const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
@@ -562,9 +566,10 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P)
 __global__ void __launch_bounds__(256) k_gram_z(GramParams P)
 {
     const int g = blockIdx.x, n = P.n;
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
     for (int i = threadIdx.x; i < n; i += 256) {
         double acc = 0;
-        for (int f = g; f < P.n_feat; f += P.groups) {
+        for (int f = g; f < n_feat; f += P.groups) {
             const int dof = P.f_dof[f];
             if (dof <= 0) continue;
             const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
@@ -590,7 +595,8 @@ __global__ void __launch_bounds__(256) k_gram_reduce(GramParams P, const uint8_t
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
-        for (int f = rank; f < P.n_feat; f += world) {
+        const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+        for (int f = rank; f < n_feat; f += world) {
             loc++;
             const int st = f_status[f];
             if (st == 0) { good++; rows += P.f_dof[f]; }
@@ -613,11 +619,13 @@ struct GemmParams {
     const double* C0; long long c0rs, c0cs;   // optional addend
     double* C; long long crs, ccs;
     double alpha, beta, diag_add;
+    const double* gate;       // optional: skip the launch when gate[0] <= 2 (fewer than 3 accepted features)
 };
 
 __global__ void __launch_bounds__(256) k_dgemm(GemmParams P)
 {
     __shared__ double sA[16][33], sB[16][33];
+    if (P.gate && !(P.gate[0] > 2.0)) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     double acc[2][2] = {{0, 0}, {0, 0}};
@@ -651,8 +659,9 @@ __global__ void __launch_bounds__(256) k_dgemm(GemmParams P)
 
 // Solves M Y = R in place (Y overwrites R) by Gauss-Jordan elimination with partial pivoting.
 // M: n x n row-major, R: n x m row-major.  Single CTA of 1024 threads; operands stay in L2.
-__global__ void __launch_bounds__(1024) k_gauss_jordan(double* M, double* R, int n, int m, int* singular)
+__global__ void __launch_bounds__(1024) k_gauss_jordan(double* M, double* R, int n, int m, int* singular, const double* gate)
 {
+    if (gate && !(gate[0] > 2.0)) return;
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_piv;
@@ -722,6 +731,8 @@ struct FinalizeParams {
     const double* x; int xdim, N, d;
     const double* dx;
     const double* Pnew;      // column-major d x d (unsymmetrised)
+    const double* P;         // prior (pass-through source)
+    const double* gate;      // counters: gate[0] = accepted features
     double* x_out; double* P_out;
 };
 
@@ -741,6 +752,12 @@ __device__ __forceinline__ void d_apply_dq(const double* dth, const double* q, d
 __global__ void __launch_bounds__(256) k_finalize(FinalizeParams P)
 {
     const int d = P.d;
+    if (!(P.gate[0] > 2.0)) {
+        // Updater.cc:621-627: too few measurements, posterior = prior
+        for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < (long long)d * d; o += (long long)gridDim.x * 256) P.P_out[o] = P.P[o];
+        if (blockIdx.x == 0) for (int i = threadIdx.x; i < P.xdim; i += 256) P.x_out[i] = P.x[i];
+        return;
+    }
     for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < (long long)d * d; o += (long long)gridDim.x * 256) {
         const int i = (int)(o % d), j = (int)(o / d);
         P.P_out[o] = .5 * (P.Pnew[(size_t)j * d + i] + P.Pnew[(size_t)i * d + j]);
@@ -788,10 +805,10 @@ struct rvio_updater {
     int* d_sing;
     int groups_cap;
     // pinned
-    double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy;
+    double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing;
     // state of an open begin/finish pair
     int cur_N, cur_xdim, cur_d, cur_nfeat, cur_rank, cur_world; bool open;
-    const uint8_t* cur_types_dev; const int32_t* cur_off_dev; const float2* cur_xy_dev;
+    const double* cur_x_dev; const double* cur_P_dev;
     std::vector<void*> allocs, hallocs;
 };
 
@@ -877,7 +894,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
-    HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1));
+    HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4);
 #undef HA
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_chi2, RVIO_CHI2_95_HOST, sizeof(double) * 500, cudaMemcpyHostToDevice, u->stream));
     RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
@@ -896,43 +913,38 @@ extern "C" void rvio_updater_destroy(rvio_updater* u)
     delete u;
 }
 
-// Uploads x,P; runs k_feature + normal terms for this rank's share.  Lists are already on the device.
-static int updater_begin_dev(rvio_updater* u, const double* x, int xdim, const double* P, int d,
-                             const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev, int n_feat,
-                             int rank, int world)
+// ------------------------------------------------------------------------------------------------
+// Device-resident core.  Stage A: per-feature kernel + normal terms into the reduce buffer.
+// Stage B: EKF solve + finalisation from the (possibly all-reduced) buffer.  Neither stage synchronises.
+// ------------------------------------------------------------------------------------------------
+namespace rvio {
+
+int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* x_dev, int xdim, const double* P_dev, int d,
+                                 const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev,
+                                 int n_feat_cap, const int* n_feat_dev, int rank, int world)
 {
-    RVIO_ARG_CHECK(x && P);
-    RVIO_ARG_CHECK(xdim >= 26 && (xdim - 26) % 7 == 0);
-    const int N = (xdim - 26) / 7;
-    RVIO_ARG_CHECK(d == 24 + 6 * N);
-    RVIO_ARG_CHECK(world >= 1 && rank >= 0 && rank < world);
-    if (N > u->Nmax || n_feat > u->Fmax) { set_error("rvio_updater_update", "exceeds capacity given at create"); return RVIO_ERR_CAPACITY; }
-    cudaStream_t s = u->stream;
-    memcpy(u->h_x, x, sizeof(double) * xdim);
-    memcpy(u->h_P, P, sizeof(double) * (size_t)d * d);
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_x, u->h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, s));
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_P, u->h_P, sizeof(double) * (size_t)d * d, cudaMemcpyHostToDevice, s));
-    u->cur_N = N; u->cur_xdim = xdim; u->cur_d = d; u->cur_nfeat = n_feat; u->cur_rank = rank; u->cur_world = world;
+    const int N = (xdim - 26) / 7, n = 6 * N;
+    u->cur_N = N; u->cur_xdim = xdim; u->cur_d = d; u->cur_nfeat = n_feat_cap; u->cur_rank = rank; u->cur_world = world;
+    u->cur_x_dev = x_dev; u->cur_P_dev = P_dev;
     u->open = true;
-    const int n = 6 * N;
-    if (n_feat > 0 && N > 0) {
+    if (n_feat_cap > 0 && N > 0) {
         FeatureParams fp;
-        fp.x = u->d_x; fp.xdim = xdim; fp.N = N; fp.P = u->d_P; fp.d = d;
-        fp.types = types_dev; fp.offsets = off_dev; fp.xy = xy_dev; fp.n_feat = n_feat;
+        fp.x = x_dev; fp.xdim = xdim; fp.N = N; fp.P = P_dev; fp.d = d;
+        fp.types = types_dev; fp.offsets = off_dev; fp.xy = xy_dev; fp.n_feat = n_feat_cap; fp.n_feat_dev = n_feat_dev;
         fp.rank = rank; fp.world = world; fp.chi2 = u->d_chi2;
         fp.f_status = u->d_fstatus; fp.f_pfinv = u->d_fpfinv; fp.f_gamma = u->d_fgamma; fp.f_dof = u->d_fdof;
         fp.f_c0 = u->d_fc0; fp.f_wc = u->d_fwc; fp.Hblk = u->d_Hblk; fp.rblk = u->d_rblk; fp.blk_rows = u->lay.Mc;
         fp.c = u->consts; fp.lay = u->lay;
         if (world > 1) {
             // features owned by other ranks must not leave stale status/dof behind
-            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat, s));
-            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat, s));
+            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat_cap, s));
+            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat_cap, s));
         }
-        RVIO_LAUNCH(k_feature, n_feat, kFeatThreads, u->lay.total_bytes, s, fp);
+        RVIO_LAUNCH(k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
         GramParams gp;
         gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc;
-        gp.n_feat = n_feat; gp.n = n; gp.blk_rows = u->lay.Mc;
-        gp.groups = n_feat < u->groups_cap ? n_feat : u->groups_cap;
+        gp.n_feat = n_feat_cap; gp.n_feat_dev = n_feat_dev; gp.n = n; gp.blk_rows = u->lay.Mc;
+        gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
         gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
         RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp);
         RVIO_LAUNCH(k_gram_z, gp.groups, 256, 0, s, gp);
@@ -941,6 +953,103 @@ static int updater_begin_dev(rvio_updater* u, const double* x, int xdim, const d
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     }
     RVIO_CUDA_TRY(cudaGetLastError());
+    return RVIO_OK;
+}
+
+int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, double* P_out_dev)
+{
+    const int N = u->cur_N, n = 6 * N, d = u->cur_d, xdim = u->cur_xdim;
+    const double* x_dev = u->cur_x_dev; const double* P_dev = u->cur_P_dev;
+    u->open = false;
+    if (n == 0) {
+        RVIO_CUDA_TRY(cudaMemcpyAsync(x_out_dev, x_dev, sizeof(double) * xdim, cudaMemcpyDeviceToDevice, s));
+        RVIO_CUDA_TRY(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
+        return RVIO_OK;
+    }
+    const double* G = u->d_red;
+    const double* z = u->d_red + (size_t)n * n;
+    const double* gate = u->d_red + (size_t)n * n + n;      // counters[0] = accepted features (Updater.cc:460)
+    const int m = d + 1;
+    // M = G * Pcc + s^2 I
+    {
+        GemmParams g;
+        g.M = n; g.N = n; g.K = n;
+        g.A = G; g.ars = n; g.acs = 1;
+        g.B = P_dev + (size_t)24 * d + 24; g.brs = 1; g.bcs = d;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_M; g.crs = n; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = u->consts.sig2; g.gate = gate;
+        launch_gemm(s, g);
+    }
+    // R = [ z | G * P[c,:] ]   (n x (1+d), row-major)
+    {
+        GemmParams g;
+        g.M = n; g.N = d; g.K = n;
+        g.A = G; g.ars = n; g.acs = 1;
+        g.B = P_dev + 24; g.brs = 1; g.bcs = d;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_R + 1; g.crs = m; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
+        launch_gemm(s, g);
+        RVIO_CUDA_TRY(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+    }
+    RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+    RVIO_LAUNCH(k_gauss_jordan, 1, 1024, sizeof(double) * (n + 2), s, u->d_M, u->d_R, n, m, u->d_sing, gate);
+    // dx = P[:,c] * y_z
+    {
+        GemmParams g;
+        g.M = d; g.N = 1; g.K = n;
+        g.A = P_dev + (size_t)24 * d; g.ars = 1; g.acs = d;
+        g.B = u->d_R; g.brs = m; g.bcs = 1;
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_dx; g.crs = 1; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
+        launch_gemm(s, g);
+    }
+    // Pnew = P - P[:,c] * Y_W    (column-major d x d)
+    {
+        GemmParams g;
+        g.M = d; g.N = d; g.K = n;
+        g.A = P_dev + (size_t)24 * d; g.ars = 1; g.acs = d;
+        g.B = u->d_R + 1; g.brs = m; g.bcs = 1;
+        g.C0 = P_dev; g.c0rs = 1; g.c0cs = d; g.C = u->d_Pnew; g.crs = 1; g.ccs = d;
+        g.alpha = -1; g.beta = 1; g.diag_add = 0; g.gate = gate;
+        launch_gemm(s, g);
+    }
+    {
+        FinalizeParams fp;
+        fp.x = x_dev; fp.xdim = xdim; fp.N = N; fp.d = d; fp.dx = u->d_dx; fp.Pnew = u->d_Pnew; fp.P = P_dev; fp.gate = gate;
+        fp.x_out = x_out_dev; fp.P_out = P_out_dev;
+        RVIO_LAUNCH(k_finalize, div_up(d * d, 256), 256, 0, s, fp);
+    }
+    RVIO_CUDA_TRY(cudaGetLastError());
+    return RVIO_OK;
+}
+
+const double* updater_counters_dev(const rvio_updater* u)
+{
+    const int n = 6 * u->cur_N;
+    return u->d_red + (size_t)n * n + n;
+}
+int updater_device(const rvio_updater* u) { return u->device; }
+
+}  // namespace rvio
+
+static int check_shapes(rvio_updater* u, const double* x, int xdim, const double* P, int d, int n_feat, int rank, int world)
+{
+    RVIO_ARG_CHECK(x && P);
+    RVIO_ARG_CHECK(xdim >= 26 && (xdim - 26) % 7 == 0);
+    const int N = (xdim - 26) / 7;
+    RVIO_ARG_CHECK(d == 24 + 6 * N);
+    RVIO_ARG_CHECK(world >= 1 && rank >= 0 && rank < world);
+    if (N > u->Nmax || n_feat > u->Fmax) { set_error("rvio_updater_update", "exceeds capacity given at create"); return RVIO_ERR_CAPACITY; }
+    return RVIO_OK;
+}
+
+static int upload_state(rvio_updater* u, const double* x, int xdim, const double* P, int d)
+{
+    cudaStream_t s = u->stream;
+    memcpy(u->h_x, x, sizeof(double) * xdim);
+    memcpy(u->h_P, P, sizeof(double) * (size_t)d * d);
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_x, u->h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_P, u->h_P, sizeof(double) * (size_t)d * d, cudaMemcpyHostToDevice, s));
     return RVIO_OK;
 }
 
@@ -968,9 +1077,11 @@ extern "C" int rvio_updater_update_begin(rvio_updater* u, const double* x, int x
 {
     RVIO_ARG_CHECK(u);
     RVIO_CUDA_TRY(cudaSetDevice(u->device));
-    int rc = upload_lists(u, types, offsets, xy, n_feat);
+    int rc = check_shapes(u, x, xdim, P, d, n_feat, rank, world);
     if (rc != RVIO_OK) return rc;
-    return updater_begin_dev(u, x, xdim, P, d, u->d_types, u->d_off, u->d_xy, n_feat, rank, world);
+    if ((rc = upload_lists(u, types, offsets, xy, n_feat)) != RVIO_OK) return rc;
+    if ((rc = upload_state(u, x, xdim, P, d)) != RVIO_OK) return rc;
+    return updater_enqueue_normal_terms(u, u->stream, u->d_x, xdim, u->d_P, d, u->d_types, u->d_off, u->d_xy, n_feat, nullptr, rank, world);
 }
 
 extern "C" int rvio_updater_reduce_buffer(rvio_updater* u, double** buf_dev, int* count)
@@ -988,82 +1099,23 @@ extern "C" int rvio_updater_update_finish(rvio_updater* u, double* x_out, double
     RVIO_ARG_CHECK(u && x_out && P_out);
     if (!u->open) { set_error("rvio_updater_update_finish", "no update in flight"); return RVIO_ERR_STATE; }
     RVIO_CUDA_TRY(cudaSetDevice(u->device));
-    u->open = false;
     cudaStream_t s = u->stream;
-    const int N = u->cur_N, n = 6 * N, d = u->cur_d, xdim = u->cur_xdim;
-    // counters decide between update and pass-through (Updater.cc:460,621-627)
+    const int n = 6 * u->cur_N, d = u->cur_d, xdim = u->cur_xdim;
+    int rc = updater_enqueue_solve(u, s, u->d_xout, u->d_Pout);
+    if (rc != RVIO_OK) return rc;
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_red, u->d_red + (size_t)n * n + n, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
-    RVIO_CUDA_TRY(cudaStreamSynchronize(s));
-    const int n_good = (int)u->h_red[0];
-    rvio_update_info inf;
-    inf.n_feat = u->cur_nfeat; inf.n_good = n_good; inf.rows_stacked = (int)u->h_red[1];
-    inf.n_reject_init = (int)u->h_red[2]; inf.n_reject_lm = (int)u->h_red[3]; inf.n_reject_gate = (int)u->h_red[4];
-    inf.updated = n_good > 2 ? 1 : 0;
-    if (info) *info = inf;
-    if (!inf.updated) {
-        memcpy(x_out, u->h_x, sizeof(double) * xdim);
-        memcpy(P_out, u->h_P, sizeof(double) * (size_t)d * d);
-        return RVIO_OK;
-    }
-    const double* G = u->d_red;
-    const double* z = u->d_red + (size_t)n * n;
-    const int m = d + 1;
-    // M = G * Pcc + s^2 I
-    {
-        GemmParams g;
-        g.M = n; g.N = n; g.K = n;
-        g.A = G; g.ars = n; g.acs = 1;
-        g.B = u->d_P + (size_t)24 * d + 24; g.brs = 1; g.bcs = d;
-        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_M; g.crs = n; g.ccs = 1;
-        g.alpha = 1; g.beta = 0; g.diag_add = u->consts.sig2;
-        launch_gemm(s, g);
-    }
-    // R = [ z | G * P[c,:] ]   (n x (1+d), row-major)
-    {
-        GemmParams g;
-        g.M = n; g.N = d; g.K = n;
-        g.A = G; g.ars = n; g.acs = 1;
-        g.B = u->d_P + 24; g.brs = 1; g.bcs = d;
-        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_R + 1; g.crs = m; g.ccs = 1;
-        g.alpha = 1; g.beta = 0; g.diag_add = 0;
-        // diag_add applies where i == j of the OUTPUT indices: must be 0 here
-        launch_gemm(s, g);
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
-    }
-    RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
-    RVIO_LAUNCH(k_gauss_jordan, 1, 1024, sizeof(double) * (n + 2), s, u->d_M, u->d_R, n, m, u->d_sing);
-    // dx = P[:,c] * y_z
-    {
-        GemmParams g;
-        g.M = d; g.N = 1; g.K = n;
-        g.A = u->d_P + (size_t)24 * d; g.ars = 1; g.acs = d;
-        g.B = u->d_R; g.brs = m; g.bcs = 1;
-        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_dx; g.crs = 1; g.ccs = 1;
-        g.alpha = 1; g.beta = 0; g.diag_add = 0;
-        launch_gemm(s, g);
-    }
-    // Pnew = P - P[:,c] * Y_W    (column-major d x d)
-    {
-        GemmParams g;
-        g.M = d; g.N = d; g.K = n;
-        g.A = u->d_P + (size_t)24 * d; g.ars = 1; g.acs = d;
-        g.B = u->d_R + 1; g.brs = m; g.bcs = 1;
-        g.C0 = u->d_P; g.c0rs = 1; g.c0cs = d; g.C = u->d_Pnew; g.crs = 1; g.ccs = d;
-        g.alpha = -1; g.beta = 1; g.diag_add = 0;
-        launch_gemm(s, g);
-    }
-    {
-        FinalizeParams fp;
-        fp.x = u->d_x; fp.xdim = xdim; fp.N = N; fp.d = d; fp.dx = u->d_dx; fp.Pnew = u->d_Pnew;
-        fp.x_out = u->d_xout; fp.P_out = u->d_Pout;
-        RVIO_LAUNCH(k_finalize, div_up(d * d, 256), 256, 0, s, fp);
-    }
-    RVIO_CUDA_TRY(cudaGetLastError());
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_x, u->d_xout, sizeof(double) * xdim, cudaMemcpyDeviceToHost, s));
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_P, u->d_Pout, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToHost, s));
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->h_sing, u->d_sing, sizeof(int), cudaMemcpyDeviceToHost, s));
     RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    rvio_update_info inf;
+    inf.n_feat = u->cur_nfeat; inf.n_good = (int)u->h_red[0]; inf.rows_stacked = (int)u->h_red[1];
+    inf.n_reject_init = (int)u->h_red[2]; inf.n_reject_lm = (int)u->h_red[3]; inf.n_reject_gate = (int)u->h_red[4];
+    inf.updated = inf.n_good > 2 ? 1 : 0;
+    if (info) *info = inf;
     memcpy(x_out, u->h_x, sizeof(double) * xdim);
     memcpy(P_out, u->h_P, sizeof(double) * (size_t)d * d);
+    if (*u->h_sing) { set_error("rvio_updater_update_finish", "singular innovation system"); return RVIO_ERR_STATE; }
     return RVIO_OK;
 }
 
@@ -1085,8 +1137,11 @@ extern "C" int rvio_updater_update_from_tracker(rvio_updater* u, rvio_tracker* t
     const TrackerBuffers* B = tracker_buffers(trk);
     int n_meas = 0;
     const int n_feat = tracker_update_counts(trk, &n_meas);
+    int rc = check_shapes(u, x, xdim, P, d, n_feat, 0, 1);
+    if (rc != RVIO_OK) return rc;
+    if ((rc = upload_state(u, x, xdim, P, d)) != RVIO_OK) return rc;
     // the tracker finished its stream work before returning (it synchronises to publish its counters)
-    int rc = updater_begin_dev(u, x, xdim, P, d, B->up_types, B->up_off, B->up_xy, n_feat, 0, 1);
+    rc = updater_enqueue_normal_terms(u, u->stream, u->d_x, xdim, u->d_P, d, B->up_types, B->up_off, B->up_xy, n_feat, nullptr, 0, 1);
     if (rc != RVIO_OK) return rc;
     return rvio_updater_update_finish(u, x_out, P_out, info);
 }

@@ -32,6 +32,7 @@ struct FeatureParams {
     const double* x; int xdim; int N;           // state, clone count
     const double* P; int d;                     // covariance, column-major
     const uint8_t* types; const int32_t* offsets; const float2* xy; int n_feat;
+    const int* n_feat_dev;                      // optional device-resident count (fused path); grid covers capacity
     int rank, world;                            // feature sharding (f % world == rank)
     const double* chi2;                         // 500-entry table
     // outputs

@@ -1,0 +1,397 @@
+// vio.cu -- fused per-frame pipeline: one rvio_vio_step == one System::MonoVIO iteration
+// (reference src/rvio/System.cc:173-365) with x, P, pyramids and feature lists resident on the device.
+// Host side keeps only what is inherently serial and tiny: the motion-detection / initialisation logic
+// (System.cc:183-249, System::initialize :115-170) and the clone counters.
+#include "common.cuh"
+#include "tracker_kernels.cuh"
+#include "filter_kernels.cuh"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace rvio {
+// tracker.cu
+int tracker_enqueue_frame_host(rvio_tracker* t, const uint8_t* img, int w, int h, int stride, int ch, const double* imu, int n_imu);
+int tracker_enqueue_frame_dev(rvio_tracker* t, const uint8_t* img_dev, int pitch, const double* imu, int n_imu);
+int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n);
+int tracker_sync(rvio_tracker* t);
+bool tracker_is_first(const rvio_tracker* t);
+const CamParams* tracker_cam(const rvio_tracker* t);
+const TrackerBuffers* tracker_buffers(const rvio_tracker* t);
+cudaStream_t tracker_stream(const rvio_tracker* t);
+const TrackerScalars* tracker_host_scalars(const rvio_tracker* t);
+// updater.cu
+int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* x_dev, int xdim, const double* P_dev, int d,
+                                 const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev,
+                                 int n_feat_cap, const int* n_feat_dev, int rank, int world);
+int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, double* P_out_dev);
+const double* updater_counters_dev(const rvio_updater* u);
+}  // namespace rvio
+
+using namespace rvio;
+
+struct rvio_vio {
+    rvio_vio_cfg cfg;
+    int device;
+    rvio_tracker* trk;
+    rvio_updater* upd;
+    cudaStream_t stream;
+    int window, min_clones, Fu, F;
+    // device state (ping-pong)
+    double* d_x[2]; double* d_P[2]; int xi, pi;
+    double* d_pose; double* d_imu; float2* d_cand;
+    // pinned
+    double* h_pose; double* h_imu; float* h_cand; double* h_cnt; double* h_state;
+    // System.cc statics, per instance
+    bool moving, ready;
+    double wm[3], am[3];
+    int n_imu_count, n_clones, n_img_after_init;
+    rvio_update_info last_info;
+    // FindNewer geometry
+    int gc, gr, offx, offy, max_per_block;
+    std::vector<void*> allocs, hallocs;
+};
+
+namespace {
+
+int xdim_of(int N) { return 26 + 7 * N; }
+int d_of(int N) { return 24 + 6 * N; }
+
+void h_quat_from_rot(const double* R, double* q)      // Numerics.h:126-167
+{
+    const double T = R[0] + R[4] + R[8];
+    if (R[0] > T && R[0] > R[4] && R[0] > R[8]) {
+        q[0] = sqrt((1 + 2 * R[0] - T) / 4);
+        q[1] = (1 / (4 * q[0])) * (R[1] + R[3]); q[2] = (1 / (4 * q[0])) * (R[2] + R[6]); q[3] = (1 / (4 * q[0])) * (R[5] - R[7]);
+    } else if (R[4] > T && R[4] > R[0] && R[4] > R[8]) {
+        q[1] = sqrt((1 + 2 * R[4] - T) / 4);
+        q[0] = (1 / (4 * q[1])) * (R[1] + R[3]); q[2] = (1 / (4 * q[1])) * (R[5] + R[7]); q[3] = (1 / (4 * q[1])) * (R[6] - R[2]);
+    } else if (R[8] > T && R[8] > R[0] && R[8] > R[4]) {
+        q[2] = sqrt((1 + 2 * R[8] - T) / 4);
+        q[0] = (1 / (4 * q[2])) * (R[2] + R[6]); q[1] = (1 / (4 * q[2])) * (R[5] + R[7]); q[3] = (1 / (4 * q[2])) * (R[1] - R[3]);
+    } else {
+        q[3] = sqrt((1 + T) / 4);
+        q[0] = (1 / (4 * q[3])) * (R[5] - R[7]); q[1] = (1 / (4 * q[3])) * (R[6] - R[2]); q[2] = (1 / (4 * q[3])) * (R[1] - R[3]);
+    }
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) q[i] /= n;
+    if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+}
+
+double nrm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// System::initialize (System.cc:115-170): x (26), P (24x24)
+void h_initialize(const rvio_vio_cfg& c, const double* w, const double* a, int n_imu, double* x, double* P)
+{
+    double g[3] = {a[0], a[1], a[2]};
+    const double gn = nrm3(g);
+    for (int k = 0; k < 3; ++k) g[k] /= gn;
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (c.enable_alignment) {
+        const double* zv = g;
+        const double ex[3] = {1, 0, 0};
+        double t[3], xv[3], yv[3];
+        for (int i = 0; i < 3; ++i) t[i] = zv[i] * zv[0] * ex[0] + zv[i] * zv[1] * ex[1] + zv[i] * zv[2] * ex[2];
+        for (int k = 0; k < 3; ++k) xv[k] = ex[k] - t[k];
+        const double n1 = nrm3(xv);
+        for (int k = 0; k < 3; ++k) xv[k] /= n1;
+        yv[0] = -zv[2] * xv[1] + zv[1] * xv[2];
+        yv[1] = zv[2] * xv[0] - zv[0] * xv[2];
+        yv[2] = -zv[1] * xv[0] + zv[0] * xv[1];
+        const double n2 = nrm3(yv);
+        for (int k = 0; k < 3; ++k) yv[k] /= n2;
+        for (int i = 0; i < 3; ++i) { R[3 * i] = xv[i]; R[3 * i + 1] = yv[i]; R[3 * i + 2] = zv[i]; }
+    }
+    memset(x, 0, 26 * sizeof(double));
+    h_quat_from_rot(R, x);
+    for (int k = 0; k < 3; ++k) x[7 + k] = g[k];
+    if (n_imu > 1)
+        for (int k = 0; k < 3; ++k) { x[20 + k] = w[k]; x[23 + k] = a[k] - c.gravity * g[k]; }
+    const double dt = 1. / c.imu_rate;
+    memset(P, 0, 24 * 24 * sizeof(double));
+    for (int k = 0; k < 6; ++k) P[k * 24 + k] = 1e-3 * 1e-3;
+    for (int k = 6; k < 9; ++k) P[k * 24 + k] = n_imu * dt * (c.sigma_a * c.sigma_a);
+    for (int k = 18; k < 21; ++k) P[k * 24 + k] = n_imu * dt * (c.sigma_wg * c.sigma_wg);
+    for (int k = 21; k < 24; ++k) P[k * 24 + k] = n_imu * dt * (c.sigma_wa * c.sigma_wa);
+}
+
+template <typename T>
+int valloc(rvio_vio* v, T** p, size_t count)
+{
+    void* q = nullptr;
+    RVIO_CUDA_TRY(cudaMalloc(&q, count * sizeof(T) + 16));
+    RVIO_CUDA_TRY(cudaMemset(q, 0, count * sizeof(T) + 16));
+    v->allocs.push_back(q);
+    *p = (T*)q;
+    return RVIO_OK;
+}
+template <typename T>
+int vhalloc(rvio_vio* v, T** p, size_t count)
+{
+    void* q = nullptr;
+    RVIO_CUDA_TRY(cudaMallocHost(&q, count * sizeof(T) + 16));
+    memset(q, 0, count * sizeof(T) + 16);
+    v->hallocs.push_back(q);
+    *p = (T*)q;
+    return RVIO_OK;
+}
+
+// Motion detection + initialisation, System.cc:183-249.  Returns the number of leading IMU rows consumed
+// (the rest of the list is what tracking / propagation see), or -1 while still waiting.
+int init_step(rvio_vio* v, const double* imu, int n_imu)
+{
+    const rvio_vio_cfg& c = v->cfg;
+    if (!v->moving) {
+        double ang[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, displ[3] = {0, 0, 0};
+        for (int s = 0; s < n_imu; ++s) {
+            const double* w = imu + 8 * s;
+            double a[3] = {w[3], w[4], w[5]};
+            const double dt = w[7];
+            const double an = nrm3(a);
+            const double a0[3] = {a[0], a[1], a[2]};
+            for (int k = 0; k < 3; ++k) a[k] -= c.gravity * a0[k] / an;
+            for (int k = 0; k < 3; ++k) {
+                ang[k] += dt * w[k];
+                vel[k] += dt * a[k];
+                displ[k] += dt * vel[k] + .5 * (dt * dt) * a[k];
+            }
+        }
+        if (nrm3(ang) > c.thr_angle || nrm3(displ) > c.thr_displ) v->moving = true;
+    }
+    int consumed = 0;
+    while (consumed < n_imu) {
+        const double* r = imu + 8 * consumed;
+        if (!v->moving) {
+            for (int k = 0; k < 3; ++k) { v->wm[k] += r[k]; v->am[k] += r[3 + k]; }
+            consumed++;
+            v->n_imu_count++;
+        } else {
+            if (v->n_imu_count == 0) {
+                for (int k = 0; k < 3; ++k) { v->wm[k] = r[k]; v->am[k] = r[3 + k]; }
+                v->n_imu_count = 1;
+            } else {
+                for (int k = 0; k < 3; ++k) { v->wm[k] /= v->n_imu_count; v->am[k] /= v->n_imu_count; }
+            }
+            v->ready = true;
+            return consumed;
+        }
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** out)
+{
+    RVIO_ARG_CHECK(cfg && out);
+    rvio_vio* v = new (std::nothrow) rvio_vio();
+    if (!v) return RVIO_ERR_CUDA;
+    v->cfg = *cfg; v->device = device;
+    int rc = rvio_tracker_create(&cfg->tracker, device, &v->trk);
+    if (rc != RVIO_OK) { delete v; return rc; }
+    rc = rvio_updater_create(&cfg->updater, device, &v->upd);
+    if (rc != RVIO_OK) { rvio_tracker_destroy(v->trk); delete v; return rc; }
+    v->stream = tracker_stream(v->trk);
+    v->window = cfg->tracker.max_track_len - 1;             // System.cc:71-72
+    v->min_clones = cfg->tracker.min_track_len - 1;         // System.cc:74-75
+    v->F = cfg->tracker.n_features; v->Fu = (v->F + 1) / 2;
+    RVIO_ARG_CHECK(cfg->updater.max_clones >= v->window && cfg->updater.max_features >= v->Fu &&
+                   cfg->updater.max_track_len >= cfg->tracker.max_track_len);
+    const size_t xmax = xdim_of(v->window), dmax = d_of(v->window);
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = valloc(v, &v->d_x[k], xmax)) != RVIO_OK) return rc;
+        if ((rc = valloc(v, &v->d_P[k], dmax * dmax)) != RVIO_OK) return rc;
+    }
+    if ((rc = valloc(v, &v->d_pose, 8)) != RVIO_OK) return rc;
+    if ((rc = valloc(v, &v->d_imu, 512 * 8)) != RVIO_OK) return rc;
+    if ((rc = valloc(v, &v->d_cand, (size_t)v->F + 1)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_pose, 8)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_imu, 512 * 8)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_cand, 2 * ((size_t)v->F + 1))) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_cnt, 8)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_state, xmax + dmax * dmax)) != RVIO_OK) return rc;
+    v->xi = v->pi = 0;
+    v->moving = v->ready = false;
+    for (int k = 0; k < 3; ++k) { v->wm[k] = 0; v->am[k] = 0; }
+    v->n_imu_count = 0; v->n_clones = 0; v->n_img_after_init = 0;
+    memset(&v->last_info, 0, sizeof v->last_info);
+    // FeatureDetector.cc:40-46 (int / float member types as in FeatureDetector.h:61-74)
+    const int W = cfg->tracker.width, H = cfg->tracker.height;
+    v->gc = (int)floor((double)W / (float)cfg->block_x);
+    v->gr = (int)floor((double)H / (float)cfg->block_y);
+    RVIO_ARG_CHECK(v->gc > 0 && v->gr > 0);
+    v->offx = (int)(.5 * (W - v->gc * (float)cfg->block_x));
+    v->offy = (int)(.5 * (H - v->gr * (float)cfg->block_y));
+    v->max_per_block = (int)((float)v->F / (v->gc * v->gr));
+    if (.75 * v->max_per_block >= kFindNewerCellCap) { set_error("rvio_vio_create", "grid cell capacity exceeded"); return RVIO_ERR_CAPACITY; }
+    *out = v;
+    return RVIO_OK;
+}
+
+extern "C" void rvio_vio_destroy(rvio_vio* v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaStreamSynchronize(v->stream);
+    for (void* p : v->allocs) cudaFree(p);
+    for (void* p : v->hallocs) cudaFreeHost(p);
+    rvio_updater_destroy(v->upd);
+    rvio_tracker_destroy(v->trk);
+    delete v;
+}
+
+static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int height, int stride, int channels,
+                         const uint8_t* img_dev, int pitch, const double* imu, int n_imu,
+                         const float* cand_host, const float* cand_dev_in, int n_cand, int cand_filtered,
+                         double* pose_out, int* pose_valid)
+{
+    RVIO_ARG_CHECK(v && pose_out && pose_valid && (n_imu == 0 || imu) && n_imu <= 512 && n_cand >= 0);
+    *pose_valid = 0;
+    RVIO_CUDA_TRY(cudaSetDevice(v->device));
+    if (n_imu < 2) return RVIO_OK;                          // InputBuffer.cc:76-77
+    cudaStream_t s = v->stream;
+    if (!v->ready) {
+        const int used = init_step(v, imu, n_imu);
+        if (used < 0) return RVIO_OK;
+        double x0[26], P0[576];
+        h_initialize(v->cfg, v->wm, v->am, v->n_imu_count, x0, P0);
+        memcpy(v->h_state, x0, sizeof x0);
+        memcpy(v->h_state + 26, P0, sizeof P0);
+        v->xi = v->pi = 0;
+        RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_x[0], v->h_state, sizeof x0, cudaMemcpyHostToDevice, s));
+        RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_P[0], v->h_state + 26, sizeof P0, cudaMemcpyHostToDevice, s));
+        RVIO_CUDA_TRY(cudaStreamSynchronize(s));
+        imu += 8 * used; n_imu -= used;
+    }
+    v->n_img_after_init++;
+    if (n_cand > v->F) n_cand = v->F;
+
+    // ---- visual tracking (System.cc:258)
+    int rc;
+    if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
+    else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
+    if (rc < 0) return rc;
+    const float2* cand_dev = nullptr;
+    if (n_cand > 0) {
+        if (cand_dev_in) cand_dev = reinterpret_cast<const float2*>(cand_dev_in);
+        else {
+            memcpy(v->h_cand, cand_host, sizeof(float) * 2 * n_cand);
+            RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, v->h_cand, sizeof(float) * 2 * n_cand, cudaMemcpyHostToDevice, s));
+            cand_dev = v->d_cand;
+        }
+    }
+    bool frame_committable = false;
+    if (rc == RVIO_FIRST_IMAGE) {
+        if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand); if (r2 != RVIO_OK) return r2; }
+        frame_committable = true;
+    } else if (rc == RVIO_OK) {
+        if (n_cand > 0) {
+            FindNewerParams fp;
+            fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = n_cand; fp.raw = cand_filtered ? 1 : 0;
+            fp.W = v->cfg.tracker.width; fp.H = v->cfg.tracker.height; fp.gc = v->gc; fp.gr = v->gr;
+            fp.offx = v->offx; fp.offy = v->offy; fp.max_per_block = v->max_per_block;
+            fp.bx = (float)v->cfg.block_x; fp.by = (float)v->cfg.block_y; fp.min_dist = v->cfg.min_dist;
+            fp.cam = *tracker_cam(v->trk);
+            int r2 = launch_find_newer_refill(s, fp);
+            if (r2 != RVIO_OK) return r2;
+        }
+        frame_committable = true;
+    }
+
+    // ---- propagation (System.cc:263)
+    const int N = v->n_clones;
+    const int xdim = xdim_of(N), d = d_of(N);
+    memcpy(v->h_imu, imu, sizeof(double) * 8 * n_imu);
+    RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_imu, v->h_imu, sizeof(double) * 8 * n_imu, cudaMemcpyHostToDevice, s));
+    {
+        PropagateParams pp;
+        pp.x_in = v->d_x[v->xi]; pp.P_in = v->d_P[v->pi]; pp.xdim = xdim; pp.d = d;
+        pp.imu = v->d_imu; pp.n_imu = n_imu; pp.x_out = v->d_x[1 - v->xi]; pp.P_out = v->d_P[1 - v->pi];
+        pp.c.gravity = v->cfg.gravity; pp.c.small_angle = v->cfg.tracker.small_angle;
+        pp.c.sigma_g = v->cfg.sigma_g; pp.c.sigma_wg = v->cfg.sigma_wg; pp.c.sigma_a = v->cfg.sigma_a; pp.c.sigma_wa = v->cfg.sigma_wa;
+        int r2 = launch_propagate(s, pp);
+        if (r2 != RVIO_OK) return r2;
+        v->xi = 1 - v->xi; v->pi = 1 - v->pi;
+    }
+    // ---- update (System.cc:266-277)
+    bool ran_update = false;
+    if (N > v->min_clones) {
+        const TrackerBuffers* B = tracker_buffers(v->trk);
+        int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[v->xi], xdim, v->d_P[v->pi], d, B->up_types, B->up_off, B->up_xy,
+                                              v->Fu, &B->sc->n_up, 0, 1);
+        if (r2 != RVIO_OK) return r2;
+        r2 = updater_enqueue_solve(v->upd, s, v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
+        if (r2 != RVIO_OK) return r2;
+        v->xi = 1 - v->xi; v->pi = 1 - v->pi;
+        ran_update = true;
+        RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    }
+    // ---- augmentation + composition (System.cc:280-365)
+    {
+        AugmentParams ap;
+        ap.x = v->d_x[v->xi]; ap.P_in = v->d_P[v->pi]; ap.P_out = v->d_P[1 - v->pi];
+        ap.d = d; ap.N = N; ap.window = v->window; ap.do_augment = v->n_img_after_init > 1 ? 1 : 0; ap.pose_out = v->d_pose;
+        int r2 = launch_augment_compose(s, ap);
+        if (r2 != RVIO_OK) return r2;
+        v->pi = 1 - v->pi;
+        if (ap.do_augment && N < v->window) v->n_clones = N + 1;
+    }
+    RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+    int r3 = tracker_sync(v->trk);                          // publishes tracker counters + synchronises the stream
+    if (r3 != RVIO_OK) return r3;
+    if (frame_committable) { r3 = rvio_tracker_commit(v->trk); if (r3 != RVIO_OK) return r3; }
+    memcpy(pose_out, v->h_pose, sizeof(double) * 7);
+    *pose_valid = 1;
+    rvio_update_info inf;
+    memset(&inf, 0, sizeof inf);
+    if (ran_update) {
+        inf.n_feat = tracker_host_scalars(v->trk)->n_up;
+        inf.n_good = (int)v->h_cnt[0]; inf.rows_stacked = (int)v->h_cnt[1];
+        inf.n_reject_init = (int)v->h_cnt[2]; inf.n_reject_lm = (int)v->h_cnt[3]; inf.n_reject_gate = (int)v->h_cnt[4];
+        inf.updated = inf.n_good > 2 ? 1 : 0;
+    }
+    v->last_info = inf;
+    return RVIO_OK;
+}
+
+extern "C" int rvio_vio_step(rvio_vio* v, const uint8_t* img, int width, int height, int stride_bytes, int channels,
+                             const double* imu, int n_imu, const float* cand_px, int n_cand, int cand_filtered,
+                             double* pose_out, int* pose_valid)
+{
+    RVIO_ARG_CHECK(v && img && (n_cand == 0 || cand_px));
+    return vio_step_impl(v, img, width, height, stride_bytes, channels, nullptr, 0, imu, n_imu, cand_px, nullptr, n_cand,
+                         cand_filtered, pose_out, pose_valid);
+}
+
+extern "C" int rvio_vio_step_dev(rvio_vio* v, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu,
+                                 const float* cand_px_dev, int n_cand, int cand_filtered, double* pose_out, int* pose_valid)
+{
+    RVIO_ARG_CHECK(v && img_dev && (n_cand == 0 || cand_px_dev));
+    return vio_step_impl(v, nullptr, 0, 0, 0, 1, img_dev, pitch_bytes, imu, n_imu, nullptr, cand_px_dev, n_cand,
+                         cand_filtered, pose_out, pose_valid);
+}
+
+extern "C" int rvio_vio_get_state(rvio_vio* v, double* x, int* xdim, double* P, int* d)
+{
+    RVIO_ARG_CHECK(v && xdim && d);
+    RVIO_CUDA_TRY(cudaSetDevice(v->device));
+    const int xd = xdim_of(v->n_clones), dd = d_of(v->n_clones);
+    *xdim = xd; *d = dd;
+    if (x) RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_state, v->d_x[v->xi], sizeof(double) * xd, cudaMemcpyDeviceToHost, v->stream));
+    if (P) RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_state + xd, v->d_P[v->pi], sizeof(double) * (size_t)dd * dd, cudaMemcpyDeviceToHost, v->stream));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(v->stream));
+    if (x) memcpy(x, v->h_state, sizeof(double) * xd);
+    if (P) memcpy(P, v->h_state + xd, sizeof(double) * (size_t)dd * dd);
+    return RVIO_OK;
+}
+
+extern "C" int rvio_vio_get_update_info(rvio_vio* v, rvio_update_info* info)
+{
+    RVIO_ARG_CHECK(v && info);
+    *info = v->last_info;
+    return RVIO_OK;
+}
+
+extern "C" rvio_tracker* rvio_vio_tracker(rvio_vio* v) { return v ? v->trk : nullptr; }
+extern "C" rvio_updater* rvio_vio_updater(rvio_vio* v) { return v ? v->upd : nullptr; }

@@ -234,3 +234,57 @@ class Updater:
         G = np.zeros((n, n)); z = np.zeros(n)
         capi.check(self.L.rvio_updater_get_normal_terms(self.h, G, z, n))
         return G, z
+
+
+class Vio:
+    """Fused per-frame pipeline (rvio_vio_*): System::MonoVIO with x, P, pyramids and feature lists on the device."""
+
+    def __init__(self, cfg, device: int = 0):
+        self.cfg = cfg
+        self.L = capi.lib()
+        self._cfg_c = capi.vio_cfg(cfg)
+        h = C.c_void_p()
+        capi.check(self.L.rvio_vio_create(C.byref(self._cfg_c), device, C.byref(h)), "rvio_vio_create")
+        self.h = h
+        self._pose = np.zeros(7)
+        self._valid = C.c_int()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rvio_vio_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, im, imu, cand=None, cand_filtered=False):
+        im = np.ascontiguousarray(im, np.uint8)
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 8)
+        nc = 0 if cand is None else len(cand)
+        cp = np.ascontiguousarray(cand, np.float32).reshape(-1) if nc else None
+        capi.check(self.L.rvio_vio_step(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
+                                        imu.ctypes.data, len(imu), cp.ctypes.data if nc else None, nc, 1 if cand_filtered else 0,
+                                        self._pose, C.byref(self._valid)), "rvio_vio_step")
+        return self._pose.copy() if self._valid.value else None
+
+    def step_dev(self, img_dev_ptr, pitch, imu, cand_dev_ptr=None, n_cand=0, cand_filtered=False):
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 8)
+        capi.check(self.L.rvio_vio_step_dev(self.h, img_dev_ptr, pitch, imu.ctypes.data, len(imu), cand_dev_ptr, n_cand,
+                                            1 if cand_filtered else 0, self._pose, C.byref(self._valid)), "rvio_vio_step_dev")
+        return self._pose.copy() if self._valid.value else None
+
+    def state(self):
+        xd, d = C.c_int(), C.c_int()
+        capi.check(self.L.rvio_vio_get_state(self.h, None, C.byref(xd), None, C.byref(d)))
+        x = np.zeros(xd.value); P = np.zeros(d.value * d.value)
+        capi.check(self.L.rvio_vio_get_state(self.h, x.ctypes.data, C.byref(xd), P.ctypes.data, C.byref(d)))
+        return x, P.reshape(d.value, d.value).T.copy()
+
+    def update_info(self):
+        inf = capi.UpdateInfo()
+        capi.check(self.L.rvio_vio_get_update_info(self.h, C.byref(inf)))
+        return inf
