@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- VIO frames/sec of the R-VIO hot path (tracker + MSCKF update) on B200, and the CPU reference arm.
+
+Contract (see task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+  step      = one frame of the hot path on a seeded synthetic EuRoC-shaped stream (BASELINE.json configs[1] by default:
+              752x480 mono + 200 Hz IMU, 200 features, 11-clone window), i.e. one System::MonoVIO iteration.
+  value     = frames/s with the frames (and the detector's corner candidates) already resident in HBM (rvio_vio_step_dev).
+  e2e       = frames/s through the public C ABI with HOST buffers (rvio_vio_step): per frame the image + IMU go up and
+              the pose comes back inside the timed region.
+  roofline  = dominant kernel of a step (per-kernel CUDA events recorded by the library on its own stream).
+  cpu_baseline / --impl reference = the same loop on the host cores: OpenCV stages through the real OpenCV (cv2, all
+              threads), Eigen stages through the single-threaded C restatement in oracle/ (the reference is single threaded).
+The corner detector is NOT on the hot path: both arms are fed the same pre-computed corner candidates
+(cv2.goodFeaturesToTrack on the equalised frame); FindNewer + refill run inside both arms.
+N > 1: one process per GPU, each rank runs an independent stream (BASELINE configs[3] style replicas, no collective on the
+data path); value = total frames / max-over-ranks time ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20260922
+T_STATIC = 0.5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- workload
+def make_workload(cfg, n_frames, seed):
+    """Seeded stream + per-frame IMU slices + corner candidates (s=1 and s=2 spacing) from the equalised frames."""
+    import cv2
+    import rvio_b200  # noqa: F401
+    from rvio_b200 import synth
+    st = synth.Stream(cfg, n_frames, seed, t_static=T_STATIC)
+    consumed = 0
+    imus = []
+    for i in range(n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        imus.append(np.ascontiguousarray(imu))
+    clahe = cv2.createCLAHE(3.0, (5, 5))
+    cand1, cand2, eqs = [], [], []
+    q = float(np.float32(cfg.qual_lvl)); md = float(np.float32(cfg.min_dist))
+    for f in st.frames:
+        eq = clahe.apply(f) if cfg.enable_equalizer else f
+        eqs.append(eq)
+        c1 = cv2.goodFeaturesToTrack(eq, cfg.n_features, q, md)
+        c2 = cv2.goodFeaturesToTrack(eq, cfg.n_features, q, 2 * md)
+        cand1.append(np.zeros((0, 2), np.float32) if c1 is None else np.ascontiguousarray(c1.reshape(-1, 2), np.float32))
+        cand2.append(np.zeros((0, 2), np.float32) if c2 is None else np.ascontiguousarray(c2.reshape(-1, 2), np.float32))
+    return dict(stream=st, frames=st.frames, imus=imus, cand1=cand1, cand2=cand2, eqs=eqs)
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self.stop = False
+        self.index = index
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                    if "Active" in val and "Not" not in val:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=3)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, cfg, wl, rank, world, local_rank):
+    import torch
+    import ctypes as C
+    from rvio_b200 import capi, host
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = capi.lib()
+    K, W = args.steps, args.warmup
+    frames, imus = wl["frames"], wl["imus"]
+    n_frames = len(frames)
+    flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def drive(vio, dev_inputs):
+        """pre-roll until the first valid pose, W warm-up steps, K timed steps.  Returns (per-step ms list, wall seconds, launches)."""
+        stream = torch.cuda.ExternalStream(L.rvio_tracker_stream(L.rvio_vio_tracker(vio.h)), device=dev)
+        if dev_inputs:
+            d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+            d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
+            d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
+            torch.cuda.synchronize()
+        got_pose = False
+        i = 0
+        step_ms, timed, warm = [], 0, 0
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        launches0 = None
+        wall = 0.0
+        while timed < K:
+            if i >= n_frames:
+                raise RuntimeError("stream too short for the requested steps")
+            cands = wl["cand2"] if got_pose else wl["cand1"]
+            timing = got_pose and warm >= W
+            if timing:
+                flush.fill_(timed & 0xff)                                  # L2 flush between timed iterations (untimed)
+                torch.cuda.synchronize()
+                if launches0 is None:
+                    launches0 = L.rvio_b200_kernel_launches()
+                ev0[timed].record(stream)
+                t0 = time.perf_counter()
+            if dev_inputs:
+                dc = (d_c2 if got_pose else d_c1)[i]
+                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
+                                    dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
+            else:
+                pose = vio.step(frames[i], imus[i], cands[i])
+            if timing:
+                wall += time.perf_counter() - t0
+                ev1[timed].record(stream)
+                timed += 1
+            elif got_pose:
+                warm += 1
+            if pose is not None:
+                got_pose = True
+            i += 1
+        torch.cuda.synchronize()
+        step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+        return step_ms, wall, L.rvio_b200_kernel_launches() - launches0, i
+
+    import torch.distributed as dist
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clk:
+        # ---- e2e leg (host buffers through the public C ABI)
+        vio = host.Vio(cfg, local_rank)
+        barrier()
+        e2e_ms, e2e_wall, _, _ = drive(vio, dev_inputs=False)
+        barrier()
+        vio.close()
+        # ---- device-resident leg (headline `value`)
+        vio = host.Vio(cfg, local_rank)
+        barrier()
+        dev_ms, dev_wall, launches, used = drive(vio, dev_inputs=True)
+        barrier()
+    # ---- per-kernel events over a few more steps (roofline leg)
+    prof = {}
+    if rank == 0:
+        L.rvio_b200_profile(1)
+        n_prof = 0
+        for i in range(used, min(used + 24, n_frames)):
+            vio.step(frames[i], imus[i], wl["cand2"][i])
+            n_prof += 1
+        L.rvio_b200_profile(0)
+        buf = C.create_string_buffer(1 << 16)
+        nbytes = L.rvio_b200_profile_report(buf, len(buf))
+        for line in buf.raw[:nbytes].decode().splitlines():
+            name, cnt, tot = line.split()
+            prof[name] = (int(cnt), float(tot), n_prof)
+    vio.close()
+
+    t_dev = float(np.sum(dev_ms)) / 1e3
+    t_e2e = float(np.sum(e2e_ms)) / 1e3
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
+                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall)
+
+
+def roofline_from_profile(prof, cfg, peaks):
+    if not prof:
+        return None, {}
+    per_step = {k: v[1] / v[2] for k, v in prof.items()}                   # ms per step per kernel
+    total = sum(per_step.values())
+    top = max(per_step, key=per_step.get)
+    cnt, tot_ms, n_steps = prof[top]
+    avg_s = tot_ms / cnt / 1e3
+    W, H, F = cfg.width, cfg.height, cfg.n_features
+    N = cfg.max_track_len - 1
+    n, d = 6 * N, 24 + 6 * N
+    # algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel must move at least once
+    alg = {
+        "k_lk": 2 * 1.328 * W * H + 20 * F,                                 # both pyramids read once + per-feature I/O
+        "k_clahe_apply": W * H + 1.0 * W * H,                               # read raw, write level 0
+        "k_clahe_lut": W * H,
+        "k_pyr_down": 1.25 * W * H,                                         # all three launches together ~ read+write 0.33WH
+        "k_feature": 8.0 * (n * n) + 8.0 * ((F + 1) // 2) * 2 * (N + 1) * n,  # Pcc once + projected blocks written
+        "k_gram": 8.0 * ((F + 1) // 2) * 2 * (N + 1) * n,
+        "k_gauss_jordan": 8.0 * (n * n + n * (d + 1)) * 2,
+        "k_dgemm": 8.0 * 3 * d * d,
+        "k_propagate": 8.0 * 2 * d * d,
+        "k_augment_compose": 8.0 * 2 * d * d,
+    }.get(top, None)
+    rf = {"kernel": top, "bound": "hbm", "launches_per_step": cnt / n_steps, "avg_launch_us": avg_s * 1e6,
+          "share_of_step_kernel_time": per_step[top] / total if total else None,
+          "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "traffic": None,
+          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks.get("_measured") else "fallback 6650 GB/s"}
+    if alg is not None:
+        rf["algorithmic_bytes_per_launch"] = alg
+        rf["achieved"] = alg / avg_s / 1e9
+        rf["frac"] = rf["achieved"] / rf["peak"] if rf["peak"] else None
+    rf["note"] = ("single-stream VIO at this size moves ~2 MB and ~50 MFLOP per frame: every kernel is latency-bound, "
+                  "the roofline fraction is reported for completeness (SURVEY 8d)")
+    return rf, {k: round(v * 1e3, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}   # us per step
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(cfg, wl, steps, warmup, threads):
+    """Same frame loop on the host: cv2 (real OpenCV) for CLAHE / pyramidal LK, oracle C port for the Eigen stages."""
+    import ctypes as C
+    import cv2
+    from oracle import oracle as orc
+    cv2.setNumThreads(threads)
+    L = orc.lib()
+    v = orc.VioOracle(cfg)
+    trk = v.tracker
+    clahe = cv2.createCLAHE(3.0, (5, 5))
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 1e-2)
+    H, Wd = cfg.height, cfg.width
+    frames, imus = wl["frames"], wl["imus"]
+    state = dict(last_eq=None)
+
+    def track(img, imu, cand1, cand2):
+        # Tracker::track with the OpenCV stages through cv2 (Tracker.cc:198-202,237-244)
+        eq = cv2.createCLAHE(3.0, (5, 5)).apply(img) if cfg.enable_equalizer else img     # new object per frame, as the reference
+        n = L.orc_tracker_n_feats(trk.h)
+        if state["last_eq"] is not None and n > 0:
+            pts = np.ctypeslib.as_array(L.orc_tracker_feats(trk.h), (n, 2)).copy()
+            nxt, stt, _ = cv2.calcOpticalFlowPyrLK(state["last_eq"], eq, pts, None, winSize=(15, 15), maxLevel=3, criteria=crit,
+                                                   flags=0, minEigThreshold=1e-3)
+            lk = np.ascontiguousarray(nxt.reshape(-1, 2), np.float32); stt = np.ascontiguousarray(stt.reshape(-1), np.uint8)
+        else:
+            lk = np.zeros((1, 2), np.float32); stt = np.zeros(1, np.uint8)
+        rc = L.orc_tracker_track_ext(trk.h, np.ascontiguousarray(eq), lk, stt, np.ascontiguousarray(imu), len(imu))
+        if rc == 2:
+            return
+        if rc == 1:
+            if len(cand1):
+                L.orc_tracker_seed(trk.h, cand1, len(cand1))
+        elif L.orc_tracker_n_free(trk.h) > 0 and len(cand2):
+            nt = L.orc_tracker_n_tracked(trk.h)
+            ref = np.ctypeslib.as_array(L.orc_tracker_tracked_px(trk.h), (max(nt, 1), 2))[:nt].copy()
+            newer = orc.find_newer(cfg, cand2, ref)
+            if len(newer):
+                L.orc_tracker_refill(trk.h, newer, len(newer))
+        L.orc_tracker_commit(trk.h)
+        state["last_eq"] = eq
+
+    trk.track = lambda img, imu: None      # VioOracle.step calls tracker.track(img, imu): replaced per frame below
+    got_pose, warm, timed, i = False, 0, 0, 0
+    t_total = 0.0
+    per = []
+    while timed < steps and i < len(frames):
+        c1, c2 = wl["cand1"][i], wl["cand2"][i]
+        trk.track = (lambda img, imu, c1=c1, c2=c2: track(img, imu, c1, c2))
+        timing = got_pose and warm >= warmup
+        t0 = time.perf_counter()
+        pose = v.step(frames[i], imus[i])
+        dt = time.perf_counter() - t0
+        if timing:
+            t_total += dt; per.append(dt); timed += 1
+        elif got_pose:
+            warm += 1
+        if pose is not None:
+            got_pose = True
+        i += 1
+    tm = np.array(v.timing[-timed:]) if timed else np.zeros((0, 2))
+    return dict(t=t_total, steps=timed, tracker_ms=float(np.median(tm[:, 0])) if timed else None,
+                filter_ms=float(np.median(tm[:, 1])) if timed else None)
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import rvio_b200  # noqa: F401
+    from rvio_b200 import synth
+    cfg = synth.baseline_config(args.config)
+    K, W = args.steps, max(args.warmup, 3)
+    args.warmup = W
+    n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 26
+    workload = {"workload": f"BASELINE configs[{args.config}]: synthetic EuRoC-shaped {cfg.width}x{cfg.height} mono + 200 Hz IMU stream, "
+                            f"{cfg.n_features} features, {cfg.max_track_len - 1}-clone window, 1 frame per step",
+                "detector": "corner candidates pre-computed (cv2.goodFeaturesToTrack on the equalised frame), identical for both arms; "
+                            "FindNewer + refill inside the timed step",
+                "l2": "384 MB device buffer rewritten between timed iterations (outside the per-step event pair)",
+                "precision": "tracker bit-exact integer/float32, filter float64"}
+    ncores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(K, 120)                                               # bounded sample of the same workload
+        wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + W + steps + 4, SEED + args.config)
+        r = run_reference(cfg, wl, steps, W, ncores)
+        fps = r["steps"] / r["t"]
+        out = {"metric": "vio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": W,
+               "ms_per_step": 1e3 * r["t"] / r["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload,
+               "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port",
+                                "sample": f"{r['steps']} frames of the same stream; OpenCV stages via cv2 {__import__('cv2').__version__} "
+                                          f"({ncores} threads), Eigen stages via oracle C port (1 thread, as the reference); "
+                                          f"median tracker {r['tracker_ms']:.3f} ms, filter {r['filter_ms']:.3f} ms"},
+               "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a B200: there is no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank)
+    res = run_b200(args, cfg, wl, rank, world, local_rank)
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["_measured"] = True
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0, "_measured": False}
+    rf, per_kernel_us = roofline_from_profile(res["prof"], cfg, peaks)
+    n_imu = int(np.median([len(x) for x in wl["imus"][-K:]]))
+    n_cand = int(np.median([len(x) for x in wl["cand2"][-K:]]))
+    h2d = cfg.width * cfg.height + n_imu * 64 + n_cand * 8
+    d2h = 56 + 4 * 46 + 64
+    value = world * K / res["t_dev"]
+    e2e = world * K / res["t_e2e"]
+    out = {"metric": "vio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": 1e3 * res["t_dev"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": dict(workload, parallelism=f"{world} independent stream(s), one per GPU"),
+           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
+           "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
+           "kernel_us_per_step": per_kernel_us,
+           "wall_ms_per_step": 1e3 * res["dev_wall"] / K}
+    if not args.no_cpu_baseline and world == 1:
+        steps = 60
+        wl2 = {k: (v[:int(T_STATIC * cfg.fps) + 4 + W + steps + 4] if isinstance(v, list) else v) for k, v in wl.items()}
+        r = run_reference(cfg, wl2, steps, min(W, 10), ncores)
+        import cv2
+        out["cpu_baseline"] = {"value": r["steps"] / r["t"], "unit": "frames/s", "cores": ncores, "kind": "port",
+                               "sample": f"{r['steps']} frames of the same stream; OpenCV stages via cv2 {cv2.__version__} ({ncores} threads), "
+                                         f"Eigen stages via oracle C port (1 thread); median tracker {r['tracker_ms']:.3f} ms, filter {r['filter_ms']:.3f} ms"}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

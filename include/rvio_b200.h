@@ -199,6 +199,9 @@ const char* rvio_b200_version(void);
 const char* rvio_b200_last_error(void);
 /* Number of kernels launched by this library since load (for bench accounting), and a reset. */
 uint64_t rvio_b200_kernel_launches(void);
+/* Per-kernel CUDA-event timing (bench.py roofline leg): enable, run some steps, then read "kernel count total_ms" lines. */
+void rvio_b200_profile(int enable);
+int rvio_b200_profile_report(char* buf, int cap);
 /* Raw CUDA stream used by a handle (so a host can order its own work / events against it). */
 void* rvio_tracker_stream(rvio_tracker* trk);
 void* rvio_updater_stream(rvio_updater* upd);

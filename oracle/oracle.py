@@ -88,6 +88,14 @@ def lib():
     L.orc_tracker_destroy.argtypes = [vp]
     L.orc_tracker_track.argtypes = [vp, u8, ci, f64, ci]
     L.orc_tracker_track.restype = ci
+    L.orc_tracker_track_ext.argtypes = [vp, u8, f32, u8, f64, ci]
+    L.orc_tracker_track_ext.restype = ci
+    L.orc_tracker_feats.argtypes = [vp]
+    L.orc_tracker_feats.restype = C.POINTER(C.c_float)
+    L.orc_tracker_n_feats.argtypes = [vp]
+    L.orc_tracker_n_feats.restype = ci
+    L.orc_tracker_last_image.argtypes = [vp]
+    L.orc_tracker_last_image.restype = C.POINTER(C.c_uint8)
     for name, rt in (("image", C.POINTER(C.c_uint8)), ("tracked_px", C.POINTER(C.c_float)),
                      ("update_types", C.POINTER(C.c_uint8)), ("update_offsets", C.POINTER(C.c_int32)),
                      ("update_xy", C.POINTER(C.c_float)), ("last_status", C.POINTER(C.c_uint8)),

@@ -107,6 +107,11 @@ void orc_tracker_destroy(orc_tracker_t* t);
  *           FindNewer) -- then orc_tracker_commit() stores the last image (Tracker.cc:395).
  */
 int  orc_tracker_track(orc_tracker_t* t, const uint8_t* img, int stride, const double* imu, int n_imu);
+int  orc_tracker_track_ext(orc_tracker_t* t, const uint8_t* eq, const float* lk_px, const uint8_t* lk_status,
+                           const double* imu, int n_imu);   /* OpenCV stages supplied by the caller (cv2) */
+const float* orc_tracker_feats(const orc_tracker_t* t);
+int  orc_tracker_n_feats(const orc_tracker_t* t);
+const uint8_t* orc_tracker_last_image(const orc_tracker_t* t);
 const uint8_t* orc_tracker_image(const orc_tracker_t* t);      /* equalised current image, w*h */
 int  orc_tracker_n_free(const orc_tracker_t* t);
 int  orc_tracker_n_tracked(const orc_tracker_t* t);             /* mvFeatsToTrack.size() after bookkeeping */

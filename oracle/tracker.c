@@ -105,6 +105,8 @@ static void emit(orc_tracker_t* t, uint8_t type, int slot)
     t->n_up = n + 1;
 }
 
+static int track_tail(orc_tracker_t* t, const double* imu, int n_imu);
+
 int orc_tracker_track(orc_tracker_t* t, const uint8_t* img, int stride, const double* imu, int n_imu)
 {
     const int w = t->w, h = t->h;
@@ -120,6 +122,31 @@ int orc_tracker_track(orc_tracker_t* t, const uint8_t* img, int stride, const do
 
     /* Tracker.cc:237-244 */
     orc_lk(t->last, t->cur, w, h, w, t->feats, n, t->last_lk, t->last_status, 15, 3, 30, 1e-2, 1e-3);
+    return track_tail(t, imu, n_imu);
+}
+
+/* Same frame step with the OpenCV stages done by the caller through the real OpenCV (cv2): `eq` is the equalised
+ * image (cv2 CLAHE), lk_px/lk_status the output of cv2.calcOpticalFlowPyrLK on (last image, eq, features).  Used by
+ * bench.py's reference arm so that the CPU baseline runs OpenCV's own SIMD/threaded code, as the reference does. */
+int orc_tracker_track_ext(orc_tracker_t* t, const uint8_t* eq, const float* lk_px, const uint8_t* lk_status,
+                          const double* imu, int n_imu)
+{
+    memcpy(t->cur, eq, (size_t)t->w * t->h);
+    if (t->first) return 1;
+    const int n = t->n_track;
+    t->last_n = n;
+    if (n == 0) return 2;
+    memcpy(t->last_lk, lk_px, sizeof(float) * 2 * (size_t)n);
+    memcpy(t->last_status, lk_status, (size_t)n);
+    return track_tail(t, imu, n_imu);
+}
+const float* orc_tracker_feats(const orc_tracker_t* t) { return t->feats; }     /* mvFeatsToTrack (committed) */
+int orc_tracker_n_feats(const orc_tracker_t* t) { return t->n_track; }
+const uint8_t* orc_tracker_last_image(const orc_tracker_t* t) { return t->last; }
+
+static int track_tail(orc_tracker_t* t, const double* imu, int n_imu)
+{
+    const int n = t->n_track;
     /* Tracker.cc:252-261 */
     undist(t, t->last_lk, n, t->last_un);
     double* pts2 = (double*)malloc(sizeof(double) * 3 * (size_t)n);

@@ -54,7 +54,7 @@ SYMBOLS = [
     "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_get_state",
     "rvio_vio_get_update_info", "rvio_vio_tracker", "rvio_vio_updater",
     "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
-    "rvio_tracker_stream", "rvio_updater_stream",
+    "rvio_tracker_stream", "rvio_updater_stream", "rvio_b200_profile", "rvio_b200_profile_report",
 ]
 
 _lib = None
@@ -114,6 +114,9 @@ def lib():
     L.rvio_b200_version.restype = C.c_char_p
     L.rvio_b200_last_error.restype = C.c_char_p
     L.rvio_b200_kernel_launches.restype = C.c_uint64
+    L.rvio_b200_profile.argtypes = [ci]
+    L.rvio_b200_profile.restype = None
+    L.rvio_b200_profile_report.argtypes = [C.c_char_p, ci]
     L.rvio_tracker_stream.argtypes = [vp]
     L.rvio_tracker_stream.restype = vp
     L.rvio_updater_stream.argtypes = [vp]

@@ -1,10 +1,37 @@
 // api_misc.cu -- library-wide state: error text, launch counter, device check, version.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 namespace rvio {
 
 thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_kernel_launches{0};
+
+std::atomic<int> g_profile_on{0};
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}
+void profile_begin(const char* name, cudaStream_t s)
+{
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+}
+void profile_end(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, s);
+}
 
 int require_b200(int device)
 {
@@ -30,3 +57,30 @@ int require_b200(int device)
 extern "C" const char* rvio_b200_version(void) { return "rvio_b200 0.1 (sm_100a)"; }
 extern "C" const char* rvio_b200_last_error(void) { return rvio::g_last_error; }
 extern "C" uint64_t rvio_b200_kernel_launches(void) { return rvio::g_kernel_launches.load(); }
+
+extern "C" void rvio_b200_profile(int enable)
+{
+    rvio::g_profile_on.store(enable ? 1 : 0);
+}
+
+// Writes "kernel count total_ms\n" lines (CUDA-event time of every launch since the last report) and clears the log.
+extern "C" int rvio_b200_profile_report(char* buf, int cap)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(rvio::g_prof_mu);
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : rvio::g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { auto& a = agg[r.name]; a.first++; a.second += ms; }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    rvio::g_prof.clear();
+    int off = 0;
+    for (auto& kv : agg) {
+        const int n = snprintf(buf + off, cap > off ? cap - off : 0, "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (n < 0 || off + n >= cap) break;
+        off += n;
+    }
+    return off;
+}

@@ -35,10 +35,18 @@ inline void set_error(const char* where, const char* what)
         }                                                                               \
     } while (0)
 
-// Counts every kernel this library launches (bench.py reports it as gpu_launches).
+extern std::atomic<int> g_profile_on;
+void profile_begin(const char* name, cudaStream_t s);
+void profile_end(cudaStream_t s);
+
+// Counts every kernel this library launches (bench.py reports it as gpu_launches); with profiling enabled
+// (rvio_b200_profile) each launch is bracketed by CUDA events on its own stream.
 #define RVIO_LAUNCH(kernel, grid, block, smem, stream, ...)                             \
     do {                                                                                \
+        const bool _prof = rvio::g_profile_on.load(std::memory_order_relaxed) != 0;     \
+        if (_prof) rvio::profile_begin(#kernel, (stream));                              \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+        if (_prof) rvio::profile_end((stream));                                         \
         rvio::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                \
     } while (0)
 
