@@ -186,6 +186,20 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         barrier()
         dev_ms, dev_wall, launches, used = drive(vio, dev_inputs=True)
         barrier()
+    # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
+    timeline = None
+    if rank == 0:
+        tl = np.zeros(6, np.float32)
+        L.rvio_vio_timeline(vio.h, 1, None)
+        acc = []
+        for i in range(used, min(used + 12, n_frames)):
+            vio.step(frames[i], imus[i], wl["cand2"][i])
+            L.rvio_vio_timeline(vio.h, 1, tl.ctypes.data)
+            acc.append(tl.copy())
+        L.rvio_vio_timeline(vio.h, 0, None)
+        used = min(used + 12, n_frames)
+        timeline = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail"],
+                            [round(float(v) * 1e3, 1) for v in np.median(np.array(acc), 0)]))
     # ---- per-kernel events over a few more steps (roofline leg)
     prof = {}
     if rank == 0:
@@ -209,7 +223,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
     return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
-                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall)
+                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline)
 
 
 def roofline_from_profile(prof, cfg, peaks):
@@ -324,7 +338,7 @@ def main():
     cfg = synth.baseline_config(args.config)
     K, W = args.steps, max(args.warmup, 3)
     args.warmup = W
-    n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 26
+    n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 40
     workload = {"workload": f"BASELINE configs[{args.config}]: synthetic EuRoC-shaped {cfg.width}x{cfg.height} mono + 200 Hz IMU stream, "
                             f"{cfg.n_features} features, {cfg.max_track_len - 1}-clone window, 1 frame per step",
                 "detector": "corner candidates pre-computed (cv2.goodFeaturesToTrack on the equalised frame), identical for both arms; "
@@ -383,7 +397,7 @@ def main():
            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
            "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
-           "kernel_us_per_step": per_kernel_us,
+           "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
            "wall_ms_per_step": 1e3 * res["dev_wall"] / K}
     if not args.no_cpu_baseline and world == 1:
         steps = 60

@@ -51,41 +51,46 @@ __global__ void k_gray(const uint8_t* __restrict__ src, int src_pitch, int chann
 }
 
 // One CTA (256 threads) per CLAHE tile: histogram of the (reflect-padded) tile, clip, redistribute, LUT.
-__global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ src, int pitch, int w, int h,
-                                                   int tw, int th, int clip, float lut_scale,
-                                                   uint8_t* __restrict__ lut /* 25 x 256 */)
+__global__ void __launch_bounds__(1024) k_clahe_lut(const uint8_t* __restrict__ src, int pitch, int w, int h,
+                                                    int tw, int th, int clip, float lut_scale,
+                                                    uint8_t* __restrict__ lut /* 25 x 256 */)
 {
     __shared__ int hist[256];
     __shared__ int sh[34];
     const int tid = threadIdx.x;
     const int tx = blockIdx.x % 5, ty = blockIdx.x / 5;
-    hist[tid] = 0;
+    if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const int area = tw * th;
-    for (int i = tid; i < area; i += 256) {
+    for (int i = tid; i < area; i += 1024) {
         const int ex = tx * tw + i % tw, ey = ty * th + i / tw;
         const int sx = reflect101(ex, w), sy = reflect101(ey, h);
         atomicAdd(&hist[src[(size_t)sy * pitch + sx]], 1);
     }
     __syncthreads();
-    int v = hist[tid];
+    // the rest is per-bin work: bins live in threads 0..255 (threads >= 256 carry zeros through the block scans)
+    int v = tid < 256 ? hist[tid] : 0;
     int excess = v > clip ? v - clip : 0;
     if (v > clip) v = clip;
     const int clipped = block_reduce_sum(excess, sh);
     const int batch = clipped / 256;
     const int residual = clipped - batch * 256;
-    v += batch;
-    if (residual != 0) {
-        int step = 256 / residual;
-        if (step < 1) step = 1;
-        if (tid % step == 0 && tid / step < residual) v++;
+    if (tid < 256) {
+        v += batch;
+        if (residual != 0) {
+            int step = 256 / residual;
+            if (step < 1) step = 1;
+            if (tid % step == 0 && tid / step < residual) v++;
+        }
     }
     int total;
     const int ex = block_exscan(v, sh, &total);
-    const int sum = ex + v;
-    int q = __float2int_rn(__fmul_rn((float)sum, lut_scale));
-    q = q < 0 ? 0 : (q > 255 ? 255 : q);
-    lut[blockIdx.x * 256 + tid] = (uint8_t)q;
+    if (tid < 256) {
+        const int sum = ex + v;
+        int q = __float2int_rn(__fmul_rn((float)sum, lut_scale));
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        lut[blockIdx.x * 256 + tid] = (uint8_t)q;
+    }
 }
 
 // Bilinear LUT interpolation; writes level 0 of the current pyramid including its reflect border.
@@ -160,13 +165,24 @@ struct LKParams {
     float min_eig_thr;
 };
 
+// Accumulation order reproduced from OpenCV's SIMD128 path (lkpyramid.cpp, LKTrackerInvoker):
+//   A-matrix: for every window row, columns 0..7 feed four float lanes l[k] (+= v(y,k); += v(y,4+k)),
+//             columns 8..14 feed one scalar float accumulator in (y,x) order; total = scalar + ((l0+l2)+(l1+l3)).
+//   b-vector: per row eight int32 pair-sums (d_k*g_k + d_{k+4}*g_{k+4}) are converted to float and added to eight
+//             lanes; columns 8..14 feed two scalar chains; b1 = s1 + ((q0+0)+(q2+0)), b2 = s2 + ((q1+0)+(q3+0)).
+// Work split: lane 2y owns window pixels (y, 0..7), lane 2y+1 owns (y, 8..14) (lanes 30,31 idle); the interpolated
+// previous-image patch stays in registers for the whole level, the next-image window is read from a 32x48 shared-memory
+// tile staged once per level with 16-byte loads (re-staged only if the window leaves it), and the float32 sums are
+// formed in OpenCV's order by walking the owning lanes with shuffles.  The two 105-term scalar chains take an exact
+// shortcut whenever every partial sum (in OpenCV's order) and every term is an integer below 2^24: float32 addition
+// is then exact, so the sum equals the integer total and is order independent; otherwise they are added one by one.
+constexpr int kTileW = 48, kTileH = 32;
+
 struct LKWarpSmem {
-    float prod[3][232];         // float staging for ordered accumulation (225 used)
-    short Iw[232], Ixw[232], Iyw[232];
-    short diff[232];
-    short dgrid[16 * 16 * 2];   // Scharr (dx,dy) on the 16x16 tap grid
+    short dgrid[16 * 16 * 2];            // Scharr (dx,dy) on the 16x16 tap grid
     unsigned char Ireg[18 * 20];
-    unsigned char Jt[16 * 16];
+    __align__(16) unsigned char tile[kTileH * kTileW];
+    __align__(16) float ch[3 * 232];     // per matrix / chain set: [y*8 + slot] (120 floats) then [120 + y*7 + t] (105 floats)
 };
 
 constexpr int kLKWarps = 2;
@@ -200,11 +216,20 @@ __device__ __forceinline__ void lk_weights(float a, float b, int* w00, int* w01,
     *w11 = 16384 - *w00 - *w01 - *w10;
 }
 
-// Accumulation order reproduced from OpenCV's SIMD128 path (lkpyramid.cpp, LKTrackerInvoker):
-//   A-matrix: for every window row, columns 0..7 feed four float lanes l[k] (+= v(y,k); += v(y,4+k)),
-//             columns 8..14 feed one scalar float accumulator in (y,x) order; total = scalar + ((l0+l2)+(l1+l3)).
-//   b-vector: per row eight int32 pair-sums (d_k*g_k + d_{k+4}*g_{k+4}) are converted to float and added to eight
-//             lanes; columns 8..14 feed two scalar chains; b1 = s1 + ((q0+0)+(q2+0)), b2 = s2 + ((q1+0)+(q3+0)).
+// Stage the kTileH x kTileW byte tile whose top-left pixel is (tx0, ty0) (tx0 multiple of 16) from level J.
+__device__ __forceinline__ void lk_stage_tile(const PyrLevel& J, int tx0, int ty0, unsigned char* tile, int lane)
+{
+    const long long total = (long long)J.pitch * (J.h + 2 * kBorder);
+    const unsigned char* origin = J.base - (ptrdiff_t)kBorder * J.pitch - kBorder;      // first byte of the level buffer
+    for (int c = lane; c < kTileH * (kTileW / 16); c += 32) {
+        const int r = c / (kTileW / 16), q = c - r * (kTileW / 16);
+        const long long flat = (long long)(ty0 + r + kBorder) * J.pitch + (tx0 + 16 * q + kBorder);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (flat >= 0 && flat + 16 <= total) v = __ldg(reinterpret_cast<const uint4*>(origin + flat));
+        *reinterpret_cast<uint4*>(tile + r * kTileW + 16 * q) = v;
+    }
+}
+
 __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
 {
     __shared__ LKWarpSmem smem_all[kLKWarps];
@@ -213,6 +238,10 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
     if (pt >= P.n) return;                       // whole warp exits together
     LKWarpSmem& S = smem_all[wib];
     const unsigned FULL = 0xffffffffu;
+    // pixel ownership
+    const int oy = lane >> 1, half_ = lane & 1;
+    const bool owner = lane < 30;
+    const int ox0 = half_ * 8, onx = half_ ? 7 : 8;
 
     const float2 p0 = P.feats[pt];
     float nx = 0.f, ny = 0.f;                   // nextPts[pt] (kept by all lanes identically)
@@ -264,35 +293,57 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
             S.dgrid[2 * i + 1] = (short)dy;
         }
         __syncwarp();
-        // ---- interpolated patch I, Ix, Iy and the A-matrix products
-        for (int i = lane; i < 225; i += 32) {
-            const int y = i / 15, x = i - y * 15;
-            const unsigned char* s = &S.Ireg[(y + 1) * 20 + (x + 1)];
-            const int ival = (s[0] * w00 + s[1] * w01 + s[20] * w10 + s[21] * w11 + (1 << 8)) >> 9;
-            const short* g = &S.dgrid[2 * (y * 16 + x)];
-            const int ixval = (g[0] * w00 + g[2] * w01 + g[32] * w10 + g[34] * w11 + (1 << 13)) >> 14;
-            const int iyval = (g[1] * w00 + g[3] * w01 + g[33] * w10 + g[35] * w11 + (1 << 13)) >> 14;
-            S.Iw[i] = (short)ival; S.Ixw[i] = (short)ixval; S.Iyw[i] = (short)iyval;
-            S.prod[0][i] = (float)(ixval * ixval);
-            S.prod[1][i] = (float)(ixval * iyval);
-            S.prod[2][i] = (float)(iyval * iyval);
+        // ---- interpolated patch I, Ix, Iy of the pixels this lane owns (registers) + A-matrix products
+        int Iw[8], Ixw[8], Iyw[8];
+        float pa11[8], pa12[8], pa22[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            Iw[j] = 0; Ixw[j] = 0; Iyw[j] = 0;
+            if (owner && j < onx) {
+                const int x = ox0 + j;
+                const unsigned char* s = &S.Ireg[(oy + 1) * 20 + (x + 1)];
+                Iw[j] = (s[0] * w00 + s[1] * w01 + s[20] * w10 + s[21] * w11 + (1 << 8)) >> 9;
+                const short* g = &S.dgrid[2 * (oy * 16 + x)];
+                Ixw[j] = (g[0] * w00 + g[2] * w01 + g[32] * w10 + g[34] * w11 + (1 << 13)) >> 14;
+                Iyw[j] = (g[1] * w00 + g[3] * w01 + g[33] * w10 + g[35] * w11 + (1 << 13)) >> 14;
+            }
+            pa11[j] = (float)(Ixw[j] * Ixw[j]);
+            pa12[j] = (float)(Ixw[j] * Iyw[j]);
+            pa22[j] = (float)(Iyw[j] * Iyw[j]);
         }
-        __syncwarp();
         float A11, A12, A22;
         {
-            float acc = 0.f;
-            if (lane < 15) {
-                const int m = lane / 5, j = lane - m * 5;
-                const float* pr = S.prod[m];
-                if (j < 4) {
-                    for (int y = 0; y < 15; ++y) {
-                        acc = __fadd_rn(pr[y * 15 + j], acc);
-                        acc = __fadd_rn(pr[y * 15 + 4 + j], acc);
-                    }
+            // stage the products: lane 2y -> slots [y*8 .. y*8+7], lane 2y+1 -> tail [120 + y*7 .. +6]
+            __syncwarp();
+            if (owner) {
+                if (half_ == 0) {
+                    float4* d0 = reinterpret_cast<float4*>(&S.ch[oy * 8]);
+                    float4* d1 = reinterpret_cast<float4*>(&S.ch[232 + oy * 8]);
+                    float4* d2 = reinterpret_cast<float4*>(&S.ch[464 + oy * 8]);
+                    d0[0] = make_float4(pa11[0], pa11[1], pa11[2], pa11[3]); d0[1] = make_float4(pa11[4], pa11[5], pa11[6], pa11[7]);
+                    d1[0] = make_float4(pa12[0], pa12[1], pa12[2], pa12[3]); d1[1] = make_float4(pa12[4], pa12[5], pa12[6], pa12[7]);
+                    d2[0] = make_float4(pa22[0], pa22[1], pa22[2], pa22[3]); d2[1] = make_float4(pa22[4], pa22[5], pa22[6], pa22[7]);
                 } else {
-                    for (int y = 0; y < 15; ++y)
 #pragma unroll
-                        for (int x = 8; x < 15; ++x) acc = __fadd_rn(acc, pr[y * 15 + x]);
+                    for (int t = 0; t < 7; ++t) {
+                        S.ch[120 + oy * 7 + t] = pa11[t];
+                        S.ch[232 + 120 + oy * 7 + t] = pa12[t];
+                        S.ch[464 + 120 + oy * 7 + t] = pa22[t];
+                    }
+                }
+            }
+            __syncwarp();
+            // 15 chain lanes: lane = 5*m + j ; j<4: SIMD lane j of matrix m (30 terms: (y,j),(y,4+j)) ; j==4: scalar chain (105 terms)
+            float acc = 0.f;
+            {
+                const int m = lane / 5, jn = lane - 5 * m;
+                const float* pr = S.ch + 232 * (m < 3 ? m : 0);
+                const bool is_long = jn == 4;
+                const int cnt = lane < 15 ? (is_long ? 105 : 30) : 0;
+#pragma unroll 5
+                for (int i = 0; i < 105; ++i) {
+                    const int off = is_long ? (120 + i) : ((i >> 1) * 8 + (i & 1) * 4 + jn);
+                    if (i < cnt) acc = __fadd_rn(acc, pr[off]);
                 }
             }
             float t[3];
@@ -319,6 +370,8 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+        int tx0 = 0, ty0 = 0;
+        bool have_tile = false;
 
         for (int j = 0; j < P.max_iter; ++j) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
@@ -327,53 +380,110 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
                 break;
             }
             lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), &w00, &w01, &w10, &w11);
-            // ---- stage the 16x16 J window
-            __syncwarp();
+            // ---- make sure the 16x16 window lies inside the staged tile
+            if (!have_tile || inx < tx0 || inx + 16 > tx0 + kTileW || iny < ty0 || iny + 16 > ty0 + kTileH) {
+                tx0 = ((inx - 8 + 1024) & ~15) - 1024;           // floor to a multiple of 16 (also for negatives)
+                ty0 = iny - 8;
+                __syncwarp();
+                lk_stage_tile(J, tx0, ty0, S.tile, lane);
+                __syncwarp();
+                have_tile = true;
+            }
+            // ---- diff for the owned pixels, SIMD-slot pair sums / tail products
+            float v[8];              // half 0: eight SIMD slot values ; half 1: v[0..6] = d*Ix
+            float u[8];              // half 1: u[0..6] = d*Iy
+            int dterm_ok = 1;        // every tail term representable (|term| < 2^24)
+            int ti1[7], ti2[7];
             {
-                const int r = lane >> 1, c0 = (lane & 1) * 8;
-                const unsigned char* q = J.base + (ptrdiff_t)(iny + r) * J.pitch + (inx + c0);
+                int dd[8];
+                const unsigned char* r0 = S.tile + (iny - ty0 + oy) * kTileW + (inx - tx0 + ox0);
+                const unsigned char* r1 = r0 + kTileW;
+                int a = owner ? r0[0] : 0, c = owner ? r1[0] : 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) S.Jt[r * 16 + c0 + c] = __ldg(q + c);
-            }
-            __syncwarp();
-            for (int i = lane; i < 225; i += 32) {
-                const int y = i / 15, x = i - y * 15;
-                const unsigned char* s = &S.Jt[y * 16 + x];
-                const int jv = (s[0] * w00 + s[1] * w01 + s[16] * w10 + s[17] * w11 + (1 << 8)) >> 9;
-                S.diff[i] = (short)(jv - S.Iw[i]);
-            }
-            __syncwarp();
-            for (int i = lane; i < 225; i += 32) {
-                const int y = i / 15, x = i - y * 15;
-                if (x < 8) {
-                    // SIMD slot c = x: pixel pair (k, k+4), k = c>>1, gradient component c&1
-                    const int k = x >> 1;
-                    const short* gsel = (x & 1) ? S.Iyw : S.Ixw;
-                    const int v = (int)S.diff[y * 15 + k] * (int)gsel[y * 15 + k] +
-                                  (int)S.diff[y * 15 + k + 4] * (int)gsel[y * 15 + k + 4];
-                    S.prod[0][i] = (float)v;
+                for (int q = 0; q < 8; ++q) {
+                    dd[q] = 0;
+                    if (owner && q < onx) {
+                        const int b = r0[q + 1], e = r1[q + 1];
+                        dd[q] = ((a * w00 + b * w01 + c * w10 + e * w11 + (1 << 8)) >> 9) - Iw[q];
+                        a = b; c = e;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { v[q] = 0.f; u[q] = 0.f; }
+                if (half_ == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[2 * k] = (float)(dd[k] * Ixw[k] + dd[k + 4] * Ixw[k + 4]);
+                        v[2 * k + 1] = (float)(dd[k] * Iyw[k] + dd[k + 4] * Iyw[k + 4]);
+                    }
                 } else {
-                    const int dv = S.diff[i];
-                    S.prod[0][i] = (float)(dv * (int)S.Ixw[i]);
-                    S.prod[1][i] = (float)(dv * (int)S.Iyw[i]);
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) {
+                        ti1[t] = dd[t] * Ixw[t]; ti2[t] = dd[t] * Iyw[t];
+                        v[t] = (float)ti1[t]; u[t] = (float)ti2[t];
+                        if (abs(ti1[t]) >= (1 << 24) || abs(ti2[t]) >= (1 << 24)) dterm_ok = 0;
+                    }
+                }
+                if (half_ == 0) {
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) { ti1[t] = 0; ti2[t] = 0; }
                 }
             }
+            // ---- stage: lane 2y -> eight SIMD slot values [y*8 + c]; lane 2y+1 -> tails [120 + y*7 + t] (Ix in set 0, Iy in set 1)
             __syncwarp();
-            float acc = 0.f;
-            if (lane < 8) {
-                for (int y = 0; y < 15; ++y) acc = __fadd_rn(acc, S.prod[0][y * 15 + lane]);
-            } else if (lane < 10) {
-                const float* pr = S.prod[lane - 8];
-                for (int y = 0; y < 15; ++y)
+            if (owner) {
+                if (half_ == 0) {
+                    float4* d0 = reinterpret_cast<float4*>(&S.ch[oy * 8]);
+                    d0[0] = make_float4(v[0], v[1], v[2], v[3]); d0[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
 #pragma unroll
-                    for (int x = 8; x < 15; ++x) acc = __fadd_rn(acc, pr[y * 15 + x]);
+                    for (int t = 0; t < 7; ++t) { S.ch[120 + oy * 7 + t] = v[t]; S.ch[232 + 120 + oy * 7 + t] = u[t]; }
+                }
             }
-            // qb0 = lanes 0..3 ; qb1 = lanes 4..7
+            // ---- exact shortcut for the two scalar chains: every term and every partial sum (in OpenCV's order) below 2^24
+            bool exact;
+            int tot1 = 0, tot2 = 0;
+            {
+                int loc1 = 0, loc2 = 0;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) { loc1 += ti1[t]; loc2 += ti2[t]; }
+                int inc1 = loc1, inc2 = loc2;               // inclusive scan over lanes (even lanes contribute 0)
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int a1 = __shfl_up_sync(FULL, inc1, o), a2 = __shfl_up_sync(FULL, inc2, o);
+                    if (lane >= o) { inc1 += a1; inc2 += a2; }
+                }
+                int ok = dterm_ok;
+                int p1 = inc1 - loc1, p2 = inc2 - loc2;      // exclusive prefix of this lane
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    p1 += ti1[t]; p2 += ti2[t];
+                    if (abs(p1) >= (1 << 24) || abs(p2) >= (1 << 24)) ok = 0;
+                }
+                // with every |term| < 2^24 no prefix can leave int32 (105 * 2^24 < 2^31); otherwise ok is already 0
+                exact = __all_sync(FULL, ok) != 0;
+                tot1 = __shfl_sync(FULL, inc1, 31); tot2 = __shfl_sync(FULL, inc2, 31);
+            }
+            __syncwarp();
+            // ---- chain lanes: 0..7 SIMD lanes (15 terms each), 8 / 9 the scalar chains (105 terms, only when not exact)
+            float acc = 0.f;
+            {
+                const bool is_long = lane >= 8;
+                const float* pr = S.ch + (lane == 9 ? 232 : 0);
+                const int cnt = lane < 8 ? 15 : ((lane < 10 && !exact) ? 105 : 0);
+                const int n_it = exact ? 15 : 105;
+#pragma unroll 5
+                for (int i = 0; i < n_it; ++i) {
+                    const int off = is_long ? (120 + i) : (i * 8 + lane);
+                    if (i < cnt) acc = __fadd_rn(acc, pr[off]);
+                }
+            }
             const float q0 = __fadd_rn(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 4));
             const float q1 = __fadd_rn(__shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 5));
             const float q2 = __fadd_rn(__shfl_sync(FULL, acc, 2), __shfl_sync(FULL, acc, 6));
             const float q3 = __fadd_rn(__shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 7));
-            const float s1 = __shfl_sync(FULL, acc, 8), s2 = __shfl_sync(FULL, acc, 9);
+            float s1 = __shfl_sync(FULL, acc, 8), s2 = __shfl_sync(FULL, acc, 9);
+            if (exact) { s1 = (float)tot1; s2 = (float)tot2; }
             const float sb1 = __fadd_rn(s1, __fadd_rn(__fadd_rn(q0, 0.f), __fadd_rn(q2, 0.f)));
             const float sb2 = __fadd_rn(s2, __fadd_rn(__fadd_rn(q1, 0.f), __fadd_rn(q3, 0.f)));
             const float b1 = __fmul_rn(sb1, FLT_SCALE), b2 = __fmul_rn(sb2, FLT_SCALE);
@@ -425,7 +535,7 @@ struct RansacParams {
     int n;                  // features fed to LK
     int use_sampson;
     double thr, small_angle;
-    double Ric[9];
+    double R[9];            // Rci * prod(dR_k) * Ric, Ransac.cc:120-155 (host, libm sin/cos as the reference)
 };
 
 __device__ __forceinline__ void m3mul(const double* A, const double* B, double* C)
@@ -447,15 +557,16 @@ __device__ __forceinline__ double epi_dist(const double* E, double x1, double y1
     return (num * num) / (Fx10 * Fx10 + Fx11 * Fx11 + Fx20 * Fx20 + Fx21 * Fx21);
 }
 
-__global__ void __launch_bounds__(256) k_ransac(RansacParams P)
+__device__ __forceinline__ void ransac_body(const RansacParams& P)
 {
     __shared__ int sh[34];
     __shared__ double sR[9];
     __shared__ double sE[kRansacIters * 9];
     __shared__ int sCnt[kRansacIters];
     __shared__ int sWinner;
+    __shared__ unsigned s_used[128];
     const int tid = threadIdx.x;
-    TrackerBuffers& B = P.B;
+    const TrackerBuffers& B = P.B;
     TrackerScalars* sc = B.sc;
     const int n = P.n;
 
@@ -472,51 +583,27 @@ __global__ void __launch_bounds__(256) k_ransac(RansacParams P)
         base += tot;
     }
     const int nc = base;
-    __syncthreads();
+    // (diagnostics are zeroed before the barrier: lanes of warp 0 may not reconverge between divergent ifs)
     if (tid < kRansacIters) { sCnt[tid] = 0; B.n_inliers[tid] = 0; }
     if (tid < 32) B.two_points[tid] = 0;
+    __syncthreads();
     if (tid == 0) { sc->n_cand = nc; sc->winner = 0; sc->ransac_ran = 0; }
     // <=16 candidates: flags untouched (Ransac.cc:201-205).  17..31 candidates make the reference spin forever in
     // SetPointPair (Ransac.cc:57-82); defined here as "flags untouched", no rand() consumed.
     if (nc < 2 * kRansacIters) return;
 
     if (tid == 0) {
-        // SetPointPair (Ransac.cc:50-83): vIndices lives in B.up_off scratch? -> use dedicated scratch: B.cand + F
-        int* used = B.cand + B.F;            // second half of the scratch (F ints), 0 = free
-        for (int i = 0; i < nc; ++i) used[i] = 0;
+        // SetPointPair (Ransac.cc:50-83); "used" is a shared-memory bitmask (nc <= 4096)
+        for (int i = 0; i < 128; ++i) s_used[i] = 0u;
         for (int it = 0; it < kRansacIters; ++it) {
             int a, b;
-            do { a = glibc_rand_next(sc) % nc; } while (used[a]);
-            do { b = glibc_rand_next(sc) % nc; } while (used[b] || a == b);
+            do { a = glibc_rand_next(sc) % nc; } while ((s_used[a >> 5] >> (a & 31)) & 1u);
+            do { b = glibc_rand_next(sc) % nc; } while (((s_used[b >> 5] >> (b & 31)) & 1u) || a == b);
             B.two_points[2 * it] = B.cand[a];
             B.two_points[2 * it + 1] = B.cand[b];
-            used[a] = 1; used[b] = 1;
+            s_used[a >> 5] |= 1u << (a & 31); s_used[b >> 5] |= 1u << (b & 31);
         }
-        // GetRotation (Ransac.cc:120-155)
-        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        for (int k = 0; k < P.n_imu; ++k) {
-            const double* wm = P.imu + 8 * k;
-            const double dt = P.imu[8 * k + 7];
-            const double w1 = sqrt(wm[0] * wm[0] + wm[1] * wm[1] + wm[2] * wm[2]);
-            const double wdt = w1 * dt;
-            const double wx[9] = {0, -wm[2], wm[1], wm[2], 0, -wm[0], -wm[1], wm[0], 0};
-            double wx2[9], dR[9];
-            m3mul(wx, wx, wx2);
-            double c1, c2;
-            if (w1 < P.small_angle) { c1 = dt; c2 = .5 * (dt * dt); }
-            else { c1 = sin(wdt) / w1; c2 = (1 - cos(wdt)) / (w1 * w1); }
-            for (int i = 0; i < 9; ++i) {
-                const double I = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
-                dR[i] = I - c1 * wx[i] + c2 * wx2[i];
-            }
-            m3mul(dR, R, R);
-        }
-        double Rci[9], T[9];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Rci[3 * i + j] = P.Ric[3 * j + i];
-        m3mul(Rci, R, T);
-        m3mul(T, P.Ric, R);
-        for (int i = 0; i < 9; ++i) sR[i] = R[i];
+        for (int i = 0; i < 9; ++i) sR[i] = P.R[i];        // GetRotation: computed on the host (see tracker_enqueue)
         sc->ransac_ran = 1;
     }
     __syncthreads();
@@ -590,7 +677,7 @@ __device__ __forceinline__ void hist_push(const TrackerBuffers& B, int slot, flo
     B.hist_len[slot] = len + 1;
 }
 
-__global__ void __launch_bounds__(256) k_bookkeep(TrackerBuffers B, int n)
+__device__ __forceinline__ void bookkeep_body(const TrackerBuffers& B, int n)
 {
     __shared__ int sh[34];
     const int tid = threadIdx.x;
@@ -679,6 +766,15 @@ __global__ void __launch_bounds__(256) k_bookkeep(TrackerBuffers B, int n)
         sc->n_up = n_up;
         sc->n_meas = n_meas;
     }
+}
+
+// RANSAC followed by the bookkeeping in ONE single-CTA launch (Tracker.cc:264-342).
+__global__ void __launch_bounds__(256) k_ransac_bookkeep(RansacParams P)
+{
+    ransac_body(P);
+    __syncthreads();
+    __threadfence_block();
+    bookkeep_body(P.B, P.n);
 }
 
 // First image (Tracker.cc:215-233): slot i <- corner i, free list = n..F-1.
@@ -921,6 +1017,38 @@ extern "C" void rvio_tracker_destroy(rvio_tracker* t)
     delete t;
 }
 
+// Ransac::GetRotation (Ransac.cc:120-155): gyro integration over the frame's IMU samples, raw gyro (no bias removal),
+// R = Rci * (prod_k dR_k) * Ric.  Depends on host data only, so it is evaluated here with the host libm.
+static void host_gyro_rotation(const double* Ric, const double* imu, int n_imu, double small_angle, double* R)
+{
+    auto mul = [](const double* A, const double* B, double* C) {
+        double T[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+        for (int i = 0; i < 9; ++i) C[i] = T[i];
+    };
+    double acc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < n_imu; ++k) {
+        const double* wm = imu + 8 * k;
+        const double dt = imu[8 * k + 7];
+        const double w1 = sqrt(wm[0] * wm[0] + wm[1] * wm[1] + wm[2] * wm[2]);
+        const double wdt = w1 * dt;
+        const double wx[9] = {0, -wm[2], wm[1], wm[2], 0, -wm[0], -wm[1], wm[0], 0};
+        double wx2[9], dR[9];
+        mul(wx, wx, wx2);
+        double c1, c2;
+        if (w1 < small_angle) { c1 = dt; c2 = .5 * (dt * dt); }
+        else { c1 = sin(wdt) / w1; c2 = (1 - cos(wdt)) / (w1 * w1); }
+        for (int i = 0; i < 9; ++i) dR[i] = ((i == 0 || i == 4 || i == 8) ? 1.0 : 0.0) - c1 * wx[i] + c2 * wx2[i];
+        mul(dR, acc, acc);
+    }
+    double Rci[9], T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Rci[3 * i + j] = Ric[3 * j + i];
+    mul(Rci, acc, T);
+    mul(T, Ric, R);
+}
+
 static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu)
 {
     RVIO_ARG_CHECK(n_imu >= 0 && n_imu <= t->imu_cap);
@@ -930,7 +1058,7 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     const dim3 blk(256), grd(div_up(t->W, 256), t->H);
     // Tracker.cc:198-202
     if (t->cfg.enable_equalizer) {
-        RVIO_LAUNCH(k_clahe_lut, 25, 256, 0, s, gray_dev, gray_pitch, t->W, t->H, t->tw, t->th, t->clip, t->lut_scale, t->d_lut);
+        RVIO_LAUNCH(k_clahe_lut, 25, 1024, 0, s, gray_dev, gray_pitch, t->W, t->H, t->tw, t->th, t->clip, t->lut_scale, t->d_lut);
         RVIO_LAUNCH(k_clahe_apply, grd, blk, 0, s, gray_dev, gray_pitch, t->d_lut, t->inv_tw, t->inv_th, cur.lv[0]);
     } else {
         RVIO_LAUNCH(k_copy_level0, grd, blk, 0, s, gray_dev, gray_pitch, cur.lv[0]);
@@ -946,8 +1074,7 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     if (n == 0) { t->frame_open = false; RVIO_CUDA_TRY(cudaGetLastError()); return RVIO_NO_FEATURES; }
 
     if (n_imu > 0) {
-        memcpy(t->h_imu, imu, sizeof(double) * 8 * n_imu);
-        RVIO_CUDA_TRY(cudaMemcpyAsync(t->d_imu, t->h_imu, sizeof(double) * 8 * n_imu, cudaMemcpyHostToDevice, s));
+        (void)0;   // the IMU samples are consumed on the host (host_gyro_rotation below): nothing to upload
     }
     LKParams lp;
     lp.prev = prev; lp.cur = cur; lp.feats = t->B.feats; lp.n = n; lp.out = t->B.lk; lp.status = t->B.status;
@@ -957,9 +1084,8 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     RansacParams rp;
     rp.B = t->B; rp.imu = t->d_imu; rp.n_imu = n_imu; rp.n = n; rp.use_sampson = t->cfg.use_sampson;
     rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle;
-    memcpy(rp.Ric, t->Ric, sizeof rp.Ric);
-    RVIO_LAUNCH(k_ransac, 1, 256, 0, s, rp);
-    RVIO_LAUNCH(k_bookkeep, 1, 256, 0, s, t->B, n);
+    host_gyro_rotation(t->Ric, imu, n_imu, t->cfg.small_angle, rp.R);
+    RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, s, rp);
     RVIO_CUDA_TRY(cudaGetLastError());
     return RVIO_OK;
 }

@@ -141,6 +141,7 @@ __device__ __forceinline__ void d_solve3(const double* A_, const double* b_, dou
 // k_feature: one CTA (128 threads) per feature
 // ================================================================================================
 constexpr int kFeatThreads = 128;
+constexpr int kSolveSmallMaxClones = 14;     // n = 84: G + M + R fit in 227 KB of shared memory
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
@@ -523,14 +524,20 @@ struct GramParams {
     double* zpart;     // [groups][n]
 };
 
-__global__ void __launch_bounds__(256) k_gram(GramParams P)
+// One launch: grid (tiles, groups).  Each CTA accumulates its 32x32 tile of G (and, for diagonal tiles, its 32 entries
+// of z) over the features of its group into a partial buffer; the LAST CTA of a tile to finish (atomic ticket) sums the
+// partials in fixed group order (deterministic) into the reduce buffer; the last CTA of tile 0 also writes the counters.
+// reduce buffer layout: [G (n*n) | z (n) | counters (8)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_local
+__global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
     __shared__ double sA[8][33], sB[8][33];
+    __shared__ int s_last;
     const int ti = blockIdx.x / P.nt, tj = blockIdx.x % P.nt, g = blockIdx.y;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int n = P.n;
     const int i0 = ti * 32, j0 = tj * 32;
     double acc[2][2] = {{0, 0}, {0, 0}};
+    double zacc = 0;
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
     for (int f = g; f < n_feat; f += P.groups) {
         const int dof = P.f_dof[f];
@@ -538,6 +545,7 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P)
         const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
         if (i0 >= c1 || i0 + 32 <= c0 || j0 >= c1 || j0 + 32 <= c0) continue;     // block is zero on this tile
         const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+        const double* rv = P.rblk + (size_t)f * P.blk_rows;
         for (int a0 = 0; a0 < dof; a0 += 8) {
             {
                 const int r = threadIdx.x >> 5, c = threadIdx.x & 31;      // 8 rows x 32 cols
@@ -552,50 +560,46 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P)
                 const double b0v = sB[r][2 * tx], b1v = sB[r][2 * tx + 1];
                 acc[0][0] += a0v * b0v; acc[0][1] += a0v * b1v; acc[1][0] += a1v * b0v; acc[1][1] += a1v * b1v;
             }
+            if (ti == tj && threadIdx.x < 32) {
+                // z rows of this tile (a diagonal tile sees every feature that touches these columns)
+                for (int r = 0; r < 8; ++r) { const int a = a0 + r; if (a < dof) zacc += sA[r][threadIdx.x] * rv[a]; }
+            }
             __syncthreads();
         }
     }
-    double* G = P.Gpart + (size_t)g * n * n;
+    double* Gp = P.Gpart + (size_t)g * n * n;
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
             const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
-            if (i < n && j < n) G[(size_t)i * n + j] = acc[a][b];
+            if (i < n && j < n) Gp[(size_t)i * n + j] = acc[a][b];
         }
-}
-
-__global__ void __launch_bounds__(256) k_gram_z(GramParams P)
-{
-    const int g = blockIdx.x, n = P.n;
-    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        double acc = 0;
-        for (int f = g; f < n_feat; f += P.groups) {
-            const int dof = P.f_dof[f];
-            if (dof <= 0) continue;
-            const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
-            if (i < c0 || i >= c1) continue;
-            const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
-            const double* r = P.rblk + (size_t)f * P.blk_rows;
-            for (int a = 0; a < dof; ++a) acc += H[(size_t)a * n + i] * r[a];
+    if (ti == tj && threadIdx.x < 32 && i0 + threadIdx.x < n) P.zpart[(size_t)g * n + i0 + threadIdx.x] = zacc;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(&tickets[blockIdx.x], 1);
+        s_last = (t == P.groups - 1) ? 1 : 0;
+        if (s_last) tickets[blockIdx.x] = 0;           // self-reset for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
+            if (i < n && j < n) {
+                double sum = 0;
+                for (int gg = 0; gg < P.groups; ++gg) sum += P.Gpart[(size_t)gg * n * n + (size_t)i * n + j];
+                red[(size_t)i * n + j] = sum;
+            }
         }
-        P.zpart[(size_t)g * n + i] = acc;
+    if (ti == tj && threadIdx.x < 32 && i0 + threadIdx.x < n) {
+        double sum = 0;
+        for (int gg = 0; gg < P.groups; ++gg) sum += P.zpart[(size_t)gg * n + i0 + threadIdx.x];
+        red[(size_t)n * n + i0 + threadIdx.x] = sum;
     }
-}
-
-// reduce buffer layout: [G (n*n) | z (n) | counters (8)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_feat_local
-__global__ void __launch_bounds__(256) k_gram_reduce(GramParams P, const uint8_t* f_status, int rank, int world, double* red)
-{
-    const int n = P.n;
-    const int total = n * n + n;
-    for (int o = blockIdx.x * 256 + threadIdx.x; o < total; o += gridDim.x * 256) {
-        double acc = 0;
-        if (o < n * n) for (int g = 0; g < P.groups; ++g) acc += P.Gpart[(size_t)g * n * n + o];
-        else for (int g = 0; g < P.groups; ++g) acc += P.zpart[(size_t)g * n + (o - n * n)];
-        red[o] = acc;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 64) {
         int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
-        const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
         for (int f = rank; f < n_feat; f += world) {
             loc++;
             const int st = f_status[f];
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(256) k_gram_reduce(GramParams P, const uint8_t
             else if (st == 2) r2++;
             else r3++;
         }
-        double* c = red + total;
+        double* c = red + (size_t)n * n + n;
         c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
     }
 }
@@ -783,6 +787,158 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeParams P)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_solve_small: the whole EKF stage (Updater.cc:540-619) in ONE CTA for small windows (n = 6N <= 84), operands in
+// shared memory:  M = G Pcc + s^2 I ;  R = [z | G P[c,:]] ;  Gauss-Jordan ;  dx = P[:,c] y ;  P+ = P - P[:,c] Y ;
+// state correction + symmetrisation.  Replaces 4 k_dgemm + k_gauss_jordan + k_finalize launches.
+// ------------------------------------------------------------------------------------------------
+struct SolveSmallParams {
+    const double* red;        // [G | z | counters]
+    const double* x; const double* P; int xdim, N, d;
+    double sig2;
+    double* x_out; double* P_out; int* singular;
+};
+
+__global__ void __launch_bounds__(1024) k_solve_small(SolveSmallParams Q)
+{
+    extern __shared__ __align__(16) double ssm[];
+    __shared__ int s_piv;
+    __shared__ double s_pinv;
+    __shared__ double s_dx[24 + 6 * 14 + 4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    const double* gate = Q.red + (size_t)n * n + n;
+    if (!(gate[0] > 2.0)) {                      // Updater.cc:621-627
+        for (int o = tid; o < d * d; o += 1024) Q.P_out[o] = Q.P[o];
+        for (int o = tid; o < Q.xdim; o += 1024) Q.x_out[o] = Q.x[o];
+        return;
+    }
+    double* G = ssm;                  // n x n (row-major; symmetric)
+    double* M = G + n * n;            // n x n
+    double* R = M + n * n;            // n x m
+    const double* P = Q.P;
+    for (int o = tid; o < n * n; o += 1024) G[o] = Q.red[o];
+    __syncthreads();
+    // P is symmetric by construction (PreIntegrator.cc:192, System.cc:300,361): P(a,b) is read as P[a d + b], i.e. with
+    // the fastest-varying index on consecutive threads (coalesced).
+    // W = G * P[c,:]  (n x d, 4x1 register tiles):  R[:,1+col] = W[:,col] ;  M = W[:,24:] + s^2 I ;  R[:,0] = z
+    {
+        const int nib = (n + 3) / 4;
+        for (int item = tid; item < nib * d; item += 1024) {
+            const int ib = item / d, col = item - ib * d;
+            const int i0 = 4 * ib;
+            const double* pc = P + (size_t)24 * d + col;
+            const double* g0 = G + (size_t)i0 * n;
+            const int r1 = (i0 + 1 < n) ? n : 0, r2 = (i0 + 2 < n) ? 2 * n : 0, r3 = (i0 + 3 < n) ? 3 * n : 0;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            for (int k = 0; k < n; ++k) {
+                const double pv = pc[(size_t)k * d];
+                a0 += g0[k] * pv; a1 += g0[r1 + k] * pv; a2 += g0[r2 + k] * pv; a3 += g0[r3 + k] * pv;
+            }
+            const double av[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q;
+                if (i < n) {
+                    R[i * m + 1 + col] = av[q];
+                    if (col >= 24) M[i * n + (col - 24)] = av[q] + ((i == col - 24) ? Q.sig2 : 0.0);
+                }
+            }
+        }
+        for (int i = tid; i < n; i += 1024) R[i * m] = Q.red[(size_t)n * n + i];
+    }
+    __syncthreads();
+    // Gauss-Jordan with partial pivoting on [M | R]; thread (c, rg) owns column c of [M | R] for rows rg, rg+TR, ...
+    {
+        const int ncols = n + m;
+        const int TC = ((ncols + 31) / 32) * 32;
+        const int TR = 1024 / TC;
+        const int c = tid % TC, rg = tid / TC;
+        const bool active = rg < TR && c < ncols;
+        double* colbase = (c < n) ? &M[c] : &R[(c < ncols ? c : n) - n];
+        const int stride = (c < n) ? n : m;
+        for (int k = 0; k < n; ++k) {
+            if (warp == 0) {
+                double best = -1.0; int bi = k;
+                for (int i = k + lane; i < n; i += 32) {
+                    const double v = fabs(M[i * n + k]);
+                    if (v > best) { best = v; bi = i; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) {
+                    s_piv = bi;
+                    if (!(best > 0)) { *Q.singular = 1; s_pinv = 0.0; }
+                    else s_pinv = 1.0 / M[bi * n + k];
+                }
+            }
+            __syncthreads();
+            const int p = s_piv;
+            const double pinv = s_pinv;
+            const bool mine = active && (c >= n || c >= k);
+            if (mine && rg == 0) {
+                const double vk = colbase[k * stride], vp = colbase[p * stride];
+                colbase[p * stride] = vk;
+                colbase[k * stride] = vp * pinv;
+            }
+            __syncthreads();
+            if (active && (c >= n || c > k)) {
+                const double rowk = colbase[k * stride];
+                for (int i = rg; i < n; i += TR) {
+                    if (i == k) continue;
+                    const double fct = M[i * n + k];           // column k is not modified during this elimination
+                    colbase[i * stride] -= fct * rowk;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // dx = P[:,c] y_z ; P(i, 24+k) = P[(24+k) d + i]
+    for (int i = tid; i < d; i += 1024) {
+        double acc = 0;
+        for (int k = 0; k < n; ++k) acc += P[(size_t)(24 + k) * d + i] * R[k * m];
+        s_dx[i] = acc;
+    }
+    // P_out = sym( P - P[:,c] Y_W )
+    for (int o = tid; o < d * d; o += 1024) {
+        const int i = o % d, j = o / d;
+        if (i > j) continue;
+        double a = 0, b = 0;
+        for (int k = 0; k < n; ++k) {
+            const double pik = P[(size_t)(24 + k) * d + i], pjk = P[(size_t)(24 + k) * d + j];
+            a += pik * R[k * m + 1 + j];
+            b += pjk * R[k * m + 1 + i];
+        }
+        const double pij = P[(size_t)j * d + i] - a, pji = P[(size_t)i * d + j] - b;
+        const double v = .5 * (pij + pji);
+        Q.P_out[(size_t)j * d + i] = v;
+        Q.P_out[(size_t)i * d + j] = v;
+    }
+    __syncthreads();
+    // state correction, Updater.cc:546-613
+    const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
+    for (int b = tid; b < 2 + N; b += 1024) {
+        int xq, eq;
+        if (b == 0) { xq = 0; eq = 0; }
+        else if (b == 1) { xq = 10; eq = 9; }
+        else { xq = 26 + 7 * (b - 2); eq = 24 + 6 * (b - 2); }
+        d_apply_dq(dx + eq, x + xq, xo + xq);
+        if (b >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
+    }
+    if (tid == 64) {
+        double g[3];
+        for (int k = 0; k < 3; ++k) xo[4 + k] = dx[3 + k] + x[4 + k];
+        for (int k = 0; k < 3; ++k) g[k] = dx[6 + k] + x[7 + k];
+        const double nn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        for (int k = 0; k < 3; ++k) xo[7 + k] = g[k] / nn;
+        for (int k = 0; k < 12; ++k) xo[14 + k] = dx[12 + k] + x[14 + k];
+    }
+}
+
 }  // namespace rvio
 
 // ================================================================================================
@@ -802,7 +958,7 @@ struct rvio_updater {
     uint8_t* d_types; int32_t* d_off; float2* d_xy;
     uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma; int32_t *d_fdof, *d_fc0, *d_fwc;
     double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2;
-    int* d_sing;
+    int* d_sing; int* d_tickets;
     int groups_cap;
     // pinned
     double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing;
@@ -883,6 +1039,11 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     if (u->lay.total_bytes > 200 * 1024) { set_error("rvio_updater_create", "max_track_len too large for shared memory"); return RVIO_ERR_CAPACITY; }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
+    {
+        const int nn = 6 * (u->Nmax < kSolveSmallMaxClones ? u->Nmax : kSolveSmallMaxClones);
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(double) * ((size_t)2 * nn * nn + (size_t)nn * (24 + nn + 1)))));
+    }
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
     u->groups_cap = 32;
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
@@ -891,7 +1052,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1);
     A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
-    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
+    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1); A(u->d_tickets, 64);
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
     HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4);
@@ -946,9 +1107,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         gp.n_feat = n_feat_cap; gp.n_feat_dev = n_feat_dev; gp.n = n; gp.blk_rows = u->lay.Mc;
         gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
         gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
-        RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp);
-        RVIO_LAUNCH(k_gram_z, gp.groups, 256, 0, s, gp);
-        RVIO_LAUNCH(k_gram_reduce, div_up(n * n + n, 256), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red);
+        RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
     } else {
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     }
@@ -964,6 +1123,16 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
     if (n == 0) {
         RVIO_CUDA_TRY(cudaMemcpyAsync(x_out_dev, x_dev, sizeof(double) * xdim, cudaMemcpyDeviceToDevice, s));
         RVIO_CUDA_TRY(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
+        return RVIO_OK;
+    }
+    if (N <= kSolveSmallMaxClones) {
+        SolveSmallParams sp;
+        sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
+        sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
+        RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+        const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * (d + 1));
+        RVIO_LAUNCH(k_solve_small, 1, 1024, smem, s, sp);
+        RVIO_CUDA_TRY(cudaGetLastError());
         return RVIO_OK;
     }
     const double* G = u->d_red;
@@ -1021,6 +1190,13 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
     }
     RVIO_CUDA_TRY(cudaGetLastError());
     return RVIO_OK;
+}
+
+// Solve against a state other than the one the normal terms were formed on (the propagated x, P of the fused path).
+int updater_enqueue_solve_on(rvio_updater* u, cudaStream_t s, const double* x_dev, const double* P_dev, double* x_out_dev, double* P_out_dev)
+{
+    u->cur_x_dev = x_dev; u->cur_P_dev = P_dev;
+    return updater_enqueue_solve(u, s, x_out_dev, P_out_dev);
 }
 
 const double* updater_counters_dev(const rvio_updater* u)

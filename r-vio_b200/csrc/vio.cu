@@ -26,6 +26,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
                                  const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev,
                                  int n_feat_cap, const int* n_feat_dev, int rank, int world);
 int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, double* P_out_dev);
+int updater_enqueue_solve_on(rvio_updater* u, cudaStream_t s, const double* x_dev, const double* P_dev, double* x_out_dev, double* P_out_dev);
 const double* updater_counters_dev(const rvio_updater* u);
 }  // namespace rvio
 
@@ -36,7 +37,10 @@ struct rvio_vio {
     int device;
     rvio_tracker* trk;
     rvio_updater* upd;
-    cudaStream_t stream;
+    cudaStream_t stream;          // main: tracker -> per-feature -> normal terms -> solve -> augment
+    cudaStream_t side;            // side: propagate, FindNewer+refill (off the critical path)
+    cudaEvent_t ev_frame_in, ev_prop_done, ev_bookkeep_done, ev_side_done;
+    bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage events on the main stream
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
@@ -193,6 +197,13 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     rc = rvio_updater_create(&cfg->updater, device, &v->upd);
     if (rc != RVIO_OK) { rvio_tracker_destroy(v->trk); delete v; return rc; }
     v->stream = tracker_stream(v->trk);
+    RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&v->side, cudaStreamNonBlocking));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_frame_in, cudaEventDisableTiming));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_prop_done, cudaEventDisableTiming));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_bookkeep_done, cudaEventDisableTiming));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_side_done, cudaEventDisableTiming));
+    v->timeline = false;
+    for (int k = 0; k < 8; ++k) { RVIO_CUDA_TRY(cudaEventCreate(&v->tl[k])); v->tl_ms[k] = 0.f; }
     v->window = cfg->tracker.max_track_len - 1;             // System.cc:71-72
     v->min_clones = cfg->tracker.min_track_len - 1;         // System.cc:74-75
     v->F = cfg->tracker.n_features; v->Fu = (v->F + 1) / 2;
@@ -234,6 +245,9 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     if (!v) return;
     cudaSetDevice(v->device);
     cudaStreamSynchronize(v->stream);
+    cudaStreamSynchronize(v->side);
+    cudaEventDestroy(v->ev_frame_in); cudaEventDestroy(v->ev_prop_done); cudaEventDestroy(v->ev_bookkeep_done); cudaEventDestroy(v->ev_side_done);
+    cudaStreamDestroy(v->side);
     for (void* p : v->allocs) cudaFree(p);
     for (void* p : v->hallocs) cudaFreeHost(p);
     rvio_updater_destroy(v->upd);
@@ -267,11 +281,33 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     v->n_img_after_init++;
     if (n_cand > v->F) n_cand = v->F;
 
-    // ---- visual tracking (System.cc:258)
+    const int N = v->n_clones;
+    const int xdim = xdim_of(N), d = d_of(N);
+    cudaStream_t side = v->side;
+    // ---- propagation (System.cc:263) on the side stream: it only needs last frame's x, P and the IMU samples, so it
+    //      overlaps the whole tracker; the solve waits for it.
+    const int xi0 = v->xi, pi0 = v->pi;             // prior (pre-propagation) buffers: also what k_feature reads
+    memcpy(v->h_imu, imu, sizeof(double) * 8 * n_imu);
+    RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_imu, v->h_imu, sizeof(double) * 8 * n_imu, cudaMemcpyHostToDevice, side));
+    {
+        PropagateParams pp;
+        pp.x_in = v->d_x[xi0]; pp.P_in = v->d_P[pi0]; pp.xdim = xdim; pp.d = d;
+        pp.imu = v->d_imu; pp.n_imu = n_imu; pp.x_out = v->d_x[1 - xi0]; pp.P_out = v->d_P[1 - pi0];
+        pp.c.gravity = v->cfg.gravity; pp.c.small_angle = v->cfg.tracker.small_angle;
+        pp.c.sigma_g = v->cfg.sigma_g; pp.c.sigma_wg = v->cfg.sigma_wg; pp.c.sigma_a = v->cfg.sigma_a; pp.c.sigma_wa = v->cfg.sigma_wa;
+        int r2 = launch_propagate(side, pp);
+        if (r2 != RVIO_OK) return r2;
+        RVIO_CUDA_TRY(cudaEventRecord(v->ev_prop_done, side));
+        v->xi = 1 - xi0; v->pi = 1 - pi0;
+    }
+
+    // ---- visual tracking (System.cc:258) on the main stream
+    if (v->timeline) cudaEventRecord(v->tl[0], s);
     int rc;
     if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
     else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
     if (rc < 0) return rc;
+    if (v->timeline) cudaEventRecord(v->tl[1], s);          // tracker kernels enqueued (upload .. bookkeeping)
     const float2* cand_dev = nullptr;
     if (n_cand > 0) {
         if (cand_dev_in) cand_dev = reinterpret_cast<const float2*>(cand_dev_in);
@@ -281,51 +317,48 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
             cand_dev = v->d_cand;
         }
     }
-    bool frame_committable = false;
+    bool frame_committable = false, side_refill = false;
     if (rc == RVIO_FIRST_IMAGE) {
         if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand); if (r2 != RVIO_OK) return r2; }
         frame_committable = true;
     } else if (rc == RVIO_OK) {
         if (n_cand > 0) {
+            // FindNewer + refill only prepare the NEXT frame's feature set: run them beside the update
+            RVIO_CUDA_TRY(cudaEventRecord(v->ev_bookkeep_done, s));
+            RVIO_CUDA_TRY(cudaStreamWaitEvent(side, v->ev_bookkeep_done, 0));
             FindNewerParams fp;
             fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = n_cand; fp.raw = cand_filtered ? 1 : 0;
             fp.W = v->cfg.tracker.width; fp.H = v->cfg.tracker.height; fp.gc = v->gc; fp.gr = v->gr;
             fp.offx = v->offx; fp.offy = v->offy; fp.max_per_block = v->max_per_block;
             fp.bx = (float)v->cfg.block_x; fp.by = (float)v->cfg.block_y; fp.min_dist = v->cfg.min_dist;
             fp.cam = *tracker_cam(v->trk);
-            int r2 = launch_find_newer_refill(s, fp);
+            int r2 = launch_find_newer_refill(side, fp);
             if (r2 != RVIO_OK) return r2;
+            side_refill = true;
         }
         frame_committable = true;
     }
 
-    // ---- propagation (System.cc:263)
-    const int N = v->n_clones;
-    const int xdim = xdim_of(N), d = d_of(N);
-    memcpy(v->h_imu, imu, sizeof(double) * 8 * n_imu);
-    RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_imu, v->h_imu, sizeof(double) * 8 * n_imu, cudaMemcpyHostToDevice, s));
-    {
-        PropagateParams pp;
-        pp.x_in = v->d_x[v->xi]; pp.P_in = v->d_P[v->pi]; pp.xdim = xdim; pp.d = d;
-        pp.imu = v->d_imu; pp.n_imu = n_imu; pp.x_out = v->d_x[1 - v->xi]; pp.P_out = v->d_P[1 - v->pi];
-        pp.c.gravity = v->cfg.gravity; pp.c.small_angle = v->cfg.tracker.small_angle;
-        pp.c.sigma_g = v->cfg.sigma_g; pp.c.sigma_wg = v->cfg.sigma_wg; pp.c.sigma_a = v->cfg.sigma_a; pp.c.sigma_wa = v->cfg.sigma_wa;
-        int r2 = launch_propagate(s, pp);
-        if (r2 != RVIO_OK) return r2;
-        v->xi = 1 - v->xi; v->pi = 1 - v->pi;
-    }
-    // ---- update (System.cc:266-277)
+    // ---- update (System.cc:266-277).  The per-feature kernel and the normal terms read only the clone states and the
+    //      clone-clone covariance block, which propagation leaves untouched (PreIntegrator.cc:186-192 rewrites the
+    //      IMU block and the cross terms only): they run on the prior buffers, concurrently with k_propagate.
     bool ran_update = false;
     if (N > v->min_clones) {
         const TrackerBuffers* B = tracker_buffers(v->trk);
-        int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[v->xi], xdim, v->d_P[v->pi], d, B->up_types, B->up_off, B->up_xy,
+        int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[xi0], xdim, v->d_P[pi0], d, B->up_types, B->up_off, B->up_xy,
                                               v->Fu, &B->sc->n_up, 0, 1);
         if (r2 != RVIO_OK) return r2;
-        r2 = updater_enqueue_solve(v->upd, s, v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
+        if (v->timeline) cudaEventRecord(v->tl[2], s);      // per-feature + normal terms done
+        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
+        if (v->timeline) cudaEventRecord(v->tl[3], s);      // (waited for propagation)
+        r2 = updater_enqueue_solve_on(v->upd, s, v->d_x[v->xi], v->d_P[v->pi], v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
         if (r2 != RVIO_OK) return r2;
         v->xi = 1 - v->xi; v->pi = 1 - v->pi;
         ran_update = true;
+        if (v->timeline) cudaEventRecord(v->tl[4], s);      // solve done
         RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
     }
     // ---- augmentation + composition (System.cc:280-365)
     {
@@ -337,9 +370,19 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         v->pi = 1 - v->pi;
         if (ap.do_augment && N < v->window) v->n_clones = N + 1;
     }
+    if (v->timeline) cudaEventRecord(v->tl[5], s);          // augmentation + composition done
+    if (side_refill) {
+        RVIO_CUDA_TRY(cudaEventRecord(v->ev_side_done, side));
+        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_side_done, 0));
+    }
     RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
     int r3 = tracker_sync(v->trk);                          // publishes tracker counters + synchronises the stream
     if (r3 != RVIO_OK) return r3;
+    if (v->timeline) {
+        cudaEventRecord(v->tl[6], s);
+        cudaEventSynchronize(v->tl[6]);
+        for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, v->tl[k], v->tl[k + 1]) == cudaSuccess) v->tl_ms[k] = ms; else v->tl_ms[k] = -1.f; }
+    }
     if (frame_committable) { r3 = rvio_tracker_commit(v->trk); if (r3 != RVIO_OK) return r3; }
     memcpy(pose_out, v->h_pose, sizeof(double) * 7);
     *pose_valid = 1;
@@ -395,3 +438,13 @@ extern "C" int rvio_vio_get_update_info(rvio_vio* v, rvio_update_info* info)
 
 extern "C" rvio_tracker* rvio_vio_tracker(rvio_vio* v) { return v ? v->trk : nullptr; }
 extern "C" rvio_updater* rvio_vio_updater(rvio_vio* v) { return v ? v->upd : nullptr; }
+
+// Debug: per-stage CUDA-event times of the main stream for the last step (ms): [tracker, per-feature+normal terms,
+// wait for propagation, solve, augment+compose, tail].  enable = 1 switches the instrumentation on.
+extern "C" int rvio_vio_timeline(rvio_vio* v, int enable, float* ms6)
+{
+    RVIO_ARG_CHECK(v);
+    v->timeline = enable != 0;
+    if (ms6) for (int k = 0; k < 6; ++k) ms6[k] = v->tl_ms[k];
+    return RVIO_OK;
+}
