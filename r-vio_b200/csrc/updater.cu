@@ -140,8 +140,9 @@ __device__ __forceinline__ void d_solve3(const double* A_, const double* b_, dou
 // ================================================================================================
 // k_feature: one CTA (128 threads) per feature
 // ================================================================================================
-constexpr int kFeatThreads = 128;
-constexpr int kSolveSmallMaxClones = 14;     // n = 84: G + M + R fit in 227 KB of shared memory
+constexpr int kFeatThreads = 256;
+constexpr int kSolveSmallMaxClones = 13;     // n = 84: M + R + P[c,:] (+ pivot row / column) fit in 227 KB of shared memory
+constexpr int kGJRows = 17;                  // rows per thread in the register-resident Gauss-Jordan (n = 84: 193 columns -> 5 row groups)
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
@@ -482,23 +483,27 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        // y = L^-1 r ; gamma = y^T y
+    if (warp == 0) {
+        // y = L^-1 r ; gamma = y^T y   (forward substitution: lanes split each dot product)
         double gamma = 0;
         for (int i = 0; i < dof; ++i) {
-            double s = rn[i];
-            for (int k = 0; k < i; ++k) s -= S[i * dof + k] * vv[k];
-            const double y = s / S[i * dof + i];
-            vv[i] = y;
+            double part = 0;
+            for (int k = lane; k < i; k += 32) part += S[i * dof + k] * vv[k];
+            part = warp_sum(part);
+            const double y = (rn[i] - part) / S[i * dof + i];
+            if (lane == 0) vv[i] = y;
+            __syncwarp();
             gamma += y * y;
         }
-        gamma = fabs(gamma);
-        P.f_gamma[f] = gamma;
-        const bool ok = gamma < P.chi2[dof - 1];
-        s_flag[2] = ok ? 1 : 0;
-        if (!ok) P.f_status[f] = 3;
-        P.f_dof[f] = ok ? dof : 0;
-        P.f_c0[f] = c0; P.f_wc[f] = wc;
+        if (lane == 0) {
+            gamma = fabs(gamma);
+            P.f_gamma[f] = gamma;
+            const bool ok = gamma < P.chi2[dof - 1];
+            s_flag[2] = ok ? 1 : 0;
+            if (!ok) P.f_status[f] = 3;
+            P.f_dof[f] = ok ? dof : 0;
+            P.f_c0[f] = c0; P.f_wc[f] = wc;
+        }
     }
     __syncthreads();
     if (!s_flag[2]) return;
@@ -589,6 +594,7 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
             const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
             if (i < n && j < n) {
                 double sum = 0;
+#pragma unroll 8
                 for (int gg = 0; gg < P.groups; ++gg) sum += P.Gpart[(size_t)gg * n * n + (size_t)i * n + j];
                 red[(size_t)i * n + j] = sum;
             }
@@ -800,40 +806,41 @@ struct SolveSmallParams {
     double* x_out; double* P_out; int* singular;
 };
 
-__global__ void __launch_bounds__(1024) k_solve_small(SolveSmallParams Q)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_solve_small(SolveSmallParams Q)
 {
     extern __shared__ __align__(16) double ssm[];
-    __shared__ int s_piv;
-    __shared__ double s_pinv;
     __shared__ double s_dx[24 + 6 * 14 + 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) {                      // Updater.cc:621-627
-        for (int o = tid; o < d * d; o += 1024) Q.P_out[o] = Q.P[o];
-        for (int o = tid; o < Q.xdim; o += 1024) Q.x_out[o] = Q.x[o];
+        for (int o = tid; o < d * d; o += THREADS) Q.P_out[o] = Q.P[o];
+        for (int o = tid; o < Q.xdim; o += THREADS) Q.x_out[o] = Q.x[o];
         return;
     }
-    double* G = ssm;                  // n x n (row-major; symmetric)
-    double* M = G + n * n;            // n x n
+    double* M = ssm;                  // n x n
     double* R = M + n * n;            // n x m
+    double* Pc = R + n * m;           // n x d : rows 24.. of P (== P[:,c]^T, P symmetric)
     const double* P = Q.P;
-    for (int o = tid; o < n * n; o += 1024) G[o] = Q.red[o];
-    __syncthreads();
+    const double* G = Q.red;          // n x n row-major (global, L1-resident; reads are warp-uniform)
     // P is symmetric by construction (PreIntegrator.cc:192, System.cc:300,361): P(a,b) is read as P[a d + b], i.e. with
     // the fastest-varying index on consecutive threads (coalesced).
+    for (int o = tid; o < n * d; o += THREADS) Pc[o] = P[(size_t)24 * d + o];
+    __syncthreads();
     // W = G * P[c,:]  (n x d, 4x1 register tiles):  R[:,1+col] = W[:,col] ;  M = W[:,24:] + s^2 I ;  R[:,0] = z
     {
         const int nib = (n + 3) / 4;
-        for (int item = tid; item < nib * d; item += 1024) {
+        for (int item = tid; item < nib * d; item += THREADS) {
             const int ib = item / d, col = item - ib * d;
             const int i0 = 4 * ib;
-            const double* pc = P + (size_t)24 * d + col;
+            const double* pc = Pc + col;
             const double* g0 = G + (size_t)i0 * n;
             const int r1 = (i0 + 1 < n) ? n : 0, r2 = (i0 + 2 < n) ? 2 * n : 0, r3 = (i0 + 3 < n) ? 3 * n : 0;
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
             for (int k = 0; k < n; ++k) {
-                const double pv = pc[(size_t)k * d];
+                const double pv = pc[k * d];
                 a0 += g0[k] * pv; a1 += g0[r1 + k] * pv; a2 += g0[r2 + k] * pv; a3 += g0[r3 + k] * pv;
             }
             const double av[4] = {a0, a1, a2, a3};
@@ -846,72 +853,125 @@ __global__ void __launch_bounds__(1024) k_solve_small(SolveSmallParams Q)
                 }
             }
         }
-        for (int i = tid; i < n; i += 1024) R[i * m] = Q.red[(size_t)n * n + i];
+        for (int i = tid; i < n; i += THREADS) R[i * m] = Q.red[(size_t)n * n + i];
     }
     __syncthreads();
-    // Gauss-Jordan with partial pivoting on [M | R]; thread (c, rg) owns column c of [M | R] for rows rg, rg+TR, ...
+    // Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (rb, cb) owns the 4x4 tile
+    // rows 4rb.., columns 4cb.. of [M | R].  Per step: the owners of pivot row p publish it, the owners of column k publish
+    // the multipliers, everybody applies the rank-1 update to its tile (16 DFMA for 8 shared loads); the pivot of step
+    // k+1 (largest |.| of column k+1 over rows not yet used) is found during the update with a packed atomicMax.
     {
+        __shared__ unsigned long long s_key[2];
+        __shared__ unsigned char s_used[96];
+        __shared__ short s_prow[96];                       // pivot row of step k
+        __shared__ short s_var[96];                        // inverse permutation
+        __shared__ double s_pinv;
+        double* s_rowk = Pc + n * d;                       // (ncols + 4) doubles: pivot row
+        double* s_colk = s_rowk + (n + m + 4);             // (n + 4) doubles: column k multipliers
         const int ncols = n + m;
-        const int TC = ((ncols + 31) / 32) * 32;
-        const int TR = 1024 / TC;
-        const int c = tid % TC, rg = tid / TC;
-        const bool active = rg < TR && c < ncols;
-        double* colbase = (c < n) ? &M[c] : &R[(c < ncols ? c : n) - n];
-        const int stride = (c < n) ? n : m;
+        const int ncb = (ncols + 3) / 4, nrb = (n + 3) / 4;
+        const int cb = tid % ncb, rb = tid / ncb;
+        const bool active = rb < nrb;
+        const int r0 = 4 * rb, c0 = 4 * cb;
+        double reg[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = r0 + r, c = c0 + j;
+                reg[r][j] = (active && i < n && c < ncols) ? ((c < n) ? M[i * n + c] : R[i * m + (c - n)]) : 0.0;
+            }
+        if (tid < 96) s_used[tid] = 0;
+        if (tid == 0) { s_key[0] = 0ull; s_key[1] = 0ull; }
+        __syncthreads();
+        if (active && cb == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r0 + r < n) atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(fabs(reg[r][0])) & ~1023ull) | (unsigned long long)(1023 - (r0 + r)));
+        }
+        __syncthreads();
+        bool singular = false;
         for (int k = 0; k < n; ++k) {
-            if (warp == 0) {
-                double best = -1.0; int bi = k;
-                for (int i = k + lane; i < n; i += 32) {
-                    const double v = fabs(M[i * n + k]);
-                    if (v > best) { best = v; bi = i; }
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_down_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                if (lane == 0) {
-                    s_piv = bi;
-                    if (!(best > 0)) { *Q.singular = 1; s_pinv = 0.0; }
-                    else s_pinv = 1.0 / M[bi * n + k];
-                }
+            const unsigned long long key = s_key[k & 1];
+            const int p = 1023 - (int)(key & 1023ull);
+            if ((key >> 10) == 0ull) { singular = true; break; }                   // uniform
+            const int pr = p & 3, kc = k & 3;
+            if (active && rb == (p >> 2)) {                                        // publish pivot row (unscaled)
+                double v0 = reg[0][0], v1 = reg[0][1], v2 = reg[0][2], v3 = reg[0][3];
+                if (pr == 1) { v0 = reg[1][0]; v1 = reg[1][1]; v2 = reg[1][2]; v3 = reg[1][3]; }
+                if (pr == 2) { v0 = reg[2][0]; v1 = reg[2][1]; v2 = reg[2][2]; v3 = reg[2][3]; }
+                if (pr == 3) { v0 = reg[3][0]; v1 = reg[3][1]; v2 = reg[3][2]; v3 = reg[3][3]; }
+                s_rowk[c0] = v0; s_rowk[c0 + 1] = v1; s_rowk[c0 + 2] = v2; s_rowk[c0 + 3] = v3;
+                if (cb == (k >> 2)) s_pinv = 1.0 / (kc == 0 ? v0 : kc == 1 ? v1 : kc == 2 ? v2 : v3);
             }
-            __syncthreads();
-            const int p = s_piv;
-            const double pinv = s_pinv;
-            const bool mine = active && (c >= n || c >= k);
-            if (mine && rg == 0) {
-                const double vk = colbase[k * stride], vp = colbase[p * stride];
-                colbase[p * stride] = vk;
-                colbase[k * stride] = vp * pinv;
+            if (active && cb == (k >> 2)) {                                        // publish column k
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    s_colk[r0 + r] = kc == 0 ? reg[r][0] : kc == 1 ? reg[r][1] : kc == 2 ? reg[r][2] : reg[r][3];
             }
+            if (tid == 0) { s_key[(k + 1) & 1] = 0ull; s_used[p] = 1; s_prow[k] = (short)p; }
             __syncthreads();
-            if (active && (c >= n || c > k)) {
-                const double rowk = colbase[k * stride];
-                for (int i = rg; i < n; i += TR) {
-                    if (i == k) continue;
-                    const double fct = M[i * n + k];           // column k is not modified during this elimination
-                    colbase[i * stride] -= fct * rowk;
+            if (active) {
+                const double pinv = s_pinv;
+                double rk[4], f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rk[j] = s_rowk[c0 + j] * pinv;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) f[r] = (r0 + r == p) ? 0.0 : s_colk[r0 + r];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) reg[r][j] -= f[r] * rk[j];
+                if (rb == (p >> 2)) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (r == pr) { reg[r][0] = rk[0]; reg[r][1] = rk[1]; reg[r][2] = rk[2]; reg[r][3] = rk[3]; }
+                }
+                if (cb == ((k + 1) >> 2) && k + 1 < n) {
+                    const int nc = (k + 1) & 3;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = r0 + r;
+                        if (i < n && !s_used[i]) {
+                            const double v = nc == 0 ? reg[r][0] : nc == 1 ? reg[r][1] : nc == 2 ? reg[r][2] : reg[r][3];
+                            atomicMax(&s_key[(k + 1) & 1], ((unsigned long long)__double_as_longlong(fabs(v)) & ~1023ull) | (unsigned long long)(1023 - i));
+                        }
+                    }
                 }
             }
             __syncthreads();
         }
+        if (singular && tid == 0) *Q.singular = 1;
+        // solution row of variable k is pivot row s_prow[k]: scatter Y = R[prow[k]] back into shared R (n x m)
+        __syncthreads();
+        if (tid < n) s_var[s_prow[tid]] = (short)tid;
+        __syncthreads();
+        if (active && !singular) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = r0 + r, c = c0 + j;
+                    if (i < n && c >= n && c < ncols) R[(int)s_var[i] * m + (c - n)] = reg[r][j];
+                }
+        }
+        __syncthreads();
     }
-    // dx = P[:,c] y_z ; P(i, 24+k) = P[(24+k) d + i]
-    for (int i = tid; i < d; i += 1024) {
+    // dx = P[:,c] y_z
+    for (int i = tid; i < d; i += THREADS) {
         double acc = 0;
-        for (int k = 0; k < n; ++k) acc += P[(size_t)(24 + k) * d + i] * R[k * m];
+        for (int k = 0; k < n; ++k) acc += Pc[k * d + i] * R[k * m];
         s_dx[i] = acc;
     }
     // P_out = sym( P - P[:,c] Y_W )
-    for (int o = tid; o < d * d; o += 1024) {
+    for (int o = tid; o < d * d; o += THREADS) {
         const int i = o % d, j = o / d;
         if (i > j) continue;
         double a = 0, b = 0;
+#pragma unroll 4
         for (int k = 0; k < n; ++k) {
-            const double pik = P[(size_t)(24 + k) * d + i], pjk = P[(size_t)(24 + k) * d + j];
-            a += pik * R[k * m + 1 + j];
-            b += pjk * R[k * m + 1 + i];
+            a += Pc[k * d + i] * R[k * m + 1 + j];
+            b += Pc[k * d + j] * R[k * m + 1 + i];
         }
         const double pij = P[(size_t)j * d + i] - a, pji = P[(size_t)i * d + j] - b;
         const double v = .5 * (pij + pji);
@@ -921,7 +981,7 @@ __global__ void __launch_bounds__(1024) k_solve_small(SolveSmallParams Q)
     __syncthreads();
     // state correction, Updater.cc:546-613
     const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
-    for (int b = tid; b < 2 + N; b += 1024) {
+    for (int b = tid; b < 2 + N; b += THREADS) {
         int xq, eq;
         if (b == 0) { xq = 0; eq = 0; }
         else if (b == 1) { xq = 10; eq = 9; }
@@ -1041,11 +1101,12 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
     {
         const int nn = 6 * (u->Nmax < kSolveSmallMaxClones ? u->Nmax : kSolveSmallMaxClones);
-        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(double) * ((size_t)2 * nn * nn + (size_t)nn * (24 + nn + 1)))));
+        const int solve_smem = (int)(sizeof(double) * ((size_t)nn * nn + (size_t)nn * (24 + nn + 1) + (size_t)nn * (24 + nn) + (size_t)(3 * nn + 25) + 16));
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small<800>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
     }
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
-    u->groups_cap = 32;
+    u->groups_cap = 16;
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
     A(u->d_x, u->xmax); A(u->d_xout, u->xmax); A(u->d_P, d * d); A(u->d_Pout, d * d); A(u->d_Pnew, d * d); A(u->d_dx, d);
     A(u->d_types, F + 1); A(u->d_off, F + 2); A(u->d_xy, F * u->Lmax + 1);
@@ -1130,8 +1191,9 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
-        const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * (d + 1));
-        RVIO_LAUNCH(k_solve_small, 1, 1024, smem, s, sp);
+        const size_t smem = sizeof(double) * ((size_t)n * n + (size_t)n * (d + 1) + (size_t)n * d + (size_t)(2 * n + d + 1) + 16);
+        if (N <= 12) RVIO_LAUNCH(k_solve_small<800>, 1, 800, smem, s, sp);       // <= 774 4x4 tiles, 80 registers per thread
+        else RVIO_LAUNCH(k_solve_small<1024>, 1, 1024, smem, s, sp);
         RVIO_CUDA_TRY(cudaGetLastError());
         return RVIO_OK;
     }

@@ -1,0 +1,240 @@
+// rvio_host.hpp -- C++ host adaptor above the C ABI (include/rvio_b200.h).
+//
+// Mirrors the reference's call surface for the hot path so that System::MonoVIO (reference src/rvio/System.cc:173-437)
+// compiles unchanged against it:
+//     class RVIO::Tracker  { void track(im, lImuData); mvFeatTypesForUpdate; mvlFeatMeasForUpdate; }   Tracker.h:43-127
+//     class RVIO::Updater  { void update(xk1k, Pk1k, types, meas); xk1k1; Pk1k1; }                      Updater.h:36-71
+// Same member names, argument meaning and "errors are not signalled" behaviour (both return void; failures of the device
+// path are kept in last_status() and leave the outputs stale / pass-through exactly like the reference's early returns).
+//
+// Two flavours:
+//   * default: dependency-free (std containers + the small POD types below).  This is what is compiled and tested here
+//     (this image has neither OpenCV C++ headers nor Eigen).
+//   * -DRVIO_B200_WITH_OPENCV_EIGEN: the literal reference signatures (cv::Mat, std::list<ImuData*>, Eigen::VectorXd /
+//     MatrixXd, cv::FileStorage constructors).  Shown for the maintainer of the reference tree; see INTEGRATION.md.
+//
+// The corner detector is not part of the hot path: exactly as in the reference it stays a host object
+// (FeatureDetector::DetectWithSubPix / FindNewer).  The adaptor calls it through the `Detector` interface below between
+// rvio_tracker_track() and rvio_tracker_commit().
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rvio_b200.h"
+
+namespace RVIO {
+
+struct Point2f { float x, y; };                       // stands in for cv::Point2f
+
+// struct ImuData, reference src/rvio/InputBuffer.h:35-51 (same field order; Eigen::Vector3d -> double[3])
+struct ImuData {
+    double AngularVel[3];
+    double LinearAccel[3];
+    double Timestamp;
+    double TimeInterval;
+};
+
+// What FeatureDetector offers Tracker::track (reference src/rvio/FeatureDetector.h:37-52).
+struct Detector {
+    virtual ~Detector() {}
+    // DetectWithSubPix(im, nCorners, s, vCorners): im is the equalised 8-bit image, row stride = width
+    virtual int DetectWithSubPix(const uint8_t* im, int width, int height, int nCorners, int s, std::vector<Point2f>& vCorners) = 0;
+    // FindNewer(vCorners, vRefCorners, qNewCorners)
+    virtual int FindNewer(const std::vector<Point2f>& vCorners, const std::vector<Point2f>& vRefCorners, std::vector<Point2f>& qNewCorners) = 0;
+};
+
+class Tracker {
+public:
+    // Tracker(const cv::FileStorage&) in the reference (Tracker.cc:37-90); here the parsed keys arrive as rvio_tracker_cfg.
+    Tracker(const rvio_tracker_cfg& cfg, Detector* detector, int device = 0)
+        : mCfg(cfg), mpFeatureDetector(detector), mHandle(nullptr), mLastStatus(RVIO_OK)
+    {
+        mLastStatus = rvio_tracker_create(&mCfg, device, &mHandle);
+        if (mLastStatus != RVIO_OK) throw std::runtime_error(std::string("rvio_tracker_create: ") + rvio_b200_last_error());
+        mEq.resize((size_t)cfg.width * cfg.height);
+        mvlFeatMeasForUpdate.resize((size_t)std::ceil(.5 * cfg.n_features));
+    }
+    ~Tracker() { rvio_tracker_destroy(mHandle); }
+    Tracker(const Tracker&) = delete;
+    Tracker& operator=(const Tracker&) = delete;
+
+    // void Tracker::track(const cv::Mat& im, std::list<ImuData*>& lImuData)   -- Tracker.h:50, called at System.cc:258
+    void track(const uint8_t* im, int width, int height, int stride_bytes, int channels, std::list<ImuData*>& lImuData)
+    {
+        std::vector<double> imu;
+        imu.reserve(lImuData.size() * 8);
+        for (const ImuData* d : lImuData) {
+            imu.insert(imu.end(), d->AngularVel, d->AngularVel + 3);
+            imu.insert(imu.end(), d->LinearAccel, d->LinearAccel + 3);
+            imu.push_back(d->Timestamp);
+            imu.push_back(d->TimeInterval);
+        }
+        const int rc = rvio_tracker_track(mHandle, im, width, height, stride_bytes, channels, imu.data(), (int)lImuData.size());
+        mLastStatus = rc;
+        if (rc < 0 || rc == RVIO_NO_FEATURES) return;              // Tracker.cc:246-250: early return, lists stay stale
+        if (rc == RVIO_FIRST_IMAGE) {
+            // Tracker.cc:204-234
+            std::vector<Point2f> corners;
+            if (rvio_tracker_get_image(mHandle, mEq.data(), mCfg.width) != RVIO_OK) return;
+            const int n = mpFeatureDetector ? mpFeatureDetector->DetectWithSubPix(mEq.data(), mCfg.width, mCfg.height, mCfg.n_features, 1, corners) : 0;
+            if (n > 0) mLastStatus = rvio_tracker_seed(mHandle, &corners[0].x, n);
+            rvio_tracker_commit(mHandle);
+            return;
+        }
+        // results: Tracker.cc:271-342
+        int nFeat = 0, nMeas = 0;
+        rvio_tracker_get_update_count(mHandle, &nFeat, &nMeas);
+        std::vector<uint8_t> types((size_t)nFeat + 1);
+        std::vector<int32_t> off((size_t)nFeat + 1);
+        std::vector<float> xy((size_t)2 * nMeas + 2);
+        rvio_tracker_get_update_lists(mHandle, types.data(), off.data(), xy.data());
+        mvFeatTypesForUpdate.assign(types.begin(), types.begin() + nFeat);
+        mvlFeatMeasForUpdate.clear();
+        mvlFeatMeasForUpdate.resize((size_t)std::ceil(.5 * mCfg.n_features));           // Tracker.cc:272-274
+        for (int f = 0; f < nFeat; ++f)
+            for (int k = off[f]; k < off[f + 1]; ++k) mvlFeatMeasForUpdate[f].push_back(Point2f{xy[2 * k], xy[2 * k + 1]});
+        // refill: Tracker.cc:344-387
+        int nFree = 0;
+        rvio_tracker_n_free(mHandle, &nFree);
+        if (nFree > 0 && mpFeatureDetector) {
+            if (rvio_tracker_get_image(mHandle, mEq.data(), mCfg.width) == RVIO_OK) {
+                std::vector<Point2f> vTempFeats, qNewFeats, vRef((size_t)mCfg.n_features);
+                mpFeatureDetector->DetectWithSubPix(mEq.data(), mCfg.width, mCfg.height, mCfg.n_features, 2, vTempFeats);
+                int nRef = 0;
+                rvio_tracker_get_tracked_px(mHandle, &vRef[0].x, &nRef);
+                vRef.resize((size_t)nRef);
+                const int nNew = mpFeatureDetector->FindNewer(vTempFeats, vRef, qNewFeats);
+                if (nNew > 0) rvio_tracker_refill(mHandle, &qNewFeats[0].x, nNew, nullptr);
+            }
+        }
+        mLastStatus = rvio_tracker_commit(mHandle);                                     // Tracker.cc:389-395
+    }
+
+    int last_status() const { return mLastStatus; }
+    rvio_tracker* handle() { return mHandle; }
+
+public:
+    // Feature types for update: '1' lose track, '2' reach the max. tracking length   (Tracker.h:66-70)
+    std::vector<unsigned char> mvFeatTypesForUpdate;
+    // Feature measurements for update (Tracker.h:72-74)
+    std::vector<std::list<Point2f> > mvlFeatMeasForUpdate;
+
+private:
+    rvio_tracker_cfg mCfg;
+    Detector* mpFeatureDetector;
+    rvio_tracker* mHandle;
+    int mLastStatus;
+    std::vector<uint8_t> mEq;
+};
+
+class Updater {
+public:
+    // Updater(const cv::FileStorage&) in the reference (Updater.cc:38-69)
+    Updater(const rvio_updater_cfg& cfg, int device = 0) : mHandle(nullptr), mLastStatus(RVIO_OK)
+    {
+        mLastStatus = rvio_updater_create(&cfg, device, &mHandle);
+        if (mLastStatus != RVIO_OK) throw std::runtime_error(std::string("rvio_updater_create: ") + rvio_b200_last_error());
+        xk1k1.assign(26, 0.0);                                                         // Updater.cc:55-56
+        Pk1k1.assign(24 * 24, 0.0);
+    }
+    ~Updater() { rvio_updater_destroy(mHandle); }
+    Updater(const Updater&) = delete;
+    Updater& operator=(const Updater&) = delete;
+
+    // void Updater::update(Eigen::VectorXd& xk1k, Eigen::MatrixXd& Pk1k, std::vector<unsigned char>&,
+    //                      std::vector<std::list<cv::Point2f> >&)   -- Updater.h:43-44, called at System.cc:268.
+    // xk1k: 26+7N doubles; Pk1k: column-major d x d (== Eigen::MatrixXd::data()).
+    void update(const std::vector<double>& xk1k, const std::vector<double>& Pk1k,
+                const std::vector<unsigned char>& vFeatTypesForUpdate,
+                const std::vector<std::list<Point2f> >& vlFeatMeasForUpdate)
+    {
+        const int xdim = (int)xk1k.size();
+        const int d = 24 + 6 * ((xdim - 26) / 7);
+        const int nFeat = (int)vFeatTypesForUpdate.size();                             // Updater.cc:90
+        std::vector<int32_t> off((size_t)nFeat + 1, 0);
+        std::vector<float> xy;
+        for (int f = 0; f < nFeat; ++f) {
+            for (const Point2f& p : vlFeatMeasForUpdate[(size_t)f]) { xy.push_back(p.x); xy.push_back(p.y); }
+            off[(size_t)f + 1] = (int32_t)(xy.size() / 2);
+        }
+        xk1k1.resize((size_t)xdim);
+        Pk1k1.resize((size_t)d * d);
+        mLastStatus = rvio_updater_update(mHandle, xk1k.data(), xdim, Pk1k.data(), d,
+                                          nFeat ? vFeatTypesForUpdate.data() : nullptr, off.data(), xy.empty() ? nullptr : xy.data(), nFeat,
+                                          xk1k1.data(), Pk1k1.data(), &mInfo);
+        if (mLastStatus != RVIO_OK) { xk1k1 = xk1k; Pk1k1 = Pk1k; }                   // keep the filter alive: posterior = prior
+    }
+
+    int last_status() const { return mLastStatus; }
+    const rvio_update_info& info() const { return mInfo; }
+    rvio_updater* handle() { return mHandle; }
+
+public:
+    // Outputs (Updater.h:50-52)
+    std::vector<double> xk1k1;
+    std::vector<double> Pk1k1;      // column-major d x d
+
+private:
+    rvio_updater* mHandle;
+    int mLastStatus;
+    rvio_update_info mInfo{};
+};
+
+}  // namespace RVIO
+
+#ifdef RVIO_B200_WITH_OPENCV_EIGEN
+// Literal reference signatures on top of the classes above (needs OpenCV >= 2.4.3 and Eigen >= 3.1 like the reference,
+// CMakeLists.txt:43-51).  Not compiled in this repository's image; see INTEGRATION.md for how it slots into src/rvio.
+#include <Eigen/Core>
+#include <opencv2/core/core.hpp>
+namespace RVIO {
+namespace ref_api {
+
+inline rvio_tracker_cfg tracker_cfg_from(const cv::FileStorage& fs)                 // keys of Tracker.cc:39-79, Ransac.cc:34-46
+{
+    rvio_tracker_cfg c;
+    std::memset(&c, 0, sizeof c);
+    c.width = (int)fs["Camera.width"]; c.height = (int)fs["Camera.height"];
+    c.fx = (float)fs["Camera.fx"]; c.fy = (float)fs["Camera.fy"]; c.cx = (float)fs["Camera.cx"]; c.cy = (float)fs["Camera.cy"];
+    c.k1 = (float)fs["Camera.k1"]; c.k2 = (float)fs["Camera.k2"]; c.p1 = (float)fs["Camera.p1"]; c.p2 = (float)fs["Camera.p2"];
+    c.k3 = (float)fs["Camera.k3"];
+    c.is_rgb = (int)fs["Camera.RGB"]; c.is_fisheye = (int)fs["Camera.Fisheye"];
+    c.enable_equalizer = (int)fs["Tracker.EnableEqualizer"];
+    c.n_features = (int)fs["Tracker.nFeatures"];
+    c.max_track_len = (int)fs["Tracker.nMaxTrackingLength"]; c.min_track_len = (int)fs["Tracker.nMinTrackingLength"];
+    c.use_sampson = (int)fs["Tracker.UseSampson"]; c.inlier_thr = (double)fs["Tracker.nInlierThrd"];
+    c.small_angle = (double)fs["IMU.nSmallAngle"];
+    cv::Mat T; fs["Camera.T_BC0"] >> T;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) c.T_BC0[4 * i + j] = T.at<double>(i, j);
+    return c;
+}
+
+// void Tracker::track(const cv::Mat& im, std::list<ImuData*>& lImuData)
+inline void track(Tracker& t, const cv::Mat& im, std::list<ImuData*>& lImuData)
+{
+    t.track(im.data, im.cols, im.rows, (int)im.step, im.channels(), lImuData);
+}
+
+// void Updater::update(Eigen::VectorXd&, Eigen::MatrixXd&, std::vector<unsigned char>&, std::vector<std::list<cv::Point2f> >&)
+inline void update(Updater& u, Eigen::VectorXd& xk1k, Eigen::MatrixXd& Pk1k, std::vector<unsigned char>& types,
+                   std::vector<std::list<cv::Point2f> >& meas, Eigen::VectorXd& xk1k1, Eigen::MatrixXd& Pk1k1)
+{
+    std::vector<double> x(xk1k.data(), xk1k.data() + xk1k.size()), P(Pk1k.data(), Pk1k.data() + Pk1k.size());
+    std::vector<std::list<Point2f> > m(meas.size());
+    for (size_t f = 0; f < meas.size(); ++f) for (const cv::Point2f& p : meas[f]) m[f].push_back(Point2f{p.x, p.y});
+    u.update(x, P, types, m);
+    xk1k1 = Eigen::Map<Eigen::VectorXd>(u.xk1k1.data(), (Eigen::Index)u.xk1k1.size());
+    const Eigen::Index d = Pk1k.rows();
+    Pk1k1 = Eigen::Map<Eigen::MatrixXd>(u.Pk1k1.data(), d, d);
+}
+
+}  // namespace ref_api
+}  // namespace RVIO
+#endif  // RVIO_B200_WITH_OPENCV_EIGEN

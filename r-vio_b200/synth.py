@@ -239,3 +239,54 @@ class Stream:
 
     def gt_pose(self, i):
         return self.traj.pose(self.frame_t[i])
+
+
+# ----------------------------------------------------------------------------- updater micro-benchmark inputs
+def make_update_case(cfg, n_feat, seed, track_len=None, mix_types=True, n_clones=None):
+    """Worst-case-shaped Updater::update inputs (SURVEY 8d): a smooth window of N relative poses, P = A A^T + eps I scaled
+    to diag ~ [1e-6 .. 1e-2], `n_feat` tracks of length `track_len` (default: maximum) from random 3-D points at 2..10 m
+    projected through the true relative poses plus N(0, sigma_px^2) noise.  Returns (x, P, types, offsets, xy)."""
+    r = np.random.default_rng(seed)
+    N = cfg.window if n_clones is None else n_clones
+    L = (N + 1) if track_len is None else track_len
+    T = np.array(cfg.T_BC0, np.float64).reshape(4, 4)
+    Ric, tic = T[:3, :3], T[:3, 3]
+    # relative poses between consecutive frames (JPL): q_i rotates frame i-1 into frame i, p_i = position of frame i in i-1
+    x = np.zeros(26 + 7 * N)
+    x[3] = 1.0; x[7:10] = [0, 0, 1.0]; x[13] = 1.0
+    Rs, ps = [], []
+    for c in range(N):
+        w = r.normal(0, 0.02, 3); ang = np.linalg.norm(w); k = w / ang
+        q = np.concatenate([k * np.sin(ang / 2), [np.cos(ang / 2)]])
+        p = r.normal(0, 0.04, 3) + np.array([0.0, 0.0, 0.03])
+        x[26 + 7 * c:30 + 7 * c] = q
+        x[30 + 7 * c:33 + 7 * c] = p
+        qx = np.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]])
+        Rs.append(np.eye(3) - 2 * q[3] * qx + 2 * qx @ qx); ps.append(p)
+    d = 24 + 6 * N
+    A = r.standard_normal((d, d)) * 0.05
+    scale = 10 ** r.uniform(-3.0, -1.0, d)
+    P = (A @ A.T + np.eye(d)) * np.outer(scale, scale)
+    P = .5 * (P + P.T)
+    sig = float(max(np.float32(cfg.sigma_px), np.float32(cfg.sigma_py)))
+    types, offsets, xy = [], [0], []
+    for f in range(n_feat):
+        t2 = mix_types and (f % 2 == 1)
+        Lf = (N + 1) if t2 else L
+        first = 0 if t2 else N - (Lf - 1)                     # first clone used (type '1': last L-1 clones)
+        # point in the first camera frame
+        pc = np.array([r.uniform(-1.5, 1.5), r.uniform(-1.0, 1.0), r.uniform(2.0, 10.0)])
+        pi = Ric @ pc + tic                                    # in IMU frame of the first image
+        meas = []
+        Racc, tacc = np.eye(3), np.zeros(3)
+        for i in range(Lf):
+            if i > 0:
+                c = first + i - 1
+                Racc = Rs[c] @ Racc
+                tacc = Rs[c] @ (tacc - ps[c])
+            pcam = Ric.T @ (Racc @ pi + tacc - tic)
+            meas.append([pcam[0] / pcam[2] + r.normal(0, sig), pcam[1] / pcam[2] + r.normal(0, sig)])
+        types.append(ord('2') if t2 else ord('1'))
+        xy.extend(meas)
+        offsets.append(len(xy))
+    return (x, P, np.array(types, np.uint8), np.array(offsets, np.int32), np.array(xy, np.float32).reshape(-1, 2))

@@ -109,3 +109,53 @@ def test_updater_passthrough_and_empty():
     xg, Pg = upd.update(x, P, np.zeros(0, np.uint8), (np.zeros(1, np.int32), np.zeros((0, 2), np.float32)))
     assert upd.info.updated == 0
     assert np.array_equal(xg, x) and np.array_equal(Pg, P)
+
+
+@pytest.mark.parametrize("idx,n_feat,n_clones", [(1, 100, None), (2, 96, None), (4, 64, None), (4, 40, 17), (2, 50, 13), (2, 50, 14)])
+def test_updater_worstcase_shapes(idx, n_feat, n_clones):
+    """SURVEY 8d micro-benchmark shapes: maximum-length tracks, 50/50 type mix; N = 11 / 25 / 30 exercise both the
+    single-CTA solve (N <= 13) and the general GEMM + Gauss-Jordan path."""
+    cfg = synth.baseline_config(idx)
+    x, P, types, off, xy = synth.make_update_case(cfg, n_feat, 100 + idx, n_clones=n_clones)
+    upd = host.Updater(cfg)
+    stats = dict(cases=0, updated=0, rank_cut_frames=0, max_dx=0.0, max_err_x=0.0)
+    d = P.shape[0]
+    _check_case(cfg, upd, x, np.ascontiguousarray(P.T).reshape(-1), types, off, xy, stats)   # column-major bytes, as the stream cases
+    print(f"config[{idx}] N={(len(x) - 26) // 7} feats={n_feat}:", stats)
+    assert stats["updated"] == 1
+
+
+def test_updater_feature_sharding_matches_unsharded():
+    """Multi-GPU form on one device: each 'rank' forms the normal terms of its share (f % world == rank); the shares are
+    summed (what ncclAllReduce does across GPUs) and the finish step must reproduce the unsharded update."""
+    import ctypes as C
+    import torch
+    from rvio_b200 import capi
+    cfg = synth.baseline_config(1)
+    x, P, types, off, xy = synth.make_update_case(cfg, 90, 7)
+    upd = host.Updater(cfg)
+    xr, Pr = upd.update(x, P, types, (off, xy))
+    L = capi.lib()
+    d = P.shape[0]; n = d - 24
+    Pc = np.ascontiguousarray(P.T)
+    world = 4
+    total = None
+    count = n * n + n + 8
+    for rank in range(world):
+        capi.check(L.rvio_updater_update_begin(upd.h, x, len(x), Pc, d, types, off, np.ascontiguousarray(xy).reshape(-1), len(types), rank, world))
+        ptr, cnt = C.c_void_p(), C.c_int()
+        capi.check(L.rvio_updater_reduce_buffer(upd.h, C.byref(ptr), C.byref(cnt)))
+        assert cnt.value == count
+        stream = torch.cuda.ExternalStream(L.rvio_updater_stream(upd.h))
+        stream.synchronize()
+        buf = torch.empty(count, dtype=torch.float64, device="cuda")
+        C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(buf.data_ptr()), ptr, C.c_size_t(8 * count), 3)
+        total = buf.clone() if total is None else total + buf
+    # write the reduced terms back (stand-in for the all-reduce result) and finish
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(ptr, C.c_void_p(total.data_ptr()), C.c_size_t(8 * count), 3)
+    torch.cuda.synchronize()
+    xo = np.empty_like(x); Po = np.empty_like(Pc); info = capi.UpdateInfo()
+    capi.check(L.rvio_updater_update_finish(upd.h, xo, Po, C.byref(info)))
+    assert info.n_good == upd.info.n_good and info.updated == 1
+    np.testing.assert_allclose(xo, xr, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Po.T, Pr, rtol=0, atol=1e-10 * np.abs(Pr).max())

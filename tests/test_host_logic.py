@@ -63,3 +63,36 @@ def test_configs_match_baseline_json():
         assert u.max_clones == N and u.max_features == (F + 1) // 2
     c = synth.baseline_config(2)
     assert (c.width, c.height) == (1280, 720)
+
+
+def _build_selfcheck(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "host_selfcheck")
+    libdir = os.path.join(ROOT, "r-vio_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-o", exe, os.path.join(libdir, "host", "host_selfcheck.cpp"),
+                           "-L" + libdir, "-lrvio_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_host_adaptor_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """r-vio_b200/host/rvio_host.hpp (the C++ twin of host.py: RVIO::Tracker / RVIO::Updater with the reference's member
+    names) builds against the C ABI; without a device its constructors throw -- no CPU fallback."""
+    import subprocess
+    import torch
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    exe = _build_selfcheck(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stdout
+    else:
+        assert out.returncode == 3 and "no device path" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_host_adaptor_runs_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_selfcheck(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "GPU path ok" in out.stdout, out.stdout + out.stderr
