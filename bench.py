@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-streams", type=int, default=8, help="extra leg: independent streams run concurrently on one GPU (BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -186,6 +187,63 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         barrier()
         dev_ms, dev_wall, launches, used = drive(vio, dev_inputs=True)
         barrier()
+    # ---- batch leg (BASELINE configs[3]: independent streams, several per GPU, no communication): S handles driven by
+    #      S host threads on the same device-resident frames; aggregate frames/s over the slowest stream (wall clock
+    #      between device synchronisations; the single-stream `value` above is the CUDA-event number).
+    batch = None
+    S = args.batch_streams
+    if S > 1:
+        import threading
+        d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+        d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
+        d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
+        vios = [host.Vio(cfg, local_rank) for _ in range(S)]
+        Kb = min(K, 100)
+        start_bar = threading.Barrier(S + 1); end_bar = threading.Barrier(S + 1)
+        errs = []
+
+        def worker(v):
+            try:
+                got, i, warm, timed = False, 0, 0, 0
+                while True:
+                    dc = (d_c2 if got else d_c1)[i]
+                    if got and warm >= W and timed == 0:
+                        start_bar.wait()
+                    pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], dc.data_ptr() if dc is not None else None,
+                                      0 if dc is None else dc.shape[0])
+                    if got and warm >= W:
+                        timed += 1
+                        if timed == Kb:
+                            break
+                    elif got:
+                        warm += 1
+                    if pose is not None:
+                        got = True
+                    i += 1
+                end_bar.wait()
+            except Exception as e:          # pragma: no cover
+                errs.append(e)
+                try:
+                    start_bar.abort(); end_bar.abort()
+                except Exception:
+                    pass
+
+        ths = [threading.Thread(target=worker, args=(v,)) for v in vios]
+        for t in ths:
+            t.start()
+        start_bar.wait()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        end_bar.wait()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for t in ths:
+            t.join()
+        for v in vios:
+            v.close()
+        if not errs:
+            batch = {"streams_per_gpu": S, "steps_per_stream": Kb, "value": S * Kb / (t1 - t0), "unit": "frames/s",
+                     "timing": "wall clock between device synchronisations, all streams concurrent"}
     # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
     timeline = None
     if rank == 0:
@@ -222,8 +280,12 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
+        if batch is not None:
+            b = torch.tensor([batch["value"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            batch["value"] = float(b[0]); batch["n_gpus"] = world
     return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
-                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline)
+                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch)
 
 
 def roofline_from_profile(prof, cfg, peaks):
@@ -398,7 +460,7 @@ def main():
                    "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
            "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
            "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
-           "wall_ms_per_step": 1e3 * res["dev_wall"] / K}
+           "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"]}
     if not args.no_cpu_baseline and world == 1:
         steps = 60
         wl2 = {k: (v[:int(T_STATIC * cfg.fps) + 4 + W + steps + 4] if isinstance(v, list) else v) for k, v in wl.items()}
