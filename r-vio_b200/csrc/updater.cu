@@ -142,7 +142,6 @@ __device__ __forceinline__ void d_solve3(const double* A_, const double* b_, dou
 // ================================================================================================
 constexpr int kFeatThreads = 256;
 constexpr int kSolveSmallMaxClones = 13;     // n = 84: M + R + P[c,:] (+ pivot row / column) fit in 227 KB of shared memory
-constexpr int kGJRows = 17;                  // rows per thread in the register-resident Gauss-Jordan (n = 84: 193 columns -> 5 row groups)
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
@@ -795,123 +794,127 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeParams P)
 
 
 // ------------------------------------------------------------------------------------------------
-// k_solve_small: the whole EKF stage (Updater.cc:540-619) in ONE CTA for small windows (n = 6N <= 84), operands in
-// shared memory:  M = G Pcc + s^2 I ;  R = [z | G P[c,:]] ;  Gauss-Jordan ;  dx = P[:,c] y ;  P+ = P - P[:,c] Y ;
-// state correction + symmetrisation.  Replaces 4 k_dgemm + k_gauss_jordan + k_finalize launches.
+// Small-window EKF stage (n = 6N <= 78), Updater.cc:540-619, in three launches:
+//   k_wgemm          W = G * P[c,:]  ->  R = [z | W],  M = W[:,24:] + s^2 I            (multi-CTA, 32x32 tiles)
+//   k_gj_small<T>    Gauss-Jordan on [M | R], register resident, ONE CTA               (the serial part)
+//   k_pout_finalize  dx = P[:,c] y, P+ = sym(P - P[:,c] Y), state correction          (multi-CTA, 32x32 tiles)
+// P is symmetric by construction (PreIntegrator.cc:192, System.cc:300,361): P(a,b) is read as P[a d + b] with the
+// fastest-varying index on consecutive threads.
 // ------------------------------------------------------------------------------------------------
 struct SolveSmallParams {
     const double* red;        // [G | z | counters]
     const double* x; const double* P; int xdim, N, d;
     double sig2;
+    double* M; double* R;     // n x n, n x (d+1) row-major (global scratch)
+    double* dx;
     double* x_out; double* P_out; int* singular;
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_solve_small(SolveSmallParams Q)
+__global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
 {
-    extern __shared__ __align__(16) double ssm[];
-    __shared__ double s_dx[24 + 6 * 14 + 4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double sA[16][33], sB[16][33];
     const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
     const double* gate = Q.red + (size_t)n * n + n;
-    if (!(gate[0] > 2.0)) {                      // Updater.cc:621-627
-        for (int o = tid; o < d * d; o += THREADS) Q.P_out[o] = Q.P[o];
-        for (int o = tid; o < Q.xdim; o += THREADS) Q.x_out[o] = Q.x[o];
-        return;
-    }
-    double* M = ssm;                  // n x n
-    double* R = M + n * n;            // n x m
-    double* Pc = R + n * m;           // n x d : rows 24.. of P (== P[:,c]^T, P symmetric)
-    const double* P = Q.P;
-    const double* G = Q.red;          // n x n row-major (global, L1-resident; reads are warp-uniform)
-    // P is symmetric by construction (PreIntegrator.cc:192, System.cc:300,361): P(a,b) is read as P[a d + b], i.e. with
-    // the fastest-varying index on consecutive threads (coalesced).
-    for (int o = tid; o < n * d; o += THREADS) Pc[o] = P[(size_t)24 * d + o];
-    __syncthreads();
-    // W = G * P[c,:]  (n x d, 4x1 register tiles):  R[:,1+col] = W[:,col] ;  M = W[:,24:] + s^2 I ;  R[:,0] = z
-    {
-        const int nib = (n + 3) / 4;
-        for (int item = tid; item < nib * d; item += THREADS) {
-            const int ib = item / d, col = item - ib * d;
-            const int i0 = 4 * ib;
-            const double* pc = Pc + col;
-            const double* g0 = G + (size_t)i0 * n;
-            const int r1 = (i0 + 1 < n) ? n : 0, r2 = (i0 + 2 < n) ? 2 * n : 0, r3 = (i0 + 3 < n) ? 3 * n : 0;
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 4
-            for (int k = 0; k < n; ++k) {
-                const double pv = pc[k * d];
-                a0 += g0[k] * pv; a1 += g0[r1 + k] * pv; a2 += g0[r2 + k] * pv; a3 += g0[r3 + k] * pv;
-            }
-            const double av[4] = {a0, a1, a2, a3};
+    if (!(gate[0] > 2.0)) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;           // rows of G, columns of P[c,:]
+    const double* G = Q.red;
+    const double* Pc = Q.P + (size_t)24 * d;                          // row k of P[c,:] = P[(24+k) d + col]
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        for (int o = threadIdx.x; o < 16 * 32; o += 256) {
+            const int kk = o >> 5, c = o & 31;
+            const int k = k0 + kk;
+            sA[kk][c] = (k < n && i0 + c < n) ? G[(size_t)k * n + i0 + c] : 0.0;       // G(i,k) == G(k,i) bit for bit (mirror tiles of k_gram)
+            sB[kk][c] = (k < n && j0 + c < d) ? Pc[(size_t)k * d + j0 + c] : 0.0;
+        }
+        __syncthreads();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i0 + q;
-                if (i < n) {
-                    R[i * m + 1 + col] = av[q];
-                    if (col >= 24) M[i * n + (col - 24)] = av[q] + ((i == col - 24) ? Q.sig2 : 0.0);
-                }
+        for (int kk = 0; kk < 16; ++kk) {
+            const double a0 = sA[kk][2 * ty], a1 = sA[kk][2 * ty + 1];
+            const double b0 = sB[kk][2 * tx], b1 = sB[kk][2 * tx + 1];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+        __syncthreads();
+    }
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + 2 * ty + a, col = j0 + 2 * tx + b;
+            if (i < n && col < d) {
+                Q.R[(size_t)i * m + 1 + col] = acc[a][b];
+                if (col >= 24) Q.M[(size_t)i * n + (col - 24)] = acc[a][b] + ((i == col - 24) ? Q.sig2 : 0.0);
             }
         }
-        for (int i = tid; i < n; i += THREADS) R[i * m] = Q.red[(size_t)n * n + i];
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const int i = i0 + threadIdx.x;
+        if (i < n) Q.R[(size_t)i * m] = Q.red[(size_t)n * n + i];
     }
+}
+
+// Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (rb, cb) owns the 4x4 tile rows
+// 4rb.., columns 4cb.. of [M | R] (rb fastest, so the threads of one column block share a warp).  Per step: the owners of
+// pivot row p publish it, the owners of column k publish the multipliers, everybody applies the rank-1 update to its tile
+// (16 DFMA for 8 shared loads); the pivot of step k+1 (largest |.| of column k+1 over rows not yet used) is found during
+// the update (warp max + one packed atomicMax per warp).  Solution rows are written back to R in variable order.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_gj_small(SolveSmallParams Q)
+{
+    __shared__ unsigned long long s_key[2];
+    __shared__ unsigned char s_used[96];
+    __shared__ short s_prow[96];
+    __shared__ short s_var[96];
+    __shared__ double s_pinv;
+    __shared__ double s_rowk[96 + 128];
+    __shared__ double s_colk[96];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    const double* gate = Q.red + (size_t)n * n + n;
+    if (!(gate[0] > 2.0)) return;
+    const int ncols = n + m;
+    const int ncb = (ncols + 3) / 4, nrb = (n + 3) / 4;
+    const int rb = tid % nrb, cb = tid / nrb;
+    const bool active = cb < ncb;
+    const int r0 = 4 * rb, c0 = 4 * cb;
+    double reg[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = r0 + r, c = c0 + j;
+            reg[r][j] = (active && i < n && c < ncols) ? ((c < n) ? Q.M[(size_t)i * n + c] : Q.R[(size_t)i * m + (c - n)]) : 0.0;
+        }
+    if (tid < 96) s_used[tid] = 0;
+    if (tid == 0) { s_key[0] = 0ull; s_key[1] = 0ull; }
     __syncthreads();
-    // Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (rb, cb) owns the 4x4 tile
-    // rows 4rb.., columns 4cb.. of [M | R].  Per step: the owners of pivot row p publish it, the owners of column k publish
-    // the multipliers, everybody applies the rank-1 update to its tile (16 DFMA for 8 shared loads); the pivot of step
-    // k+1 (largest |.| of column k+1 over rows not yet used) is found during the update with a packed atomicMax.
-    {
-        __shared__ unsigned long long s_key[2];
-        __shared__ unsigned char s_used[96];
-        __shared__ short s_prow[96];                       // pivot row of step k
-        __shared__ short s_var[96];                        // inverse permutation
-        __shared__ double s_pinv;
-        double* s_rowk = Pc + n * d;                       // (ncols + 4) doubles: pivot row
-        double* s_colk = s_rowk + (n + m + 4);             // (n + 4) doubles: column k multipliers
-        const int ncols = n + m;
-        const int ncb = (ncols + 3) / 4, nrb = (n + 3) / 4;
-        const int cb = tid % ncb, rb = tid / ncb;
-        const bool active = rb < nrb;
-        const int r0 = 4 * rb, c0 = 4 * cb;
-        double reg[4][4];
+    if (active && cb == 0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = r0 + r, c = c0 + j;
-                reg[r][j] = (active && i < n && c < ncols) ? ((c < n) ? M[i * n + c] : R[i * m + (c - n)]) : 0.0;
-            }
-        if (tid < 96) s_used[tid] = 0;
-        if (tid == 0) { s_key[0] = 0ull; s_key[1] = 0ull; }
-        __syncthreads();
-        if (active && cb == 0) {
+            if (r0 + r < n) atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(fabs(reg[r][0])) & ~1023ull) | (unsigned long long)(1023 - (r0 + r)));
+    }
+    __syncthreads();
+    bool singular = false;
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long key = s_key[k & 1];
+        const int p = 1023 - (int)(key & 1023ull);
+        if ((key >> 10) == 0ull) { singular = true; break; }                   // uniform
+        const int pr = p & 3, kc = k & 3;
+        if (active && rb == (p >> 2)) {                                        // publish pivot row (unscaled)
+            double v0 = reg[0][0], v1 = reg[0][1], v2 = reg[0][2], v3 = reg[0][3];
+            if (pr == 1) { v0 = reg[1][0]; v1 = reg[1][1]; v2 = reg[1][2]; v3 = reg[1][3]; }
+            if (pr == 2) { v0 = reg[2][0]; v1 = reg[2][1]; v2 = reg[2][2]; v3 = reg[2][3]; }
+            if (pr == 3) { v0 = reg[3][0]; v1 = reg[3][1]; v2 = reg[3][2]; v3 = reg[3][3]; }
+            s_rowk[c0] = v0; s_rowk[c0 + 1] = v1; s_rowk[c0 + 2] = v2; s_rowk[c0 + 3] = v3;
+            if (cb == (k >> 2)) s_pinv = 1.0 / (kc == 0 ? v0 : kc == 1 ? v1 : kc == 2 ? v2 : v3);
+        }
+        if (active && cb == (k >> 2)) {                                        // publish column k
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (r0 + r < n) atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(fabs(reg[r][0])) & ~1023ull) | (unsigned long long)(1023 - (r0 + r)));
+                s_colk[r0 + r] = kc == 0 ? reg[r][0] : kc == 1 ? reg[r][1] : kc == 2 ? reg[r][2] : reg[r][3];
         }
+        if (tid == 0) { s_key[(k + 1) & 1] = 0ull; s_used[p] = 1; s_prow[k] = (short)p; }
         __syncthreads();
-        bool singular = false;
-        for (int k = 0; k < n; ++k) {
-            const unsigned long long key = s_key[k & 1];
-            const int p = 1023 - (int)(key & 1023ull);
-            if ((key >> 10) == 0ull) { singular = true; break; }                   // uniform
-            const int pr = p & 3, kc = k & 3;
-            if (active && rb == (p >> 2)) {                                        // publish pivot row (unscaled)
-                double v0 = reg[0][0], v1 = reg[0][1], v2 = reg[0][2], v3 = reg[0][3];
-                if (pr == 1) { v0 = reg[1][0]; v1 = reg[1][1]; v2 = reg[1][2]; v3 = reg[1][3]; }
-                if (pr == 2) { v0 = reg[2][0]; v1 = reg[2][1]; v2 = reg[2][2]; v3 = reg[2][3]; }
-                if (pr == 3) { v0 = reg[3][0]; v1 = reg[3][1]; v2 = reg[3][2]; v3 = reg[3][3]; }
-                s_rowk[c0] = v0; s_rowk[c0 + 1] = v1; s_rowk[c0 + 2] = v2; s_rowk[c0 + 3] = v3;
-                if (cb == (k >> 2)) s_pinv = 1.0 / (kc == 0 ? v0 : kc == 1 ? v1 : kc == 2 ? v2 : v3);
-            }
-            if (active && cb == (k >> 2)) {                                        // publish column k
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    s_colk[r0 + r] = kc == 0 ? reg[r][0] : kc == 1 ? reg[r][1] : kc == 2 ? reg[r][2] : reg[r][3];
-            }
-            if (tid == 0) { s_key[(k + 1) & 1] = 0ull; s_used[p] = 1; s_prow[k] = (short)p; }
-            __syncthreads();
-            if (active) {
+        {
+            if (active) {                                  // (threads beyond the last column block hold zeros and no smem slot)
                 const double pinv = s_pinv;
                 double rk[4], f[4];
 #pragma unroll
@@ -927,67 +930,116 @@ __global__ void __launch_bounds__(THREADS) k_solve_small(SolveSmallParams Q)
                     for (int r = 0; r < 4; ++r)
                         if (r == pr) { reg[r][0] = rk[0]; reg[r][1] = rk[1]; reg[r][2] = rk[2]; reg[r][3] = rk[3]; }
                 }
-                if (cb == ((k + 1) >> 2) && k + 1 < n) {
-                    const int nc = (k + 1) & 3;
+            }
+            // next pivot: warps that hold threads of column block (k+1)/4 reduce their candidates, one atomic per warp
+            const int nk = k + 1;
+            const int cb_lo = (tid - lane) / nrb, cb_hi = (tid - lane + 31) / nrb;       // column blocks present in this warp
+            if (nk < n && (nk >> 2) >= cb_lo && (nk >> 2) <= cb_hi) {
+                unsigned long long best = 0ull;
+                if (active && cb == (nk >> 2)) {
+                    const int nc = nk & 3;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int i = r0 + r;
                         if (i < n && !s_used[i]) {
                             const double v = nc == 0 ? reg[r][0] : nc == 1 ? reg[r][1] : nc == 2 ? reg[r][2] : reg[r][3];
-                            atomicMax(&s_key[(k + 1) & 1], ((unsigned long long)__double_as_longlong(fabs(v)) & ~1023ull) | (unsigned long long)(1023 - i));
+                            const unsigned long long kk = ((unsigned long long)__double_as_longlong(fabs(v)) & ~1023ull) | (unsigned long long)(1023 - i);
+                            best = kk > best ? kk : best;
                         }
                     }
                 }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = other > best ? other : best;
+                }
+                if (lane == 0 && best) atomicMax(&s_key[nk & 1], best);
             }
-            __syncthreads();
         }
-        if (singular && tid == 0) *Q.singular = 1;
-        // solution row of variable k is pivot row s_prow[k]: scatter Y = R[prow[k]] back into shared R (n x m)
         __syncthreads();
-        if (tid < n) s_var[s_prow[tid]] = (short)tid;
+    }
+    if (singular) { if (tid == 0) *Q.singular = 1; return; }
+    if (tid < n) s_var[s_prow[tid]] = (short)tid;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = r0 + r, c = c0 + j;
+                if (i < n && c >= n && c < ncols) Q.R[(size_t)s_var[i] * m + (c - n)] = reg[r][j];
+            }
+    }
+}
+
+// dx = P[:,c] y ; P_out = sym(P - P[:,c] Y) on 32x32 tiles (each tile also forms its transposed product so that both
+// mirror tiles write bit-identical values); block (0,0) then applies the state correction (Updater.cc:546-613).
+__global__ void __launch_bounds__(256) k_pout_finalize(SolveSmallParams Q)
+{
+    __shared__ double sPi[16][33], sPj[16][33], sYi[16][33], sYj[16][33];
+    __shared__ double s_dx[24 + 6 * 13 + 8];
+    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    const double* gate = Q.red + (size_t)n * n + n;
+    const int tid = threadIdx.x;
+    const int nb = (d + 31) / 32;
+    if (!(gate[0] > 2.0)) {                       // Updater.cc:621-627: posterior = prior
+        for (int o = blockIdx.x * 256 + tid; o < d * d; o += gridDim.x * 256) Q.P_out[o] = Q.P[o];
+        if (blockIdx.x == 0) for (int o = tid; o < Q.xdim; o += 256) Q.x_out[o] = Q.x[o];
+        return;
+    }
+    const int ti = blockIdx.x / nb, tj = blockIdx.x % nb;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int i0 = ti * 32, j0 = tj * 32;
+    const double* Pc = Q.P + (size_t)24 * d;                          // Pc[k][i] = P(i, 24+k)
+    const double* Y = Q.R + 1;                                        // Y[k][j] at Q.R[k*m + 1 + j]
+    double a[2][2] = {{0, 0}, {0, 0}}, b[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        for (int o = tid; o < 16 * 32; o += 256) {
+            const int kk = o >> 5, c = o & 31;
+            const int k = k0 + kk;
+            const bool kv = k < n;
+            sPi[kk][c] = (kv && i0 + c < d) ? Pc[(size_t)k * d + i0 + c] : 0.0;
+            sPj[kk][c] = (kv && j0 + c < d) ? Pc[(size_t)k * d + j0 + c] : 0.0;
+            sYi[kk][c] = (kv && i0 + c < d) ? Y[(size_t)k * m + i0 + c] : 0.0;
+            sYj[kk][c] = (kv && j0 + c < d) ? Y[(size_t)k * m + j0 + c] : 0.0;
+        }
         __syncthreads();
-        if (active && !singular) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+        for (int kk = 0; kk < 16; ++kk) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = r0 + r, c = c0 + j;
-                    if (i < n && c >= n && c < ncols) R[(int)s_var[i] * m + (c - n)] = reg[r][j];
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    a[u][v] += sPi[kk][2 * ty + u] * sYj[kk][2 * tx + v];          // (P[:,c] Y)(i, j)
+                    b[u][v] += sPj[kk][2 * tx + v] * sYi[kk][2 * ty + u];          // (P[:,c] Y)(j, i)
                 }
         }
         __syncthreads();
     }
-    // dx = P[:,c] y_z
-    for (int i = tid; i < d; i += THREADS) {
+    for (int u = 0; u < 2; ++u)
+        for (int v = 0; v < 2; ++v) {
+            const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
+            if (i < d && j < d) {
+                const double pij = Q.P[(size_t)j * d + i] - a[u][v], pji = Q.P[(size_t)i * d + j] - b[u][v];
+                Q.P_out[(size_t)j * d + i] = .5 * (pij + pji);
+            }
+        }
+    if (blockIdx.x != 0) return;
+    // dx and the state correction (block 0)
+    for (int i = tid; i < d; i += 256) {
         double acc = 0;
-        for (int k = 0; k < n; ++k) acc += Pc[k * d + i] * R[k * m];
+        for (int k = 0; k < n; ++k) acc += Pc[(size_t)k * d + i] * Q.R[(size_t)k * m];
         s_dx[i] = acc;
     }
-    // P_out = sym( P - P[:,c] Y_W )
-    for (int o = tid; o < d * d; o += THREADS) {
-        const int i = o % d, j = o / d;
-        if (i > j) continue;
-        double a = 0, b = 0;
-#pragma unroll 4
-        for (int k = 0; k < n; ++k) {
-            a += Pc[k * d + i] * R[k * m + 1 + j];
-            b += Pc[k * d + j] * R[k * m + 1 + i];
-        }
-        const double pij = P[(size_t)j * d + i] - a, pji = P[(size_t)i * d + j] - b;
-        const double v = .5 * (pij + pji);
-        Q.P_out[(size_t)j * d + i] = v;
-        Q.P_out[(size_t)i * d + j] = v;
-    }
     __syncthreads();
-    // state correction, Updater.cc:546-613
     const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
-    for (int b = tid; b < 2 + N; b += THREADS) {
+    for (int bq = tid; bq < 2 + N; bq += 256) {
         int xq, eq;
-        if (b == 0) { xq = 0; eq = 0; }
-        else if (b == 1) { xq = 10; eq = 9; }
-        else { xq = 26 + 7 * (b - 2); eq = 24 + 6 * (b - 2); }
+        if (bq == 0) { xq = 0; eq = 0; }
+        else if (bq == 1) { xq = 10; eq = 9; }
+        else { xq = 26 + 7 * (bq - 2); eq = 24 + 6 * (bq - 2); }
         d_apply_dq(dx + eq, x + xq, xo + xq);
-        if (b >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
+        if (bq >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
     }
     if (tid == 64) {
         double g[3];
@@ -1099,12 +1151,6 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     if (u->lay.total_bytes > 200 * 1024) { set_error("rvio_updater_create", "max_track_len too large for shared memory"); return RVIO_ERR_CAPACITY; }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
-    {
-        const int nn = 6 * (u->Nmax < kSolveSmallMaxClones ? u->Nmax : kSolveSmallMaxClones);
-        const int solve_smem = (int)(sizeof(double) * ((size_t)nn * nn + (size_t)nn * (24 + nn + 1) + (size_t)nn * (24 + nn) + (size_t)(3 * nn + 25) + 16));
-        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small<800>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
-        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, solve_smem));
-    }
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
     u->groups_cap = 16;
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
@@ -1189,11 +1235,14 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
     if (N <= kSolveSmallMaxClones) {
         SolveSmallParams sp;
         sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
+        sp.M = u->d_M; sp.R = u->d_R; sp.dx = u->d_dx;
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
-        const size_t smem = sizeof(double) * ((size_t)n * n + (size_t)n * (d + 1) + (size_t)n * d + (size_t)(2 * n + d + 1) + 16);
-        if (N <= 12) RVIO_LAUNCH(k_solve_small<800>, 1, 800, smem, s, sp);       // <= 774 4x4 tiles, 80 registers per thread
-        else RVIO_LAUNCH(k_solve_small<1024>, 1, 1024, smem, s, sp);
+        RVIO_LAUNCH(k_wgemm, dim3(div_up(d, 32), div_up(n, 32)), 256, 0, s, sp);
+        if (N <= 12) RVIO_LAUNCH(k_gj_small<800>, 1, 800, 0, s, sp);          // <= 774 4x4 tiles, 80 registers per thread
+        else RVIO_LAUNCH(k_gj_small<1024>, 1, 1024, 0, s, sp);
+        const int nb = div_up(d, 32);
+        RVIO_LAUNCH(k_pout_finalize, nb * nb, 256, 0, s, sp);
         RVIO_CUDA_TRY(cudaGetLastError());
         return RVIO_OK;
     }
