@@ -851,110 +851,88 @@ __global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
     }
 }
 
-// Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (rb, cb) owns the 4x4 tile rows
-// 4rb.., columns 4cb.. of [M | R] (rb fastest, so the threads of one column block share a warp).  Per step: the owners of
-// pivot row p publish it, the owners of column k publish the multipliers, everybody applies the rank-1 update to its tile
-// (16 DFMA for 8 shared loads); the pivot of step k+1 (largest |.| of column k+1 over rows not yet used) is found during
-// the update (warp max + one packed atomicMax per warp).  Solution rows are written back to R in variable order.
+// Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (i, cb) owns row i, columns
+// 16cb..16cb+15 of [M | R] (i fastest: a warp holds 32 rows of one column block, so the pivot row is a broadcast load).
+// Step k: the owners of pivot row p publish it unscaled, the owners of column k publish the multipliers (pivot row: piv-1,
+// which turns the common update  row -= f/piv * pivot_row  into the scaling of the pivot row itself), everybody updates
+// 16 registers with 16 DFMA; the pivot of step k+1 (largest |.| of column k+1 over rows not yet used) is found during the
+// update (warp max + one packed atomicMax per warp).  Solution rows go back to R in variable order.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_gj_small(SolveSmallParams Q)
 {
-    __shared__ unsigned long long s_key[2];
+    __shared__ unsigned s_key[2];                     // packed pivot key: float32 bits of |v| (top 22 bits) | (1023 - row)
     __shared__ unsigned char s_used[96];
     __shared__ short s_prow[96];
     __shared__ short s_var[96];
-    __shared__ double s_pinv;
-    __shared__ double s_rowk[96 + 128];
-    __shared__ double s_colk[96];
+    __shared__ __align__(16) double s_rowk[208];      // pivot row, unscaled
+    __shared__ double s_colk[2][96];                  // column k (double buffered: column k+1 is published during step k)
+    __shared__ double s_rcp[2][96];                   // 1 / column value (the winner's entry is the pivot reciprocal)
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) return;
     const int ncols = n + m;
-    const int ncb = (ncols + 3) / 4, nrb = (n + 3) / 4;
-    const int rb = tid % nrb, cb = tid / nrb;
+    const int ncb = (ncols + 15) / 16;
+    const int i = tid % n, cb = tid / n;
     const bool active = cb < ncb;
-    const int r0 = 4 * rb, c0 = 4 * cb;
-    double reg[4][4];
+    const int c0 = 16 * cb;
+    double reg[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = r0 + r, c = c0 + j;
-            reg[r][j] = (active && i < n && c < ncols) ? ((c < n) ? Q.M[(size_t)i * n + c] : Q.R[(size_t)i * m + (c - n)]) : 0.0;
-        }
+    for (int j = 0; j < 16; ++j) {
+        const int c = c0 + j;
+        reg[j] = (active && c < ncols) ? ((c < n) ? Q.M[(size_t)i * n + c] : Q.R[(size_t)i * m + (c - n)]) : 0.0;
+    }
     if (tid < 96) s_used[tid] = 0;
-    if (tid == 0) { s_key[0] = 0ull; s_key[1] = 0ull; }
+    if (tid == 0) { s_key[0] = 0u; s_key[1] = 0u; }
     __syncthreads();
     if (active && cb == 0) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (r0 + r < n) atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(fabs(reg[r][0])) & ~1023ull) | (unsigned long long)(1023 - (r0 + r)));
+        const double v = reg[0];
+        s_colk[0][i] = v;
+        s_rcp[0][i] = 1.0 / v;
+        atomicMax(&s_key[0], (__float_as_uint((float)fabs(v)) & ~1023u) | (unsigned)(1023 - i));
     }
     __syncthreads();
     bool singular = false;
     for (int k = 0; k < n; ++k) {
-        const unsigned long long key = s_key[k & 1];
-        const int p = 1023 - (int)(key & 1023ull);
-        if ((key >> 10) == 0ull) { singular = true; break; }                   // uniform
-        const int pr = p & 3, kc = k & 3;
-        if (active && rb == (p >> 2)) {                                        // publish pivot row (unscaled)
-            double v0 = reg[0][0], v1 = reg[0][1], v2 = reg[0][2], v3 = reg[0][3];
-            if (pr == 1) { v0 = reg[1][0]; v1 = reg[1][1]; v2 = reg[1][2]; v3 = reg[1][3]; }
-            if (pr == 2) { v0 = reg[2][0]; v1 = reg[2][1]; v2 = reg[2][2]; v3 = reg[2][3]; }
-            if (pr == 3) { v0 = reg[3][0]; v1 = reg[3][1]; v2 = reg[3][2]; v3 = reg[3][3]; }
-            s_rowk[c0] = v0; s_rowk[c0 + 1] = v1; s_rowk[c0 + 2] = v2; s_rowk[c0 + 3] = v3;
-            if (cb == (k >> 2)) s_pinv = 1.0 / (kc == 0 ? v0 : kc == 1 ? v1 : kc == 2 ? v2 : v3);
-        }
-        if (active && cb == (k >> 2)) {                                        // publish column k
+        const unsigned key = s_key[k & 1];
+        const int p = 1023 - (int)(key & 1023u);
+        if ((key >> 10) == 0u) { singular = true; break; }                     // uniform
+        if (active && i == p) {                                                // publish the pivot row (unscaled)
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                s_colk[r0 + r] = kc == 0 ? reg[r][0] : kc == 1 ? reg[r][1] : kc == 2 ? reg[r][2] : reg[r][3];
+            for (int j = 0; j < 16; ++j) s_rowk[c0 + j] = reg[j];
         }
-        if (tid == 0) { s_key[(k + 1) & 1] = 0ull; s_used[p] = 1; s_prow[k] = (short)p; }
+        if (tid == 0) { s_key[(k + 1) & 1] = 0u; s_used[p] = 1; s_prow[k] = (short)p; }
         __syncthreads();
-        {
-            if (active) {                                  // (threads beyond the last column block hold zeros and no smem slot)
-                const double pinv = s_pinv;
-                double rk[4], f[4];
+        if (active) {
+            // multiplier: column value / pivot; for the pivot row itself (piv - 1) / piv, which scales it by 1/piv
+            const double cv = s_colk[k & 1][i];
+            const double f = ((i == p) ? (cv - 1.0) : cv) * s_rcp[k & 1][p];
+            const double2* rk = reinterpret_cast<const double2*>(&s_rowk[c0]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rk[j] = s_rowk[c0 + j] * pinv;
+            for (int j = 0; j < 8; ++j) {
+                const double2 r2 = rk[j];
+                reg[2 * j] -= f * r2.x;
+                reg[2 * j + 1] -= f * r2.y;
+            }
+        }
+        // publish column k+1 (+ reciprocals) and find its pivot among the rows not used yet
+        const int nk = k + 1;
+        const int cb_lo = (tid - lane) / n, cb_hi = (tid - lane + 31) / n;
+        if (nk < n && (nk >> 4) >= cb_lo && (nk >> 4) <= cb_hi) {
+            unsigned best = 0u;
+            if (active && cb == (nk >> 4)) {
+                const int nc = nk & 15;
+                double v = reg[0];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) f[r] = (r0 + r == p) ? 0.0 : s_colk[r0 + r];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) reg[r][j] -= f[r] * rk[j];
-                if (rb == (p >> 2)) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (r == pr) { reg[r][0] = rk[0]; reg[r][1] = rk[1]; reg[r][2] = rk[2]; reg[r][3] = rk[3]; }
+                for (int j = 1; j < 16; ++j) if (j == nc) v = reg[j];
+                s_colk[nk & 1][i] = v;
+                if (!s_used[i]) {
+                    best = (__float_as_uint((float)fabs(v)) & ~1023u) | (unsigned)(1023 - i);
+                    s_rcp[nk & 1][i] = 1.0 / v;
                 }
             }
-            // next pivot: warps that hold threads of column block (k+1)/4 reduce their candidates, one atomic per warp
-            const int nk = k + 1;
-            const int cb_lo = (tid - lane) / nrb, cb_hi = (tid - lane + 31) / nrb;       // column blocks present in this warp
-            if (nk < n && (nk >> 2) >= cb_lo && (nk >> 2) <= cb_hi) {
-                unsigned long long best = 0ull;
-                if (active && cb == (nk >> 2)) {
-                    const int nc = nk & 3;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int i = r0 + r;
-                        if (i < n && !s_used[i]) {
-                            const double v = nc == 0 ? reg[r][0] : nc == 1 ? reg[r][1] : nc == 2 ? reg[r][2] : reg[r][3];
-                            const unsigned long long kk = ((unsigned long long)__double_as_longlong(fabs(v)) & ~1023ull) | (unsigned long long)(1023 - i);
-                            best = kk > best ? kk : best;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-                    best = other > best ? other : best;
-                }
-                if (lane == 0 && best) atomicMax(&s_key[nk & 1], best);
-            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (lane == 0 && best) atomicMax(&s_key[nk & 1], best);
         }
         __syncthreads();
     }
@@ -962,13 +940,12 @@ __global__ void __launch_bounds__(THREADS) k_gj_small(SolveSmallParams Q)
     if (tid < n) s_var[s_prow[tid]] = (short)tid;
     __syncthreads();
     if (active) {
+        const int row = s_var[i];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = r0 + r, c = c0 + j;
-                if (i < n && c >= n && c < ncols) Q.R[(size_t)s_var[i] * m + (c - n)] = reg[r][j];
-            }
+        for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            if (c >= n && c < ncols) Q.R[(size_t)row * m + (c - n)] = reg[j];
+        }
     }
 }
 
@@ -1239,7 +1216,7 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
         RVIO_LAUNCH(k_wgemm, dim3(div_up(d, 32), div_up(n, 32)), 256, 0, s, sp);
-        if (N <= 12) RVIO_LAUNCH(k_gj_small<800>, 1, 800, 0, s, sp);          // <= 774 4x4 tiles, 80 registers per thread
+        if (n * div_up(n + d + 1, 16) <= 704) RVIO_LAUNCH(k_gj_small<704>, 1, 704, 0, s, sp);     // one thread per (row, 16-column block)
         else RVIO_LAUNCH(k_gj_small<1024>, 1, 1024, 0, s, sp);
         const int nb = div_up(d, 32);
         RVIO_LAUNCH(k_pout_finalize, nb * nb, 256, 0, s, sp);
