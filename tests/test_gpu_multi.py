@@ -1,0 +1,22 @@
+"""GPU (>= 2 devices): feature-sharded update with one NCCL all-reduce (tests/dist_sharded_update.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_update_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (covered on one GPU by test_updater_feature_sharding_matches_unsharded)")
+    world = 2 if n < 4 else 4
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(ROOT, "tests", "dist_sharded_update.py")],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, RVIO_TEST_FEATS="192"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded update ok" in out.stdout
