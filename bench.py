@@ -247,7 +247,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
     timeline = None
     if rank == 0:
-        tl = np.zeros(6, np.float32)
+        tl = np.zeros(8, np.float32)
         L.rvio_vio_timeline(vio.h, 1, None)
         acc = []
         for i in range(used, min(used + 12, n_frames)):
@@ -256,7 +256,8 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
             acc.append(tl.copy())
         L.rvio_vio_timeline(vio.h, 0, None)
         used = min(used + 12, n_frames)
-        timeline = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail"],
+        timeline = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail",
+                             "host_enqueue", "host_blocked_in_sync"],
                             [round(float(v) * 1e3, 1) for v in np.median(np.array(acc), 0)]))
     # ---- per-kernel events over a few more steps (roofline leg)
     prof = {}

@@ -188,8 +188,9 @@ int rvio_vio_get_state(rvio_vio* vio, double* x, int* xdim, double* P, int* d);
 /* Update counters of the last step (n_feat = 0 when no update ran). */
 int rvio_vio_get_update_info(rvio_vio* vio, rvio_update_info* info);
 /* Debug: per-stage CUDA-event times (ms) of the last step on the main stream: [tracker, per-feature + normal terms,
- * wait for propagation, solve, augment + compose, tail]; enable != 0 switches the instrumentation on. */
-int rvio_vio_timeline(rvio_vio* vio, int enable, float* ms6);
+ * wait for propagation, solve, augment + compose, tail], then two host wall-clock times of the same step: [enqueue of
+ * the whole frame, blocked in the one synchronisation]; enable != 0 switches the event instrumentation on. */
+int rvio_vio_timeline(rvio_vio* vio, int enable, float* ms8);
 /* The tracker / updater handles the pipeline owns (for the debug getters above). */
 rvio_tracker* rvio_vio_tracker(rvio_vio* vio);
 rvio_updater* rvio_vio_updater(rvio_vio* vio);

@@ -805,7 +805,8 @@ struct SolveSmallParams {
     const double* red;        // [G | z | counters]
     const double* x; const double* P; int xdim, N, d;
     double sig2;
-    double* M; double* R;     // n x n, n x (d+1) row-major (global scratch)
+    double* T;                // [M | z | W] TRANSPOSED: column c of the n x (n + d + 1) system at T[c * n .. c * n + n)
+    double* Yt;               // solution, transposed: Yt[c * n + k] = Y(k, c), c = 0 (dx part) .. d
     double* dx;
     double* x_out; double* P_out; int* singular;
 };
@@ -813,10 +814,10 @@ struct SolveSmallParams {
 __global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
 {
     __shared__ double sA[16][33], sB[16][33];
-    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    const int N = Q.N, n = 6 * N, d = Q.d;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) return;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;         // tx walks the rows of G (fastest in the transposed output)
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;           // rows of G, columns of P[c,:]
     const double* G = Q.red;
     const double* Pc = Q.P + (size_t)24 * d;                          // row k of P[c,:] = P[(24+k) d + col]
@@ -831,120 +832,175 @@ __global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            const double a0 = sA[kk][2 * ty], a1 = sA[kk][2 * ty + 1];
-            const double b0 = sB[kk][2 * tx], b1 = sB[kk][2 * tx + 1];
+            const double a0 = sA[kk][2 * tx], a1 = sA[kk][2 * tx + 1];
+            const double b0 = sB[kk][2 * ty], b1 = sB[kk][2 * ty + 1];
             acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
         }
         __syncthreads();
     }
+    double* Tz = Q.T + (size_t)n * n;                                 // column n: z, columns n+1..n+d: W
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
-            const int i = i0 + 2 * ty + a, col = j0 + 2 * tx + b;
+            const int i = i0 + 2 * tx + a, col = j0 + 2 * ty + b;
             if (i < n && col < d) {
-                Q.R[(size_t)i * m + 1 + col] = acc[a][b];
-                if (col >= 24) Q.M[(size_t)i * n + (col - 24)] = acc[a][b] + ((i == col - 24) ? Q.sig2 : 0.0);
+                Tz[(size_t)(1 + col) * n + i] = acc[a][b];
+                if (col >= 24) Q.T[(size_t)(col - 24) * n + i] = acc[a][b] + ((i == col - 24) ? Q.sig2 : 0.0);
             }
         }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         const int i = i0 + threadIdx.x;
-        if (i < n) Q.R[(size_t)i * m] = Q.red[(size_t)n * n + i];
+        if (i < n) Tz[i] = Q.red[(size_t)n * n + i];
     }
 }
 
-// Gauss-Jordan on [M | R] with implicit row pivoting, operands in REGISTERS: thread (i, cb) owns row i, columns
-// 16cb..16cb+15 of [M | R] (i fastest: a warp holds 32 rows of one column block, so the pivot row is a broadcast load).
-// Step k: the owners of pivot row p publish it unscaled, the owners of column k publish the multipliers (pivot row: piv-1,
-// which turns the common update  row -= f/piv * pivot_row  into the scaling of the pivot row itself), everybody updates
-// 16 registers with 16 DFMA; the pivot of step k+1 (largest |.| of column k+1 over rows not yet used) is found during the
-// update (warp max + one packed atomicMax per warp).  Solution rows go back to R in variable order.
+// Blocked Gauss-Jordan on the augmented system [M | z | W] (n x (n + d + 1)) with implicit row pivoting, ONE CTA, operands
+// in REGISTERS: thread (i, cb) owns row i, columns 32cb..32cb+31.  The 6N serial pivot steps are grouped into panels of 8:
+//   panel phase   three warps (one row per lane) eliminate inside the 8 panel columns only, synchronising on a named
+//                 barrier: per step a REDUX max over packed keys (float32 bits of |v| | 1023 - row) picks the largest
+//                 unused row, its panel entries are broadcast through shared memory, every row updates its <= 7 remaining
+//                 panel entries and the coefficients C(row, t) of  new_row = keep * row + sum_t C(row,t) * old_pivot_row_t
+//   block update  all threads apply the 8 steps at once to their 32 columns: 8 DFMAs per element, pivot rows and C read
+//                 from shared memory (3 CTA barriers per panel instead of 2 per pivot step).
+// After the last panel row p_k holds Y(k, :) in the right-hand-side columns.
+constexpr int kGJPanel = 8, kGJCols = 32, kGJMaxRows = 96, kGJMaxCols = 192;
+
+__device__ __forceinline__ void gj_bar96() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_gj_small(SolveSmallParams Q)
+__global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 {
-    __shared__ unsigned s_key[2];                     // packed pivot key: float32 bits of |v| (top 22 bits) | (1023 - row)
-    __shared__ unsigned char s_used[96];
-    __shared__ short s_prow[96];
-    __shared__ short s_var[96];
-    __shared__ __align__(16) double s_rowk[208];      // pivot row, unscaled
-    __shared__ double s_colk[2][96];                  // column k (double buffered: column k+1 is published during step k)
-    __shared__ double s_rcp[2][96];                   // 1 / column value (the winner's entry is the pivot reciprocal)
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    __shared__ double s_pan[kGJPanel][kGJMaxRows];                    // current values of the panel columns, [t][row]
+    __shared__ double s_C[kGJPanel][kGJMaxRows];                      // coefficients of the block update, [t][row]
+    __shared__ __align__(16) double s_rows[kGJPanel][kGJMaxCols];     // old pivot rows, [t][column]
+    __shared__ __align__(16) double s_pa[kGJPanel], s_pc[kGJPanel];   // pivot row inside the panel: values, coefficients
+    __shared__ unsigned s_key[4];
+    __shared__ short s_piv[kGJPanel], s_prow[kGJMaxRows], s_var[kGJMaxRows];
+    __shared__ unsigned char s_used[kGJMaxRows];
+    __shared__ int s_sing;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = Q.N, n = 6 * N, m = Q.d + 1, ncols = n + m;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) return;
-    const int ncols = n + m;
-    const int ncb = (ncols + 15) / 16;
+    const int ncb = (ncols + kGJCols - 1) / kGJCols;
     const int i = tid % n, cb = tid / n;
     const bool active = cb < ncb;
-    const int c0 = 16 * cb;
-    double reg[16];
+    const int c0 = kGJCols * cb;
+    double reg[kGJCols];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < kGJCols; ++j) {
         const int c = c0 + j;
-        reg[j] = (active && c < ncols) ? ((c < n) ? Q.M[(size_t)i * n + c] : Q.R[(size_t)i * m + (c - n)]) : 0.0;
+        reg[j] = (active && c < ncols) ? Q.T[(size_t)c * n + i] : 0.0;
     }
-    if (tid < 96) s_used[tid] = 0;
-    if (tid == 0) { s_key[0] = 0u; s_key[1] = 0u; }
-    __syncthreads();
+    if (tid < kGJMaxRows) s_used[tid] = 0;
+    if (tid == 0) s_sing = 0;
+    for (int o = tid; o < kGJPanel * kGJMaxCols; o += THREADS) (&s_rows[0][0])[o] = 0.0;
     if (active && cb == 0) {
-        const double v = reg[0];
-        s_colk[0][i] = v;
-        s_rcp[0][i] = 1.0 / v;
-        atomicMax(&s_key[0], (__float_as_uint((float)fabs(v)) & ~1023u) | (unsigned)(1023 - i));
+#pragma unroll
+        for (int t = 0; t < kGJPanel; ++t) s_pan[t][i] = reg[t];
     }
     __syncthreads();
-    bool singular = false;
-    for (int k = 0; k < n; ++k) {
-        const unsigned key = s_key[k & 1];
-        const int p = 1023 - (int)(key & 1023u);
-        if ((key >> 10) == 0u) { singular = true; break; }                     // uniform
-        if (active && i == p) {                                                // publish the pivot row (unscaled)
+    for (int k0 = 0; k0 < n; k0 += kGJPanel) {
+        const int pw = (n - k0 < kGJPanel) ? n - k0 : kGJPanel;
+        if (tid < kGJMaxRows) {                                                  // ---- panel phase: warps 0..2, row = tid
+            const int r = tid;
+            const bool valid = r < n;
+            double a[kGJPanel], C[kGJPanel];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s_rowk[c0 + j] = reg[j];
-        }
-        if (tid == 0) { s_key[(k + 1) & 1] = 0u; s_used[p] = 1; s_prow[k] = (short)p; }
-        __syncthreads();
-        if (active) {
-            // multiplier: column value / pivot; for the pivot row itself (piv - 1) / piv, which scales it by 1/piv
-            const double cv = s_colk[k & 1][i];
-            const double f = ((i == p) ? (cv - 1.0) : cv) * s_rcp[k & 1][p];
-            const double2* rk = reinterpret_cast<const double2*>(&s_rowk[c0]);
+            for (int t = 0; t < kGJPanel; ++t) { a[t] = valid ? s_pan[t][r] : 0.0; C[t] = 0.0; }
+            bool free_r = valid && !s_used[r];
+            bool sing = false;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double2 r2 = rk[j];
-                reg[2 * j] -= f * r2.x;
-                reg[2 * j + 1] -= f * r2.y;
-            }
-        }
-        // publish column k+1 (+ reciprocals) and find its pivot among the rows not used yet
-        const int nk = k + 1;
-        const int cb_lo = (tid - lane) / n, cb_hi = (tid - lane + 31) / n;
-        if (nk < n && (nk >> 4) >= cb_lo && (nk >> 4) <= cb_hi) {
-            unsigned best = 0u;
-            if (active && cb == (nk >> 4)) {
-                const int nc = nk & 15;
-                double v = reg[0];
+            for (int t = 0; t < kGJPanel; ++t) {
+                if (t >= pw) break;                                              // uniform
+                unsigned key = free_r ? ((__float_as_uint((float)fabs(a[t])) & ~1023u) | (unsigned)(1023 - r)) : 0u;
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0) s_key[warp] = key;
+                gj_bar96();
+                const unsigned k01 = max(s_key[0], s_key[1]);
+                key = max(k01, s_key[2]);
+                if ((key >> 10) == 0u) { sing = true; break; }                   // uniform over the 96 threads
+                const int p = 1023 - (int)(key & 1023u);
+                if (r == p) {
 #pragma unroll
-                for (int j = 1; j < 16; ++j) if (j == nc) v = reg[j];
-                s_colk[nk & 1][i] = v;
-                if (!s_used[i]) {
-                    best = (__float_as_uint((float)fabs(v)) & ~1023u) | (unsigned)(1023 - i);
-                    s_rcp[nk & 1][i] = 1.0 / v;
+                    for (int u = 0; u < kGJPanel; ++u) { s_pa[u] = a[u]; s_pc[u] = C[u]; }
+                    s_piv[t] = (short)p; s_prow[k0 + t] = (short)p; s_used[r] = 1;
+                    free_r = false;
+                }
+                gj_bar96();
+                double pa[kGJPanel], pc[kGJPanel];
+#pragma unroll
+                for (int u = 0; u < kGJPanel; u += 2) {
+                    const double2 va = *reinterpret_cast<const double2*>(&s_pa[u]);
+                    const double2 vc = *reinterpret_cast<const double2*>(&s_pc[u]);
+                    pa[u] = va.x; pa[u + 1] = va.y; pc[u] = vc.x; pc[u + 1] = vc.y;
+                }
+                const double rcp = 1.0 / pa[t];
+                if (r == p) {                                                    // scale the pivot row
+#pragma unroll
+                    for (int u = 0; u < kGJPanel; ++u) {
+                        if (u > t) a[u] *= rcp;
+                        if (u < t) C[u] *= rcp;
+                    }
+                    a[t] = 1.0; C[t] = rcp;
+                } else {                                                         // eliminate column k0 + t from row r
+                    const double g = a[t] * rcp;
+#pragma unroll
+                    for (int u = 0; u < kGJPanel; ++u) {
+                        if (u > t) a[u] -= g * pa[u];
+                        if (u < t) C[u] -= g * pc[u];
+                    }
+                    a[t] = 0.0; C[t] = -g;
                 }
             }
-            best = __reduce_max_sync(0xffffffffu, best);
-            if (lane == 0 && best) atomicMax(&s_key[nk & 1], best);
+#pragma unroll
+            for (int t = 0; t < kGJPanel; ++t) s_C[t][r] = (t < pw && valid) ? C[t] : 0.0;
+            if (sing && tid == 0) s_sing = 1;
+        }
+        __syncthreads();
+        if (s_sing) break;                                                       // uniform
+        int myt = -1;
+#pragma unroll
+        for (int t = 0; t < kGJPanel; ++t) if (t < pw && s_piv[t] == i) myt = t;
+        const bool live = active && cb >= (k0 >> 5);                             // column blocks left of the panel are final
+        if (live && myt >= 0) {
+            double2* dst = reinterpret_cast<double2*>(&s_rows[myt][c0]);
+#pragma unroll
+            for (int j = 0; j < kGJCols / 2; ++j) dst[j] = make_double2(reg[2 * j], reg[2 * j + 1]);
+        }
+        __syncthreads();
+        if (live) {
+            double c[kGJPanel];
+#pragma unroll
+            for (int t = 0; t < kGJPanel; ++t) c[t] = s_C[t][i];
+            const double keep = (myt >= 0) ? 0.0 : 1.0;
+#pragma unroll
+            for (int j = 0; j < kGJCols / 2; ++j) {
+                double x0 = keep * reg[2 * j], x1 = keep * reg[2 * j + 1];
+#pragma unroll
+                for (int t = 0; t < kGJPanel; ++t) {
+                    const double2 r2 = *reinterpret_cast<const double2*>(&s_rows[t][c0 + 2 * j]);
+                    x0 += c[t] * r2.x; x1 += c[t] * r2.y;
+                }
+                reg[2 * j] = x0; reg[2 * j + 1] = x1;
+            }
+        }
+        const int nk0 = k0 + kGJPanel;
+        if (nk0 < n && active && cb == (nk0 >> 5)) {                             // stage the next panel's columns
+            const int sub = (nk0 & 31) >> 3;
+#pragma unroll
+            for (int j = 0; j < kGJCols; ++j) if ((j >> 3) == sub) s_pan[j & 7][i] = reg[j];
         }
         __syncthreads();
     }
-    if (singular) { if (tid == 0) *Q.singular = 1; return; }
+    if (s_sing) { if (tid == 0) *Q.singular = 1; return; }
     if (tid < n) s_var[s_prow[tid]] = (short)tid;
     __syncthreads();
     if (active) {
-        const int row = s_var[i];
+        const int row = s_var[i];                                                // this register row is row `row` of the solution
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < kGJCols; ++j) {
             const int c = c0 + j;
-            if (c >= n && c < ncols) Q.R[(size_t)row * m + (c - n)] = reg[j];
+            if (c >= n && c < ncols) Q.Yt[(size_t)(c - n) * n + row] = reg[j];
         }
     }
 }
@@ -955,7 +1011,7 @@ __global__ void __launch_bounds__(256) k_pout_finalize(SolveSmallParams Q)
 {
     __shared__ double sPi[16][33], sPj[16][33], sYi[16][33], sYj[16][33];
     __shared__ double s_dx[24 + 6 * 13 + 8];
-    const int N = Q.N, n = 6 * N, d = Q.d, m = d + 1;
+    const int N = Q.N, n = 6 * N, d = Q.d;
     const double* gate = Q.red + (size_t)n * n + n;
     const int tid = threadIdx.x;
     const int nb = (d + 31) / 32;
@@ -968,7 +1024,7 @@ __global__ void __launch_bounds__(256) k_pout_finalize(SolveSmallParams Q)
     const int tx = tid & 15, ty = tid >> 4;
     const int i0 = ti * 32, j0 = tj * 32;
     const double* Pc = Q.P + (size_t)24 * d;                          // Pc[k][i] = P(i, 24+k)
-    const double* Y = Q.R + 1;                                        // Y[k][j] at Q.R[k*m + 1 + j]
+    const double* Y = Q.Yt + n;                                       // Y(k, j) at Yt[(1 + j) * n + k]
     double a[2][2] = {{0, 0}, {0, 0}}, b[2][2] = {{0, 0}, {0, 0}};
     for (int k0 = 0; k0 < n; k0 += 16) {
         for (int o = tid; o < 16 * 32; o += 256) {
@@ -977,8 +1033,13 @@ __global__ void __launch_bounds__(256) k_pout_finalize(SolveSmallParams Q)
             const bool kv = k < n;
             sPi[kk][c] = (kv && i0 + c < d) ? Pc[(size_t)k * d + i0 + c] : 0.0;
             sPj[kk][c] = (kv && j0 + c < d) ? Pc[(size_t)k * d + j0 + c] : 0.0;
-            sYi[kk][c] = (kv && i0 + c < d) ? Y[(size_t)k * m + i0 + c] : 0.0;
-            sYj[kk][c] = (kv && j0 + c < d) ? Y[(size_t)k * m + j0 + c] : 0.0;
+        }
+        for (int o = tid; o < 16 * 32; o += 256) {                        // Y is stored transposed: k fastest
+            const int kk = o & 15, c = o >> 4;
+            const int k = k0 + kk;
+            const bool kv = k < n;
+            sYi[kk][c] = (kv && i0 + c < d) ? Y[(size_t)(i0 + c) * n + k] : 0.0;
+            sYj[kk][c] = (kv && j0 + c < d) ? Y[(size_t)(j0 + c) * n + k] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -1005,7 +1066,7 @@ __global__ void __launch_bounds__(256) k_pout_finalize(SolveSmallParams Q)
     // dx and the state correction (block 0)
     for (int i = tid; i < d; i += 256) {
         double acc = 0;
-        for (int k = 0; k < n; ++k) acc += Pc[(size_t)k * d + i] * Q.R[(size_t)k * m];
+        for (int k = 0; k < n; ++k) acc += Pc[(size_t)k * d + i] * Q.Yt[k];
         s_dx[i] = acc;
     }
     __syncthreads();
@@ -1046,7 +1107,7 @@ struct rvio_updater {
     double *d_x, *d_P, *d_xout, *d_Pout, *d_Pnew, *d_dx;
     uint8_t* d_types; int32_t* d_off; float2* d_xy;
     uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma; int32_t *d_fdof, *d_fc0, *d_fwc;
-    double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2;
+    double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2, *d_T, *d_Yt;
     int* d_sing; int* d_tickets;
     int groups_cap;
     // pinned
@@ -1136,7 +1197,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1);
     A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
-    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1); A(u->d_tickets, 64);
+    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1); A(u->d_tickets, 64);
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
     HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4);
@@ -1212,12 +1273,12 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
     if (N <= kSolveSmallMaxClones) {
         SolveSmallParams sp;
         sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
-        sp.M = u->d_M; sp.R = u->d_R; sp.dx = u->d_dx;
+        sp.T = u->d_T; sp.Yt = u->d_Yt; sp.dx = u->d_dx;
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
         RVIO_LAUNCH(k_wgemm, dim3(div_up(d, 32), div_up(n, 32)), 256, 0, s, sp);
-        if (n * div_up(n + d + 1, 16) <= 704) RVIO_LAUNCH(k_gj_small<704>, 1, 704, 0, s, sp);     // one thread per (row, 16-column block)
-        else RVIO_LAUNCH(k_gj_small<1024>, 1, 1024, 0, s, sp);
+        if (n * div_up(n + d + 1, kGJCols) <= 352) RVIO_LAUNCH(k_gj_block<352>, 1, 352, 0, s, sp);  // one thread per (row, 32-column block)
+        else RVIO_LAUNCH(k_gj_block<480>, 1, 480, 0, s, sp);
         const int nb = div_up(d, 32);
         RVIO_LAUNCH(k_pout_finalize, nb * nb, 256, 0, s, sp);
         RVIO_CUDA_TRY(cudaGetLastError());

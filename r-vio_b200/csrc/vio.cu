@@ -2,6 +2,7 @@
 // (reference src/rvio/System.cc:173-365) with x, P, pyramids and feature lists resident on the device.
 // Host side keeps only what is inherently serial and tiny: the motion-detection / initialisation logic
 // (System.cc:183-249, System::initialize :115-170) and the clone counters.
+#include <time.h>
 #include "common.cuh"
 #include "tracker_kernels.cuh"
 #include "filter_kernels.cuh"
@@ -265,6 +266,8 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     RVIO_CUDA_TRY(cudaSetDevice(v->device));
     if (n_imu < 2) return RVIO_OK;                          // InputBuffer.cc:76-77
     cudaStream_t s = v->stream;
+    timespec h0, h1, h2;
+    clock_gettime(CLOCK_MONOTONIC, &h0);
     if (!v->ready) {
         const int used = init_step(v, imu, n_imu);
         if (used < 0) return RVIO_OK;
@@ -376,8 +379,12 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_side_done, 0));
     }
     RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+    clock_gettime(CLOCK_MONOTONIC, &h1);
     int r3 = tracker_sync(v->trk);                          // publishes tracker counters + synchronises the stream
     if (r3 != RVIO_OK) return r3;
+    clock_gettime(CLOCK_MONOTONIC, &h2);
+    v->tl_ms[6] = (float)((h1.tv_sec - h0.tv_sec) * 1e3 + (h1.tv_nsec - h0.tv_nsec) * 1e-6);   // host: enqueue
+    v->tl_ms[7] = (float)((h2.tv_sec - h1.tv_sec) * 1e3 + (h2.tv_nsec - h1.tv_nsec) * 1e-6);   // host: blocked in the sync
     if (v->timeline) {
         cudaEventRecord(v->tl[6], s);
         cudaEventSynchronize(v->tl[6]);
@@ -441,10 +448,10 @@ extern "C" rvio_updater* rvio_vio_updater(rvio_vio* v) { return v ? v->upd : nul
 
 // Debug: per-stage CUDA-event times of the main stream for the last step (ms): [tracker, per-feature+normal terms,
 // wait for propagation, solve, augment+compose, tail].  enable = 1 switches the instrumentation on.
-extern "C" int rvio_vio_timeline(rvio_vio* v, int enable, float* ms6)
+extern "C" int rvio_vio_timeline(rvio_vio* v, int enable, float* ms8)
 {
     RVIO_ARG_CHECK(v);
     v->timeline = enable != 0;
-    if (ms6) for (int k = 0; k < 6; ++k) ms6[k] = v->tl_ms[k];
+    if (ms8) for (int k = 0; k < 8; ++k) ms8[k] = v->tl_ms[k];
     return RVIO_OK;
 }

@@ -19,6 +19,8 @@ def launches(src, dst):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
         k = row["Kernel Name"].split("(")[0]
+        if k.startswith("void "):
+            k = k[5:]
         v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
         v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
         a = agg.setdefault(k, [0, 0.0, []]); a[0] += 1; a[1] += v; a[2].append(v)
@@ -75,7 +77,60 @@ def full(src, dst):
     open(dst, "w").write("\n".join(out) + "\n")
 
 
+def _f(x):
+    try:
+        return float(x.replace(',', ''))
+    except ValueError:
+        return 0.0
+
+
+def source(src, dst, top=12):
+    """Hot source lines per kernel (warp-stall samples, executed warp instructions, dominant stall reason) from an
+    --import-source capture; SASS rows of the source page are aggregated per CUDA-C line."""
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    names = []
+    for r in rows[2:]:
+        k = r[rows[0].index("Kernel Name")].split("(")[0].replace("void ", "")
+        if k not in names:
+            names.append(k)
+    out = [f"# ncu source page: `{src}` (hot CUDA-C lines; share of warp-stall samples / of executed warp instructions)", ""]
+    for k in names:
+        pat = k.split("<")[0]
+        txt = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", f"regex:{pat}"],
+                             capture_output=True, text=True).stdout
+        agg, hdr, fname = {}, None, "?"
+        for r in csv.reader(txt.splitlines()):
+            if not r:
+                continue
+            if r[0] == "File Name":
+                fname = r[1].split("/")[-1]; continue
+            if r[0] == "Line No":
+                hdr = r; continue
+            if hdr is None or len(r) < len(hdr):
+                continue
+            try:
+                ln = int(r[0])
+            except ValueError:
+                continue
+            i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")
+            st = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+            a = agg.setdefault((fname, ln), [r[1].strip(), 0.0, 0.0, collections.Counter()])
+            a[1] += _f(r[i_s]); a[2] += _f(r[i_i])
+            for i in st:
+                a[3][hdr[i]] += _f(r[i])
+        tot = sum(v[1] for v in agg.values()) or 1.0
+        toti = sum(v[2] for v in agg.values()) or 1.0
+        out += [f"## `{k}`", "", f"{int(tot)} samples, {int(toti)} warp instructions", "",
+                "| file:line | samples % | instr % | top stall | source |", "|---|---|---|---|---|"]
+        for (fn, ln), (text, smp, ins, stl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+            ts = stl.most_common(1)[0][0] if stl else ""
+            out.append(f"| {fn}:{ln} | {100 * smp / tot:.1f} | {100 * ins / toti:.1f} | {ts} | `{text[:100].replace('|', '/')}` |")
+        out.append("")
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
-    (launches if mode == "launches" else full)(src, dst)
+    {"launches": launches, "full": full, "source": source}[mode](src, dst)
     print("wrote", dst)
