@@ -854,26 +854,41 @@ __global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
 }
 
 // Blocked Gauss-Jordan on the augmented system [M | z | W] (n x (n + d + 1)) with implicit row pivoting, ONE CTA, operands
-// in REGISTERS: thread (i, cb) owns row i, columns 32cb..32cb+31.  The 6N serial pivot steps are grouped into panels of 8:
-//   panel phase   three warps (one row per lane) eliminate inside the 8 panel columns only, synchronising on a named
-//                 barrier: per step a REDUX max over packed keys (float32 bits of |v| | 1023 - row) picks the largest
-//                 unused row, its panel entries are broadcast through shared memory, every row updates its <= 7 remaining
-//                 panel entries and the coefficients C(row, t) of  new_row = keep * row + sum_t C(row,t) * old_pivot_row_t
-//   block update  all threads apply the 8 steps at once to their 32 columns: 8 DFMAs per element, pivot rows and C read
-//                 from shared memory (3 CTA barriers per panel instead of 2 per pivot step).
+// in REGISTERS: thread (g, cb) owns the 4 x 8 tile rows 4g..4g+3, columns 8cb..8cb+7.  The 6N serial pivot steps are
+// grouped into panels of 8 (= one column block):
+//   panel phase   three warps (one row per lane) eliminate inside the 8 panel columns only, ONE named barrier per step:
+//                 a REDUX max over packed keys (high word of |v| | 1023 - row) gives each warp's best unused row, whose
+//                 lane publishes its panel entries, coefficients and pivot reciprocal speculatively; after the barrier
+//                 every row reads the three keys, takes the winner's record, updates its <= 7 remaining panel entries and
+//                 the coefficients C(row, t) of   new_row = keep * row + sum_t C(row, t) * old_pivot_row_t
+//   block update  all threads apply the 8 steps at once to their tile: 8 DFMAs per element, pivot rows and C read from
+//                 shared memory as 128-bit words (3 CTA barriers per panel instead of 2 per pivot step).
 // After the last panel row p_k holds Y(k, :) in the right-hand-side columns.
-constexpr int kGJPanel = 8, kGJCols = 32, kGJMaxRows = 96, kGJMaxCols = 192;
+constexpr int kGJPanel = 8, kGJMaxRows = 96, kGJMaxCols = 192;
 
 __device__ __forceinline__ void gj_bar96() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+
+// 1 / v to double precision from the float32 reciprocal and two Newton steps (|v| is inside the float32 range: the
+// pivot keys already assume that).
+__device__ __forceinline__ double gj_rcp(double v)
+{
+    const double av = fabs(v);
+    if (!(av > 1e-30 && av < 1e30)) return 1.0 / v;
+    double r = (double)__frcp_rn((float)v);
+    double e = fma(-v, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-v, r, 1.0);
+    return fma(r, e, r);
+}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 {
-    __shared__ double s_pan[kGJPanel][kGJMaxRows];                    // current values of the panel columns, [t][row]
-    __shared__ double s_C[kGJPanel][kGJMaxRows];                      // coefficients of the block update, [t][row]
+    __shared__ __align__(16) double s_pan[kGJPanel][kGJMaxRows];      // current values of the panel columns, [t][row]
+    __shared__ __align__(16) double s_C[kGJPanel][kGJMaxRows];        // coefficients of the block update, [t][row]
     __shared__ __align__(16) double s_rows[kGJPanel][kGJMaxCols];     // old pivot rows, [t][column]
-    __shared__ __align__(16) double s_pa[kGJPanel], s_pc[kGJPanel];   // pivot row inside the panel: values, coefficients
-    __shared__ unsigned s_key[4];
+    __shared__ __align__(16) double s_cand[2][3][18];                 // per step parity, per warp: a[8], C[8], 1/pivot
+    __shared__ unsigned s_key[2][4];
     __shared__ short s_piv[kGJPanel], s_prow[kGJMaxRows], s_var[kGJMaxRows];
     __shared__ unsigned char s_used[kGJMaxRows];
     __shared__ int s_sing;
@@ -881,22 +896,26 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
     const int N = Q.N, n = 6 * N, m = Q.d + 1, ncols = n + m;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) return;
-    const int ncb = (ncols + kGJCols - 1) / kGJCols;
-    const int i = tid % n, cb = tid / n;
+    const int ng = (n + 3) >> 2, ncb = (ncols + 7) >> 3;
+    const int g = tid % ng, cb = tid / ng;
     const bool active = cb < ncb;
-    const int c0 = kGJCols * cb;
-    double reg[kGJCols];
+    const int r0 = 4 * g, c0 = 8 * cb;
+    double reg[4][8];
 #pragma unroll
-    for (int j = 0; j < kGJCols; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        reg[j] = (active && c < ncols) ? Q.T[(size_t)c * n + i] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) reg[r][j] = (active && c < ncols && r0 + r < n) ? Q.T[(size_t)c * n + r0 + r] : 0.0;
     }
     if (tid < kGJMaxRows) s_used[tid] = 0;
     if (tid == 0) s_sing = 0;
     for (int o = tid; o < kGJPanel * kGJMaxCols; o += THREADS) (&s_rows[0][0])[o] = 0.0;
     if (active && cb == 0) {
 #pragma unroll
-        for (int t = 0; t < kGJPanel; ++t) s_pan[t][i] = reg[t];
+        for (int t = 0; t < kGJPanel; ++t) {
+            *reinterpret_cast<double2*>(&s_pan[t][r0]) = make_double2(reg[0][t], reg[1][t]);
+            *reinterpret_cast<double2*>(&s_pan[t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
+        }
     }
     __syncthreads();
     for (int k0 = 0; k0 < n; k0 += kGJPanel) {
@@ -912,29 +931,30 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 #pragma unroll
             for (int t = 0; t < kGJPanel; ++t) {
                 if (t >= pw) break;                                              // uniform
-                unsigned key = free_r ? ((__float_as_uint((float)fabs(a[t])) & ~1023u) | (unsigned)(1023 - r)) : 0u;
-                key = __reduce_max_sync(0xffffffffu, key);
-                if (lane == 0) s_key[warp] = key;
-                gj_bar96();
-                const unsigned k01 = max(s_key[0], s_key[1]);
-                key = max(k01, s_key[2]);
-                if ((key >> 10) == 0u) { sing = true; break; }                   // uniform over the 96 threads
-                const int p = 1023 - (int)(key & 1023u);
-                if (r == p) {
+                const int par = t & 1;
+                const unsigned key = free_r ? (((unsigned)__double2hiint(fabs(a[t])) & ~1023u) | (unsigned)(1023 - r)) : 0u;   // exponent + 10 mantissa bits | row
+                const double my_rcp = gj_rcp(free_r ? a[t] : 1.0);                 // only a free row can become the pivot
+                const unsigned wkey = __reduce_max_sync(0xffffffffu, key);
+                if (key == wkey && (wkey >> 10) != 0u) {                         // this warp's candidate (keys are unique)
+                    double2* dst = reinterpret_cast<double2*>(&s_cand[par][warp][0]);
 #pragma unroll
-                    for (int u = 0; u < kGJPanel; ++u) { s_pa[u] = a[u]; s_pc[u] = C[u]; }
-                    s_piv[t] = (short)p; s_prow[k0 + t] = (short)p; s_used[r] = 1;
-                    free_r = false;
+                    for (int u = 0; u < 4; ++u) { dst[u] = make_double2(a[2 * u], a[2 * u + 1]); dst[4 + u] = make_double2(C[2 * u], C[2 * u + 1]); }
+                    s_cand[par][warp][16] = my_rcp;
                 }
+                if (lane == 0) s_key[par][warp] = wkey;
                 gj_bar96();
+                const unsigned k01 = max(s_key[par][0], s_key[par][1]);
+                const unsigned best = max(k01, s_key[par][2]);
+                if ((best >> 10) == 0u) { sing = true; break; }                  // uniform over the 96 threads
+                const int p = 1023 - (int)(best & 1023u);
+                const double2* src = reinterpret_cast<const double2*>(&s_cand[par][p >> 5][0]);
                 double pa[kGJPanel], pc[kGJPanel];
 #pragma unroll
-                for (int u = 0; u < kGJPanel; u += 2) {
-                    const double2 va = *reinterpret_cast<const double2*>(&s_pa[u]);
-                    const double2 vc = *reinterpret_cast<const double2*>(&s_pc[u]);
-                    pa[u] = va.x; pa[u + 1] = va.y; pc[u] = vc.x; pc[u + 1] = vc.y;
+                for (int u = 0; u < 4; ++u) {
+                    const double2 va = src[u], vc = src[4 + u];
+                    pa[2 * u] = va.x; pa[2 * u + 1] = va.y; pc[2 * u] = vc.x; pc[2 * u + 1] = vc.y;
                 }
-                const double rcp = 1.0 / pa[t];
+                const double rcp = s_cand[par][p >> 5][16];
                 if (r == p) {                                                    // scale the pivot row
 #pragma unroll
                     for (int u = 0; u < kGJPanel; ++u) {
@@ -942,14 +962,16 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
                         if (u < t) C[u] *= rcp;
                     }
                     a[t] = 1.0; C[t] = rcp;
+                    s_piv[t] = (short)p; s_prow[k0 + t] = (short)p; s_used[r] = 1;
+                    free_r = false;
                 } else {                                                         // eliminate column k0 + t from row r
-                    const double g = a[t] * rcp;
+                    const double f = a[t] * rcp;
 #pragma unroll
                     for (int u = 0; u < kGJPanel; ++u) {
-                        if (u > t) a[u] -= g * pa[u];
-                        if (u < t) C[u] -= g * pc[u];
+                        if (u > t) a[u] -= f * pa[u];
+                        if (u < t) C[u] -= f * pc[u];
                     }
-                    a[t] = 0.0; C[t] = -g;
+                    a[t] = 0.0; C[t] = -f;
                 }
             }
 #pragma unroll
@@ -958,37 +980,53 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
         }
         __syncthreads();
         if (s_sing) break;                                                       // uniform
-        int myt = -1;
+        int myt[4] = {-1, -1, -1, -1};
 #pragma unroll
-        for (int t = 0; t < kGJPanel; ++t) if (t < pw && s_piv[t] == i) myt = t;
-        const bool live = active && cb >= (k0 >> 5);                             // column blocks left of the panel are final
-        if (live && myt >= 0) {
-            double2* dst = reinterpret_cast<double2*>(&s_rows[myt][c0]);
+        for (int t = 0; t < kGJPanel; ++t) {
+            const int pr = (t < pw) ? s_piv[t] - r0 : -1;
 #pragma unroll
-            for (int j = 0; j < kGJCols / 2; ++j) dst[j] = make_double2(reg[2 * j], reg[2 * j + 1]);
+            for (int r = 0; r < 4; ++r) if (pr == r) myt[r] = t;
+        }
+        const bool live = active && (cb > (k0 >> 3) || (cb == (k0 >> 3) && pw < kGJPanel));   // left of the panel: final (a short last panel shares its block with right-hand-side columns)
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (myt[r] >= 0) {
+                    double2* dst = reinterpret_cast<double2*>(&s_rows[myt[r]][c0]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_double2(reg[r][2 * j], reg[r][2 * j + 1]);
+                }
         }
         __syncthreads();
         if (live) {
-            double c[kGJPanel];
 #pragma unroll
-            for (int t = 0; t < kGJPanel; ++t) c[t] = s_C[t][i];
-            const double keep = (myt >= 0) ? 0.0 : 1.0;
+            for (int r = 0; r < 4; ++r)
+                if (myt[r] >= 0) {
 #pragma unroll
-            for (int j = 0; j < kGJCols / 2; ++j) {
-                double x0 = keep * reg[2 * j], x1 = keep * reg[2 * j + 1];
-#pragma unroll
-                for (int t = 0; t < kGJPanel; ++t) {
-                    const double2 r2 = *reinterpret_cast<const double2*>(&s_rows[t][c0 + 2 * j]);
-                    x0 += c[t] * r2.x; x1 += c[t] * r2.y;
+                    for (int j = 0; j < 8; ++j) reg[r][j] = 0.0;
                 }
-                reg[2 * j] = x0; reg[2 * j + 1] = x1;
+#pragma unroll
+            for (int t = 0; t < kGJPanel; ++t) {
+                double row[8], cc[4];
+                const double2* rs = reinterpret_cast<const double2*>(&s_rows[t][c0]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const double2 v2 = rs[j]; row[2 * j] = v2.x; row[2 * j + 1] = v2.y; }
+                const double2 c01 = *reinterpret_cast<const double2*>(&s_C[t][r0]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&s_C[t][r0 + 2]);
+                cc[0] = c01.x; cc[1] = c01.y; cc[2] = c23.x; cc[3] = c23.y;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) reg[r][j] += cc[r] * row[j];
             }
         }
         const int nk0 = k0 + kGJPanel;
-        if (nk0 < n && active && cb == (nk0 >> 5)) {                             // stage the next panel's columns
-            const int sub = (nk0 & 31) >> 3;
+        if (nk0 < n && active && cb == (nk0 >> 3)) {                             // stage the next panel's columns
 #pragma unroll
-            for (int j = 0; j < kGJCols; ++j) if ((j >> 3) == sub) s_pan[j & 7][i] = reg[j];
+            for (int t = 0; t < kGJPanel; ++t) {
+                *reinterpret_cast<double2*>(&s_pan[t][r0]) = make_double2(reg[0][t], reg[1][t]);
+                *reinterpret_cast<double2*>(&s_pan[t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
+            }
         }
         __syncthreads();
     }
@@ -996,11 +1034,15 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
     if (tid < n) s_var[s_prow[tid]] = (short)tid;
     __syncthreads();
     if (active) {
-        const int row = s_var[i];                                                // this register row is row `row` of the solution
 #pragma unroll
-        for (int j = 0; j < kGJCols; ++j) {
-            const int c = c0 + j;
-            if (c >= n && c < ncols) Q.Yt[(size_t)(c - n) * n + row] = reg[j];
+        for (int r = 0; r < 4; ++r) {
+            if (r0 + r >= n) continue;
+            const int row = s_var[r0 + r];                                       // this register row is row `row` of the solution
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                if (c >= n && c < ncols) Q.Yt[(size_t)(c - n) * n + row] = reg[r][j];
+            }
         }
     }
 }
@@ -1277,7 +1319,7 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
         RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
         RVIO_LAUNCH(k_wgemm, dim3(div_up(d, 32), div_up(n, 32)), 256, 0, s, sp);
-        if (n * div_up(n + d + 1, kGJCols) <= 352) RVIO_LAUNCH(k_gj_block<352>, 1, 352, 0, s, sp);  // one thread per (row, 32-column block)
+        if (div_up(n, 4) * div_up(n + d + 1, 8) <= 352) RVIO_LAUNCH(k_gj_block<352>, 1, 352, 0, s, sp);   // one thread per 4 x 8 tile
         else RVIO_LAUNCH(k_gj_block<480>, 1, 480, 0, s, sp);
         const int nb = div_up(d, 32);
         RVIO_LAUNCH(k_pout_finalize, nb * nb, 256, 0, s, sp);

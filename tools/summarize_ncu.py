@@ -84,7 +84,7 @@ def _f(x):
         return 0.0
 
 
-def source(src, dst, top=12):
+def source(src, dst, top=22):
     """Hot source lines per kernel (warp-stall samples, executed warp instructions, dominant stall reason) from an
     --import-source capture; SASS rows of the source page are aggregated per CUDA-C line."""
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
