@@ -191,6 +191,10 @@ int rvio_vio_get_update_info(rvio_vio* vio, rvio_update_info* info);
  * wait for propagation, solve, augment + compose, tail], then two host wall-clock times of the same step: [enqueue of
  * the whole frame, blocked in the one synchronisation]; enable != 0 switches the event instrumentation on. */
 int rvio_vio_timeline(rvio_vio* vio, int enable, float* ms8);
+/* Steady-state frames are replayed as CUDA graphs (one graph per ping-pong parity / input mode). enable: 1 on (default),
+ * 0 off (every frame is enqueued operation by operation), negative: leave unchanged; *graph_launches (optional) receives
+ * the number of frames replayed so far. */
+int rvio_vio_graphs(rvio_vio* vio, int enable, uint64_t* graph_launches);
 /* The tracker / updater handles the pipeline owns (for the debug getters above). */
 rvio_tracker* rvio_vio_tracker(rvio_vio* vio);
 rvio_updater* rvio_vio_updater(rvio_vio* vio);

@@ -12,6 +12,7 @@ thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_kernel_launches{0};
 
 std::atomic<int> g_profile_on{0};
+thread_local bool t_replay = false;
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;

@@ -39,15 +39,26 @@ extern std::atomic<int> g_profile_on;
 void profile_begin(const char* name, cudaStream_t s);
 void profile_end(cudaStream_t s);
 
+// Frame-graph replay (vio.cu): the per-frame enqueue code runs once under stream capture to build a CUDA graph; on later
+// frames with the same signature it runs again with t_replay set, which turns every stream operation (RVIO_LAUNCH,
+// RVIO_ENQ) into a no-op so that only the host-side state advances, and the instantiated graph is launched instead.
+extern thread_local bool t_replay;
+
+#define RVIO_ENQ(expr)                                                                  \
+    do {                                                                                \
+        if (!rvio::t_replay) RVIO_CUDA_TRY(expr);                                       \
+    } while (0)
+
 // Counts every kernel this library launches (bench.py reports it as gpu_launches); with profiling enabled
 // (rvio_b200_profile) each launch is bracketed by CUDA events on its own stream.
 #define RVIO_LAUNCH(kernel, grid, block, smem, stream, ...)                             \
     do {                                                                                \
+        rvio::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                \
+        if (rvio::t_replay) break;                                                      \
         const bool _prof = rvio::g_profile_on.load(std::memory_order_relaxed) != 0;     \
         if (_prof) rvio::profile_begin(#kernel, (stream));                              \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
         if (_prof) rvio::profile_end((stream));                                         \
-        rvio::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                \
     } while (0)
 
 // Verifies that `device` is a usable sm_100 part; the product has no other path.

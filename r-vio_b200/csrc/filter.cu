@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(576) k_propagate(PropagateParams Q)
                            Q.c.sigma_a * Q.c.sigma_a, Q.c.sigma_a * Q.c.sigma_a, Q.c.sigma_a * Q.c.sigma_a,
                            Q.c.sigma_wa * Q.c.sigma_wa, Q.c.sigma_wa * Q.c.sigma_wa, Q.c.sigma_wa * Q.c.sigma_wa};
     __shared__ double s_w[3], s_a[3];
-    for (int s = 0; s < Q.n_imu; ++s) {
+    const int n_imu = Q.hdr ? Q.hdr[0] : Q.n_imu;
+    for (int s = 0; s < n_imu; ++s) {
         if (tid == 0) {
             const double* wm = Q.imu + 8 * s;
             const double* am = wm + 3;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
     TrackerBuffers& B = Q.B;
     TrackerScalars* sc = B.sc;
     const int n_ref = sc->n_new;
-    const int nc = Q.n_cand;
+    const int nc = Q.hdr ? min(Q.hdr[1], Q.n_cand) : Q.n_cand;
     for (int k = tid; k < nc; k += 1024) s_acc[k] = 0;
     __syncthreads();
     const int n_cells = Q.gc * Q.gr;
@@ -478,19 +479,19 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
 int launch_propagate(cudaStream_t s, const PropagateParams& p)
 {
     RVIO_LAUNCH(k_propagate, 1, 576, 0, s, p);
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 int launch_augment_compose(cudaStream_t s, const AugmentParams& p)
 {
     RVIO_LAUNCH(k_augment_compose, 1, 576, 0, s, p);
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 int launch_find_newer_refill(cudaStream_t s, const FindNewerParams& p)
 {
     RVIO_LAUNCH(k_find_newer_refill, 1, 1024, (size_t)(p.n_cand + 16), s, p);
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 

@@ -10,6 +10,7 @@ struct ImuConsts { double gravity, small_angle, sigma_g, sigma_wg, sigma_a, sigm
 struct PropagateParams {
     const double* x_in; const double* P_in; int xdim, d;
     const double* imu; int n_imu;         // device, n_imu x 8
+    const int* hdr;                        // optional device frame header {n_imu, n_cand}: overrides n_imu (frame graphs)
     double* x_out; double* P_out;
     ImuConsts c;
 };
@@ -25,7 +26,8 @@ constexpr int kFindNewerCellCap = 128;
 
 struct FindNewerParams {
     TrackerBuffers B;
-    const float2* cand; int n_cand;        // detector output (device)
+    const float2* cand; int n_cand;        // detector output (device); n_cand is the capacity when hdr is set
+    const int* hdr;                        // optional device frame header {n_imu, n_cand}
     int raw;                               // 1: candidates are already FindNewer-filtered
     int W, H, gc, gr, offx, offy, max_per_block;
     float bx, by, min_dist;

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(256) k_pyr_down(PyrLevel src, PyrLevel dst)
 struct LKParams {
     Pyramid prev, cur;
     const float2* feats;
-    int n;
+    int n;                // number of features to track (upper bound when n_dev is set)
+    const int* n_dev;     // optional: the count lives on the device (fused pipeline / frame graphs)
     float2* out;
     uint8_t* status;
     float2* un;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
     __shared__ LKWarpSmem smem_all[kLKWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pt = blockIdx.x * kLKWarps + wib;
-    if (pt >= P.n) return;                       // whole warp exits together
+    if (pt >= (P.n_dev ? *P.n_dev : P.n)) return;   // whole warp exits together
     LKWarpSmem& S = smem_all[wib];
     const unsigned FULL = 0xffffffffu;
     // pixel ownership
@@ -530,12 +531,11 @@ __device__ __forceinline__ int glibc_rand_next(TrackerScalars* sc)
 
 struct RansacParams {
     TrackerBuffers B;
-    const double* imu;      // n_imu x 8
-    int n_imu;
-    int n;                  // features fed to LK
+    int n;                  // features fed to LK (ignored when n_dev is set)
+    const int* n_dev;
     int use_sampson;
     double thr, small_angle;
-    double R[9];            // Rci * prod(dR_k) * Ric, Ransac.cc:120-155 (host, libm sin/cos as the reference)
+    const double* R;        // device, 9 doubles: Rci * prod(dR_k) * Ric, Ransac.cc:120-155 (evaluated on the host with libm)
 };
 
 __device__ __forceinline__ void m3mul(const double* A, const double* B, double* C)
@@ -557,7 +557,7 @@ __device__ __forceinline__ double epi_dist(const double* E, double x1, double y1
     return (num * num) / (Fx10 * Fx10 + Fx11 * Fx11 + Fx20 * Fx20 + Fx21 * Fx21);
 }
 
-__device__ __forceinline__ void ransac_body(const RansacParams& P)
+__device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
 {
     __shared__ int sh[34];
     __shared__ double sR[9];
@@ -568,7 +568,6 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P)
     const int tid = threadIdx.x;
     const TrackerBuffers& B = P.B;
     TrackerScalars* sc = B.sc;
-    const int n = P.n;
 
     // flags start as the LK status (Tracker.cc:264 passes vInlierFlag in/out)
     for (int i = tid; i < n; i += 256) B.flags[i] = B.status[i];
@@ -603,7 +602,7 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P)
             B.two_points[2 * it + 1] = B.cand[b];
             s_used[a >> 5] |= 1u << (a & 31); s_used[b >> 5] |= 1u << (b & 31);
         }
-        for (int i = 0; i < 9; ++i) sR[i] = P.R[i];        // GetRotation: computed on the host (see tracker_enqueue)
+        for (int i = 0; i < 9; ++i) sR[i] = P.R[i];        // GetRotation: evaluated on the host, uploaded per frame (see tracker_enqueue)
         sc->ransac_ran = 1;
     }
     __syncthreads();
@@ -771,10 +770,11 @@ __device__ __forceinline__ void bookkeep_body(const TrackerBuffers& B, int n)
 // RANSAC followed by the bookkeeping in ONE single-CTA launch (Tracker.cc:264-342).
 __global__ void __launch_bounds__(256) k_ransac_bookkeep(RansacParams P)
 {
-    ransac_body(P);
+    const int n = P.n_dev ? *P.n_dev : P.n;       // read before anything below rewrites the scalars
+    ransac_body(P, n);
     __syncthreads();
     __threadfence_block();
-    bookkeep_body(P.B, P.n);
+    bookkeep_body(P.B, n);
 }
 
 // First image (Tracker.cc:215-233): slot i <- corner i, free list = n..F-1.
@@ -854,11 +854,11 @@ struct rvio_tracker {
     Pyramid pyr[2];             // [cur_idx] = current, [1-cur_idx] = previous
     int cur_idx;
     TrackerBuffers B;
-    double* d_imu; int imu_cap;
+    double* d_R; int imu_cap;   // RANSAC rotation of the frame (9 doubles)
     float2* d_px_in;            // seed/refill staging
     // pinned host staging
     uint8_t* h_img; size_t h_img_bytes;
-    double* h_imu;
+    double* h_R;
     float* h_px;
     TrackerScalars* h_sc;
     // CLAHE constants
@@ -913,7 +913,7 @@ int build_pyramid_layout(rvio_tracker* t, int which)
 
 int sync_scalars(rvio_tracker* t)
 {
-    RVIO_CUDA_TRY(cudaMemcpyAsync(t->h_sc, t->B.sc, sizeof(TrackerScalars), cudaMemcpyDeviceToHost, t->stream));
+    RVIO_ENQ(cudaMemcpyAsync(t->h_sc, t->B.sc, sizeof(TrackerScalars), cudaMemcpyDeviceToHost, t->stream));
     RVIO_CUDA_TRY(cudaStreamSynchronize(t->stream));
     return RVIO_OK;
 }
@@ -972,12 +972,12 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     A(B.up_types, (size_t)t->Fu + 1); A(B.up_off, (size_t)t->Fu + 2); A(B.up_xy, ((size_t)t->Fu + 1) * t->Lmax);
     A(B.cand, 2 * F); A(B.two_points, 32); A(B.n_inliers, 16); A(B.hyp, 16 * 9); A(B.sc, 1);
     t->imu_cap = 512;
-    A(t->d_imu, (size_t)t->imu_cap * 8);
+    A(t->d_R, 16);
     A(t->d_px_in, F);
 #undef A
     t->h_img_bytes = (size_t)t->W * t->H * 4;
     RVIO_CUDA_TRY(cudaMallocHost((void**)&t->h_img, t->h_img_bytes));
-    RVIO_CUDA_TRY(cudaMallocHost((void**)&t->h_imu, sizeof(double) * 8 * t->imu_cap));
+    RVIO_CUDA_TRY(cudaMallocHost((void**)&t->h_R, sizeof(double) * 16));
     RVIO_CUDA_TRY(cudaMallocHost((void**)&t->h_px, sizeof(float) * 2 * F));
     RVIO_CUDA_TRY(cudaMallocHost((void**)&t->h_sc, sizeof(TrackerScalars)));
     // glibc rand() never seeded == srand(1): build the state on the host (random_r.c) and upload
@@ -1012,7 +1012,7 @@ extern "C" void rvio_tracker_destroy(rvio_tracker* t)
     cudaSetDevice(t->device);
     cudaStreamSynchronize(t->stream);
     for (void* p : t->allocs) cudaFree(p);
-    cudaFreeHost(t->h_img); cudaFreeHost(t->h_imu); cudaFreeHost(t->h_px); cudaFreeHost(t->h_sc);
+    cudaFreeHost(t->h_img); cudaFreeHost(t->h_R); cudaFreeHost(t->h_px); cudaFreeHost(t->h_sc);
     cudaStreamDestroy(t->stream);
     delete t;
 }
@@ -1049,13 +1049,22 @@ static void host_gyro_rotation(const double* Ric, const double* imu, int n_imu, 
     mul(T, Ric, R);
 }
 
-static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu)
+// Enqueues one frame (no synchronisation).  dev_count: the number of features to track is read from the device scalars
+// (sc->n_new of the previous frame) instead of the host mirror, which makes the launch parameters frame-invariant (the
+// fused pipeline replays this sequence as a CUDA graph).
+static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu, bool dev_count = false)
 {
     RVIO_ARG_CHECK(n_imu >= 0 && n_imu <= t->imu_cap);
     cudaStream_t s = t->stream;
     const Pyramid& cur = t->pyr[t->cur_idx];
     const Pyramid& prev = t->pyr[1 - t->cur_idx];
     const dim3 blk(256), grd(div_up(t->W, 256), t->H);
+    const bool will_track = !t->first && t->n_track > 0;
+    if (will_track) {
+        // Ransac::GetRotation on the host (libm), uploaded ahead of the image kernels so that it is off the critical path
+        host_gyro_rotation(t->Ric, imu, n_imu, t->cfg.small_angle, t->h_R);
+        RVIO_ENQ(cudaMemcpyAsync(t->d_R, t->h_R, sizeof(double) * 9, cudaMemcpyHostToDevice, s));
+    }
     // Tracker.cc:198-202
     if (t->cfg.enable_equalizer) {
         RVIO_LAUNCH(k_clahe_lut, 25, 1024, 0, s, gray_dev, gray_pitch, t->W, t->H, t->tw, t->th, t->clip, t->lut_scale, t->d_lut);
@@ -1068,25 +1077,22 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
         RVIO_LAUNCH(k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
     }
     t->frame_open = true;
-    if (t->first) { RVIO_CUDA_TRY(cudaGetLastError()); return RVIO_FIRST_IMAGE; }
+    if (t->first) { RVIO_ENQ(cudaGetLastError()); return RVIO_FIRST_IMAGE; }
     const int n = t->n_track;
     t->last_n = n;
-    if (n == 0) { t->frame_open = false; RVIO_CUDA_TRY(cudaGetLastError()); return RVIO_NO_FEATURES; }
+    if (n == 0) { t->frame_open = false; RVIO_ENQ(cudaGetLastError()); return RVIO_NO_FEATURES; }
 
-    if (n_imu > 0) {
-        (void)0;   // the IMU samples are consumed on the host (host_gyro_rotation below): nothing to upload
-    }
     LKParams lp;
-    lp.prev = prev; lp.cur = cur; lp.feats = t->B.feats; lp.n = n; lp.out = t->B.lk; lp.status = t->B.status;
+    lp.prev = prev; lp.cur = cur; lp.feats = t->B.feats; lp.out = t->B.lk; lp.status = t->B.status;
+    lp.n = dev_count ? t->F : n; lp.n_dev = dev_count ? &t->B.sc->n_new : nullptr;
     lp.un = t->B.un; lp.cam = t->cam; lp.max_iter = 30; lp.eps_sq_f = 0.f; lp.eps_sq = 1e-2 * 1e-2;
     lp.min_eig_thr = 1e-3f;
-    RVIO_LAUNCH(k_lk, div_up(n, kLKWarps), kLKWarps * 32, 0, s, lp);
+    RVIO_LAUNCH(k_lk, div_up(lp.n, kLKWarps), kLKWarps * 32, 0, s, lp);
     RansacParams rp;
-    rp.B = t->B; rp.imu = t->d_imu; rp.n_imu = n_imu; rp.n = n; rp.use_sampson = t->cfg.use_sampson;
-    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle;
-    host_gyro_rotation(t->Ric, imu, n_imu, t->cfg.small_angle, rp.R);
+    rp.B = t->B; rp.n = n; rp.n_dev = lp.n_dev; rp.use_sampson = t->cfg.use_sampson;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
     RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, s, rp);
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 
@@ -1103,9 +1109,9 @@ static int upload_image(rvio_tracker* t, const uint8_t* img, int width, int heig
     for (int y = 0; y < height; ++y) memcpy(t->h_img + (size_t)y * row, img + (size_t)y * stride_bytes, row);
     cudaStream_t s = t->stream;
     if (channels == 1) {
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_gray, t->gray_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
+        RVIO_ENQ(cudaMemcpy2DAsync(t->d_gray, t->gray_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
     } else {
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(t->d_in, t->in_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
+        RVIO_ENQ(cudaMemcpy2DAsync(t->d_in, t->in_pitch, t->h_img, row, row, height, cudaMemcpyHostToDevice, s));
         RVIO_LAUNCH(k_gray, dim3(div_up(width, 256), height), 256, 0, s, t->d_in, (int)t->in_pitch, channels,
                     t->cfg.is_rgb, t->d_gray, (int)t->gray_pitch, width, height);
     }
@@ -1295,21 +1301,40 @@ int tracker_enqueue_frame_host(rvio_tracker* t, const uint8_t* img, int w, int h
     RVIO_ARG_CHECK(t && img && w == t->W && h == t->H && (ch == 1 || ch == 3 || ch == 4) && stride >= w * ch);
     const int rc = upload_image(t, img, w, h, stride, ch);
     if (rc != RVIO_OK) return rc;
-    return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu);
+    return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu, true);
 }
 int tracker_enqueue_frame_dev(rvio_tracker* t, const uint8_t* img_dev, int pitch, const double* imu, int n_imu)
 {
-    return tracker_enqueue(t, img_dev, pitch, imu, n_imu);
+    return tracker_enqueue(t, img_dev, pitch, imu, n_imu, true);
 }
+// Frame already staged in the tracker's own gray buffer (see tracker_gray): frame-invariant launch parameters.
+int tracker_enqueue_frame_staged(rvio_tracker* t, const double* imu, int n_imu)
+{
+    return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu, true);
+}
+uint8_t* tracker_gray(rvio_tracker* t, size_t* pitch) { *pitch = t->gray_pitch; return t->d_gray; }
 int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n)
 {
     if (n > t->F) n = t->F;
     RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, px_dev, n, t->cam);
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     t->first = false;
     return RVIO_OK;
 }
 int tracker_sync(rvio_tracker* t) { return sync_scalars(t); }
+// The two halves of tracker_sync: the device->host copy of the scalars is part of the frame's stream work (replayable),
+// the wait is not.
+int tracker_enqueue_scalars(rvio_tracker* t)
+{
+    RVIO_ENQ(cudaMemcpyAsync(t->h_sc, t->B.sc, sizeof(TrackerScalars), cudaMemcpyDeviceToHost, t->stream));
+    return RVIO_OK;
+}
+int tracker_wait(rvio_tracker* t)
+{
+    RVIO_CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return RVIO_OK;
+}
+int tracker_parity(const rvio_tracker* t) { return t->cur_idx; }
 bool tracker_is_first(const rvio_tracker* t) { return t->first; }
 const CamParams* tracker_cam(const rvio_tracker* t) { return &t->cam; }
 int tracker_n_track(const rvio_tracker* t) { return t->n_track; }

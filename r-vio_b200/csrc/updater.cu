@@ -1,4 +1,5 @@
 // updater.cu -- CUDA kernels + C ABI of the MSCKF update half of the hot path (see updater_kernels.cuh).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tracker_kernels.cuh"
 #include "updater_kernels.cuh"
@@ -853,51 +854,163 @@ __global__ void __launch_bounds__(256) k_wgemm(SolveSmallParams Q)
     }
 }
 
-// Blocked Gauss-Jordan on the augmented system [M | z | W] (n x (n + d + 1)) with implicit row pivoting, ONE CTA, operands
-// in REGISTERS: thread (g, cb) owns the 4 x 8 tile rows 4g..4g+3, columns 8cb..8cb+7.  The 6N serial pivot steps are
-// grouped into panels of 8 (= one column block):
-//   panel phase   three warps (one row per lane) eliminate inside the 8 panel columns only, ONE named barrier per step:
-//                 a REDUX max over packed keys (high word of |v| | 1023 - row) gives each warp's best unused row, whose
-//                 lane publishes its panel entries, coefficients and pivot reciprocal speculatively; after the barrier
-//                 every row reads the three keys, takes the winner's record, updates its <= 7 remaining panel entries and
-//                 the coefficients C(row, t) of   new_row = keep * row + sum_t C(row, t) * old_pivot_row_t
-//   block update  all threads apply the 8 steps at once to their tile: 8 DFMAs per element, pivot rows and C read from
-//                 shared memory as 128-bit words (3 CTA barriers per panel instead of 2 per pivot step).
+// Blocked Gauss-Jordan on the augmented system [M | z | W] (n x (n + d + 1)) with implicit row pivoting, ONE CTA, warp
+// specialised.  The 6N serial pivot steps are grouped into panels of 8 (= one column block):
+//   warps 0..2 (panel group, one row per lane) hold the 8 panel columns in registers and eliminate inside the panel, one
+//                 named barrier per step: a REDUX max over packed keys (high word of |v| | 1023 - row) gives each warp's
+//                 best unused row, whose lane publishes its panel entries, coefficients and pivot reciprocal
+//                 speculatively; after the barrier every row takes the winner's record and updates its remaining panel
+//                 entries and the coefficients C(row, t) of  new_row = keep * row + sum_t C(row, t) * old_pivot_row_t.
+//                 The step loop is NOT unrolled (the current column is always register 0, entries shift down by one per
+//                 step): these kernels are instruction-fetch bound when a single warp walks through unrolled code.
+//                 The group then applies the panel to the NEXT panel's columns itself (their pre-update values were staged
+//                 in shared memory by the owning workers one panel earlier) and continues with the next panel at once:
+//                 the serial chain never waits for the block update.
+//   warps 3.. (workers)   thread (g, cb) owns the 4 x 8 register tile rows 4g..4g+3, columns 8cb..8cb+7 and applies the 8
+//                 steps of a panel at once: 8 DFMAs per element, pivot rows and C read from shared memory as 128-bit words;
+//                 they run up to one panel behind the panel group (C and the pivot list are double buffered).
 // After the last panel row p_k holds Y(k, :) in the right-hand-side columns.
-constexpr int kGJPanel = 8, kGJMaxRows = 96, kGJMaxCols = 192;
+constexpr int kGJPanel = 8, kGJMaxRows = 96, kGJMaxCols = 192, kGJPanelThreads = 96;
 
-__device__ __forceinline__ void gj_bar96() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void gj_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void gj_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// 1 / v to double precision from the float32 reciprocal and two Newton steps (|v| is inside the float32 range: the
-// pivot keys already assume that).
+// 1 / v to double precision from the approximate float32 reciprocal and two Newton steps (|v| is inside the float32
+// range for any usable pivot).
 __device__ __forceinline__ double gj_rcp(double v)
 {
-    const double av = fabs(v);
-    if (!(av > 1e-30 && av < 1e30)) return 1.0 / v;
-    double r = (double)__frcp_rn((float)v);
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)v));
+    double r = (double)r0;
     double e = fma(-v, r, 1.0);
     r = fma(r, e, r);
     e = fma(-v, r, 1.0);
     return fma(r, e, r);
 }
 
+struct GJShared {
+    double old[2][kGJPanel][kGJMaxRows];       // a column block before the previous panel is applied, [block parity][col][row]
+    double C[2][kGJPanel][kGJMaxRows];         // coefficients of the block update, [panel parity][t][row]
+    double rows[kGJPanel][kGJMaxCols];         // old pivot rows, [t][column]
+    double cand[2][3][18];                     // per step parity, per panel warp: a[8], C[8], 1/pivot
+    unsigned key[2][4];
+    short piv[2][kGJPanel];
+    short prow[kGJMaxRows], var[kGJMaxRows];
+    int sing;
+};
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 {
-    __shared__ __align__(16) double s_pan[kGJPanel][kGJMaxRows];      // current values of the panel columns, [t][row]
-    __shared__ __align__(16) double s_C[kGJPanel][kGJMaxRows];        // coefficients of the block update, [t][row]
-    __shared__ __align__(16) double s_rows[kGJPanel][kGJMaxCols];     // old pivot rows, [t][column]
-    __shared__ __align__(16) double s_cand[2][3][18];                 // per step parity, per warp: a[8], C[8], 1/pivot
-    __shared__ unsigned s_key[2][4];
-    __shared__ short s_piv[kGJPanel], s_prow[kGJMaxRows], s_var[kGJMaxRows];
-    __shared__ unsigned char s_used[kGJMaxRows];
-    __shared__ int s_sing;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(16) GJShared S;
+    constexpr int NW = THREADS - kGJPanelThreads;                     // worker threads
+    const int tid = threadIdx.x, lane = tid & 31;
     const int N = Q.N, n = 6 * N, m = Q.d + 1, ncols = n + m;
     const double* gate = Q.red + (size_t)n * n + n;
     if (!(gate[0] > 2.0)) return;
     const int ng = (n + 3) >> 2, ncb = (ncols + 7) >> 3;
-    const int g = tid % ng, cb = tid / ng;
+    const int npan = (n + kGJPanel - 1) / kGJPanel;
+    if (tid == 0) S.sing = 0;
+    for (int o = tid; o < kGJPanel * kGJMaxCols; o += THREADS) (&S.rows[0][0])[o] = 0.0;
+
+    if (tid < kGJPanelThreads) {
+        // ================================================================== panel group: row = tid
+        const int r = tid, warp = tid >> 5;
+        const bool valid = r < n;
+        bool free_r = valid;
+        __syncthreads();                                                         // blocks 0 and 1 staged by their owners
+        double a[kGJPanel], C[kGJPanel];                                         // a[0]: current column; C[0]: newest step
+#pragma unroll
+        for (int t = 0; t < kGJPanel; ++t) a[t] = valid ? S.old[0][t][r] : 0.0;
+        bool sing = false;
+#pragma unroll 1
+        for (int pi = 0; pi < npan; ++pi) {
+            const int k0 = pi * kGJPanel, buf = pi & 1;
+            const int pw = (n - k0 < kGJPanel) ? n - k0 : kGJPanel;
+#pragma unroll
+            for (int t = 0; t < kGJPanel; ++t) C[t] = 0.0;
+            bool mine = false;                                                   // row r became a pivot row in this panel
+#pragma unroll 1
+            for (int t = 0; t < pw; ++t) {
+                const int par = t & 1;
+                const unsigned key = free_r ? (((unsigned)__double2hiint(fabs(a[0])) & ~1023u) | (unsigned)(1023 - r)) : 0u;
+                double my_rcp = gj_rcp(free_r ? a[0] : 1.0);                     // started before the maximum is known
+                asm volatile("" : "+d"(my_rcp));
+                const unsigned wkey = __reduce_max_sync(0xffffffffu, key);
+                if (key == wkey && (wkey >> 10) != 0u) {                         // this warp's candidate (keys are unique)
+                    double2* dst = reinterpret_cast<double2*>(&S.cand[par][warp][0]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { dst[u] = make_double2(a[2 * u], a[2 * u + 1]); dst[4 + u] = make_double2(C[2 * u], C[2 * u + 1]); }
+                    S.cand[par][warp][16] = my_rcp;
+                }
+                if (lane == 0) S.key[par][warp] = wkey;
+                gj_bar_sync(4, kGJPanelThreads);
+                const unsigned best = max(max(S.key[par][0], S.key[par][1]), S.key[par][2]);
+                if ((best >> 10) == 0u) { sing = true; break; }                  // uniform over the panel group
+                const int p = 1023 - (int)(best & 1023u);
+                const double2* src = reinterpret_cast<const double2*>(&S.cand[par][p >> 5][0]);
+                double pa[kGJPanel], pc[kGJPanel];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2 va = src[u], vc = src[4 + u];
+                    pa[2 * u] = va.x; pa[2 * u + 1] = va.y; pc[2 * u] = vc.x; pc[2 * u + 1] = vc.y;
+                }
+                const double rcp = S.cand[par][p >> 5][16];
+                const bool is_p = r == p;
+                const double f = is_p ? 0.0 : a[0] * rcp;                        // eliminate the current column from row r
+#pragma unroll
+                for (int u = 0; u < kGJPanel - 1; ++u) a[u] = fma(-f, pa[u + 1], a[u + 1]);
+                a[kGJPanel - 1] = 0.0;
+#pragma unroll
+                for (int u = kGJPanel - 1; u > 0; --u) C[u] = fma(-f, pc[u - 1], C[u - 1]);
+                C[0] = -f;
+                if (is_p) {                                                      // the pivot row itself: scaled old values
+#pragma unroll
+                    for (int u = 0; u < kGJPanel - 1; ++u) a[u] = pa[u + 1] * rcp;
+#pragma unroll
+                    for (int u = kGJPanel - 1; u > 0; --u) C[u] = pc[u - 1] * rcp;
+                    C[0] = rcp;
+                    S.piv[buf][t] = (short)p; S.prow[k0 + t] = (short)p;
+                    free_r = false; mine = true;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kGJPanel; ++i) {                                 // C[i] belongs to step pw - 1 - i
+                const int tgt = (i < pw) ? pw - 1 - i : i;
+                S.C[buf][tgt][r] = (i < pw) ? C[i] : 0.0;
+            }
+            if (sing && tid == 0) S.sing = 1;
+            __threadfence_block();
+            gj_bar_arrive(1, THREADS);                                           // panel pi factored
+            if (sing) break;
+            if (pi + 1 < npan) {
+                // look-ahead: apply this panel to the next panel's columns (staged, pre-update) and keep them in registers
+                if (pi > 0) gj_bar_sync(3, THREADS);                             // block pi + 1 staged by its owners
+                gj_bar_sync(4, kGJPanelThreads);                                 // S.piv of this panel visible to the whole group
+                const int ob = (pi + 1) & 1;
+#pragma unroll
+                for (int j = 0; j < kGJPanel; ++j) a[j] = (valid && !mine) ? S.old[ob][j][r] : 0.0;
+#pragma unroll 1
+                for (int i = 0; i < pw; ++i) {                                   // C[i] multiplies the old pivot row of step pw - 1 - i
+                    const int pr = S.piv[buf][pw - 1 - i];
+                    double ci = 0.0;
+#pragma unroll
+                    for (int u = 0; u < kGJPanel; ++u) if (u == i) ci = C[u];
+#pragma unroll
+                    for (int j = 0; j < kGJPanel; ++j) a[j] = fma(ci, S.old[ob][j][pr], a[j]);
+                }
+            }
+        }
+        __syncthreads();
+        if (r < n) S.var[S.prow[r]] = (short)r;
+        __syncthreads();
+        if (S.sing && tid == 0) *Q.singular = 1;
+        return;
+    }
+
+    // ====================================================================== workers
+    const int w = tid - kGJPanelThreads;
+    const int g = w % ng, cb = w / ng;
     const bool active = cb < ncb;
     const int r0 = 4 * g, c0 = 8 * cb;
     double reg[4][8];
@@ -907,97 +1020,39 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 #pragma unroll
         for (int r = 0; r < 4; ++r) reg[r][j] = (active && c < ncols && r0 + r < n) ? Q.T[(size_t)c * n + r0 + r] : 0.0;
     }
-    if (tid < kGJMaxRows) s_used[tid] = 0;
-    if (tid == 0) s_sing = 0;
-    for (int o = tid; o < kGJPanel * kGJMaxCols; o += THREADS) (&s_rows[0][0])[o] = 0.0;
-    if (active && cb == 0) {
+    if (active && cb < 2) {
 #pragma unroll
         for (int t = 0; t < kGJPanel; ++t) {
-            *reinterpret_cast<double2*>(&s_pan[t][r0]) = make_double2(reg[0][t], reg[1][t]);
-            *reinterpret_cast<double2*>(&s_pan[t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
+            *reinterpret_cast<double2*>(&S.old[cb][t][r0]) = make_double2(reg[0][t], reg[1][t]);
+            *reinterpret_cast<double2*>(&S.old[cb][t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
         }
     }
     __syncthreads();
-    for (int k0 = 0; k0 < n; k0 += kGJPanel) {
+#pragma unroll 1
+    for (int pi = 0; pi < npan; ++pi) {
+        const int k0 = pi * kGJPanel, buf = pi & 1;
         const int pw = (n - k0 < kGJPanel) ? n - k0 : kGJPanel;
-        if (tid < kGJMaxRows) {                                                  // ---- panel phase: warps 0..2, row = tid
-            const int r = tid;
-            const bool valid = r < n;
-            double a[kGJPanel], C[kGJPanel];
-#pragma unroll
-            for (int t = 0; t < kGJPanel; ++t) { a[t] = valid ? s_pan[t][r] : 0.0; C[t] = 0.0; }
-            bool free_r = valid && !s_used[r];
-            bool sing = false;
-#pragma unroll
-            for (int t = 0; t < kGJPanel; ++t) {
-                if (t >= pw) break;                                              // uniform
-                const int par = t & 1;
-                const unsigned key = free_r ? (((unsigned)__double2hiint(fabs(a[t])) & ~1023u) | (unsigned)(1023 - r)) : 0u;   // exponent + 10 mantissa bits | row
-                const double my_rcp = gj_rcp(free_r ? a[t] : 1.0);                 // only a free row can become the pivot
-                const unsigned wkey = __reduce_max_sync(0xffffffffu, key);
-                if (key == wkey && (wkey >> 10) != 0u) {                         // this warp's candidate (keys are unique)
-                    double2* dst = reinterpret_cast<double2*>(&s_cand[par][warp][0]);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { dst[u] = make_double2(a[2 * u], a[2 * u + 1]); dst[4 + u] = make_double2(C[2 * u], C[2 * u + 1]); }
-                    s_cand[par][warp][16] = my_rcp;
-                }
-                if (lane == 0) s_key[par][warp] = wkey;
-                gj_bar96();
-                const unsigned k01 = max(s_key[par][0], s_key[par][1]);
-                const unsigned best = max(k01, s_key[par][2]);
-                if ((best >> 10) == 0u) { sing = true; break; }                  // uniform over the 96 threads
-                const int p = 1023 - (int)(best & 1023u);
-                const double2* src = reinterpret_cast<const double2*>(&s_cand[par][p >> 5][0]);
-                double pa[kGJPanel], pc[kGJPanel];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double2 va = src[u], vc = src[4 + u];
-                    pa[2 * u] = va.x; pa[2 * u + 1] = va.y; pc[2 * u] = vc.x; pc[2 * u + 1] = vc.y;
-                }
-                const double rcp = s_cand[par][p >> 5][16];
-                if (r == p) {                                                    // scale the pivot row
-#pragma unroll
-                    for (int u = 0; u < kGJPanel; ++u) {
-                        if (u > t) a[u] *= rcp;
-                        if (u < t) C[u] *= rcp;
-                    }
-                    a[t] = 1.0; C[t] = rcp;
-                    s_piv[t] = (short)p; s_prow[k0 + t] = (short)p; s_used[r] = 1;
-                    free_r = false;
-                } else {                                                         // eliminate column k0 + t from row r
-                    const double f = a[t] * rcp;
-#pragma unroll
-                    for (int u = 0; u < kGJPanel; ++u) {
-                        if (u > t) a[u] -= f * pa[u];
-                        if (u < t) C[u] -= f * pc[u];
-                    }
-                    a[t] = 0.0; C[t] = -f;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < kGJPanel; ++t) s_C[t][r] = (t < pw && valid) ? C[t] : 0.0;
-            if (sing && tid == 0) s_sing = 1;
-        }
-        __syncthreads();
-        if (s_sing) break;                                                       // uniform
+        gj_bar_sync(1, THREADS);                                                 // C and the pivot list of panel pi are ready
+        if (S.sing) break;                                                       // uniform
         int myt[4] = {-1, -1, -1, -1};
 #pragma unroll
         for (int t = 0; t < kGJPanel; ++t) {
-            const int pr = (t < pw) ? s_piv[t] - r0 : -1;
+            const int pr = (t < pw) ? S.piv[buf][t] - r0 : -1;
 #pragma unroll
             for (int r = 0; r < 4; ++r) if (pr == r) myt[r] = t;
         }
-        const bool live = active && (cb > (k0 >> 3) || (cb == (k0 >> 3) && pw < kGJPanel));   // left of the panel: final (a short last panel shares its block with right-hand-side columns)
+        // left of the panel everything is final (a short last panel shares its block with right-hand-side columns)
+        const bool live = active && (cb > (k0 >> 3) || (cb == (k0 >> 3) && pw < kGJPanel));
         if (live) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (myt[r] >= 0) {
-                    double2* dst = reinterpret_cast<double2*>(&s_rows[myt[r]][c0]);
+                    double2* dst = reinterpret_cast<double2*>(&S.rows[myt[r]][c0]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dst[j] = make_double2(reg[r][2 * j], reg[r][2 * j + 1]);
                 }
         }
-        __syncthreads();
+        gj_bar_sync(2, NW);                                                      // pivot rows published (workers only)
         if (live) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -1005,14 +1060,14 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) reg[r][j] = 0.0;
                 }
-#pragma unroll
+#pragma unroll 1
             for (int t = 0; t < kGJPanel; ++t) {
                 double row[8], cc[4];
-                const double2* rs = reinterpret_cast<const double2*>(&s_rows[t][c0]);
+                const double2* rs = reinterpret_cast<const double2*>(&S.rows[t][c0]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const double2 v2 = rs[j]; row[2 * j] = v2.x; row[2 * j + 1] = v2.y; }
-                const double2 c01 = *reinterpret_cast<const double2*>(&s_C[t][r0]);
-                const double2 c23 = *reinterpret_cast<const double2*>(&s_C[t][r0 + 2]);
+                const double2 c01 = *reinterpret_cast<const double2*>(&S.C[buf][t][r0]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&S.C[buf][t][r0 + 2]);
                 cc[0] = c01.x; cc[1] = c01.y; cc[2] = c23.x; cc[3] = c23.y;
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -1020,24 +1075,26 @@ __global__ void __launch_bounds__(THREADS) k_gj_block(SolveSmallParams Q)
                     for (int j = 0; j < 8; ++j) reg[r][j] += cc[r] * row[j];
             }
         }
-        const int nk0 = k0 + kGJPanel;
-        if (nk0 < n && active && cb == (nk0 >> 3)) {                             // stage the next panel's columns
+        if (pi + 2 < npan) {                                                     // block pi + 2 (panels 0..pi applied) for the look-ahead
+            if (active && cb == pi + 2) {
 #pragma unroll
-            for (int t = 0; t < kGJPanel; ++t) {
-                *reinterpret_cast<double2*>(&s_pan[t][r0]) = make_double2(reg[0][t], reg[1][t]);
-                *reinterpret_cast<double2*>(&s_pan[t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
+                for (int t = 0; t < kGJPanel; ++t) {
+                    *reinterpret_cast<double2*>(&S.old[buf][t][r0]) = make_double2(reg[0][t], reg[1][t]);
+                    *reinterpret_cast<double2*>(&S.old[buf][t][r0 + 2]) = make_double2(reg[2][t], reg[3][t]);
+                }
             }
+            __threadfence_block();
+            gj_bar_arrive(3, THREADS);
         }
-        __syncthreads();
     }
-    if (s_sing) { if (tid == 0) *Q.singular = 1; return; }
-    if (tid < n) s_var[s_prow[tid]] = (short)tid;
     __syncthreads();
+    __syncthreads();                                                             // S.var written by the panel group
+    if (S.sing) return;
     if (active) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             if (r0 + r >= n) continue;
-            const int row = s_var[r0 + r];                                       // this register row is row `row` of the solution
+            const int row = S.var[r0 + r];                                       // this register row is row `row` of the solution
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = c0 + j;
@@ -1285,8 +1342,8 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         fp.c = u->consts; fp.lay = u->lay;
         if (world > 1) {
             // features owned by other ranks must not leave stale status/dof behind
-            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat_cap, s));
-            RVIO_CUDA_TRY(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat_cap, s));
+            RVIO_ENQ(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat_cap, s));
+            RVIO_ENQ(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat_cap, s));
         }
         RVIO_LAUNCH(k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
         GramParams gp;
@@ -1296,9 +1353,9 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
         RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
     } else {
-        RVIO_CUDA_TRY(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
+        RVIO_ENQ(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     }
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 
@@ -1308,8 +1365,8 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
     const double* x_dev = u->cur_x_dev; const double* P_dev = u->cur_P_dev;
     u->open = false;
     if (n == 0) {
-        RVIO_CUDA_TRY(cudaMemcpyAsync(x_out_dev, x_dev, sizeof(double) * xdim, cudaMemcpyDeviceToDevice, s));
-        RVIO_CUDA_TRY(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
+        RVIO_ENQ(cudaMemcpyAsync(x_out_dev, x_dev, sizeof(double) * xdim, cudaMemcpyDeviceToDevice, s));
+        RVIO_ENQ(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
         return RVIO_OK;
     }
     if (N <= kSolveSmallMaxClones) {
@@ -1317,13 +1374,13 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
         sp.T = u->d_T; sp.Yt = u->d_Yt; sp.dx = u->d_dx;
         sp.x_out = x_out_dev; sp.P_out = P_out_dev; sp.singular = u->d_sing;
-        RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+        RVIO_ENQ(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
         RVIO_LAUNCH(k_wgemm, dim3(div_up(d, 32), div_up(n, 32)), 256, 0, s, sp);
-        if (div_up(n, 4) * div_up(n + d + 1, 8) <= 352) RVIO_LAUNCH(k_gj_block<352>, 1, 352, 0, s, sp);   // one thread per 4 x 8 tile
-        else RVIO_LAUNCH(k_gj_block<480>, 1, 480, 0, s, sp);
+        if (kGJPanelThreads + div_up(n, 4) * div_up(n + d + 1, 8) <= 448) RVIO_LAUNCH(k_gj_block<448>, 1, 448, 0, s, sp);   // 3 panel warps + one thread per 4 x 8 tile
+        else RVIO_LAUNCH(k_gj_block<576>, 1, 576, 0, s, sp);
         const int nb = div_up(d, 32);
         RVIO_LAUNCH(k_pout_finalize, nb * nb, 256, 0, s, sp);
-        RVIO_CUDA_TRY(cudaGetLastError());
+        RVIO_ENQ(cudaGetLastError());
         return RVIO_OK;
     }
     const double* G = u->d_red;
@@ -1349,9 +1406,9 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_R + 1; g.crs = m; g.ccs = 1;
         g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
         launch_gemm(s, g);
-        RVIO_CUDA_TRY(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+        RVIO_ENQ(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
     }
-    RVIO_CUDA_TRY(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+    RVIO_ENQ(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
     RVIO_LAUNCH(k_gauss_jordan, 1, 1024, sizeof(double) * (n + 2), s, u->d_M, u->d_R, n, m, u->d_sing, gate);
     // dx = P[:,c] * y_z
     {
@@ -1379,7 +1436,7 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         fp.x_out = x_out_dev; fp.P_out = P_out_dev;
         RVIO_LAUNCH(k_finalize, div_up(d * d, 256), 256, 0, s, fp);
     }
-    RVIO_CUDA_TRY(cudaGetLastError());
+    RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 
@@ -1415,8 +1472,8 @@ static int upload_state(rvio_updater* u, const double* x, int xdim, const double
     cudaStream_t s = u->stream;
     memcpy(u->h_x, x, sizeof(double) * xdim);
     memcpy(u->h_P, P, sizeof(double) * (size_t)d * d);
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_x, u->h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, s));
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_P, u->h_P, sizeof(double) * (size_t)d * d, cudaMemcpyHostToDevice, s));
+    RVIO_ENQ(cudaMemcpyAsync(u->d_x, u->h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, s));
+    RVIO_ENQ(cudaMemcpyAsync(u->d_P, u->h_P, sizeof(double) * (size_t)d * d, cudaMemcpyHostToDevice, s));
     return RVIO_OK;
 }
 
@@ -1432,9 +1489,9 @@ static int upload_lists(rvio_updater* u, const uint8_t* types, const int32_t* of
     memcpy(u->h_types, types, n_feat);
     memcpy(u->h_off, offsets, sizeof(int32_t) * (n_feat + 1));
     memcpy(u->h_xy, xy, sizeof(float) * 2 * n_meas);
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_types, u->h_types, n_feat, cudaMemcpyHostToDevice, s));
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_off, u->h_off, sizeof(int32_t) * (n_feat + 1), cudaMemcpyHostToDevice, s));
-    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_xy, u->h_xy, sizeof(float) * 2 * n_meas, cudaMemcpyHostToDevice, s));
+    RVIO_ENQ(cudaMemcpyAsync(u->d_types, u->h_types, n_feat, cudaMemcpyHostToDevice, s));
+    RVIO_ENQ(cudaMemcpyAsync(u->d_off, u->h_off, sizeof(int32_t) * (n_feat + 1), cudaMemcpyHostToDevice, s));
+    RVIO_ENQ(cudaMemcpyAsync(u->d_xy, u->h_xy, sizeof(float) * 2 * n_meas, cudaMemcpyHostToDevice, s));
     return RVIO_OK;
 }
 

@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 namespace rvio {
@@ -16,7 +17,13 @@ namespace rvio {
 int tracker_enqueue_frame_host(rvio_tracker* t, const uint8_t* img, int w, int h, int stride, int ch, const double* imu, int n_imu);
 int tracker_enqueue_frame_dev(rvio_tracker* t, const uint8_t* img_dev, int pitch, const double* imu, int n_imu);
 int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n);
+int tracker_enqueue_frame_staged(rvio_tracker* t, const double* imu, int n_imu);
+uint8_t* tracker_gray(rvio_tracker* t, size_t* pitch);
 int tracker_sync(rvio_tracker* t);
+int tracker_enqueue_scalars(rvio_tracker* t);
+int tracker_wait(rvio_tracker* t);
+int tracker_parity(const rvio_tracker* t);
+int tracker_n_track(const rvio_tracker* t);
 bool tracker_is_first(const rvio_tracker* t);
 const CamParams* tracker_cam(const rvio_tracker* t);
 const TrackerBuffers* tracker_buffers(const rvio_tracker* t);
@@ -41,11 +48,16 @@ struct rvio_vio {
     cudaStream_t stream;          // main: tracker -> per-feature -> normal terms -> solve -> augment
     cudaStream_t side;            // side: propagate, FindNewer+refill (off the critical path)
     cudaEvent_t ev_frame_in, ev_prop_done, ev_bookkeep_done, ev_side_done;
+    // frame graphs: the steady-state frame is a fixed sequence of ~20 stream operations whose parameters only depend on a
+    // few host-known bits (ping-pong parities, input mode, IMU block size); it is captured once per signature and replayed
+    bool use_graphs;
+    std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
+    uint64_t graph_launches;
     bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage events on the main stream
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
-    double* d_pose; double* d_imu; float2* d_cand;
+    double* d_pose; double* d_imu; float2* d_cand;      // d_imu: [frame header {n_imu, n_cand} (16 B)][n_imu x 8 doubles]
     // pinned
     double* h_pose; double* h_imu; float* h_cand; double* h_cnt; double* h_state;
     // System.cc statics, per instance
@@ -204,6 +216,7 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_bookkeep_done, cudaEventDisableTiming));
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_side_done, cudaEventDisableTiming));
     v->timeline = false;
+    v->use_graphs = true; v->graph_launches = 0;
     for (int k = 0; k < 8; ++k) { RVIO_CUDA_TRY(cudaEventCreate(&v->tl[k])); v->tl_ms[k] = 0.f; }
     v->window = cfg->tracker.max_track_len - 1;             // System.cc:71-72
     v->min_clones = cfg->tracker.min_track_len - 1;         // System.cc:74-75
@@ -216,10 +229,10 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
         if ((rc = valloc(v, &v->d_P[k], dmax * dmax)) != RVIO_OK) return rc;
     }
     if ((rc = valloc(v, &v->d_pose, 8)) != RVIO_OK) return rc;
-    if ((rc = valloc(v, &v->d_imu, 512 * 8)) != RVIO_OK) return rc;
+    if ((rc = valloc(v, &v->d_imu, 512 * 8 + 2)) != RVIO_OK) return rc;
     if ((rc = valloc(v, &v->d_cand, (size_t)v->F + 1)) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_pose, 8)) != RVIO_OK) return rc;
-    if ((rc = vhalloc(v, &v->h_imu, 512 * 8)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_imu, 512 * 8 + 2)) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_cand, 2 * ((size_t)v->F + 1))) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_cnt, 8)) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_state, xmax + dmax * dmax)) != RVIO_OK) return rc;
@@ -247,6 +260,7 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     cudaSetDevice(v->device);
     cudaStreamSynchronize(v->stream);
     cudaStreamSynchronize(v->side);
+    for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second);
     cudaEventDestroy(v->ev_frame_in); cudaEventDestroy(v->ev_prop_done); cudaEventDestroy(v->ev_bookkeep_done); cudaEventDestroy(v->ev_side_done);
     cudaStreamDestroy(v->side);
     for (void* p : v->allocs) cudaFree(p);
@@ -254,6 +268,109 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     rvio_updater_destroy(v->upd);
     rvio_tracker_destroy(v->trk);
     delete v;
+}
+
+struct FrameOutcome { bool committable, ran_update; };
+
+// Everything one frame puts on the two streams, from the IMU upload to the device->host copies of the results; no
+// synchronisation and no host-visible result is touched here, so the sequence can be captured into a CUDA graph and
+// replayed (with rvio::t_replay set the stream operations are skipped and only the host-side bookkeeping advances).
+static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int width, int height, int stride, int channels,
+                         const uint8_t* img_dev, int pitch, const double* imu, int n_imu, size_t imu_bytes,
+                         const float2* cand_dev, bool cand_upload, int n_cand, int cand_cap, int cand_filtered, FrameOutcome* out)
+{
+    cudaStream_t s = v->stream, side = v->side;
+    const int N = v->n_clones;
+    const int xdim = xdim_of(N), d = d_of(N);
+    const int* hdr = reinterpret_cast<const int*>(v->d_imu);
+    out->committable = false; out->ran_update = false;
+    // ---- propagation (System.cc:263) on the side stream: it only needs last frame's x, P and the IMU samples, so it
+    //      overlaps the whole tracker; the solve waits for it.
+    RVIO_ENQ(cudaEventRecord(v->ev_frame_in, s));
+    RVIO_ENQ(cudaStreamWaitEvent(side, v->ev_frame_in, 0));
+    const int xi0 = v->xi, pi0 = v->pi;             // prior (pre-propagation) buffers: also what k_feature reads
+    RVIO_ENQ(cudaMemcpyAsync(v->d_imu, v->h_imu, imu_bytes, cudaMemcpyHostToDevice, side));
+    {
+        PropagateParams pp;
+        pp.x_in = v->d_x[xi0]; pp.P_in = v->d_P[pi0]; pp.xdim = xdim; pp.d = d;
+        pp.imu = v->d_imu + 2; pp.n_imu = n_imu; pp.hdr = hdr; pp.x_out = v->d_x[1 - xi0]; pp.P_out = v->d_P[1 - pi0];
+        pp.c.gravity = v->cfg.gravity; pp.c.small_angle = v->cfg.tracker.small_angle;
+        pp.c.sigma_g = v->cfg.sigma_g; pp.c.sigma_wg = v->cfg.sigma_wg; pp.c.sigma_a = v->cfg.sigma_a; pp.c.sigma_wa = v->cfg.sigma_wa;
+        int r2 = launch_propagate(side, pp);
+        if (r2 != RVIO_OK) return r2;
+        RVIO_ENQ(cudaEventRecord(v->ev_prop_done, side));
+        v->xi = 1 - xi0; v->pi = 1 - pi0;
+    }
+
+    // ---- visual tracking (System.cc:258) on the main stream
+    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[0], s));
+    int rc;
+    if (staged) rc = tracker_enqueue_frame_staged(v->trk, imu, n_imu);
+    else if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
+    else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
+    if (rc < 0) return rc;
+    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[1], s));          // tracker kernels enqueued (upload .. bookkeeping)
+    if (n_cand > 0 && cand_upload)
+        RVIO_ENQ(cudaMemcpyAsync(v->d_cand, v->h_cand, sizeof(float) * 2 * cand_cap, cudaMemcpyHostToDevice, s));
+    bool side_refill = false;
+    if (rc == RVIO_FIRST_IMAGE) {
+        if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand); if (r2 != RVIO_OK) return r2; }
+        out->committable = true;
+    } else if (rc == RVIO_OK) {
+        if (n_cand > 0) {
+            // FindNewer + refill only prepare the NEXT frame's feature set: run them beside the update
+            RVIO_ENQ(cudaEventRecord(v->ev_bookkeep_done, s));
+            RVIO_ENQ(cudaStreamWaitEvent(side, v->ev_bookkeep_done, 0));
+            FindNewerParams fp;
+            fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = cand_cap; fp.hdr = hdr; fp.raw = cand_filtered ? 1 : 0;
+            fp.W = v->cfg.tracker.width; fp.H = v->cfg.tracker.height; fp.gc = v->gc; fp.gr = v->gr;
+            fp.offx = v->offx; fp.offy = v->offy; fp.max_per_block = v->max_per_block;
+            fp.bx = (float)v->cfg.block_x; fp.by = (float)v->cfg.block_y; fp.min_dist = v->cfg.min_dist;
+            fp.cam = *tracker_cam(v->trk);
+            int r2 = launch_find_newer_refill(side, fp);
+            if (r2 != RVIO_OK) return r2;
+            side_refill = true;
+        }
+        out->committable = true;
+    }
+
+    // ---- update (System.cc:266-277).  The per-feature kernel and the normal terms read only the clone states and the
+    //      clone-clone covariance block, which propagation leaves untouched (PreIntegrator.cc:186-192 rewrites the
+    //      IMU block and the cross terms only): they run on the prior buffers, concurrently with k_propagate.
+    if (N > v->min_clones) {
+        const TrackerBuffers* B = tracker_buffers(v->trk);
+        int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[xi0], xdim, v->d_P[pi0], d, B->up_types, B->up_off, B->up_xy,
+                                              v->Fu, &B->sc->n_up, 0, 1);
+        if (r2 != RVIO_OK) return r2;
+        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[2], s));      // per-feature + normal terms done
+        RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
+        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[3], s));      // (waited for propagation)
+        r2 = updater_enqueue_solve_on(v->upd, s, v->d_x[v->xi], v->d_P[v->pi], v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
+        if (r2 != RVIO_OK) return r2;
+        v->xi = 1 - v->xi; v->pi = 1 - v->pi;
+        out->ran_update = true;
+        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[4], s));      // solve done
+        RVIO_ENQ(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+        RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
+    }
+    // ---- augmentation + composition (System.cc:280-365)
+    {
+        AugmentParams ap;
+        ap.x = v->d_x[v->xi]; ap.P_in = v->d_P[v->pi]; ap.P_out = v->d_P[1 - v->pi];
+        ap.d = d; ap.N = N; ap.window = v->window; ap.do_augment = v->n_img_after_init > 1 ? 1 : 0; ap.pose_out = v->d_pose;
+        int r2 = launch_augment_compose(s, ap);
+        if (r2 != RVIO_OK) return r2;
+        v->pi = 1 - v->pi;
+        if (ap.do_augment && N < v->window) v->n_clones = N + 1;
+    }
+    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[5], s));          // augmentation + composition done
+    if (side_refill) {
+        RVIO_ENQ(cudaEventRecord(v->ev_side_done, side));
+        RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_side_done, 0));
+    }
+    RVIO_ENQ(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+    return tracker_enqueue_scalars(v->trk);                  // tracker counters follow everything else on the main stream
 }
 
 static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int height, int stride, int channels,
@@ -284,103 +401,65 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     v->n_img_after_init++;
     if (n_cand > v->F) n_cand = v->F;
 
-    const int N = v->n_clones;
-    const int xdim = xdim_of(N), d = d_of(N);
-    cudaStream_t side = v->side;
-    // ---- propagation (System.cc:263) on the side stream: it only needs last frame's x, P and the IMU samples, so it
-    //      overlaps the whole tracker; the solve waits for it.
-    const int xi0 = v->xi, pi0 = v->pi;             // prior (pre-propagation) buffers: also what k_feature reads
-    memcpy(v->h_imu, imu, sizeof(double) * 8 * n_imu);
-    RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_imu, v->h_imu, sizeof(double) * 8 * n_imu, cudaMemcpyHostToDevice, side));
-    {
-        PropagateParams pp;
-        pp.x_in = v->d_x[xi0]; pp.P_in = v->d_P[pi0]; pp.xdim = xdim; pp.d = d;
-        pp.imu = v->d_imu; pp.n_imu = n_imu; pp.x_out = v->d_x[1 - xi0]; pp.P_out = v->d_P[1 - pi0];
-        pp.c.gravity = v->cfg.gravity; pp.c.small_angle = v->cfg.tracker.small_angle;
-        pp.c.sigma_g = v->cfg.sigma_g; pp.c.sigma_wg = v->cfg.sigma_wg; pp.c.sigma_a = v->cfg.sigma_a; pp.c.sigma_wa = v->cfg.sigma_wa;
-        int r2 = launch_propagate(side, pp);
-        if (r2 != RVIO_OK) return r2;
-        RVIO_CUDA_TRY(cudaEventRecord(v->ev_prop_done, side));
-        v->xi = 1 - xi0; v->pi = 1 - pi0;
-    }
+    // ---- per-frame host staging (pinned): frame header + IMU rows, corner candidates
+    int* hh = reinterpret_cast<int*>(v->h_imu);
+    hh[0] = n_imu; hh[1] = n_cand; hh[2] = hh[3] = 0;
+    memcpy(v->h_imu + 2, imu, sizeof(double) * 8 * n_imu);
+    if (n_cand > 0 && !cand_dev_in) memcpy(v->h_cand, cand_host, sizeof(float) * 2 * n_cand);
 
-    // ---- visual tracking (System.cc:258) on the main stream
-    if (v->timeline) cudaEventRecord(v->tl[0], s);
+    // ---- a steady-state frame (window full, features being tracked) is replayed as a CUDA graph
+    const bool steady = v->use_graphs && !v->timeline && g_profile_on.load(std::memory_order_relaxed) == 0 &&
+                        !tracker_is_first(v->trk) && tracker_n_track(v->trk) > 0 && v->n_clones == v->window &&
+                        v->n_clones > v->min_clones && v->n_img_after_init > 1;
+    FrameOutcome fo;
     int rc;
-    if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
-    else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
-    if (rc < 0) return rc;
-    if (v->timeline) cudaEventRecord(v->tl[1], s);          // tracker kernels enqueued (upload .. bookkeeping)
-    const float2* cand_dev = nullptr;
-    if (n_cand > 0) {
-        if (cand_dev_in) cand_dev = reinterpret_cast<const float2*>(cand_dev_in);
-        else {
-            memcpy(v->h_cand, cand_host, sizeof(float) * 2 * n_cand);
-            RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, v->h_cand, sizeof(float) * 2 * n_cand, cudaMemcpyHostToDevice, s));
-            cand_dev = v->d_cand;
+    if (steady) {
+        const int imu16 = (n_imu + 15) / 16;
+        const size_t imu_bytes = 16 + sizeof(double) * 8 * 16 * (size_t)imu16;
+        // inputs that arrive in caller-owned device memory are copied into the pipeline's own buffers first (the graph's
+        // kernel arguments are fixed addresses)
+        if (img_dev) {
+            size_t gp; uint8_t* g = tracker_gray(v->trk, &gp);
+            RVIO_CUDA_TRY(cudaMemcpy2DAsync(g, gp, img_dev, pitch, v->cfg.tracker.width, v->cfg.tracker.height, cudaMemcpyDeviceToDevice, s));
         }
-    }
-    bool frame_committable = false, side_refill = false;
-    if (rc == RVIO_FIRST_IMAGE) {
-        if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand); if (r2 != RVIO_OK) return r2; }
-        frame_committable = true;
-    } else if (rc == RVIO_OK) {
-        if (n_cand > 0) {
-            // FindNewer + refill only prepare the NEXT frame's feature set: run them beside the update
-            RVIO_CUDA_TRY(cudaEventRecord(v->ev_bookkeep_done, s));
-            RVIO_CUDA_TRY(cudaStreamWaitEvent(side, v->ev_bookkeep_done, 0));
-            FindNewerParams fp;
-            fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = n_cand; fp.raw = cand_filtered ? 1 : 0;
-            fp.W = v->cfg.tracker.width; fp.H = v->cfg.tracker.height; fp.gc = v->gc; fp.gr = v->gr;
-            fp.offx = v->offx; fp.offy = v->offy; fp.max_per_block = v->max_per_block;
-            fp.bx = (float)v->cfg.block_x; fp.by = (float)v->cfg.block_y; fp.min_dist = v->cfg.min_dist;
-            fp.cam = *tracker_cam(v->trk);
-            int r2 = launch_find_newer_refill(side, fp);
-            if (r2 != RVIO_OK) return r2;
-            side_refill = true;
+        if (n_cand > 0 && cand_dev_in)
+            RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, cand_dev_in, sizeof(float) * 2 * n_cand, cudaMemcpyDeviceToDevice, s));
+        const uint64_t key = (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
+                             (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)(img_dev != nullptr) << 5 | (uint64_t)(channels & 7) << 6 |
+                             (uint64_t)(cand_dev_in != nullptr) << 9 | (uint64_t)imu16 << 10;
+        auto it = v->graphs.find(key);
+        const bool cand_upload = n_cand > 0 && !cand_dev_in;
+        if (it != v->graphs.end()) {
+            t_replay = true;
+            rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
+                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, &fo);
+            t_replay = false;
+            if (rc != RVIO_OK) return rc;
+            RVIO_CUDA_TRY(cudaGraphLaunch(it->second, s));
+        } else {
+            RVIO_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
+                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, &fo);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != RVIO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) { set_error("cudaStreamEndCapture", cudaGetErrorString(ce)); return RVIO_ERR_CUDA; }
+            cudaGraphExec_t ex = nullptr;
+            const cudaError_t ci = cudaGraphInstantiate(&ex, g, 0);
+            cudaGraphDestroy(g);
+            if (ci != cudaSuccess) { set_error("cudaGraphInstantiate", cudaGetErrorString(ci)); return RVIO_ERR_CUDA; }
+            v->graphs.emplace(key, ex);
+            RVIO_CUDA_TRY(cudaGraphLaunch(ex, s));
         }
-        frame_committable = true;
-    }
-
-    // ---- update (System.cc:266-277).  The per-feature kernel and the normal terms read only the clone states and the
-    //      clone-clone covariance block, which propagation leaves untouched (PreIntegrator.cc:186-192 rewrites the
-    //      IMU block and the cross terms only): they run on the prior buffers, concurrently with k_propagate.
-    bool ran_update = false;
-    if (N > v->min_clones) {
-        const TrackerBuffers* B = tracker_buffers(v->trk);
-        int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[xi0], xdim, v->d_P[pi0], d, B->up_types, B->up_off, B->up_xy,
-                                              v->Fu, &B->sc->n_up, 0, 1);
-        if (r2 != RVIO_OK) return r2;
-        if (v->timeline) cudaEventRecord(v->tl[2], s);      // per-feature + normal terms done
-        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
-        if (v->timeline) cudaEventRecord(v->tl[3], s);      // (waited for propagation)
-        r2 = updater_enqueue_solve_on(v->upd, s, v->d_x[v->xi], v->d_P[v->pi], v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
-        if (r2 != RVIO_OK) return r2;
-        v->xi = 1 - v->xi; v->pi = 1 - v->pi;
-        ran_update = true;
-        if (v->timeline) cudaEventRecord(v->tl[4], s);      // solve done
-        RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+        v->graph_launches++;
     } else {
-        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
+        const float2* cand_dev = cand_dev_in ? reinterpret_cast<const float2*>(cand_dev_in) : v->d_cand;
+        rc = enqueue_frame(v, false, img_host, width, height, stride, channels, img_dev, pitch, imu, n_imu,
+                           16 + sizeof(double) * 8 * (size_t)n_imu, cand_dev, n_cand > 0 && !cand_dev_in, n_cand, n_cand, cand_filtered, &fo);
+        if (rc != RVIO_OK) return rc;
     }
-    // ---- augmentation + composition (System.cc:280-365)
-    {
-        AugmentParams ap;
-        ap.x = v->d_x[v->xi]; ap.P_in = v->d_P[v->pi]; ap.P_out = v->d_P[1 - v->pi];
-        ap.d = d; ap.N = N; ap.window = v->window; ap.do_augment = v->n_img_after_init > 1 ? 1 : 0; ap.pose_out = v->d_pose;
-        int r2 = launch_augment_compose(s, ap);
-        if (r2 != RVIO_OK) return r2;
-        v->pi = 1 - v->pi;
-        if (ap.do_augment && N < v->window) v->n_clones = N + 1;
-    }
-    if (v->timeline) cudaEventRecord(v->tl[5], s);          // augmentation + composition done
-    if (side_refill) {
-        RVIO_CUDA_TRY(cudaEventRecord(v->ev_side_done, side));
-        RVIO_CUDA_TRY(cudaStreamWaitEvent(s, v->ev_side_done, 0));
-    }
-    RVIO_CUDA_TRY(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
     clock_gettime(CLOCK_MONOTONIC, &h1);
-    int r3 = tracker_sync(v->trk);                          // publishes tracker counters + synchronises the stream
+    int r3 = tracker_wait(v->trk);                          // the one synchronisation of the frame
     if (r3 != RVIO_OK) return r3;
     clock_gettime(CLOCK_MONOTONIC, &h2);
     v->tl_ms[6] = (float)((h1.tv_sec - h0.tv_sec) * 1e3 + (h1.tv_nsec - h0.tv_nsec) * 1e-6);   // host: enqueue
@@ -390,12 +469,12 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         cudaEventSynchronize(v->tl[6]);
         for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, v->tl[k], v->tl[k + 1]) == cudaSuccess) v->tl_ms[k] = ms; else v->tl_ms[k] = -1.f; }
     }
-    if (frame_committable) { r3 = rvio_tracker_commit(v->trk); if (r3 != RVIO_OK) return r3; }
+    if (fo.committable) { r3 = rvio_tracker_commit(v->trk); if (r3 != RVIO_OK) return r3; }
     memcpy(pose_out, v->h_pose, sizeof(double) * 7);
     *pose_valid = 1;
     rvio_update_info inf;
     memset(&inf, 0, sizeof inf);
-    if (ran_update) {
+    if (fo.ran_update) {
         inf.n_feat = tracker_host_scalars(v->trk)->n_up;
         inf.n_good = (int)v->h_cnt[0]; inf.rows_stacked = (int)v->h_cnt[1];
         inf.n_reject_init = (int)v->h_cnt[2]; inf.n_reject_lm = (int)v->h_cnt[3]; inf.n_reject_gate = (int)v->h_cnt[4];
@@ -440,6 +519,14 @@ extern "C" int rvio_vio_get_update_info(rvio_vio* v, rvio_update_info* info)
 {
     RVIO_ARG_CHECK(v && info);
     *info = v->last_info;
+    return RVIO_OK;
+}
+
+extern "C" int rvio_vio_graphs(rvio_vio* v, int enable, uint64_t* graph_launches)
+{
+    RVIO_ARG_CHECK(v);
+    if (enable >= 0) v->use_graphs = enable != 0;
+    if (graph_launches) *graph_launches = v->graph_launches;
     return RVIO_OK;
 }
 
