@@ -144,7 +144,8 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
             cands = wl["cand2"] if got_pose else wl["cand1"]
             timing = got_pose and warm >= W
             if timing:
-                flush.fill_(timed & 0xff)                                  # L2 flush between timed iterations (untimed)
+                if not os.environ.get("RVIO_BENCH_NO_FLUSH"):              # diagnostic switch only: a number taken without the flush is not a bench value
+                    flush.fill_(timed & 0xff)                              # L2 flush between timed iterations (untimed)
                 torch.cuda.synchronize()
                 if launches0 is None:
                     launches0 = L.rvio_b200_kernel_launches()

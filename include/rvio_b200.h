@@ -42,7 +42,8 @@ typedef struct rvio_tracker_cfg {
     float   fx, fy, cx, cy;           /* Camera.fx.. (read into float: Tracker.cc:39-42) */
     float   k1, k2, p1, p2, k3;       /* Camera.k1.. ; k3 == 0 -> 4-coefficient model (Tracker.cc:56-61) */
     int32_t is_rgb;                   /* Camera.RGB (channel order for 3/4-channel input, Tracker.cc:183-196) */
-    int32_t is_fisheye;               /* Camera.Fisheye: must be 0 (radtan); 1 -> RVIO_ERR_ARG (not implemented) */
+    int32_t is_fisheye;               /* Camera.Fisheye: 0 radtan (cv::undistortPoints), 1 equidistant (cv::fisheye::undistortPoints
+                                       * with (k1,k2,p1,p2) as its four coefficients, Tracker.cc:119; k3 must then be 0) */
     int32_t enable_equalizer;         /* Tracker.EnableEqualizer */
     int32_t n_features;               /* Tracker.nFeatures */
     int32_t max_track_len;            /* Tracker.nMaxTrackingLength */
@@ -69,6 +70,20 @@ int rvio_tracker_track(rvio_tracker* trk, const uint8_t* img, int width, int hei
                        int channels, const double* imu, int n_imu);
 /* Same, image already resident in device memory (single channel, pitch in bytes). */
 int rvio_tracker_track_dev(rvio_tracker* trk, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu);
+
+/* Feature-sharded form of rvio_tracker_track (one stream, features split over `world` GPUs, every rank holds
+ * the same tracker state and sees the same frame):
+ *   _track_begin   image pipeline (redundant on every rank: cheaper than exchanging the pyramid) + pyramidal LK and
+ *                  undistortion for the feature indices [rank*S, (rank+1)*S), S = ceil(nFeatures / world); same return
+ *                  codes as rvio_tracker_track
+ *   _lk_results    device pointers of the per-feature LK outputs (float2 pixels, float2 normalized, u8 status; capacity
+ *                  nFeatures + 64 entries each) and S: the caller all-gathers the shards in place (NCCL, <= 17 B/feature)
+ *   _track_finish  2-point RANSAC + bookkeeping (Tracker.cc:264-342) on the complete arrays, identical on every rank.
+ * Seeding / refill / commit are the ordinary calls, replicated. */
+int rvio_tracker_track_begin(rvio_tracker* trk, const uint8_t* img, int width, int height, int stride_bytes,
+                             int channels, const double* imu, int n_imu, int rank, int world);
+int rvio_tracker_lk_results(rvio_tracker* trk, int world, void** lk_px_dev, void** undist_dev, void** status_dev, int* shard);
+int rvio_tracker_track_finish(rvio_tracker* trk);
 
 /* Equalised current image (what the reference's detector sees: Tracker.cc:207,350). out: width*height bytes. */
 int rvio_tracker_get_image(rvio_tracker* trk, uint8_t* out, int out_stride_bytes);

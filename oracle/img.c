@@ -408,3 +408,37 @@ void orc_undistort(const float* px, int n, const float* K4, const float* D5, flo
         out[2 * i + 1] = (float)y;
     }
 }
+
+/* cv::fisheye::undistortPoints(src, dst, K, D) with no R/P (Tracker.cc:119), OpenCV 4.x: Newton iterations on
+ * theta (at most 10, stop when |fix| < 1e-8), scale = tan(theta) / theta_d; a point that did not converge or whose theta
+ * changed sign becomes (-1e6, -1e6).  D4 = the four coefficients the reference passes (Camera.k1, k2, p1, p2 read as k1..k4). */
+void orc_undistort_fisheye(const float* px, int n, const float* K4, const float* D4, float* out)
+{
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    const double k0 = D4[0], k1 = D4[1], k2 = D4[2], k3 = D4[3];
+    const double eps = 1e-8, half_pi = 3.1415926535897932384626433832795 / 2.;
+    for (int i = 0; i < n; ++i) {
+        const double u = px[2 * i], v = px[2 * i + 1];
+        const double pwx = (u - cx) / fx, pwy = (v - cy) / fy;
+        double theta_d = sqrt(pwx * pwx + pwy * pwy);
+        theta_d = fmin(fmax(-half_pi, theta_d), half_pi);
+        int converged = 0;
+        double theta = theta_d, scale = 0.0;
+        if (fabs(theta_d) > eps) {
+            for (int j = 0; j < 10; ++j) {
+                const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+                const double a = k0 * t2, b = k1 * t4, c = k2 * t6, d = k3 * t8;
+                const double fix = (theta * (1 + a + b + c + d) - theta_d) / (1 + 3 * a + 5 * b + 7 * c + 9 * d);
+                theta = theta - fix;
+                if (fabs(fix) < eps) { converged = 1; break; }
+            }
+            scale = tan(theta) / theta_d;
+        } else {
+            converged = 1;
+        }
+        const int flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+        if (converged && !flipped) { out[2 * i] = (float)(pwx * scale); out[2 * i + 1] = (float)(pwy * scale); }
+        else { out[2 * i] = -1000000.0f; out[2 * i + 1] = -1000000.0f; }
+    }
+}
+

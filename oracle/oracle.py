@@ -30,7 +30,8 @@ class TrackerCfg(C.Structure):
                 ("n_features", C.c_int), ("max_track_len", C.c_int), ("min_track_len", C.c_int),
                 ("enable_equalizer", C.c_int), ("use_sampson", C.c_int),
                 ("inlier_thr", C.c_double), ("small_angle", C.c_double), ("T_BC0", C.c_double * 16),
-                ("img_w", C.c_int), ("img_h", C.c_int), ("min_dist", C.c_double), ("block_x", C.c_int), ("block_y", C.c_int)]
+                ("img_w", C.c_int), ("img_h", C.c_int), ("min_dist", C.c_double), ("block_x", C.c_int), ("block_y", C.c_int),
+                ("is_fisheye", C.c_int)]
 
 
 class UpdaterCfg(C.Structure):
@@ -77,6 +78,7 @@ def lib():
     L.orc_lk.argtypes = [u8, u8, ci, ci, ci, f32, ci, f32, u8, ci, ci, ci, cd, cd]
     L.orc_lk.restype = ci
     L.orc_undistort.argtypes = [f32, ci, f32, f32, f32]
+    L.orc_undistort_fisheye.argtypes = [f32, ci, f32, f32, f32]
     L.orc_rand_seed.argtypes = [C.POINTER(RandState), C.c_uint]
     L.orc_rand_next.argtypes = [C.POINTER(RandState)]
     L.orc_rand_next.restype = ci
@@ -141,6 +143,7 @@ def tracker_cfg(cfg) -> TrackerCfg:
     t.inlier_thr, t.small_angle = cfg.inlier_thr, cfg.small_angle
     t.T_BC0 = (C.c_double * 16)(*cfg.T_BC0)
     t.img_w, t.img_h, t.min_dist, t.block_x, t.block_y = cfg.width, cfg.height, cfg.min_dist, cfg.block_x, cfg.block_y
+    t.is_fisheye = int(getattr(cfg, "fisheye", 0))
     return t
 
 
@@ -183,7 +186,10 @@ def undistort(px, cfg):
     K = np.array([cfg.fx, cfg.fy, cfg.cx, cfg.cy], np.float32)
     D = np.array([cfg.k1, cfg.k2, cfg.p1, cfg.p2, cfg.k3], np.float32)
     out = np.empty_like(px)
-    lib().orc_undistort(px, len(px), K, D, out)
+    if getattr(cfg, "fisheye", 0):
+        lib().orc_undistort_fisheye(px, len(px), K, np.ascontiguousarray(D[:4]), out)
+    else:
+        lib().orc_undistort(px, len(px), K, D, out)
     return out
 
 

@@ -50,6 +50,8 @@ int orc_lk(const uint8_t* prev, const uint8_t* next, int w, int h, int stride,
 /* cv::undistortPoints(src, dst, K, D) with no R/P: pixel -> undistorted normalized, Tracker.cc:100-132.
  * K = {fx,fy,cx,cy} (float32-rounded), D = {k1,k2,p1,p2,k3}. */
 void orc_undistort(const float* px, int n, const float* K4, const float* D5, float* out);
+/* cv::fisheye::undistortPoints(src, dst, K, D) (Tracker.cc:119), D4 = (k1..k4). */
+void orc_undistort_fisheye(const float* px, int n, const float* K4, const float* D4, float* out);
 
 /* ---------- glibc rand() restatement (oracle/ransac.c) ---------- */
 typedef struct { int32_t r[34]; int f, b; } orc_rand_t;
@@ -93,6 +95,7 @@ typedef struct {
     /* FeatureDetector.cc:29-48 */
     int   img_w, img_h;
     double min_dist; int block_x, block_y;
+    int   is_fisheye;                 /* Camera.Fisheye, Tracker.cc:119 */
 } orc_tracker_cfg_t;
 
 orc_tracker_t* orc_tracker_create(const orc_tracker_cfg_t* cfg);

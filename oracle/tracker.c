@@ -92,7 +92,8 @@ static void undist(const orc_tracker_t* t, const float* px, int n, float* out)
 {
     float K[4] = {t->cfg.fx, t->cfg.fy, t->cfg.cx, t->cfg.cy};
     float D[5] = {t->cfg.k1, t->cfg.k2, t->cfg.p1, t->cfg.p2, t->cfg.k3};
-    orc_undistort(px, n, K, D, out);
+    if (t->cfg.is_fisheye) orc_undistort_fisheye(px, n, K, D, out);
+    else orc_undistort(px, n, K, D, out);
 }
 
 static void emit(orc_tracker_t* t, uint8_t type, int slot)

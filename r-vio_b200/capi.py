@@ -44,7 +44,7 @@ class UpdateInfo(C.Structure):
 
 # every symbol include/rvio_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "rvio_tracker_create", "rvio_tracker_destroy", "rvio_tracker_track", "rvio_tracker_track_dev",
+    "rvio_tracker_create", "rvio_tracker_destroy", "rvio_tracker_track", "rvio_tracker_track_dev", "rvio_tracker_track_begin", "rvio_tracker_lk_results", "rvio_tracker_track_finish",
     "rvio_tracker_get_image", "rvio_tracker_n_free", "rvio_tracker_get_tracked_px", "rvio_tracker_seed",
     "rvio_tracker_refill", "rvio_tracker_commit", "rvio_tracker_get_update_count", "rvio_tracker_get_update_lists",
     "rvio_tracker_get_debug", "rvio_tracker_get_ransac_debug", "rvio_tracker_get_pyramid",
@@ -79,6 +79,9 @@ def lib():
     L.rvio_tracker_destroy.restype = None
     L.rvio_tracker_track.argtypes = [vp, u8, ci, ci, ci, ci, vp, ci]
     L.rvio_tracker_track_dev.argtypes = [vp, vp, ci, vp, ci]
+    L.rvio_tracker_track_begin.argtypes = [vp, u8, ci, ci, ci, ci, vp, ci, ci, ci]
+    L.rvio_tracker_lk_results.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi]
+    L.rvio_tracker_track_finish.argtypes = [vp]
     L.rvio_tracker_get_image.argtypes = [vp, u8, ci]
     L.rvio_tracker_n_free.argtypes = [vp, pi]
     L.rvio_tracker_get_tracked_px.argtypes = [vp, f32, pi]
@@ -142,7 +145,7 @@ def tracker_cfg(cfg) -> TrackerCfg:
     t.width, t.height = cfg.width, cfg.height
     for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3"):
         setattr(t, k, float(np.float32(getattr(cfg, k))))
-    t.is_rgb, t.is_fisheye, t.enable_equalizer = 0, 0, cfg.enable_equalizer
+    t.is_rgb, t.is_fisheye, t.enable_equalizer = 0, int(getattr(cfg, "fisheye", 0)), cfg.enable_equalizer
     t.n_features, t.max_track_len, t.min_track_len = cfg.n_features, cfg.max_track_len, cfg.min_track_len
     t.use_sampson, t.inlier_thr, t.small_angle = cfg.use_sampson, cfg.inlier_thr, cfg.small_angle
     t.T_BC0 = (C.c_double * 16)(*cfg.T_BC0)

@@ -360,23 +360,6 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
 // ------------------------------------------------------------------------------------------------
 // k_find_newer_refill: FeatureDetector::FindNewer (one warp per grid cell) + Tracker refill, single CTA.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void f_undistort(const CamParams& c, float u_, float v_, float* ox, float* oy)
-{
-    const double u = (double)u_, v = (double)v_;
-    double x = (u - c.cx) * c.ifx, y = (v - c.cy) * c.ify;
-    const double x0 = x, y0 = y;
-    for (int j = 0; j < 5; ++j) {
-        const double r2 = x * x + y * y;
-        const double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
-        if (icdist < 0) { x = (u - c.cx) * c.ifx; y = (v - c.cy) * c.ify; break; }
-        const double dX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
-        const double dY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
-        x = (x0 - dX) * icdist;
-        y = (y0 - dY) * icdist;
-    }
-    *ox = (float)x; *oy = (float)y;
-}
-
 __device__ __forceinline__ int fn_cell(const FindNewerParams& Q, float2 p)
 {
     // FeatureDetector.cc:83-91 / :101-105 ; returns -1 outside the grid area
@@ -454,7 +437,7 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
             const int slot = B.freeq[(head + r) % (B.F + 1)];
             const float2 p = Q.cand[k];
             float ux, uy;
-            f_undistort(Q.cam, p.x, p.y, &ux, &uy);
+            cam_undistort(Q.cam, p.x, p.y, &ux, &uy);
             B.slots_new[n_new0 + r] = slot;
             B.feats_new[n_new0 + r] = p;
             B.pts1_new[n_new0 + r] = make_float2(ux, uy);

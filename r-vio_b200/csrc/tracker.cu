@@ -156,6 +156,7 @@ struct LKParams {
     const float2* feats;
     int n;                // number of features to track (upper bound when n_dev is set)
     const int* n_dev;     // optional: the count lives on the device (fused pipeline / frame graphs)
+    int first, last;      // feature index range of this launch (feature sharding across GPUs; [0, INT_MAX) otherwise)
     float2* out;
     uint8_t* status;
     float2* un;
@@ -188,25 +189,6 @@ struct LKWarpSmem {
 
 constexpr int kLKWarps = 2;
 
-__device__ __forceinline__ void undistort_point(const CamParams& c, float u_, float v_, float* ox, float* oy)
-{
-    // cv::undistortPoints, 5 fixed-point iterations in double (Tracker.cc:117)
-    const double u = (double)u_, v = (double)v_;
-    double x = (u - c.cx) * c.ifx, y = (v - c.cy) * c.ify;
-    const double x0 = x, y0 = y;
-    for (int j = 0; j < 5; ++j) {
-        const double r2 = x * x + y * y;
-        const double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
-        if (icdist < 0) { x = (u - c.cx) * c.ifx; y = (v - c.cy) * c.ify; break; }
-        const double dX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
-        const double dY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
-        x = (x0 - dX) * icdist;
-        y = (y0 - dY) * icdist;
-    }
-    *ox = (float)x;
-    *oy = (float)y;
-}
-
 __device__ __forceinline__ void lk_weights(float a, float b, int* w00, int* w01, int* w10, int* w11)
 {
     const float s = 16384.f;
@@ -235,8 +217,8 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
 {
     __shared__ LKWarpSmem smem_all[kLKWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int pt = blockIdx.x * kLKWarps + wib;
-    if (pt >= (P.n_dev ? *P.n_dev : P.n)) return;   // whole warp exits together
+    const int pt = P.first + blockIdx.x * kLKWarps + wib;
+    if (pt >= (P.n_dev ? *P.n_dev : P.n) || pt >= P.last) return;   // whole warp exits together
     LKWarpSmem& S = smem_all[wib];
     const unsigned FULL = 0xffffffffu;
     // pixel ownership
@@ -510,7 +492,7 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
         P.out[pt] = make_float2(outx, outy);
         P.status[pt] = (uint8_t)status;
         float ux, uy;
-        undistort_point(P.cam, outx, outy, &ux, &uy);      // all points, also status 0 (Tracker.cc:253)
+        cam_undistort(P.cam, outx, outy, &ux, &uy);      // all points, also status 0 (Tracker.cc:253)
         P.un[pt] = make_float2(ux, uy);
     }
 }
@@ -784,7 +766,7 @@ __global__ void k_seed(TrackerBuffers B, const float2* __restrict__ px, int n, C
     if (i < n) {
         const float2 p = px[i];
         float ux, uy;
-        undistort_point(cam, p.x, p.y, &ux, &uy);
+        cam_undistort(cam, p.x, p.y, &ux, &uy);
         B.feats_new[i] = p;
         B.slots_new[i] = i;
         B.pts1_new[i] = make_float2(ux, uy);
@@ -813,7 +795,7 @@ __global__ void k_refill(TrackerBuffers B, const float2* __restrict__ px, int n_
         const int slot = B.freeq[(head + k) % (B.F + 1)];
         const float2 p = px[k];
         float ux, uy;
-        undistort_point(cam, p.x, p.y, &ux, &uy);
+        cam_undistort(cam, p.x, p.y, &ux, &uy);
         B.slots_new[n_new + k] = slot;
         B.feats_new[n_new + k] = p;
         B.pts1_new[n_new + k] = make_float2(ux, uy);
@@ -844,6 +826,7 @@ struct rvio_tracker {
     int n_track;                // host mirror of mnFeatsToTrack
     int last_n;                 // features fed to LK in the last track()
     bool frame_open;            // track() ran, commit() pending
+    bool shard_open;            // track_begin() ran, track_finish() pending
     CamParams cam;
     double Ric[9];
     // device memory
@@ -925,7 +908,10 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     RVIO_ARG_CHECK(cfg && out);
     RVIO_ARG_CHECK(cfg->width > 0 && cfg->height > 0 && cfg->n_features > 0);
     RVIO_ARG_CHECK(cfg->max_track_len >= 2 && cfg->min_track_len >= 1);
-    if (cfg->is_fisheye) { set_error("rvio_tracker_create", "fisheye model not implemented (Tracker.cc:119)"); return RVIO_ERR_ARG; }
+    if (cfg->is_fisheye && cfg->k3 != 0.f) {    // the reference would hand cv::fisheye five coefficients: OpenCV asserts D.total() == 4
+        set_error("rvio_tracker_create", "Camera.Fisheye with Camera.k3 != 0: cv::fisheye::undistortPoints takes exactly 4 coefficients (Tracker.cc:56-61,119)");
+        return RVIO_ERR_ARG;
+    }
     int rc = require_b200(device);
     if (rc != RVIO_OK) return rc;
     rvio_tracker* t = new (std::nothrow) rvio_tracker();
@@ -934,14 +920,14 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     t->W = cfg->width; t->H = cfg->height; t->F = cfg->n_features;
     t->Fu = (cfg->n_features + 1) / 2;                     // ceil(.5*nFeatures), Tracker.cc:74
     t->Lmax = cfg->max_track_len; t->Lmin = cfg->min_track_len;
-    t->first = true; t->n_track = 0; t->last_n = 0; t->frame_open = false; t->cur_idx = 0;
+    t->first = true; t->n_track = 0; t->last_n = 0; t->frame_open = false; t->shard_open = false; t->cur_idx = 0;
     RVIO_CUDA_TRY(cudaSetDevice(device));
     RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     // camera (float-rounded values widened to double: Tracker.cc:39-61)
     CamParams& c = t->cam;
     c.fx = cfg->fx; c.fy = cfg->fy; c.cx = cfg->cx; c.cy = cfg->cy;
     c.ifx = 1. / c.fx; c.ify = 1. / c.fy;
-    c.k1 = cfg->k1; c.k2 = cfg->k2; c.p1 = cfg->p1; c.p2 = cfg->p2; c.k3 = cfg->k3;
+    c.k1 = cfg->k1; c.k2 = cfg->k2; c.p1 = cfg->p1; c.p2 = cfg->p2; c.k3 = cfg->k3; c.fisheye = cfg->is_fisheye ? 1 : 0;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) t->Ric[3 * i + j] = cfg->T_BC0[4 * i + j];   // Ransac.cc:41-46
     // CLAHE geometry (OpenCV CLAHE_Impl::apply)
@@ -967,7 +953,7 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     const size_t F = (size_t)t->F;
 #define A(p, n) if ((rc = dalloc(t, &(p), (n))) != RVIO_OK) return rc
     A(B.feats, F); A(B.slots, F); A(B.pts1, F); A(B.feats_new, F); A(B.slots_new, F); A(B.pts1_new, F);
-    A(B.lk, F); A(B.un, F); A(B.status, F); A(B.flags, F);
+    A(B.lk, F + 64); A(B.un, F + 64); A(B.status, F + 64); A(B.flags, F);     // + 64: equal-sized shards of an all-gather may overhang F
     A(B.hist, F * B.hist_cap); A(B.hist_head, F); A(B.hist_len, F); A(B.freeq, F + 1);
     A(B.up_types, (size_t)t->Fu + 1); A(B.up_off, (size_t)t->Fu + 2); A(B.up_xy, ((size_t)t->Fu + 1) * t->Lmax);
     A(B.cand, 2 * F); A(B.two_points, 32); A(B.n_inliers, 16); A(B.hyp, 16 * 9); A(B.sc, 1);
@@ -1052,7 +1038,8 @@ static void host_gyro_rotation(const double* Ric, const double* imu, int n_imu, 
 // Enqueues one frame (no synchronisation).  dev_count: the number of features to track is read from the device scalars
 // (sc->n_new of the previous frame) instead of the host mirror, which makes the launch parameters frame-invariant (the
 // fused pipeline replays this sequence as a CUDA graph).
-static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu, bool dev_count = false)
+static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pitch, const double* imu, int n_imu, bool dev_count = false,
+                           int shard_rank = 0, int shard_world = 1, bool finish = true)
 {
     RVIO_ARG_CHECK(n_imu >= 0 && n_imu <= t->imu_cap);
     cudaStream_t s = t->stream;
@@ -1087,7 +1074,15 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     lp.n = dev_count ? t->F : n; lp.n_dev = dev_count ? &t->B.sc->n_new : nullptr;
     lp.un = t->B.un; lp.cam = t->cam; lp.max_iter = 30; lp.eps_sq_f = 0.f; lp.eps_sq = 1e-2 * 1e-2;
     lp.min_eig_thr = 1e-3f;
-    RVIO_LAUNCH(k_lk, div_up(lp.n, kLKWarps), kLKWarps * 32, 0, s, lp);
+    lp.first = 0; lp.last = 0x7fffffff;
+    int n_lk = lp.n;
+    if (shard_world > 1) {                                   // equal shards of ceil(F / world) feature indices
+        const int S = div_up(t->F, shard_world);
+        lp.first = shard_rank * S; lp.last = lp.first + S;
+        n_lk = S;
+    }
+    RVIO_LAUNCH(k_lk, div_up(n_lk, kLKWarps), kLKWarps * 32, 0, s, lp);
+    if (!finish) { RVIO_ENQ(cudaGetLastError()); return RVIO_OK; }
     RansacParams rp;
     rp.B = t->B; rp.n = n; rp.n_dev = lp.n_dev; rp.use_sampson = t->cfg.use_sampson;
     rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
@@ -1138,6 +1133,51 @@ extern "C" int rvio_tracker_track_dev(rvio_tracker* t, const uint8_t* img_dev, i
     RVIO_ARG_CHECK(n_imu == 0 || imu);
     RVIO_CUDA_TRY(cudaSetDevice(t->device));
     return tracker_run(t, img_dev, pitch_bytes, imu, n_imu);
+}
+
+// ---- feature-sharded tracking: LK on this rank's share of the feature indices, the caller all-gathers the
+//      per-feature LK results between _begin and _finish, RANSAC + bookkeeping then run replicated on the complete arrays.
+extern "C" int rvio_tracker_track_begin(rvio_tracker* t, const uint8_t* img, int width, int height, int stride_bytes,
+                                        int channels, const double* imu, int n_imu, int rank, int world)
+{
+    RVIO_ARG_CHECK(t && img);
+    RVIO_ARG_CHECK(width == t->W && height == t->H);
+    RVIO_ARG_CHECK(channels == 1 || channels == 3 || channels == 4);
+    RVIO_ARG_CHECK(stride_bytes >= width * channels);
+    RVIO_ARG_CHECK(n_imu == 0 || imu);
+    RVIO_ARG_CHECK(world >= 1 && world <= 64 && rank >= 0 && rank < world);
+    RVIO_CUDA_TRY(cudaSetDevice(t->device));
+    const int rcu = upload_image(t, img, width, height, stride_bytes, channels);
+    if (rcu != RVIO_OK) return rcu;
+    const int rc = tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu, false, rank, world, false);
+    if (rc < 0) return rc;
+    t->shard_open = rc == RVIO_OK;
+    RVIO_CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return rc;
+}
+
+extern "C" int rvio_tracker_lk_results(rvio_tracker* t, int world, void** lk_px_dev, void** undist_dev, void** status_dev, int* shard)
+{
+    RVIO_ARG_CHECK(t && world >= 1 && world <= 64);
+    if (lk_px_dev) *lk_px_dev = t->B.lk;
+    if (undist_dev) *undist_dev = t->B.un;
+    if (status_dev) *status_dev = t->B.status;
+    if (shard) *shard = div_up(t->F, world);
+    return RVIO_OK;
+}
+
+extern "C" int rvio_tracker_track_finish(rvio_tracker* t)
+{
+    RVIO_ARG_CHECK(t);
+    if (!t->shard_open) { set_error("rvio_tracker_track_finish", "no sharded frame open"); return RVIO_ERR_STATE; }
+    t->shard_open = false;
+    RVIO_CUDA_TRY(cudaSetDevice(t->device));
+    RansacParams rp;
+    rp.B = t->B; rp.n = t->last_n; rp.n_dev = nullptr; rp.use_sampson = t->cfg.use_sampson;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
+    RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, t->stream, rp);
+    RVIO_CUDA_TRY(cudaGetLastError());
+    return sync_scalars(t);
 }
 
 extern "C" int rvio_tracker_get_image(rvio_tracker* t, uint8_t* out, int out_stride)

@@ -36,7 +36,55 @@ struct Pyramid {
 
 struct CamParams {                   // float-rounded intrinsics widened to double (Tracker.cc:39-61)
     double fx, fy, cx, cy, ifx, ify, k1, k2, p1, p2, k3;
+    int fisheye;                     // Camera.Fisheye: (k1, k2, p1, p2) are the equidistant model's k1..k4 (Tracker.cc:119)
 };
+
+// Tracker::UndistortAndNormalize for one point (Tracker.cc:100-132): pixel -> undistorted normalized coordinates.
+//   radtan   cv::undistortPoints, 5 fixed-point iterations in double
+//   fisheye  cv::fisheye::undistortPoints (OpenCV 4.x): Newton on theta, at most 10 iterations / |fix| < 1e-8,
+//            scale = tan(theta) / theta_d; (-1e6, -1e6) when not converged or theta changed sign
+// Both translation units that use it are compiled with -fmad=false (the host libraries evaluate these in plain double).
+__device__ __forceinline__ void cam_undistort(const CamParams& c, float u_, float v_, float* ox, float* oy)
+{
+    const double u = (double)u_, v = (double)v_;
+    if (c.fisheye) {
+        const double pwx = (u - c.cx) / c.fx, pwy = (v - c.cy) / c.fy;
+        const double half_pi = 3.1415926535897932384626433832795 / 2.;
+        double theta_d = sqrt(pwx * pwx + pwy * pwy);
+        theta_d = fmin(fmax(-half_pi, theta_d), half_pi);
+        bool converged = false;
+        double theta = theta_d, scale = 0.0;
+        if (fabs(theta_d) > 1e-8) {
+            for (int j = 0; j < 10; ++j) {
+                const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+                const double a = c.k1 * t2, b = c.k2 * t4, cc = c.p1 * t6, d = c.p2 * t8;
+                const double fix = (theta * (1 + a + b + cc + d) - theta_d) / (1 + 3 * a + 5 * b + 7 * cc + 9 * d);
+                theta = theta - fix;
+                if (fabs(fix) < 1e-8) { converged = true; break; }
+            }
+            scale = tan(theta) / theta_d;
+        } else {
+            converged = true;
+        }
+        const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+        if (converged && !flipped) { *ox = (float)(pwx * scale); *oy = (float)(pwy * scale); }
+        else { *ox = -1000000.0f; *oy = -1000000.0f; }
+        return;
+    }
+    double x = (u - c.cx) * c.ifx, y = (v - c.cy) * c.ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+        if (icdist < 0) { x = (u - c.cx) * c.ifx; y = (v - c.cy) * c.ify; break; }
+        const double dX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+        const double dY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    *ox = (float)x;
+    *oy = (float)y;
+}
 
 // Device-resident scalar state of one tracker (mirrors a handful of Tracker members).
 struct TrackerScalars {

@@ -141,14 +141,27 @@ class Tracker:
         return out
 
     # -- Tracker::track ---------------------------------------------------------------------
-    def track(self, im, lImuData, detections=None):
+    def track(self, im, lImuData, detections=None, shard=None):
         """Tracker::track (Tracker.cc:179-396).  `detections`: optional pre-computed corner list that replaces the
-        detector call for this frame (seed list on the first image, FindNewer output afterwards)."""
+        detector call for this frame (seed list on the first image, FindNewer output afterwards).
+        `shard` = (rank, world, exchange): feature-sharded form -- LK runs for this rank's share of the feature
+        indices only, `exchange(lk_ptr, un_ptr, status_ptr, shard_size)` all-gathers the three per-feature arrays in
+        place (device pointers), RANSAC + bookkeeping then run replicated."""
         im = np.ascontiguousarray(im, np.uint8)
         ch = 1 if im.ndim == 2 else im.shape[2]
         imu = np.ascontiguousarray(lImuData, np.float64).reshape(-1, 8)
-        rc = capi.check(self.L.rvio_tracker_track(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
-                                                  imu.ctypes.data, len(imu)), "rvio_tracker_track")
+        if shard is None:
+            rc = capi.check(self.L.rvio_tracker_track(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
+                                                      imu.ctypes.data, len(imu)), "rvio_tracker_track")
+        else:
+            rank, world, exchange = shard
+            rc = capi.check(self.L.rvio_tracker_track_begin(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
+                                                            imu.ctypes.data, len(imu), rank, world), "rvio_tracker_track_begin")
+            if rc == capi.OK:
+                lk, un, st, S = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+                capi.check(self.L.rvio_tracker_lk_results(self.h, world, C.byref(lk), C.byref(un), C.byref(st), C.byref(S)))
+                exchange(lk.value, un.value, st.value, S.value)
+                capi.check(self.L.rvio_tracker_track_finish(self.h), "rvio_tracker_track_finish")
         if rc == capi.NO_FEATURES:
             return rc
         if rc == capi.FIRST_IMAGE:
@@ -170,6 +183,13 @@ class Tracker:
                     capi.check(self.L.rvio_tracker_refill(self.h, np.ascontiguousarray(newer), len(newer), C.byref(used)))
         capi.check(self.L.rvio_tracker_commit(self.h), "rvio_tracker_commit")
         return rc
+
+
+def shard_range(n_features: int, rank: int, world: int):
+    """Feature indices [lo, hi) whose LK rank `rank` of `world` computes (rvio_tracker_track_begin): equal shards of
+    ceil(nFeatures / world) indices, so that the exchange is one fixed-size all-gather."""
+    S = -(-n_features // world)
+    return rank * S, min((rank + 1) * S, n_features), S
 
 
 class Updater:

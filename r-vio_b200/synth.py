@@ -44,6 +44,7 @@ class Config:
     p1: float = 0.00019359
     p2: float = 1.76187114e-05
     k3: float = 0.0
+    fisheye: int = 0              # Camera.Fisheye (k1, k2, p1, p2 are then the equidistant k1..k4, Tracker.cc:119)
     sigma_px: float = 0.002180293
     sigma_py: float = 0.002186767
     T_BC0: tuple = (0.0148655429818, -0.999880929698, 0.00414029679422, -0.0216401454975,
@@ -66,6 +67,44 @@ class Config:
     thr_angle: float = 0.005
     thr_displ: float = 0.01
     enable_alignment: int = 1
+
+    # reference YAML key -> field (config/rvio_euroc.yaml; System.cc:53-83, Tracker.cc:37-90, Updater.cc:38-53)
+    YAML_KEYS = {
+        "IMU.dps": "imu_rate", "IMU.sigma_g": "sigma_g", "IMU.sigma_wg": "sigma_wg", "IMU.sigma_a": "sigma_a",
+        "IMU.sigma_wa": "sigma_wa", "IMU.nG": "gravity", "IMU.nSmallAngle": "small_angle",
+        "Camera.fps": "fps", "Camera.Fisheye": "fisheye", "Camera.width": "width", "Camera.height": "height",
+        "Camera.fx": "fx", "Camera.fy": "fy", "Camera.cx": "cx", "Camera.cy": "cy", "Camera.k1": "k1", "Camera.k2": "k2",
+        "Camera.p1": "p1", "Camera.p2": "p2", "Camera.k3": "k3", "Camera.sigma_px": "sigma_px", "Camera.sigma_py": "sigma_py",
+        "Camera.T_BC0": "T_BC0", "Camera.nTimeOffset": "time_offset",
+        "Tracker.nFeatures": "n_features", "Tracker.nMaxTrackingLength": "max_track_len",
+        "Tracker.nMinTrackingLength": "min_track_len", "Tracker.nMinDist": "min_dist", "Tracker.nQualLvl": "qual_lvl",
+        "Tracker.nBlockSizeX": "block_x", "Tracker.nBlockSizeY": "block_y", "Tracker.EnableEqualizer": "enable_equalizer",
+        "Tracker.UseSampson": "use_sampson", "Tracker.nInlierThrd": "inlier_thr",
+        "INI.nThresholdAngle": "thr_angle", "INI.nThresholdDispl": "thr_displ", "INI.EnableAlignment": "enable_alignment",
+    }
+
+    @classmethod
+    def from_yaml(cls, path: str) -> "Config":
+        """Reads the reference's OpenCV-FileStorage YAML (the `%YAML:1.0` header and `!!opencv-matrix` tags are
+        stripped; a matrix keeps its `data` list)."""
+        import yaml
+        text = open(path).read()
+        text = "\n".join(l for l in text.splitlines() if not l.startswith("%YAML")).replace("!!opencv-matrix", "")
+        doc = yaml.safe_load(text) or {}
+        c = cls()
+        types = {f.name: f.type for f in dataclasses.fields(cls)}
+        for key, field in cls.YAML_KEYS.items():
+            if key not in doc:
+                continue
+            v = doc[key]
+            if isinstance(v, dict):
+                v = tuple(float(e) for e in v["data"])
+            elif types.get(field) in (int, "int"):
+                v = int(v)
+            else:
+                v = float(v)
+            setattr(c, field, v)
+        return c
 
     @property
     def window(self) -> int:          # System.cc:71-72

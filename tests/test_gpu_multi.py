@@ -20,3 +20,17 @@ def test_sharded_update_nccl():
                          capture_output=True, text=True, timeout=600, env=dict(os.environ, RVIO_TEST_FEATS="192"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "sharded update ok" in out.stdout
+
+
+def test_sharded_tracker_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                          "--master-port", "29534", os.path.join(ROOT, "tests", "dist_sharded_tracker.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded tracker ok" in out.stdout
+

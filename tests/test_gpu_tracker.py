@@ -89,3 +89,83 @@ def test_tracker_stress_1280x720():
     s = _run_stream(cfg, 14, 20260924, 0, check_pyr=True)
     print("config3 stream stats:", s)
     assert s["frames"] >= 10
+
+
+def test_tracker_stream_fisheye_model():
+    """Camera.Fisheye: 1 (Tracker.cc:119): same stream, the equidistant undistortion in every stage that normalises pixels
+    (LK epilogue, seeding, refill) -- undistorted coordinates, RANSAC votes and update lists stay bit-identical."""
+    cfg = synth.baseline_config(1)
+    cfg.fisheye = 1
+    cfg.k1, cfg.k2, cfg.p1, cfg.p2, cfg.k3 = -0.0127, 0.0154, -0.0201, 0.0072, 0.0
+    s = _run_stream(cfg, 30, 20260925, 0, check_pyr=False)
+    print("fisheye stream stats:", s)
+    assert s["frames"] >= 25 and s["emitted"] > 0
+
+
+def test_tracker_feature_sharding_matches_unsharded():
+    """Multi-GPU form on one device: two tracker handles play ranks 0 and 1 of a 2-way feature-sharded stream
+    (LK for half of the feature indices each), the per-feature LK arrays are exchanged slice by slice (what the NCCL
+    all-gather does across GPUs, tests/dist_sharded_tracker.py), RANSAC + bookkeeping run on both: every observable of both
+    ranks must equal the unsharded tracker's, bit for bit."""
+    import ctypes as C
+    cfg = synth.baseline_config(1)
+    n_frames = 20
+    st = synth.Stream(cfg, n_frames, 20260927, t_static=0.25)
+    det = lambda img, n, s: orc.detect_with_subpix(img, n, s, cfg)
+    ref = host.Tracker(cfg, 0, det)
+    ranks = [host.Tracker(cfg, 0, det) for _ in range(2)]
+    L = capi.lib()
+    cudart = C.cdll.LoadLibrary("libcudart.so.12")
+    world = 2
+    consumed = 0
+    checked = 0
+    for i in range(n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        if len(imu) < 2:
+            continue
+        im = st.frames[i]
+        rc_ref = ref.track(im, imu)
+        imu_c = np.ascontiguousarray(imu, np.float64).reshape(-1, 8)
+        rcs, ptrs = [], []
+        for r, t in enumerate(ranks):
+            rc = capi.check(L.rvio_tracker_track_begin(t.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], 1,
+                                                       imu_c.ctypes.data, len(imu_c), r, world))
+            rcs.append(rc)
+            lk, un, stt, S = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+            capi.check(L.rvio_tracker_lk_results(t.h, world, C.byref(lk), C.byref(un), C.byref(stt), C.byref(S)))
+            ptrs.append((lk.value, un.value, stt.value, S.value))
+        assert rcs[0] == rcs[1] == (capi.FIRST_IMAGE if rc_ref == 1 else rc_ref)
+        if rcs[0] == capi.OK:
+            S = ptrs[0][3]
+            assert S == host.shard_range(cfg.n_features, 0, world)[2]
+            for src in range(world):                       # rank src's slice -> the other rank
+                dst = 1 - src
+                for k, item in ((0, 8), (1, 8), (2, 1)):
+                    cudart.cudaMemcpy(C.c_void_p(ptrs[dst][k] + src * S * item), C.c_void_p(ptrs[src][k] + src * S * item),
+                                      C.c_size_t(S * item), 3)
+            for t in ranks:
+                capi.check(L.rvio_tracker_track_finish(t.h))
+        # the remaining host flow (seed / refill / commit) is the ordinary one, replicated
+        for t in ranks:
+            if rcs[0] == capi.FIRST_IMAGE:
+                pts = np.ascontiguousarray(det(t.equalized_image(), cfg.n_features, 1), np.float32).reshape(-1, 2)
+                capi.check(L.rvio_tracker_seed(t.h, pts, len(pts)))
+            elif rcs[0] == capi.OK and t.n_free() > 0:
+                newer = host.find_newer(cfg, det(t.equalized_image(), cfg.n_features, 2), t.tracked_px())
+                if len(newer):
+                    used = C.c_int()
+                    capi.check(L.rvio_tracker_refill(t.h, np.ascontiguousarray(newer), len(newer), C.byref(used)))
+            if rcs[0] != capi.NO_FEATURES:
+                capi.check(L.rvio_tracker_commit(t.h))
+        if rcs[0] == capi.OK:
+            d0 = ref.debug()
+            t0, o0, x0 = ref.update_lists()
+            for t in ranks:
+                d1 = t.debug()
+                assert np.array_equal(d0["status"], d1["status"]) and np.array_equal(d0["flags"], d1["flags"]), i
+                assert np.array_equal(_bits(d0["lk"]), _bits(d1["lk"])) and np.array_equal(_bits(d0["un"]), _bits(d1["un"])), i
+                t1, o1, x1 = t.update_lists()
+                assert np.array_equal(t0, t1) and np.array_equal(o0, o1) and np.array_equal(_bits(x0), _bits(x1)), i
+            checked += 1
+    assert checked >= 12
+

@@ -96,3 +96,57 @@ def test_cpp_host_adaptor_runs_on_gpu(tmp_path):
     exe = _build_selfcheck(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "GPU path ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_io_formats_roundtrip(tmp_path):
+    """EuRoC ASL layout in, stamped_pose_ests.dat / time_cost.dat out.  A synthetic stream written as ASL
+    and read back must reproduce the frames and, image by image, the IMU rows InputBuffer::GetMeasurements hands out
+    (InputBuffer.cc:53-81), with dt = stamp difference to the previous message (rvio_mono.cc:103-108)."""
+    from rvio_b200 import io_formats
+    cfg = synth.baseline_config(0)
+    cfg.width, cfg.height = 160, 120
+    st = synth.Stream(cfg, 6, 5, t_static=0.1)
+    io_formats.write_asl(str(tmp_path), st.frame_t, st.frames, st.imu)
+    rd = io_formats.EurocAslReader(str(tmp_path), cfg.time_offset)
+    assert len(rd) == 6
+    consumed = 0
+    seen = 0
+    frames = {round(t, 6): (im, rows) for t, im, rows in rd}
+    for i in range(6):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        if len(imu) < 2:
+            continue
+        im, rows = frames[round(float(st.frame_t[i]), 6)]
+        assert np.array_equal(im, st.frames[i])
+        assert rows.shape == (len(imu), 8)
+        np.testing.assert_allclose(rows[:, :6], imu[:, :6], rtol=0, atol=0)      # repr() round-trips doubles exactly
+        np.testing.assert_allclose(rows[:, 6], imu[:, 6], rtol=0, atol=1e-9)     # stamps are integer nanoseconds
+        seen += 1
+    assert seen >= 4
+    w = io_formats.PoseWriter(str(tmp_path / "out"))
+    w.write(1403715273.262142976, [0.1, -0.2, 0.3, 0, 0, 0.6, 0.8], 1, 0.25, 0.125)
+    w.close()
+    p = io_formats.read_pose_file(str(tmp_path / "out" / "stamped_pose_ests.dat"))
+    assert p.shape == (1, 8) and p[0, 0] == 1403715273.262142976 and p[0, 7] == 0.8
+    assert open(tmp_path / "out" / "time_cost.dat").read().split() == ["1", "0.25", "0.125"]
+
+
+def test_config_from_reference_yaml(tmp_path):
+    """The YAML keys are the reference's (config/rvio_euroc.yaml); written here from the defaults, not read from it."""
+    y = tmp_path / "cfg.yaml"
+    y.write_text("%YAML:1.0\nIMU.dps: 100\nCamera.Fisheye: 1\nCamera.fx: 300.5\nTracker.nFeatures: 321\n"
+                 "Tracker.nMaxTrackingLength: 9\nCamera.T_BC0: !!opencv-matrix\n    rows: 4\n    cols: 4\n    dt: d\n"
+                 "    data: [1, 0, 0, 0.1, 0, 1, 0, 0.2, 0, 0, 1, 0.3, 0, 0, 0, 1]\n")
+    c = synth.Config.from_yaml(str(y))
+    assert (c.imu_rate, c.fisheye, c.fx, c.n_features, c.max_track_len) == (100.0, 1, 300.5, 321, 9)
+    assert c.T_BC0[3] == 0.1 and len(c.T_BC0) == 16 and c.window == 8
+
+
+def test_shard_range_covers_all_features():
+    for F, world in [(200, 2), (200, 3), (2048, 8), (150, 4), (7, 8)]:
+        seen = []
+        for r in range(world):
+            lo, hi, S = host.shard_range(F, r, world)
+            assert S == -(-F // world)
+            seen += list(range(lo, hi))
+        assert seen == list(range(F))

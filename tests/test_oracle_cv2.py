@@ -79,3 +79,23 @@ def test_gray_conversion_formula(gold):
     f = lambda b, g, r: ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
     assert np.array_equal(f(bgr[..., 0], bgr[..., 1], bgr[..., 2]), gold["bgr2gray"])
     assert np.array_equal(f(bgr[..., 2], bgr[..., 1], bgr[..., 0]), gold["rgb2gray"])
+
+
+def test_live_cv2_fisheye_undistort():
+    """cv::fisheye::undistortPoints (Tracker.cc:119, Camera.Fisheye: 1) restated in oracle/img.c, bit for bit against cv2:
+    points all over the image (incl. far outside: the non-converged / clipped branch) and two coefficient sets."""
+    cv2 = pytest.importorskip("cv2")
+    r = np.random.default_rng(11)
+    for D in ([-0.0127, 0.0154, -0.0201, 0.0072], [0.21, -0.35, 0.6, -0.4]):
+        K4 = np.array([458.654, 457.296, 367.215, 248.375], np.float32)
+        D4 = np.array(D, np.float32)
+        px = np.concatenate([np.stack([r.uniform(-50, 800, 3000), r.uniform(-50, 530, 3000)], 1),
+                             np.stack([r.uniform(-4000, 5000, 500), r.uniform(-4000, 5000, 500)], 1),
+                             [[367.215, 248.375], [367.2150001, 248.375]]]).astype(np.float32)
+        K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+        want = cv2.fisheye.undistortPoints(px.reshape(-1, 1, 2), K, D4.reshape(4, 1)).reshape(-1, 2)
+        got = np.empty_like(px)
+        orc.lib().orc_undistort_fisheye(px, len(px), K4, D4, got)
+        bad = (_bits(got) != _bits(want)).any(1)
+        assert not bad.any(), (D, int(bad.sum()), px[bad][:4], got[bad][:4], want[bad][:4])
+
