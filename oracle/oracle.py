@@ -77,6 +77,10 @@ def lib():
     L.orc_scharr.argtypes = [u8, ci, ci, ci, i16]
     L.orc_lk.argtypes = [u8, u8, ci, ci, ci, f32, ci, f32, u8, ci, ci, ci, cd, cd]
     L.orc_lk.restype = ci
+    L.orc_min_eig_map.argtypes = [u8, ci, ci, ci, f32]
+    L.orc_good_features.argtypes = [u8, ci, ci, ci, ci, cd, cd, f32]
+    L.orc_corner_subpix.argtypes = [u8, ci, ci, ci, f32, ci, ci, ci, cd]
+    L.orc_detect_with_subpix.argtypes = [u8, ci, ci, ci, ci, ci, cd, cd, f32]
     L.orc_undistort.argtypes = [f32, ci, f32, f32, f32]
     L.orc_undistort_fisheye.argtypes = [f32, ci, f32, f32, f32]
     L.orc_rand_seed.argtypes = [C.POINTER(RandState), C.c_uint]
@@ -246,6 +250,22 @@ def detect_with_subpix(img, n_corners, s, cfg):
     hw = int(math.floor(.5 * float(np.float32(cfg.min_dist))))
     cv2.cornerSubPix(img, c, (hw, hw), (-1, -1), (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 1e-2))
     return c.reshape(-1, 2)
+
+
+def detect_restated(img, n_corners, s, cfg):
+    """FeatureDetector::DetectWithSubPix through the C restatement (oracle/detector.c) instead of cv2."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((max(n_corners, 1), 2), np.float32)
+    n = lib().orc_detect_with_subpix(img, img.shape[1], img.shape[0], img.strides[0], n_corners, s,
+                                     float(np.float32(cfg.qual_lvl)), float(np.float32(cfg.min_dist)), out)
+    return out[:n].copy()
+
+
+def min_eig_map(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    e = np.empty(img.shape, np.float32)
+    lib().orc_min_eig_map(img, img.shape[1], img.shape[0], img.strides[0], e)
+    return e
 
 
 def find_newer(cfg, corners, ref):

@@ -123,6 +123,12 @@ void orc_tracker_seed(orc_tracker_t* t, const float* px, int n);
 int  orc_tracker_refill(orc_tracker_t* t, const float* px, int n);
 void orc_tracker_commit(orc_tracker_t* t);
 
+/* ---------- detector (oracle/detector.c), FeatureDetector.cc:55-75 via OpenCV imgproc (restated; see the file header) */
+void orc_min_eig_map(const uint8_t* img, int w, int h, int stride, float* eig);     /* cv::cornerMinEigenVal(img, 3, 3) */
+int  orc_good_features(const uint8_t* img, int w, int h, int stride, int max_corners, double quality, double min_dist, float* out_xy);
+void orc_corner_subpix(const uint8_t* img, int w, int h, int stride, float* xy, int n, int half_win, int max_iter, double eps);
+int  orc_detect_with_subpix(const uint8_t* img, int w, int h, int stride, int n_corners, int s, double quality, double min_dist, float* out_xy);
+
 /* FeatureDetector::FindNewer grid filter (FeatureDetector.cc:78-150). Returns number kept, writes px. */
 int  orc_find_newer(const orc_tracker_cfg_t* cfg, const float* corners, int n_corners,
                     const float* ref, int n_ref, float* out);
