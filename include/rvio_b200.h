@@ -85,6 +85,11 @@ int rvio_tracker_track_begin(rvio_tracker* trk, const uint8_t* img, int width, i
 int rvio_tracker_lk_results(rvio_tracker* trk, int world, void** lk_px_dev, void** undist_dev, void** status_dev, int* shard);
 int rvio_tracker_track_finish(rvio_tracker* trk);
 
+/* FeatureDetector::DetectWithSubPix(equalised current image, nFeatures, s) ON THE DEVICE (FeatureDetector.cc:55-75:
+ * cv::goodFeaturesToTrack(quality = Tracker.nQualLvl, minDistance = s * Tracker.nMinDist) + cv::cornerSubPix(half window
+ * floor(.5 nMinDist), 30 iterations / 0.01)); s = 1 on the first image (Tracker.cc:207), 2 for the refill (:350).
+ * xy_out: up to nFeatures float2 pixels, strongest first; valid between rvio_tracker_track and rvio_tracker_commit. */
+int rvio_tracker_detect(rvio_tracker* trk, int s, float min_dist, float quality, float* xy_out, int* n_out);
 /* Equalised current image (what the reference's detector sees: Tracker.cc:207,350). out: width*height bytes. */
 int rvio_tracker_get_image(rvio_tracker* trk, uint8_t* out, int out_stride_bytes);
 /* mlFreeIndices.size() after bookkeeping (Tracker.cc:344) */
@@ -183,6 +188,7 @@ typedef struct rvio_vio_cfg {
     /* FeatureDetector grid filter (FeatureDetector.cc:31-46) */
     float   min_dist;
     int32_t block_x, block_y;
+    float   qual_lvl;                 /* Tracker.nQualLvl (device detector only) */
 } rvio_vio_cfg;
 
 int  rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** out);
@@ -190,7 +196,9 @@ void rvio_vio_destroy(rvio_vio* vio);
 
 /* One frame.  cand_px: n_cand detector corners (float2 pixels) for THIS image: used as seeds on the first tracked
  * image (Tracker.cc:204-234) and passed through FindNewer on the device afterwards (cand_filtered = 0), or taken as
- * already FindNewer-filtered (cand_filtered = 1).  pose_out = [pGk(3), qkG(4)] (System.cc:369-374); *pose_valid = 0
+ * already FindNewer-filtered (cand_filtered = 1).  n_cand < 0: the corners come from the device detector
+ * (FeatureDetector::DetectWithSubPix on the GPU, beside LK and the update; cand_px is ignored) -- the whole
+ * Tracker::track then runs without the host.  pose_out = [pGk(3), qkG(4)] (System.cc:369-374); *pose_valid = 0
  * while the filter is still initialising (System.cc:183-249). */
 int rvio_vio_step(rvio_vio* vio, const uint8_t* img, int width, int height, int stride_bytes, int channels,
                   const double* imu, int n_imu, const float* cand_px, int n_cand, int cand_filtered,

@@ -12,7 +12,8 @@
  *   threshold (float)(max * quality), 3x3 local maximum on rows/cols 1..n-2, order by (value desc, index desc), greedy
  *   minimum-distance selection on a cell grid, at most nCorners  (== cv2)
  *   cornerSubPix: float32 bilinear 17x17 patch (a11*p00 + a12*p01 + a21*p10 + a22*p11, left to right, no fma), float32
- *   gradients, double accumulation in row-major window order.
+ *   gradients, double accumulation: 32 strided partial sums (window index mod 32) combined by an xor butterfly -- the
+ *   order a warp produces; OpenCV adds row-major, the difference is O(1e-16) relative.
  * Pinned against cv2 4.13 in tests/test_oracle_detector.py (corner sets and sub-pixel positions, stated tolerances). */
 #include "rvio_oracle.h"
 
@@ -183,18 +184,28 @@ void orc_corner_subpix(const uint8_t* img, int w, int h, int stride, float* xy, 
         int iter = 0; double err = 0;
         do {
             rect_subpix(img, w, h, stride, cIx, cIy, pw, pw, patch);
-            double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
-            for (int i = 0; i < ww; ++i)
-                for (int j = 0; j < ww; ++j) {
-                    const double m = mask[i * ww + j];
-                    const double tgx = patch[(i + 1) * pw + j + 2] - patch[(i + 1) * pw + j];
-                    const double tgy = patch[(i + 2) * pw + j + 1] - patch[i * pw + j + 1];
-                    const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
-                    const double px = j - hw, py = i - hw;
-                    a += gxx; b += gxy; c += gyy;
-                    bb1 += gxx * px + gxy * py;
-                    bb2 += gxy * px + gyy * py;
+            /* accumulation order = the CUDA kernel's: window position k = i*ww + j goes to partial sum k % 32 (a lane),
+             * the 32 partials are combined by an xor butterfly (16, 8, 4, 2, 1) */
+            double part[5][32];
+            memset(part, 0, sizeof part);
+            for (int k = 0; k < ww * ww; ++k) {
+                const int i = k / ww, j = k - i * ww, l = k & 31;
+                const double m = mask[k];
+                const double tgx = patch[(i + 1) * pw + j + 2] - patch[(i + 1) * pw + j];
+                const double tgy = patch[(i + 2) * pw + j + 1] - patch[i * pw + j + 1];
+                const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                const double px = j - hw, py = i - hw;
+                part[0][l] += gxx; part[1][l] += gxy; part[2][l] += gyy;
+                part[3][l] += gxx * px + gxy * py;
+                part[4][l] += gxy * px + gyy * py;
+            }
+            for (int q = 0; q < 5; ++q)
+                for (int msk = 16; msk >= 1; msk >>= 1) {
+                    double nw[32];
+                    for (int l = 0; l < 32; ++l) nw[l] = part[q][l] + part[q][l ^ msk];
+                    memcpy(part[q], nw, sizeof nw);
                 }
+            const double a = part[0][0], b = part[1][0], c = part[2][0], bb1 = part[3][0], bb2 = part[4][0];
             const double det = a * c - b * b;
             if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
             const double scale = 1.0 / det;

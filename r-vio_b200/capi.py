@@ -34,7 +34,8 @@ class VioCfg(C.Structure):
     _fields_ = [("tracker", TrackerCfg), ("updater", UpdaterCfg),
                 ("imu_rate", C.c_double), ("sigma_g", C.c_double), ("sigma_wg", C.c_double), ("sigma_a", C.c_double),
                 ("sigma_wa", C.c_double), ("gravity", C.c_double), ("thr_angle", C.c_double), ("thr_displ", C.c_double),
-                ("enable_alignment", C.c_int32), ("min_dist", C.c_float), ("block_x", C.c_int32), ("block_y", C.c_int32)]
+                ("enable_alignment", C.c_int32), ("min_dist", C.c_float), ("block_x", C.c_int32), ("block_y", C.c_int32),
+                ("qual_lvl", C.c_float)]
 
 
 class UpdateInfo(C.Structure):
@@ -44,7 +45,7 @@ class UpdateInfo(C.Structure):
 
 # every symbol include/rvio_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "rvio_tracker_create", "rvio_tracker_destroy", "rvio_tracker_track", "rvio_tracker_track_dev", "rvio_tracker_track_begin", "rvio_tracker_lk_results", "rvio_tracker_track_finish",
+    "rvio_tracker_create", "rvio_tracker_destroy", "rvio_tracker_track", "rvio_tracker_track_dev", "rvio_tracker_track_begin", "rvio_tracker_lk_results", "rvio_tracker_track_finish", "rvio_tracker_detect",
     "rvio_tracker_get_image", "rvio_tracker_n_free", "rvio_tracker_get_tracked_px", "rvio_tracker_seed",
     "rvio_tracker_refill", "rvio_tracker_commit", "rvio_tracker_get_update_count", "rvio_tracker_get_update_lists",
     "rvio_tracker_get_debug", "rvio_tracker_get_ransac_debug", "rvio_tracker_get_pyramid",
@@ -82,6 +83,7 @@ def lib():
     L.rvio_tracker_track_begin.argtypes = [vp, u8, ci, ci, ci, ci, vp, ci, ci, ci]
     L.rvio_tracker_lk_results.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi]
     L.rvio_tracker_track_finish.argtypes = [vp]
+    L.rvio_tracker_detect.argtypes = [vp, ci, C.c_float, C.c_float, f32, pi]
     L.rvio_tracker_get_image.argtypes = [vp, u8, ci]
     L.rvio_tracker_n_free.argtypes = [vp, pi]
     L.rvio_tracker_get_tracked_px.argtypes = [vp, f32, pi]
@@ -169,4 +171,5 @@ def vio_cfg(cfg) -> VioCfg:
     v.imu_rate, v.sigma_g, v.sigma_wg, v.sigma_a, v.sigma_wa = cfg.imu_rate, cfg.sigma_g, cfg.sigma_wg, cfg.sigma_a, cfg.sigma_wa
     v.gravity, v.thr_angle, v.thr_displ, v.enable_alignment = cfg.gravity, cfg.thr_angle, cfg.thr_displ, cfg.enable_alignment
     v.min_dist, v.block_x, v.block_y = float(np.float32(cfg.min_dist)), cfg.block_x, cfg.block_y
+    v.qual_lvl = float(np.float32(cfg.qual_lvl))
     return v

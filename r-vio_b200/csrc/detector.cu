@@ -1,0 +1,350 @@
+// detector.cu -- FeatureDetector::DetectWithSubPix on the device (reference src/rvio/FeatureDetector.cc:55-75:
+// cv::goodFeaturesToTrack + cv::cornerSubPix on the equalised frame, called from Tracker.cc:207,350).
+// Compiled for sm_100a with -fmad=false; the arithmetic contract is the one written down in oracle/detector.c (the CPU
+// restatement this path is checked against bit for bit; that file is pinned against cv2).
+//   k_det_eig     min-eigenvalue map (Sobel 3 + 3x3 box, float32 / double sums) + global maximum          W*H/1024 CTAs
+//   k_det_nms     threshold (float)(max * quality), 3x3 local maxima -> packed keys (value bits | y | x)    W*H/1024 CTAs
+//   k_det_select  strongest-first blocks: histogram, gather, bitonic sort, greedy minimum-distance selection      1 CTA
+//   k_det_subpix  cornerSubPix, one warp per corner                                                         n/4 CTAs
+#include "common.cuh"
+#include "tracker_kernels.cuh"
+#include "detector_kernels.cuh"
+
+#include <math.h>
+
+namespace rvio {
+
+__device__ __forceinline__ int d_refl101(int i, int n)
+{
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------------ min-eigenvalue map
+__global__ void __launch_bounds__(1024) k_det_eig(DetParams P)
+{
+    __shared__ float s_xx[34][35], s_xy[34][35], s_yy[34][35];
+    __shared__ unsigned s_max;
+    const int W = P.img.w, H = P.img.h;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const float k1 = (float)(1.0 / (255.0 * 4 * 3)), k0 = __fmul_rn(2.f, k1);
+    if (tid == 0) s_max = 0u;
+    // covariance products on the 34 x 34 halo tile; a position outside the image takes the products OF its reflected
+    // position (cv::boxFilter reflects the product images, not the pixels)
+    for (int o = tid; o < 34 * 34; o += 1024) {
+        const int ty = o / 34, tx = o - ty * 34;
+        const int y = d_refl101(y0 + ty - 1, H), x = d_refl101(x0 + tx - 1, W);
+        float xx = 0.f, xy = 0.f, yy = 0.f;
+        if (y < H && x < W && y >= 0 && x >= 0) {
+            const uint8_t* c = P.img.base + (ptrdiff_t)y * P.img.pitch + x;        // the level keeps a reflect-101 border
+            float r[3], q[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint8_t* rp = c + (ptrdiff_t)(k - 1) * P.img.pitch;
+                const float pm = (float)rp[-1], pc = (float)rp[0], pp = (float)rp[1];
+                r[k] = __fsub_rn(pp, pm);
+                q[k] = __fmaf_rn(pp, k1, __fmaf_rn(pc, k0, __fmul_rn(pm, k1)));
+            }
+            const float dx = __fmaf_rn(__fadd_rn(r[0], r[2]), k1, __fmul_rn(r[1], k0));
+            const float dy = __fsub_rn(q[2], q[0]);
+            xx = __fmul_rn(dx, dx); xy = __fmul_rn(dx, dy); yy = __fmul_rn(dy, dy);
+        }
+        s_xx[ty][tx] = xx; s_xy[ty][tx] = xy; s_yy[ty][tx] = yy;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    float e = 0.f;
+    if (x < W && y < H) {
+        double a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                a += (double)s_xx[threadIdx.y + j][threadIdx.x + i];
+                b += (double)s_xy[threadIdx.y + j][threadIdx.x + i];
+                c += (double)s_yy[threadIdx.y + j][threadIdx.x + i];
+            }
+        const float fa = __fmul_rn((float)a, 0.5f), fb = (float)b, fc = __fmul_rn((float)c, 0.5f);
+        const float t = __fsub_rn(fa, fc);
+        e = __fsub_rn(__fadd_rn(fa, fc), sqrtf(__fadd_rn(__fmul_rn(t, t), __fmul_rn(fb, fb))));
+        P.eig[(size_t)y * W + x] = e;
+    }
+    // maximum (the map is >= 0 up to rounding; negative values never win against the 0 start, like cv::minMaxLoc on a
+    // map that contains a positive value)
+    unsigned bits = (e > 0.f) ? __float_as_uint(e) : 0u;
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((tid & 31) == 0 && bits) atomicMax(&s_max, bits);
+    __syncthreads();
+    if (tid == 0 && s_max) atomicMax(&P.ctrl->max_bits, s_max);
+}
+
+// ------------------------------------------------------------------------------------------------ threshold + NMS
+__global__ void __launch_bounds__(1024) k_det_nms(DetParams P)
+{
+    const int W = P.img.w, H = P.img.h;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+    if (x < 1 || y < 1 || x > W - 2 || y > H - 2) return;
+    const float thr = (float)((double)__uint_as_float(P.ctrl->max_bits) * P.quality);
+    const float* e = P.eig + (size_t)y * W + x;
+    const float v = e[0];
+    if (!(v > thr)) return;
+    bool is_max = true;
+#pragma unroll
+    for (int j = -1; j <= 1; ++j)
+#pragma unroll
+        for (int i = -1; i <= 1; ++i) is_max = is_max && !(e[(ptrdiff_t)j * W + i] > v);
+    if (!is_max) return;
+    const int pos = atomicAdd(&P.ctrl->n_cand, 1);
+    if (pos < P.key_cap) P.keys[pos] = ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned)y << 16) | (unsigned)x;
+    else P.ctrl->overflow = 1;
+}
+
+// ------------------------------------------------------------------------------------------------ sort + greedy selection
+// cv::goodFeaturesToTrack walks the local maxima in descending (value, address) order and keeps a corner when no kept corner
+// lies closer than the minimum distance, until max_corners are kept.  Only a prefix of that order is ever looked at, so
+// the candidates are taken block by block from the top of a histogram over the leading float bits: gather <= 4096 keys,
+// bitonic sort, then a warp resolves them 32 at a time (each lane tests its candidate against the kept corners of the 3x3
+// neighbouring cells; the survivors of a batch are settled in rank order).
+constexpr int kDetBlock = 4096, kDetBins = 1024;
+
+__global__ void __launch_bounds__(1024) k_det_select(DetParams P)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ int s_hist[kDetBins];
+    __shared__ int s_lo, s_take, s_count, s_nout, s_stop;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);
+    const int tid = threadIdx.x, lane = tid & 31;
+    int nc = P.ctrl->n_cand;
+    if (nc > P.key_cap) nc = P.key_cap;
+    const unsigned max_bits = P.ctrl->max_bits;
+    const unsigned thr_bits = __float_as_uint((float)((double)__uint_as_float(max_bits) * P.quality));
+    int shift = 17;
+    while ((int)((max_bits >> shift) - (thr_bits >> shift)) + 1 > kDetBins) ++shift;
+    const unsigned base = thr_bits >> shift;
+    const int nbins = (int)((max_bits >> shift) - base) + 1;
+    for (int i = tid; i < kDetBins; i += 1024) s_hist[i] = 0;
+    const int cell = P.cell, gw = P.gw, gh = P.gh;
+    unsigned char* cnt = dsm + (size_t)kDetBlock * 8;
+    unsigned* slots = reinterpret_cast<unsigned*>(cnt + ((gw * gh + 15) & ~15));
+    for (int i = tid; i < gw * gh; i += 1024) cnt[i] = 0;
+    if (tid == 0) { s_nout = 0; s_stop = 0; }
+    __syncthreads();
+    for (int i = tid; i < nc; i += 1024) atomicAdd(&s_hist[(int)(((unsigned)(P.keys[i] >> 32) >> shift) - base)], 1);
+    __syncthreads();
+    const double md2 = P.min_dist * P.min_dist;
+    int hi = nbins;
+    while (hi > 0) {
+        if (tid == 0) {                                   // next block of bins from the top, at most kDetBlock candidates
+            int lo = hi, acc = 0;
+            while (lo > 0 && acc + s_hist[lo - 1] <= kDetBlock) { acc += s_hist[lo - 1]; --lo; }
+            if (lo == hi) { P.ctrl->overflow = 1; s_stop = 1; }    // one bin alone exceeds the block
+            s_lo = lo; s_take = acc; s_count = 0;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const int lo = s_lo, take = s_take;
+        for (int i = tid; i < nc; i += 1024) {
+            const unsigned long long kk = P.keys[i];
+            const int b = (int)(((unsigned)(kk >> 32) >> shift) - base);
+            if (b >= lo && b < hi) keys[atomicAdd(&s_count, 1)] = kk;
+        }
+        int np2 = 32;
+        while (np2 < take) np2 <<= 1;
+        __syncthreads();
+        for (int i = take + tid; i < np2; i += 1024) keys[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1)                // bitonic sort, descending
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += 1024) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long a = keys[i], b = keys[l];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid < 32) {
+            int n_out = s_nout;
+            for (int k0 = 0; k0 < take && n_out < P.max_corners; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < take;
+                const unsigned lo32 = valid ? (unsigned)keys[k] : 0u;
+                const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
+                const int xc = x / cell, yc = y / cell;
+                bool alive = valid;
+                if (alive) {                                            // against the corners kept so far
+                    const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0), x2 = min(xc + 1, gw - 1), y2 = min(yc + 1, gh - 1);
+                    for (int yy = y1; yy <= y2 && alive; ++yy)
+                        for (int xx = x1; xx <= x2 && alive; ++xx) {
+                            const int c = yy * gw + xx, m = cnt[c];
+                            for (int q = 0; q < m; ++q) {
+                                const unsigned pq = slots[c * kDetCellSlots + q];
+                                const int dx = x - (int)(pq & 0xffffu), dy = y - (int)(pq >> 16);
+                                if ((double)(dx * dx + dy * dy) < md2) { alive = false; break; }
+                            }
+                        }
+                }
+                unsigned surv = __ballot_sync(0xffffffffu, alive);     // the survivors are settled in rank order
+                while (surv && n_out < P.max_corners) {
+                    const int j = __ffs(surv) - 1;
+                    const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                    if (lane == j) {
+                        P.out[n_out] = make_float2((float)x, (float)y);
+                        const int c = yc * gw + xc, m = cnt[c];
+                        if (m < kDetCellSlots) { slots[c * kDetCellSlots + m] = lo32; cnt[c] = (unsigned char)(m + 1); }
+                        else P.ctrl->overflow = 1;
+                        alive = false;
+                    } else if (alive) {
+                        const int dx = x - xj, dy = y - yj;
+                        if ((double)(dx * dx + dy * dy) < md2) alive = false;
+                    }
+                    ++n_out;
+                    __syncwarp();
+                    surv = __ballot_sync(0xffffffffu, alive);
+                }
+            }
+            if (lane == 0) { s_nout = n_out; if (n_out >= P.max_corners) s_stop = 1; }
+        }
+        __syncthreads();
+        if (s_stop) break;
+        hi = lo;
+    }
+    if (tid == 0) P.ctrl->n_out = s_nout;
+}
+
+// ------------------------------------------------------------------------------------------------ cornerSubPix
+__global__ void __launch_bounds__(128) k_det_subpix(DetParams P)
+{
+    __shared__ float s_patch[4][33 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int k = blockIdx.x * 4 + wib;
+    if (k >= P.ctrl->n_out) return;
+    const int W = P.img.w, H = P.img.h;
+    const int hw = P.hw, ww = 2 * hw + 1, pw = ww + 2;
+    float* patch = s_patch[wib];
+    const float2 c0 = P.out[k];
+    float cx = c0.x, cy = c0.y;
+    int iter = 0;
+    double err = 0;
+    const double eps = P.subpix_eps * P.subpix_eps;
+    do {
+        // getRectSubPix: (ww+2)^2 float patch centred at (cx, cy), bilinear, replicated border
+        {
+            const float ox = __fsub_rn(cx, __fmul_rn((float)(pw - 1), 0.5f)), oy = __fsub_rn(cy, __fmul_rn((float)(pw - 1), 0.5f));
+            const int ix = (int)floorf(ox), iy = (int)floorf(oy);
+            const float a = __fsub_rn(ox, (float)ix), b = __fsub_rn(oy, (float)iy);
+            const float a11 = __fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), a12 = __fmul_rn(a, __fsub_rn(1.f, b));
+            const float a21 = __fmul_rn(__fsub_rn(1.f, a), b), a22 = __fmul_rn(a, b);
+            for (int o = lane; o < pw * pw; o += 32) {
+                const int i = o / pw, j = o - i * pw;
+                const int y0 = min(max(iy + i, 0), H - 1), y1 = min(max(iy + i + 1, 0), H - 1);
+                const int x0 = min(max(ix + j, 0), W - 1), x1 = min(max(ix + j + 1, 0), W - 1);
+                const uint8_t* r0 = P.img.base + (ptrdiff_t)y0 * P.img.pitch;
+                const uint8_t* r1 = P.img.base + (ptrdiff_t)y1 * P.img.pitch;
+                float v = __fmul_rn((float)r0[x0], a11);
+                v = __fadd_rn(v, __fmul_rn((float)r0[x1], a12));
+                v = __fadd_rn(v, __fmul_rn((float)r1[x0], a21));
+                v = __fadd_rn(v, __fmul_rn((float)r1[x1], a22));
+                patch[o] = v;
+            }
+        }
+        __syncwarp();
+        double sa = 0, sb = 0, sc = 0, s1 = 0, s2 = 0;
+        for (int q = lane; q < ww * ww; q += 32) {
+            const int i = q / ww, j = q - i * ww;
+            const double m = (double)P.mask[q];
+            const double tgx = (double)__fsub_rn(patch[(i + 1) * pw + j + 2], patch[(i + 1) * pw + j]);
+            const double tgy = (double)__fsub_rn(patch[(i + 2) * pw + j + 1], patch[i * pw + j + 1]);
+            const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+            const double px = (double)(j - hw), py = (double)(i - hw);
+            sa += gxx; sb += gxy; sc += gyy;
+            s1 += gxx * px + gxy * py;
+            s2 += gxy * px + gyy * py;
+        }
+#pragma unroll
+        for (int msk = 16; msk >= 1; msk >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, msk); sb += __shfl_xor_sync(0xffffffffu, sb, msk);
+            sc += __shfl_xor_sync(0xffffffffu, sc, msk); s1 += __shfl_xor_sync(0xffffffffu, s1, msk);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, msk);
+        }
+        __syncwarp();
+        const double det = sa * sc - sb * sb;
+        if (fabs(det) <= 2.220446049250313e-16 * 2.220446049250313e-16) break;
+        const double scale = 1.0 / det;
+        const float nx = (float)((double)cx + sc * scale * s1 - sb * scale * s2);
+        const float ny = (float)((double)cy - sb * scale * s1 + sa * scale * s2);
+        const float ex = __fsub_rn(nx, cx), ey = __fsub_rn(ny, cy);
+        err = (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+        cx = nx; cy = ny;
+        if (cx < 0 || cx >= (float)W || cy < 0 || cy >= (float)H) break;
+    } while (++iter < P.subpix_iters && err > eps);
+    if (fabsf(__fsub_rn(cx, c0.x)) > (float)hw || fabsf(__fsub_rn(cy, c0.y)) > (float)hw) { cx = c0.x; cy = c0.y; }
+    if (lane == 0) P.out[k] = make_float2(cx, cy);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int detector_create(Detector* D, int W, int H, int max_corners)
+{
+    memset(D, 0, sizeof *D);
+    D->W = W; D->H = H; D->max_corners = max_corners;
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->eig, sizeof(float) * (size_t)W * H));
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->keys, sizeof(unsigned long long) * kDetKeyCap));
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->ctrl, sizeof(DetCtrl)));
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->out, sizeof(float2) * ((size_t)max_corners + 1)));
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->mask, sizeof(float) * 31 * 31));
+    RVIO_CUDA_TRY(cudaMemset(D->ctrl, 0, sizeof(DetCtrl)));
+    RVIO_CUDA_TRY(cudaMallocHost((void**)&D->h_mask, sizeof(float) * 31 * 31));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_det_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    D->mask_hw = -1;
+    return RVIO_OK;
+}
+
+void detector_destroy(Detector* D)
+{
+    cudaFree(D->eig); cudaFree(D->keys); cudaFree(D->ctrl); cudaFree(D->out); cudaFree(D->mask);
+    cudaFreeHost(D->h_mask);
+}
+
+// Enqueues DetectWithSubPix(level0, max_corners, s) on `st`; the corners land in D->out, their number in D->ctrl->n_out.
+int detector_enqueue(Detector* D, cudaStream_t st, const PyrLevel& level0, int s, float min_dist_f, float quality_f)
+{
+    DetParams P;
+    P.img = level0; P.eig = D->eig; P.ctrl = D->ctrl; P.keys = D->keys; P.key_cap = kDetKeyCap;
+    P.out = D->out; P.max_corners = D->max_corners;
+    P.quality = (double)quality_f;
+    P.min_dist = (double)((float)s * min_dist_f);
+    P.hw = (int)floor(.5 * min_dist_f);                               // FeatureDetector.cc:68
+    if (P.hw < 1 || P.hw > 15 || P.min_dist < 1) { set_error("detector_enqueue", "Tracker.nMinDist outside the supported range [2, 31]"); return RVIO_ERR_ARG; }
+    P.subpix_iters = 30; P.subpix_eps = 1e-2;                        // FeatureDetector.cc:70
+    P.cell = (int)lrint(P.min_dist);
+    P.gw = (D->W + P.cell - 1) / P.cell; P.gh = (D->H + P.cell - 1) / P.cell;
+    const size_t smem = (size_t)kDetBlock * 8 + (((size_t)P.gw * P.gh + 15) & ~(size_t)15) + (size_t)P.gw * P.gh * kDetCellSlots * 4;
+    if (smem > 200 * 1024) { set_error("detector_enqueue", "minimum-distance grid does not fit in shared memory (Tracker.nMinDist too small for this image size)"); return RVIO_ERR_CAPACITY; }
+    if (D->mask_hw != P.hw) {                                        // cornerSubPix window weights (host libm, like OpenCV)
+        const int ww = 2 * P.hw + 1;
+        float mx[31];
+        for (int j = 0; j < ww; ++j) { const float x = (float)(j - P.hw) / P.hw; mx[j] = (float)exp(-x * x); }
+        for (int i = 0; i < ww; ++i) {
+            const float y = (float)(i - P.hw) / P.hw;
+            const float vy = (float)exp(-y * y);
+            for (int j = 0; j < ww; ++j) D->h_mask[i * ww + j] = (float)(vy * mx[j]);
+        }
+        RVIO_CUDA_TRY(cudaMemcpy(D->mask, D->h_mask, sizeof(float) * ww * ww, cudaMemcpyHostToDevice));   // once per window size
+        D->mask_hw = P.hw;
+    }
+    P.mask = D->mask;
+    RVIO_ENQ(cudaMemsetAsync(D->ctrl, 0, sizeof(DetCtrl), st));
+    const dim3 grid(div_up(D->W, 32), div_up(D->H, 32)), blk(32, 32);
+    RVIO_LAUNCH(k_det_eig, grid, blk, 0, st, P);
+    RVIO_LAUNCH(k_det_nms, grid, blk, 0, st, P);
+    RVIO_LAUNCH(k_det_select, 1, 1024, smem, st, P);
+    RVIO_LAUNCH(k_det_subpix, div_up(D->max_corners, 4), 128, 0, st, P);
+    RVIO_ENQ(cudaGetLastError());
+    return RVIO_OK;
+}
+
+}  // namespace rvio

@@ -1,0 +1,34 @@
+// detector_kernels.cuh -- parameter blocks of the device detector (see detector.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "tracker_kernels.cuh"
+
+namespace rvio {
+
+constexpr int kDetKeyCap = 65536;       // local maxima above the quality threshold that are kept (more: overflow flag)
+constexpr int kDetCellSlots = 4;        // accepted corners per grid cell (cell side == minimum distance: at most 2 fit)
+
+struct DetCtrl { unsigned max_bits; int n_cand; int n_out; int overflow; };
+
+struct DetParams {
+    PyrLevel img;                       // equalised frame (pyramid level 0, reflect-101 border)
+    float* eig;                         // W * H
+    DetCtrl* ctrl;
+    unsigned long long* keys; int key_cap;
+    float2* out; int max_corners;
+    double quality, min_dist;
+    int cell, gw, gh;
+    int hw, subpix_iters; double subpix_eps;
+    const float* mask;
+};
+
+struct Detector {
+    int W, H, max_corners;
+    float* eig; unsigned long long* keys; DetCtrl* ctrl; float2* out; float* mask; float* h_mask; int mask_hw;
+};
+
+int detector_create(Detector* D, int W, int H, int max_corners);
+void detector_destroy(Detector* D);
+int detector_enqueue(Detector* D, cudaStream_t st, const PyrLevel& level0, int s, float min_dist, float quality);
+
+}  // namespace rvio

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
     TrackerBuffers& B = Q.B;
     TrackerScalars* sc = B.sc;
     const int n_ref = sc->n_new;
-    const int nc = Q.hdr ? min(Q.hdr[1], Q.n_cand) : Q.n_cand;
+    const int nc = Q.n_cand_dev ? min(*Q.n_cand_dev, Q.n_cand) : Q.n_cand;
     for (int k = tid; k < nc; k += 1024) s_acc[k] = 0;
     __syncthreads();
     const int n_cells = Q.gc * Q.gr;

@@ -26,8 +26,8 @@ constexpr int kFindNewerCellCap = 128;
 
 struct FindNewerParams {
     TrackerBuffers B;
-    const float2* cand; int n_cand;        // detector output (device); n_cand is the capacity when hdr is set
-    const int* hdr;                        // optional device frame header {n_imu, n_cand}
+    const float2* cand; int n_cand;        // detector output (device); n_cand is the capacity when n_cand_dev is set
+    const int* n_cand_dev;                 // optional: the count lives on the device (frame header / device detector)
     int raw;                               // 1: candidates are already FindNewer-filtered
     int W, H, gc, gr, offx, offy, max_per_block;
     float bx, by, min_dist;

@@ -2,6 +2,7 @@
 // Compiled for sm_100a with -fmad=false (bit-exact float32/float64 contract).
 #include "common.cuh"
 #include "tracker_kernels.cuh"
+#include "detector_kernels.cuh"
 #include "device_utils.cuh"
 
 #include <math.h>
@@ -760,9 +761,10 @@ __global__ void __launch_bounds__(256) k_ransac_bookkeep(RansacParams P)
 }
 
 // First image (Tracker.cc:215-233): slot i <- corner i, free list = n..F-1.
-__global__ void k_seed(TrackerBuffers B, const float2* __restrict__ px, int n, CamParams cam)
+__global__ void k_seed(TrackerBuffers B, const float2* __restrict__ px, int n, const int* __restrict__ n_dev, CamParams cam)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(*n_dev, B.F);                 // corner count produced on the device (device detector)
     if (i < n) {
         const float2 p = px[i];
         float ux, uy;
@@ -827,6 +829,8 @@ struct rvio_tracker {
     int last_n;                 // features fed to LK in the last track()
     bool frame_open;            // track() ran, commit() pending
     bool shard_open;            // track_begin() ran, track_finish() pending
+    Detector det;               // FeatureDetector::DetectWithSubPix on the device (detector.cu)
+    cudaEvent_t ev_level0;      // recorded when the equalised level 0 of the current frame is complete
     CamParams cam;
     double Ric[9];
     // device memory
@@ -923,6 +927,8 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     t->first = true; t->n_track = 0; t->last_n = 0; t->frame_open = false; t->shard_open = false; t->cur_idx = 0;
     RVIO_CUDA_TRY(cudaSetDevice(device));
     RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&t->ev_level0, cudaEventDisableTiming));
+    if ((rc = detector_create(&t->det, t->W, t->H, t->F)) != RVIO_OK) return rc;
     // camera (float-rounded values widened to double: Tracker.cc:39-61)
     CamParams& c = t->cam;
     c.fx = cfg->fx; c.fy = cfg->fy; c.cx = cfg->cx; c.cy = cfg->cy;
@@ -998,6 +1004,7 @@ extern "C" void rvio_tracker_destroy(rvio_tracker* t)
     cudaSetDevice(t->device);
     cudaStreamSynchronize(t->stream);
     for (void* p : t->allocs) cudaFree(p);
+    detector_destroy(&t->det); cudaEventDestroy(t->ev_level0);
     cudaFreeHost(t->h_img); cudaFreeHost(t->h_R); cudaFreeHost(t->h_px); cudaFreeHost(t->h_sc);
     cudaStreamDestroy(t->stream);
     delete t;
@@ -1059,6 +1066,7 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     } else {
         RVIO_LAUNCH(k_copy_level0, grd, blk, 0, s, gray_dev, gray_pitch, cur.lv[0]);
     }
+    RVIO_ENQ(cudaEventRecord(t->ev_level0, s));            // what the detector needs (Tracker.cc:207,350 pass the equalised image)
     for (int l = 1; l < cur.levels; ++l) {
         const dim3 g(div_up(cur.lv[l].w, 256), cur.lv[l].h);
         RVIO_LAUNCH(k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
@@ -1180,6 +1188,23 @@ extern "C" int rvio_tracker_track_finish(rvio_tracker* t)
     return sync_scalars(t);
 }
 
+// FeatureDetector::DetectWithSubPix(equalised current image, nFeatures, s) on the device (FeatureDetector.cc:55-75).
+extern "C" int rvio_tracker_detect(rvio_tracker* t, int s_factor, float min_dist, float quality, float* xy_out, int* n_out)
+{
+    RVIO_ARG_CHECK(t && xy_out && n_out && (s_factor == 1 || s_factor == 2));
+    if (!t->frame_open) { set_error("rvio_tracker_detect", "no open frame (call rvio_tracker_track first)"); return RVIO_ERR_STATE; }
+    RVIO_CUDA_TRY(cudaSetDevice(t->device));
+    const int rc = detector_enqueue(&t->det, t->stream, t->pyr[t->cur_idx].lv[0], s_factor, min_dist, quality);
+    if (rc != RVIO_OK) return rc;
+    DetCtrl ctrl;
+    RVIO_CUDA_TRY(cudaMemcpyAsync(&ctrl, t->det.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost, t->stream));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(t->stream));
+    if (ctrl.overflow) { set_error("rvio_tracker_detect", "more local maxima than the detector keeps (or a grid cell overflowed)"); return RVIO_ERR_CAPACITY; }
+    *n_out = ctrl.n_out;
+    if (ctrl.n_out > 0) RVIO_CUDA_TRY(cudaMemcpy(xy_out, t->det.out, sizeof(float2) * ctrl.n_out, cudaMemcpyDeviceToHost));
+    return RVIO_OK;
+}
+
 extern "C" int rvio_tracker_get_image(rvio_tracker* t, uint8_t* out, int out_stride)
 {
     RVIO_ARG_CHECK(t && out && out_stride >= t->W);
@@ -1221,7 +1246,7 @@ extern "C" int rvio_tracker_seed(rvio_tracker* t, const float* px, int n)
     RVIO_CUDA_TRY(cudaSetDevice(t->device));
     memcpy(t->h_px, px, sizeof(float) * 2 * n);
     RVIO_CUDA_TRY(cudaMemcpyAsync(t->d_px_in, t->h_px, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, t->stream));
-    RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, t->d_px_in, n, t->cam);
+    RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, t->d_px_in, n, (const int*)nullptr, t->cam);
     RVIO_CUDA_TRY(cudaGetLastError());
     t->first = false;
     return sync_scalars(t);
@@ -1353,10 +1378,10 @@ int tracker_enqueue_frame_staged(rvio_tracker* t, const double* imu, int n_imu)
     return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu, true);
 }
 uint8_t* tracker_gray(rvio_tracker* t, size_t* pitch) { *pitch = t->gray_pitch; return t->d_gray; }
-int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n)
+int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n, const int* n_dev)
 {
     if (n > t->F) n = t->F;
-    RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, px_dev, n, t->cam);
+    RVIO_LAUNCH(k_seed, div_up(t->F, 256), 256, 0, t->stream, t->B, px_dev, n, n_dev, t->cam);
     RVIO_ENQ(cudaGetLastError());
     t->first = false;
     return RVIO_OK;
@@ -1375,6 +1400,10 @@ int tracker_wait(rvio_tracker* t)
     return RVIO_OK;
 }
 int tracker_parity(const rvio_tracker* t) { return t->cur_idx; }
+Detector* tracker_detector(rvio_tracker* t) { return &t->det; }
+const PyrLevel* tracker_level0(const rvio_tracker* t) { return &t->pyr[t->cur_idx].lv[0]; }
+cudaEvent_t tracker_level0_event(const rvio_tracker* t) { return t->ev_level0; }
+void tracker_set_first(rvio_tracker* t, bool first) { t->first = first; }
 bool tracker_is_first(const rvio_tracker* t) { return t->first; }
 const CamParams* tracker_cam(const rvio_tracker* t) { return &t->cam; }
 int tracker_n_track(const rvio_tracker* t) { return t->n_track; }

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "tracker_kernels.cuh"
 #include "filter_kernels.cuh"
+#include "detector_kernels.cuh"
 
 #include <math.h>
 #include <new>
@@ -16,7 +17,11 @@ namespace rvio {
 // tracker.cu
 int tracker_enqueue_frame_host(rvio_tracker* t, const uint8_t* img, int w, int h, int stride, int ch, const double* imu, int n_imu);
 int tracker_enqueue_frame_dev(rvio_tracker* t, const uint8_t* img_dev, int pitch, const double* imu, int n_imu);
-int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n);
+int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n, const int* n_dev);
+Detector* tracker_detector(rvio_tracker* t);
+const PyrLevel* tracker_level0(const rvio_tracker* t);
+cudaEvent_t tracker_level0_event(const rvio_tracker* t);
+void tracker_set_first(rvio_tracker* t, bool first);
 int tracker_enqueue_frame_staged(rvio_tracker* t, const double* imu, int n_imu);
 uint8_t* tracker_gray(rvio_tracker* t, size_t* pitch);
 int tracker_sync(rvio_tracker* t);
@@ -47,6 +52,8 @@ struct rvio_vio {
     rvio_updater* upd;
     cudaStream_t stream;          // main: tracker -> per-feature -> normal terms -> solve -> augment
     cudaStream_t side;            // side: propagate, FindNewer+refill (off the critical path)
+    cudaStream_t dets;            // device detector (DetectWithSubPix), beside LK / RANSAC / propagate
+    cudaEvent_t ev_det_done;
     cudaEvent_t ev_frame_in, ev_prop_done, ev_bookkeep_done, ev_side_done;
     // frame graphs: the steady-state frame is a fixed sequence of ~20 stream operations whose parameters only depend on a
     // few host-known bits (ping-pong parities, input mode, IMU block size); it is captured once per signature and replayed
@@ -211,6 +218,8 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     if (rc != RVIO_OK) { rvio_tracker_destroy(v->trk); delete v; return rc; }
     v->stream = tracker_stream(v->trk);
     RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&v->side, cudaStreamNonBlocking));
+    RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&v->dets, cudaStreamNonBlocking));
+    RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_det_done, cudaEventDisableTiming));
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_frame_in, cudaEventDisableTiming));
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_prop_done, cudaEventDisableTiming));
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_bookkeep_done, cudaEventDisableTiming));
@@ -262,7 +271,7 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     cudaStreamSynchronize(v->side);
     for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second);
     cudaEventDestroy(v->ev_frame_in); cudaEventDestroy(v->ev_prop_done); cudaEventDestroy(v->ev_bookkeep_done); cudaEventDestroy(v->ev_side_done);
-    cudaStreamDestroy(v->side);
+    cudaStreamDestroy(v->side); cudaStreamDestroy(v->dets); cudaEventDestroy(v->ev_det_done);
     for (void* p : v->allocs) cudaFree(p);
     for (void* p : v->hallocs) cudaFreeHost(p);
     rvio_updater_destroy(v->upd);
@@ -277,7 +286,8 @@ struct FrameOutcome { bool committable, ran_update; };
 // replayed (with rvio::t_replay set the stream operations are skipped and only the host-side bookkeeping advances).
 static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int width, int height, int stride, int channels,
                          const uint8_t* img_dev, int pitch, const double* imu, int n_imu, size_t imu_bytes,
-                         const float2* cand_dev, bool cand_upload, int n_cand, int cand_cap, int cand_filtered, FrameOutcome* out)
+                         const float2* cand_dev, bool cand_upload, int n_cand, int cand_cap, int cand_filtered, bool use_det,
+                         FrameOutcome* out)
 {
     cudaStream_t s = v->stream, side = v->side;
     const int N = v->n_clones;
@@ -310,19 +320,32 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
     if (rc < 0) return rc;
     if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[1], s));          // tracker kernels enqueued (upload .. bookkeeping)
-    if (n_cand > 0 && cand_upload)
+    const int* n_cand_dev = hdr + 1;
+    if (use_det && rc != RVIO_NO_FEATURES) {
+        // FeatureDetector::DetectWithSubPix on its own stream: it only needs the equalised level 0, so it runs beside
+        // the pyramid, LK, RANSAC and the propagation; FindNewer (or the seeding) waits for it
+        Detector* D = tracker_detector(v->trk);
+        RVIO_ENQ(cudaStreamWaitEvent(v->dets, tracker_level0_event(v->trk), 0));
+        int r2 = detector_enqueue(D, v->dets, *tracker_level0(v->trk), rc == RVIO_FIRST_IMAGE ? 1 : 2, v->cfg.min_dist, v->cfg.qual_lvl);
+        if (r2 != RVIO_OK) return r2;
+        RVIO_ENQ(cudaEventRecord(v->ev_det_done, v->dets));
+        cand_dev = D->out; n_cand_dev = &D->ctrl->n_out; n_cand = cand_cap = v->F; cand_filtered = 0;
+    }
+    if (n_cand > 0 && cand_upload && !use_det)
         RVIO_ENQ(cudaMemcpyAsync(v->d_cand, v->h_cand, sizeof(float) * 2 * cand_cap, cudaMemcpyHostToDevice, s));
     bool side_refill = false;
     if (rc == RVIO_FIRST_IMAGE) {
-        if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand); if (r2 != RVIO_OK) return r2; }
+        if (use_det) RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_det_done, 0));
+        if (n_cand > 0) { int r2 = tracker_enqueue_seed_dev(v->trk, cand_dev, n_cand, use_det ? n_cand_dev : nullptr); if (r2 != RVIO_OK) return r2; }
         out->committable = true;
     } else if (rc == RVIO_OK) {
         if (n_cand > 0) {
             // FindNewer + refill only prepare the NEXT frame's feature set: run them beside the update
             RVIO_ENQ(cudaEventRecord(v->ev_bookkeep_done, s));
             RVIO_ENQ(cudaStreamWaitEvent(side, v->ev_bookkeep_done, 0));
+            if (use_det) RVIO_ENQ(cudaStreamWaitEvent(side, v->ev_det_done, 0));
             FindNewerParams fp;
-            fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = cand_cap; fp.hdr = hdr; fp.raw = cand_filtered ? 1 : 0;
+            fp.B = *tracker_buffers(v->trk); fp.cand = cand_dev; fp.n_cand = cand_cap; fp.n_cand_dev = n_cand_dev; fp.raw = cand_filtered ? 1 : 0;
             fp.W = v->cfg.tracker.width; fp.H = v->cfg.tracker.height; fp.gc = v->gc; fp.gr = v->gr;
             fp.offx = v->offx; fp.offy = v->offy; fp.max_per_block = v->max_per_block;
             fp.bx = (float)v->cfg.block_x; fp.by = (float)v->cfg.block_y; fp.min_dist = v->cfg.min_dist;
@@ -378,7 +401,9 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
                          const float* cand_host, const float* cand_dev_in, int n_cand, int cand_filtered,
                          double* pose_out, int* pose_valid)
 {
-    RVIO_ARG_CHECK(v && pose_out && pose_valid && (n_imu == 0 || imu) && n_imu <= 512 && n_cand >= 0);
+    RVIO_ARG_CHECK(v && pose_out && pose_valid && (n_imu == 0 || imu) && n_imu <= 512);
+    const bool use_det = n_cand < 0;                      // corners from the device detector
+    if (use_det) { n_cand = 0; cand_host = nullptr; cand_dev_in = nullptr; }
     *pose_valid = 0;
     RVIO_CUDA_TRY(cudaSetDevice(v->device));
     if (n_imu < 2) return RVIO_OK;                          // InputBuffer.cc:76-77
@@ -407,6 +432,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     memcpy(v->h_imu + 2, imu, sizeof(double) * 8 * n_imu);
     if (n_cand > 0 && !cand_dev_in) memcpy(v->h_cand, cand_host, sizeof(float) * 2 * n_cand);
 
+    const bool was_first = tracker_is_first(v->trk);
     // ---- a steady-state frame (window full, features being tracked) is replayed as a CUDA graph
     const bool steady = v->use_graphs && !v->timeline && g_profile_on.load(std::memory_order_relaxed) == 0 &&
                         !tracker_is_first(v->trk) && tracker_n_track(v->trk) > 0 && v->n_clones == v->window &&
@@ -424,7 +450,8 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         }
         if (n_cand > 0 && cand_dev_in)
             RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, cand_dev_in, sizeof(float) * 2 * n_cand, cudaMemcpyDeviceToDevice, s));
-        const uint64_t key = (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
+        const uint64_t key = (uint64_t)use_det << 20 |
+                             (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
                              (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)(img_dev != nullptr) << 5 | (uint64_t)(channels & 7) << 6 |
                              (uint64_t)(cand_dev_in != nullptr) << 9 | (uint64_t)imu16 << 10;
         auto it = v->graphs.find(key);
@@ -432,14 +459,14 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         if (it != v->graphs.end()) {
             t_replay = true;
             rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
-                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, &fo);
+                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, use_det, &fo);
             t_replay = false;
             if (rc != RVIO_OK) return rc;
             RVIO_CUDA_TRY(cudaGraphLaunch(it->second, s));
         } else {
             RVIO_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
-                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, &fo);
+                               v->d_cand, cand_upload, n_cand, v->F, cand_filtered, use_det, &fo);
             cudaGraph_t g = nullptr;
             const cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != RVIO_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -455,7 +482,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     } else {
         const float2* cand_dev = cand_dev_in ? reinterpret_cast<const float2*>(cand_dev_in) : v->d_cand;
         rc = enqueue_frame(v, false, img_host, width, height, stride, channels, img_dev, pitch, imu, n_imu,
-                           16 + sizeof(double) * 8 * (size_t)n_imu, cand_dev, n_cand > 0 && !cand_dev_in, n_cand, n_cand, cand_filtered, &fo);
+                           16 + sizeof(double) * 8 * (size_t)n_imu, cand_dev, n_cand > 0 && !cand_dev_in, n_cand, n_cand, cand_filtered, use_det, &fo);
         if (rc != RVIO_OK) return rc;
     }
     clock_gettime(CLOCK_MONOTONIC, &h1);
@@ -468,6 +495,9 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         cudaEventRecord(v->tl[6], s);
         cudaEventSynchronize(v->tl[6]);
         for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, v->tl[k], v->tl[k + 1]) == cudaSuccess) v->tl_ms[k] = ms; else v->tl_ms[k] = -1.f; }
+    }
+    if (use_det && was_first && tracker_host_scalars(v->trk)->n_new == 0) {     // Tracker.cc:209-213: nothing detected, still "first image"
+        tracker_set_first(v->trk, true);
     }
     if (fo.committable) { r3 = rvio_tracker_commit(v->trk); if (r3 != RVIO_OK) return r3; }
     memcpy(pose_out, v->h_pose, sizeof(double) * 7);
@@ -488,7 +518,7 @@ extern "C" int rvio_vio_step(rvio_vio* v, const uint8_t* img, int width, int hei
                              const double* imu, int n_imu, const float* cand_px, int n_cand, int cand_filtered,
                              double* pose_out, int* pose_valid)
 {
-    RVIO_ARG_CHECK(v && img && (n_cand == 0 || cand_px));
+    RVIO_ARG_CHECK(v && img && (n_cand <= 0 || cand_px));
     return vio_step_impl(v, img, width, height, stride_bytes, channels, nullptr, 0, imu, n_imu, cand_px, nullptr, n_cand,
                          cand_filtered, pose_out, pose_valid);
 }
@@ -496,7 +526,7 @@ extern "C" int rvio_vio_step(rvio_vio* v, const uint8_t* img, int width, int hei
 extern "C" int rvio_vio_step_dev(rvio_vio* v, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu,
                                  const float* cand_px_dev, int n_cand, int cand_filtered, double* pose_out, int* pose_valid)
 {
-    RVIO_ARG_CHECK(v && img_dev && (n_cand == 0 || cand_px_dev));
+    RVIO_ARG_CHECK(v && img_dev && (n_cand <= 0 || cand_px_dev));
     return vio_step_impl(v, nullptr, 0, 0, 0, 1, img_dev, pitch_bytes, imu, n_imu, nullptr, cand_px_dev, n_cand,
                          cand_filtered, pose_out, pose_valid);
 }

@@ -97,6 +97,19 @@ class Tracker:
         capi.check(self.L.rvio_tracker_get_image(self.h, self._eq, self._eq.strides[0]), "get_image")
         return self._eq
 
+    def _detect(self, s):
+        if isinstance(self.detector, str) and self.detector == "device":
+            return self.detect(s)
+        return self.detector(self.equalized_image(), self.cfg.n_features, s)
+
+    def detect(self, s):
+        """FeatureDetector::DetectWithSubPix(equalised current image, nFeatures, s) on the device (rvio_tracker_detect)."""
+        out = np.zeros((self.cfg.n_features, 2), np.float32)
+        n = C.c_int()
+        capi.check(self.L.rvio_tracker_detect(self.h, int(s), float(np.float32(self.cfg.min_dist)), float(np.float32(self.cfg.qual_lvl)),
+                                              out, C.byref(n)), "rvio_tracker_detect")
+        return out[:n.value].copy()
+
     def n_free(self):
         n = C.c_int()
         capi.check(self.L.rvio_tracker_n_free(self.h, C.byref(n)))
@@ -165,7 +178,7 @@ class Tracker:
         if rc == capi.NO_FEATURES:
             return rc
         if rc == capi.FIRST_IMAGE:
-            pts = detections if detections is not None else self.detector(self.equalized_image(), self.cfg.n_features, 1)
+            pts = detections if detections is not None else self._detect(1)
             pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
             capi.check(self.L.rvio_tracker_seed(self.h, pts if len(pts) else np.zeros((1, 2), np.float32), len(pts)))
         else:
@@ -176,7 +189,7 @@ class Tracker:
                 if detections is not None:
                     newer = np.ascontiguousarray(detections, np.float32).reshape(-1, 2)
                 else:
-                    cand = self.detector(self.equalized_image(), self.cfg.n_features, 2)
+                    cand = self._detect(2)
                     newer = find_newer(self.cfg, cand, self.tracked_px())
                 if len(newer):
                     used = C.c_int()
@@ -280,14 +293,18 @@ class Vio:
         except Exception:
             pass
 
-    def step(self, im, imu, cand=None, cand_filtered=False):
+    def step(self, im, imu, cand=None, cand_filtered=False, device_detector=False):
+        """One frame.  cand: detector corners computed by the caller; device_detector=True: FeatureDetector::DetectWithSubPix
+        runs on the GPU inside the step instead (n_cand = -1 at the C ABI)."""
         im = np.ascontiguousarray(im, np.uint8)
         ch = 1 if im.ndim == 2 else im.shape[2]
         imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 8)
         nc = 0 if cand is None else len(cand)
         cp = np.ascontiguousarray(cand, np.float32).reshape(-1) if nc else None
+        if device_detector:
+            nc, cp = -1, None
         capi.check(self.L.rvio_vio_step(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
-                                        imu.ctypes.data, len(imu), cp.ctypes.data if nc else None, nc, 1 if cand_filtered else 0,
+                                        imu.ctypes.data, len(imu), cp.ctypes.data if nc > 0 else None, nc, 1 if cand_filtered else 0,
                                         self._pose, C.byref(self._valid)), "rvio_vio_step")
         return self._pose.copy() if self._valid.value else None
 
