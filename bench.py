@@ -43,12 +43,16 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detector", default="inloop", choices=["inloop", "precomputed"],
+                    help="inloop (default): FeatureDetector::DetectWithSubPix runs inside every timed step, on the GPU in this arm and "
+                         "through cv2 in the reference arm (the whole Tracker::track); precomputed: corner candidates prepared "
+                         "beforehand, identical for both arms")
     ap.add_argument("--batch-streams", type=int, default=8, help="extra leg: independent streams run concurrently on one GPU (BASELINE configs[3])")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------- workload
-def make_workload(cfg, n_frames, seed):
+def make_workload(cfg, n_frames, seed, precompute=True):
     """Seeded stream + per-frame IMU slices + corner candidates (s=1 and s=2 spacing) from the equalised frames."""
     import cv2
     import rvio_b200  # noqa: F401
@@ -63,6 +67,9 @@ def make_workload(cfg, n_frames, seed):
     cand1, cand2, eqs = [], [], []
     q = float(np.float32(cfg.qual_lvl)); md = float(np.float32(cfg.min_dist))
     for f in st.frames:
+        if not precompute:                                 # the detector runs inside the timed step
+            cand1.append(np.zeros((0, 2), np.float32)); cand2.append(np.zeros((0, 2), np.float32))
+            continue
         eq = clahe.apply(f) if cfg.enable_equalizer else f
         eqs.append(eq)
         c1 = cv2.goodFeaturesToTrack(eq, cfg.n_features, q, md)
@@ -122,6 +129,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     frames, imus = wl["frames"], wl["imus"]
     n_frames = len(frames)
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    inloop = args.detector == "inloop"
 
     def drive(vio, dev_inputs):
         """pre-roll until the first valid pose, W warm-up steps, K timed steps.  Returns (per-step ms list, wall seconds, launches)."""
@@ -152,11 +160,14 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                 ev0[timed].record(stream)
                 t0 = time.perf_counter()
             if dev_inputs:
-                dc = (d_c2 if got_pose else d_c1)[i]
-                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
-                                    dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
+                if inloop:
+                    pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
+                else:
+                    dc = (d_c2 if got_pose else d_c1)[i]
+                    pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
+                                        dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
             else:
-                pose = vio.step(frames[i], imus[i], cands[i])
+                pose = vio.step(frames[i], imus[i], cands[i], device_detector=inloop)
             if timing:
                 wall += time.perf_counter() - t0
                 ev1[timed].record(stream)
@@ -210,8 +221,11 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                     dc = (d_c2 if got else d_c1)[i]
                     if got and warm >= W and timed == 0:
                         start_bar.wait()
-                    pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], dc.data_ptr() if dc is not None else None,
-                                      0 if dc is None else dc.shape[0])
+                    if inloop:
+                        pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
+                    else:
+                        pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], dc.data_ptr() if dc is not None else None,
+                                          0 if dc is None else dc.shape[0])
                     if got and warm >= W:
                         timed += 1
                         if timed == Kb:
@@ -252,7 +266,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         L.rvio_vio_timeline(vio.h, 1, None)
         acc = []
         for i in range(used, min(used + 12, n_frames)):
-            vio.step(frames[i], imus[i], wl["cand2"][i])
+            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
             L.rvio_vio_timeline(vio.h, 1, tl.ctypes.data)
             acc.append(tl.copy())
         L.rvio_vio_timeline(vio.h, 0, None)
@@ -266,7 +280,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         L.rvio_b200_profile(1)
         n_prof = 0
         for i in range(used, min(used + 24, n_frames)):
-            vio.step(frames[i], imus[i], wl["cand2"][i])
+            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
             n_prof += 1
         L.rvio_b200_profile(0)
         buf = C.create_string_buffer(1 << 16)
@@ -312,6 +326,8 @@ def roofline_from_profile(prof, cfg, peaks):
         "k_gauss_jordan": 8.0 * (n * n + n * (d + 1)) * 2,
         "k_dgemm": 8.0 * 3 * d * d,
         "k_propagate": 8.0 * 2 * d * d,
+        "k_det_eig": 5.0 * W * H,                                         # equalised frame read once, float map written
+        "k_det_nms": 4.0 * W * H,
         "k_augment_compose": 8.0 * 2 * d * d,
     }.get(top, None)
     rf = {"kernel": top, "bound": "hbm", "launches_per_step": cnt / n_steps, "avg_launch_us": avg_s * 1e6,
@@ -328,7 +344,7 @@ def roofline_from_profile(prof, cfg, peaks):
 
 
 # ----------------------------------------------------------------------------------------- reference arm
-def run_reference(cfg, wl, steps, warmup, threads):
+def run_reference(cfg, wl, steps, warmup, threads, inloop=True):
     """Same frame loop on the host: cv2 (real OpenCV) for CLAHE / pyramidal LK, oracle C port for the Eigen stages."""
     import ctypes as C
     import cv2
@@ -357,9 +373,14 @@ def run_reference(cfg, wl, steps, warmup, threads):
         rc = L.orc_tracker_track_ext(trk.h, np.ascontiguousarray(eq), lk, stt, np.ascontiguousarray(imu), len(imu))
         if rc == 2:
             return
+        if inloop:                                                     # FeatureDetector::DetectWithSubPix through cv2, as the reference calls it
+            if rc == 1:
+                cand1 = orc.detect_with_subpix(eq, cfg.n_features, 1, cfg)             # Tracker.cc:207
+            elif L.orc_tracker_n_free(trk.h) > 0:
+                cand2 = orc.detect_with_subpix(eq, cfg.n_features, 2, cfg)             # Tracker.cc:350
         if rc == 1:
             if len(cand1):
-                L.orc_tracker_seed(trk.h, cand1, len(cand1))
+                L.orc_tracker_seed(trk.h, np.ascontiguousarray(cand1, np.float32), len(cand1))
         elif L.orc_tracker_n_free(trk.h) > 0 and len(cand2):
             nt = L.orc_tracker_n_tracked(trk.h)
             ref = np.ctypeslib.as_array(L.orc_tracker_tracked_px(trk.h), (max(nt, 1), 2))[:nt].copy()
@@ -405,8 +426,11 @@ def main():
     n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 40
     workload = {"workload": f"BASELINE configs[{args.config}]: synthetic EuRoC-shaped {cfg.width}x{cfg.height} mono + 200 Hz IMU stream, "
                             f"{cfg.n_features} features, {cfg.max_track_len - 1}-clone window, 1 frame per step",
-                "detector": "corner candidates pre-computed (cv2.goodFeaturesToTrack on the equalised frame), identical for both arms; "
-                            "FindNewer + refill inside the timed step",
+                "detector": ("FeatureDetector::DetectWithSubPix inside every timed step (whole Tracker::track): device kernels in this arm, "
+                             "cv2.goodFeaturesToTrack + cornerSubPix in the reference arm; FindNewer + refill inside the step"
+                             if args.detector == "inloop" else
+                             "corner candidates pre-computed (cv2.goodFeaturesToTrack on the equalised frame), identical for both arms; "
+                             "FindNewer + refill inside the timed step"),
                 "l2": "384 MB device buffer rewritten between timed iterations (outside the per-step event pair)",
                 "precision": "tracker bit-exact integer/float32, filter float64"}
     ncores = os.cpu_count() or 1
@@ -415,8 +439,8 @@ def main():
         if rank != 0:
             return
         steps = min(K, 120)                                               # bounded sample of the same workload
-        wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + W + steps + 4, SEED + args.config)
-        r = run_reference(cfg, wl, steps, W, ncores)
+        wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + W + steps + 4, SEED + args.config, args.detector == "precomputed")
+        r = run_reference(cfg, wl, steps, W, ncores, args.detector == "inloop")
         fps = r["steps"] / r["t"]
         out = {"metric": "vio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": W,
                "ms_per_step": 1e3 * r["t"] / r["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -436,7 +460,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank)
+    wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank, args.detector == "precomputed")
     res = run_b200(args, cfg, wl, rank, world, local_rank)
     if rank != 0:
         if world > 1:
@@ -466,7 +490,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         steps = 60
         wl2 = {k: (v[:int(T_STATIC * cfg.fps) + 4 + W + steps + 4] if isinstance(v, list) else v) for k, v in wl.items()}
-        r = run_reference(cfg, wl2, steps, min(W, 10), ncores)
+        r = run_reference(cfg, wl2, steps, min(W, 10), ncores, args.detector == "inloop")
         import cv2
         out["cpu_baseline"] = {"value": r["steps"] / r["t"], "unit": "frames/s", "cores": ncores, "kind": "port",
                                "sample": f"{r['steps']} frames of the same stream; OpenCV stages via cv2 {cv2.__version__} ({ncores} threads), "

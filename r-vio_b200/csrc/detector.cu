@@ -107,6 +107,31 @@ __global__ void __launch_bounds__(1024) k_det_nms(DetParams P)
 // the candidates are taken block by block from the top of a histogram over the leading float bits: gather <= 4096 keys,
 // bitonic sort, then a warp resolves them 32 at a time (each lane tests its candidate against the kept corners of the 3x3
 // neighbouring cells; the survivors of a batch are settled in rank order).
+
+// true when (x, y) lies closer than sqrt(md2) to a corner kept in one of the 3 x 3 cells around (xc, yc): the nine cell
+// counts are loaded first (independent loads), then only the occupied slots are visited
+__device__ __forceinline__ bool det_near_kept(const unsigned char* cnt, const unsigned* slots, int gw, int gh, int xc, int yc,
+                                              int x, int y, double md2)
+{
+    int cidx[9], m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = yc + k / 3 - 1, xx = xc + k % 3 - 1;
+        const bool in = yy >= 0 && yy < gh && xx >= 0 && xx < gw;
+        cidx[k] = in ? yy * gw + xx : 0;
+        m[k] = in ? (int)cnt[cidx[k]] : 0;
+    }
+    bool near = false;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        for (int q = 0; q < m[k]; ++q) {
+            const unsigned pq = slots[cidx[k] * kDetCellSlots + q];
+            const int dx = x - (int)(pq & 0xffffu), dy = y - (int)(pq >> 16);
+            near = near || ((double)(dx * dx + dy * dy) < md2);
+        }
+    return near;
+}
+
 constexpr int kDetBlock = 4096, kDetBins = 1024;
 
 __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
@@ -131,15 +156,34 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
     for (int i = tid; i < gw * gh; i += 1024) cnt[i] = 0;
     if (tid == 0) { s_nout = 0; s_stop = 0; }
     __syncthreads();
-    for (int i = tid; i < nc; i += 1024) atomicAdd(&s_hist[(int)(((unsigned)(P.keys[i] >> 32) >> shift) - base)], 1);
-    __syncthreads();
     const double md2 = P.min_dist * P.min_dist;
-    int hi = nbins;
-    while (hi > 0) {
+    bool first_round = true;
+    while (true) {
+        // candidates that lie within the minimum distance of a corner kept in an earlier round can never be kept: drop them
+        // (all 1024 threads), so that the serial part below only sees candidates that still have a chance
+        for (int i = tid; i < kDetBins; i += 1024) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < nc; i += 1024) {
+            unsigned long long kk = P.keys[i];
+            if (kk == 0ull) continue;
+            if (!first_round) {
+                const unsigned lo32 = (unsigned)kk;
+                const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
+                const int xc = x / cell, yc = y / cell;
+                const bool alive = !det_near_kept(cnt, slots, gw, gh, xc, yc, x, y, md2);
+                if (!alive) { P.keys[i] = 0ull; continue; }
+            }
+            atomicAdd(&s_hist[(int)(((unsigned)(kk >> 32) >> shift) - base)], 1);
+        }
+        first_round = false;
+        __syncthreads();
         if (tid == 0) {                                   // next block of bins from the top, at most kDetBlock candidates
+            int hi = nbins;
+            while (hi > 0 && s_hist[hi - 1] == 0) --hi;
             int lo = hi, acc = 0;
             while (lo > 0 && acc + s_hist[lo - 1] <= kDetBlock) { acc += s_hist[lo - 1]; --lo; }
-            if (lo == hi) { P.ctrl->overflow = 1; s_stop = 1; }    // one bin alone exceeds the block
+            if (hi > 0 && lo == hi) { P.ctrl->overflow = 1; s_stop = 1; }    // one bin alone exceeds the block
+            if (hi == 0) s_stop = 1;                      // nothing left
             s_lo = lo; s_take = acc; s_count = 0;
         }
         __syncthreads();
@@ -147,8 +191,9 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
         const int lo = s_lo, take = s_take;
         for (int i = tid; i < nc; i += 1024) {
             const unsigned long long kk = P.keys[i];
+            if (kk == 0ull) continue;
             const int b = (int)(((unsigned)(kk >> 32) >> shift) - base);
-            if (b >= lo && b < hi) keys[atomicAdd(&s_count, 1)] = kk;
+            if (b >= lo) { keys[atomicAdd(&s_count, 1)] = kk; P.keys[i] = 0ull; }      // consumed by this round
         }
         int np2 = 32;
         while (np2 < take) np2 <<= 1;
@@ -176,18 +221,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                 const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
                 const int xc = x / cell, yc = y / cell;
                 bool alive = valid;
-                if (alive) {                                            // against the corners kept so far
-                    const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0), x2 = min(xc + 1, gw - 1), y2 = min(yc + 1, gh - 1);
-                    for (int yy = y1; yy <= y2 && alive; ++yy)
-                        for (int xx = x1; xx <= x2 && alive; ++xx) {
-                            const int c = yy * gw + xx, m = cnt[c];
-                            for (int q = 0; q < m; ++q) {
-                                const unsigned pq = slots[c * kDetCellSlots + q];
-                                const int dx = x - (int)(pq & 0xffffu), dy = y - (int)(pq >> 16);
-                                if ((double)(dx * dx + dy * dy) < md2) { alive = false; break; }
-                            }
-                        }
-                }
+                if (alive) alive = !det_near_kept(cnt, slots, gw, gh, xc, yc, x, y, md2);      // against the corners kept so far
                 unsigned surv = __ballot_sync(0xffffffffu, alive);     // the survivors are settled in rank order
                 while (surv && n_out < P.max_corners) {
                     const int j = __ffs(surv) - 1;
@@ -211,7 +245,6 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
         }
         __syncthreads();
         if (s_stop) break;
-        hi = lo;
     }
     if (tid == 0) P.ctrl->n_out = s_nout;
 }
@@ -220,50 +253,112 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
 __global__ void __launch_bounds__(128) k_det_subpix(DetParams P)
 {
     __shared__ float s_patch[4][33 * 33];
+    __shared__ unsigned char s_px[4][34 * 36];                       // (pw + 1)^2 source pixels of the current patch
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * 4 + wib;
     if (k >= P.ctrl->n_out) return;
     const int W = P.img.w, H = P.img.h;
-    const int hw = P.hw, ww = 2 * hw + 1, pw = ww + 2;
+    const int hw = P.hw, ww = 2 * hw + 1, pw = ww + 2, sw = pw + 1;
     float* patch = s_patch[wib];
+    unsigned char* px = s_px[wib];
     const float2 c0 = P.out[k];
     float cx = c0.x, cy = c0.y;
     int iter = 0;
     double err = 0;
     const double eps = P.subpix_eps * P.subpix_eps;
+    // per-lane element tables, fixed for the whole refinement (window sizes up to 15 x 15 take the register path)
+    constexpr int kSrcPer = 11, kPatPer = 10, kWinPer = 8;            // ceil(18*18/32), ceil(17*17/32), ceil(15*15/32)
+    const bool small = hw <= 7;
+    short src_i[kSrcPer], src_j[kSrcPer], pat_o[kPatPer], win_o[kWinPer];
+    signed char win_x[kWinPer], win_y[kWinPer];
+    float win_m[kWinPer];
+    if (small) {
+#pragma unroll
+        for (int u = 0; u < kSrcPer; ++u) { const int o = u * 32 + lane; src_i[u] = (short)(o / sw); src_j[u] = (short)(o - (o / sw) * sw); }
+#pragma unroll
+        for (int u = 0; u < kPatPer; ++u) { const int o = u * 32 + lane; pat_o[u] = (short)((o / pw) * sw + (o - (o / pw) * pw)); }
+#pragma unroll
+        for (int u = 0; u < kWinPer; ++u) {
+            const int q = u * 32 + lane, i = q / ww, j = q - i * ww;
+            win_o[u] = (short)(i * pw + j); win_x[u] = (signed char)(j - hw); win_y[u] = (signed char)(i - hw);
+            win_m[u] = (q < ww * ww) ? P.mask[q] : 0.f;
+        }
+    }
     do {
         // getRectSubPix: (ww+2)^2 float patch centred at (cx, cy), bilinear, replicated border
-        {
-            const float ox = __fsub_rn(cx, __fmul_rn((float)(pw - 1), 0.5f)), oy = __fsub_rn(cy, __fmul_rn((float)(pw - 1), 0.5f));
-            const int ix = (int)floorf(ox), iy = (int)floorf(oy);
-            const float a = __fsub_rn(ox, (float)ix), b = __fsub_rn(oy, (float)iy);
-            const float a11 = __fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), a12 = __fmul_rn(a, __fsub_rn(1.f, b));
-            const float a21 = __fmul_rn(__fsub_rn(1.f, a), b), a22 = __fmul_rn(a, b);
+        const float ox = __fsub_rn(cx, __fmul_rn((float)(pw - 1), 0.5f)), oy = __fsub_rn(cy, __fmul_rn((float)(pw - 1), 0.5f));
+        const int ix = (int)floorf(ox), iy = (int)floorf(oy);
+        const float a = __fsub_rn(ox, (float)ix), b = __fsub_rn(oy, (float)iy);
+        const float a11 = __fmul_rn(__fsub_rn(1.f, a), __fsub_rn(1.f, b)), a12 = __fmul_rn(a, __fsub_rn(1.f, b));
+        const float a21 = __fmul_rn(__fsub_rn(1.f, a), b), a22 = __fmul_rn(a, b);
+        double sa = 0, sb = 0, sc = 0, s1 = 0, s2 = 0;
+        if (small) {
+            // one round trip to global memory: the (pw+1)^2 source pixels (coordinates clamped to the image); the
+            // bilinear taps then come from shared memory
+            unsigned char v[kSrcPer];
+#pragma unroll
+            for (int u = 0; u < kSrcPer; ++u) {
+                const int yy = min(max(iy + src_i[u], 0), H - 1), xx = min(max(ix + src_j[u], 0), W - 1);
+                v[u] = (u * 32 + lane < sw * sw) ? P.img.base[(ptrdiff_t)yy * P.img.pitch + xx] : (unsigned char)0;
+            }
+#pragma unroll
+            for (int u = 0; u < kSrcPer; ++u) if (u * 32 + lane < sw * sw) px[u * 32 + lane] = v[u];
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kPatPer; ++u) {
+                const int o = u * 32 + lane;
+                if (o < pw * pw) {
+                    const unsigned char* q = px + pat_o[u];
+                    float t = __fmul_rn((float)q[0], a11);
+                    t = __fadd_rn(t, __fmul_rn((float)q[1], a12));
+                    t = __fadd_rn(t, __fmul_rn((float)q[sw], a21));
+                    t = __fadd_rn(t, __fmul_rn((float)q[sw + 1], a22));
+                    patch[o] = t;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kWinPer; ++u) {
+                if (u * 32 + lane < ww * ww) {
+                    const float* pp = patch + win_o[u];
+                    const double m = (double)win_m[u];
+                    const double tgx = (double)__fsub_rn(pp[pw + 2], pp[pw]);
+                    const double tgy = (double)__fsub_rn(pp[2 * pw + 1], pp[1]);
+                    const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                    const double px_ = (double)win_x[u], py_ = (double)win_y[u];
+                    sa += gxx; sb += gxy; sc += gyy;
+                    s1 += gxx * px_ + gxy * py_;
+                    s2 += gxy * px_ + gyy * py_;
+                }
+            }
+        } else {
+            for (int o = lane; o < sw * sw; o += 32) {
+                const int i = o / sw, j = o - i * sw;
+                const int yy = min(max(iy + i, 0), H - 1), xx = min(max(ix + j, 0), W - 1);
+                px[o] = P.img.base[(ptrdiff_t)yy * P.img.pitch + xx];
+            }
+            __syncwarp();
             for (int o = lane; o < pw * pw; o += 32) {
                 const int i = o / pw, j = o - i * pw;
-                const int y0 = min(max(iy + i, 0), H - 1), y1 = min(max(iy + i + 1, 0), H - 1);
-                const int x0 = min(max(ix + j, 0), W - 1), x1 = min(max(ix + j + 1, 0), W - 1);
-                const uint8_t* r0 = P.img.base + (ptrdiff_t)y0 * P.img.pitch;
-                const uint8_t* r1 = P.img.base + (ptrdiff_t)y1 * P.img.pitch;
-                float v = __fmul_rn((float)r0[x0], a11);
-                v = __fadd_rn(v, __fmul_rn((float)r0[x1], a12));
-                v = __fadd_rn(v, __fmul_rn((float)r1[x0], a21));
-                v = __fadd_rn(v, __fmul_rn((float)r1[x1], a22));
-                patch[o] = v;
+                const unsigned char* q = px + i * sw + j;
+                float t = __fmul_rn((float)q[0], a11);
+                t = __fadd_rn(t, __fmul_rn((float)q[1], a12));
+                t = __fadd_rn(t, __fmul_rn((float)q[sw], a21));
+                t = __fadd_rn(t, __fmul_rn((float)q[sw + 1], a22));
+                patch[o] = t;
             }
-        }
-        __syncwarp();
-        double sa = 0, sb = 0, sc = 0, s1 = 0, s2 = 0;
-        for (int q = lane; q < ww * ww; q += 32) {
-            const int i = q / ww, j = q - i * ww;
-            const double m = (double)P.mask[q];
-            const double tgx = (double)__fsub_rn(patch[(i + 1) * pw + j + 2], patch[(i + 1) * pw + j]);
-            const double tgy = (double)__fsub_rn(patch[(i + 2) * pw + j + 1], patch[i * pw + j + 1]);
-            const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
-            const double px = (double)(j - hw), py = (double)(i - hw);
-            sa += gxx; sb += gxy; sc += gyy;
-            s1 += gxx * px + gxy * py;
-            s2 += gxy * px + gyy * py;
+            __syncwarp();
+            for (int q = lane; q < ww * ww; q += 32) {
+                const int i = q / ww, j = q - i * ww;
+                const double m = (double)P.mask[q];
+                const double tgx = (double)__fsub_rn(patch[(i + 1) * pw + j + 2], patch[(i + 1) * pw + j]);
+                const double tgy = (double)__fsub_rn(patch[(i + 2) * pw + j + 1], patch[i * pw + j + 1]);
+                const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                const double px_ = (double)(j - hw), py_ = (double)(i - hw);
+                sa += gxx; sb += gxy; sc += gyy;
+                s1 += gxx * px_ + gxy * py_;
+                s2 += gxy * px_ + gyy * py_;
+            }
         }
 #pragma unroll
         for (int msk = 16; msk >= 1; msk >>= 1) {
