@@ -328,6 +328,8 @@ def roofline_from_profile(prof, cfg, peaks):
         "k_propagate": 8.0 * 2 * d * d,
         "k_det_eig": 5.0 * W * H,                                         # equalised frame read once, float map written
         "k_det_nms": 4.0 * W * H,
+        "k_det_select": 2 * 8.0 * 0.053 * W * H,                          # candidate keys (5.3% of the pixels are local maxima on this stream), read twice
+        "k_det_subpix": F * 30 * 18.0 * 18.0,                             # source window per corner and iteration
         "k_augment_compose": 8.0 * 2 * d * d,
     }.get(top, None)
     rf = {"kernel": top, "bound": "hbm", "launches_per_step": cnt / n_steps, "avg_launch_us": avg_s * 1e6,
@@ -338,6 +340,13 @@ def roofline_from_profile(prof, cfg, peaks):
         rf["algorithmic_bytes_per_launch"] = alg
         rf["achieved"] = alg / avg_s / 1e9
         rf["frac"] = rf["achieved"] / rf["peak"] if rf["peak"] else None
+    try:                                                                    # measured DRAM traffic of the same kernel (committed ncu summary)
+        import glob
+        tr = json.load(open(sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic_r*.json")))[-1]))
+        rf["traffic"] = tr["bytes_per_launch"].get(top)
+        rf["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     rf["note"] = ("single-stream VIO at this size moves ~2 MB and ~50 MFLOP per frame: every kernel is latency-bound, "
                   "the roofline fraction is reported for completeness (SURVEY 8d)")
     return rf, {k: round(v * 1e3, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}   # us per step

@@ -128,9 +128,9 @@ def test_argument_and_capacity_errors():
     assert L.rvio_tracker_track(g.h, img.reshape(-1), 100, 100, 100, 1, imu.ctypes.data, 10) == -1       # wrong size
     assert b"argument" in L.rvio_b200_last_error()
     assert L.rvio_tracker_commit(g.h) == -3                                                              # no open frame
-    tc = capi.tracker_cfg(cfg); tc.is_fisheye = 1
+    tc = capi.tracker_cfg(cfg); tc.is_fisheye = 1; tc.k3 = 0.01
     h = C.c_void_p()
-    assert L.rvio_tracker_create(C.byref(tc), 0, C.byref(h)) == -1                                       # fisheye not implemented
+    assert L.rvio_tracker_create(C.byref(tc), 0, C.byref(h)) == -1                                       # fisheye takes 4 coefficients (cv::fisheye asserts)
     upd = host.Updater(cfg)
     N = cfg.window + 1                                                                                   # one clone too many
     x = np.zeros(26 + 7 * N); P = np.eye(24 + 6 * N)

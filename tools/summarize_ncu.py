@@ -84,7 +84,7 @@ def _f(x):
         return 0.0
 
 
-def source(src, dst, top=22):
+def source(src, dst, top=10):
     """Hot source lines per kernel (warp-stall samples, executed warp instructions, dominant stall reason) from an
     --import-source capture; SASS rows of the source page are aggregated per CUDA-C line."""
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -92,7 +92,7 @@ def source(src, dst, top=22):
     names = []
     for r in rows[2:]:
         k = r[rows[0].index("Kernel Name")].split("(")[0].replace("void ", "")
-        if k not in names:
+        if k not in names and k.startswith("k_"):
             names.append(k)
     out = [f"# ncu source page: `{src}` (hot CUDA-C lines; share of warp-stall samples / of executed warp instructions)", ""]
     for k in names:
@@ -112,6 +112,8 @@ def source(src, dst, top=22):
             try:
                 ln = int(r[0])
             except ValueError:
+                continue
+            if "# Samples" not in hdr or "Instructions Executed" not in hdr:
                 continue
             i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")
             st = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
