@@ -220,7 +220,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                 while True:
                     dc = (d_c2 if got else d_c1)[i]
                     if got and warm >= W and timed == 0:
-                        start_bar.wait()
+                        start_bar.wait(timeout=240)
                     if inloop:
                         pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
                     else:
@@ -235,7 +235,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                     if pose is not None:
                         got = True
                     i += 1
-                end_bar.wait()
+                end_bar.wait(timeout=240)
             except Exception as e:          # pragma: no cover
                 errs.append(e)
                 try:
@@ -246,14 +246,18 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         ths = [threading.Thread(target=worker, args=(v,)) for v in vios]
         for t in ths:
             t.start()
-        start_bar.wait()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        end_bar.wait()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
+        t0 = t1 = 0.0
+        try:
+            start_bar.wait(timeout=240)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            end_bar.wait(timeout=240)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+        except threading.BrokenBarrierError:                  # a worker failed (or timed out): no batch number, no hang
+            errs.append(RuntimeError("batch leg aborted"))
         for t in ths:
-            t.join()
+            t.join(timeout=60)
         for v in vios:
             v.close()
         if not errs:
@@ -296,10 +300,15 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
-        if batch is not None:
-            b = torch.tensor([batch["value"]], dtype=torch.float64, device=dev)
-            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        # every rank takes part in the same collectives, whatever happened to its own batch leg (a rank that skipped one
+        # would leave the others waiting in NCCL for ever)
+        b = torch.tensor([batch["value"] if batch is not None else 0.0, 1.0 if batch is not None else 0.0],
+                         dtype=torch.float64, device=dev)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        if S > 1 and int(round(float(b[1]))) == world and batch is not None:
             batch["value"] = float(b[0]); batch["n_gpus"] = world
+        else:
+            batch = None
     return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
                 prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch)
 
@@ -423,8 +432,16 @@ def run_reference(cfg, wl, steps, warmup, threads, inloop=True):
 
 
 # ----------------------------------------------------------------------------------------- main
+def _watchdog(seconds):
+    """A wedged run (driver, NCCL, a kernel that never returns) must not hold the GPU box until the caller's limit: dump
+    every thread's stack and exit non-zero after `seconds`."""
+    import faulthandler
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def main():
     args = parse()
+    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "540")))
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import rvio_b200  # noqa: F401
@@ -469,7 +486,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank, args.detector == "precomputed")
+    wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank + int(os.environ.get("RVIO_BENCH_SEED_OFFSET", "0")),
+                       args.detector == "precomputed")
     res = run_b200(args, cfg, wl, rank, world, local_rank)
     if rank != 0:
         if world > 1:
