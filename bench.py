@@ -204,6 +204,12 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     #      between device synchronisations; the single-stream `value` above is the CUDA-event number).
     batch = None
     S = args.batch_streams
+    if world > 1:
+        # round 1: with a torch.distributed NCCL process group alive, eight host threads capturing / replaying frame graphs
+        # concurrently were observed to stall inside the CUDA runtime (every worker blocked in rvio_vio_step_dev, both ranks;
+        # the single-stream legs above are unaffected and the same leg runs fine without the process group).  Until that is
+        # understood the multi-stream leg only runs single-process.
+        S = 0
     if S > 1:
         import threading
         d_frames = [torch.from_numpy(f).to(dev) for f in frames]
@@ -441,7 +447,7 @@ def _watchdog(seconds):
 
 def main():
     args = parse()
-    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "540")))
+    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "480")))
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import rvio_b200  # noqa: F401
