@@ -54,7 +54,8 @@ class Tracker {
 public:
     // Tracker(const cv::FileStorage&) in the reference (Tracker.cc:37-90); here the parsed keys arrive as rvio_tracker_cfg.
     Tracker(const rvio_tracker_cfg& cfg, Detector* detector, int device = 0)
-        : mCfg(cfg), mpFeatureDetector(detector), mHandle(nullptr), mLastStatus(RVIO_OK)
+        : mCfg(cfg), mpFeatureDetector(detector), mHandle(nullptr), mLastStatus(RVIO_OK), mbDeviceDetector(false),
+          mnMinDist(0.f), mnQualLvl(0.f)
     {
         mLastStatus = rvio_tracker_create(&mCfg, device, &mHandle);
         if (mLastStatus != RVIO_OK) throw std::runtime_error(std::string("rvio_tracker_create: ") + rvio_b200_last_error());
@@ -62,6 +63,10 @@ public:
         mvlFeatMeasForUpdate.resize((size_t)std::ceil(.5 * cfg.n_features));
     }
     ~Tracker() { rvio_tracker_destroy(mHandle); }
+    // FeatureDetector::DetectWithSubPix on the GPU (rvio_tracker_detect) instead of through the host detector object;
+    // nMinDist / nQualLvl are Tracker.nMinDist / Tracker.nQualLvl (FeatureDetector.cc:31-32).  FindNewer stays with the
+    // Detector object passed to the constructor.
+    void UseDeviceDetector(float nMinDist, float nQualLvl) { mbDeviceDetector = true; mnMinDist = nMinDist; mnQualLvl = nQualLvl; }
     Tracker(const Tracker&) = delete;
     Tracker& operator=(const Tracker&) = delete;
 
@@ -82,8 +87,7 @@ public:
         if (rc == RVIO_FIRST_IMAGE) {
             // Tracker.cc:204-234
             std::vector<Point2f> corners;
-            if (rvio_tracker_get_image(mHandle, mEq.data(), mCfg.width) != RVIO_OK) return;
-            const int n = mpFeatureDetector ? mpFeatureDetector->DetectWithSubPix(mEq.data(), mCfg.width, mCfg.height, mCfg.n_features, 1, corners) : 0;
+            const int n = DetectWithSubPix(1, corners);
             if (n > 0) mLastStatus = rvio_tracker_seed(mHandle, &corners[0].x, n);
             rvio_tracker_commit(mHandle);
             return;
@@ -104,9 +108,9 @@ public:
         int nFree = 0;
         rvio_tracker_n_free(mHandle, &nFree);
         if (nFree > 0 && mpFeatureDetector) {
-            if (rvio_tracker_get_image(mHandle, mEq.data(), mCfg.width) == RVIO_OK) {
+            {
                 std::vector<Point2f> vTempFeats, qNewFeats, vRef((size_t)mCfg.n_features);
-                mpFeatureDetector->DetectWithSubPix(mEq.data(), mCfg.width, mCfg.height, mCfg.n_features, 2, vTempFeats);
+                DetectWithSubPix(2, vTempFeats);
                 int nRef = 0;
                 rvio_tracker_get_tracked_px(mHandle, &vRef[0].x, &nRef);
                 vRef.resize((size_t)nRef);
@@ -120,6 +124,23 @@ public:
     int last_status() const { return mLastStatus; }
     rvio_tracker* handle() { return mHandle; }
 
+private:
+    // mpFeatureDetector->DetectWithSubPix(im, mnMaxFeatsPerImage, s, corners) (Tracker.cc:207,350) on the equalised image
+    int DetectWithSubPix(int s, std::vector<Point2f>& vCorners)
+    {
+        vCorners.clear();
+        if (mbDeviceDetector) {
+            vCorners.resize((size_t)mCfg.n_features);
+            int n = 0;
+            const int rc = rvio_tracker_detect(mHandle, s, mnMinDist, mnQualLvl, &vCorners[0].x, &n);
+            if (rc != RVIO_OK) { mLastStatus = rc; n = 0; }
+            vCorners.resize((size_t)n);
+            return n;
+        }
+        if (!mpFeatureDetector || rvio_tracker_get_image(mHandle, mEq.data(), mCfg.width) != RVIO_OK) return 0;
+        return mpFeatureDetector->DetectWithSubPix(mEq.data(), mCfg.width, mCfg.height, mCfg.n_features, s, vCorners);
+    }
+
 public:
     // Feature types for update: '1' lose track, '2' reach the max. tracking length   (Tracker.h:66-70)
     std::vector<unsigned char> mvFeatTypesForUpdate;
@@ -131,6 +152,8 @@ private:
     Detector* mpFeatureDetector;
     rvio_tracker* mHandle;
     int mLastStatus;
+    bool mbDeviceDetector;
+    float mnMinDist, mnQualLvl;
     std::vector<uint8_t> mEq;
 };
 
