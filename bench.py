@@ -471,7 +471,7 @@ def main():
         if rank != 0:
             return
         steps = min(K, 120)                                               # bounded sample of the same workload
-        wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + W + steps + 4, SEED + args.config, args.detector == "precomputed")
+        wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + W + steps + 30, SEED + args.config, args.detector == "precomputed")
         r = run_reference(cfg, wl, steps, W, ncores, args.detector == "inloop")
         fps = r["steps"] / r["t"]
         out = {"metric": "vio_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": W,
