@@ -261,6 +261,14 @@ def detect_restated(img, n_corners, s, cfg):
     return out[:n].copy()
 
 
+def good_features(img, max_corners, quality, min_dist):
+    """cv::goodFeaturesToTrack through the C restatement: integer-pixel corners, strongest first."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((max(max_corners, 1) if max_corners > 0 else img.size // 4, 2), np.float32)
+    n = lib().orc_good_features(img, img.shape[1], img.shape[0], img.strides[0], max_corners, float(quality), float(min_dist), out)
+    return out[:n].copy()
+
+
 def min_eig_map(img):
     img = np.ascontiguousarray(img, np.uint8)
     e = np.empty(img.shape, np.float32)
