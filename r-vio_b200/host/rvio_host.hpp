@@ -13,9 +13,13 @@
 //   * -DRVIO_B200_WITH_OPENCV_EIGEN: the literal reference signatures (cv::Mat, std::list<ImuData*>, Eigen::VectorXd /
 //     MatrixXd, cv::FileStorage constructors).  Shown for the maintainer of the reference tree; see INTEGRATION.md.
 //
-// The corner detector is not part of the hot path: exactly as in the reference it stays a host object
-// (FeatureDetector::DetectWithSubPix / FindNewer).  The adaptor calls it through the `Detector` interface below between
-// rvio_tracker_track() and rvio_tracker_commit().
+// The corner detector: by default, exactly as in the reference, a host object
+// (FeatureDetector::DetectWithSubPix / FindNewer) that the adaptor calls through the `Detector` interface below between
+// rvio_tracker_track() and rvio_tracker_commit(); Tracker::UseDeviceDetector() moves DetectWithSubPix onto the GPU.
+//
+//     class RVIO::FusedVio { bool MonoVIO(im, lImuData, pose) }  -- one System::MonoVIO iteration (System.cc:173-365) as
+//     ONE device call (rvio_vio_step): track, propagate, update, augment and compose with x, P, pyramids and feature lists
+//     resident on the GPU, detector included; only the pose [pGk, qkG] of System.cc:369-374 comes back.
 #pragma once
 
 #include <cmath>
@@ -208,6 +212,47 @@ private:
     rvio_updater* mHandle;
     int mLastStatus;
     rvio_update_info mInfo{};
+};
+
+// One System::MonoVIO iteration per call (System.cc:173-365) on the device.  cfg carries every key System, Tracker, Updater,
+// PreIntegrator and FeatureDetector read from the YAML (rvio_vio_cfg).  The motion-detection / initialisation statics of
+// System.cc:175-249 live in the handle, so several sequences can run in one process.
+class FusedVio {
+public:
+    explicit FusedVio(const rvio_vio_cfg& cfg, int device = 0) : mHandle(nullptr), mLastStatus(RVIO_OK)
+    {
+        mLastStatus = rvio_vio_create(&cfg, device, &mHandle);
+        if (mLastStatus != RVIO_OK) throw std::runtime_error(std::string("rvio_vio_create: ") + rvio_b200_last_error());
+    }
+    ~FusedVio() { rvio_vio_destroy(mHandle); }
+    FusedVio(const FusedVio&) = delete;
+    FusedVio& operator=(const FusedVio&) = delete;
+
+    // pMeasurements = {image, imus} of System.cc:179-181.  Returns true when a pose was produced (false while the filter is
+    // still initialising, System.cc:183-249); pose = [pGk(3), qkG(4)] as written to stamped_pose_ests.dat (System.cc:371-373).
+    bool MonoVIO(const uint8_t* im, int width, int height, int stride_bytes, int channels, const std::list<ImuData*>& lImuData,
+                 double pose[7])
+    {
+        std::vector<double> imu;
+        imu.reserve(lImuData.size() * 8);
+        for (const ImuData* d : lImuData) {
+            imu.insert(imu.end(), d->AngularVel, d->AngularVel + 3);
+            imu.insert(imu.end(), d->LinearAccel, d->LinearAccel + 3);
+            imu.push_back(d->Timestamp);
+            imu.push_back(d->TimeInterval);
+        }
+        int valid = 0;
+        mLastStatus = rvio_vio_step(mHandle, im, width, height, stride_bytes, channels, imu.data(), (int)lImuData.size(),
+                                    nullptr, /*n_cand: device detector*/ -1, 0, pose, &valid);
+        return mLastStatus >= 0 && valid != 0;
+    }
+
+    int last_status() const { return mLastStatus; }
+    rvio_vio* handle() { return mHandle; }
+
+private:
+    rvio_vio* mHandle;
+    int mLastStatus;
 };
 
 }  // namespace RVIO
