@@ -21,6 +21,8 @@ def main():
     ap.add_argument("asl_dir"); ap.add_argument("out_dir")
     ap.add_argument("--config", default=None, help="R-VIO yaml (keys of config/rvio_euroc.yaml); default: EuRoC values")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--detector", default="device", choices=["device", "host"],
+                    help="device: FeatureDetector::DetectWithSubPix on the GPU inside the step; host: cv2 on the equalised frame")
     args = ap.parse_args()
     cfg = synth.Config.from_yaml(args.config) if args.config else synth.Config()
     import cv2
@@ -33,10 +35,12 @@ def main():
     started = False
     for t, im, imu in io_formats.EurocAslReader(args.asl_dir, cfg.time_offset):
         t0 = time.perf_counter()
-        eq = clahe.apply(im) if cfg.enable_equalizer else im     # the image the reference's detector sees (Tracker.cc:198-207)
-        cand = orc.detect_with_subpix(eq, cfg.n_features, 2 if started else 1, cfg)
+        cand = None
+        if args.detector == "host":
+            eq = clahe.apply(im) if cfg.enable_equalizer else im     # the image the reference's detector sees (Tracker.cc:198-207)
+            cand = orc.detect_with_subpix(eq, cfg.n_features, 2 if started else 1, cfg)
         t1 = time.perf_counter()
-        pose = vio.step(im, imu, cand)
+        pose = vio.step(im, imu, cand, device_detector=args.detector == "device")
         t2 = time.perf_counter()
         if pose is not None:
             started = True
