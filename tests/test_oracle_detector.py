@@ -60,3 +60,39 @@ def test_detect_with_subpix_matches_cv2(s):
     print(f"s={s}: {common}/{tot} corners common, {tight} within 1e-4 px, worst sub-pixel difference {worst:.2e} px")
     # an iteration more or less at the eps = 0.01 px stopping rule moves a corner by up to a few 0.01 px
     assert common >= 0.97 * tot and tight >= 0.98 * tot and worst < 5e-2
+
+
+def test_golden_detector_and_fisheye():
+    """Committed fixture (oracle/make_golden_detector.py, cv2 4.13.0): corner lists of goodFeaturesToTrack, cornerSubPix
+    positions, the min-eigenvalue maps and cv::fisheye::undistortPoints on the golden frames -- no live cv2 needed."""
+    import os
+    root = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(root, "golden", "detector_golden.npz"))
+    t = np.load(os.path.join(root, "golden", "tracker_golden.npz"))
+
+    class C:            # just the two keys detect_restated reads
+        qual_lvl = 0.01
+        min_dist = 15.0
+    n_corner = n_tight = 0
+    for k, img in enumerate(t["clahe"]):
+        img = np.ascontiguousarray(img)
+        if k == 0:
+            e = orc.min_eig_map(img)
+            w = img.shape[1]
+            assert int((e[:, :w - 17] != g["eig0"][:, :w - 17]).sum()) <= 1e-4 * e.size
+            np.testing.assert_allclose(e, g["eig0"], rtol=1e-4, atol=2e-8)
+        for s, md in ((1, 15.0), (2, 15.0), (1, 8.0)):
+            C.min_dist = md
+            want_i = g[f"gftt{k}_s{s}_d{int(md)}"]
+            got_i = orc.good_features(img, 128, float(np.float32(0.01)), s * md)
+            assert np.array_equal(got_i, want_i), (k, s, md)                   # integer corners: identical, same order
+            want = g[f"subpix{k}_s{s}_d{int(md)}"]
+            got = orc.detect_restated(img, 128, s, C)
+            d = np.linalg.norm(got - want, axis=1)
+            n_corner += len(d); n_tight += int((d < 1e-4).sum())
+            assert d.max() < 5e-2, (k, s, md, float(d.max()))
+    assert n_corner > 300 and n_tight >= 0.98 * n_corner
+    un = np.empty_like(g["fisheye_px"])
+    orc.lib().orc_undistort_fisheye(np.ascontiguousarray(g["fisheye_px"]), len(un), np.ascontiguousarray(g["fisheye_K4"]),
+                                    np.ascontiguousarray(g["fisheye_D4"]), un)
+    assert np.array_equal(un.view(np.uint32), g["fisheye_un"].view(np.uint32))
