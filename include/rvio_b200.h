@@ -133,7 +133,20 @@ typedef struct rvio_updater_cfg {
 typedef struct rvio_update_info {
     int32_t n_feat, n_good, rows_stacked, updated;
     int32_t n_reject_init, n_reject_lm, n_reject_gate;
+    int32_t rank;                     /* rows of the compressed system that entered the EKF step (nRank, Updater.cc:515-524) */
+    int32_t rank_flags;               /* RVIO_RANK_* bits below */
 } rvio_update_info;
+
+/* Model compression (Updater.cc:474-536).  The reference keeps the rows of its Givens trapezoid up to the FIRST row with
+ * norm < 1e-4; when a dependent column sits in the middle of the stacked Jacobian that cut also discards later,
+ * informative rows.  RVIO_RANK_RULE_REFERENCE (default) reproduces exactly that; RVIO_RANK_RULE_FULL_INFORMATION keeps
+ * every row (the normal terms of the whole stack).  rank_flags of rvio_update_info reports per frame what happened. */
+#define RVIO_RANK_RULE_REFERENCE         0
+#define RVIO_RANK_RULE_FULL_INFORMATION  1
+#define RVIO_RANK_CUT_DISCARDED  1    /* the reference's cut discarded information on this frame */
+#define RVIO_RANK_BY_SWEEP       2    /* decided by replaying the reference's Givens sweep (otherwise by the certificate) */
+#define RVIO_RANK_UNDECIDED      4    /* feature-sharded call with a dependent column in the middle: full information used */
+#define RVIO_RANK_REBUILT        8    /* normal terms rebuilt from the kept rows */
 
 /* Updater::Updater(const cv::FileStorage&)  -- System.cc:98 */
 int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio_updater** out);
@@ -151,6 +164,10 @@ int rvio_updater_update(rvio_updater* upd, const double* x, int xdim, const doub
  * (no D2H/H2D of the lists); both handles must live on the same device. */
 int rvio_updater_update_from_tracker(rvio_updater* upd, rvio_tracker* trk, const double* x, int xdim,
                                      const double* P, int d, double* x_out, double* P_out, rvio_update_info* info);
+
+/* Selects the compression rule (see above).  May be called between frames at any time (also on the updater a fused
+ * pipeline owns: rvio_vio_updater). */
+int rvio_updater_set_rank_rule(rvio_updater* upd, int mode);
 
 /* Per-feature parity observables of the last update: status (0 accepted, 1 init reject, 2 LM reject, 3 gate reject),
  * inverse-depth estimate [phi psi rho], Mahalanobis distance, dof. */

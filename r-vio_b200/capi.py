@@ -40,7 +40,7 @@ class VioCfg(C.Structure):
 
 class UpdateInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_feat", "n_good", "rows_stacked", "updated",
-                                          "n_reject_init", "n_reject_lm", "n_reject_gate")]
+                                          "n_reject_init", "n_reject_lm", "n_reject_gate", "rank", "rank_flags")]
 
 
 # every symbol include/rvio_b200.h declares (tests check that the library exports all of them)
@@ -51,7 +51,7 @@ SYMBOLS = [
     "rvio_tracker_get_debug", "rvio_tracker_get_ransac_debug", "rvio_tracker_get_pyramid",
     "rvio_updater_create", "rvio_updater_destroy", "rvio_updater_update", "rvio_updater_update_from_tracker",
     "rvio_updater_get_debug", "rvio_updater_get_normal_terms", "rvio_updater_update_begin",
-    "rvio_updater_reduce_buffer", "rvio_updater_update_finish",
+    "rvio_updater_reduce_buffer", "rvio_updater_update_finish", "rvio_updater_set_rank_rule",
     "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_get_state",
     "rvio_vio_get_update_info", "rvio_vio_tracker", "rvio_vio_updater", "rvio_vio_timeline", "rvio_vio_graphs",
     "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
@@ -105,6 +105,7 @@ def lib():
     L.rvio_updater_update_begin.argtypes = [vp, f64, ci, f64, ci, u8, i32, f32, ci, ci, ci]
     L.rvio_updater_reduce_buffer.argtypes = [vp, C.POINTER(vp), pi]
     L.rvio_updater_update_finish.argtypes = [vp, f64, f64, C.POINTER(UpdateInfo)]
+    L.rvio_updater_set_rank_rule.argtypes = [vp, ci]
     L.rvio_vio_create.argtypes = [C.POINTER(VioCfg), ci, C.POINTER(vp)]
     L.rvio_vio_destroy.argtypes = [vp]
     L.rvio_vio_destroy.restype = None

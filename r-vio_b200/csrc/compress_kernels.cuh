@@ -1,0 +1,29 @@
+// compress_kernels.cuh -- parameters of the reference compression rule stage (compress.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvio {
+
+struct RankRuleParams {
+    double* red;              // [G (n*n) | z (n) | counters (8)], rewritten in place when the cut discards rows
+    int n, world;
+    const int* rule_dev;      // 0 = the reference's rule (Updater.cc:515-524), 1 = full information
+    double* U_glob;           // n x (n|1) scratch for windows too large for shared memory
+    int use_glob;
+    int32_t* rr;              // record: [0] mode (0 off, 1 unchanged, 2 rebuilt, 3 sweep needed, 4 undecided), [1] rows kept,
+                              //         [2] N' (columns after the trailing-zero drop), [3] sweep requested, [4] rows >= 1e-4 after the sweep
+};
+
+struct GivensRefParams {
+    const double* Hblk; const double* rblk; const int32_t* f_dof;
+    int n_feat; const int* n_feat_dev; int n, blk_rows;
+    double* red; int32_t* rr;
+    double* win;              // window storage in global memory when it does not fit in shared memory
+};
+
+int compress_configure(int nmax);
+size_t givens_window_doubles(int n);
+int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq, int nmax);
+
+}  // namespace rvio

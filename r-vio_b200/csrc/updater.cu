@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "tracker_kernels.cuh"
 #include "updater_kernels.cuh"
+#include "compress_kernels.cuh"
 #include "chi2_table.h"
 
 #include <math.h>
@@ -1208,11 +1209,13 @@ struct rvio_updater {
     uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma; int32_t *d_fdof, *d_fc0, *d_fwc;
     double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2, *d_T, *d_Yt;
     int* d_sing; int* d_tickets;
+    int* d_rule; int32_t* d_rr; double *d_U, *d_gwin;      // reference compression rule (compress.cu)
+    int rank_rule;
     int groups_cap;
     // pinned
-    double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing;
+    double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing; int* h_rule;
     // state of an open begin/finish pair
-    int cur_N, cur_xdim, cur_d, cur_nfeat, cur_rank, cur_world; bool open;
+    int cur_N, cur_xdim, cur_d, cur_nfeat, cur_rank, cur_world; bool open; const int* cur_nfeat_dev;
     const double* cur_x_dev; const double* cur_P_dev;
     std::vector<void*> allocs, hallocs;
 };
@@ -1296,12 +1299,16 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1);
     A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
-    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1); A(u->d_tickets, 64);
+    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
+    A(u->d_tickets, (size_t)div_up((int)n, 32) * div_up((int)n, 32) + 64);
+    A(u->d_rule, 4); A(u->d_rr, 8); A(u->d_U, n * (n + 1)); A(u->d_gwin, givens_window_doubles((int)n));
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
-    HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4);
+    HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4); HA(u->h_rule, 4);
 #undef HA
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_chi2, RVIO_CHI2_95_HOST, sizeof(double) * 500, cudaMemcpyHostToDevice, u->stream));
+    u->rank_rule = 0;                                    // the reference's rule (d_rule is zero-initialised)
+    if ((rc = compress_configure(u->nmax)) != RVIO_OK) return rc;
     RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
     *out = u;
     return RVIO_OK;
@@ -1330,7 +1337,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
 {
     const int N = (xdim - 26) / 7, n = 6 * N;
     u->cur_N = N; u->cur_xdim = xdim; u->cur_d = d; u->cur_nfeat = n_feat_cap; u->cur_rank = rank; u->cur_world = world;
-    u->cur_x_dev = x_dev; u->cur_P_dev = P_dev;
+    u->cur_x_dev = x_dev; u->cur_P_dev = P_dev; u->cur_nfeat_dev = n_feat_dev;
     u->open = true;
     if (n_feat_cap > 0 && N > 0) {
         FeatureParams fp;
@@ -1368,6 +1375,16 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         RVIO_ENQ(cudaMemcpyAsync(x_out_dev, x_dev, sizeof(double) * xdim, cudaMemcpyDeviceToDevice, s));
         RVIO_ENQ(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
         return RVIO_OK;
+    }
+    {
+        // which rows the reference's compression keeps (Updater.cc:474-536): may rewrite [G | z] in place
+        RankRuleParams rq;
+        rq.red = u->d_red; rq.n = n; rq.world = u->cur_world; rq.rule_dev = u->d_rule; rq.U_glob = u->d_U; rq.use_glob = 0; rq.rr = u->d_rr;
+        GivensRefParams gq;
+        gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.f_dof = u->d_fdof; gq.n_feat = u->cur_nfeat; gq.n_feat_dev = u->cur_nfeat_dev;
+        gq.n = n; gq.blk_rows = u->lay.Mc; gq.red = u->d_red; gq.rr = u->d_rr; gq.win = u->d_gwin;
+        const int r2 = enqueue_rank_rule(s, rq, gq, n);
+        if (r2 != RVIO_OK) return r2;
     }
     if (N <= kSolveSmallMaxClones) {
         SolveSmallParams sp;
@@ -1536,6 +1553,7 @@ extern "C" int rvio_updater_update_finish(rvio_updater* u, double* x_out, double
     inf.n_feat = u->cur_nfeat; inf.n_good = (int)u->h_red[0]; inf.rows_stacked = (int)u->h_red[1];
     inf.n_reject_init = (int)u->h_red[2]; inf.n_reject_lm = (int)u->h_red[3]; inf.n_reject_gate = (int)u->h_red[4];
     inf.updated = inf.n_good > 2 ? 1 : 0;
+    inf.rank = (int)u->h_red[6]; inf.rank_flags = (int)u->h_red[7];
     if (info) *info = inf;
     memcpy(x_out, u->h_x, sizeof(double) * xdim);
     memcpy(P_out, u->h_P, sizeof(double) * (size_t)d * d);
@@ -1596,3 +1614,14 @@ extern "C" int rvio_updater_get_normal_terms(rvio_updater* u, double* G, double*
 }
 
 extern "C" void* rvio_updater_stream(rvio_updater* u) { return u ? (void*)u->stream : nullptr; }
+
+extern "C" int rvio_updater_set_rank_rule(rvio_updater* u, int mode)
+{
+    RVIO_ARG_CHECK(u && (mode == RVIO_RANK_RULE_REFERENCE || mode == RVIO_RANK_RULE_FULL_INFORMATION));
+    RVIO_CUDA_TRY(cudaSetDevice(u->device));
+    u->rank_rule = mode;
+    *u->h_rule = mode;
+    RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_rule, u->h_rule, sizeof(int), cudaMemcpyHostToDevice, u->stream));
+    RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
+    return RVIO_OK;
+}

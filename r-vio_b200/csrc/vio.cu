@@ -509,6 +509,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         inf.n_good = (int)v->h_cnt[0]; inf.rows_stacked = (int)v->h_cnt[1];
         inf.n_reject_init = (int)v->h_cnt[2]; inf.n_reject_lm = (int)v->h_cnt[3]; inf.n_reject_gate = (int)v->h_cnt[4];
         inf.updated = inf.n_good > 2 ? 1 : 0;
+        inf.rank = (int)v->h_cnt[6]; inf.rank_flags = (int)v->h_cnt[7];
     }
     v->last_info = inf;
     return RVIO_OK;

@@ -257,6 +257,10 @@ class Updater:
         self.xk1k1, self.Pk1k1 = xo, Po.T.copy()
         return self.xk1k1, self.Pk1k1
 
+    def set_rank_rule(self, full_information: bool):
+        """False (default): the reference's first-small-row cut (Updater.cc:515-524); True: keep every row."""
+        capi.check(self.L.rvio_updater_set_rank_rule(self.h, 1 if full_information else 0))
+
     def debug(self, n_feat):
         st = np.zeros(max(n_feat, 1), np.uint8); pf = np.zeros(3 * max(n_feat, 1)); gm = np.zeros(max(n_feat, 1))
         dof = np.zeros(max(n_feat, 1), np.int32)
@@ -320,6 +324,9 @@ class Vio:
         x = np.zeros(xd.value); P = np.zeros(d.value * d.value)
         capi.check(self.L.rvio_vio_get_state(self.h, x.ctypes.data, C.byref(xd), P.ctypes.data, C.byref(d)))
         return x, P.reshape(d.value, d.value).T.copy()
+
+    def set_rank_rule(self, full_information: bool):
+        capi.check(self.L.rvio_updater_set_rank_rule(self.L.rvio_vio_updater(self.h), 1 if full_information else 0))
 
     def update_info(self):
         inf = capi.UpdateInfo()

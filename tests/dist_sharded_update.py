@@ -65,9 +65,8 @@ def main():
         msg = f"sharded update ok: world={world} feats={n_feat} N={cfg.window} good={info.n_good} rows={info.rows_stacked} ms/update={min(times):.3f}"
         if os.environ.get("RVIO_TEST_ORACLE", "1") == "1":
             from oracle import oracle as orc
-            orc.lib().orc_updater_set_rank_rule(1)
-            xc, Pcpu, oi = orc.updater_update(cfg, x, P, types, off, xy)
-            orc.lib().orc_updater_set_rank_rule(0)
+            xc, Pcpu, oi = orc.updater_update(cfg, x, P, types, off, xy)       # the reference's rule
+            assert info.rank == oi.rank and not (info.rank_flags & 4), (info.rank, oi.rank, info.rank_flags)
             np.testing.assert_allclose(xo, xc, rtol=0, atol=1e-9)
             msg += " (matches CPU oracle)"
         print(msg)

@@ -76,7 +76,6 @@ def test_vio_with_device_detector_matches_oracle():
     o = orc.VioOracle(cfg, det) if "detector" in orc.VioOracle.__init__.__code__.co_varnames else None
     if o is None:
         pytest.skip("oracle pipeline has no pluggable detector")
-    orc.lib().orc_updater_set_rank_rule(1)
     try:
         consumed = 0
         worst = 0.0
@@ -93,4 +92,4 @@ def test_vio_with_device_detector_matches_oracle():
                 worst = max(worst, float(np.abs(pg[:3] - po[:3]).max()))
         assert poses >= 25 and worst < 1e-7, (poses, worst)
     finally:
-        orc.lib().orc_updater_set_rank_rule(0)
+        pass

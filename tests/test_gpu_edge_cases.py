@@ -143,13 +143,7 @@ def _case(cfg, n_feat, seed, **kw):
 
 
 def _compare_update(cfg, x, P, types, off, xy, expect_updated=None):
-    xo, Po, info, dbg = orc.updater_update(cfg, x, P, types, off, xy, debug=True)
-    if info.updated and info.rank < info.rank_full:
-        orc.lib().orc_updater_set_rank_rule(1)
-        try:
-            xo, Po, _, _ = orc.updater_update(cfg, x, P, types, off, xy, debug=True)
-        finally:
-            orc.lib().orc_updater_set_rank_rule(0)
+    xo, Po, info, dbg = orc.updater_update(cfg, x, P, types, off, xy, debug=True)      # the reference's rule
     upd = host.Updater(cfg)
     xg, Pg = upd.update(x, P, types, (off, xy))
     gd = upd.debug(len(types))
@@ -157,6 +151,8 @@ def _compare_update(cfg, x, P, types, off, xy, expect_updated=None):
     assert (upd.info.n_good, upd.info.n_reject_init, upd.info.n_reject_lm, upd.info.n_reject_gate) == \
            (info.n_good, info.n_reject_init, info.n_reject_lm, info.n_reject_gate)
     assert upd.info.updated == info.updated
+    if info.updated:
+        assert upd.info.rank == info.rank
     if expect_updated is not None:
         assert info.updated == expect_updated
     np.testing.assert_allclose(xg, xo, rtol=0, atol=1e-9)

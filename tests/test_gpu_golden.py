@@ -75,3 +75,33 @@ def test_color_conversion_vs_opencv(is_rgb, key):
     capi.check(L.rvio_tracker_get_image(h, out, W))
     assert np.array_equal(out, g[key])
     L.rvio_tracker_destroy(h)
+
+
+UGOLD = os.path.join(os.path.dirname(__file__), "golden", "update_golden.npz")
+
+
+def test_update_golden_vectors():
+    """Updater::update on the device against the frozen vectors of oracle/make_golden_update.py (reference rule; shapes of
+    configs 1, 2, 3, 5; includes the frames where the reference's first-small-row cut discards rows and where only the
+    replay of its Givens sweep can decide).  float64: x 1e-9, P 1e-9 relative, kept-row count and per-feature status exact."""
+    g = np.load(UGOLD)
+    seen_cut = seen_sweep = 0
+    for name in g["names"]:
+        cfg = synth.baseline_config(int(g[f"{name}/cfg"]))
+        upd = host.Updater(cfg)
+        x, P = g[f"{name}/x"], g[f"{name}/P"]
+        xg, Pg = upd.update(x, P, g[f"{name}/types"], (g[f"{name}/off"], g[f"{name}/xy"]))
+        gi = upd.info
+        gd = upd.debug(len(g[f"{name}/types"]))
+        assert np.array_equal(gd["status"], g[f"{name}/status"]), name
+        ok = g[f"{name}/status"] == 0
+        np.testing.assert_allclose(gd["gamma"][ok], g[f"{name}/gamma"][ok], rtol=1e-8, err_msg=name)
+        assert gi.n_good == int(g[f"{name}/n_good"]) and gi.rows_stacked == int(g[f"{name}/rows"]), name
+        assert gi.rank == int(g[f"{name}/rank"]), (name, gi.rank, int(g[f"{name}/rank"]), gi.rank_flags)
+        cut = int(g[f"{name}/rank"]) < int(g[f"{name}/rank_full"])
+        assert bool(gi.rank_flags & 1) == cut, (name, gi.rank_flags)
+        seen_cut += int(cut); seen_sweep += int(bool(gi.rank_flags & 2))
+        np.testing.assert_allclose(xg, g[f"{name}/x_out"], rtol=0, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(Pg, g[f"{name}/P_out"], rtol=0, atol=1e-9 * np.abs(g[f"{name}/P_out"]).max(), err_msg=name)
+        upd.close()
+    assert seen_cut >= 2 and seen_sweep >= 2

@@ -3,9 +3,11 @@
 Tolerances (float64 device arithmetic, different but algebraically identical factorisations):
   per-feature inverse depth 1e-9, Mahalanobis distance 1e-8 relative, normal terms 1e-9 relative,
   state 1e-9 absolute (bar in BASELINE.json: 1e-5 m / 1e-4 rad), covariance 1e-9 relative to max|P|.
-The reference's first-small-row rank cut (Updater.cc:515-524) can discard informative rows of the compressed system;
-the CUDA path compresses to normal terms and never does.  Frames where the cut bites (oracle rank < rank_full) are
-compared against the oracle with the cut disabled, and counted.
+The reference's first-small-row rank cut (Updater.cc:515-524) can discard informative rows of the compressed system.
+The device reproduces it (compress.cu: certificate on the normal terms, or a replay of the reference's Givens sweep);
+every case here is compared against the oracle in its DEFAULT (reference) rule, the kept-row count included, and the
+frames where the cut discards information are counted.  The full-information mode is compared against the oracle with
+the cut disabled.
 """
 import numpy as np
 import pytest
@@ -38,15 +40,26 @@ def _check_case(cfg, upd, x, Pc, types, off, xy, stats):
     n = d - 24
     L = orc.lib()
     L.orc_updater_set_rank_rule(0)
-    xo, Po, info, dbg = orc.updater_update(cfg, x, P, types, off, xy, debug=True)
+    xo, Po, info, dbg = orc.updater_update(cfg, x, P, types, off, xy, debug=True)          # the reference's rule
     cut = info.updated and info.rank < info.rank_full
-    if cut:
-        L.orc_updater_set_rank_rule(1)
-        xo, Po, info2, _ = orc.updater_update(cfg, x, P, types, off, xy, debug=True)
-        L.orc_updater_set_rank_rule(0)
-        stats["rank_cut_frames"] += 1
     xg, Pg = upd.update(x, P, types, (off, xy))
     gi = upd.info
+    if info.updated:
+        assert gi.rank == info.rank, (gi.rank, info.rank, info.rank_full, gi.rank_flags)
+        assert bool(gi.rank_flags & 1) == bool(cut), (gi.rank_flags, info.rank, info.rank_full)
+        stats["by_sweep"] = stats.get("by_sweep", 0) + int(bool(gi.rank_flags & 2))
+    if cut:
+        stats["rank_cut_frames"] += 1
+        # the other mode: every row kept == the oracle with the cut disabled
+        L.orc_updater_set_rank_rule(1)
+        xf, Pf, _, _ = orc.updater_update(cfg, x, P, types, off, xy, debug=True)
+        L.orc_updater_set_rank_rule(0)
+        upd.set_rank_rule(True)
+        xg2, Pg2 = upd.update(x, P, types, (off, xy))
+        upd.set_rank_rule(False)
+        np.testing.assert_allclose(xg2, xf, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(Pg2, Pf, rtol=0, atol=1e-9 * np.abs(Pf).max())
+        stats["cut_effect"] = max(stats.get("cut_effect", 0.0), float(np.abs(xf - xo).max()))
     nf = len(types)
     assert gi.n_feat == nf
     if nf:
@@ -59,7 +72,7 @@ def _check_case(cfg, upd, x, Pc, types, off, xy, stats):
         np.testing.assert_allclose(gd["gamma"][gok], dbg["gamma"][gok], rtol=1e-8, atol=1e-10)
         assert gi.n_good == info.n_good and gi.rows_stacked == info.rows_stacked
         assert (gi.n_reject_init, gi.n_reject_lm, gi.n_reject_gate) == (info.n_reject_init, info.n_reject_lm, info.n_reject_gate)
-        if info.rows_stacked > 0:
+        if info.rows_stacked > 0 and not (gi.rank_flags & 8):
             G, z = upd.normal_terms(n)
             Go = dbg["H"].T @ dbg["H"]; zo = dbg["H"].T @ dbg["r"]
             np.testing.assert_allclose(G, Go, rtol=0, atol=1e-9 * max(1.0, np.abs(Go).max()))
@@ -76,7 +89,7 @@ def _check_case(cfg, upd, x, Pc, types, off, xy, stats):
 
 def test_updater_stream_config2():
     cfg = synth.baseline_config(1)
-    cases = _collect_cases(cfg, 70, 20260923)
+    cases = _collect_cases(cfg, 100, 20260923)
     assert len(cases) >= 40
     upd = host.Updater(cfg)
     stats = dict(cases=0, updated=0, rank_cut_frames=0, max_dx=0.0, max_err_x=0.0)
@@ -84,6 +97,7 @@ def test_updater_stream_config2():
         _check_case(cfg, upd, *c, stats)
     print("updater config2:", stats)
     assert stats["updated"] >= 30
+    assert stats["rank_cut_frames"] >= 1                  # frame 47 of this stream: '2' and '1' supports are disjoint
 
 
 def test_updater_stream_config1():

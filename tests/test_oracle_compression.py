@@ -1,0 +1,94 @@
+"""CPU: the compression / rank-cut / EKF stage of oracle/updater.c (Updater.cc:460-619) against a second, independent
+restatement (oracle/np_compress.py: wavefront-ordered Givens + SciPy Householder QR + numpy gain) -- the stage the parity
+claim hinges on.  Covers the reference-rule branch itself, including the frame where the cut discards informative rows."""
+import numpy as np
+import pytest
+
+import rvio_b200  # noqa: F401
+from rvio_b200 import synth
+from oracle import oracle as orc, np_compress as npc
+
+
+def _stream_cases(cfg, n_frames, seed):
+    st = synth.Stream(cfg, n_frames, seed, t_static=0.5)
+    v = orc.VioOracle(cfg)
+    consumed, out = 0, []
+    for i in range(st.n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        v.step(st.frames[i], imu)
+        if v.last_info is not None and v.last_info.updated:
+            out.append((i,) + tuple(a.copy() for a in v.last_update_in))
+        v.last_info = None
+    return out
+
+
+@pytest.fixture(scope="module")
+def cases2():
+    return synth.baseline_config(1), _stream_cases(synth.baseline_config(1), 72, 20260923)
+
+
+def _check(cfg, x, Pc, types, off, xy):
+    d = int(round(np.sqrt(len(Pc)))); P = Pc.reshape(d, d).T.copy()
+    xo, Po, info, dbg = orc.updater_update(cfg, x, P, types, off, xy, debug=True)        # default = reference rule
+    sigma = float(max(np.float32(cfg.sigma_px), np.float32(cfg.sigma_py)))
+    Hn, rn, ci = npc.compress_reference(dbg["H"], dbg["r"])
+    assert ci["rank"] == info.rank, (ci["rank"], info.rank)
+    assert ci["rank_full"] == info.rank_full
+    assert bool(ci["compressed"]) == bool(info.compressed)
+    xn, Pn = npc.ekf_reference_form(x, P, Hn, rn, sigma)
+    np.testing.assert_allclose(xo, xn, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Po, Pn, rtol=0, atol=1e-10 * np.abs(Po).max())
+    if ci["compressed"]:
+        # Householder QR (SciPy): rows before the first dependent column are unique up to sign
+        Rq, j = npc.unique_rows_by_qr(dbg["H"])
+        k = min(j, info.rank)
+        np.testing.assert_allclose(np.abs(Rq[:k]), np.abs(ci["trapezoid"][:k]), rtol=0, atol=1e-9 * max(1.0, np.abs(Rq).max()))
+        assert info.rank >= min(j, ci["Np"]) or ci["norms"][info.rank] < 1e-4
+        if info.rank == info.rank_full:               # nothing informative dropped: kept rows carry all of H^T H
+            G = dbg["H"].T @ dbg["H"]
+            np.testing.assert_allclose(Hn.T @ Hn, G, rtol=0, atol=1e-9 * max(1.0, np.abs(G).max()))
+    return info
+
+
+def test_compression_stage_two_restatements_agree_on_the_stream(cases2):
+    cfg, cs = cases2
+    n_comp = n_cut = 0
+    for (i, x, Pc, types, off, xy) in cs:
+        info = _check(cfg, x, Pc, types, off, xy)
+        n_comp += int(info.compressed)
+        n_cut += int(info.compressed and info.rank < info.rank_full)
+    print(f"{len(cs)} updates, {n_comp} compressed, {n_cut} where the cut discards informative rows")
+    assert n_comp >= 25 and n_cut >= 1                    # frame 47: rank 29 of 38
+
+
+@pytest.mark.parametrize("idx,n_feat,n_clones", [(0, 40, None), (1, 60, None), (2, 40, None), (1, 30, 14)])
+def test_compression_stage_worstcase_shapes(idx, n_feat, n_clones):
+    cfg = synth.baseline_config(idx)
+    x, P, types, off, xy = synth.make_update_case(cfg, n_feat, 300 + idx, n_clones=n_clones)
+    info = _check(cfg, x, np.ascontiguousarray(P.T).reshape(-1), types, off, xy)
+    assert info.updated and info.compressed
+
+
+def test_disjoint_supports_trigger_the_cut():
+    """'2' features cover the first clones, short '1' features the last ones: the stacked Jacobian has a dependent column
+    in the middle and the reference's cut drops every '1' row (the mechanism behind frame 47)."""
+    cfg = synth.baseline_config(1)
+    N = cfg.window
+    xa, Pa, ta, oa, xya = synth.make_update_case(cfg, 24, 5, track_len=4, mix_types=True)
+    info = _check(cfg, xa, np.ascontiguousarray(Pa.T).reshape(-1), ta, oa, xya)
+    assert info.compressed and info.rank < info.rank_full
+    assert info.rank == 6 * ((N + 2) // 2 - 1) - 1        # rank of the '2' block: 6 (ceil(Lmax/2) - 1) columns minus the gauge direction
+
+
+def test_oracle_reproduces_golden_update_vectors():
+    """tests/golden/update_golden.npz (oracle/make_golden_update.py): the C restatement still produces the frozen outputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "update_golden.npz"))
+    for name in g["names"]:
+        cfg = synth.baseline_config(int(g[f"{name}/cfg"]))
+        xo, Po, info, dbg = orc.updater_update(cfg, g[f"{name}/x"], g[f"{name}/P"], g[f"{name}/types"], g[f"{name}/off"],
+                                               g[f"{name}/xy"], debug=True)
+        assert info.rank == int(g[f"{name}/rank"]) and info.rank_full == int(g[f"{name}/rank_full"]), name
+        assert np.array_equal(dbg["status"], g[f"{name}/status"]), name
+        np.testing.assert_allclose(xo, g[f"{name}/x_out"], rtol=0, atol=1e-12, err_msg=name)
+        np.testing.assert_allclose(Po, g[f"{name}/P_out"], rtol=0, atol=1e-12 * np.abs(Po).max(), err_msg=name)
