@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the configs[2] stress stream and the worst-case update micro-benchmarks")
     ap.add_argument("--detector", default="inloop", choices=["inloop", "precomputed"],
                     help="inloop (default): FeatureDetector::DetectWithSubPix runs inside every timed step, on the GPU in this arm and "
                          "through cv2 in the reference arm (the whole Tracker::track); precomputed: corner candidates prepared "
@@ -81,105 +82,198 @@ def make_workload(cfg, n_frames, seed, precompute=True):
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, read in-process through NVML (nvidia-ml-py) every 100 ms: no
+    nvidia-smi process is forked while a step is being timed (round 1 forked one per rank every 200 ms).  Falls back to one
+    nvidia-smi query before and one after the region when NVML cannot be loaded."""
+    _BITS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self.samples, self.max_mhz, self.reasons, self.power = [], None, set(), []
         self.stop = False
         self.index = index
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
         self.th = threading.Thread(target=self.run, daemon=True)
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _nvml_sample(self):
+        nv = self.nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+        except Exception:
+            pass
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self._BITS.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi_sample(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                if "Active" in val and "Not" not in val:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
-                    if "Active" in val and "Not" not in val:
-                        self.reasons.add(name)
+                self._nvml_sample()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def __enter__(self):
-        self.th.start()
+        if self.nv is not None:
+            self.th.start()
+        else:
+            self._smi_sample()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.th.join(timeout=3)
+        if self.nv is not None:
+            self.th.join(timeout=3)
+        else:
+            self._smi_sample()
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None,
+                "how": "NVML in-process, 100 ms" if self.nv is not None else "nvidia-smi before/after the timed region"}
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this rank (and the pinned staging buffers it allocates afterwards, by first touch) to the CPUs of the NUMA node
+    its GPU hangs off, split evenly between the ranks that share the node.  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(local_rank))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        path = f"/sys/bus/pci/devices/{bus}/"
+        node = int(open(path + "numa_node").read())
+        cpus = open(path + "local_cpulist").read().strip()
+        ids = []
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.extend(range(int(a), int(b or a) + 1))
+        ids = sorted(set(ids) & os.sched_getaffinity(0))
+        if not ids:
+            return {"numa_node": node, "bound": False}
+        # ranks on the same node take disjoint slices
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        per_node = max(1, (local_world + 1) // 2) if local_world > 1 else 1
+        k = local_rank % per_node
+        sl = ids[k * len(ids) // per_node:(k + 1) * len(ids) // per_node] or ids
+        os.sched_setaffinity(0, sl)
+        return {"numa_node": node, "bound": True, "cpus": f"{sl[0]}-{sl[-1]} ({len(sl)})"}
+    except Exception as e:          # pragma: no cover
+        return {"bound": False, "why": repr(e)[:80]}
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
+def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush):
+    """pre-roll until the first valid pose, W warm-up steps, K timed steps (per-step CUDA events on the library's own stream,
+    L2 flush between timed steps outside the event pair).  Returns (per-step ms list, wall seconds, launches, frames used)."""
+    import torch
+    frames, imus = wl["frames"], wl["imus"]
+    n_frames = len(frames)
+    stream = torch.cuda.ExternalStream(L.rvio_tracker_stream(L.rvio_vio_tracker(vio.h)), device=dev)
+    if dev_inputs:
+        d_frames = [torch.from_numpy(f).to(dev) for f in frames]
+        d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
+        d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
+        torch.cuda.synchronize()
+    got_pose = False
+    i = 0
+    timed, warm = 0, 0
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = None
+    wall = 0.0
+    infos = []
+    while timed < K:
+        if i >= n_frames:
+            raise RuntimeError("stream too short for the requested steps")
+        cands = wl["cand2"] if got_pose else wl["cand1"]
+        timing = got_pose and warm >= W
+        if timing:
+            if not os.environ.get("RVIO_BENCH_NO_FLUSH"):              # diagnostic switch only: a number taken without the flush is not a bench value
+                flush.fill_(timed & 0xff)                              # L2 flush between timed iterations (untimed)
+            torch.cuda.synchronize()
+            if launches0 is None:
+                launches0 = L.rvio_b200_kernel_launches()
+            ev0[timed].record(stream)
+            t0 = time.perf_counter()
+        if dev_inputs:
+            if inloop:
+                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
+            else:
+                dc = (d_c2 if got_pose else d_c1)[i]
+                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
+                                    dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
+        else:
+            pose = vio.step(frames[i], imus[i], cands[i], device_detector=inloop)
+        if timing:
+            wall += time.perf_counter() - t0
+            ev1[timed].record(stream)
+            timed += 1
+            ui = vio.update_info()
+            infos.append((int(ui.n_feat), int(ui.n_good), int(ui.rows_stacked), int(ui.rank), int(ui.rank_flags)))
+        elif got_pose:
+            warm += 1
+        if pose is not None:
+            got_pose = True
+        i += 1
+    torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    return step_ms, wall, L.rvio_b200_kernel_launches() - launches0, i, infos
+
+
 def run_b200(args, cfg, wl, rank, world, local_rank):
     import torch
     import ctypes as C
     from rvio_b200 import capi, host
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank)
     L = capi.lib()
     K, W = args.steps, args.warmup
     frames, imus = wl["frames"], wl["imus"]
     n_frames = len(frames)
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     inloop = args.detector == "inloop"
-
-    def drive(vio, dev_inputs):
-        """pre-roll until the first valid pose, W warm-up steps, K timed steps.  Returns (per-step ms list, wall seconds, launches)."""
-        stream = torch.cuda.ExternalStream(L.rvio_tracker_stream(L.rvio_vio_tracker(vio.h)), device=dev)
-        if dev_inputs:
-            d_frames = [torch.from_numpy(f).to(dev) for f in frames]
-            d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
-            d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
-            torch.cuda.synchronize()
-        got_pose = False
-        i = 0
-        step_ms, timed, warm = [], 0, 0
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        launches0 = None
-        wall = 0.0
-        while timed < K:
-            if i >= n_frames:
-                raise RuntimeError("stream too short for the requested steps")
-            cands = wl["cand2"] if got_pose else wl["cand1"]
-            timing = got_pose and warm >= W
-            if timing:
-                if not os.environ.get("RVIO_BENCH_NO_FLUSH"):              # diagnostic switch only: a number taken without the flush is not a bench value
-                    flush.fill_(timed & 0xff)                              # L2 flush between timed iterations (untimed)
-                torch.cuda.synchronize()
-                if launches0 is None:
-                    launches0 = L.rvio_b200_kernel_launches()
-                ev0[timed].record(stream)
-                t0 = time.perf_counter()
-            if dev_inputs:
-                if inloop:
-                    pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
-                else:
-                    dc = (d_c2 if got_pose else d_c1)[i]
-                    pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
-                                        dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
-            else:
-                pose = vio.step(frames[i], imus[i], cands[i], device_detector=inloop)
-            if timing:
-                wall += time.perf_counter() - t0
-                ev1[timed].record(stream)
-                timed += 1
-            elif got_pose:
-                warm += 1
-            if pose is not None:
-                got_pose = True
-            i += 1
-        torch.cuda.synchronize()
-        step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
-        return step_ms, wall, L.rvio_b200_kernel_launches() - launches0, i
 
     import torch.distributed as dist
     def barrier():
@@ -191,13 +285,13 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         # ---- e2e leg (host buffers through the public C ABI)
         vio = host.Vio(cfg, local_rank)
         barrier()
-        e2e_ms, e2e_wall, _, _ = drive(vio, dev_inputs=False)
+        e2e_ms, e2e_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush)
         barrier()
         vio.close()
         # ---- device-resident leg (headline `value`)
         vio = host.Vio(cfg, local_rank)
         barrier()
-        dev_ms, dev_wall, launches, used = drive(vio, dev_inputs=True)
+        dev_ms, dev_wall, launches, used, infos = drive(L, vio, wl, K, W, dev, inloop, True, flush)
         barrier()
     # ---- batch leg (BASELINE configs[3]: independent streams, several per GPU, no communication): S handles driven by
     #      S host threads on the same device-resident frames; aggregate frames/s over the slowest stream (wall clock
@@ -302,8 +396,12 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
 
     t_dev = float(np.sum(dev_ms)) / 1e3
     t_e2e = float(np.sum(e2e_ms)) / 1e3
+    t_dev_rank, t_e2e_rank = [t_dev], [t_e2e]
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)                                           # per-rank times: the slow rank is named in the JSON line
+        t_dev_rank = [float(e[0]) for e in every]; t_e2e_rank = [float(e[1]) for e in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
         # every rank takes part in the same collectives, whatever happened to its own batch leg (a rank that skipped one
@@ -316,7 +414,112 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         else:
             batch = None
     return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
-                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch)
+                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch, infos=infos, affinity=affinity,
+                t_dev_rank=t_dev_rank, t_e2e_rank=t_e2e_rank)
+
+
+def update_cost_model(rows_per_feat, n, d):
+    """SURVEY 8(d) accounting for one Updater::update: fp32-equivalent flops (Householder accounting for the compression)
+    and algorithmic bytes (float64 here: H written once, read by the gate and by the compression; P in + out)."""
+    r = np.asarray(rows_per_feat, np.float64)
+    R = float(r.sum())
+    f_gate = float((2 * r * n * n + 2 * r * r * n).sum())
+    f_qr = max(0.0, 2 * R * n * n - (2.0 / 3.0) * n ** 3) if R > n else 0.0
+    rk = min(R, n)
+    f_ekf = 4 * d ** 3 + 2 * d * d * rk + 2 * rk ** 3 + 4 * d * n * rk + 2 * d * rk * rk + 2 * rk * n * n + 2 * rk * rk * n
+    return dict(R=int(R), flops=f_gate + f_qr + f_ekf, f_gate=f_gate, f_qr=f_qr, f_ekf=f_ekf,
+                bytes=8.0 * R * n * 3 + 16.0 * d * d)
+
+
+UPDATE_KERNELS = ("k_feature", "k_gate", "k_gram", "k_rank_rule", "k_givens_ref", "k_wgemm", "k_gj_block", "k_pout_finalize", "k_dgemm",
+                  "k_gauss_jordan", "k_finalize", "k_chol", "k_tsqr")
+
+
+def _profile_report(L):
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    nbytes = L.rvio_b200_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.raw[:nbytes].decode().splitlines():
+        name, cnt, tot = line.split()
+        out[name] = (int(cnt), float(tot))
+    return out
+
+
+def update_worstcase_leg(L, dev, flush, peaks, idx, reps=4):
+    """SURVEY 8(d) updater micro-benchmark: F_u maximum-length type-'1' tracks (the tallest stacked H of the config):
+    14 700 x 150 (configs[2]) and 60 416 x 180 (configs[4]).  Per-kernel CUDA events inside the library; the update-kernel
+    roofline is algorithmic bytes / flops of the whole update over the summed kernel time."""
+    import torch
+    from rvio_b200 import synth, host
+    cfg = synth.baseline_config(idx)
+    Fu = (cfg.n_features + 1) // 2
+    x, P, types, off, xy = synth.make_update_case(cfg, Fu, 900 + idx, mix_types=False)
+    N = cfg.max_track_len - 1; n = 6 * N; d = 24 + n
+    upd = host.Updater(cfg, dev.index)
+    for _ in range(2):
+        upd.update(x, P, types, (off, xy))
+    info = upd.info
+    dof = upd.debug(len(types))["dof"]
+    L.rvio_b200_profile(1)
+    wall = []
+    for r in range(reps):
+        flush.fill_(r); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        upd.update(x, P, types, (off, xy))
+        wall.append(time.perf_counter() - t0)
+    L.rvio_b200_profile(0)
+    prof = _profile_report(L)
+    upd.close()
+    per = {k: v[1] / reps for k, v in prof.items()}                        # ms per update
+    t_upd = sum(v for k, v in per.items() if any(k.startswith(u) for u in UPDATE_KERNELS)) / 1e3
+    cm = update_cost_model(dof[dof > 0], n, d)
+    gbs = cm["bytes"] / t_upd / 1e9
+    tfl = cm["flops"] / t_upd / 1e12
+    top = max(per, key=per.get)
+    return {"workload": f"BASELINE configs[{idx}] worst-case update: {Fu} type-'1' tracks of length {cfg.max_track_len}, N={N} clones, "
+                        f"stacked H {cm['R']} x {n}, float64", "n_good": int(info.n_good), "rows": int(info.rows_stacked),
+            "rank": int(info.rank), "rank_flags": int(info.rank_flags),
+            "ms_update_kernels": 1e3 * t_upd, "ms_through_c_abi": 1e3 * float(np.median(wall)),
+            "updates_per_s": 1.0 / t_upd,
+            "roofline_update": {"bound": "hbm", "algorithmic_bytes": cm["bytes"], "flops": cm["flops"],
+                                "flops_split": {"gate": cm["f_gate"], "compression_householder": cm["f_qr"], "ekf": cm["f_ekf"]},
+                                "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                "tflops": tfl, "tensor_peak_tflops_bf16": peaks.get("bf16_tflops"),
+                                "frac_of_tensor_peak": tfl / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+                                "top_kernel": top},
+            "kernel_us_per_update": {k: round(v * 1e3, 1) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
+
+
+def stress_leg(args, L, dev, flush, peaks, rank):
+    """BASELINE configs[2]: 1280x720 frames, 600 features, 25-clone window on one GPU (short stream: the window must fill)."""
+    import rvio_b200  # noqa: F401
+    from rvio_b200 import synth, host
+    cfg = synth.baseline_config(2)
+    Ks, Ws = 10, cfg.max_track_len + 6
+    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 4, SEED + 2, args.detector == "precomputed")
+    inloop = args.detector == "inloop"
+    vio = host.Vio(cfg, dev.index)
+    e2e_ms, _, _, _, _ = drive(L, vio, wl, Ks, Ws, dev, inloop, False, flush)
+    vio.close()
+    vio = host.Vio(cfg, dev.index)
+    dev_ms, _, launches, used, infos = drive(L, vio, wl, Ks, Ws, dev, inloop, True, flush)
+    L.rvio_b200_profile(1)
+    n_prof = 0
+    for i in range(used, min(used + 4, len(wl["frames"]))):
+        vio.step(wl["frames"][i], wl["imus"][i], wl["cand2"][i], device_detector=inloop)
+        n_prof += 1
+    L.rvio_b200_profile(0)
+    prof = _profile_report(L)
+    vio.close()
+    per = {k: v[1] / max(n_prof, 1) for k, v in prof.items()}
+    N = cfg.max_track_len - 1; n = 6 * N; d = 24 + n
+    return {"workload": f"BASELINE configs[2]: synthetic {cfg.width}x{cfg.height} stream, {cfg.n_features} features, {N}-clone window",
+            "steps": Ks, "warmup": Ws, "value": Ks / (float(np.sum(dev_ms)) / 1e3), "unit": "frames/s",
+            "ms_per_step": float(np.mean(dev_ms)), "e2e": {"value": Ks / (float(np.sum(e2e_ms)) / 1e3), "unit": "frames/s",
+                                                            "h2d_bytes_per_step": cfg.width * cfg.height + 10 * 64},
+            "gpu_launches": int(launches), "update_frames": [list(t) for t in infos],
+            "kernel_us_per_step": {k: round(v * 1e3, 1) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
 
 
 def roofline_from_profile(prof, cfg, peaks):
@@ -447,7 +650,7 @@ def _watchdog(seconds):
 
 def main():
     args = parse()
-    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "480")))
+    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "900")))
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import rvio_b200  # noqa: F401
@@ -514,12 +717,36 @@ def main():
     e2e = world * K / res["t_e2e"]
     out = {"metric": "vio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": 1e3 * res["t_dev"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": dict(workload, parallelism=f"{world} independent stream(s), one per GPU"),
+           "dtype": "f64", "data": "synthetic", "config": workload,
            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
            "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
            "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
            "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"]}
+    out["parallelism"] = f"{world} independent stream(s), one per GPU (no collective on the data path)"
+    out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
+                                   "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}
+    out["cpu_affinity"] = res["affinity"]
+    out["update_frames"] = {"rows_kept_flags": [list(t) for t in res["infos"][:32]],
+                            "note": "(n_feat, accepted, stacked rows, rows kept by the reference's rank rule, flags) per timed step; the "
+                                    "device runs the reference rule (RVIO_RANK_RULE_REFERENCE), the mode the parity tests cover"}
+    if world == 1 and not args.no_extra_legs:
+        import torch as _t
+        from rvio_b200 import capi as _capi
+        dev = _t.device("cuda", local_rank)
+        fl = _t.empty(384 << 20, dtype=_t.uint8, device=dev)
+        Lb = _capi.lib()
+        try:
+            out["stress"] = stress_leg(args, Lb, dev, fl, peaks, rank)
+        except Exception as e:          # pragma: no cover
+            out["stress"] = {"error": repr(e)[:200]}
+        out["update_worstcase"] = {}
+        for idx in (2, 4):
+            try:
+                out["update_worstcase"][f"configs[{idx}]"] = update_worstcase_leg(Lb, dev, fl, peaks, idx)
+            except Exception as e:      # pragma: no cover
+                out["update_worstcase"][f"configs[{idx}]"] = {"error": repr(e)[:200]}
+        del fl
     if not args.no_cpu_baseline and world == 1:
         steps = 60
         wl2 = {k: (v[:int(T_STATIC * cfg.fps) + 4 + W + steps + 4] if isinstance(v, list) else v) for k, v in wl.items()}

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_np, s_k, s_mode;
-    __shared__ double s_lost, s_tr;
+    __shared__ double s_lost;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* cnt = Q.red + (size_t)n * n + n;
     const double* G = Q.red;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
             if (k == jstop && lost >= 1e-8) mode = (Q.world == 1) ? 3 : 4;      // needs the reference's own sweep
             else if (k == jstop && lost < 1e-10 * fmax(1.0, tr)) mode = 1;      // nothing dropped (lost is rounding noise)
             else mode = 2;                                                      // rebuild [G | z] from the kept rows
-            s_mode = mode; s_lost = lost; s_tr = tr;
+            s_mode = mode; s_lost = lost;
         }
     }
     __syncthreads();
@@ -347,13 +347,19 @@ size_t givens_smem_bytes(int n, bool* smem_window)
 
 int compress_configure(int nmax)
 {
+    // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
+    // given the largest dynamic shared memory it can be launched with
     bool g;
-    const size_t rr = rank_rule_smem_bytes(nmax, &g);
+    size_t rr = rank_rule_smem_bytes(nmax, &g);
+    if (g) rr = 200 * 1024;
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr));
     bool w;
-    const size_t gv = givens_smem_bytes(nmax, &w);
-    if (w) RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
-    else RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
+    size_t gv = givens_smem_bytes(nmax, &w);
+    if (!w) {
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
+        gv = 200 * 1024;
+    }
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
     return RVIO_OK;
 }
 
