@@ -26,6 +26,8 @@ extern "C" {
 #define RVIO_OK               0
 #define RVIO_FIRST_IMAGE      1   /* track(): first image equalised; caller must seed (Tracker.cc:204-234) */
 #define RVIO_NO_FEATURES      2   /* track(): nothing to track, state untouched (Tracker.cc:246-250) */
+#define RVIO_DETECTOR_TRUNCATED 3  /* rvio_vio_step with the device detector: the frame was processed (outputs valid), but the detector
+                                   * kept only part of its corner candidates (capacity); rvio_b200_last_error() has the text */
 #define RVIO_ERR_ARG         -1
 #define RVIO_ERR_CUDA        -2
 #define RVIO_ERR_STATE       -3

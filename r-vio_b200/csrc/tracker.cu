@@ -916,6 +916,10 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
         set_error("rvio_tracker_create", "Camera.Fisheye with Camera.k3 != 0: cv::fisheye::undistortPoints takes exactly 4 coefficients (Tracker.cc:56-61,119)");
         return RVIO_ERR_ARG;
     }
+    if (cfg->n_features > 4096) {               // the RANSAC pair sampler keeps its 'used' set as a 4096-bit mask in shared memory
+        set_error("rvio_tracker_create", "Tracker.nFeatures > 4096 is not supported");
+        return RVIO_ERR_CAPACITY;
+    }
     int rc = require_b200(device);
     if (rc != RVIO_OK) return rc;
     rvio_tracker* t = new (std::nothrow) rvio_tracker();

@@ -66,7 +66,7 @@ struct rvio_vio {
     double* d_x[2]; double* d_P[2]; int xi, pi;
     double* d_pose; double* d_imu; float2* d_cand;      // d_imu: [frame header {n_imu, n_cand} (16 B)][n_imu x 8 doubles]
     // pinned
-    double* h_pose; double* h_imu; float* h_cand; double* h_cnt; double* h_state;
+    double* h_pose; double* h_imu; float* h_cand; double* h_cnt; double* h_state; int* h_detctrl;
     // System.cc statics, per instance
     bool moving, ready;
     double wm[3], am[3];
@@ -244,6 +244,8 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     if ((rc = vhalloc(v, &v->h_imu, 512 * 8 + 2)) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_cand, 2 * ((size_t)v->F + 1))) != RVIO_OK) return rc;
     if ((rc = vhalloc(v, &v->h_cnt, 8)) != RVIO_OK) return rc;
+    if ((rc = vhalloc(v, &v->h_detctrl, 4)) != RVIO_OK) return rc;
+    memset(v->h_detctrl, 0, 4 * sizeof(int));
     if ((rc = vhalloc(v, &v->h_state, xmax + dmax * dmax)) != RVIO_OK) return rc;
     v->xi = v->pi = 0;
     v->moving = v->ready = false;
@@ -393,6 +395,8 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_side_done, 0));
     }
     RVIO_ENQ(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+    if (use_det && rc != RVIO_NO_FEATURES && (rc == RVIO_FIRST_IMAGE || side_refill))     // main stream is ordered after the detector here
+        RVIO_ENQ(cudaMemcpyAsync(v->h_detctrl, tracker_detector(v->trk)->ctrl, sizeof(DetCtrl), cudaMemcpyDeviceToHost, s));
     return tracker_enqueue_scalars(v->trk);                  // tracker counters follow everything else on the main stream
 }
 
@@ -512,6 +516,13 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         inf.rank = (int)v->h_cnt[6]; inf.rank_flags = (int)v->h_cnt[7];
     }
     v->last_info = inf;
+    if (use_det && v->h_detctrl[3]) {
+        // DetCtrl.overflow: more local maxima than the detector keeps, one histogram bin larger than a selection block, or a
+        // grid cell with too many corners -- the frame was processed, but from a truncated corner set
+        v->h_detctrl[3] = 0;
+        set_error("rvio_vio_step", "device detector overflow: the frame was seeded / refilled from a truncated corner set");
+        return RVIO_DETECTOR_TRUNCATED;
+    }
     return RVIO_OK;
 }
 

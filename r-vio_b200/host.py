@@ -307,9 +307,9 @@ class Vio:
         cp = np.ascontiguousarray(cand, np.float32).reshape(-1) if nc else None
         if device_detector:
             nc, cp = -1, None
-        capi.check(self.L.rvio_vio_step(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
-                                        imu.ctypes.data, len(imu), cp.ctypes.data if nc > 0 else None, nc, 1 if cand_filtered else 0,
-                                        self._pose, C.byref(self._valid)), "rvio_vio_step")
+        self.last_rc = capi.check(self.L.rvio_vio_step(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch,
+                                                       imu.ctypes.data, len(imu), cp.ctypes.data if nc > 0 else None, nc,
+                                                       1 if cand_filtered else 0, self._pose, C.byref(self._valid)), "rvio_vio_step")
         return self._pose.copy() if self._valid.value else None
 
     def step_dev(self, img_dev_ptr, pitch, imu, cand_dev_ptr=None, n_cand=0, cand_filtered=False):

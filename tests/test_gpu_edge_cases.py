@@ -216,3 +216,24 @@ def test_update_during_window_warmup():
     for N in (3, 4, 6):
         x, P, types, off, xy = _case(cfg, 12, 20 + N, n_clones=N)
         info, _ = _compare_update(cfg, x, P, types, off, xy, expect_updated=1)
+
+
+def test_fused_path_reports_detector_overflow():
+    """the fused path with the device detector must not drop DetCtrl.overflow.  A 1280x720 white-noise frame has
+    ~100 000 local maxima above the quality threshold (> the 65 536 the detector keeps): the step still returns its
+    outputs, with RVIO_DETECTOR_TRUNCATED (3) and a message; ordinary frames return RVIO_OK."""
+    from rvio_b200 import capi
+    cfg = synth.baseline_config(2)
+    st = synth.Stream(cfg, 16, 5, t_static=0.25)
+    r = np.random.default_rng(3)
+    vio = host.Vio(cfg, 0)
+    consumed, codes = 0, []
+    for i in range(st.n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        noise = r.integers(0, 256, (cfg.height, cfg.width), dtype=np.uint8)
+        p = vio.step(noise if i >= 8 else st.frames[i], imu, device_detector=True)
+        codes.append((i, vio.last_rc, p is not None))
+    vio.close()
+    assert any(rc == 3 and valid for (_, rc, valid) in codes), codes
+    assert b"overflow" in capi.lib().rvio_b200_last_error()
+    assert all(rc in (0, 3) for (_, rc, _) in codes)

@@ -109,3 +109,34 @@ def test_vio_full_information_mode_and_size_of_the_rank_cut():
     print(f"modes agree to {before:.2e} m before frame {first_cut}, differ by up to {after:.2e} m after it")
     assert before < 1e-7
     assert 1e-4 < after < 2e-2
+
+
+def test_run_asl_tool_matches_oracle_loop(tmp_path):
+    """tools/run_asl.py (EuRoC ASL tree in, stamped_pose_ests.dat out: System.cc:369-380) on a small synthetic ASL tree, device
+    detector; the file is diffed against the oracle's MonoVIO loop fed by the same reader (detector = the C restatement)."""
+    import subprocess
+    import sys
+    import os
+    from rvio_b200 import io_formats
+    cfg = synth.baseline_config(0)
+    st = synth.Stream(cfg, 44, 31, t_static=0.5)
+    io_formats.write_asl(str(tmp_path / "asl"), st.frame_t, st.frames, st.imu)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ycfg = tmp_path / "cfg.yaml"
+    ycfg.write_text("%YAML:1.0\nTracker.nFeatures: 150\nTracker.nMaxTrackingLength: 11\n")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_asl.py"), str(tmp_path / "asl"), str(tmp_path / "out"),
+                        "--config", str(ycfg)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    got = io_formats.read_pose_file(str(tmp_path / "out" / "stamped_pose_ests.dat"))
+    cfg2 = synth.Config.from_yaml(str(ycfg))
+    o = orc.VioOracle(cfg2, lambda img, k, s: orc.detect_restated(img, k, s, cfg2))
+    want = []
+    for t, im, imu in io_formats.EurocAslReader(str(tmp_path / "asl"), cfg2.time_offset):
+        p = o.step(im, imu)
+        if p is not None:
+            want.append(np.concatenate([[t], p]))
+    want = np.array(want)
+    assert got.shape == want.shape and len(got) >= 15, (got.shape, want.shape)
+    assert np.array_equal(got[:, 0], want[:, 0])                      # stamps
+    assert np.abs(got[:, 1:4] - want[:, 1:4]).max() < 1e-7            # positions
+    assert np.abs(np.abs(np.sum(got[:, 4:] * want[:, 4:], axis=1)) - 1).max() < 1e-12     # quaternions (sign-free)

@@ -25,20 +25,32 @@ def main():
                     help="device: FeatureDetector::DetectWithSubPix on the GPU inside the step; host: cv2 on the equalised frame")
     args = ap.parse_args()
     cfg = synth.Config.from_yaml(args.config) if args.config else synth.Config()
-    import cv2
-    from oracle import oracle as orc            # detector = real OpenCV (FeatureDetector.cc:55-75 stays on the host)
+    host_detect = None
+    if args.detector == "host":                 # the caller's own detector: real OpenCV, as FeatureDetector.cc:55-75 calls it
+        import math
+        import cv2
+        clahe = cv2.createCLAHE(3.0, (5, 5))
+        q, md = float(np.float32(cfg.qual_lvl)), float(np.float32(cfg.min_dist))
+        hw = int(math.floor(.5 * md))
+
+        def host_detect(eq, s):
+            c = cv2.goodFeaturesToTrack(eq, cfg.n_features, q, s * md)
+            if c is None or len(c) == 0:
+                return np.zeros((0, 2), np.float32)
+            c = np.ascontiguousarray(c.reshape(-1, 1, 2), np.float32)
+            cv2.cornerSubPix(eq, c, (hw, hw), (-1, -1), (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 1e-2))
+            return c.reshape(-1, 2)
 
     vio = host.Vio(cfg, args.device)
     out = io_formats.PoseWriter(args.out_dir)
-    clahe = cv2.createCLAHE(3.0, (5, 5))
     k = 0
     started = False
     for t, im, imu in io_formats.EurocAslReader(args.asl_dir, cfg.time_offset):
         t0 = time.perf_counter()
         cand = None
-        if args.detector == "host":
+        if host_detect is not None:
             eq = clahe.apply(im) if cfg.enable_equalizer else im     # the image the reference's detector sees (Tracker.cc:198-207)
-            cand = orc.detect_with_subpix(eq, cfg.n_features, 2 if started else 1, cfg)
+            cand = host_detect(eq, 2 if started else 1)
         t1 = time.perf_counter()
         pose = vio.step(im, imu, cand, device_detector=args.detector == "device")
         t2 = time.perf_counter()
