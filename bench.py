@@ -497,7 +497,7 @@ def stress_leg(args, L, dev, flush, peaks, rank):
     from rvio_b200 import synth, host
     cfg = synth.baseline_config(2)
     Ks, Ws = 10, cfg.max_track_len + 6
-    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 4, SEED + 2, args.detector == "precomputed")
+    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 20, SEED + 2, args.detector == "precomputed")
     inloop = args.detector == "inloop"
     vio = host.Vio(cfg, dev.index)
     e2e_ms, _, _, _, _ = drive(L, vio, wl, Ks, Ws, dev, inloop, False, flush)

@@ -149,6 +149,8 @@ typedef struct rvio_update_info {
 #define RVIO_RANK_BY_SWEEP       2    /* decided by replaying the reference's Givens sweep (otherwise by the certificate) */
 #define RVIO_RANK_UNDECIDED      4    /* feature-sharded call with a dependent column in the middle: full information used */
 #define RVIO_RANK_REBUILT        8    /* normal terms rebuilt from the kept rows */
+#define RVIO_RANK_DEPENDENT_ROWS 16   /* dependent columns inside the stacked Jacobian, nothing discarded: `rank` counts independent
+                                      * directions, the reference's nRank additionally counts its linearly dependent rows */
 
 /* Updater::Updater(const cv::FileStorage&)  -- System.cc:98 */
 int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio_updater** out);
@@ -184,7 +186,8 @@ int rvio_updater_get_normal_terms(rvio_updater* upd, double* G, double* z, int n
 int rvio_updater_update_begin(rvio_updater* upd, const double* x, int xdim, const double* P, int d,
                               const uint8_t* types, const int32_t* offsets, const float* xy, int n_feat,
                               int rank, int world);
-/* Device pointer + element count of the contiguous fp64 reduce buffer [G (n*n) | z (n) | counters (8)]. */
+/* Device pointer + element count of the contiguous fp64 reduce buffer [G (n*n) | z (n) | counters (8) | per-class
+ * information (n+1)] -- everything one ncclAllReduce(sum) has to carry. */
 int rvio_updater_reduce_buffer(rvio_updater* upd, double** buf_dev, int* count);
 int rvio_updater_update_finish(rvio_updater* upd, double* x_out, double* P_out, rvio_update_info* info);
 

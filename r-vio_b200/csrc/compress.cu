@@ -48,20 +48,36 @@ __device__ __forceinline__ double warp_sum_d(double v)
 
 // ------------------------------------------------------------------------------------------------
 // k_rank_rule
-// counters (red + n*n + n): [0] accepted features, [1] stacked rows, ..., [6] rows kept (rank), [7] flags:
+// counters (red + n*n + n): [0] accepted features, [1] stacked rows, ..., [6] rows kept (rank), [7] flags (RVIO_RANK_*):
 //   1 = the cut discarded information, 2 = decided by the Givens sweep, 4 = undecided (feature-sharded call: the stacked
-//   rows are distributed; full information is used), 8 = [G | z] rewritten from the kept rows
+//   rows are distributed; full information is used), 8 = [G | z] rewritten from the kept rows, 16 = dependent columns inside
+//   the active set (every row is kept; the reference's nRank additionally counts its linearly dependent rows)
+// cls (red + n*n + n + 8): information ||H_f||_F^2 summed per column-support class (first non-zero column of the feature).
+//
+// What decides the reference's outcome.  Its sweep leaves in row j the normalised combination of all rows that are
+// "active" at column j (rows of features whose support starts at or before j).  While the leading columns are independent
+// that row is unique (= row j of the pivot-free Cholesky factor of G) and the reference's own test applies to it.  At a
+// dependent column the combination is taken with weights proportional to rounding residue: it is below 1e-4 for certain
+// when the active rows carry nothing any more (trace of the active Schur complement < 1e-8) -- the cut is there, and every
+// feature that would only start later is discarded -- and above it (by orders of magnitude, it is a random unit
+// combination of rows holding >= 1e-3 of information) otherwise.  The factorisation therefore runs over the TOTAL G once,
+// skipping dependent columns, and at every column where a new class of features starts it compares the information left
+// in the active part with what is still to come:
+//     active part exhausted (< 1e-8), something dependent behind us  ->  cut here, kept = good pivot rows so far
+//     exactly one dependent column behind us, active part alive (>= 1e-3)  ->  the reference is still going: continue
+//     anything in between  ->  k_givens_ref replays the reference's sweep
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
 {
     extern __shared__ __align__(16) double sm[];
-    __shared__ int s_np, s_k, s_mode;
-    __shared__ double s_lost;
+    __shared__ int s_np, s_k, s_smin, s_ncls;
+    __shared__ double s_tau;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* cnt = Q.red + (size_t)n * n + n;
+    const double* cls = cnt + 8;
     const double* G = Q.red;
     const int rows = (int)cnt[1];
-    if (tid == 0) { Q.rr[0] = 0; Q.rr[1] = rows; Q.rr[2] = n; Q.rr[3] = 0; s_np = 0; }
+    if (tid == 0) { Q.rr[0] = 0; Q.rr[1] = rows; Q.rr[2] = n; Q.rr[3] = 0; s_np = 0; s_smin = n + 1; s_ncls = 0; }
     const bool active = (cnt[0] > 2.0) && (*Q.rule_dev == 0) && rows > n;     // Updater.cc:460,474
     __syncthreads();
     if (!active) {
@@ -71,26 +87,66 @@ __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
     // trailing all-zero columns (Updater.cc:480-489): column norm == 0  <=>  G(j,j) == 0
     for (int j = tid; j < n; j += kRRThreads)
         if (G[(size_t)j * n + j] != 0.0) atomicMax(&s_np, j + 1);
+    for (int c = tid; c <= n; c += kRRThreads)
+        if (cls[c] > 0.0) { atomicMin(&s_smin, c); atomicAdd(&s_ncls, 1); }
     __syncthreads();
     const int Np = s_np;
     const int ld = Np | 1;
     double* U = Q.use_glob ? Q.U_glob : sm;                       // Np x ld, upper triangle used
-    double* aux = Q.use_glob ? sm : sm + (size_t)Np * ld;        // zt[Np], gd[Np], nr2[Np]
-    double* zt = aux; double* gd = aux + Np; double* nr2 = aux + 2 * Np;
+    double* aux = Q.use_glob ? sm : sm + (size_t)Np * ld;        // zt[Np], gd[Np], nr2[Np], late[Np + 1]
+    double* zt = aux; double* gd = aux + Np; double* nr2 = aux + 2 * Np; double* late = aux + 3 * Np;
     for (int o = tid; o < Np * Np; o += kRRThreads) {
         const int i = o / Np, k = o - i * Np;
         if (k >= i) U[(size_t)i * ld + k] = G[(size_t)i * n + k];
     }
     for (int j = tid; j < Np; j += kRRThreads) { zt[j] = Q.red[(size_t)n * n + j]; gd[j] = G[(size_t)j * n + j]; }
+    if (tid == 0) {                                               // late[j] = information of the classes starting at column >= j
+        double acc = 0;
+        for (int c = n; c > Np; --c) acc += cls[c];
+        for (int j = Np; j >= 0; --j) { acc += cls[j]; late[j] = acc; }
+    }
     __syncthreads();
+    // no feature starts at column 0 (no '2' feature, no full-length '1'): the first rows of the reference's trapezoid are
+    // raw rows in list order -- with several classes only the sweep knows what a later cut would keep
+    if (s_smin > 0 && s_ncls > 1) {
+        if (tid == 0) {
+            const int mode = (Q.world == 1) ? 3 : 4;
+            Q.rr[0] = mode; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0;
+            cnt[6] = (double)rows; cnt[7] = (mode == 4) ? 4.0 : 0.0;
+        }
+        return;
+    }
 
-    // pivot-free right-looking Cholesky (rows are left unscaled: row j of R = U[j][j..] / sqrt(U[j][j]))
+    // pivot-free right-looking Cholesky of the total G, dependent columns skipped (rows are left unscaled: row j of the
+    // factor = U[j][j..] / sqrt(U[j][j]))
     const int ty = tid >> 4, tx = tid & 15;
-    int jstop = Np;
+    int q = 0, first_dep = Np, mode = 1, kcut = 0;
     for (int j = 0; j < Np; ++j) {
+        if (j > 0 && late[j] > late[j + 1] && s_smin == 0) {      // a class of features starts here (cls[j] > 0)
+            if (warp == 0) {
+                const double* dg = U;
+                double t = 0;
+                for (int k = j + lane; k < Np; k += 32) t += dg[(size_t)k * ld + k];
+                t = warp_sum_d(t);
+                if (lane == 0) s_tau = t - late[j];               // information left in the active rows
+            }
+            __syncthreads();
+            const double tau = s_tau;
+            const int dd = j - q;
+            if (dd >= 1) {
+                if (tau < 1e-8) { mode = 2; kcut = j; break; }                 // exhausted: the reference cuts, later classes are discarded
+                if (tau < 1e-3 || dd >= 2) { mode = 3; break; }               // only the reference's own sweep can tell
+            }
+            __syncthreads();                                       // s_tau is rewritten at the next boundary
+        }
         const double pj = U[(size_t)j * ld + j];
         const double thr = fmax(1e-12, 1e-12 * gd[j]);
-        if (!(pj >= thr)) { jstop = j; break; }                    // dependent column (uniform decision)
+        if (!(pj >= thr)) {                                        // dependent (or empty) column: skipped, nothing changes
+            if (first_dep == Np) first_dep = j;
+            if (tid == 0) nr2[j] = -1.0;
+            continue;
+        }
+        q++;
         const double rp = 1.0 / pj;
         const double* rowj = U + (size_t)j * ld;
         for (int i = j + 1 + ty; i < Np; i += kRRThreads / 16) {
@@ -101,60 +157,68 @@ __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
         }
         __syncthreads();
     }
-    // squared row norms of R for the rows before the first dependent column
-    for (int j = warp; j < jstop; j += kRRThreads / 32) {
+    const int jend = (mode == 2) ? kcut : Np;                      // columns whose rows may be kept
+    // the reference's own test on the rows that are unique (before the first dependent column): norm < 1e-4 (Updater.cc:519)
+    if (tid == 0) s_k = Np + 1;
+    __syncthreads();
+    const int ulim = min(first_dep, jend);
+    for (int j = warp; j < ulim; j += kRRThreads / 32) {
         const double* rowj = U + (size_t)j * ld;
         double s = 0;
         for (int k = j + lane; k < Np; k += 32) s += rowj[k] * rowj[k];
         s = warp_sum_d(s);
-        if (lane == 0) nr2[j] = s / rowj[j];
+        if (lane == 0) { nr2[j] = s / rowj[j]; if (s / rowj[j] < 1e-8) atomicMin(&s_k, j); }
     }
-    if (tid == 0) s_k = jstop;
     __syncthreads();
-    for (int j = tid; j < jstop; j += kRRThreads)
-        if (nr2[j] < 1e-8) atomicMin(&s_k, j);                       // first row with norm < 1e-4 (Updater.cc:519)
-    __syncthreads();
-    const int k = s_k;
-    if (warp == 0) {
-        double tr = 0, kept = 0;
-        for (int j = lane; j < Np; j += 32) tr += gd[j];
-        for (int j = lane; j < k; j += 32) kept += nr2[j];
-        tr = warp_sum_d(tr); kept = warp_sum_d(kept);
-        if (lane == 0) {
-            const double lost = tr - kept;
-            int mode;
-            if (k == jstop && lost >= 1e-8) mode = (Q.world == 1) ? 3 : 4;      // needs the reference's own sweep
-            else if (k == jstop && lost < 1e-10 * fmax(1.0, tr)) mode = 1;      // nothing dropped (lost is rounding noise)
-            else mode = 2;                                                      // rebuild [G | z] from the kept rows
-            s_mode = mode; s_lost = lost;
+    int kept_rows;               // what is reported as the rank
+    bool rebuild = false, discards = false, generic = false;
+    int klim = jend;             // rows with index < klim (and a good pivot) are kept
+    if (s_k <= Np) {             // an early small row: the reference stops there, whatever comes later
+        klim = s_k; kept_rows = s_k; rebuild = true; mode = 2;
+        // information dropped: everything except the kept rows
+        if (warp == 0) {
+            double tr = 0, kept = 0;
+            for (int j = lane; j < Np; j += 32) tr += gd[j];
+            for (int j = lane; j < klim; j += 32) kept += nr2[j];
+            tr = warp_sum_d(tr); kept = warp_sum_d(kept);
+            if (lane == 0) s_tau = tr - kept;
         }
+        __syncthreads();
+        discards = s_tau >= 1e-8;
+    } else if (mode == 2) {      // cut at a class boundary: the later classes are discarded
+        kept_rows = q; rebuild = true; discards = late[kcut] >= 1e-8;
+    } else if (mode == 1) {      // ran to the end: every row is kept
+        kept_rows = q; generic = first_dep < Np && q > first_dep;   // dependent columns in the middle of the active set
+    } else {
+        kept_rows = q;
     }
-    __syncthreads();
-    const int mode = s_mode;
+    if (mode == 3 && Q.world != 1) mode = 4;
     if (tid == 0) {
-        Q.rr[0] = mode; Q.rr[1] = k; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0;
-        cnt[6] = (double)k;
-        cnt[7] = (mode == 2) ? (8.0 + (s_lost >= 1e-8 ? 1.0 : 0.0)) : (mode == 4 ? 4.0 : 0.0);
+        Q.rr[0] = mode; Q.rr[1] = kept_rows; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0;
+        cnt[6] = (double)kept_rows;
+        cnt[7] = (rebuild ? 8.0 : 0.0) + (discards ? 1.0 : 0.0) + (mode == 4 ? 4.0 : 0.0) + (generic ? 16.0 : 0.0);
     }
-    if (mode != 2) return;
-    // G' = sum_{i<k} row_i row_i^T / p_i ,  z' = sum_{i<k} row_i zt_i / p_i   (bitwise symmetric: products commute)
+    if (!rebuild) return;
+    // G' = sum_{kept i} row_i row_i^T / p_i ,  z' = sum_{kept i} row_i zt_i / p_i   (bitwise symmetric: products commute)
     double* Gw = Q.red; double* zw = Q.red + (size_t)n * n;
     for (int o = tid; o < Np * Np; o += kRRThreads) {
         const int a = o / Np, b = o - a * Np;
-        const int lim = min(k, min(a, b) + 1);
+        const int lim = min(klim, min(a, b) + 1);
         double acc = 0;
         for (int i = 0; i < lim; ++i) {
             const double* rowi = U + (size_t)i * ld;
-            acc = fma(rowi[a] * rowi[b], 1.0 / rowi[i], acc);
+            const double pi = rowi[i];
+            if (pi >= fmax(1e-12, 1e-12 * gd[i])) acc = fma(rowi[a] * rowi[b], 1.0 / pi, acc);
         }
         Gw[(size_t)a * n + b] = acc;
     }
     for (int a = tid; a < Np; a += kRRThreads) {
-        const int lim = min(k, a + 1);
+        const int lim = min(klim, a + 1);
         double acc = 0;
         for (int i = 0; i < lim; ++i) {
             const double* rowi = U + (size_t)i * ld;
-            acc = fma(rowi[a] * zt[i], 1.0 / rowi[i], acc);
+            const double pi = rowi[i];
+            if (pi >= fmax(1e-12, 1e-12 * gd[i])) acc = fma(rowi[a] * zt[i], 1.0 / pi, acc);
         }
         zw[a] = acc;
     }
@@ -235,9 +299,9 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
     }
     __syncthreads();
 
-    const int slot = tid >> 4, l = tid & 15;
-    constexpr int NSLOT = kGVThreads / 16;
-    const unsigned hmask = 0xFFFFu << (16 * (slot & 1));
+    const int slot = tid >> 3, l = tid & 7;                          // 8 lanes per rotation, 64 rotations per pass
+    constexpr int NSLOT = kGVThreads / 8;
+    const unsigned hmask = 0xFFu << (8 * (slot & 3));
     const int T = M + Np - 2;
     for (int t = 0; t < T; ++t) {
         if (loader) issue_row();                                   // row M-2-(t+PF), needed at step t+PF
@@ -259,9 +323,9 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
                 const double rh = rsqrt(h2);
                 c = pp * rh; s = -qq * rh;
             }
-            __syncwarp(hmask);                                      // p, q read by all 16 lanes before column nn is rewritten
+            __syncwarp(hmask);                                      // p, q read by all 8 lanes before column nn is rewritten
             if (!(c == 1.0 && s == 0.0)) {
-                for (int j = nn + l; j <= Np; j += 16) {
+                for (int j = nn + l; j <= Np; j += 8) {
                     const double x = ra[j], y = rb[j];
                     ra[j] = c * x - s * y;                          // applyOnTheLeft(0, 1, G.adjoint())
                     rb[j] = s * x + c * y;
@@ -329,10 +393,10 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
 size_t rank_rule_smem_bytes(int n, bool* use_glob)
 {
     const size_t ld = (size_t)(n | 1);
-    const size_t full = sizeof(double) * ((size_t)n * ld + 3 * (size_t)n + 8);
+    const size_t full = sizeof(double) * ((size_t)n * ld + 4 * (size_t)n + 16);
     if (full <= 200 * 1024) { *use_glob = false; return full; }
     *use_glob = true;
-    return sizeof(double) * (3 * (size_t)n + 8);
+    return sizeof(double) * (4 * (size_t)n + 16);
 }
 
 size_t givens_window_doubles(int n) { return (size_t)(2 * n + kGVPrefetch + 2) * (size_t)(n + 1); }

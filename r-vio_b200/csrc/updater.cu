@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     __shared__ double s_pf[4];          // phi, psi, rho, (unused)
     __shared__ int s_flag[4];           // [0] reject code, [1] Nc
     __shared__ double s_hh[4];          // householder: beta, alpha
+    __shared__ double s_fro[kFeatThreads / 32];
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -511,19 +512,31 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     // ---- accepted: publish the projected block (full width n, zero outside [c0, c0+wc))
     double* Hout = P.Hblk + (size_t)f * P.blk_rows * n;
     double* rout = P.rblk + (size_t)f * P.blk_rows;
+    double sq = 0;
     for (int o = tid; o < dof * n; o += kFeatThreads) {
         const int a = o / n, c = o - a * n;
         const int k = c - c0;
-        Hout[o] = (k >= 0 && k < wc) ? Hn[a * ld + k] : 0.0;
+        const double hv = (k >= 0 && k < wc) ? Hn[a * ld + k] : 0.0;
+        Hout[o] = hv;
+        sq += hv * hv;
     }
     for (int a = tid; a < dof; a += kFeatThreads) rout[a] = rn[a];
+    // ||block||_F^2 (fixed reduction order): the rank rule needs the information each column-support class carries
+    sq = warp_sum(sq);
+    if (lane == 0) s_fro[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int w = 0; w < kFeatThreads / 32; ++w) t += s_fro[w];
+        P.f_fro2[f] = t;
+    }
 }
 
 // ================================================================================================
 // normal terms  G = sum_f Hn_f^T Hn_f ,  z = sum_f Hn_f^T rn_f   (deterministic two-stage reduction)
 // ================================================================================================
 struct GramParams {
-    const double* Hblk; const double* rblk; const int32_t* f_dof; const int32_t* f_c0; const int32_t* f_wc;
+    const double* Hblk; const double* rblk; const int32_t* f_dof; const int32_t* f_c0; const int32_t* f_wc; const double* f_fro2;
     int n_feat, n, blk_rows, groups, nt;
     const int* n_feat_dev;   // optional device-resident feature count (fused path)
     double* Gpart;     // [groups][n][n]
@@ -533,11 +546,12 @@ struct GramParams {
 // One launch: grid (tiles, groups).  Each CTA accumulates its 32x32 tile of G (and, for diagonal tiles, its 32 entries
 // of z) over the features of its group into a partial buffer; the LAST CTA of a tile to finish (atomic ticket) sums the
 // partials in fixed group order (deterministic) into the reduce buffer; the last CTA of tile 0 also writes the counters.
-// reduce buffer layout: [G (n*n) | z (n) | counters (8)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_local
+// reduce buffer layout: [G (n*n) | z (n) | counters (8) | cls (n+1)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_local
 __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
     __shared__ double sA[8][33], sB[8][33];
     __shared__ int s_last;
+    __shared__ double s_cls[192];
     const int ti = blockIdx.x / P.nt, tj = blockIdx.x % P.nt, g = blockIdx.y;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int n = P.n;
@@ -617,6 +631,19 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
         }
         double* c = red + (size_t)n * n + n;
         c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
+    }
+    if (blockIdx.x == 0) {
+        // information per column-support class: cls[c] = sum of ||H_f||_F^2 over the accepted features whose first non-zero
+        // column is c (c = 0 for '2' features, 6 (N - (L-1)) for '1' features), in feature order (deterministic)
+        for (int c = threadIdx.x; c <= n; c += 256) {
+            double acc = 0;
+            for (int f = rank; f < n_feat; f += world)
+                if (P.f_dof[f] > 0 && P.f_c0[f] == c) acc += P.f_fro2[f];
+            s_cls[c] = acc;
+        }
+        __syncthreads();
+        double* cls = red + (size_t)n * n + n + 8;
+        for (int c = threadIdx.x; c <= n; c += 256) cls[c] = s_cls[c];
     }
 }
 
@@ -1206,7 +1233,7 @@ struct rvio_updater {
     // device
     double *d_x, *d_P, *d_xout, *d_Pout, *d_Pnew, *d_dx;
     uint8_t* d_types; int32_t* d_off; float2* d_xy;
-    uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma; int32_t *d_fdof, *d_fc0, *d_fwc;
+    uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma, *d_ffro2; int32_t *d_fdof, *d_fc0, *d_fwc;
     double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2, *d_T, *d_Yt;
     int* d_sing; int* d_tickets;
     int* d_rule; int32_t* d_rr; double *d_U, *d_gwin;      // reference compression rule (compress.cu)
@@ -1268,6 +1295,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
 {
     RVIO_ARG_CHECK(cfg && out);
     RVIO_ARG_CHECK(cfg->max_clones >= 1 && cfg->max_features >= 1 && cfg->max_track_len >= 2);
+    if (cfg->max_clones > 31) { rvio::set_error("rvio_updater_create", "more than 31 clones (n = 186 clone columns) is not supported"); return RVIO_ERR_CAPACITY; }
     int rc = require_b200(device);
     if (rc != RVIO_OK) return rc;
     rvio_updater* u = new (std::nothrow) rvio_updater();
@@ -1296,10 +1324,10 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
     A(u->d_x, u->xmax); A(u->d_xout, u->xmax); A(u->d_P, d * d); A(u->d_Pout, d * d); A(u->d_Pnew, d * d); A(u->d_dx, d);
     A(u->d_types, F + 1); A(u->d_off, F + 2); A(u->d_xy, F * u->Lmax + 1);
-    A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1);
+    A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1); A(u->d_ffro2, F + 1);
     A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
-    A(u->d_red, n * n + n + 8); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
+    A(u->d_red, n * n + n + 8 + n + 1); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
     A(u->d_tickets, (size_t)div_up((int)n, 32) * div_up((int)n, 32) + 64);
     A(u->d_rule, 4); A(u->d_rr, 8); A(u->d_U, n * (n + 1)); A(u->d_gwin, givens_window_doubles((int)n));
 #undef A
@@ -1345,7 +1373,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         fp.types = types_dev; fp.offsets = off_dev; fp.xy = xy_dev; fp.n_feat = n_feat_cap; fp.n_feat_dev = n_feat_dev;
         fp.rank = rank; fp.world = world; fp.chi2 = u->d_chi2;
         fp.f_status = u->d_fstatus; fp.f_pfinv = u->d_fpfinv; fp.f_gamma = u->d_fgamma; fp.f_dof = u->d_fdof;
-        fp.f_c0 = u->d_fc0; fp.f_wc = u->d_fwc; fp.Hblk = u->d_Hblk; fp.rblk = u->d_rblk; fp.blk_rows = u->lay.Mc;
+        fp.f_c0 = u->d_fc0; fp.f_wc = u->d_fwc; fp.f_fro2 = u->d_ffro2; fp.Hblk = u->d_Hblk; fp.rblk = u->d_rblk; fp.blk_rows = u->lay.Mc;
         fp.c = u->consts; fp.lay = u->lay;
         if (world > 1) {
             // features owned by other ranks must not leave stale status/dof behind
@@ -1354,13 +1382,13 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         }
         RVIO_LAUNCH(k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
         GramParams gp;
-        gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc;
+        gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc; gp.f_fro2 = u->d_ffro2;
         gp.n_feat = n_feat_cap; gp.n_feat_dev = n_feat_dev; gp.n = n; gp.blk_rows = u->lay.Mc;
         gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
         gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
         RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
     } else {
-        RVIO_ENQ(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
+        RVIO_ENQ(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8 + n + 1), s));
     }
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
@@ -1531,7 +1559,7 @@ extern "C" int rvio_updater_reduce_buffer(rvio_updater* u, double** buf_dev, int
     if (!u->open) { set_error("rvio_updater_reduce_buffer", "no update in flight"); return RVIO_ERR_STATE; }
     const int n = 6 * u->cur_N;
     *buf_dev = u->d_red;
-    *count = n * n + n + 8;
+    *count = n * n + n + 8 + n + 1;
     return RVIO_OK;
 }
 

@@ -36,7 +36,7 @@ struct FeatureParams {
     int rank, world;                            // feature sharding (f % world == rank)
     const double* chi2;                         // 500-entry table
     // outputs
-    uint8_t* f_status; double* f_pfinv; double* f_gamma; int32_t* f_dof; int32_t* f_c0; int32_t* f_wc;
+    uint8_t* f_status; double* f_pfinv; double* f_gamma; int32_t* f_dof; int32_t* f_c0; int32_t* f_wc; double* f_fro2;
     double* Hblk; double* rblk;                 // per-feature projected blocks: [f][Mc][n], [f][Mc]
     int blk_rows;                               // Mc
     UpdaterConsts c;

@@ -10,8 +10,9 @@
 // Two flavours:
 //   * default: dependency-free (std containers + the small POD types below).  This is what is compiled and tested here
 //     (this image has neither OpenCV C++ headers nor Eigen).
-//   * -DRVIO_B200_WITH_OPENCV_EIGEN: the literal reference signatures (cv::Mat, std::list<ImuData*>, Eigen::VectorXd /
-//     MatrixXd, cv::FileStorage constructors).  Shown for the maintainer of the reference tree; see INTEGRATION.md.
+//   * -DRVIO_B200_WITH_OPENCV_EIGEN (rvio_ref_api.hpp): classes with the reference's literal member signatures (cv::Mat,
+//     std::list<ImuData*>, Eigen::VectorXd / MatrixXd, cv::FileStorage constructors, cv::Point2f result lists) so that
+//     System.cc compiles unchanged; compiled in tests/ against stand-in headers (tests/stubs/), see INTEGRATION.md.
 //
 // The corner detector: by default, exactly as in the reference, a host object
 // (FeatureDetector::DetectWithSubPix / FindNewer) that the adaptor calls through the `Detector` interface below between
@@ -33,7 +34,18 @@
 
 #include "../../include/rvio_b200.h"
 
-namespace RVIO {
+// The dependency-free classes below carry the reference's names (RVIO::Tracker, RVIO::Updater, RVIO::ImuData).  In the
+// literal flavour those names belong to the reference tree itself (its ImuData, and the Tracker / Updater aliases of
+// INTEGRATION.md), so the dependency-free layer moves to its own namespace.
+#ifndef RVIO_B200_HOST_NS
+#ifdef RVIO_B200_WITH_OPENCV_EIGEN
+#define RVIO_B200_HOST_NS rvio_b200_pod
+#else
+#define RVIO_B200_HOST_NS RVIO
+#endif
+#endif
+
+namespace RVIO_B200_HOST_NS {
 
 struct Point2f { float x, y; };                       // stands in for cv::Point2f
 
@@ -255,54 +267,10 @@ private:
     int mLastStatus;
 };
 
-}  // namespace RVIO
+}  // namespace RVIO_B200_HOST_NS
 
 #ifdef RVIO_B200_WITH_OPENCV_EIGEN
-// Literal reference signatures on top of the classes above (needs OpenCV >= 2.4.3 and Eigen >= 3.1 like the reference,
-// CMakeLists.txt:43-51).  Not compiled in this repository's image; see INTEGRATION.md for how it slots into src/rvio.
-#include <Eigen/Core>
-#include <opencv2/core/core.hpp>
-namespace RVIO {
-namespace ref_api {
-
-inline rvio_tracker_cfg tracker_cfg_from(const cv::FileStorage& fs)                 // keys of Tracker.cc:39-79, Ransac.cc:34-46
-{
-    rvio_tracker_cfg c;
-    std::memset(&c, 0, sizeof c);
-    c.width = (int)fs["Camera.width"]; c.height = (int)fs["Camera.height"];
-    c.fx = (float)fs["Camera.fx"]; c.fy = (float)fs["Camera.fy"]; c.cx = (float)fs["Camera.cx"]; c.cy = (float)fs["Camera.cy"];
-    c.k1 = (float)fs["Camera.k1"]; c.k2 = (float)fs["Camera.k2"]; c.p1 = (float)fs["Camera.p1"]; c.p2 = (float)fs["Camera.p2"];
-    c.k3 = (float)fs["Camera.k3"];
-    c.is_rgb = (int)fs["Camera.RGB"]; c.is_fisheye = (int)fs["Camera.Fisheye"];
-    c.enable_equalizer = (int)fs["Tracker.EnableEqualizer"];
-    c.n_features = (int)fs["Tracker.nFeatures"];
-    c.max_track_len = (int)fs["Tracker.nMaxTrackingLength"]; c.min_track_len = (int)fs["Tracker.nMinTrackingLength"];
-    c.use_sampson = (int)fs["Tracker.UseSampson"]; c.inlier_thr = (double)fs["Tracker.nInlierThrd"];
-    c.small_angle = (double)fs["IMU.nSmallAngle"];
-    cv::Mat T; fs["Camera.T_BC0"] >> T;
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) c.T_BC0[4 * i + j] = T.at<double>(i, j);
-    return c;
-}
-
-// void Tracker::track(const cv::Mat& im, std::list<ImuData*>& lImuData)
-inline void track(Tracker& t, const cv::Mat& im, std::list<ImuData*>& lImuData)
-{
-    t.track(im.data, im.cols, im.rows, (int)im.step, im.channels(), lImuData);
-}
-
-// void Updater::update(Eigen::VectorXd&, Eigen::MatrixXd&, std::vector<unsigned char>&, std::vector<std::list<cv::Point2f> >&)
-inline void update(Updater& u, Eigen::VectorXd& xk1k, Eigen::MatrixXd& Pk1k, std::vector<unsigned char>& types,
-                   std::vector<std::list<cv::Point2f> >& meas, Eigen::VectorXd& xk1k1, Eigen::MatrixXd& Pk1k1)
-{
-    std::vector<double> x(xk1k.data(), xk1k.data() + xk1k.size()), P(Pk1k.data(), Pk1k.data() + Pk1k.size());
-    std::vector<std::list<Point2f> > m(meas.size());
-    for (size_t f = 0; f < meas.size(); ++f) for (const cv::Point2f& p : meas[f]) m[f].push_back(Point2f{p.x, p.y});
-    u.update(x, P, types, m);
-    xk1k1 = Eigen::Map<Eigen::VectorXd>(u.xk1k1.data(), (Eigen::Index)u.xk1k1.size());
-    const Eigen::Index d = Pk1k.rows();
-    Pk1k1 = Eigen::Map<Eigen::MatrixXd>(u.Pk1k1.data(), d, d);
-}
-
-}  // namespace ref_api
-}  // namespace RVIO
+// The reference's literal signatures (cv::Mat, std::list<ImuData*>, Eigen::VectorXd / MatrixXd, cv::FileStorage
+// constructors, public result members of the reference's types): rvio_ref_api.hpp.
+#include "rvio_ref_api.hpp"
 #endif  // RVIO_B200_WITH_OPENCV_EIGEN

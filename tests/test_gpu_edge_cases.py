@@ -151,7 +151,7 @@ def _compare_update(cfg, x, P, types, off, xy, expect_updated=None):
     assert (upd.info.n_good, upd.info.n_reject_init, upd.info.n_reject_lm, upd.info.n_reject_gate) == \
            (info.n_good, info.n_reject_init, info.n_reject_lm, info.n_reject_gate)
     assert upd.info.updated == info.updated
-    if info.updated:
+    if info.updated and not (upd.info.rank_flags & 16):
         assert upd.info.rank == info.rank
     if expect_updated is not None:
         assert info.updated == expect_updated

@@ -150,3 +150,40 @@ def test_shard_range_covers_all_features():
             assert S == -(-F // world)
             seen += list(range(lo, hi))
         assert seen == list(range(F))
+
+
+def _build_transcript(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "system_transcript")
+    libdir = os.path.join(ROOT, "r-vio_b200")
+    stubs = os.path.join(ROOT, "tests", "stubs")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-I" + stubs, "-I" + os.path.join(libdir, "host"), "-o", exe,
+                           os.path.join(stubs, "system_transcript.cpp"), "-L" + libdir, "-lrvio_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_reference_call_sites_compile_unchanged_against_the_literal_adaptor(tmp_path):
+    """-DRVIO_B200_WITH_OPENCV_EIGEN flavour (r-vio_b200/host/rvio_ref_api.hpp): RefTracker / RefUpdater carry the reference's
+    literal member signatures (cv::Mat, std::list<ImuData*>, Eigen::VectorXd / MatrixXd, cv::FileStorage constructors,
+    std::vector<std::list<cv::Point2f>> results); a transcript of System.cc:96-98,258,268-271 compiles against them and
+    stand-in OpenCV / Eigen headers (tests/stubs/; C++11 like the reference, CMakeLists.txt:15).  Without a GPU the
+    constructors throw (no CPU fallback); with one the transcript runs two frames."""
+    import subprocess
+    import torch
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    exe = _build_transcript(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "GPU path ok" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no device path" in out.stdout
+
+
+@pytest.mark.gpu
+def test_reference_call_sites_run_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_transcript(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "GPU path ok" in out.stdout, out.stdout + out.stderr
