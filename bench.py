@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the feature-sharded configs[4] leg (N > 1 only)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the configs[2] stress stream and the worst-case update micro-benchmarks")
     ap.add_argument("--detector", default="inloop", choices=["inloop", "precomputed"],
                     help="inloop (default): FeatureDetector::DetectWithSubPix runs inside every timed step, on the GPU in this arm and "
@@ -363,6 +364,15 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         if not errs:
             batch = {"streams_per_gpu": S, "steps_per_stream": Kb, "value": S * Kb / (t1 - t0), "unit": "frames/s",
                      "timing": "wall clock between device synchronisations, all streams concurrent"}
+    # ---- feature-sharded single stream (BASELINE configs[4]: 2048 features, 30-clone window): every rank is fed the same
+    #      frames; LK all-gather + normal-term all-reduce are enqueued by the library on its own stream (in the frame graph)
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded = sharded_leg(args, L, dev, flush, rank, world, local_rank)
+        except Exception as e:          # pragma: no cover
+            sharded = {"error": repr(e)[:300]}
+        barrier()
     # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
     timeline = None
     if rank == 0:
@@ -414,7 +424,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         else:
             batch = None
     return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
-                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch, infos=infos, affinity=affinity,
+                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch, infos=infos, affinity=affinity, sharded=sharded,
                 t_dev_rank=t_dev_rank, t_e2e_rank=t_e2e_rank)
 
 
@@ -489,6 +499,49 @@ def update_worstcase_leg(L, dev, flush, peaks, idx, reps=4):
                                 "frac_of_tensor_peak": tfl / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
                                 "top_kernel": top},
             "kernel_us_per_update": {k: round(v * 1e3, 1) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
+
+
+def sharded_leg(args, L, dev, flush, rank, world, local_rank):
+    """BASELINE configs[4]: ONE stream, 2048 features / 30 clones, feature-sharded over the N GPUs.  Value =
+    frames/s of that stream (max over ranks of the device time); rank 0 afterwards runs the same stream unsharded."""
+    import torch
+    import torch.distributed as dist
+    import rvio_b200  # noqa: F401
+    from rvio_b200 import synth, host
+    cfg = synth.baseline_config(4)
+    Ks, Ws = min(args.steps, 20), cfg.max_track_len + 6
+    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 20, SEED + 4, False)      # same seed on every rank: same frames
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    vio = host.Vio(cfg, local_rank)
+    vio.shard_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    ag_us, ar_us = vio.shard_probe(50)
+    dist.barrier(); torch.cuda.synchronize()
+    ms, _, launches, used, infos = drive(L, vio, wl, Ks, Ws, dev, True, True, flush)
+    glaunch = vio.graph_launches()
+    vio.close()
+    t = torch.tensor([float(np.sum(ms)) / 1e3], dtype=torch.float64, device=dev)
+    every = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(every, t)
+    tmax = max(float(e[0]) for e in every)
+    out = {"workload": f"BASELINE configs[4]: one synthetic {cfg.width}x{cfg.height} stream, {cfg.n_features} features, {cfg.max_track_len - 1}-clone window, "
+                       f"feature-sharded over {world} GPUs (LK all-gather + normal-term all-reduce in stream)",
+           "n_gpus": world, "steps": Ks, "warmup": Ws, "value": Ks / tmax, "unit": "frames/s", "ms_per_step": 1e3 * tmax / Ks,
+           "per_rank_ms_per_step": [round(1e3 * float(e[0]) / Ks, 4) for e in every],
+           "collectives_us_per_frame": {"allgather_lk": round(ag_us, 2), "allreduce_normal_terms": round(ar_us, 2),
+                                        "bytes": {"allgather": 17 * ((cfg.n_features + world - 1) // world) * world,
+                                                  "allreduce": 8 * ((6 * (cfg.max_track_len - 1)) ** 2 + 2 * 6 * (cfg.max_track_len - 1) + 9)}},
+           "graph_replays": glaunch, "gpu_launches": int(launches),
+           "update_frames": [list(x) for x in infos[:8]]}
+    if rank == 0:
+        ref = host.Vio(cfg, local_rank)
+        ms1, _, _, _, _ = drive(L, ref, wl, Ks, Ws, dev, True, True, flush)
+        ref.close()
+        out["unsharded_same_stream"] = {"value": Ks / (float(np.sum(ms1)) / 1e3), "ms_per_step": float(np.mean(ms1))}
+        out["speedup_vs_1gpu"] = (float(np.sum(ms1)) / 1e3) / tmax
+    return out
 
 
 def stress_leg(args, L, dev, flush, peaks, rank):
@@ -722,7 +775,7 @@ def main():
                    "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
            "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
            "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
-           "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"]}
+           "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"], "sharded": res["sharded"]}
     out["parallelism"] = f"{world} independent stream(s), one per GPU (no collective on the data path)"
     out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
                                    "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}

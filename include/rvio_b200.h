@@ -240,6 +240,19 @@ int rvio_vio_timeline(rvio_vio* vio, int enable, float* ms8);
  * 0 off (every frame is enqueued operation by operation), negative: leave unchanged; *graph_launches (optional) receives
  * the number of frames replayed so far. */
 int rvio_vio_graphs(rvio_vio* vio, int enable, uint64_t* graph_launches);
+/* Feature-sharded single stream (BASELINE configs[4]): `world` processes, one GPU each, every one fed the same
+ * frames.  Rank 0 obtains a 128-byte NCCL id (rvio_b200_nccl_unique_id), the host distributes it (MPI, sockets,
+ * torch.distributed ...), every rank calls rvio_vio_shard_init before its first frame.  From then on rvio_vio_step runs
+ * pyramidal LK for the feature indices [rank*S, (rank+1)*S), S = ceil(nFeatures / world), all-gathers the per-feature
+ * results (ncclAllGather, <= 17 B / feature), runs RANSAC + bookkeeping replicated, builds the Jacobian blocks / gate /
+ * normal terms of the features f % world == rank, sums [G | z | counters] with ONE ncclAllReduce and solves replicated --
+ * both collectives on the pipeline's own stream, inside the captured frame graph.  Poses are identical on every rank.
+ * libnccl.so.2 is loaded at run time; nothing else in this library needs it. */
+int rvio_b200_nccl_unique_id(void* id128);
+int rvio_vio_shard_init(rvio_vio* vio, int rank, int world, const void* nccl_unique_id);
+/* Measurement aid: enqueues `iters` x (the frame's all-gather + all-reduce, at this configuration's sizes) on the pipeline's
+ * stream and returns the mean time of each in microseconds (us2[0] all-gather, us2[1] all-reduce); collective on all ranks. */
+int rvio_vio_shard_probe(rvio_vio* vio, int iters, float* us2);
 /* The tracker / updater handles the pipeline owns (for the debug getters above). */
 rvio_tracker* rvio_vio_tracker(rvio_vio* vio);
 rvio_updater* rvio_vio_updater(rvio_vio* vio);

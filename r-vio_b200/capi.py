@@ -53,7 +53,7 @@ SYMBOLS = [
     "rvio_updater_get_debug", "rvio_updater_get_normal_terms", "rvio_updater_update_begin",
     "rvio_updater_reduce_buffer", "rvio_updater_update_finish", "rvio_updater_set_rank_rule",
     "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_get_state",
-    "rvio_vio_get_update_info", "rvio_vio_tracker", "rvio_vio_updater", "rvio_vio_timeline", "rvio_vio_graphs",
+    "rvio_vio_get_update_info", "rvio_vio_shard_init", "rvio_vio_shard_probe", "rvio_b200_nccl_unique_id", "rvio_vio_tracker", "rvio_vio_updater", "rvio_vio_timeline", "rvio_vio_graphs",
     "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
     "rvio_tracker_stream", "rvio_updater_stream", "rvio_b200_profile", "rvio_b200_profile_report",
 ]
@@ -113,6 +113,9 @@ def lib():
     L.rvio_vio_step_dev.argtypes = [vp, vp, ci, vp, ci, vp, ci, ci, f64, pi]
     L.rvio_vio_get_state.argtypes = [vp, vp, pi, vp, pi]
     L.rvio_vio_get_update_info.argtypes = [vp, C.POINTER(UpdateInfo)]
+    L.rvio_vio_shard_init.argtypes = [vp, ci, ci, vp]
+    L.rvio_b200_nccl_unique_id.argtypes = [vp]
+    L.rvio_vio_shard_probe.argtypes = [vp, ci, vp]
     L.rvio_vio_timeline.argtypes = [vp, ci, vp]
     L.rvio_vio_graphs.argtypes = [vp, ci, vp]
     L.rvio_vio_tracker.argtypes = [vp]

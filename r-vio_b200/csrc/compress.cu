@@ -32,7 +32,6 @@ namespace rvio {
 
 namespace {
 
-constexpr int kRRThreads = 512;
 constexpr int kGVThreads = 512;
 constexpr int kGVPrefetch = 6;        // rows in flight ahead of the wavefront
 constexpr int kGVMaxFeat = 1024;      // accepted-feature list kept in shared memory
@@ -47,6 +46,108 @@ __device__ __forceinline__ double warp_sum_d(double v)
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// Register-resident symmetric factorisation engine (one CTA, kSFThreads threads).
+//
+// The lower triangle of a symmetric m x m matrix (m <= 188, optionally one extra row carrying a right-hand side) lives in
+// 4 x 8 register tiles, one tile per thread: the rank-1 update of a right-looking Cholesky step then costs 12 shared-memory
+// reads and 32 DFMAs per thread instead of three shared-memory accesses per DFMA.  Per step: the owners of column j publish
+// it to shared memory (double buffered -> ONE barrier per step), every thread reads the pivot, decides (uniformly) whether
+// the column is dependent (skipped, nothing changes) and otherwise scales the column by 1/sqrt(pivot), writes it out as
+// column j of the lower factor L (= row j of the upper factor R) and updates its tile.
+// Used for the pivot-free Cholesky of G (rank rule; right-hand side z -> y with R^T y = z) and for the Cholesky of the
+// innovation matrix S of the large-window EKF step.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSFThreads = 576;
+constexpr int kSFMaxRows = 188;           // 47 row tiles -> 576 tiles
+
+struct SFTile { int tr, tc, r0, c0; bool valid; };
+
+__device__ __forceinline__ int sf_before(int t) { const int u = t >> 1; return (t & 1) ? (u + 1) * (u + 1) : u * u + u; }   // tiles in row-tiles < t
+
+__device__ __forceinline__ SFTile sf_tile_of(int t, int rows_total)
+{
+    // row-tile tr (rows 4 tr .. 4 tr + 3) has the column tiles tc = 0 .. tr / 2 (columns 8 tc .. 8 tc + 7)
+    SFTile T;
+    int tr = 0;
+    while (t >= sf_before(tr + 1)) ++tr;
+    T.tr = tr; T.tc = t - sf_before(tr); T.r0 = 4 * tr; T.c0 = 8 * T.tc;
+    T.valid = T.r0 < rows_total;
+    return T;
+}
+
+// Factorises in place.  a: this thread's tile.  m: matrix order, aug: 1 when row m carries the right-hand side.
+// col: shared double[2][kSFMaxRows + 4].  L: global, column j of the lower factor at L[j * ldl + i], i = j .. m (+aug).
+// pv: shared double[m] pivots (negative for skipped columns).  SKIP: dependent columns (pivot < max(1e-12, 1e-12 gd[j])) are
+// skipped; otherwise a non-positive pivot sets *bad.  on_column(j) is called by ALL threads before column j is processed
+// (used by the rank rule for its class-boundary test; may return false to stop: then the function returns j);
+// after_pivot(j, dependent) is called by all threads once the pivot of column j is known.
+template <bool SKIP, class OnColumn, class AfterPivot>
+__device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, int m, int aug, double* col, double* L, int ldl,
+                                          double* pv, const double* gd, int* bad, OnColumn on_column, AfterPivot after_pivot)
+{
+    const int rows_total = m + aug;
+    int buf = 0;
+    for (int j = 0; j < m; ++j) {
+        if (!on_column(j)) return j;
+        double* cj = col + buf * (kSFMaxRows + 4);
+        const int tcj = j >> 3, jj = j & 7;
+        if (T.valid && T.tc == tcj && T.r0 + 3 >= j) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int r = T.r0 + x;
+                if (r >= j && r < rows_total) {
+                    double v = 0;
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) if (y == jj) v = a[x][y];
+                    cj[r] = v;
+                }
+            }
+        }
+        __syncthreads();
+        const double p = cj[j];
+        bool dep;
+        if (SKIP) dep = !(p >= fmax(1e-12, 1e-12 * gd[j]));
+        else { dep = false; if (!(p > 0.0) && threadIdx.x == 0) *bad = 1; }
+        if (threadIdx.x == 0) pv[j] = dep ? -1.0 : p;
+        after_pivot(j, dep);                                       // every thread, same value
+        if (!dep) {
+            const double rs = rsqrt(p);
+            for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) L[(size_t)j * ldl + i] = cj[i] * rs;
+            if (T.valid && T.r0 + 3 > j && T.c0 + 7 > j) {
+                double lr[4], lc[8];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { const int r = T.r0 + x; lr[x] = (r > j && r < rows_total) ? cj[r] * rs : 0.0; }
+#pragma unroll
+                for (int y = 0; y < 8; ++y) { const int c = T.c0 + y; lc[y] = (c > j && c < m) ? cj[c] * rs : 0.0; }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) a[x][y] = fma(-lr[x], lc[y], a[x][y]);
+            }
+        }
+        buf ^= 1;
+    }
+    return m;
+}
+
+// loads the lower triangle (+ optional extra row rhs) of a row-major symmetric matrix with leading dimension ld
+__device__ __forceinline__ void sf_load(double (&a)[4][8], const SFTile& T, const double* A, int ld, int m, const double* rhs, int aug)
+{
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int r = T.r0 + x, c = T.c0 + y;
+            double v = 0;
+            if (T.valid && c < m) {
+                if (r < m) { if (c <= r) v = A[(size_t)r * ld + c]; }
+                else if (aug && r == m) v = rhs[c];
+            }
+            a[x][y] = v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_rank_rule
 // counters (red + n*n + n): [0] accepted features, [1] stacked rows, ..., [6] rows kept (rank), [7] flags (RVIO_RANK_*):
 //   1 = the cut discarded information, 2 = decided by the Givens sweep, 4 = undecided (feature-sharded call: the stacked
@@ -59,17 +160,20 @@ __device__ __forceinline__ double warp_sum_d(double v)
 // that row is unique (= row j of the pivot-free Cholesky factor of G) and the reference's own test applies to it.  At a
 // dependent column the combination is taken with weights proportional to rounding residue: it is below 1e-4 for certain
 // when the active rows carry nothing any more (trace of the active Schur complement < 1e-8) -- the cut is there, and every
-// feature that would only start later is discarded -- and above it (by orders of magnitude, it is a random unit
-// combination of rows holding >= 1e-3 of information) otherwise.  The factorisation therefore runs over the TOTAL G once,
-// skipping dependent columns, and at every column where a new class of features starts it compares the information left
-// in the active part with what is still to come:
+// feature that would only start later is discarded -- and above it (by orders of magnitude: a random unit combination of
+// rows holding >= 1e-3 of information) otherwise.  The factorisation therefore runs over the TOTAL G once, skipping
+// dependent columns, and at every column where a new class of features starts it compares the information left in the
+// active part with what is still to come:
 //     active part exhausted (< 1e-8), something dependent behind us  ->  cut here, kept = good pivot rows so far
 //     exactly one dependent column behind us, active part alive (>= 1e-3)  ->  the reference is still going: continue
 //     anything in between  ->  k_givens_ref replays the reference's sweep
+// With Q.emit_R the kept rows (scaled, zero padded to n x n) and y are also written out: the large-window EKF step works on
+// them (R-form: S = R Pcc R^T + s^2 I).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
+__global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 {
-    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_col[2][kSFMaxRows + 4];
+    __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows], s_diag[kSFMaxRows];
     __shared__ int s_np, s_k, s_smin, s_ncls;
     __shared__ double s_tau;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -77,151 +181,198 @@ __global__ void __launch_bounds__(kRRThreads) k_rank_rule(RankRuleParams Q)
     const double* cls = cnt + 8;
     const double* G = Q.red;
     const int rows = (int)cnt[1];
-    if (tid == 0) { Q.rr[0] = 0; Q.rr[1] = rows; Q.rr[2] = n; Q.rr[3] = 0; s_np = 0; s_smin = n + 1; s_ncls = 0; }
-    const bool active = (cnt[0] > 2.0) && (*Q.rule_dev == 0) && rows > n;     // Updater.cc:460,474
-    __syncthreads();
-    if (!active) {
-        if (tid == 0) { cnt[6] = (cnt[0] > 2.0) ? (double)rows : 0.0; cnt[7] = 0.0; }
-        return;
+    const bool updating = cnt[0] > 2.0;                                            // Updater.cc:460
+    const bool rule = updating && (*Q.rule_dev == 0) && rows > n;                  // Updater.cc:474
+    if (tid == 0) {
+        Q.rr[0] = 0; Q.rr[1] = rows; Q.rr[2] = n; Q.rr[3] = 0;
+        s_np = 0; s_smin = n + 1; s_ncls = 0; s_k = n + 1;
+        cnt[6] = updating ? (double)rows : 0.0; cnt[7] = 0.0;
     }
+    if (!updating || (!rule && !Q.emit_R)) return;
+    __syncthreads();
     // trailing all-zero columns (Updater.cc:480-489): column norm == 0  <=>  G(j,j) == 0
-    for (int j = tid; j < n; j += kRRThreads)
-        if (G[(size_t)j * n + j] != 0.0) atomicMax(&s_np, j + 1);
-    for (int c = tid; c <= n; c += kRRThreads)
+    for (int j = tid; j < n; j += kSFThreads) {
+        const double g = G[(size_t)j * n + j];
+        s_gd[j] = g;
+        if (g != 0.0) atomicMax(&s_np, j + 1);
+    }
+    for (int c = tid; c <= n; c += kSFThreads)
         if (cls[c] > 0.0) { atomicMin(&s_smin, c); atomicAdd(&s_ncls, 1); }
     __syncthreads();
     const int Np = s_np;
-    const int ld = Np | 1;
-    double* U = Q.use_glob ? Q.U_glob : sm;                       // Np x ld, upper triangle used
-    double* aux = Q.use_glob ? sm : sm + (size_t)Np * ld;        // zt[Np], gd[Np], nr2[Np], late[Np + 1]
-    double* zt = aux; double* gd = aux + Np; double* nr2 = aux + 2 * Np; double* late = aux + 3 * Np;
-    for (int o = tid; o < Np * Np; o += kRRThreads) {
-        const int i = o / Np, k = o - i * Np;
-        if (k >= i) U[(size_t)i * ld + k] = G[(size_t)i * n + k];
-    }
-    for (int j = tid; j < Np; j += kRRThreads) { zt[j] = Q.red[(size_t)n * n + j]; gd[j] = G[(size_t)j * n + j]; }
     if (tid == 0) {                                               // late[j] = information of the classes starting at column >= j
         double acc = 0;
         for (int c = n; c > Np; --c) acc += cls[c];
-        for (int j = Np; j >= 0; --j) { acc += cls[j]; late[j] = acc; }
+        for (int j = Np; j >= 0; --j) { acc += cls[j]; s_late[j] = acc; }
+        s_late[Np + 1] = 0.0;
     }
     __syncthreads();
     // no feature starts at column 0 (no '2' feature, no full-length '1'): the first rows of the reference's trapezoid are
     // raw rows in list order -- with several classes only the sweep knows what a later cut would keep
-    if (s_smin > 0 && s_ncls > 1) {
-        if (tid == 0) {
-            const int mode = (Q.world == 1) ? 3 : 4;
-            Q.rr[0] = mode; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0;
-            cnt[6] = (double)rows; cnt[7] = (mode == 4) ? 4.0 : 0.0;
-        }
-        return;
-    }
+    const bool raw_top = rule && s_smin > 0 && s_ncls > 1;
+    const bool boundaries = rule && s_smin == 0 && !raw_top;
 
-    // pivot-free right-looking Cholesky of the total G, dependent columns skipped (rows are left unscaled: row j of the
-    // factor = U[j][j..] / sqrt(U[j][j]))
-    const int ty = tid >> 4, tx = tid & 15;
-    int q = 0, first_dep = Np, mode = 1, kcut = 0;
-    for (int j = 0; j < Np; ++j) {
-        if (j > 0 && late[j] > late[j + 1] && s_smin == 0) {      // a class of features starts here (cls[j] > 0)
+    const SFTile T = sf_tile_of(tid, Np + 1);
+    double a[4][8];
+    sf_load(a, T, G, n, Np, Q.red + (size_t)n * n, 1);
+    const int ldl = n + 1;
+    double* L = Q.L;                                              // columns of the lower factor == rows of R, plus y at index Np
+    int q = 0, first_dep = Np;                                    // (thread-uniform copies)
+    int mode = 1, kcut = 0;
+    bool undecided = false;
+    auto after_pivot = [&](int j, bool dep) { if (!dep) q++; else if (first_dep == Np) first_dep = j; };
+    auto on_column = [&](int j) -> bool {
+        if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {   // a class of features starts here (cls[j] > 0)
+            // information left in the active rows = trace of the current Schur complement minus what has not started yet
+            if (T.valid && T.tr * 4 <= T.c0 + 7 && T.r0 + 3 >= T.c0) {          // tiles crossing the diagonal
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 8; ++y)
+                        if (T.r0 + x == T.c0 + y && T.r0 + x < Np) s_diag[T.r0 + x] = a[x][y];
+            }
+            __syncthreads();
             if (warp == 0) {
-                const double* dg = U;
                 double t = 0;
-                for (int k = j + lane; k < Np; k += 32) t += dg[(size_t)k * ld + k];
+                for (int k = j + lane; k < Np; k += 32) t += s_diag[k];
                 t = warp_sum_d(t);
-                if (lane == 0) s_tau = t - late[j];               // information left in the active rows
+                if (lane == 0) s_tau = t - s_late[j];
             }
             __syncthreads();
             const double tau = s_tau;
             const int dd = j - q;
             if (dd >= 1) {
-                if (tau < 1e-8) { mode = 2; kcut = j; break; }                 // exhausted: the reference cuts, later classes are discarded
-                if (tau < 1e-3 || dd >= 2) { mode = 3; break; }               // only the reference's own sweep can tell
+                if (tau < 1e-8) { mode = 2; kcut = j; return false; }                // exhausted: the reference cuts, later classes are discarded
+                if (tau < 1e-3 || dd >= 2) {                                        // only the reference's own sweep can tell
+                    if (Q.world == 1) { mode = 3; return false; }
+                    undecided = true;                                               // feature-sharded: keep everything, say so
+                }
             }
-            __syncthreads();                                       // s_tau is rewritten at the next boundary
         }
-        const double pj = U[(size_t)j * ld + j];
-        const double thr = fmax(1e-12, 1e-12 * gd[j]);
-        if (!(pj >= thr)) {                                        // dependent (or empty) column: skipped, nothing changes
-            if (first_dep == Np) first_dep = j;
-            if (tid == 0) nr2[j] = -1.0;
-            continue;
-        }
-        q++;
-        const double rp = 1.0 / pj;
-        const double* rowj = U + (size_t)j * ld;
-        for (int i = j + 1 + ty; i < Np; i += kRRThreads / 16) {
-            const double f = rowj[i] * rp;
-            double* rowi = U + (size_t)i * ld;
-            for (int k = i + tx; k < Np; k += 16) rowi[k] -= f * rowj[k];
-            if (tx == 0) zt[i] -= f * zt[j];
-        }
-        __syncthreads();
-    }
-    const int jend = (mode == 2) ? kcut : Np;                      // columns whose rows may be kept
+        return true;
+    };
+    const int jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], L, ldl, s_pv, s_gd, nullptr, on_column, after_pivot);
+    __syncthreads();
+    if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
+    const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
     // the reference's own test on the rows that are unique (before the first dependent column): norm < 1e-4 (Updater.cc:519)
-    if (tid == 0) s_k = Np + 1;
-    __syncthreads();
-    const int ulim = min(first_dep, jend);
-    for (int j = warp; j < ulim; j += kRRThreads / 32) {
-        const double* rowj = U + (size_t)j * ld;
-        double s = 0;
-        for (int k = j + lane; k < Np; k += 32) s += rowj[k] * rowj[k];
-        s = warp_sum_d(s);
-        if (lane == 0) { nr2[j] = s / rowj[j]; if (s / rowj[j] < 1e-8) atomicMin(&s_k, j); }
+    const int ulim = rule ? min(first_dep, jend) : 0;
+    for (int j = warp; j < jend; j += kSFThreads / 32) {
+        if (s_pv[j] < 0.0) { if (lane == 0) s_nr2[j] = 0.0; continue; }
+        const double* cj = L + (size_t)j * ldl;
+        double sq = 0;
+        for (int i = j + lane; i < Np; i += 32) sq += cj[i] * cj[i];
+        sq = warp_sum_d(sq);
+        if (lane == 0) { s_nr2[j] = sq; if (j < ulim && sq < 1e-8) atomicMin(&s_k, j); }
     }
     __syncthreads();
-    int kept_rows;               // what is reported as the rank
+    int kept_rows = q;
     bool rebuild = false, discards = false, generic = false;
-    int klim = jend;             // rows with index < klim (and a good pivot) are kept
-    if (s_k <= Np) {             // an early small row: the reference stops there, whatever comes later
+    int klim = jend;             // columns with index < klim (and a good pivot) are kept
+    if (rule && s_k <= n) {      // an early small row: the reference stops there, whatever comes later
         klim = s_k; kept_rows = s_k; rebuild = true; mode = 2;
-        // information dropped: everything except the kept rows
-        if (warp == 0) {
+        if (warp == 0) {         // information dropped: everything except the kept rows
             double tr = 0, kept = 0;
-            for (int j = lane; j < Np; j += 32) tr += gd[j];
-            for (int j = lane; j < klim; j += 32) kept += nr2[j];
+            for (int j = lane; j < Np; j += 32) tr += s_gd[j];
+            for (int j = lane; j < klim; j += 32) kept += s_nr2[j];
             tr = warp_sum_d(tr); kept = warp_sum_d(kept);
             if (lane == 0) s_tau = tr - kept;
         }
         __syncthreads();
         discards = s_tau >= 1e-8;
     } else if (mode == 2) {      // cut at a class boundary: the later classes are discarded
-        kept_rows = q; rebuild = true; discards = late[kcut] >= 1e-8;
+        rebuild = true; discards = s_late[kcut] >= 1e-8;
     } else if (mode == 1) {      // ran to the end: every row is kept
-        kept_rows = q; generic = first_dep < Np && q > first_dep;   // dependent columns in the middle of the active set
-    } else {
-        kept_rows = q;
+        generic = rule && first_dep < Np && q > first_dep;        // dependent columns in the middle of the active set
     }
-    if (mode == 3 && Q.world != 1) mode = 4;
+    if (undecided && mode == 1) { mode = 4; generic = false; }
+    if (!rule) { mode = 0; rebuild = false; }
     if (tid == 0) {
-        Q.rr[0] = mode; Q.rr[1] = kept_rows; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0;
-        cnt[6] = (double)kept_rows;
+        Q.rr[0] = mode; Q.rr[1] = kept_rows; Q.rr[2] = Np; Q.rr[3] = (mode == 3) ? 1 : 0; Q.rr[5] = klim;
+        cnt[6] = rule ? (double)kept_rows : (double)rows;
         cnt[7] = (rebuild ? 8.0 : 0.0) + (discards ? 1.0 : 0.0) + (mode == 4 ? 4.0 : 0.0) + (generic ? 16.0 : 0.0);
     }
+    if (Q.emit_R && mode != 3) {
+        // kept rows of R (= columns of L with a good pivot below klim), zero padded to n x n, and y
+        const int kl = klim;
+        for (int o = tid; o < n * n; o += kSFThreads) {
+            const int j = o / n, i = o - j * n;
+            double v = 0;
+            if (j < kl && j < Np && s_pv[j] >= 0.0 && i >= j && i < Np) v = L[(size_t)j * ldl + i];
+            Q.Rc[o] = v;
+        }
+        for (int j = tid; j < n; j += kSFThreads) Q.yc[j] = (j < kl && j < Np && s_pv[j] >= 0.0) ? L[(size_t)j * ldl + Np] : 0.0;
+    }
     if (!rebuild) return;
-    // G' = sum_{kept i} row_i row_i^T / p_i ,  z' = sum_{kept i} row_i zt_i / p_i   (bitwise symmetric: products commute)
+    // G' = sum_{kept j} L_j L_j^T ,  z' = sum_{kept j} L_j y_j   (bitwise symmetric: products commute)
     double* Gw = Q.red; double* zw = Q.red + (size_t)n * n;
-    for (int o = tid; o < Np * Np; o += kRRThreads) {
-        const int a = o / Np, b = o - a * Np;
-        const int lim = min(klim, min(a, b) + 1);
+    for (int o = tid; o < Np * Np; o += kSFThreads) {
+        const int r = o / Np, c = o - r * Np;
+        const int lim = min(klim, min(r, c) + 1);
         double acc = 0;
-        for (int i = 0; i < lim; ++i) {
-            const double* rowi = U + (size_t)i * ld;
-            const double pi = rowi[i];
-            if (pi >= fmax(1e-12, 1e-12 * gd[i])) acc = fma(rowi[a] * rowi[b], 1.0 / pi, acc);
-        }
-        Gw[(size_t)a * n + b] = acc;
+        for (int j = 0; j < lim; ++j)
+            if (s_pv[j] >= 0.0) acc = fma(L[(size_t)j * ldl + r], L[(size_t)j * ldl + c], acc);
+        Gw[(size_t)r * n + c] = acc;
     }
-    for (int a = tid; a < Np; a += kRRThreads) {
-        const int lim = min(klim, a + 1);
+    for (int r = tid; r < Np; r += kSFThreads) {
+        const int lim = min(klim, r + 1);
         double acc = 0;
-        for (int i = 0; i < lim; ++i) {
-            const double* rowi = U + (size_t)i * ld;
-            const double pi = rowi[i];
-            if (pi >= fmax(1e-12, 1e-12 * gd[i])) acc = fma(rowi[a] * zt[i], 1.0 / pi, acc);
-        }
-        zw[a] = acc;
+        for (int j = 0; j < lim; ++j)
+            if (s_pv[j] >= 0.0) acc = fma(L[(size_t)j * ldl + r], L[(size_t)j * ldl + Np], acc);
+        zw[r] = acc;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, register resident), then  Y = L^-1 [W | y]
+// (k_trsm, one CTA per 8 right-hand-side columns, L in shared memory).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSFThreads, 1) k_chol_S(const double* S, int m, double* L, int* bad, const double* gate)
+{
+    __shared__ double s_col[2][kSFMaxRows + 4];
+    __shared__ double s_pv[kSFMaxRows];
+    if (gate && !(gate[0] > 2.0)) return;
+    const SFTile T = sf_tile_of(threadIdx.x, m);
+    double a[4][8];
+    sf_load(a, T, S, m, m, nullptr, 0);
+    sym_factor<false>(a, T, m, 0, &s_col[0][0], L, m, s_pv, nullptr, bad, [](int) { return true; }, [](int, bool) {});
+}
+
+// B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  L: column j at L[j * m + i], i >= j.
+constexpr int kTrsmCols = 8;
+__global__ void __launch_bounds__(192) k_trsm(const double* L, int m, double* B, int ldb, int nb, const double* gate)
+{
+    extern __shared__ __align__(16) double sL[];                 // packed lower triangle, column j at off(j) = j m - j (j-1) / 2
+    __shared__ double s_y[2][kTrsmCols];
+    if (gate && !(gate[0] > 2.0)) return;
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * kTrsmCols;
+    for (int j = 0; j < m; ++j) {
+        const size_t off = (size_t)j * m - (size_t)j * (j - 1) / 2;
+        for (int i = j + tid; i < m; i += 192) sL[off + (i - j)] = L[(size_t)j * m + i];
+    }
+    double b[kTrsmCols];
+#pragma unroll
+    for (int c = 0; c < kTrsmCols; ++c) b[c] = (tid < m && c0 + c < nb) ? B[(size_t)tid * ldb + c0 + c] : 0.0;
+    __syncthreads();
+    int buf = 0;
+    for (int j = 0; j < m; ++j) {
+        const size_t off = (size_t)j * m - (size_t)j * (j - 1) / 2;
+        if (tid == j) {
+            const double inv = 1.0 / sL[off];
+#pragma unroll
+            for (int c = 0; c < kTrsmCols; ++c) { b[c] *= inv; s_y[buf][c] = b[c]; }
+        }
+        __syncthreads();
+        if (tid > j && tid < m) {
+            const double l = sL[off + (tid - j)];
+#pragma unroll
+            for (int c = 0; c < kTrsmCols; ++c) b[c] = fma(-l, s_y[buf][c], b[c]);
+        }
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int c = 0; c < kTrsmCols; ++c) if (tid < m && c0 + c < nb) B[(size_t)tid * ldb + c0 + c] = b[c];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -380,6 +531,13 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
         }
         zw[a] = acc;
     }
+    if (Q.emit_R) {                                                // R-form consumers: the kept rows themselves
+        for (int o = tid; o < n * n; o += kGVThreads) {
+            const int i = o / n, c = o - i * n;
+            Q.Rc[o] = (i < k && c >= i && c < Np) ? W[(size_t)(i % WIN) * LD + c] : 0.0;
+        }
+        for (int i = tid; i < n; i += kGVThreads) Q.yc[i] = (i < k) ? W[(size_t)(i % WIN) * LD + Np] : 0.0;
+    }
     if (tid == 0) {
         Q.rr[1] = k; Q.rr[4] = s_full;
         cnt[6] = (double)k;
@@ -390,15 +548,6 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-size_t rank_rule_smem_bytes(int n, bool* use_glob)
-{
-    const size_t ld = (size_t)(n | 1);
-    const size_t full = sizeof(double) * ((size_t)n * ld + 4 * (size_t)n + 16);
-    if (full <= 200 * 1024) { *use_glob = false; return full; }
-    *use_glob = true;
-    return sizeof(double) * (4 * (size_t)n + 16);
-}
-
 size_t givens_window_doubles(int n) { return (size_t)(2 * n + kGVPrefetch + 2) * (size_t)(n + 1); }
 
 size_t givens_smem_bytes(int n, bool* smem_window)
@@ -413,10 +562,6 @@ int compress_configure(int nmax)
 {
     // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
     // given the largest dynamic shared memory it can be launched with
-    bool g;
-    size_t rr = rank_rule_smem_bytes(nmax, &g);
-    if (g) rr = 200 * 1024;
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr));
     bool w;
     size_t gv = givens_smem_bytes(nmax, &w);
     if (!w) {
@@ -424,23 +569,31 @@ int compress_configure(int nmax)
         gv = 200 * 1024;
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8))));
     return RVIO_OK;
 }
 
-// Enqueues the rank rule on [G | z | counters] (after the all-reduce in the feature-sharded form).
-int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq_in, const GivensRefParams& gq_in, int nmax)
+// Enqueues the rank rule on [G | z | counters | classes] (after the all-reduce in the feature-sharded form).
+int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq_in, int n)
 {
-    RankRuleParams rq = rq_in;
-    bool g;
-    const size_t rr = rank_rule_smem_bytes(nmax, &g);
-    rq.use_glob = g ? 1 : 0;
-    RVIO_LAUNCH(k_rank_rule, 1, kRRThreads, rr, s, rq);
+    if (n + 1 > kSFMaxRows) { set_error("enqueue_rank_rule", "window too large"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_rank_rule, 1, kSFThreads, 0, s, rq);
     if (rq.world == 1) {
         bool w;
-        const size_t gv = givens_smem_bytes(nmax, &w);
+        const size_t gv = givens_smem_bytes(n, &w);
         if (w) RVIO_LAUNCH(k_givens_ref<true>, 1, kGVThreads, gv, s, gq_in);
         else RVIO_LAUNCH(k_givens_ref<false>, 1, kGVThreads, gv, s, gq_in);
     }
+    RVIO_ENQ(cudaGetLastError());
+    return RVIO_OK;
+}
+
+// Serial part of the large-window EKF step: S (n x n) -> L ; B (n x nb, leading dimension ldb) <- L^-1 B.
+int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate)
+{
+    if (n > kSFMaxRows || n > 192) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_chol_S, 1, kSFThreads, 0, s, S, n, L, bad, gate);
+    RVIO_LAUNCH(k_trsm, div_up(nb, kTrsmCols), 192, sizeof(double) * ((size_t)n * (n + 1) / 2 + 8), s, L, n, B, ldb, nb, gate);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

@@ -1381,6 +1381,30 @@ int tracker_enqueue_frame_staged(rvio_tracker* t, const double* imu, int n_imu)
 {
     return tracker_enqueue(t, t->d_gray, (int)t->gray_pitch, imu, n_imu, true);
 }
+// Feature-sharded frame of the fused path: image pipeline + LK for this rank's share of the feature indices (device-side
+// feature count); the caller all-gathers the LK arrays on the same stream and then calls tracker_enqueue_ransac.
+int tracker_enqueue_frame_sharded(rvio_tracker* t, const uint8_t* img_host, int w, int h, int stride, int ch, const uint8_t* img_dev, int pitch,
+                                  bool staged, const double* imu, int n_imu, int rank, int world)
+{
+    if (!staged && !img_dev) {
+        RVIO_ARG_CHECK(img_host && w == t->W && h == t->H && (ch == 1 || ch == 3 || ch == 4) && stride >= w * ch);
+        const int rc = upload_image(t, img_host, w, h, stride, ch);
+        if (rc != RVIO_OK) return rc;
+    }
+    const uint8_t* g = (staged || !img_dev) ? t->d_gray : img_dev;
+    const int gp = (staged || !img_dev) ? (int)t->gray_pitch : pitch;
+    return tracker_enqueue(t, g, gp, imu, n_imu, true, rank, world, false);
+}
+int tracker_enqueue_ransac(rvio_tracker* t)
+{
+    RansacParams rp;
+    rp.B = t->B; rp.n = t->last_n; rp.n_dev = &t->B.sc->n_new; rp.use_sampson = t->cfg.use_sampson;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
+    RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, t->stream, rp);
+    RVIO_ENQ(cudaGetLastError());
+    return RVIO_OK;
+}
+int tracker_shard_size(const rvio_tracker* t, int world) { return div_up(t->F, world); }
 uint8_t* tracker_gray(rvio_tracker* t, size_t* pitch) { *pitch = t->gray_pitch; return t->d_gray; }
 int tracker_enqueue_seed_dev(rvio_tracker* t, const float2* px_dev, int n, const int* n_dev)
 {

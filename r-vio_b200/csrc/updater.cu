@@ -1236,7 +1236,7 @@ struct rvio_updater {
     uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma, *d_ffro2; int32_t *d_fdof, *d_fc0, *d_fwc;
     double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2, *d_T, *d_Yt;
     int* d_sing; int* d_tickets;
-    int* d_rule; int32_t* d_rr; double *d_U, *d_gwin;      // reference compression rule (compress.cu)
+    int* d_rule; int32_t* d_rr; double *d_L, *d_gwin, *d_Rc, *d_yc, *d_S, *d_LS, *d_W;      // reference compression rule + R-form EKF step (compress.cu)
     int rank_rule;
     int groups_cap;
     // pinned
@@ -1329,7 +1329,8 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
     A(u->d_red, n * n + n + 8 + n + 1); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
     A(u->d_tickets, (size_t)div_up((int)n, 32) * div_up((int)n, 32) + 64);
-    A(u->d_rule, 4); A(u->d_rr, 8); A(u->d_U, n * (n + 1)); A(u->d_gwin, givens_window_doubles((int)n));
+    A(u->d_rule, 4); A(u->d_rr, 8); A(u->d_L, n * (n + 1) + 8); A(u->d_gwin, givens_window_doubles((int)n));
+    A(u->d_Rc, n * n); A(u->d_yc, n); A(u->d_S, n * n); A(u->d_LS, n * n); A(u->d_W, n * (d + 1));
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
     HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4); HA(u->h_rule, 4);
@@ -1404,17 +1405,21 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         RVIO_ENQ(cudaMemcpyAsync(P_out_dev, P_dev, sizeof(double) * (size_t)d * d, cudaMemcpyDeviceToDevice, s));
         return RVIO_OK;
     }
+    const bool small = N <= kSolveSmallMaxClones;
     {
-        // which rows the reference's compression keeps (Updater.cc:474-536): may rewrite [G | z] in place
+        // which rows the reference's compression keeps (Updater.cc:474-536): may rewrite [G | z] in place; for the
+        // large-window path it also hands over the kept rows R (G = R^T R) and y (R^T y = z)
         RankRuleParams rq;
-        rq.red = u->d_red; rq.n = n; rq.world = u->cur_world; rq.rule_dev = u->d_rule; rq.U_glob = u->d_U; rq.use_glob = 0; rq.rr = u->d_rr;
+        rq.red = u->d_red; rq.n = n; rq.world = u->cur_world; rq.rule_dev = u->d_rule; rq.L = u->d_L; rq.rr = u->d_rr;
+        rq.emit_R = small ? 0 : 1; rq.Rc = u->d_Rc; rq.yc = u->d_yc;
         GivensRefParams gq;
         gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.f_dof = u->d_fdof; gq.n_feat = u->cur_nfeat; gq.n_feat_dev = u->cur_nfeat_dev;
         gq.n = n; gq.blk_rows = u->lay.Mc; gq.red = u->d_red; gq.rr = u->d_rr; gq.win = u->d_gwin;
+        gq.emit_R = rq.emit_R; gq.Rc = u->d_Rc; gq.yc = u->d_yc;
         const int r2 = enqueue_rank_rule(s, rq, gq, n);
         if (r2 != RVIO_OK) return r2;
     }
-    if (N <= kSolveSmallMaxClones) {
+    if (small) {
         SolveSmallParams sp;
         sp.red = u->d_red; sp.x = x_dev; sp.P = P_dev; sp.xdim = xdim; sp.N = N; sp.d = d; sp.sig2 = u->consts.sig2;
         sp.T = u->d_T; sp.Yt = u->d_Yt; sp.dx = u->d_dx;
@@ -1428,49 +1433,51 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         RVIO_ENQ(cudaGetLastError());
         return RVIO_OK;
     }
-    const double* G = u->d_red;
-    const double* z = u->d_red + (size_t)n * n;
+    // ---- large windows (N > 13, e.g. the EuRoC default of 14 clones, configs[2] / [4]): the EKF step in the reference's own
+    //      form on the kept rows R (n x n, zero padded; Updater.cc:540-619 with Hn = R):
+    //          W = R P[c,:]        S = W[:,c] R^T + s^2 I  (SPD)        S = L L^T        Y = L^-1 [W | y]
+    //          dx = Y^T y~         P+ = P - Y^T Y                       (y~ = L^-1 y = last column of Y)
+    //      GEMMs on all SMs, the Cholesky in one register-resident CTA, the triangular solves one CTA per 8 columns.
     const double* gate = u->d_red + (size_t)n * n + n;      // counters[0] = accepted features (Updater.cc:460)
     const int m = d + 1;
-    // M = G * Pcc + s^2 I
     {
-        GemmParams g;
+        GemmParams g;                                        // W = Rc * P[c,:]   -> d_W (n x m row-major, column d reserved for y)
+        g.M = n; g.N = d; g.K = n;
+        g.A = u->d_Rc; g.ars = n; g.acs = 1;
+        g.B = P_dev + 24; g.brs = 1; g.bcs = d;              // P[c,:](k, j) = P(24 + k, j) = P_dev[j * d + 24 + k]
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_W; g.crs = m; g.ccs = 1;
+        g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
+        launch_gemm(s, g);
+        RVIO_ENQ(cudaMemcpy2DAsync(u->d_W + d, sizeof(double) * m, u->d_yc, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
+    }
+    {
+        GemmParams g;                                        // S = W[:, 24:] * Rc^T + s^2 I
         g.M = n; g.N = n; g.K = n;
-        g.A = G; g.ars = n; g.acs = 1;
-        g.B = P_dev + (size_t)24 * d + 24; g.brs = 1; g.bcs = d;
-        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_M; g.crs = n; g.ccs = 1;
+        g.A = u->d_W + 24; g.ars = m; g.acs = 1;
+        g.B = u->d_Rc; g.brs = 1; g.bcs = n;                 // Rc^T(k, j) = Rc[j * n + k]
+        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_S; g.crs = n; g.ccs = 1;
         g.alpha = 1; g.beta = 0; g.diag_add = u->consts.sig2; g.gate = gate;
         launch_gemm(s, g);
     }
-    // R = [ z | G * P[c,:] ]   (n x (1+d), row-major)
-    {
-        GemmParams g;
-        g.M = n; g.N = d; g.K = n;
-        g.A = G; g.ars = n; g.acs = 1;
-        g.B = P_dev + 24; g.brs = 1; g.bcs = d;
-        g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_R + 1; g.crs = m; g.ccs = 1;
-        g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
-        launch_gemm(s, g);
-        RVIO_ENQ(cudaMemcpy2DAsync(u->d_R, sizeof(double) * m, z, sizeof(double), sizeof(double), n, cudaMemcpyDeviceToDevice, s));
-    }
     RVIO_ENQ(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
-    RVIO_LAUNCH(k_gauss_jordan, 1, 1024, sizeof(double) * (n + 2), s, u->d_M, u->d_R, n, m, u->d_sing, gate);
-    // dx = P[:,c] * y_z
     {
-        GemmParams g;
+        const int r2 = enqueue_chol_trsm(s, u->d_S, n, u->d_LS, u->d_W, m, m, u->d_sing, gate);
+        if (r2 != RVIO_OK) return r2;
+    }
+    {
+        GemmParams g;                                        // dx = Y^T y~
         g.M = d; g.N = 1; g.K = n;
-        g.A = P_dev + (size_t)24 * d; g.ars = 1; g.acs = d;
-        g.B = u->d_R; g.brs = m; g.bcs = 1;
+        g.A = u->d_W; g.ars = 1; g.acs = m;
+        g.B = u->d_W + d; g.brs = m; g.bcs = 1;
         g.C0 = nullptr; g.c0rs = g.c0cs = 0; g.C = u->d_dx; g.crs = 1; g.ccs = 1;
         g.alpha = 1; g.beta = 0; g.diag_add = 0; g.gate = gate;
         launch_gemm(s, g);
     }
-    // Pnew = P - P[:,c] * Y_W    (column-major d x d)
     {
-        GemmParams g;
+        GemmParams g;                                        // Pnew = P - Y^T Y   (column-major d x d)
         g.M = d; g.N = d; g.K = n;
-        g.A = P_dev + (size_t)24 * d; g.ars = 1; g.acs = d;
-        g.B = u->d_R + 1; g.brs = m; g.bcs = 1;
+        g.A = u->d_W; g.ars = 1; g.acs = m;
+        g.B = u->d_W; g.brs = m; g.bcs = 1;
         g.C0 = P_dev; g.c0rs = 1; g.c0cs = d; g.C = u->d_Pnew; g.crs = 1; g.ccs = d;
         g.alpha = -1; g.beta = 1; g.diag_add = 0; g.gate = gate;
         launch_gemm(s, g);
@@ -1498,6 +1505,12 @@ const double* updater_counters_dev(const rvio_updater* u)
     return u->d_red + (size_t)n * n + n;
 }
 int updater_device(const rvio_updater* u) { return u->device; }
+double* updater_reduce_dev(rvio_updater* u, int* count)
+{
+    const int n = 6 * u->cur_N;
+    *count = n * n + n + 8 + n + 1;
+    return u->d_red;
+}
 
 }  // namespace rvio
 

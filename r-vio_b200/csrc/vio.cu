@@ -4,6 +4,7 @@
 // (System.cc:183-249, System::initialize :115-170) and the clone counters.
 #include <time.h>
 #include "common.cuh"
+#include "shard.cuh"
 #include "tracker_kernels.cuh"
 #include "filter_kernels.cuh"
 #include "detector_kernels.cuh"
@@ -41,6 +42,11 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
 int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, double* P_out_dev);
 int updater_enqueue_solve_on(rvio_updater* u, cudaStream_t s, const double* x_dev, const double* P_dev, double* x_out_dev, double* P_out_dev);
 const double* updater_counters_dev(const rvio_updater* u);
+double* updater_reduce_dev(rvio_updater* u, int* count);
+int tracker_enqueue_frame_sharded(rvio_tracker* t, const uint8_t* img_host, int w, int h, int stride, int ch, const uint8_t* img_dev, int pitch,
+                                  bool staged, const double* imu, int n_imu, int rank, int world);
+int tracker_enqueue_ransac(rvio_tracker* t);
+int tracker_shard_size(const rvio_tracker* t, int world);
 }  // namespace rvio
 
 using namespace rvio;
@@ -72,6 +78,7 @@ struct rvio_vio {
     double wm[3], am[3];
     int n_imu_count, n_clones, n_img_after_init;
     rvio_update_info last_info;
+    ShardComm shard;              // feature-sharded single stream (rvio_vio_shard_init): world > 1
     // FindNewer geometry
     int gc, gr, offx, offy, max_per_block;
     std::vector<void*> allocs, hallocs;
@@ -276,6 +283,7 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     cudaStreamDestroy(v->side); cudaStreamDestroy(v->dets); cudaEventDestroy(v->ev_det_done);
     for (void* p : v->allocs) cudaFree(p);
     for (void* p : v->hallocs) cudaFreeHost(p);
+    shard_comm_destroy(&v->shard);
     rvio_updater_destroy(v->upd);
     rvio_tracker_destroy(v->trk);
     delete v;
@@ -317,7 +325,20 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     // ---- visual tracking (System.cc:258) on the main stream
     if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[0], s));
     int rc;
-    if (staged) rc = tracker_enqueue_frame_staged(v->trk, imu, n_imu);
+    const int world = v->shard.world, srank = v->shard.rank;
+    if (world > 1) {
+        // feature-sharded: LK for this rank's share of the feature indices, one all-gather of the per-feature results on
+        // this stream, RANSAC + bookkeeping replicated (bit-identical on every rank)
+        rc = tracker_enqueue_frame_sharded(v->trk, img_host, width, height, stride, channels, img_dev, pitch, staged, imu, n_imu, srank, world);
+        if (rc < 0) return rc;
+        if (rc == RVIO_OK) {
+            const TrackerBuffers* Bs = tracker_buffers(v->trk);
+            int r2 = shard_allgather_lk(&v->shard, s, Bs->lk, Bs->un, Bs->status, tracker_shard_size(v->trk, world));
+            if (r2 != RVIO_OK) return r2;
+            r2 = tracker_enqueue_ransac(v->trk);
+            if (r2 != RVIO_OK) return r2;
+        }
+    } else if (staged) rc = tracker_enqueue_frame_staged(v->trk, imu, n_imu);
     else if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
     else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
     if (rc < 0) return rc;
@@ -365,8 +386,14 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     if (N > v->min_clones) {
         const TrackerBuffers* B = tracker_buffers(v->trk);
         int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[xi0], xdim, v->d_P[pi0], d, B->up_types, B->up_off, B->up_xy,
-                                              v->Fu, &B->sc->n_up, 0, 1);
+                                              v->Fu, &B->sc->n_up, srank, world);
         if (r2 != RVIO_OK) return r2;
+        if (world > 1) {                                               // the single reduce of the sharded update, in stream
+            int cnt = 0;
+            double* red = updater_reduce_dev(v->upd, &cnt);
+            r2 = shard_allreduce_terms(&v->shard, s, red, cnt);
+            if (r2 != RVIO_OK) return r2;
+        }
         if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[2], s));      // per-feature + normal terms done
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
         if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[3], s));      // (waited for propagation)
@@ -570,6 +597,45 @@ extern "C" int rvio_vio_graphs(rvio_vio* v, int enable, uint64_t* graph_launches
     if (enable >= 0) v->use_graphs = enable != 0;
     if (graph_launches) *graph_launches = v->graph_launches;
     return RVIO_OK;
+}
+
+extern "C" int rvio_vio_shard_init(rvio_vio* v, int rank, int world, const void* nccl_unique_id)
+{
+    RVIO_ARG_CHECK(v && nccl_unique_id && world >= 1 && world <= 64 && rank >= 0 && rank < world);
+    if (v->n_img_after_init > 0 || v->ready) { set_error("rvio_vio_shard_init", "must be called before the first frame"); return RVIO_ERR_STATE; }
+    if (world == 1) return RVIO_OK;
+    return shard_comm_create(&v->shard, rank, world, nccl_unique_id, v->device);
+}
+
+extern "C" int rvio_vio_shard_probe(rvio_vio* v, int iters, float* us2)
+{
+    RVIO_ARG_CHECK(v && us2 && iters > 0);
+    if (v->shard.world <= 1) { us2[0] = us2[1] = 0.f; return RVIO_OK; }
+    RVIO_CUDA_TRY(cudaSetDevice(v->device));
+    cudaStream_t s = v->stream;
+    const TrackerBuffers* B = tracker_buffers(v->trk);
+    const int S = tracker_shard_size(v->trk, v->shard.world);
+    const int n = 6 * v->window;
+    const int cnt = n * n + n + 8 + n + 1;
+    double* scratch = nullptr;
+    RVIO_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * cnt));
+    RVIO_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * cnt, s));
+    cudaEvent_t e0, e1, e2;
+    RVIO_CUDA_TRY(cudaEventCreate(&e0)); RVIO_CUDA_TRY(cudaEventCreate(&e1)); RVIO_CUDA_TRY(cudaEventCreate(&e2));
+    int rc = RVIO_OK;
+    for (int k = 0; k < 3 && rc == RVIO_OK; ++k) { rc = shard_allgather_lk(&v->shard, s, B->lk, B->un, B->status, S); if (rc == RVIO_OK) rc = shard_allreduce_terms(&v->shard, s, scratch, cnt); }
+    cudaEventRecord(e0, s);
+    for (int k = 0; k < iters && rc == RVIO_OK; ++k) rc = shard_allgather_lk(&v->shard, s, B->lk, B->un, B->status, S);
+    cudaEventRecord(e1, s);
+    for (int k = 0; k < iters && rc == RVIO_OK; ++k) rc = shard_allreduce_terms(&v->shard, s, scratch, cnt);
+    cudaEventRecord(e2, s);
+    cudaStreamSynchronize(s);
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    us2[0] = 1e3f * a / iters; us2[1] = 1e3f * b / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaFree(scratch);
+    return rc;
 }
 
 extern "C" rvio_tracker* rvio_vio_tracker(rvio_vio* v) { return v ? v->trk : nullptr; }

@@ -273,6 +273,12 @@ class Updater:
         return G, z
 
 
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    capi.check(capi.lib().rvio_b200_nccl_unique_id(buf), "rvio_b200_nccl_unique_id")
+    return buf.raw
+
+
 class Vio:
     """Fused per-frame pipeline (rvio_vio_*): System::MonoVIO with x, P, pyramids and feature lists on the device."""
 
@@ -327,6 +333,24 @@ class Vio:
 
     def set_rank_rule(self, full_information: bool):
         capi.check(self.L.rvio_updater_set_rank_rule(self.L.rvio_vio_updater(self.h), 1 if full_information else 0))
+
+    def graph_launches(self) -> int:
+        n = C.c_uint64()
+        capi.check(self.L.rvio_vio_graphs(self.h, -1, C.byref(n)))
+        return int(n.value)
+
+    def shard_init(self, rank: int, world: int, unique_id: bytes):
+        """Feature-sharded single stream (rvio_vio_shard_init): call on every rank before the first frame with the 128-byte id
+        rank 0 got from nccl_unique_id()."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        capi.check(self.L.rvio_vio_shard_init(self.h, rank, world, buf), "rvio_vio_shard_init")
+
+    def shard_probe(self, iters: int = 50):
+        """us per frame spent in the two collectives of the sharded frame (all-gather of the LK results + all-reduce of the
+        normal terms), measured on the pipeline's own stream with nothing else in flight."""
+        us = (C.c_float * 2)()
+        capi.check(self.L.rvio_vio_shard_probe(self.h, iters, us), "rvio_vio_shard_probe")
+        return float(us[0]), float(us[1])
 
     def update_info(self):
         inf = capi.UpdateInfo()

@@ -224,14 +224,17 @@ def test_fused_path_reports_detector_overflow():
     outputs, with RVIO_DETECTOR_TRUNCATED (3) and a message; ordinary frames return RVIO_OK."""
     from rvio_b200 import capi
     cfg = synth.baseline_config(2)
-    st = synth.Stream(cfg, 16, 5, t_static=0.25)
+    st = synth.Stream(cfg, 40, 5, t_static=0.5)
     r = np.random.default_rng(3)
     vio = host.Vio(cfg, 0)
-    consumed, codes = 0, []
+    consumed, codes, first_pose = 0, [], None
     for i in range(st.n_frames):
         imu, consumed = st.imu_for_frame(i, consumed)
         noise = r.integers(0, 256, (cfg.height, cfg.width), dtype=np.uint8)
-        p = vio.step(noise if i >= 8 else st.frames[i], imu, device_detector=True)
+        use_noise = first_pose is not None and i >= first_pose + 3
+        p = vio.step(noise if use_noise else st.frames[i], imu, device_detector=True)
+        if p is not None and first_pose is None:
+            first_pose = i
         codes.append((i, vio.last_rc, p is not None))
     vio.close()
     assert any(rc == 3 and valid for (_, rc, valid) in codes), codes
