@@ -1,5 +1,6 @@
 // tracker.cu -- CUDA kernels + C ABI of the tracker half of the hot path (see tracker_kernels.cuh).
 // Compiled for sm_100a with -fmad=false (bit-exact float32/float64 contract).
+#include <cuda.h>
 #include "common.cuh"
 #include "tracker_kernels.cuh"
 #include "detector_kernels.cuh"
@@ -181,10 +182,16 @@ struct LKParams {
 // is then exact, so the sum equals the integer total and is order independent; otherwise they are added one by one.
 constexpr int kTileW = 48, kTileH = 32;
 
-struct LKWarpSmem {
+// TMA descriptors of the CURRENT pyramid's levels (one 2-D u8 tensor per level: the whole padded level buffer), passed
+// to k_lk as a __grid_constant__ parameter; the next-image tile is fetched with cp.async.bulk.tensor.2d into shared memory
+// and its arrival is awaited on a per-warp mbarrier (north_star: "image pyramid staged through TMA into shared memory").
+struct LKTmaps { CUtensorMap lv[kMaxLevels]; };
+
+struct __align__(128) LKWarpSmem {
+    __align__(128) unsigned char tile[kTileH * kTileW];      // TMA destination (128-byte aligned)
+    __align__(8) unsigned long long mbar;                    // transaction barrier of the tile loads
     short dgrid[16 * 16 * 2];            // Scharr (dx,dy) on the 16x16 tap grid
     unsigned char Ireg[18 * 20];
-    __align__(16) unsigned char tile[kTileH * kTileW];
     __align__(16) float ch[3 * 232];     // per matrix / chain set: [y*8 + slot] (120 floats) then [120 + y*7 + t] (105 floats)
 };
 
@@ -200,6 +207,35 @@ __device__ __forceinline__ void lk_weights(float a, float b, int* w00, int* w01,
     *w11 = 16384 - *w00 - *w01 - *w10;
 }
 
+// ---- TMA / mbarrier primitives (sm_100a PTX)
+__device__ __forceinline__ unsigned lk_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lk_mbar_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem_addr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// One lane: order the warp's earlier generic-proxy reads of the tile before the async-proxy write, arm the barrier with
+// the tile's byte count and start the 2-D tensor copy of the kTileW x kTileH box whose top-left element is (x, y).
+__device__ __forceinline__ void lk_tma_load_tile(const CUtensorMap* map, unsigned char* tile, unsigned long long* bar, int x, int y)
+{
+    const unsigned dst = lk_smem_addr(tile), mb = lk_smem_addr(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(kTileW * kTileH)) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned mb = lk_smem_addr(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// (pre-TMA staging, kept for the sharded / reference comparison build: -DRVIO_LK_NO_TMA)
 // Stage the kTileH x kTileW byte tile whose top-left pixel is (tx0, ty0) (tx0 multiple of 16) from level J.
 __device__ __forceinline__ void lk_stage_tile(const PyrLevel& J, int tx0, int ty0, unsigned char* tile, int lane)
 {
@@ -214,13 +250,16 @@ __device__ __forceinline__ void lk_stage_tile(const PyrLevel& J, int tx0, int ty
     }
 }
 
-__global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
+__global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P, const __grid_constant__ LKTmaps M)
 {
     __shared__ LKWarpSmem smem_all[kLKWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pt = P.first + blockIdx.x * kLKWarps + wib;
     if (pt >= (P.n_dev ? *P.n_dev : P.n) || pt >= P.last) return;   // whole warp exits together
     LKWarpSmem& S = smem_all[wib];
+    unsigned tma_phase = 0;
+    if (lane == 0) lk_mbar_init(&S.mbar);
+    __syncwarp();
     const unsigned FULL = 0xffffffffu;
     // pixel ownership
     const int oy = lane >> 1, half_ = lane & 1;
@@ -369,7 +408,15 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P)
                 tx0 = ((inx - 8 + 1024) & ~15) - 1024;           // floor to a multiple of 16 (also for negatives)
                 ty0 = iny - 8;
                 __syncwarp();
+#ifdef RVIO_LK_NO_TMA
                 lk_stage_tile(J, tx0, ty0, S.tile, lane);
+#else
+                // TMA: one lane issues the box copy (coordinates relative to the padded level buffer; out-of-buffer parts are
+                // zero filled by the hardware), the warp waits on the tile's transaction barrier
+                if (lane == 0) lk_tma_load_tile(&M.lv[level], S.tile, &S.mbar, tx0 + kBorder, ty0 + kBorder);
+                lk_mbar_wait(&S.mbar, tma_phase);
+                tma_phase ^= 1u;
+#endif
                 __syncwarp();
                 have_tile = true;
             }
@@ -839,6 +886,7 @@ struct rvio_tracker {
     uint8_t* d_lut;
     uint8_t* d_pyr_mem[2];
     Pyramid pyr[2];             // [cur_idx] = current, [1-cur_idx] = previous
+    LKTmaps tmaps[2];           // TMA descriptors of the levels of pyr[0] / pyr[1]
     int cur_idx;
     TrackerBuffers B;
     double* d_R; int imu_cap;   // RANSAC rotation of the frame (9 doubles)
@@ -895,6 +943,38 @@ int build_pyramid_layout(rvio_tracker* t, int which)
         P.lv[l].base = mem + offs[l] + (size_t)kBorder * pitches[l] + kBorder;
         P.lv[l].pitch = pitches[l]; P.lv[l].w = ws[l]; P.lv[l].h = hs[l];
     }
+    return RVIO_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int build_tensor_maps(rvio_tracker* t, int which)
+{
+    static PFN_tmapEncodeTiled enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        RVIO_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cudaGetDriverEntryPoint", "cuTensorMapEncodeTiled not available"); return RVIO_ERR_CUDA; }
+        enc = (PFN_tmapEncodeTiled)fn;
+    }
+    const Pyramid& P = t->pyr[which];
+    memset(&t->tmaps[which], 0, sizeof(LKTmaps));
+    for (int l = 0; l < P.levels; ++l) {
+        const PyrLevel& L = P.lv[l];
+        void* origin = (void*)(L.base - (ptrdiff_t)kBorder * L.pitch - kBorder);      // first byte of the padded level buffer
+        const cuuint64_t dims[2] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * kBorder)};
+        const cuuint64_t strides[1] = {(cuuint64_t)L.pitch};
+        const cuuint32_t box[2] = {(cuuint32_t)kTileW, (cuuint32_t)kTileH};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&t->tmaps[which].lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, origin, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled", "failed for a pyramid level"); return RVIO_ERR_CUDA; }
+    }
+    for (int l = P.levels; l < kMaxLevels; ++l) t->tmaps[which].lv[l] = t->tmaps[which].lv[0];
     return RVIO_OK;
 }
 
@@ -958,6 +1038,8 @@ extern "C" int rvio_tracker_create(const rvio_tracker_cfg* cfg, int device, rvio
     if ((rc = dalloc(t, &t->d_lut, 25 * 256)) != RVIO_OK) return rc;
     if ((rc = build_pyramid_layout(t, 0)) != RVIO_OK) return rc;
     if ((rc = build_pyramid_layout(t, 1)) != RVIO_OK) return rc;
+    if ((rc = build_tensor_maps(t, 0)) != RVIO_OK) return rc;
+    if ((rc = build_tensor_maps(t, 1)) != RVIO_OK) return rc;
     TrackerBuffers& B = t->B;
     B.F = t->F; B.Fu = t->Fu; B.Lmax = t->Lmax; B.Lmin = t->Lmin; B.hist_cap = t->Lmax + 1;
     const size_t F = (size_t)t->F;
@@ -1093,7 +1175,7 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
         lp.first = shard_rank * S; lp.last = lp.first + S;
         n_lk = S;
     }
-    RVIO_LAUNCH(k_lk, div_up(n_lk, kLKWarps), kLKWarps * 32, 0, s, lp);
+    RVIO_LAUNCH(k_lk, div_up(n_lk, kLKWarps), kLKWarps * 32, 0, s, lp, t->tmaps[t->cur_idx]);
     if (!finish) { RVIO_ENQ(cudaGetLastError()); return RVIO_OK; }
     RansacParams rp;
     rp.B = t->B; rp.n = n; rp.n_dev = lp.n_dev; rp.use_sampson = t->cfg.use_sampson;
