@@ -59,6 +59,8 @@ __device__ __forceinline__ double warp_sum_d(double v)
 // ------------------------------------------------------------------------------------------------
 constexpr int kSFThreads = 576;
 constexpr int kSFMaxRows = 188;           // 47 row tiles -> 576 tiles
+constexpr int kSFColLen = kSFMaxRows + (kSFMaxRows >> 3) + 8;      // published column, padded: element i lives at i + (i >> 3)
+__device__ __forceinline__ int sf_ci(int i) { return i + (i >> 3); }   // tiles are 8 columns apart: 9 tc + y hits 16 different banks
 
 struct SFTile { int tr, tc, r0, c0; bool valid; };
 
@@ -76,20 +78,21 @@ __device__ __forceinline__ SFTile sf_tile_of(int t, int rows_total)
 }
 
 // Factorises in place.  a: this thread's tile.  m: matrix order, aug: 1 when row m carries the right-hand side.
-// col: shared double[2][kSFMaxRows + 4].  L: global, column j of the lower factor at L[j * ldl + i], i = j .. m (+aug).
+// col: shared double[2][kSFColLen].  L: column j of the lower factor at L[j * ldl + i], i = j .. m (+aug); with PACKED at
+// L[j m - j (j-1) / 2 + (i - j)] and 1 / L(j,j) at invd[j] (what k_trsm reads).
 // pv: shared double[m] pivots (negative for skipped columns).  SKIP: dependent columns (pivot < max(1e-12, 1e-12 gd[j])) are
 // skipped; otherwise a non-positive pivot sets *bad.  on_column(j) is called by ALL threads before column j is processed
 // (used by the rank rule for its class-boundary test; may return false to stop: then the function returns j);
 // after_pivot(j, dependent) is called by all threads once the pivot of column j is known.
-template <bool SKIP, class OnColumn, class AfterPivot>
+template <bool SKIP, bool PACKED, class OnColumn, class AfterPivot>
 __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, int m, int aug, double* col, double* L, int ldl,
-                                          double* pv, const double* gd, int* bad, OnColumn on_column, AfterPivot after_pivot)
+                                          double* pv, const double* gd, int* bad, double* invd, OnColumn on_column, AfterPivot after_pivot)
 {
     const int rows_total = m + aug;
     int buf = 0;
     for (int j = 0; j < m; ++j) {
         if (!on_column(j)) return j;
-        double* cj = col + buf * (kSFMaxRows + 4);
+        double* cj = col + buf * kSFColLen;
         const int tcj = j >> 3, jj = j & 7;
         if (T.valid && T.tc == tcj && T.r0 + 3 >= j) {
 #pragma unroll
@@ -99,12 +102,12 @@ __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, in
                     double v = 0;
 #pragma unroll
                     for (int y = 0; y < 8; ++y) if (y == jj) v = a[x][y];
-                    cj[r] = v;
+                    cj[sf_ci(r)] = v;
                 }
             }
         }
         __syncthreads();
-        const double p = cj[j];
+        const double p = cj[sf_ci(j)];
         bool dep;
         if (SKIP) dep = !(p >= fmax(1e-12, 1e-12 * gd[j]));
         else { dep = false; if (!(p > 0.0) && threadIdx.x == 0) *bad = 1; }
@@ -112,13 +115,19 @@ __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, in
         after_pivot(j, dep);                                       // every thread, same value
         if (!dep) {
             const double rs = rsqrt(p);
-            for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) L[(size_t)j * ldl + i] = cj[i] * rs;
+            if (PACKED) {
+                double* Lj = L + ((size_t)j * m - (size_t)j * (j - 1) / 2) - j;
+                for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) Lj[i] = cj[sf_ci(i)] * rs;
+                if (threadIdx.x == 0) invd[j] = rs;
+            } else {
+                for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) L[(size_t)j * ldl + i] = cj[sf_ci(i)] * rs;
+            }
             if (T.valid && T.r0 + 3 > j && T.c0 + 7 > j) {
                 double lr[4], lc[8];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) { const int r = T.r0 + x; lr[x] = (r > j && r < rows_total) ? cj[r] * rs : 0.0; }
+                for (int x = 0; x < 4; ++x) { const int r = T.r0 + x; lr[x] = (r > j && r < rows_total) ? cj[sf_ci(r)] * rs : 0.0; }
 #pragma unroll
-                for (int y = 0; y < 8; ++y) { const int c = T.c0 + y; lc[y] = (c > j && c < m) ? cj[c] * rs : 0.0; }
+                for (int y = 0; y < 8; ++y) { const int c = T.c0 + y; lc[y] = (c > j && c < m) ? cj[sf_ci(c)] * rs : 0.0; }
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -172,7 +181,7 @@ __device__ __forceinline__ void sf_load(double (&a)[4][8], const SFTile& T, cons
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 {
-    __shared__ double s_col[2][kSFMaxRows + 4];
+    __shared__ double s_col[2][kSFColLen];
     __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows], s_diag[kSFMaxRows];
     __shared__ int s_np, s_k, s_smin, s_ncls;
     __shared__ double s_tau;
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         }
         return true;
     };
-    const int jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], L, ldl, s_pv, s_gd, nullptr, on_column, after_pivot);
+    const int jstop = sym_factor<true, false>(a, T, Np, 1, &s_col[0][0], L, ldl, s_pv, s_gd, nullptr, nullptr, on_column, after_pivot);
     __syncthreads();
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
     const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
@@ -327,45 +336,46 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 // Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, register resident), then  Y = L^-1 [W | y]
 // (k_trsm, one CTA per 8 right-hand-side columns, L in shared memory).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSFThreads, 1) k_chol_S(const double* S, int m, double* L, int* bad, const double* gate)
+__global__ void __launch_bounds__(kSFThreads, 1) k_chol_S(const double* S, int m, double* Lp, double* invd, int* bad, const double* gate)
 {
-    __shared__ double s_col[2][kSFMaxRows + 4];
+    __shared__ double s_col[2][kSFColLen];
     __shared__ double s_pv[kSFMaxRows];
     if (gate && !(gate[0] > 2.0)) return;
     const SFTile T = sf_tile_of(threadIdx.x, m);
     double a[4][8];
     sf_load(a, T, S, m, m, nullptr, 0);
-    sym_factor<false>(a, T, m, 0, &s_col[0][0], L, m, s_pv, nullptr, bad, [](int) { return true; }, [](int, bool) {});
+    sym_factor<false, true>(a, T, m, 0, &s_col[0][0], Lp, 0, s_pv, nullptr, bad, invd, [](int) { return true; }, [](int, bool) {});
 }
 
-// B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  L: column j at L[j * m + i], i >= j.
+// B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  Lp: packed lower factor (column j
+// at j m - j (j-1) / 2), invd[j] = 1 / L(j,j).  One CTA per kTrsmCols columns, one thread per row, the factor in shared memory.
 constexpr int kTrsmCols = 8;
-__global__ void __launch_bounds__(192) k_trsm(const double* L, int m, double* B, int ldb, int nb, const double* gate)
+__global__ void __launch_bounds__(192) k_trsm(const double* Lp, const double* invd, int m, double* B, int ldb, int nb, const double* gate)
 {
-    extern __shared__ __align__(16) double sL[];                 // packed lower triangle, column j at off(j) = j m - j (j-1) / 2
+    extern __shared__ __align__(16) double sL[];                 // packed lower triangle, then invd[m]
     __shared__ double s_y[2][kTrsmCols];
     if (gate && !(gate[0] > 2.0)) return;
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * kTrsmCols;
-    for (int j = 0; j < m; ++j) {
-        const size_t off = (size_t)j * m - (size_t)j * (j - 1) / 2;
-        for (int i = j + tid; i < m; i += 192) sL[off + (i - j)] = L[(size_t)j * m + i];
-    }
+    const int np = m * (m + 1) / 2;
+    double* sI = sL + np;
+    for (int e = tid; e < np; e += 192) sL[e] = Lp[e];           // linear copy: many loads in flight
+    for (int e = tid; e < m; e += 192) sI[e] = invd[e];
     double b[kTrsmCols];
 #pragma unroll
     for (int c = 0; c < kTrsmCols; ++c) b[c] = (tid < m && c0 + c < nb) ? B[(size_t)tid * ldb + c0 + c] : 0.0;
     __syncthreads();
     int buf = 0;
     for (int j = 0; j < m; ++j) {
-        const size_t off = (size_t)j * m - (size_t)j * (j - 1) / 2;
+        const int off = j * m - j * (j - 1) / 2 - j;             // column j, element i at off + i
         if (tid == j) {
-            const double inv = 1.0 / sL[off];
+            const double inv = sI[j];
 #pragma unroll
             for (int c = 0; c < kTrsmCols; ++c) { b[c] *= inv; s_y[buf][c] = b[c]; }
         }
         __syncthreads();
         if (tid > j && tid < m) {
-            const double l = sL[off + (tid - j)];
+            const double l = sL[off + tid];
 #pragma unroll
             for (int c = 0; c < kTrsmCols; ++c) b[c] = fma(-l, s_y[buf][c], b[c]);
         }
@@ -569,7 +579,7 @@ int compress_configure(int nmax)
         gv = 200 * 1024;
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + nmax + 8))));
     return RVIO_OK;
 }
 
@@ -592,8 +602,9 @@ int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefP
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate)
 {
     if (n > kSFMaxRows || n > 192) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
-    RVIO_LAUNCH(k_chol_S, 1, kSFThreads, 0, s, S, n, L, bad, gate);
-    RVIO_LAUNCH(k_trsm, div_up(nb, kTrsmCols), 192, sizeof(double) * ((size_t)n * (n + 1) / 2 + 8), s, L, n, B, ldb, nb, gate);
+    double* invd = L + (size_t)n * (n + 1) / 2;                 // the scratch is n x n: room for the packed factor and 1 / diag
+    RVIO_LAUNCH(k_chol_S, 1, kSFThreads, 0, s, S, n, L, invd, bad, gate);
+    RVIO_LAUNCH(k_trsm, div_up(nb, kTrsmCols), 192, sizeof(double) * ((size_t)n * (n + 1) / 2 + n + 8), s, L, invd, n, B, ldb, nb, gate);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ int s_hist[kDetBins];
-    __shared__ int s_lo, s_take, s_count, s_nout, s_stop, s_und;
+    __shared__ int s_lo, s_take, s_count, s_nout, s_stop;
     __shared__ int s_warp[32];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -152,12 +152,9 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
     const int nbins = (int)((max_bits >> shift) - base) + 1;
     for (int i = tid; i < kDetBins; i += 1024) s_hist[i] = 0;
     const int cell = P.cell, gw = P.gw, gh = P.gh;
-    unsigned char* cnt = dsm + (size_t)kDetBlock * 8;
+    unsigned char* cnt = dsm + (size_t)kDetBlock * 16;
     unsigned* slots = reinterpret_cast<unsigned*>(cnt + ((gw * gh + 15) & ~15));
-    int* head = reinterpret_cast<int*>(slots + (size_t)gw * gh * kDetCellSlots);          // per-cell list of this block's candidates
-    unsigned* emit = reinterpret_cast<unsigned*>(head + gw * gh);                          // corners kept in this block, rank order
-    short* nxt = reinterpret_cast<short*>(emit + kDetBlock);
-    unsigned char* st8 = reinterpret_cast<unsigned char*>(nxt + kDetBlock);               // 0 undecided, 1 kept, 2 rejected
+    unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(dsm + (size_t)kDetBlock * 8);     // second buffer of the compaction
     for (int i = tid; i < gw * gh; i += 1024) cnt[i] = 0;
     if (tid == 0) { s_nout = 0; s_stop = 0; }
     __syncthreads();
@@ -217,97 +214,93 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                 }
                 __syncthreads();
             }
-        // ---- greedy minimum-distance selection of the sorted block by PARALLEL ROUNDS (tests/test_detector_parallel_rounds.py
-        //      shows the equivalence with the strongest-first scan): a candidate is kept as soon as every stronger candidate
-        //      closer than the distance is rejected, rejected as soon as one of them is kept.  Decisions are final, so the
-        //      rounds may read states while they change.  Candidates near a corner kept in an EARLIER block were dropped by
-        //      the filter pass above.  All 1024 threads, ~10-20 rounds, instead of one warp walking 4096 candidates.
-        for (int i = tid; i < gw * gh; i += 1024) head[i] = -1;
-        __syncthreads();
-        for (int k = tid; k < take; k += 1024) {
-            const unsigned lo32 = (unsigned)keys[k];
-            const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-            st8[k] = 0;
-            nxt[k] = (short)atomicExch(&head[(y / cell) * gw + (x / cell)], k);
-        }
-        __syncthreads();
-        while (true) {
-            if (tid == 0) s_und = 0;
-            __syncthreads();
-            int und = 0;
-            for (int k = tid; k < take; k += 1024) {
-                if (st8[k] != 0) continue;
-                const unsigned lo32 = (unsigned)keys[k];
-                const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-                const int xc = x / cell, yc = y / cell;
-                bool rej = false, pend = false;
-                for (int q = 0; q < 9 && !rej; ++q) {
-                    const int yy = yc + q / 3 - 1, xx = xc + q % 3 - 1;
-                    if (yy < 0 || yy >= gh || xx < 0 || xx >= gw) continue;
-                    for (int j = head[yy * gw + xx]; j >= 0; j = nxt[j]) {
-                        if (j >= k) continue;                                  // only stronger candidates matter
-                        const unsigned pj = (unsigned)keys[j];
-                        const int dx = x - (int)(pj & 0xffffu), dy = y - (int)(pj >> 16);
-                        if ((double)(dx * dx + dy * dy) < md2) {
-                            const int sj = st8[j];
-                            if (sj == 1) { rej = true; break; }
-                            if (sj == 0) pend = true;
-                        }
-                    }
-                }
-                if (rej) st8[k] = 2;
-                else if (!pend) st8[k] = 1;
-                else und = 1;
-            }
-            if (und) s_und = 1;
-            __syncthreads();
-            if (!s_und) break;
-            __syncthreads();
-        }
-        // kept candidates in rank order -> output slots (block-wide exclusive scan over the sorted block), corner limit applied
+        // ---- greedy minimum-distance selection of the sorted block: resolve / filter / compact iterations.
+        //      (1) one warp settles the 32 strongest candidates still alive, in rank order (they are known to be clear of
+        //          every corner kept so far); (2) ALL threads test the remaining candidates against the corners kept so far
+        //          (3 x 3 cells of the minimum-distance grid) -- a candidate within the distance of a kept, stronger corner can
+        //          never be kept; (3) the survivors are compacted, in rank order, to the front (block scan).  Every iteration
+        //          retires the 32 strongest plus everything they shadow, so the serial warp only ever sees genuine contenders.
         {
-            const int per = (take + 1023) / 1024;
-            const int k0 = tid * per;
-            int local = 0;
-            for (int u = 0; u < per; ++u) { const int k = k0 + u; if (k < take && st8[k] == 1) local++; }
-            int incl = local;
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) s_warp[tid >> 5] = incl;
-            __syncthreads();
-            if (tid < 32) {
-                int w = s_warp[tid];
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-                s_warp[tid] = w;
-            }
-            __syncthreads();
-            int pos = incl - local + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
-            const int n_before = s_nout;
-            for (int u = 0; u < per; ++u) {
-                const int k = k0 + u;
-                if (k < take && st8[k] == 1) {
-                    const int slot = n_before + pos;
-                    if (slot < P.max_corners) {
-                        const unsigned lo32 = (unsigned)keys[k];
-                        P.out[slot] = make_float2((float)(lo32 & 0xffffu), (float)(lo32 >> 16));
-                        emit[pos] = lo32;                                       // pos < max_corners - n_before <= kDetBlock
+            unsigned long long* cur = keys;
+            unsigned long long* alt = keys2;
+            int n_alive = take;
+            int n_out = s_nout;
+            bool block_first = true;
+            while (n_alive > 0 && n_out < P.max_corners) {
+                if (block_first) {
+                    // the sorted block has not been tested against the corners kept in EARLIER blocks' later iterations: the filter
+                    // pass above did that before the gather, so the front of the block is clear
+                    block_first = false;
+                }
+                if (tid < 32) {
+                    const int k = lane;
+                    const bool valid = k < n_alive;
+                    const unsigned lo32 = valid ? (unsigned)cur[k] : 0u;
+                    const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
+                    const int xc = x / cell, yc = y / cell;
+                    bool alive = valid;
+                    unsigned surv = __ballot_sync(0xffffffffu, alive);
+                    int no = n_out;
+                    while (surv && no < P.max_corners) {
+                        const int j = __ffs(surv) - 1;
+                        const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                        if (lane == j) {
+                            P.out[no] = make_float2((float)x, (float)y);
+                            const int c = yc * gw + xc, m = cnt[c];
+                            if (m < kDetCellSlots) { slots[c * kDetCellSlots + m] = lo32; cnt[c] = (unsigned char)(m + 1); }
+                            else P.ctrl->overflow = 1;
+                            alive = false;
+                        } else if (alive) {
+                            const int dx = x - xj, dy = y - yj;
+                            if ((double)(dx * dx + dy * dy) < md2) alive = false;
+                        }
+                        ++no;
+                        __syncwarp();
+                        surv = __ballot_sync(0xffffffffu, alive);
                     }
-                    pos++;
+                    if (lane == 0) s_nout = no;
                 }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const int total = s_warp[31];
-                int n_new = total;
-                if (n_before + n_new > P.max_corners) n_new = P.max_corners - n_before;
-                for (int e = 0; e < n_new; ++e) {                               // kept corners join the grid the later blocks are filtered against
-                    const unsigned lo32 = emit[e];
-                    const int c = (int)((lo32 >> 16) / cell) * gw + (int)((lo32 & 0xffffu) / cell), m = cnt[c];
-                    if (m < kDetCellSlots) { slots[c * kDetCellSlots + m] = lo32; cnt[c] = (unsigned char)(m + 1); }
-                    else P.ctrl->overflow = 1;
+                __syncthreads();
+                n_out = s_nout;
+                if (n_out >= P.max_corners) break;
+                // (2) + (3): candidates 32.. against the grid, survivors compacted in rank order
+                const int rest = n_alive - 32;
+                if (rest <= 0) { n_alive = 0; break; }
+                const int per = (rest + 1023) / 1024;
+                const int k0 = 32 + tid * per;
+                unsigned long long mine[4];
+                int local = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u;
+                    unsigned long long kk = 0ull;
+                    if (u < per && k < n_alive) {
+                        kk = cur[k];
+                        const unsigned lo32 = (unsigned)kk;
+                        const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
+                        if (det_near_kept(cnt, slots, gw, gh, x / cell, y / cell, x, y, md2)) kk = 0ull;
+                    }
+                    mine[u] = kk;
+                    local += kk != 0ull;
                 }
-                s_nout = n_before + n_new;
-                if (s_nout >= P.max_corners) s_stop = 1;
+                int incl = local;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                if (lane == 31) s_warp[tid >> 5] = incl;
+                __syncthreads();
+                if (tid < 32) {
+                    int w = s_warp[tid];
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+                    s_warp[tid] = w;
+                }
+                __syncthreads();
+                int pos = incl - local + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (mine[u] != 0ull) alt[pos++] = mine[u];
+                n_alive = s_warp[31];
+                __syncthreads();
+                unsigned long long* t2 = cur; cur = alt; alt = t2;
             }
+            if (tid == 0 && s_nout >= P.max_corners) s_stop = 1;
         }
         __syncthreads();
         if (s_stop) break;
@@ -483,8 +476,7 @@ int detector_enqueue(Detector* D, cudaStream_t st, const PyrLevel& level0, int s
     P.subpix_iters = 30; P.subpix_eps = 1e-2;                        // FeatureDetector.cc:70
     P.cell = (int)lrint(P.min_dist);
     P.gw = (D->W + P.cell - 1) / P.cell; P.gh = (D->H + P.cell - 1) / P.cell;
-    const size_t smem = (size_t)kDetBlock * 8 + (((size_t)P.gw * P.gh + 15) & ~(size_t)15) + (size_t)P.gw * P.gh * kDetCellSlots * 4 +
-                        (size_t)P.gw * P.gh * 4 + (size_t)kDetBlock * (4 + 2 + 1) + 64;
+    const size_t smem = (size_t)kDetBlock * 16 + (((size_t)P.gw * P.gh + 15) & ~(size_t)15) + (size_t)P.gw * P.gh * kDetCellSlots * 4 + 64;
     if (smem > 200 * 1024) { set_error("detector_enqueue", "minimum-distance grid does not fit in shared memory (Tracker.nMinDist too small for this image size)"); return RVIO_ERR_CAPACITY; }
     if (D->mask_hw != P.hw) {                                        // cornerSubPix window weights (host libm, like OpenCV)
         const int ww = 2 * P.hw + 1;
