@@ -211,6 +211,11 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush):
     frames, imus = wl["frames"], wl["imus"]
     n_frames = len(frames)
     stream = torch.cuda.ExternalStream(L.rvio_tracker_stream(L.rvio_vio_tracker(vio.h)), device=dev)
+    if not dev_inputs:
+        # e2e leg: host frames in PINNED memory (the contract's "host->device copy of that step's inputs from pinned host
+        # memory"); the library DMA's a pinned single-channel frame straight into its gray buffer inside the timed call
+        keep = [torch.from_numpy(f).pin_memory() for f in frames]
+        frames = [k.numpy() for k in keep]
     if dev_inputs:
         d_frames = [torch.from_numpy(f).to(dev) for f in frames]
         d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
@@ -299,43 +304,44 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     #      between device synchronisations; the single-stream `value` above is the CUDA-event number).
     batch = None
     S = args.batch_streams
-    if world > 1:
-        # round 1: with a torch.distributed NCCL process group alive, eight host threads capturing / replaying frame graphs
-        # concurrently were observed to stall inside the CUDA runtime (every worker blocked in rvio_vio_step_dev, both ranks;
-        # the single-stream legs above are unaffected and the same leg runs fine without the process group).  Until that is
-        # understood the multi-stream leg only runs single-process.
-        S = 0
     if S > 1:
+        # Round 1 saw this leg stall under torchrun: eight host threads were CAPTURING frame graphs concurrently while an NCCL
+        # process group (its watchdog / proxy threads) was alive.  Pre-roll and warm-up (which is where every frame graph of a
+        # stream is captured) now run one stream after the other on the main thread; the worker threads only replay.
         import threading
         d_frames = [torch.from_numpy(f).to(dev) for f in frames]
         d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
         d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
         vios = [host.Vio(cfg, local_rank) for _ in range(S)]
         Kb = min(K, 100)
+
+        def one(v, i, got):
+            dc = (d_c2 if got else d_c1)[i]
+            if inloop:
+                return v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
+            return v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], dc.data_ptr() if dc is not None else None,
+                              0 if dc is None else dc.shape[0])
+
+        starts = []
+        for v in vios:                                        # sequential pre-roll + warm-up (+ 4 steady frames: both graph parities exist)
+            got, i, warm = False, 0, 0
+            while not (got and warm >= W + 4):
+                pose = one(v, i, got)
+                if got:
+                    warm += 1
+                if pose is not None:
+                    got = True
+                i += 1
+            starts.append(i)
+        torch.cuda.synchronize()
         start_bar = threading.Barrier(S + 1); end_bar = threading.Barrier(S + 1)
         errs = []
 
-        def worker(v):
+        def worker(v, i0):
             try:
-                got, i, warm, timed = False, 0, 0, 0
-                while True:
-                    dc = (d_c2 if got else d_c1)[i]
-                    if got and warm >= W and timed == 0:
-                        start_bar.wait(timeout=240)
-                    if inloop:
-                        pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
-                    else:
-                        pose = v.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], dc.data_ptr() if dc is not None else None,
-                                          0 if dc is None else dc.shape[0])
-                    if got and warm >= W:
-                        timed += 1
-                        if timed == Kb:
-                            break
-                    elif got:
-                        warm += 1
-                    if pose is not None:
-                        got = True
-                    i += 1
+                start_bar.wait(timeout=240)
+                for k in range(Kb):
+                    one(v, i0 + k, True)
                 end_bar.wait(timeout=240)
             except Exception as e:          # pragma: no cover
                 errs.append(e)
@@ -344,26 +350,31 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                 except Exception:
                     pass
 
-        ths = [threading.Thread(target=worker, args=(v,)) for v in vios]
-        for t in ths:
-            t.start()
+        if max(starts) + Kb > n_frames:
+            errs.append(RuntimeError("stream too short for the batch leg"))
+        ths = [threading.Thread(target=worker, args=(v, i0)) for v, i0 in zip(vios, starts)]
         t0 = t1 = 0.0
-        try:
-            start_bar.wait(timeout=240)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            end_bar.wait(timeout=240)
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-        except threading.BrokenBarrierError:                  # a worker failed (or timed out): no batch number, no hang
-            errs.append(RuntimeError("batch leg aborted"))
-        for t in ths:
-            t.join(timeout=60)
+        if not errs:
+            for t in ths:
+                t.start()
+            try:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                start_bar.wait(timeout=240)
+                end_bar.wait(timeout=240)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+            except threading.BrokenBarrierError:                  # a worker failed (or timed out): no batch number, no hang
+                errs.append(RuntimeError("batch leg aborted"))
+            for t in ths:
+                t.join(timeout=60)
         for v in vios:
             v.close()
         if not errs:
             batch = {"streams_per_gpu": S, "steps_per_stream": Kb, "value": S * Kb / (t1 - t0), "unit": "frames/s",
-                     "timing": "wall clock between device synchronisations, all streams concurrent"}
+                     "timing": "wall clock between device synchronisations, all streams concurrent (graphs captured beforehand, one stream at a time)"}
+        else:
+            batch = None
     # ---- feature-sharded single stream (BASELINE configs[4]: 2048 features, 30-clone window): every rank is fed the same
     #      frames; LK all-gather + normal-term all-reduce are enqueued by the library on its own stream (in the frame graph)
     sharded = None

@@ -78,15 +78,15 @@ __device__ __forceinline__ SFTile sf_tile_of(int t, int rows_total)
 }
 
 // Factorises in place.  a: this thread's tile.  m: matrix order, aug: 1 when row m carries the right-hand side.
-// col: shared double[2][kSFColLen].  L: column j of the lower factor at L[j * ldl + i], i = j .. m (+aug); with PACKED at
-// L[j m - j (j-1) / 2 + (i - j)] and 1 / L(j,j) at invd[j] (what k_trsm reads).
+// col: shared double[2][kSFColLen].  store(j, i, v, rs): element i (i = j .. m + aug - 1) of column j of the lower factor,
+// rs = 1 / L(j,j).
 // pv: shared double[m] pivots (negative for skipped columns).  SKIP: dependent columns (pivot < max(1e-12, 1e-12 gd[j])) are
 // skipped; otherwise a non-positive pivot sets *bad.  on_column(j) is called by ALL threads before column j is processed
 // (used by the rank rule for its class-boundary test; may return false to stop: then the function returns j);
 // after_pivot(j, dependent) is called by all threads once the pivot of column j is known.
-template <bool SKIP, bool PACKED, class OnColumn, class AfterPivot>
-__device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, int m, int aug, double* col, double* L, int ldl,
-                                          double* pv, const double* gd, int* bad, double* invd, OnColumn on_column, AfterPivot after_pivot)
+template <bool SKIP, class Store, class OnColumn, class AfterPivot>
+__device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, int m, int aug, double* col, Store store,
+                                          double* pv, const double* gd, int* bad, OnColumn on_column, AfterPivot after_pivot)
 {
     const int rows_total = m + aug;
     int buf = 0;
@@ -103,6 +103,9 @@ __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, in
 #pragma unroll
                     for (int y = 0; y < 8; ++y) if (y == jj) v = a[x][y];
                     cj[sf_ci(r)] = v;
+                    // the owner of the pivot also publishes 1 / sqrt(pivot): computed ONCE per step (every warp doing it for
+                    // itself costs ~40 FP64-pipe instructions x 18 warps per step, more than the rank-1 update itself)
+                    if (r == j) cj[kSFColLen - 1] = (v > 0.0) ? rsqrt(v) : 0.0;
                 }
             }
         }
@@ -114,14 +117,8 @@ __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, in
         if (threadIdx.x == 0) pv[j] = dep ? -1.0 : p;
         after_pivot(j, dep);                                       // every thread, same value
         if (!dep) {
-            const double rs = rsqrt(p);
-            if (PACKED) {
-                double* Lj = L + ((size_t)j * m - (size_t)j * (j - 1) / 2) - j;
-                for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) Lj[i] = cj[sf_ci(i)] * rs;
-                if (threadIdx.x == 0) invd[j] = rs;
-            } else {
-                for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) L[(size_t)j * ldl + i] = cj[sf_ci(i)] * rs;
-            }
+            const double rs = cj[kSFColLen - 1];
+            for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) store(j, i, cj[sf_ci(i)] * rs, rs);
             if (T.valid && T.r0 + 3 > j && T.c0 + 7 > j) {
                 double lr[4], lc[8];
 #pragma unroll
@@ -137,6 +134,19 @@ __device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, in
         buf ^= 1;
     }
     return m;
+}
+
+// loads the tile from val(r, c) for r < rows_total, c < m, c <= r (lower triangle; rows >= m are the extra rows)
+template <class Val>
+__device__ __forceinline__ void sf_load_fn(double (&a)[4][8], const SFTile& T, int m, int rows_total, Val val)
+{
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int r = T.r0 + x, c = T.c0 + y;
+            a[x][y] = (T.valid && c < m && r < rows_total && (c <= r)) ? val(r, c) : 0.0;
+        }
 }
 
 // loads the lower triangle (+ optional extra row rhs) of a row-major symmetric matrix with leading dimension ld
@@ -209,10 +219,12 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         if (cls[c] > 0.0) { atomicMin(&s_smin, c); atomicAdd(&s_ncls, 1); }
     __syncthreads();
     const int Np = s_np;
+    for (int c = tid; c <= n; c += kSFThreads) s_nr2[c < kSFMaxRows ? c : kSFMaxRows - 1] = cls[c];      // staged: the suffix sum below must not walk global memory
+    __syncthreads();
     if (tid == 0) {                                               // late[j] = information of the classes starting at column >= j
         double acc = 0;
-        for (int c = n; c > Np; --c) acc += cls[c];
-        for (int j = Np; j >= 0; --j) { acc += cls[j]; s_late[j] = acc; }
+        for (int c = n; c > Np; --c) acc += s_nr2[c];
+        for (int j = Np; j >= 0; --j) { acc += s_nr2[j]; s_late[j] = acc; }
         s_late[Np + 1] = 0.0;
     }
     __syncthreads();
@@ -260,7 +272,8 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         }
         return true;
     };
-    const int jstop = sym_factor<true, false>(a, T, Np, 1, &s_col[0][0], L, ldl, s_pv, s_gd, nullptr, nullptr, on_column, after_pivot);
+    auto store_L = [&](int j, int i, double v, double) { L[(size_t)j * ldl + i] = v; };
+    const int jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], store_L, s_pv, s_gd, nullptr, on_column, after_pivot);
     __syncthreads();
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
     const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
@@ -344,7 +357,11 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_chol_S(const double* S, int m
     const SFTile T = sf_tile_of(threadIdx.x, m);
     double a[4][8];
     sf_load(a, T, S, m, m, nullptr, 0);
-    sym_factor<false, true>(a, T, m, 0, &s_col[0][0], Lp, 0, s_pv, nullptr, bad, invd, [](int) { return true; }, [](int, bool) {});
+    auto store_packed = [&](int j, int i, double v, double rs) {
+        Lp[((size_t)j * m - (size_t)j * (j - 1) / 2) + (i - j)] = v;
+        if (i == j) invd[j] = rs;
+    };
+    sym_factor<false>(a, T, m, 0, &s_col[0][0], store_packed, s_pv, nullptr, bad, [](int) { return true; }, [](int, bool) {});
 }
 
 // B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  Lp: packed lower factor (column j
@@ -383,6 +400,177 @@ __global__ void __launch_bounds__(192) k_trsm(const double* Lp, const double* in
     }
 #pragma unroll
     for (int c = 0; c < kTrsmCols; ++c) if (tid < m && c0 + c < nb) B[(size_t)tid * ldb + c0 + c] = b[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_solve_small_R -- the whole EKF step of a small window (n + d + 1 <= 188, i.e. N <= 13) in ONE CTA, R-form
+// (Updater.cc:540-619 with Hn = R, the kept rows handed over by the rank rule, zero rows where a column was dropped):
+//     W = R P[c,:]            (n x d, shared memory, 2 x 4 register tiles)
+//     S = W[:,c] R^T + s^2 I  (n x n, SPD)
+//     [ S ; W^T ; y^T ]  ->  register-resident Cholesky with the d + 1 right-hand sides as extra rows: the extra rows of the
+//                            factor are Y^T = (L^-1 [W | y])^T, i.e. factorisation and triangular solves in the same sweep
+//     dx = Y^T y~ ,  P+ = sym(P) - Y^T Y ,  state correction (quaternions multiplicative, Updater.cc:546-613)
+// Replaces k_wgemm + k_gj_block + k_pout_finalize (three launches, a pivoted Gauss-Jordan on the non-symmetric G Pcc + s^2 I).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sr_quat_mul(const double* q1, const double* q2, double* out)      // Numerics.h:30-63
+{
+    double q[4];
+    q[0] = q1[3] * q2[0] + q1[2] * q2[1] - q1[1] * q2[2] + q1[0] * q2[3];
+    q[1] = -q1[2] * q2[0] + q1[3] * q2[1] + q1[0] * q2[2] + q1[1] * q2[3];
+    q[2] = q1[1] * q2[0] - q1[0] * q2[1] + q1[3] * q2[2] + q1[2] * q2[3];
+    q[3] = -q1[0] * q2[0] - q1[1] * q2[1] - q1[2] * q2[2] + q1[3] * q2[3];
+    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double sg = (q[3] / nrm < 0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = sg * (q[i] / nrm);
+}
+__device__ __forceinline__ void sr_apply_dq(const double* dth, const double* q, double* out)      // Updater.cc:549-566
+{
+    double dq[4] = {.5 * dth[0], .5 * dth[1], .5 * dth[2], 0};
+    const double vn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+    if (vn < 1) dq[3] = sqrt(1 - vn * vn);
+    else {
+        const double sc = 1 / sqrt(1 + vn * vn);
+        dq[0] *= sc; dq[1] *= sc; dq[2] *= sc; dq[3] = sc;
+    }
+    sr_quat_mul(dq, q, out);
+}
+
+__global__ void __launch_bounds__(kSFThreads, 1) k_solve_small_R(SolveSmallRParams Q)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_col[2][kSFColLen];
+    __shared__ double s_pv[kSFMaxRows];
+    __shared__ double s_dx[kSFMaxRows];
+    const int tid = threadIdx.x;
+    const int N = Q.N, n = 6 * N, d = Q.d;
+    if (!(Q.gate[0] > 2.0)) {                                      // Updater.cc:621-627: too few features, posterior = prior
+        for (int o = tid; o < d * d; o += kSFThreads) Q.P_out[o] = Q.P[o];
+        for (int o = tid; o < Q.xdim; o += kSFThreads) Q.x_out[o] = Q.x[o];
+        return;
+    }
+    const int ldr = n + 1, ldp = d | 1, ldw = (d + 1) | 1;
+    double* sR = sm;                                               // n x ldr
+    double* sP = sR + (size_t)n * ldr;                             // n x ldp: P[c,:]   -- later S (n x ldr)
+    double* sW = sP + (size_t)n * ldp;                             // n x ldw: [W | y]  -- later Y (columns of the factor, extra rows only)
+    double* sS = sP;
+    for (int o = tid; o < n * n; o += kSFThreads) { const int r = o / n, c = o - r * n; sR[r * ldr + c] = Q.Rc[o]; }
+    for (int o = tid; o < n * d; o += kSFThreads) { const int j = o / n, k = o - j * n; sP[k * ldp + j] = Q.P[(size_t)j * d + 24 + k]; }   // P(24+k, j)
+    __syncthreads();
+    // ---- W = R P[c,:]   (R upper triangular: k starts at the row index)
+    {
+        const int tr_n = (n + 1) / 2, tc_n = (d + 3) / 4;
+        for (int t = tid; t < tr_n * tc_n; t += kSFThreads) {
+            const int r0 = 2 * (t / tc_n), j0 = 4 * (t % tc_n);
+            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            const bool r1ok = r0 + 1 < n;
+            for (int k = r0; k < n; ++k) {
+                const double a0 = sR[r0 * ldr + k], a1 = r1ok ? sR[(r0 + 1) * ldr + k] : 0.0;
+                const double* pk = sP + k * ldp + j0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double b = (j0 + y < d) ? pk[y] : 0.0;
+                    acc[0][y] = fma(a0, b, acc[0][y]);
+                    acc[1][y] = fma(a1, b, acc[1][y]);
+                }
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+                if (j0 + y < d) { sW[r0 * ldw + j0 + y] = acc[0][y]; if (r1ok) sW[(r0 + 1) * ldw + j0 + y] = acc[1][y]; }
+        }
+        for (int r = tid; r < n; r += kSFThreads) sW[r * ldw + d] = Q.yc[r];
+    }
+    __syncthreads();
+    // ---- S = W[:, 24:] R^T + s^2 I  (lower triangle; R[c][k] = 0 for k < c)
+    {
+        const int tn = (n + 1) / 2, tcn = (n + 3) / 4;
+        for (int t = tid; t < tn * tcn; t += kSFThreads) {
+            const int r0 = 2 * (t / tcn), c0 = 4 * (t % tcn);
+            if (c0 > r0 + 1) continue;                              // tile entirely above the diagonal
+            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            const bool r1ok = r0 + 1 < n;
+            for (int k = c0; k < n; ++k) {
+                const double w0 = sW[r0 * ldw + 24 + k], w1 = r1ok ? sW[(r0 + 1) * ldw + 24 + k] : 0.0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double b = (c0 + y < n) ? sR[(c0 + y) * ldr + k] : 0.0;
+                    acc[0][y] = fma(w0, b, acc[0][y]);
+                    acc[1][y] = fma(w1, b, acc[1][y]);
+                }
+            }
+            // sS aliases sP: every thread is past the W product (barrier above)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int c = c0 + y;
+                if (c < n) {
+                    if (c <= r0) sS[r0 * ldr + c] = acc[0][y] + (c == r0 ? Q.sig2 : 0.0);
+                    if (r1ok && c <= r0 + 1) sS[(r0 + 1) * ldr + c] = acc[1][y] + (c == r0 + 1 ? Q.sig2 : 0.0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- Cholesky of S with [W | y]^T as extra rows: the extra rows of column j of the factor are Y(j, :)
+    const int rows_total = n + d + 1;
+    const SFTile T = sf_tile_of(tid, rows_total);
+    double a[4][8];
+    sf_load_fn(a, T, n, rows_total, [&](int r, int c) { return (r < n) ? sS[r * ldr + c] : sW[c * ldw + (r - n)]; });
+    __syncthreads();                                               // W is in registers: its storage becomes Y
+    double* sY = sW;
+    auto store_Y = [&](int j, int i, double v, double) { if (i >= n) sY[j * ldw + (i - n)] = v; };
+    sym_factor<false>(a, T, n, d + 1, &s_col[0][0], store_Y, s_pv, nullptr, Q.bad, [](int) { return true; }, [](int, bool) {});
+    __syncthreads();
+    // ---- dx = Y^T y~
+    for (int i = tid; i < d; i += kSFThreads) {
+        double acc = 0;
+        for (int k = 0; k < n; ++k) acc = fma(sY[k * ldw + i], sY[k * ldw + d], acc);
+        s_dx[i] = acc;
+    }
+    // ---- P+ = sym(P) - Y^T Y
+    {
+        const int tn = (d + 1) / 2, tcn = (d + 3) / 4;
+        for (int t = tid; t < tn * tcn; t += kSFThreads) {
+            const int i0 = 2 * (t / tcn), j0 = 4 * (t % tcn);
+            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            const bool i1ok = i0 + 1 < d;
+            for (int k = 0; k < n; ++k) {
+                const double* yk = sY + k * ldw;
+                const double u0 = yk[i0], u1 = i1ok ? yk[i0 + 1] : 0.0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double b = (j0 + y < d) ? yk[j0 + y] : 0.0;
+                    acc[0][y] = fma(u0, b, acc[0][y]);
+                    acc[1][y] = fma(u1, b, acc[1][y]);
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = i0 + x, j = j0 + y;
+                    if (i < d && j < d) Q.P_out[(size_t)j * d + i] = .5 * (Q.P[(size_t)j * d + i] + Q.P[(size_t)i * d + j]) - acc[x][y];
+                }
+        }
+    }
+    __syncthreads();
+    // ---- state correction (Updater.cc:546-613)
+    const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
+    for (int bq = tid; bq < 2 + N; bq += kSFThreads) {
+        int xq, eq;
+        if (bq == 0) { xq = 0; eq = 0; }
+        else if (bq == 1) { xq = 10; eq = 9; }
+        else { xq = 26 + 7 * (bq - 2); eq = 24 + 6 * (bq - 2); }
+        sr_apply_dq(dx + eq, x + xq, xo + xq);
+        if (bq >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
+    }
+    if (tid == 64) {
+        double g[3];
+        for (int k = 0; k < 3; ++k) xo[4 + k] = dx[3 + k] + x[4 + k];
+        for (int k = 0; k < 3; ++k) g[k] = dx[6 + k] + x[7 + k];
+        const double nn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        for (int k = 0; k < 3; ++k) xo[7 + k] = g[k] / nn;
+        for (int k = 0; k < 12; ++k) xo[14 + k] = dx[12 + k] + x[14 + k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,6 +756,11 @@ size_t givens_smem_bytes(int n, bool* smem_window)
     return sizeof(double) * ((size_t)n + 8);
 }
 
+size_t solve_small_smem_bytes(int n, int d)
+{
+    return sizeof(double) * ((size_t)n * (n + 1) + (size_t)n * (d | 1) + (size_t)n * ((d + 1) | 1) + 16);
+}
+
 int compress_configure(int nmax)
 {
     // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
@@ -579,6 +772,10 @@ int compress_configure(int nmax)
         gv = 200 * 1024;
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
+    {
+        const int ns = nmax < 78 ? nmax : 78;
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small_R, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem_bytes(ns, 24 + ns)));
+    }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + nmax + 8))));
     return RVIO_OK;
 }
@@ -594,6 +791,16 @@ int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefP
         if (w) RVIO_LAUNCH(k_givens_ref<true>, 1, kGVThreads, gv, s, gq_in);
         else RVIO_LAUNCH(k_givens_ref<false>, 1, kGVThreads, gv, s, gq_in);
     }
+    RVIO_ENQ(cudaGetLastError());
+    return RVIO_OK;
+}
+
+// Whole small-window EKF step in one CTA (n + d + 1 <= kSFMaxRows).
+int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
+{
+    const int n = 6 * q.N;
+    if (n + q.d + 1 > kSFMaxRows) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_solve_small_R, 1, kSFThreads, solve_small_smem_bytes(n, q.d), s, q);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

@@ -24,7 +24,17 @@ struct GivensRefParams {
     int emit_R; double* Rc; double* yc;       // as in RankRuleParams
 };
 
+// single-CTA R-form EKF step of a small window (k_solve_small_R)
+struct SolveSmallRParams {
+    const double* Rc; const double* yc;      // kept rows of R (n x n, zero rows where dropped), y
+    const double* x; const double* P; int xdim, N, d;
+    double sig2;
+    const double* gate;                       // counters: gate[0] = accepted features
+    double* x_out; double* P_out; int* bad;
+};
+
 int compress_configure(int nmax);
+int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q);
 size_t givens_window_doubles(int n);
 int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq, int n);
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate);

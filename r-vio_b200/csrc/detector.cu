@@ -133,6 +133,7 @@ __device__ __forceinline__ bool det_near_kept(const unsigned char* cnt, const un
 }
 
 constexpr int kDetBlock = 4096, kDetBins = 1024;
+constexpr int kDetWarpBatch = 8;          // sub-batches of 32 the settling warp takes per iteration
 
 __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
 {
@@ -233,30 +234,36 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                     block_first = false;
                 }
                 if (tid < 32) {
-                    const int k = lane;
-                    const bool valid = k < n_alive;
-                    const unsigned lo32 = valid ? (unsigned)cur[k] : 0u;
-                    const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-                    const int xc = x / cell, yc = y / cell;
-                    bool alive = valid;
-                    unsigned surv = __ballot_sync(0xffffffffu, alive);
+                    // kDetWarpBatch strongest candidates still alive, 32 at a time: the first 32 are clear of every kept corner;
+                    // the following ones are tested against the corners this warp has just kept (grid lookups, one lane each)
                     int no = n_out;
-                    while (surv && no < P.max_corners) {
-                        const int j = __ffs(surv) - 1;
-                        const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-                        if (lane == j) {
-                            P.out[no] = make_float2((float)x, (float)y);
-                            const int c = yc * gw + xc, m = cnt[c];
-                            if (m < kDetCellSlots) { slots[c * kDetCellSlots + m] = lo32; cnt[c] = (unsigned char)(m + 1); }
-                            else P.ctrl->overflow = 1;
-                            alive = false;
-                        } else if (alive) {
-                            const int dx = x - xj, dy = y - yj;
-                            if ((double)(dx * dx + dy * dy) < md2) alive = false;
+                    for (int sb = 0; sb < kDetWarpBatch && sb * 32 < n_alive && no < P.max_corners; ++sb) {
+                        const int k = sb * 32 + lane;
+                        const bool valid = k < n_alive;
+                        const unsigned lo32 = valid ? (unsigned)cur[k] : 0u;
+                        const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
+                        const int xc = x / cell, yc = y / cell;
+                        bool alive = valid;
+                        if (alive && sb > 0) alive = !det_near_kept(cnt, slots, gw, gh, xc, yc, x, y, md2);
+                        unsigned surv = __ballot_sync(0xffffffffu, alive);
+                        while (surv && no < P.max_corners) {
+                            const int j = __ffs(surv) - 1;
+                            const int xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+                            if (lane == j) {
+                                P.out[no] = make_float2((float)x, (float)y);
+                                const int c = yc * gw + xc, m = cnt[c];
+                                if (m < kDetCellSlots) { slots[c * kDetCellSlots + m] = lo32; cnt[c] = (unsigned char)(m + 1); }
+                                else P.ctrl->overflow = 1;
+                                alive = false;
+                            } else if (alive) {
+                                const int dx = x - xj, dy = y - yj;
+                                if ((double)(dx * dx + dy * dy) < md2) alive = false;
+                            }
+                            ++no;
+                            __syncwarp();
+                            surv = __ballot_sync(0xffffffffu, alive);
                         }
-                        ++no;
                         __syncwarp();
-                        surv = __ballot_sync(0xffffffffu, alive);
                     }
                     if (lane == 0) s_nout = no;
                 }
@@ -264,10 +271,10 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                 n_out = s_nout;
                 if (n_out >= P.max_corners) break;
                 // (2) + (3): candidates 32.. against the grid, survivors compacted in rank order
-                const int rest = n_alive - 32;
+                const int rest = n_alive - 32 * kDetWarpBatch;
                 if (rest <= 0) { n_alive = 0; break; }
                 const int per = (rest + 1023) / 1024;
-                const int k0 = 32 + tid * per;
+                const int k0 = 32 * kDetWarpBatch + tid * per;
                 unsigned long long mine[4];
                 int local = 0;
 #pragma unroll

@@ -1238,6 +1238,7 @@ struct rvio_updater {
     int* d_sing; int* d_tickets;
     int* d_rule; int32_t* d_rr; double *d_L, *d_gwin, *d_Rc, *d_yc, *d_S, *d_LS, *d_W;      // reference compression rule + R-form EKF step (compress.cu)
     int rank_rule;
+    bool legacy_small_solve;    // RVIO_B200_LEGACY_SOLVE=1: the round-1 G-form solve (k_wgemm + k_gj_block + k_pout_finalize), for A/B timing
     int groups_cap;
     // pinned
     double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing; int* h_rule;
@@ -1337,6 +1338,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
 #undef HA
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_chi2, RVIO_CHI2_95_HOST, sizeof(double) * 500, cudaMemcpyHostToDevice, u->stream));
     u->rank_rule = 0;                                    // the reference's rule (d_rule is zero-initialised)
+    { const char* e = getenv("RVIO_B200_LEGACY_SOLVE"); u->legacy_small_solve = e && e[0] == '1'; }
     if ((rc = compress_configure(u->nmax)) != RVIO_OK) return rc;
     RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
     *out = u;
@@ -1411,13 +1413,21 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         // large-window path it also hands over the kept rows R (G = R^T R) and y (R^T y = z)
         RankRuleParams rq;
         rq.red = u->d_red; rq.n = n; rq.world = u->cur_world; rq.rule_dev = u->d_rule; rq.L = u->d_L; rq.rr = u->d_rr;
-        rq.emit_R = small ? 0 : 1; rq.Rc = u->d_Rc; rq.yc = u->d_yc;
+        rq.emit_R = 1; rq.Rc = u->d_Rc; rq.yc = u->d_yc;
         GivensRefParams gq;
         gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.f_dof = u->d_fdof; gq.n_feat = u->cur_nfeat; gq.n_feat_dev = u->cur_nfeat_dev;
         gq.n = n; gq.blk_rows = u->lay.Mc; gq.red = u->d_red; gq.rr = u->d_rr; gq.win = u->d_gwin;
         gq.emit_R = rq.emit_R; gq.Rc = u->d_Rc; gq.yc = u->d_yc;
         const int r2 = enqueue_rank_rule(s, rq, gq, n);
         if (r2 != RVIO_OK) return r2;
+    }
+    if (small && !u->legacy_small_solve) {
+        // the whole EKF step in one CTA, R-form (compress.cu: k_solve_small_R)
+        SolveSmallRParams q;
+        q.Rc = u->d_Rc; q.yc = u->d_yc; q.x = x_dev; q.P = P_dev; q.xdim = xdim; q.N = N; q.d = d; q.sig2 = u->consts.sig2;
+        q.gate = u->d_red + (size_t)n * n + n; q.x_out = x_out_dev; q.P_out = P_out_dev; q.bad = u->d_sing;
+        RVIO_ENQ(cudaMemsetAsync(u->d_sing, 0, sizeof(int), s));
+        return enqueue_solve_small_R(s, q);
     }
     if (small) {
         SolveSmallParams sp;

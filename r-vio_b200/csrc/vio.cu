@@ -470,6 +470,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
                         v->n_clones > v->min_clones && v->n_img_after_init > 1;
     FrameOutcome fo;
     int rc;
+    bool host_pinned = false;
     if (steady) {
         const int imu16 = (n_imu + 15) / 16;
         const size_t imu_bytes = 16 + sizeof(double) * 8 * 16 * (size_t)imu16;
@@ -478,25 +479,37 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         if (img_dev) {
             size_t gp; uint8_t* g = tracker_gray(v->trk, &gp);
             RVIO_CUDA_TRY(cudaMemcpy2DAsync(g, gp, img_dev, pitch, v->cfg.tracker.width, v->cfg.tracker.height, cudaMemcpyDeviceToDevice, s));
+        } else if (channels == 1) {
+            // a single-channel frame in PINNED host memory (cudaHostAlloc / cudaHostRegister by the caller) is DMA'd straight
+            // into the pipeline's gray buffer: no staging copy on the host; the frame graph then runs its "staged" variant
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, img_host) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+                size_t gp; uint8_t* g = tracker_gray(v->trk, &gp);
+                RVIO_CUDA_TRY(cudaMemcpy2DAsync(g, gp, img_host, stride, v->cfg.tracker.width, v->cfg.tracker.height, cudaMemcpyHostToDevice, s));
+                host_pinned = true;
+            } else {
+                cudaGetLastError();
+            }
         }
         if (n_cand > 0 && cand_dev_in)
             RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, cand_dev_in, sizeof(float) * 2 * n_cand, cudaMemcpyDeviceToDevice, s));
+        const bool staged_in = img_dev != nullptr || host_pinned;
         const uint64_t key = (uint64_t)use_det << 20 |
                              (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
-                             (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)(img_dev != nullptr) << 5 | (uint64_t)(channels & 7) << 6 |
+                             (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)staged_in << 5 | (uint64_t)(channels & 7) << 6 |
                              (uint64_t)(cand_dev_in != nullptr) << 9 | (uint64_t)imu16 << 10;
         auto it = v->graphs.find(key);
         const bool cand_upload = n_cand > 0 && !cand_dev_in;
         if (it != v->graphs.end()) {
             t_replay = true;
-            rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
+            rc = enqueue_frame(v, staged_in, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
                                v->d_cand, cand_upload, n_cand, v->F, cand_filtered, use_det, &fo);
             t_replay = false;
             if (rc != RVIO_OK) return rc;
             RVIO_CUDA_TRY(cudaGraphLaunch(it->second, s));
         } else {
             RVIO_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            rc = enqueue_frame(v, img_dev != nullptr, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
+            rc = enqueue_frame(v, staged_in, img_host, width, height, stride, channels, nullptr, 0, imu, n_imu, imu_bytes,
                                v->d_cand, cand_upload, n_cand, v->F, cand_filtered, use_det, &fo);
             cudaGraph_t g = nullptr;
             const cudaError_t ce = cudaStreamEndCapture(s, &g);
