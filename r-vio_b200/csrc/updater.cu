@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 
     if (tid == 0) {
         P.f_status[f] = 0; P.f_dof[f] = 0; P.f_c0[f] = 0; P.f_wc[f] = 0;
+        if (P.f_pend) P.f_pend[f] = 0;
         P.f_gamma[f] = nan("");
         P.f_pfinv[3 * f] = P.f_pfinv[3 * f + 1] = P.f_pfinv[3 * f + 2] = nan("");
         s_flag[0] = 0;
@@ -426,6 +427,32 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     const double* Hn = Hx + Nc * ld;       // projected block, dof x wc (row stride ld)
     const double* rn = rr + Nc;
 
+    if (P.gate_mode == 1) {
+        // large windows: the gate's tall product H_stack * Pcc runs on the tensor cores afterwards (k_dmma_hp, FP64 DMMA) and
+        // k_gate decides; here the projected block of EVERY triangulated feature is published, its dof kept aside
+        double* Hout = P.Hblk + (size_t)f * P.blk_rows * n;
+        double* rout = P.rblk + (size_t)f * P.blk_rows;
+        double sq = 0;
+        for (int o = tid; o < dof * n; o += kFeatThreads) {
+            const int a = o / n, c = o - a * n;
+            const int k = c - c0;
+            const double hv = (k >= 0 && k < wc) ? Hn[a * ld + k] : 0.0;
+            Hout[o] = hv;
+            sq += hv * hv;
+        }
+        for (int a = tid; a < dof; a += kFeatThreads) rout[a] = rn[a];
+        sq = warp_sum(sq);
+        if (lane == 0) s_fro[warp] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0;
+            for (int w = 0; w < kFeatThreads / 32; ++w) t += s_fro[w];
+            P.f_fro2[f] = t;
+            P.f_pend[f] = dof; P.f_c0[f] = c0; P.f_wc[f] = wc;
+        }
+        return;
+    }
+
     // ---- Mahalanobis gate, Updater.cc:404-422:  S = Hn Pcc Hn^T + s^2 I ; gamma = |r^T S^-1 r|
     for (int i = tid; i < dof * dof; i += kFeatThreads) S[i] = 0.0;
     __syncthreads();
@@ -529,6 +556,217 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         double t = 0;
         for (int w = 0; w < kFeatThreads / 32; ++w) t += s_fro[w];
         P.f_fro2[f] = t;
+    }
+}
+
+// ================================================================================================
+// Large windows: the gate's dense product on the tensor cores.
+//   k_dmma_hp   T = H_stack * Pcc    ((F * Mc) x n) * (n x n), FP64 tensor-core MMA (mma.sync m8n8k4 .f64 -> DMMA): the
+//               one genuinely dense GEMM of the update (5.2 GFLOP at configs[4]); FP64 because the accept / reject
+//               decision and the filter state must match the reference to 1e-9 -- tcgen05 has no FP64 kind.
+//               CTA tile 128 x 64, K chunks of 32 through a cp.async double buffer, 8 warps x (32 x 32) register tiles.
+//   k_gate      per feature: S = T_f H_f^T + s^2 I (only the feature's own column range), Cholesky, Mahalanobis distance,
+//               chi^2 decision (Updater.cc:404-455).
+// ================================================================================================
+constexpr int kGM = 128, kGN = 64, kGK = 32, kGLdA = kGK + 4, kGLdB = kGN + 8;
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+struct DmmaParams {
+    const double* A; int lda;     // M x K row-major
+    const double* B; int ldb;     // K x N row-major (row k at B + k * ldb)
+    double* C; int ldc;           // M x N row-major
+    int M, N, K;
+    const int* n_rows_dev; int rows_per;      // optional: M = *n_rows_dev * rows_per (device-side feature count)
+};
+
+__global__ void __launch_bounds__(256) k_dmma_hp(DmmaParams Q)
+{
+    extern __shared__ __align__(16) double gsm[];
+    double* As = gsm;                                   // [2][kGM][kGLdA]
+    double* Bs = gsm + 2 * kGM * kGLdA;                 // [2][kGK][kGLdB]
+    const int M = Q.n_rows_dev ? min(Q.M, *Q.n_rows_dev * Q.rows_per) : Q.M;
+    const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
+    if (m0 >= M) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+    const int nk = (Q.K + kGK - 1) / kGK;
+    auto load_chunk = [&](int kc, int buf) {
+        const int k0 = kc * kGK;
+        double* a = As + buf * kGM * kGLdA;
+        double* b = Bs + buf * kGK * kGLdB;
+        for (int p = tid; p < kGM * (kGK / 2); p += 256) {          // 16-byte pieces of the A tile
+            const int r = p / (kGK / 2), q = p - r * (kGK / 2);
+            const int row = m0 + r, k = k0 + 2 * q;
+            const bool ok = row < M && k < Q.K;
+            cp_async16_zfill(a + r * kGLdA + 2 * q, Q.A + (size_t)(ok ? row : 0) * Q.lda + (ok ? k : 0), ok);
+        }
+        for (int p = tid; p < kGK * (kGN / 2); p += 256) {          // B tile
+            const int r = p / (kGN / 2), q = p - r * (kGN / 2);
+            const int k = k0 + r, col = n0 + 2 * q;
+            const bool ok = k < Q.K && col < Q.N;
+            cp_async16_zfill(b + r * kGLdB + 2 * q, Q.B + (size_t)(ok ? k : 0) * Q.ldb + (ok ? col : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_chunk(0, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nk) { load_chunk(kc + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double* a = As + buf * kGM * kGLdA + (wm * 32 + g) * kGLdA + t;
+        const double* b = Bs + buf * kGK * kGLdB + t * kGLdB + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < kGK; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = a[i * 8 * kGLdA + kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b[kk * kGLdB + j * 8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm * 32 + i * 8 + g;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + wn * 32 + j * 8 + 2 * t;
+            if (col + 1 < Q.N) *reinterpret_cast<double2*>(Q.C + (size_t)row * Q.ldc + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else if (col < Q.N) Q.C[(size_t)row * Q.ldc + col] = acc[i][j][0];
+        }
+    }
+}
+
+struct GateParams {
+    const double* Hblk; const double* rblk; const double* T;      // [f][Mc][n], [f][Mc], [f][Mc][n]
+    const int32_t* f_pend; const int32_t* f_c0; const int32_t* f_wc;
+    int n_feat; const int* n_feat_dev; int n, blk_rows, rank, world;
+    double sig2; const double* chi2;
+    uint8_t* f_status; double* f_gamma; int32_t* f_dof;
+};
+
+constexpr int kGateThreads = 256;
+__global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
+{
+    extern __shared__ __align__(16) double sg[];                  // S[dof*dof], v[dof], chunk T[dof][33], chunk H[dof][33]
+    __shared__ double s_piv;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+    if (f >= n_feat || f % P.world != P.rank) return;
+    const int dof = P.f_pend[f];
+    if (dof <= 0) return;
+    const int n = P.n, c0 = P.f_c0[f], wc = P.f_wc[f];
+    double* S = sg; double* vv = S + dof * dof; double* cT = vv + dof; double* cH = cT + dof * 33;
+    const double* Hf = P.Hblk + (size_t)f * P.blk_rows * n;
+    const double* Tf = P.T + (size_t)f * P.blk_rows * n;
+    const int na = (dof + 1) / 2;
+    // S = T_f H_f^T over the feature's column range, 2 x 2 register tiles, 32-column chunks staged in shared memory
+    double acc[4][4];
+    int ta[4], tb[4], nt = 0;
+    for (int o = tid; o < na * na && nt < 4; o += kGateThreads) { ta[nt] = 2 * (o / na); tb[nt] = 2 * (o % na); ++nt; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0; }
+    for (int j0 = 0; j0 < wc; j0 += 32) {
+        const int jw = min(32, wc - j0);
+        for (int o = tid; o < dof * 32; o += kGateThreads) {
+            const int a = o >> 5, jj = o & 31;
+            const bool ok = jj < jw;
+            cT[a * 33 + jj] = ok ? Tf[(size_t)a * n + c0 + j0 + jj] : 0.0;
+            cH[a * 33 + jj] = ok ? Hf[(size_t)a * n + c0 + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < nt) {
+                const double* t0 = cT + ta[u] * 33; const double* t1 = (ta[u] + 1 < dof) ? t0 + 33 : t0;
+                const double* h0 = cH + tb[u] * 33; const double* h1 = (tb[u] + 1 < dof) ? h0 + 33 : h0;
+                for (int jj = 0; jj < 32; ++jj) {
+                    const double x0 = t0[jj], x1 = t1[jj], y0 = h0[jj], y1 = h1[jj];
+                    acc[u][0] = fma(x0, y0, acc[u][0]); acc[u][1] = fma(x0, y1, acc[u][1]);
+                    acc[u][2] = fma(x1, y0, acc[u][2]); acc[u][3] = fma(x1, y1, acc[u][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (u < nt) {
+            const int a = ta[u], b = tb[u];
+            S[a * dof + b] = acc[u][0];
+            if (b + 1 < dof) S[a * dof + b + 1] = acc[u][1];
+            if (a + 1 < dof) { S[(a + 1) * dof + b] = acc[u][2]; if (b + 1 < dof) S[(a + 1) * dof + b + 1] = acc[u][3]; }
+        }
+    __syncthreads();
+    // symmetrise + noise (Updater.cc:417-418)
+    for (int o = tid; o < dof * dof; o += kGateThreads) {
+        const int a = o / dof, b = o - a * dof;
+        if (a <= b) {
+            double v = .5 * (S[a * dof + b] + S[b * dof + a]);
+            if (a == b) v = S[a * dof + a] + P.sig2;
+            S[a * dof + b] = v;
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < dof * dof; o += kGateThreads) {
+        const int a = o / dof, b = o - a * dof;
+        if (a > b) S[a * dof + b] = S[b * dof + a];
+    }
+    __syncthreads();
+    for (int j = 0; j < dof; ++j) {                                // Cholesky S = L L^T (lower)
+        if (tid == 0) { const double dj = S[j * dof + j]; s_piv = (dj > 0) ? sqrt(dj) : nan(""); }
+        __syncthreads();
+        const double dj = s_piv;
+        for (int i = j + tid; i < dof; i += kGateThreads) S[i * dof + j] = (i == j) ? dj : S[i * dof + j] / dj;
+        __syncthreads();
+        const int rem = dof - j - 1;
+        for (int o = tid; o < rem * rem; o += kGateThreads) {
+            const int a = j + 1 + o / rem, b = j + 1 + o % rem;
+            if (b <= a) S[a * dof + b] -= S[a * dof + j] * S[b * dof + j];
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {                                               // gamma = |L^-1 r|^2
+        const double* rn = P.rblk + (size_t)f * P.blk_rows;
+        double gamma = 0;
+        for (int i = 0; i < dof; ++i) {
+            double part = 0;
+            for (int k = lane; k < i; k += 32) part += S[i * dof + k] * vv[k];
+            part = warp_sum(part);
+            const double y = (rn[i] - part) / S[i * dof + i];
+            if (lane == 0) vv[i] = y;
+            __syncwarp();
+            gamma += y * y;
+        }
+        if (lane == 0) {
+            gamma = fabs(gamma);
+            P.f_gamma[f] = gamma;
+            const bool ok = gamma < P.chi2[dof - 1];
+            if (!ok) P.f_status[f] = 3;
+            P.f_dof[f] = ok ? dof : 0;
+        }
     }
 }
 
@@ -644,6 +882,128 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
         __syncthreads();
         double* cls = red + (size_t)n * n + n + 8;
         for (int c = threadIdx.x; c <= n; c += 256) cls[c] = s_cls[c];
+    }
+}
+
+// Normal terms on the tensor cores (large windows): the same two-stage deterministic reduction as k_gram, 64 x 64 tiles of
+// the UPPER triangle of G (mirrored by the reducing CTA), the products through FP64 DMMA (A(i,k) = H(k,i), B(k,j) = H(k,j):
+// both fragments come from the same k-major row chunk in shared memory).  128 threads = 4 warps x (32 x 32).
+constexpr int kGramT = 64, kGramLd = kGramT + 8, kGramRows = 32;
+__global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
+{
+    __shared__ __align__(16) double sI[kGramRows][kGramLd], sJ[kGramRows][kGramLd];
+    __shared__ double s_r[kGramRows];
+    __shared__ int s_last;
+    __shared__ double s_cls[192];
+    const int n = P.n, nt = P.nt, g = blockIdx.y;
+    // upper-triangle tile pair from the linear index
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+    const int tj = ti + rem;
+    const int i0 = ti * kGramT, j0 = tj * kGramT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, gq = lane >> 2, t = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0; acc[a][b][1] = 0; }
+    double zacc = 0;
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+    for (int f = g; f < n_feat; f += P.groups) {
+        const int dof = P.f_dof[f];
+        if (dof <= 0) continue;
+        const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
+        if (i0 >= c1 || i0 + kGramT <= c0 || j0 >= c1 || j0 + kGramT <= c0) continue;     // block is zero on this tile
+        const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+        const double* rv = P.rblk + (size_t)f * P.blk_rows;
+        for (int a0 = 0; a0 < dof; a0 += kGramRows) {
+            for (int o = tid; o < kGramRows * kGramT; o += 128) {
+                const int r = o / kGramT, c = o - r * kGramT;
+                const int a = a0 + r;
+                const bool rok = a < dof;
+                sI[r][c] = (rok && i0 + c < n) ? H[(size_t)a * n + i0 + c] : 0.0;
+                sJ[r][c] = (rok && j0 + c < n) ? H[(size_t)a * n + j0 + c] : 0.0;
+            }
+            if (ti == tj && tid < kGramRows) s_r[tid] = (a0 + tid < dof) ? rv[a0 + tid] : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < kGramRows; kk += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) af[a] = sI[kk + t][wm * 32 + a * 8 + gq];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = sJ[kk + t][wn * 32 + b * 8 + gq];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma_8x8x4(acc[a][b], af[a], bf[b]);
+            }
+            if (ti == tj && tid < kGramT) {
+#pragma unroll 8
+                for (int r = 0; r < kGramRows; ++r) zacc = fma(sI[r][tid], s_r[r], zacc);
+            }
+            __syncthreads();
+        }
+    }
+    double* Gp = P.Gpart + (size_t)g * n * n;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + wm * 32 + a * 8 + gq, j = j0 + wn * 32 + b * 8 + 2 * t;
+            if (i < n && j < n) Gp[(size_t)i * n + j] = acc[a][b][0];
+            if (i < n && j + 1 < n) Gp[(size_t)i * n + j + 1] = acc[a][b][1];
+        }
+    if (ti == tj && tid < kGramT && i0 + tid < n) P.zpart[(size_t)g * n + i0 + tid] = zacc;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int tk = atomicAdd(&tickets[blockIdx.x], 1);
+        s_last = (tk == P.groups - 1) ? 1 : 0;
+        if (s_last) tickets[blockIdx.x] = 0;           // self-reset for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < kGramT * kGramT; e += 128) {
+        const int i = i0 + e / kGramT, j = j0 + e % kGramT;
+        if (i < n && j < n && (ti != tj || j >= i)) {           // diagonal tiles: the DMMA order of (i,j) and (j,i) differs -> take the upper part
+            double sum = 0;
+#pragma unroll 8
+            for (int gg = 0; gg < P.groups; ++gg) sum += P.Gpart[(size_t)gg * n * n + (size_t)i * n + j];
+            red[(size_t)i * n + j] = sum;
+            red[(size_t)j * n + i] = sum;                        // mirror: G bitwise symmetric
+        }
+    }
+    if (ti == tj && tid < kGramT && i0 + tid < n) {
+        double sum = 0;
+        for (int gg = 0; gg < P.groups; ++gg) sum += P.zpart[(size_t)gg * n + i0 + tid];
+        red[(size_t)n * n + i0 + tid] = sum;
+    }
+    if (blockIdx.x == 0 && tid == 64) {
+        int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
+        for (int f = rank; f < n_feat; f += world) {
+            loc++;
+            const int st = f_status[f];
+            if (st == 0) { good++; rows += P.f_dof[f]; }
+            else if (st == 1) r1++;
+            else if (st == 2) r2++;
+            else r3++;
+        }
+        double* c = red + (size_t)n * n + n;
+        c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = tid; c <= n; c += 128) {
+            double a2 = 0;
+            for (int f = rank; f < n_feat; f += world)
+                if (P.f_dof[f] > 0 && P.f_c0[f] == c) a2 += P.f_fro2[f];
+            s_cls[c] = a2;
+        }
+        __syncthreads();
+        double* cls = red + (size_t)n * n + n + 8;
+        for (int c = tid; c <= n; c += 128) cls[c] = s_cls[c];
     }
 }
 
@@ -1233,7 +1593,8 @@ struct rvio_updater {
     // device
     double *d_x, *d_P, *d_xout, *d_Pout, *d_Pnew, *d_dx;
     uint8_t* d_types; int32_t* d_off; float2* d_xy;
-    uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma, *d_ffro2; int32_t *d_fdof, *d_fc0, *d_fwc;
+    uint8_t* d_fstatus; double *d_fpfinv, *d_fgamma, *d_ffro2, *d_Tg; int32_t *d_fdof, *d_fc0, *d_fwc, *d_fpend;
+    int gate_tensor_min_n;      // windows with n >= this run the gate's H_stack * Pcc product on the tensor cores (FP64 DMMA)
     double *d_Hblk, *d_rblk, *d_Gpart, *d_zpart, *d_red, *d_M, *d_R, *d_chi2, *d_T, *d_Yt;
     int* d_sing; int* d_tickets;
     int* d_rule; int32_t* d_rr; double *d_L, *d_gwin, *d_Rc, *d_yc, *d_S, *d_LS, *d_W;      // reference compression rule + R-form EKF step (compress.cu)
@@ -1320,12 +1681,17 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     if (u->lay.total_bytes > 200 * 1024) { set_error("rvio_updater_create", "max_track_len too large for shared memory"); return RVIO_ERR_CAPACITY; }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_dmma_hp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * kGM * kGLdA + 2 * kGK * kGLdB))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)u->lay.Dc * u->lay.Dc + u->lay.Dc + 66 * u->lay.Dc + 8))));
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
-    u->groups_cap = 16;
+    u->groups_cap = cfg->max_clones * 6 >= 96 ? 48 : 16;      // partial normal terms per tile (the tensor-core variant spreads wider)
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
     A(u->d_x, u->xmax); A(u->d_xout, u->xmax); A(u->d_P, d * d); A(u->d_Pout, d * d); A(u->d_Pnew, d * d); A(u->d_dx, d);
     A(u->d_types, F + 1); A(u->d_off, F + 2); A(u->d_xy, F * u->Lmax + 1);
-    A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1); A(u->d_ffro2, F + 1);
+    A(u->d_fstatus, F + 1); A(u->d_fpfinv, 3 * F + 3); A(u->d_fgamma, F + 1); A(u->d_fdof, F + 1); A(u->d_fc0, F + 1); A(u->d_fwc, F + 1); A(u->d_ffro2, F + 1); A(u->d_fpend, F + 1);
+    u->gate_tensor_min_n = 96;
+    { const char* e = getenv("RVIO_B200_GATE_TENSOR_MIN_N"); if (e) u->gate_tensor_min_n = atoi(e); }
+    if ((int)n >= u->gate_tensor_min_n) { A(u->d_Tg, F * Mc * n); } else u->d_Tg = nullptr;
     A(u->d_Hblk, F * Mc * n); A(u->d_rblk, F * Mc);
     A(u->d_Gpart, (size_t)u->groups_cap * n * n); A(u->d_zpart, (size_t)u->groups_cap * n);
     A(u->d_red, n * n + n + 8 + n + 1); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
@@ -1383,13 +1749,34 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
             RVIO_ENQ(cudaMemsetAsync(u->d_fdof, 0, sizeof(int32_t) * n_feat_cap, s));
             RVIO_ENQ(cudaMemsetAsync(u->d_fstatus, 0xff, n_feat_cap, s));
         }
+        const bool tensor_gate = u->d_Tg != nullptr && n >= u->gate_tensor_min_n;
+        fp.gate_mode = tensor_gate ? 1 : 0; fp.f_pend = u->d_fpend;
         RVIO_LAUNCH(k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
+        if (tensor_gate) {
+            // Updater.cc:416: the per-feature products H~ Pcc as ONE tall GEMM on the tensor cores, then the per-feature gate
+            DmmaParams dq;
+            dq.A = u->d_Hblk; dq.lda = n; dq.B = P_dev + (size_t)24 * d + 24; dq.ldb = d; dq.C = u->d_Tg; dq.ldc = n;
+            dq.M = n_feat_cap * u->lay.Mc; dq.N = n; dq.K = n; dq.n_rows_dev = n_feat_dev; dq.rows_per = u->lay.Mc;
+            RVIO_LAUNCH(k_dmma_hp, dim3(div_up(dq.M, kGM), div_up(n, kGN)), 256, sizeof(double) * (2 * kGM * kGLdA + 2 * kGK * kGLdB), s, dq);
+            GateParams gq;
+            gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.T = u->d_Tg; gq.f_pend = u->d_fpend; gq.f_c0 = u->d_fc0; gq.f_wc = u->d_fwc;
+            gq.n_feat = n_feat_cap; gq.n_feat_dev = n_feat_dev; gq.n = n; gq.blk_rows = u->lay.Mc; gq.rank = rank; gq.world = world;
+            gq.sig2 = u->consts.sig2; gq.chi2 = u->d_chi2; gq.f_status = u->d_fstatus; gq.f_gamma = u->d_fgamma; gq.f_dof = u->d_fdof;
+            const int Dc = u->lay.Dc;
+            RVIO_LAUNCH(k_gate, n_feat_cap, kGateThreads, sizeof(double) * ((size_t)Dc * Dc + Dc + 66 * Dc + 8), s, gq);
+        }
         GramParams gp;
         gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc; gp.f_fro2 = u->d_ffro2;
         gp.n_feat = n_feat_cap; gp.n_feat_dev = n_feat_dev; gp.n = n; gp.blk_rows = u->lay.Mc;
-        gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
+        gp.groups = n_feat_cap < 16 ? n_feat_cap : 16;
         gp.nt = div_up(n, 32); gp.Gpart = u->d_Gpart; gp.zpart = u->d_zpart;
-        RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
+        if (tensor_gate) {
+            gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
+            gp.nt = div_up(n, kGramT);
+            RVIO_LAUNCH(k_gram_dmma, dim3(gp.nt * (gp.nt + 1) / 2, gp.groups), 128, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
+        } else {
+            RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
+        }
     } else {
         RVIO_ENQ(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8 + n + 1), s));
     }

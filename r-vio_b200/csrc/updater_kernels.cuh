@@ -38,6 +38,8 @@ struct FeatureParams {
     // outputs
     uint8_t* f_status; double* f_pfinv; double* f_gamma; int32_t* f_dof; int32_t* f_c0; int32_t* f_wc; double* f_fro2;
     double* Hblk; double* rblk;                 // per-feature projected blocks: [f][Mc][n], [f][Mc]
+    int gate_mode;                              // 0: chi^2 gate inside k_feature; 1: publish every triangulated block, k_dmma_hp + k_gate decide
+    int32_t* f_pend;                            // gate_mode 1: dof of the block waiting for its gate
     int blk_rows;                               // Mc
     UpdaterConsts c;
     FeatLayout lay;

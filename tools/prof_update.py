@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Small driver for ncu: runs Updater::update on a worst-case shaped case a few times.
+    ncu --set full --import-source on -k regex:'k_chol_S|k_rank_rule|k_solve_small_R' -c 6 -o gpurun_out/prof python tools/prof_update.py 1 2
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rvio_b200  # noqa: E402,F401
+from rvio_b200 import synth, host  # noqa: E402
+
+for idx in [int(a) for a in sys.argv[1:]] or [1]:
+    cfg = synth.baseline_config(idx)
+    nf = min((cfg.n_features + 1) // 2, 256)
+    x, P, types, off, xy = synth.make_update_case(cfg, nf, 900 + idx, mix_types=False)
+    upd = host.Updater(cfg)
+    for _ in range(3):
+        upd.update(x, P, types, (off, xy))
+    print(idx, upd.info.n_good, upd.info.rows_stacked, upd.info.rank, upd.info.rank_flags)
+    upd.close()
