@@ -189,8 +189,10 @@ __device__ __forceinline__ void sf_load(double (&a)[4][8], const SFTile& T, cons
 // With Q.emit_R the kept rows (scaled, zero padded to n x n) and y are also written out: the large-window EKF step works on
 // them (R-form: S = R Pcc R^T + s^2 I).
 // ------------------------------------------------------------------------------------------------
+template <bool SMALL>
 __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 {
+    extern __shared__ __align__(16) double rsm[];            // SMALL: the factor itself, Np x ld (one thread per row)
     __shared__ double s_col[2][kSFColLen];
     __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows], s_diag[kSFMaxRows];
     __shared__ int s_np, s_k, s_smin, s_ncls;
@@ -233,47 +235,98 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
     const bool raw_top = rule && s_smin > 0 && s_ncls > 1;
     const bool boundaries = rule && s_smin == 0 && !raw_top;
 
-    const SFTile T = sf_tile_of(tid, Np + 1);
-    double a[4][8];
-    sf_load(a, T, G, n, Np, Q.red + (size_t)n * n, 1);
-    const int ldl = n + 1;
-    double* L = Q.L;                                              // columns of the lower factor == rows of R, plus y at index Np
+    const int ldl = SMALL ? ((Np + 2) | 1) : (n + 1);
+    double* L = SMALL ? rsm : Q.L;                                // columns of the lower factor == rows of R, plus y at index Np
     int q = 0, first_dep = Np;                                    // (thread-uniform copies)
     int mode = 1, kcut = 0;
     bool undecided = false;
     auto after_pivot = [&](int j, bool dep) { if (!dep) q++; else if (first_dep == Np) first_dep = j; };
-    auto on_column = [&](int j) -> bool {
-        if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {   // a class of features starts here (cls[j] > 0)
-            // information left in the active rows = trace of the current Schur complement minus what has not started yet
-            if (T.valid && T.tr * 4 <= T.c0 + 7 && T.r0 + 3 >= T.c0) {          // tiles crossing the diagonal
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 8; ++y)
-                        if (T.r0 + x == T.c0 + y && T.r0 + x < Np) s_diag[T.r0 + x] = a[x][y];
-            }
-            __syncthreads();
-            if (warp == 0) {
-                double t = 0;
-                for (int k = j + lane; k < Np; k += 32) t += s_diag[k];
-                t = warp_sum_d(t);
-                if (lane == 0) s_tau = t - s_late[j];
-            }
-            __syncthreads();
-            const double tau = s_tau;
-            const int dd = j - q;
-            if (dd >= 1) {
-                if (tau < 1e-8) { mode = 2; kcut = j; return false; }                // exhausted: the reference cuts, later classes are discarded
-                if (tau < 1e-3 || dd >= 2) {                                        // only the reference's own sweep can tell
-                    if (Q.world == 1) { mode = 3; return false; }
-                    undecided = true;                                               // feature-sharded: keep everything, say so
-                }
+    // class-boundary test (see above); tau = trace of the current Schur complement - information that has not started yet
+    auto boundary_decision = [&](int j, double tau) -> bool {
+        const int dd = j - q;
+        if (dd >= 1) {
+            if (tau < 1e-8) { mode = 2; kcut = j; return false; }                // exhausted: the reference cuts, later classes are discarded
+            if (tau < 1e-3 || dd >= 2) {                                        // only the reference's own sweep can tell
+                if (Q.world == 1) { mode = 3; return false; }
+                undecided = true;                                               // feature-sharded: keep everything, say so
             }
         }
         return true;
     };
-    auto store_L = [&](int j, int i, double v, double) { L[(size_t)j * ldl + i] = v; };
-    const int jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], store_L, s_pv, s_gd, nullptr, on_column, after_pivot);
+    int jstop = Np;
+    if (SMALL) {
+        // ---- small windows: ONE THREAD PER ROW of the upper factor in shared memory.  Per step a thread walks its own row
+        //      (U(i,k) -= U(j,i) / p * U(j,k), k = i .. N', plus the right-hand side): the cost of a step is the length of the
+        //      remaining row, not a fixed block-wide round trip -- ~N'^2 / 2 shared-memory updates in total.
+        double* U = rsm;
+        for (int o = tid; o < Np * (Np + 1); o += kSFThreads) {
+            const int i = o / (Np + 1), k = o - i * (Np + 1);
+            if (k >= i) U[i * ldl + k] = (k < Np) ? G[(size_t)i * n + k] : Q.red[(size_t)n * n + i];
+        }
+        __syncthreads();
+        for (int j = 0; j < Np; ++j) {
+            if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {
+                if (warp == 0) {
+                    double t = 0;
+                    for (int k = j + lane; k < Np; k += 32) t += U[k * ldl + k];
+                    t = warp_sum_d(t);
+                    if (lane == 0) s_tau = t - s_late[j];
+                }
+                __syncthreads();
+                const double tau = s_tau;
+                __syncthreads();
+                if (!boundary_decision(j, tau)) { jstop = j; break; }
+            }
+            const double pj = U[j * ldl + j];
+            const bool dep = !(pj >= fmax(1e-12, 1e-12 * s_gd[j]));
+            if (tid == 0) s_pv[j] = dep ? -1.0 : pj;
+            after_pivot(j, dep);
+            if (dep) continue;                                     // nothing changes: no barrier needed
+            const int i = j + 1 + tid;
+            if (i < Np) {
+                const double f = U[j * ldl + i] / pj;
+                const double* rj = U + j * ldl;
+                double* ri = U + i * ldl;
+                for (int k = i; k <= Np; ++k) ri[k] = fma(-f, rj[k], ri[k]);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // rows of R: U(j, j..) / sqrt(p_j); the right-hand side becomes y
+        for (int j = warp; j < jstop; j += kSFThreads / 32) {
+            if (s_pv[j] < 0.0) continue;
+            const double rs = rsqrt(s_pv[j]);
+            for (int k = j + lane; k <= Np; k += 32) U[j * ldl + k] *= rs;
+        }
+    } else {
+        const SFTile T = sf_tile_of(tid, Np + 1);
+        double a[4][8];
+        sf_load(a, T, G, n, Np, Q.red + (size_t)n * n, 1);
+        auto on_column = [&](int j) -> bool {
+            if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {   // a class of features starts here (cls[j] > 0)
+                if (T.valid && T.tr * 4 <= T.c0 + 7 && T.r0 + 3 >= T.c0) {          // tiles crossing the diagonal
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 8; ++y)
+                            if (T.r0 + x == T.c0 + y && T.r0 + x < Np) s_diag[T.r0 + x] = a[x][y];
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    double t = 0;
+                    for (int k = j + lane; k < Np; k += 32) t += s_diag[k];
+                    t = warp_sum_d(t);
+                    if (lane == 0) s_tau = t - s_late[j];
+                }
+                __syncthreads();
+                const double tau = s_tau;
+                return boundary_decision(j, tau);
+            }
+            return true;
+        };
+        auto store_L = [&](int j, int i, double v, double) { L[(size_t)j * ldl + i] = v; };
+        jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], store_L, s_pv, s_gd, nullptr, on_column, after_pivot);
+    }
     __syncthreads();
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
     const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
@@ -436,36 +489,38 @@ __device__ __forceinline__ void sr_apply_dq(const double* dth, const double* q, 
     sr_quat_mul(dq, q, out);
 }
 
-__global__ void __launch_bounds__(kSFThreads, 1) k_solve_small_R(SolveSmallRParams Q)
+constexpr int kSRThreads = 256;
+__global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRParams Q)
 {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double s_col[2][kSFColLen];
-    __shared__ double s_pv[kSFMaxRows];
+    __shared__ double s_rs[kSFMaxRows];
     __shared__ double s_dx[kSFMaxRows];
     const int tid = threadIdx.x;
     const int N = Q.N, n = 6 * N, d = Q.d;
     if (!(Q.gate[0] > 2.0)) {                                      // Updater.cc:621-627: too few features, posterior = prior
-        for (int o = tid; o < d * d; o += kSFThreads) Q.P_out[o] = Q.P[o];
-        for (int o = tid; o < Q.xdim; o += kSFThreads) Q.x_out[o] = Q.x[o];
+        for (int o = tid; o < d * d; o += kSRThreads) Q.P_out[o] = Q.P[o];
+        for (int o = tid; o < Q.xdim; o += kSRThreads) Q.x_out[o] = Q.x[o];
         return;
     }
-    const int ldr = n + 1, ldp = d | 1, ldw = (d + 1) | 1;
-    double* sR = sm;                                               // n x ldr
-    double* sP = sR + (size_t)n * ldr;                             // n x ldp: P[c,:]   -- later S (n x ldr)
-    double* sW = sP + (size_t)n * ldp;                             // n x ldw: [W | y]  -- later Y (columns of the factor, extra rows only)
-    double* sS = sP;
-    for (int o = tid; o < n * n; o += kSFThreads) { const int r = o / n, c = o - r * n; sR[r * ldr + c] = Q.Rc[o]; }
-    for (int o = tid; o < n * d; o += kSFThreads) { const int j = o / n, k = o - j * n; sP[k * ldp + j] = Q.P[(size_t)j * d + 24 + k]; }   // P(24+k, j)
+    // A: (n + d + 1) x lda.  Rows 0..n-1: lower triangle of S, then of its Cholesky factor.  Rows n + c: column c of [W | y],
+    // after the factorisation column c of Y = L^-1 [W | y] (the right-hand sides ride along as extra rows).
+    const int rows_total = n + d + 1;
+    const int lda = n + 1, ldp = d + 1;                            // both odd: rows of consecutive threads fall into different banks
+    double* A = sm;
+    double* sR = A + (size_t)rows_total * lda;                     // n x lda
+    double* sP = sR + (size_t)n * lda;                             // n x ldp: P[c,:]
+    for (int o = tid; o < n * n; o += kSRThreads) { const int r = o / n, c = o - r * n; sR[r * lda + c] = Q.Rc[o]; }
+    for (int o = tid; o < n * d; o += kSRThreads) { const int j = o / n, k = o - j * n; sP[k * ldp + j] = Q.P[(size_t)j * d + 24 + k]; }   // P(24+k, j)
     __syncthreads();
-    // ---- W = R P[c,:]   (R upper triangular: k starts at the row index)
+    // ---- W = R P[c,:]  (R upper triangular), written transposed into the extra rows of A
     {
         const int tr_n = (n + 1) / 2, tc_n = (d + 3) / 4;
-        for (int t = tid; t < tr_n * tc_n; t += kSFThreads) {
+        for (int t = tid; t < tr_n * tc_n; t += kSRThreads) {
             const int r0 = 2 * (t / tc_n), j0 = 4 * (t % tc_n);
             double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
             const bool r1ok = r0 + 1 < n;
             for (int k = r0; k < n; ++k) {
-                const double a0 = sR[r0 * ldr + k], a1 = r1ok ? sR[(r0 + 1) * ldr + k] : 0.0;
+                const double a0 = sR[r0 * lda + k], a1 = r1ok ? sR[(r0 + 1) * lda + k] : 0.0;
                 const double* pk = sP + k * ldp + j0;
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
@@ -476,69 +531,87 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_solve_small_R(SolveSmallRPara
             }
 #pragma unroll
             for (int y = 0; y < 4; ++y)
-                if (j0 + y < d) { sW[r0 * ldw + j0 + y] = acc[0][y]; if (r1ok) sW[(r0 + 1) * ldw + j0 + y] = acc[1][y]; }
+                if (j0 + y < d) { A[(n + j0 + y) * lda + r0] = acc[0][y]; if (r1ok) A[(n + j0 + y) * lda + r0 + 1] = acc[1][y]; }
         }
-        for (int r = tid; r < n; r += kSFThreads) sW[r * ldw + d] = Q.yc[r];
+        for (int r = tid; r < n; r += kSRThreads) A[(n + d) * lda + r] = Q.yc[r];
     }
     __syncthreads();
-    // ---- S = W[:, 24:] R^T + s^2 I  (lower triangle; R[c][k] = 0 for k < c)
+    // ---- S = W[:, 24:] R^T + s^2 I  (lower triangle; R[c][k] = 0 for k < c) into rows 0..n-1 of A
     {
         const int tn = (n + 1) / 2, tcn = (n + 3) / 4;
-        for (int t = tid; t < tn * tcn; t += kSFThreads) {
+        for (int t = tid; t < tn * tcn; t += kSRThreads) {
             const int r0 = 2 * (t / tcn), c0 = 4 * (t % tcn);
             if (c0 > r0 + 1) continue;                              // tile entirely above the diagonal
             double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
             const bool r1ok = r0 + 1 < n;
             for (int k = c0; k < n; ++k) {
-                const double w0 = sW[r0 * ldw + 24 + k], w1 = r1ok ? sW[(r0 + 1) * ldw + 24 + k] : 0.0;
+                const double* wk = A + (n + 24 + k) * lda;          // W(:, 24 + k)
+                const double w0 = wk[r0], w1 = r1ok ? wk[r0 + 1] : 0.0;
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
-                    const double b = (c0 + y < n) ? sR[(c0 + y) * ldr + k] : 0.0;
+                    const double b = (c0 + y < n) ? sR[(c0 + y) * lda + k] : 0.0;
                     acc[0][y] = fma(w0, b, acc[0][y]);
                     acc[1][y] = fma(w1, b, acc[1][y]);
                 }
             }
-            // sS aliases sP: every thread is past the W product (barrier above)
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 const int c = c0 + y;
                 if (c < n) {
-                    if (c <= r0) sS[r0 * ldr + c] = acc[0][y] + (c == r0 ? Q.sig2 : 0.0);
-                    if (r1ok && c <= r0 + 1) sS[(r0 + 1) * ldr + c] = acc[1][y] + (c == r0 + 1 ? Q.sig2 : 0.0);
+                    if (c <= r0) A[r0 * lda + c] = acc[0][y] + (c == r0 ? Q.sig2 : 0.0);
+                    if (r1ok && c <= r0 + 1) A[(r0 + 1) * lda + c] = acc[1][y] + (c == r0 + 1 ? Q.sig2 : 0.0);
                 }
             }
         }
     }
     __syncthreads();
-    // ---- Cholesky of S with [W | y]^T as extra rows: the extra rows of column j of the factor are Y(j, :)
-    const int rows_total = n + d + 1;
-    const SFTile T = sf_tile_of(tid, rows_total);
-    double a[4][8];
-    sf_load_fn(a, T, n, rows_total, [&](int r, int c) { return (r < n) ? sS[r * ldr + c] : sW[c * ldw + (r - n)]; });
-    __syncthreads();                                               // W is in registers: its storage becomes Y
-    double* sY = sW;
-    auto store_Y = [&](int j, int i, double v, double) { if (i >= n) sY[j * ldw + (i - n)] = v; };
-    sym_factor<false>(a, T, n, d + 1, &s_col[0][0], store_Y, s_pv, nullptr, Q.bad, [](int) { return true; }, [](int, bool) {});
+    // ---- right-looking Cholesky, ONE THREAD PER ROW (rows of S and the extra rows alike): at step j row i does
+    //      A(i,k) -= A(i,j) / p * A(k,j) for k = j+1 .. min(i, n-1).  Columns stay unscaled until the end (every thread reads
+    //      column j while its owners would be rescaling it).  One barrier per step; the work of a step is the remaining row.
+    {
+        const int i = tid;
+        for (int j = 0; j < n; ++j) {
+            const double p = A[j * lda + j];
+            if (!(p > 0.0)) { if (tid == 0) *Q.bad = 1; }
+            if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
+            if (i > j && i < rows_total && p > 0.0) {
+                double* ri = A + i * lda;
+                const double f = ri[j] / p;
+                const int kmax = min(i, n - 1);
+                const double* cj = A + j;                          // column j: A(k, j) = cj[k * lda]
+                for (int k = j + 1; k <= kmax; ++k) ri[k] = fma(-f, cj[k * lda], ri[k]);
+            }
+            __syncthreads();
+        }
+        for (int o = tid; o < rows_total * n; o += kSRThreads) {   // scale the columns: L(i,j) = A(i,j) / sqrt(p_j)
+            const int r = o / n, c = o - r * n;
+            if (c <= r) A[r * lda + c] *= s_rs[c];
+        }
+    }
     __syncthreads();
-    // ---- dx = Y^T y~
-    for (int i = tid; i < d; i += kSFThreads) {
+    // ---- dx = Y^T y~ ;  Y(j, c) = A(n + c, j)
+    for (int c = tid; c < d; c += kSRThreads) {
+        const double* yc_ = A + (n + c) * lda; const double* yd = A + (n + d) * lda;
         double acc = 0;
-        for (int k = 0; k < n; ++k) acc = fma(sY[k * ldw + i], sY[k * ldw + d], acc);
-        s_dx[i] = acc;
+        for (int k = 0; k < n; ++k) acc = fma(yc_[k], yd[k], acc);
+        s_dx[c] = acc;
     }
     // ---- P+ = sym(P) - Y^T Y
     {
         const int tn = (d + 1) / 2, tcn = (d + 3) / 4;
-        for (int t = tid; t < tn * tcn; t += kSFThreads) {
+        for (int t = tid; t < tn * tcn; t += kSRThreads) {
             const int i0 = 2 * (t / tcn), j0 = 4 * (t % tcn);
             double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
             const bool i1ok = i0 + 1 < d;
+            const double* u0p = A + (n + i0) * lda; const double* u1p = i1ok ? u0p + lda : u0p;
+            const double* vp[4];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) vp[y] = A + (n + min(j0 + y, d - 1)) * lda;
             for (int k = 0; k < n; ++k) {
-                const double* yk = sY + k * ldw;
-                const double u0 = yk[i0], u1 = i1ok ? yk[i0 + 1] : 0.0;
+                const double u0 = u0p[k], u1 = u1p[k];
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
-                    const double b = (j0 + y < d) ? yk[j0 + y] : 0.0;
+                    const double b = vp[y][k];
                     acc[0][y] = fma(u0, b, acc[0][y]);
                     acc[1][y] = fma(u1, b, acc[1][y]);
                 }
@@ -555,7 +628,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_solve_small_R(SolveSmallRPara
     __syncthreads();
     // ---- state correction (Updater.cc:546-613)
     const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
-    for (int bq = tid; bq < 2 + N; bq += kSFThreads) {
+    for (int bq = tid; bq < 2 + N; bq += kSRThreads) {
         int xq, eq;
         if (bq == 0) { xq = 0; eq = 0; }
         else if (bq == 1) { xq = 10; eq = 9; }
@@ -758,11 +831,18 @@ size_t givens_smem_bytes(int n, bool* smem_window)
 
 size_t solve_small_smem_bytes(int n, int d)
 {
-    return sizeof(double) * ((size_t)n * (n + 1) + (size_t)n * (d | 1) + (size_t)n * ((d + 1) | 1) + 16);
+    return sizeof(double) * ((size_t)(n + d + 1) * (n + 1) + (size_t)n * (n + 1) + (size_t)n * (d + 1) + 16);
 }
+
+constexpr int kRankSmallMaxN = 96;        // windows up to 16 clones: one thread per row of the factor in shared memory
+constexpr int kSolveSmallRMaxN = 72;      // windows up to 12 clones: the whole EKF step in one CTA (197 KB of shared memory)
 
 int compress_configure(int nmax)
 {
+    {
+        const int ns = nmax < kRankSmallMaxN ? nmax : kRankSmallMaxN;
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)ns * ((ns + 2) | 1) + 8))));
+    }
     // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
     // given the largest dynamic shared memory it can be launched with
     bool w;
@@ -773,7 +853,7 @@ int compress_configure(int nmax)
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_givens_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv));
     {
-        const int ns = nmax < 78 ? nmax : 78;
+        const int ns = nmax < kSolveSmallRMaxN ? nmax : kSolveSmallRMaxN;
         RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small_R, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem_bytes(ns, 24 + ns)));
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + nmax + 8))));
@@ -784,7 +864,8 @@ int compress_configure(int nmax)
 int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq_in, int n)
 {
     if (n + 1 > kSFMaxRows) { set_error("enqueue_rank_rule", "window too large"); return RVIO_ERR_CAPACITY; }
-    RVIO_LAUNCH(k_rank_rule, 1, kSFThreads, 0, s, rq);
+    if (n <= kRankSmallMaxN) RVIO_LAUNCH(k_rank_rule<true>, 1, kSFThreads, sizeof(double) * ((size_t)n * ((n + 2) | 1) + 8), s, rq);
+    else RVIO_LAUNCH(k_rank_rule<false>, 1, kSFThreads, 0, s, rq);
     if (rq.world == 1) {
         bool w;
         const size_t gv = givens_smem_bytes(n, &w);
@@ -799,8 +880,8 @@ int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefP
 int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
 {
     const int n = 6 * q.N;
-    if (n + q.d + 1 > kSFMaxRows) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
-    RVIO_LAUNCH(k_solve_small_R, 1, kSFThreads, solve_small_smem_bytes(n, q.d), s, q);
+    if (n > kSolveSmallRMaxN || n + q.d + 1 > kSRThreads) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_solve_small_R, 1, kSRThreads, solve_small_smem_bytes(n, q.d), s, q);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

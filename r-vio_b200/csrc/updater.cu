@@ -143,7 +143,7 @@ __device__ __forceinline__ void d_solve3(const double* A_, const double* b_, dou
 // k_feature: one CTA (128 threads) per feature
 // ================================================================================================
 constexpr int kFeatThreads = 256;
-constexpr int kSolveSmallMaxClones = 13;     // n = 84: M + R + P[c,:] (+ pivot row / column) fit in 227 KB of shared memory
+constexpr int kSolveSmallMaxClones = 12;     // n = 72: the single-CTA EKF step (k_solve_small_R) fits in 227 KB of shared memory
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
