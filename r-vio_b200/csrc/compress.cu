@@ -46,125 +46,15 @@ __device__ __forceinline__ double warp_sum_d(double v)
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Register-resident symmetric factorisation engine (one CTA, kSFThreads threads).
-//
-// The lower triangle of a symmetric m x m matrix (m <= 188, optionally one extra row carrying a right-hand side) lives in
-// 4 x 8 register tiles, one tile per thread: the rank-1 update of a right-looking Cholesky step then costs 12 shared-memory
-// reads and 32 DFMAs per thread instead of three shared-memory accesses per DFMA.  Per step: the owners of column j publish
-// it to shared memory (double buffered -> ONE barrier per step), every thread reads the pivot, decides (uniformly) whether
-// the column is dependent (skipped, nothing changes) and otherwise scales the column by 1/sqrt(pivot), writes it out as
-// column j of the lower factor L (= row j of the upper factor R) and updates its tile.
-// Used for the pivot-free Cholesky of G (rank rule; right-hand side z -> y with R^T y = z) and for the Cholesky of the
-// innovation matrix S of the large-window EKF step.
+// Single-CTA factorisations of this file (Cholesky of G for the rank rule, of S for the EKF step) all use ONE THREAD PER ROW
+// with the matrix in shared memory: per elimination step a thread walks only its own remaining row, and warps whose rows
+// are finished just meet the barrier.  A register-tiled, block-wide variant (4 x 8 tiles, 576 threads, one published column
+// per step) was built and measured first: 0.9 - 1.1 us per step regardless of n (60 us for N' = 30, 194 us for n = 180) --
+// every one of its 18 warps walks the whole ~700-instruction step body, so it is instruction-issue bound, not latency
+// bound.  The per-row form issues only the instructions of live rows.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSFThreads = 576;
-constexpr int kSFMaxRows = 188;           // 47 row tiles -> 576 tiles
-constexpr int kSFColLen = kSFMaxRows + (kSFMaxRows >> 3) + 8;      // published column, padded: element i lives at i + (i >> 3)
-__device__ __forceinline__ int sf_ci(int i) { return i + (i >> 3); }   // tiles are 8 columns apart: 9 tc + y hits 16 different banks
-
-struct SFTile { int tr, tc, r0, c0; bool valid; };
-
-__device__ __forceinline__ int sf_before(int t) { const int u = t >> 1; return (t & 1) ? (u + 1) * (u + 1) : u * u + u; }   // tiles in row-tiles < t
-
-__device__ __forceinline__ SFTile sf_tile_of(int t, int rows_total)
-{
-    // row-tile tr (rows 4 tr .. 4 tr + 3) has the column tiles tc = 0 .. tr / 2 (columns 8 tc .. 8 tc + 7)
-    SFTile T;
-    int tr = 0;
-    while (t >= sf_before(tr + 1)) ++tr;
-    T.tr = tr; T.tc = t - sf_before(tr); T.r0 = 4 * tr; T.c0 = 8 * T.tc;
-    T.valid = T.r0 < rows_total;
-    return T;
-}
-
-// Factorises in place.  a: this thread's tile.  m: matrix order, aug: 1 when row m carries the right-hand side.
-// col: shared double[2][kSFColLen].  store(j, i, v, rs): element i (i = j .. m + aug - 1) of column j of the lower factor,
-// rs = 1 / L(j,j).
-// pv: shared double[m] pivots (negative for skipped columns).  SKIP: dependent columns (pivot < max(1e-12, 1e-12 gd[j])) are
-// skipped; otherwise a non-positive pivot sets *bad.  on_column(j) is called by ALL threads before column j is processed
-// (used by the rank rule for its class-boundary test; may return false to stop: then the function returns j);
-// after_pivot(j, dependent) is called by all threads once the pivot of column j is known.
-template <bool SKIP, class Store, class OnColumn, class AfterPivot>
-__device__ __forceinline__ int sym_factor(double (&a)[4][8], const SFTile& T, int m, int aug, double* col, Store store,
-                                          double* pv, const double* gd, int* bad, OnColumn on_column, AfterPivot after_pivot)
-{
-    const int rows_total = m + aug;
-    int buf = 0;
-    for (int j = 0; j < m; ++j) {
-        if (!on_column(j)) return j;
-        double* cj = col + buf * kSFColLen;
-        const int tcj = j >> 3, jj = j & 7;
-        if (T.valid && T.tc == tcj && T.r0 + 3 >= j) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int r = T.r0 + x;
-                if (r >= j && r < rows_total) {
-                    double v = 0;
-#pragma unroll
-                    for (int y = 0; y < 8; ++y) if (y == jj) v = a[x][y];
-                    cj[sf_ci(r)] = v;
-                    // the owner of the pivot also publishes 1 / sqrt(pivot): computed ONCE per step (every warp doing it for
-                    // itself costs ~40 FP64-pipe instructions x 18 warps per step, more than the rank-1 update itself)
-                    if (r == j) cj[kSFColLen - 1] = (v > 0.0) ? rsqrt(v) : 0.0;
-                }
-            }
-        }
-        __syncthreads();
-        const double p = cj[sf_ci(j)];
-        bool dep;
-        if (SKIP) dep = !(p >= fmax(1e-12, 1e-12 * gd[j]));
-        else { dep = false; if (!(p > 0.0) && threadIdx.x == 0) *bad = 1; }
-        if (threadIdx.x == 0) pv[j] = dep ? -1.0 : p;
-        after_pivot(j, dep);                                       // every thread, same value
-        if (!dep) {
-            const double rs = cj[kSFColLen - 1];
-            for (int i = j + (int)threadIdx.x; i < rows_total; i += kSFThreads) store(j, i, cj[sf_ci(i)] * rs, rs);
-            if (T.valid && T.r0 + 3 > j && T.c0 + 7 > j) {
-                double lr[4], lc[8];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) { const int r = T.r0 + x; lr[x] = (r > j && r < rows_total) ? cj[sf_ci(r)] * rs : 0.0; }
-#pragma unroll
-                for (int y = 0; y < 8; ++y) { const int c = T.c0 + y; lc[y] = (c > j && c < m) ? cj[sf_ci(c)] * rs : 0.0; }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 8; ++y) a[x][y] = fma(-lr[x], lc[y], a[x][y]);
-            }
-        }
-        buf ^= 1;
-    }
-    return m;
-}
-
-// loads the tile from val(r, c) for r < rows_total, c < m, c <= r (lower triangle; rows >= m are the extra rows)
-template <class Val>
-__device__ __forceinline__ void sf_load_fn(double (&a)[4][8], const SFTile& T, int m, int rows_total, Val val)
-{
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-            const int r = T.r0 + x, c = T.c0 + y;
-            a[x][y] = (T.valid && c < m && r < rows_total && (c <= r)) ? val(r, c) : 0.0;
-        }
-}
-
-// loads the lower triangle (+ optional extra row rhs) of a row-major symmetric matrix with leading dimension ld
-__device__ __forceinline__ void sf_load(double (&a)[4][8], const SFTile& T, const double* A, int ld, int m, const double* rhs, int aug)
-{
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-            const int r = T.r0 + x, c = T.c0 + y;
-            double v = 0;
-            if (T.valid && c < m) {
-                if (r < m) { if (c <= r) v = A[(size_t)r * ld + c]; }
-                else if (aug && r == m) v = rhs[c];
-            }
-            a[x][y] = v;
-        }
-}
+constexpr int kSFThreads = 576;           // rank-rule CTA (post-pass loops are sized for it)
+constexpr int kSFMaxRows = 188;           // n + 1 <= 188 (31 clones)
 
 // ------------------------------------------------------------------------------------------------
 // k_rank_rule
@@ -189,12 +79,13 @@ __device__ __forceinline__ void sf_load(double (&a)[4][8], const SFTile& T, cons
 // With Q.emit_R the kept rows (scaled, zero padded to n x n) and y are also written out: the large-window EKF step works on
 // them (R-form: S = R Pcc R^T + s^2 I).
 // ------------------------------------------------------------------------------------------------
-template <bool SMALL>
+// PACKED = false: rows of the factor in a rectangular shared-memory array (n <= 96), which the post-pass reads in place;
+// PACKED = true: rows packed (row i holds columns i .. N' and the right-hand side), written out to Q.L afterwards.
+template <bool PACKED>
 __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 {
-    extern __shared__ __align__(16) double rsm[];            // SMALL: the factor itself, Np x ld (one thread per row)
-    __shared__ double s_col[2][kSFColLen];
-    __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows], s_diag[kSFMaxRows];
+    extern __shared__ __align__(16) double rsm[];            // the factor itself, one thread per row
+    __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows];
     __shared__ int s_np, s_k, s_smin, s_ncls;
     __shared__ double s_tau;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,8 +126,8 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
     const bool raw_top = rule && s_smin > 0 && s_ncls > 1;
     const bool boundaries = rule && s_smin == 0 && !raw_top;
 
-    const int ldl = SMALL ? ((Np + 2) | 1) : (n + 1);
-    double* L = SMALL ? rsm : Q.L;                                // columns of the lower factor == rows of R, plus y at index Np
+    const int ldl = PACKED ? (n + 1) : ((Np + 2) | 1);
+    double* L = PACKED ? Q.L : rsm;                               // rows of R (= columns of the lower factor), y at index Np
     int q = 0, first_dep = Np;                                    // (thread-uniform copies)
     int mode = 1, kcut = 0;
     bool undecided = false;
@@ -254,21 +145,23 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         return true;
     };
     int jstop = Np;
-    if (SMALL) {
-        // ---- small windows: ONE THREAD PER ROW of the upper factor in shared memory.  Per step a thread walks its own row
+    {
+        // ---- ONE THREAD PER ROW of the upper factor in shared memory.  Per step a thread walks its own row
         //      (U(i,k) -= U(j,i) / p * U(j,k), k = i .. N', plus the right-hand side): the cost of a step is the length of the
-        //      remaining row, not a fixed block-wide round trip -- ~N'^2 / 2 shared-memory updates in total.
+        //      remaining rows, and warps whose rows are finished only meet the barrier.  (A register-tiled block-wide scheme
+        //      was measured 5x slower here: every warp walks the whole step body, and instruction issue, not latency, bounds it.)
         double* U = rsm;
+        auto row = [&](int i) -> double* { return PACKED ? (U + (size_t)i * (Np + 1) - (size_t)i * (i - 1) / 2 - i) : (U + (size_t)i * ldl); };   // row(i)[k], k >= i
         for (int o = tid; o < Np * (Np + 1); o += kSFThreads) {
             const int i = o / (Np + 1), k = o - i * (Np + 1);
-            if (k >= i) U[i * ldl + k] = (k < Np) ? G[(size_t)i * n + k] : Q.red[(size_t)n * n + i];
+            if (k >= i) row(i)[k] = (k < Np) ? G[(size_t)i * n + k] : Q.red[(size_t)n * n + i];
         }
         __syncthreads();
         for (int j = 0; j < Np; ++j) {
             if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {
                 if (warp == 0) {
                     double t = 0;
-                    for (int k = j + lane; k < Np; k += 32) t += U[k * ldl + k];
+                    for (int k = j + lane; k < Np; k += 32) t += row(k)[k];
                     t = warp_sum_d(t);
                     if (lane == 0) s_tau = t - s_late[j];
                 }
@@ -277,16 +170,16 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
                 __syncthreads();
                 if (!boundary_decision(j, tau)) { jstop = j; break; }
             }
-            const double pj = U[j * ldl + j];
+            const double* rj = row(j);
+            const double pj = rj[j];
             const bool dep = !(pj >= fmax(1e-12, 1e-12 * s_gd[j]));
             if (tid == 0) s_pv[j] = dep ? -1.0 : pj;
             after_pivot(j, dep);
             if (dep) continue;                                     // nothing changes: no barrier needed
             const int i = j + 1 + tid;
             if (i < Np) {
-                const double f = U[j * ldl + i] / pj;
-                const double* rj = U + j * ldl;
-                double* ri = U + i * ldl;
+                const double f = rj[i] / pj;
+                double* ri = row(i);
                 for (int k = i; k <= Np; ++k) ri[k] = fma(-f, rj[k], ri[k]);
             }
             __syncthreads();
@@ -296,36 +189,12 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         for (int j = warp; j < jstop; j += kSFThreads / 32) {
             if (s_pv[j] < 0.0) continue;
             const double rs = rsqrt(s_pv[j]);
-            for (int k = j + lane; k <= Np; k += 32) U[j * ldl + k] *= rs;
-        }
-    } else {
-        const SFTile T = sf_tile_of(tid, Np + 1);
-        double a[4][8];
-        sf_load(a, T, G, n, Np, Q.red + (size_t)n * n, 1);
-        auto on_column = [&](int j) -> bool {
-            if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {   // a class of features starts here (cls[j] > 0)
-                if (T.valid && T.tr * 4 <= T.c0 + 7 && T.r0 + 3 >= T.c0) {          // tiles crossing the diagonal
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 8; ++y)
-                            if (T.r0 + x == T.c0 + y && T.r0 + x < Np) s_diag[T.r0 + x] = a[x][y];
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    double t = 0;
-                    for (int k = j + lane; k < Np; k += 32) t += s_diag[k];
-                    t = warp_sum_d(t);
-                    if (lane == 0) s_tau = t - s_late[j];
-                }
-                __syncthreads();
-                const double tau = s_tau;
-                return boundary_decision(j, tau);
+            double* rj = row(j);
+            for (int k = j + lane; k <= Np; k += 32) {
+                const double v = rj[k] * rs;
+                if (PACKED) L[(size_t)j * ldl + k] = v; else rj[k] = v;
             }
-            return true;
-        };
-        auto store_L = [&](int j, int i, double v, double) { L[(size_t)j * ldl + i] = v; };
-        jstop = sym_factor<true>(a, T, Np, 1, &s_col[0][0], store_L, s_pv, s_gd, nullptr, on_column, after_pivot);
+        }
     }
     __syncthreads();
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
@@ -402,19 +271,39 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 // Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, register resident), then  Y = L^-1 [W | y]
 // (k_trsm, one CTA per 8 right-hand-side columns, L in shared memory).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSFThreads, 1) k_chol_S(const double* S, int m, double* Lp, double* invd, int* bad, const double* gate)
+constexpr int kCholThreads = 192;
+__global__ void __launch_bounds__(kCholThreads, 1) k_chol_S(const double* S, int m, double* Lp, double* invd, int* bad, const double* gate)
 {
-    __shared__ double s_col[2][kSFColLen];
-    __shared__ double s_pv[kSFMaxRows];
+    extern __shared__ __align__(16) double csm[];                // lower triangle, row i at i (i + 1) / 2
+    __shared__ double s_rs[kSFMaxRows + 8];
     if (gate && !(gate[0] > 2.0)) return;
-    const SFTile T = sf_tile_of(threadIdx.x, m);
-    double a[4][8];
-    sf_load(a, T, S, m, m, nullptr, 0);
-    auto store_packed = [&](int j, int i, double v, double rs) {
-        Lp[((size_t)j * m - (size_t)j * (j - 1) / 2) + (i - j)] = v;
-        if (i == j) invd[j] = rs;
-    };
-    sym_factor<false>(a, T, m, 0, &s_col[0][0], store_packed, s_pv, nullptr, bad, [](int) { return true; }, [](int, bool) {});
+    const int tid = threadIdx.x;
+    double* A = csm;
+    for (int o = tid; o < m * m; o += kCholThreads) {
+        const int r = o / m, c = o - r * m;
+        if (c <= r) A[r * (r + 1) / 2 + c] = S[(size_t)r * m + c];
+    }
+    __syncthreads();
+    // right-looking Cholesky, one thread per row: A(i,k) -= A(i,j) / p * A(k,j), k = j+1 .. i; columns unscaled until the end
+    const int i = tid;
+    double* ri = A + i * (i + 1) / 2;
+    for (int j = 0; j < m; ++j) {
+        const double p = A[j * (j + 1) / 2 + j];
+        if (!(p > 0.0)) { if (tid == 0) *bad = 1; }
+        if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
+        if (i > j && i < m && p > 0.0) {
+            const double f = ri[j] / p;
+            int offk = (j + 1) * (j + 2) / 2 + j;                  // A(k, j), k = j + 1
+            for (int k = j + 1; k <= i; ++k) { ri[k] = fma(-f, A[offk], ri[k]); offk += k + 1; }
+        }
+        __syncthreads();
+    }
+    // the factor, column packed (what k_trsm reads): column j at j m - j (j-1) / 2, element i at + (i - j)
+    for (int o = tid; o < m * m; o += kCholThreads) {
+        const int r = o / m, c = o - r * m;
+        if (c <= r) Lp[((size_t)c * m - (size_t)c * (c - 1) / 2) + (r - c)] = A[r * (r + 1) / 2 + c] * s_rs[c];
+    }
+    for (int j = tid; j < m; j += kCholThreads) invd[j] = s_rs[j];
 }
 
 // B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  Lp: packed lower factor (column j
@@ -841,7 +730,9 @@ int compress_configure(int nmax)
 {
     {
         const int ns = nmax < kRankSmallMaxN ? nmax : kRankSmallMaxN;
-        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)ns * ((ns + 2) | 1) + 8))));
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)ns * ((ns + 2) | 1) + 8))));
+        if (nmax > kRankSmallMaxN)
+            RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)(nmax + 1) * (nmax + 2) / 2 + 8))));
     }
     // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
     // given the largest dynamic shared memory it can be launched with
@@ -856,6 +747,7 @@ int compress_configure(int nmax)
         const int ns = nmax < kSolveSmallRMaxN ? nmax : kSolveSmallRMaxN;
         RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small_R, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem_bytes(ns, 24 + ns)));
     }
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_chol_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8))));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + nmax + 8))));
     return RVIO_OK;
 }
@@ -864,8 +756,8 @@ int compress_configure(int nmax)
 int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq_in, int n)
 {
     if (n + 1 > kSFMaxRows) { set_error("enqueue_rank_rule", "window too large"); return RVIO_ERR_CAPACITY; }
-    if (n <= kRankSmallMaxN) RVIO_LAUNCH(k_rank_rule<true>, 1, kSFThreads, sizeof(double) * ((size_t)n * ((n + 2) | 1) + 8), s, rq);
-    else RVIO_LAUNCH(k_rank_rule<false>, 1, kSFThreads, 0, s, rq);
+    if (n <= kRankSmallMaxN) RVIO_LAUNCH(k_rank_rule<false>, 1, kSFThreads, sizeof(double) * ((size_t)n * ((n + 2) | 1) + 8), s, rq);
+    else RVIO_LAUNCH(k_rank_rule<true>, 1, kSFThreads, sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + 8), s, rq);
     if (rq.world == 1) {
         bool w;
         const size_t gv = givens_smem_bytes(n, &w);
@@ -889,9 +781,9 @@ int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
 // Serial part of the large-window EKF step: S (n x n) -> L ; B (n x nb, leading dimension ldb) <- L^-1 B.
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate)
 {
-    if (n > kSFMaxRows || n > 192) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
+    if (n > kCholThreads) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
     double* invd = L + (size_t)n * (n + 1) / 2;                 // the scratch is n x n: room for the packed factor and 1 / diag
-    RVIO_LAUNCH(k_chol_S, 1, kSFThreads, 0, s, S, n, L, invd, bad, gate);
+    RVIO_LAUNCH(k_chol_S, 1, kCholThreads, sizeof(double) * ((size_t)n * (n + 1) / 2 + 8), s, S, n, L, invd, bad, gate);
     RVIO_LAUNCH(k_trsm, div_up(nb, kTrsmCols), 192, sizeof(double) * ((size_t)n * (n + 1) / 2 + n + 8), s, L, invd, n, B, ldb, nb, gate);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
