@@ -10,6 +10,8 @@
 #include "filter_kernels.cuh"
 #include "device_utils.cuh"
 
+#include <mutex>
+
 namespace rvio {
 
 #define PP(P, d, i, j) (P)[(size_t)(j) * (d) + (i)]
@@ -371,7 +373,7 @@ __device__ __forceinline__ int fn_cell(const FindNewerParams& Q, float2 p)
 
 __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
 {
-    extern __shared__ unsigned char s_acc[];         // accepted flag per candidate
+    extern __shared__ __align__(8) unsigned char s_dyn[];
     __shared__ int sh[34];
     __shared__ float2 s_list[32][kFindNewerCellCap];  // accepted points per warp's current cell
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -379,7 +381,13 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
     TrackerScalars* sc = B.sc;
     const int n_ref = sc->n_new;
     const int nc = Q.n_cand_dev ? min(*Q.n_cand_dev, Q.n_cand) : Q.n_cand;
-    for (int k = tid; k < nc; k += 1024) s_acc[k] = 0;
+    // dynamic shared memory: candidates, their grid cells, the cells of the features already there, accepted flags
+    float2* s_cand = reinterpret_cast<float2*>(s_dyn);                              // Q.n_cand
+    short* s_cell = reinterpret_cast<short*>(s_cand + Q.n_cand);                    // Q.n_cand
+    short* s_rcell = s_cell + Q.n_cand;                                             // B.F
+    unsigned char* s_acc = reinterpret_cast<unsigned char*>(s_rcell + B.F);         // Q.n_cand
+    for (int k = tid; k < nc; k += 1024) { const float2 p = Q.cand[k]; s_cand[k] = p; s_cell[k] = (short)fn_cell(Q, p); s_acc[k] = 0; }
+    for (int r = tid; r < n_ref; r += 1024) s_rcell[r] = (short)fn_cell(Q, B.feats_new[r]);
     __syncthreads();
     const int n_cells = Q.gc * Q.gr;
     const double lim = .75 * (double)Q.max_per_block;
@@ -387,36 +395,41 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
         for (int cell = warp; cell < n_cells; cell += 32) {
             // refs already in this cell
             int cnt = 0;
-            for (int r = lane; r < n_ref; r += 32) cnt += (fn_cell(Q, B.feats_new[r]) == cell) ? 1 : 0;
+            for (int r = lane; r < n_ref; r += 32) cnt += (s_rcell[r] == cell) ? 1 : 0;
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            const int col = cell % Q.gc, row = cell / Q.gc;
+            const float xl = __fadd_rn(__fmul_rn((float)col, Q.bx), (float)Q.offx), xr = __fadd_rn(xl, Q.bx);
+            const float yt = __fadd_rn(__fmul_rn((float)row, Q.by), (float)Q.offy), yb = __fadd_rn(yt, Q.by);
             int n_acc = 0;
-            for (int k = 0; k < nc; ++k) {
-                const float2 p = Q.cand[k];
-                if (fn_cell(Q, p) != cell) continue;                           // warp-uniform
-                const int col = cell % Q.gc, row = cell / Q.gc;
-                const float xl = __fadd_rn(__fmul_rn((float)col, Q.bx), (float)Q.offx), xr = __fadd_rn(xl, Q.bx);
-                const float yt = __fadd_rn(__fmul_rn((float)row, Q.by), (float)Q.offy), yb = __fadd_rn(yt, Q.by);
-                if (fabs((double)__fsub_rn(p.x, xl)) < (double)Q.min_dist || fabs((double)__fsub_rn(p.x, xr)) < (double)Q.min_dist ||
-                    fabs((double)__fsub_rn(p.y, yt)) < (double)Q.min_dist || fabs((double)__fsub_rn(p.y, yb)) < (double)Q.min_dist) continue;
-                if (!((double)(float)(cnt + n_acc) < lim)) continue;
-                // every point of the cell must be farther than min_dist (FeatureDetector.cc:125-134)
-                int close = 0;
-                for (int r = lane; r < n_ref; r += 32) {
-                    const float2 q = B.feats_new[r];
-                    if (fn_cell(Q, q) != cell) continue;
-                    const double dx = (double)__fsub_rn(p.x, q.x), dy = (double)__fsub_rn(p.y, q.y);
-                    if (!(sqrt(dx * dx + dy * dy) > (double)Q.min_dist)) close = 1;
-                }
-                for (int a = lane; a < n_acc; a += 32) {
-                    const float2 q = s_list[warp][a];
-                    const double dx = (double)__fsub_rn(p.x, q.x), dy = (double)__fsub_rn(p.y, q.y);
-                    if (!(sqrt(dx * dx + dy * dy) > (double)Q.min_dist)) close = 1;
-                }
-                close = __any_sync(0xffffffffu, close);
-                if (!close) {
-                    if (lane == 0) { s_acc[k] = 1; if (n_acc < kFindNewerCellCap) s_list[warp][n_acc] = p; }
-                    n_acc++;
-                    __syncwarp();
+            for (int k0 = 0; k0 < nc; k0 += 32) {
+                // the candidates of this cell among k0 .. k0+31, visited in candidate order (FeatureDetector.cc:99)
+                unsigned in_cell = __ballot_sync(0xffffffffu, k0 + lane < nc && s_cell[k0 + lane] == cell);
+                while (in_cell) {
+                    const int k = k0 + __ffs(in_cell) - 1;
+                    in_cell &= in_cell - 1;
+                    const float2 p = s_cand[k];
+                    if (fabs((double)__fsub_rn(p.x, xl)) < (double)Q.min_dist || fabs((double)__fsub_rn(p.x, xr)) < (double)Q.min_dist ||
+                        fabs((double)__fsub_rn(p.y, yt)) < (double)Q.min_dist || fabs((double)__fsub_rn(p.y, yb)) < (double)Q.min_dist) continue;
+                    if (!((double)(float)(cnt + n_acc) < lim)) continue;
+                    // every point of the cell must be farther than min_dist (FeatureDetector.cc:125-134)
+                    int close = 0;
+                    for (int r = lane; r < n_ref; r += 32) {
+                        if (s_rcell[r] != cell) continue;
+                        const float2 q = B.feats_new[r];
+                        const double dx = (double)__fsub_rn(p.x, q.x), dy = (double)__fsub_rn(p.y, q.y);
+                        if (!(sqrt(dx * dx + dy * dy) > (double)Q.min_dist)) close = 1;
+                    }
+                    for (int a = lane; a < n_acc; a += 32) {
+                        const float2 q = s_list[warp][a];
+                        const double dx = (double)__fsub_rn(p.x, q.x), dy = (double)__fsub_rn(p.y, q.y);
+                        if (!(sqrt(dx * dx + dy * dy) > (double)Q.min_dist)) close = 1;
+                    }
+                    close = __any_sync(0xffffffffu, close);
+                    if (!close) {
+                        if (lane == 0) { s_acc[k] = 1; if (n_acc < kFindNewerCellCap) s_list[warp][n_acc] = p; }
+                        n_acc++;
+                        __syncwarp();
+                    }
                 }
             }
         }
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(1024) k_find_newer_refill(FindNewerParams Q)
         const int r = base + ex;
         if (f && r < fq_n) {
             const int slot = B.freeq[(head + r) % (B.F + 1)];
-            const float2 p = Q.cand[k];
+            const float2 p = s_cand[k];
             float ux, uy;
             cam_undistort(Q.cam, p.x, p.y, &ux, &uy);
             B.slots_new[n_new0 + r] = slot;
@@ -473,7 +486,9 @@ int launch_augment_compose(cudaStream_t s, const AugmentParams& p)
 }
 int launch_find_newer_refill(cudaStream_t s, const FindNewerParams& p)
 {
-    RVIO_LAUNCH(k_find_newer_refill, 1, 1024, (size_t)(p.n_cand + 16), s, p);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(k_find_newer_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+    RVIO_LAUNCH(k_find_newer_refill, 1, 1024, (size_t)p.n_cand * (8 + 2 + 1) + (size_t)p.B.F * 2 + 64, s, p);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
