@@ -6,15 +6,15 @@
 // the kept rows Hn, rn only through  G = Hn^T Hn,  z = Hn^T rn, so the product path keeps its normal-term form
 // (k_gram -> solve) and this file only decides WHICH rows the reference keeps and rewrites [G | z] accordingly:
 //
-//   k_rank_rule   (every compressed frame, one CTA)   pivot-free Cholesky of G = R^T R, which yields the rows of the
-//                 reference's trapezoid as long as the leading columns are independent (R is unique up to row signs for
-//                 ANY orthogonal triangularisation).  Let j* be the first dependent column.  If the information left after
-//                 j* columns (the trace of the Schur complement = ||B||_F^2 of the remaining block B) is below (1e-4)^2, the
-//                 reference's row j* (a unit combination of the rows of B) is below 1e-4: the cut is at j* and discards
-//                 nothing -> [G | z] stay as they are.  If an earlier row is already below 1e-4 the cut is there and
-//                 [G | z] are rebuilt from the kept rows.  Otherwise (a dependent column in the MIDDLE with information
-//                 after it -- e.g. '2' features covering the first clones, '1' features the last ones, disjoint supports)
-//                 the outcome depends on the reference's own rotation order and exact-zero pattern: k_givens_ref decides.
+//   k_rank_rule   (every updating frame, one CTA)   pivot-free Cholesky of G = R^T R (one thread per row, shared memory),
+//                 which yields the rows of the reference's trapezoid as long as the leading columns are independent (R is
+//                 unique up to row signs for ANY orthogonal triangularisation) -- the reference's own test (norm < 1e-4)
+//                 applies to them.  At a dependent column the reference's row is a unit combination of the rows still
+//                 "active" there (features whose column support starts at or before it) with rounding-residue weights:
+//                 below 1e-4 for certain when the active rows are exhausted (trace of the active Schur complement < 1e-8:
+//                 the cut is there, every class of features that would only start later is discarded and [G | z] are
+//                 rebuilt from the kept rows), orders of magnitude above it otherwise.  Everything in between is left to
+//                 k_givens_ref.  Also hands the kept rows R and y (R^T y = z) to the EKF step (R-form).
 //   k_givens_ref  (only then, one CTA)   the reference's Givens sweep itself, rotation for rotation, scheduled as a
 //                 wavefront: rotation (column n, rows m-1,m) runs at step t = (M-1-m) + 2n; all rotations of a step touch
 //                 disjoint row pairs, M + N' - 2 dependent steps instead of ~M N'.  The rows live in a circular
@@ -22,6 +22,7 @@
 //                 exactly once, by cp.async, a few steps ahead).  Special cases of Eigen's makeGivens (q == 0 -> identity,
 //                 p == 0 -> row swap) are kept exactly: they are what moves the exact zeros around and make the reference's
 //                 outcome deterministic.  Then the first-small-row cut, and [G | z] := kept rows.
+//   k_solve_small_R / k_chol_S + k_trsm   the EKF step itself on the kept rows (Updater.cc:540-619), see below.
 //
 // Both kernels read the mode from device memory (0 = reference rule, 1 = full information: keep [G | z] of all rows), so
 // captured frame graphs stay valid when the mode is switched.
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, register resident), then  Y = L^-1 [W | y]
+// Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, one thread per row, packed triangle in shared memory), then  Y = L^-1 [W | y]
 // (k_trsm, one CTA per 8 right-hand-side columns, L in shared memory).
 // ------------------------------------------------------------------------------------------------
 constexpr int kCholThreads = 192;

@@ -3,13 +3,12 @@
 // Replaces Updater::update (reference src/rvio/Updater.cc:72-628):
 //   k_feature       one CTA per feature: relative-pose chain (:118-141), inverse-depth LM triangulation (:146-269),
 //                   Jacobian blocks (:271-368), left-nullspace projection (:370-402), chi^2 gate (:404-455)
-//   k_gram / k_gram_z / k_gram_reduce
-//                   compression of the stacked system to its normal terms G = H^T H, z = H^T r  (:460-536)
-//   k_dgemm, k_gauss_jordan, k_finalize
-//                   EKF gain / state correction / covariance (:540-619) in the algebraically identical form
-//                        dx = P[:,c] (G Pcc + s^2 I)^-1 z ,   P+ = P - P[:,c] (G Pcc + s^2 I)^-1 G P[c,:]
-// See DESIGN.md "Updater" for the equivalence argument and for the one deliberate deviation (the reference's
-// first-small-row rank cut, Updater.cc:515-524, can discard informative rows; the normal-term form never does).
+//   k_dmma_hp + k_gate (n >= 96)   the gate's H~ Pcc of all features as one tall FP64 tensor-core GEMM, then the per-feature decision
+//   k_gram / k_gram_dmma           the stacked system's normal terms G = H^T H, z = H^T r and the per-class information
+//   compress.cu                    which rows the reference's compression keeps (Updater.cc:474-536) and the EKF step
+//                                  (Updater.cc:540-619) on those rows:  S = R Pcc R^T + s^2 I,  K = P R^T S^-1, Joseph form
+//                                  == dx = Y^T y~,  P+ = P - Y^T Y  with  Y = L^-1 [R P[c,:] | y],  S = L L^T
+// See DESIGN.md for the kernels, the rank rule and the remaining deliberate deviations.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
