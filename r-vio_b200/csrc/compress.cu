@@ -54,6 +54,13 @@ __device__ __forceinline__ double warp_sum_d(double v)
 // every one of its 18 warps walks the whole ~700-instruction step body, so it is instruction-issue bound, not latency
 // bound.  The per-row form issues only the instructions of live rows.
 // ------------------------------------------------------------------------------------------------
+#ifdef RVIO_B200_PHASE_CLOCKS
+// (profiling build only: make PHASES=1) per-phase SM clock stamps of the single-CTA kernels, read back by tools/prof_update.py
+__device__ long long g_phase_clk[64];
+#define PHASE_CLK(k) do { if (threadIdx.x == 0) g_phase_clk[k] = clock64(); } while (0)
+#else
+#define PHASE_CLK(k) do { } while (0)
+#endif
 constexpr int kSFThreads = 576;           // rank-rule CTA (post-pass loops are sized for it)
 constexpr int kSFMaxRows = 188;           // n + 1 <= 188 (31 clones)
 
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         if (cls[c] > 0.0) { atomicMin(&s_smin, c); atomicAdd(&s_ncls, 1); }
     __syncthreads();
     const int Np = s_np;
+    PHASE_CLK(16);
     for (int c = tid; c <= n; c += kSFThreads) s_nr2[c < kSFMaxRows ? c : kSFMaxRows - 1] = cls[c];      // staged: the suffix sum below must not walk global memory
     __syncthreads();
     if (tid == 0) {                                               // late[j] = information of the classes starting at column >= j
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
     const bool raw_top = rule && s_smin > 0 && s_ncls > 1;
     const bool boundaries = rule && s_smin == 0 && !raw_top;
 
-    const int ldl = PACKED ? (n + 1) : ((Np + 2) | 1);
+    const int ldl = PACKED ? (n + 1) : ((Np + 2) & ~1);      // even: thread i walks row i from column i, stride ldl + 1 doubles (odd) between lanes
     double* L = PACKED ? Q.L : rsm;                               // rows of R (= columns of the lower factor), y at index Np
     int q = 0, first_dep = Np;                                    // (thread-uniform copies)
     int mode = 1, kcut = 0;
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
             if (k >= i) row(i)[k] = (k < Np) ? G[(size_t)i * n + k] : Q.red[(size_t)n * n + i];
         }
         __syncthreads();
+        PHASE_CLK(17);
         for (int j = 0; j < Np; ++j) {
             if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {
                 if (warp == 0) {
@@ -179,13 +188,23 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
             if (dep) continue;                                     // nothing changes: no barrier needed
             const int i = j + 1 + tid;
             if (i < Np) {
-                const double f = rj[i] / pj;
-                double* ri = row(i);
-                for (int k = i; k <= Np; ++k) ri[k] = fma(-f, rj[k], ri[k]);
+                const double f = -rj[i] / pj;
+                double* __restrict__ ri = row(i);
+                const double* __restrict__ rjj = rj;
+                int k = i;
+                for (; k + 8 <= Np + 1; k += 8) {                  // 8 loads in flight, then 8 stores (the rows do not alias)
+                    double a[8], b[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a[u] = rjj[k + u]; b[u] = ri[k + u]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
+                }
+                for (; k <= Np; ++k) ri[k] = fma(f, rjj[k], ri[k]);
             }
             __syncthreads();
         }
         __syncthreads();
+        PHASE_CLK(18);
         // rows of R: U(j, j..) / sqrt(p_j); the right-hand side becomes y
         for (int j = warp; j < jstop; j += kSFThreads / 32) {
             if (s_pv[j] < 0.0) continue;
@@ -198,6 +217,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         }
     }
     __syncthreads();
+    PHASE_CLK(19);
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
     const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
     // the reference's own test on the rows that are unique (before the first dependent column): norm < 1e-4 (Updater.cc:519)
@@ -211,6 +231,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         if (lane == 0) { s_nr2[j] = sq; if (j < ulim && sq < 1e-8) atomicMin(&s_k, j); }
     }
     __syncthreads();
+    PHASE_CLK(20);
     int kept_rows = q;
     bool rebuild = false, discards = false, generic = false;
     int klim = jend;             // columns with index < klim (and a good pivot) are kept
@@ -248,6 +269,7 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         }
         for (int j = tid; j < n; j += kSFThreads) Q.yc[j] = (j < kl && j < Np && s_pv[j] >= 0.0) ? L[(size_t)j * ldl + Np] : 0.0;
     }
+    PHASE_CLK(21);
     if (!rebuild) return;
     // G' = sum_{kept j} L_j L_j^T ,  z' = sum_{kept j} L_j y_j   (bitwise symmetric: products commute)
     double* Gw = Q.red; double* zw = Q.red + (size_t)n * n;
@@ -287,15 +309,23 @@ __global__ void __launch_bounds__(kCholThreads, 1) k_chol_S(const double* S, int
     __syncthreads();
     // right-looking Cholesky, one thread per row: A(i,k) -= A(i,j) / p * A(k,j), k = j+1 .. i; columns unscaled until the end
     const int i = tid;
-    double* ri = A + i * (i + 1) / 2;
+    double* __restrict__ ri = A + i * (i + 1) / 2;
     for (int j = 0; j < m; ++j) {
         const double p = A[j * (j + 1) / 2 + j];
         if (!(p > 0.0)) { if (tid == 0) *bad = 1; }
         if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
         if (i > j && i < m && p > 0.0) {
-            const double f = ri[j] / p;
+            const double f = -ri[j] / p;
             int offk = (j + 1) * (j + 2) / 2 + j;                  // A(k, j), k = j + 1
-            for (int k = j + 1; k <= i; ++k) { ri[k] = fma(-f, A[offk], ri[k]); offk += k + 1; }
+            int k = j + 1;
+            for (; k + 8 <= i + 1; k += 8) {
+                double a[8], b[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[u] = A[offk]; offk += k + u + 1; b[u] = ri[k + u]; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
+            }
+            for (; k <= i; ++k) { ri[k] = fma(f, A[offk], ri[k]); offk += k + 1; }
         }
         __syncthreads();
     }
@@ -399,9 +429,11 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
     double* A = sm;
     double* sR = A + (size_t)rows_total * lda;                     // n x lda
     double* sP = sR + (size_t)n * lda;                             // n x ldp: P[c,:]
+    PHASE_CLK(0);
     for (int o = tid; o < n * n; o += kSRThreads) { const int r = o / n, c = o - r * n; sR[r * lda + c] = Q.Rc[o]; }
     for (int o = tid; o < n * d; o += kSRThreads) { const int j = o / n, k = o - j * n; sP[k * ldp + j] = Q.P[(size_t)j * d + 24 + k]; }   // P(24+k, j)
     __syncthreads();
+    PHASE_CLK(1);
     // ---- W = R P[c,:]  (R upper triangular), written transposed into the extra rows of A
     {
         const int tr_n = (n + 1) / 2, tc_n = (d + 3) / 4;
@@ -426,6 +458,7 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         for (int r = tid; r < n; r += kSRThreads) A[(n + d) * lda + r] = Q.yc[r];
     }
     __syncthreads();
+    PHASE_CLK(2);
     // ---- S = W[:, 24:] R^T + s^2 I  (lower triangle; R[c][k] = 0 for k < c) into rows 0..n-1 of A
     {
         const int tn = (n + 1) / 2, tcn = (n + 3) / 4;
@@ -455,6 +488,7 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         }
     }
     __syncthreads();
+    PHASE_CLK(3);
     // ---- right-looking Cholesky, ONE THREAD PER ROW (rows of S and the extra rows alike): at step j row i does
     //      A(i,k) -= A(i,j) / p * A(k,j) for k = j+1 .. min(i, n-1).  Columns stay unscaled until the end (every thread reads
     //      column j while its owners would be rescaling it).  One barrier per step; the work of a step is the remaining row.
@@ -465,20 +499,30 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
             if (!(p > 0.0)) { if (tid == 0) *Q.bad = 1; }
             if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
             if (i > j && i < rows_total && p > 0.0) {
-                double* ri = A + i * lda;
-                const double f = ri[j] / p;
+                double* __restrict__ ri = A + i * lda;
+                const double f = -ri[j] / p;
                 const int kmax = min(i, n - 1);
-                const double* cj = A + j;                          // column j: A(k, j) = cj[k * lda]
-                for (int k = j + 1; k <= kmax; ++k) ri[k] = fma(-f, cj[k * lda], ri[k]);
+                const double* __restrict__ cj = A + j;             // column j: A(k, j) = cj[k * lda] (never written during step j)
+                int k = j + 1;
+                for (; k + 8 <= kmax + 1; k += 8) {
+                    double a[8], b[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a[u] = cj[(k + u) * lda]; b[u] = ri[k + u]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
+                }
+                for (; k <= kmax; ++k) ri[k] = fma(f, cj[k * lda], ri[k]);
             }
             __syncthreads();
         }
+        PHASE_CLK(4);
         for (int o = tid; o < rows_total * n; o += kSRThreads) {   // scale the columns: L(i,j) = A(i,j) / sqrt(p_j)
             const int r = o / n, c = o - r * n;
             if (c <= r) A[r * lda + c] *= s_rs[c];
         }
     }
     __syncthreads();
+    PHASE_CLK(5);
     // ---- dx = Y^T y~ ;  Y(j, c) = A(n + c, j)
     for (int c = tid; c < d; c += kSRThreads) {
         const double* yc_ = A + (n + c) * lda; const double* yd = A + (n + d) * lda;
@@ -516,6 +560,7 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         }
     }
     __syncthreads();
+    PHASE_CLK(6);
     // ---- state correction (Updater.cc:546-613)
     const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
     for (int bq = tid; bq < 2 + N; bq += kSRThreads) {
@@ -791,3 +836,11 @@ int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double*
 }
 
 }  // namespace rvio
+
+#ifdef RVIO_B200_PHASE_CLOCKS
+extern "C" int rvio_b200_phase_clocks(long long* out, int n)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, rvio::g_phase_clk, sizeof(long long) * (n < 64 ? n : 64));
+}
+#endif

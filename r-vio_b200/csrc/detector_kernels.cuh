@@ -6,7 +6,8 @@
 namespace rvio {
 
 constexpr int kDetKeyCap = 65536;       // local maxima above the quality threshold that are kept (more: overflow flag)
-constexpr int kDetCellSlots = 4;        // accepted corners per grid cell (cell side == minimum distance: at most 2 fit)
+constexpr int kDetCellSlots = 2;        // accepted corners per grid cell: integer pixels in a cell of side ~minDistance that are >= minDistance apart
+                                        // can only be the two ends of a diagonal (any axis-aligned pair is at most side - 1 apart)
 
 struct DetCtrl { unsigned max_bits; int n_cand; int n_out; int overflow; };
 
