@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librvio_b200.so")
+LIB_PATH = os.environ.get("RVIO_B200_LIB") or os.path.join(_HERE, "librvio_b200.so")      # (override: the profiling variant, make PHASES=1)
 
 OK, FIRST_IMAGE, NO_FEATURES = 0, 1, 2
 

@@ -44,15 +44,44 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
+// Eight warp sums for the price of nine shuffles: after the call lane 4 m (m = 0 .. 7) holds the warp total of v[m]
+// (recursive halving over lane bits 4, 3, 2, then plain butterflies over bits 1, 0; fixed order -> deterministic).
+__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
+{
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    double w[4], u[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double send = h16 ? v[k] : v[k + 4], keep = h16 ? v[k + 4] : v[k];
+        w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double send = h8 ? w[k] : w[k + 2], keep = h8 ? w[k + 2] : w[k];
+        u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double send = h4 ? u[0] : u[1], keep = h4 ? u[1] : u[0];
+    double t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Single-CTA factorisations of this file (Cholesky of G for the rank rule, of S for the EKF step) all use ONE THREAD PER ROW
-// with the matrix in shared memory: per elimination step a thread walks only its own remaining row, and warps whose rows
-// are finished just meet the barrier.  A register-tiled, block-wide variant (4 x 8 tiles, 576 threads, one published column
-// per step) was built and measured first: 0.9 - 1.1 us per step regardless of n (60 us for N' = 30, 194 us for n = 180) --
-// every one of its 18 warps walks the whole ~700-instruction step body, so it is instruction-issue bound, not latency
-// bound.  The per-row form issues only the instructions of live rows.
+// Single-CTA factorisations of this file (Cholesky of G for the rank rule, of S for the EKF step): BLOCKED, 8 columns per
+// panel, on a TILE-PACKED lower trapezoid in shared memory (8 x 8 tiles of 64 doubles; tile (I, J) of the lower triangle
+// at I (I + 1) / 2 + J, full tile rows below the square part for right-hand sides that ride along as extra rows):
+//   per panel   every thread factors the 8 x 8 diagonal tile redundantly in registers (no barrier inside the panel),
+//               thread i then solves its own row of the panel against it (36 FMAs, row in registers)      -> barrier
+//               the trailing tiles C(I,K) -= L(I) L(K)^T go through FP64 DMMA (mma.sync m8n8k4): both fragments of a
+//               tile product are one conflict-free LDS.128 each (lane (g, t) takes columns 2t, 2t+1 of row g -- the k
+//               index of the product is permuted the same way on both operands), the C tile one LDS.128 / STS.128 -> barrier
+// 2 barriers per 8 columns instead of one per column, and the O(n^3) part runs on the tensor pipe.
+// History, measured on B200: one thread per row with the rows in shared memory (one barrier per column, LDS + DFMA + STS
+// per element): 59 us at n = 66, 250 - 350 us at n = 150 - 180; a register-tiled block-wide scheme before that: ~1 us per
+// column regardless of n (instruction-issue bound).
 // ------------------------------------------------------------------------------------------------
 #ifdef RVIO_B200_PHASE_CLOCKS
 // (profiling build only: make PHASES=1) per-phase SM clock stamps of the single-CTA kernels, read back by tools/prof_update.py
@@ -61,8 +90,178 @@ __device__ long long g_phase_clk[64];
 #else
 #define PHASE_CLK(k) do { } while (0)
 #endif
-constexpr int kSFThreads = 576;           // rank-rule CTA (post-pass loops are sized for it)
-constexpr int kSFMaxRows = 188;           // n + 1 <= 188 (31 clones)
+constexpr int kBCThreads = 256;           // threads of the blocked-Cholesky CTAs (8 warps; rows of the trapezoid <= 256)
+constexpr int kBCWarps = kBCThreads / 32;
+constexpr int kSFMaxRows = 200;           // padded columns + right-hand side row (31 clones: 186 -> 192 + 8)
+
+struct TileTri {
+    double* t; int tc, tr;                // tc tile columns (square lower triangle), tr >= tc tile rows
+    __device__ __forceinline__ int toff(int I, int J) const { return (I < tc ? (I * (I + 1)) / 2 : (tc * (tc + 1)) / 2 + (I - tc) * tc) + J; }
+    __device__ __forceinline__ double* tile(int I, int J) const { return t + ((size_t)toff(I, J) << 6); }
+    __device__ __forceinline__ double* at(int i, int j) const { return tile(i >> 3, j >> 3) + ((i & 7) << 3) + (j & 7); }
+};
+__host__ __device__ inline int tile_tri_count(int tc, int tr) { return tc * (tc + 1) / 2 + (tr - tc) * tc; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// C (8 x 8, lane (g, t) holds C[g][2t], C[g][2t+1]) += A B^T for two 8 x 8 row-major tiles given as their (g, 2t..2t+1) pairs
+__device__ __forceinline__ void tile_mma(double2& c, const double2& a, const double2& b)
+{
+    dmma884(c.x, c.y, a.x, b.x);
+    dmma884(c.x, c.y, a.y, b.y);
+}
+
+// Blocked Cholesky of the trapezoid T (rows 0 .. nrows-1; columns 0 .. 8 T.tc - 1), in place: L below and on the diagonal.
+//   pivot_ok(j, p)   thread-uniform: false -> column j is skipped (its column of L is zero)
+//   RANK only: nact = number of real columns (the rest is identity padding); is_boundary(j) says where a class test is due,
+//   on_column(j, dep, is_b, tau, colnorm2) is walked over the columns in order after each panel (thread-uniform) and returns
+//   false to stop (nothing after the current panel is touched then).  tau = trace of the Schur complement of the columns
+//   >= j restricted to real rows; colnorm2 = sum_i L(i,j)^2 over real rows.  s_part: 2 x 8 x kBCWarps doubles.
+// Returns the number of panels done.
+template <bool RANK, class OkFn, class BndFn, class ColFn>
+__device__ __forceinline__ int tile_cholesky(const TileTri& T, int nrows, int nact, OkFn pivot_ok, BndFn is_boundary, ColFn on_column,
+                                             double* s_pv, double* s_part)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    int J = 0;
+    for (; J < T.tc; ++J) {
+        __syncthreads();
+        // ---- diagonal tile -> registers, factored redundantly by every thread
+        double D[8][8];
+        {
+            const double* dt = T.tile(J, J);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    if (c <= r) { const double2 v = *reinterpret_cast<const double2*>(dt + r * 8 + c); D[r][c] = v.x; D[r][c + 1] = v.y; }
+                    else { D[r][c] = 0.0; D[r][c + 1] = 0.0; }
+                }
+        }
+        double rs[8], ptau[8];
+        unsigned okmask = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = 8 * J + c;
+            const double p = D[c][c];
+            if (RANK) {                                             // trace of the Schur complement at column j, rows of this panel
+                double a = 0;
+#pragma unroll
+                for (int r = c; r < 8; ++r) if (8 * J + r < nact) a += D[r][r];
+                ptau[c] = a;
+            }
+            const bool ok = pivot_ok(j, p);
+            okmask |= (ok ? 1u : 0u) << c;
+            const double r_ = ok ? rsqrt(p) : 0.0;
+            rs[c] = r_;
+            D[c][c] = p * r_;
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) D[r][c] *= r_;
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r)
+#pragma unroll
+                for (int c2 = c + 1; c2 <= r; ++c2) D[r][c2] = fma(-D[r][c], D[c2][c], D[r][c2]);
+            if (tid == 0) s_pv[j] = ok ? p : -1.0;
+        }
+        // ---- my row of the panel: rows of the diagonal tile store the factor, rows below solve against it
+        const int i = 8 * J + tid;
+        double l[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) l[c] = 0.0;
+        if (i < nrows) {
+            double2* rp = reinterpret_cast<double2*>(T.tile(i >> 3, J) + ((i & 7) << 3));
+            if (tid < 8) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (tid == r) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) l[c] = (c <= r) ? D[r][c] : 0.0;
+                    }
+            } else {
+                double a[8];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) { const double2 v = rp[c >> 1]; a[c] = v.x; a[c + 1] = v.y; }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double v = a[c];
+#pragma unroll
+                    for (int c1 = 0; c1 < c; ++c1) v = fma(-l[c1], D[c][c1], v);
+                    l[c] = v * rs[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) rp[c >> 1] = make_double2(l[c], l[c + 1]);
+        }
+        unsigned bmask = 0;
+        if (RANK) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (is_boundary(8 * J + c)) bmask |= 1u << c;
+            const bool real = i < nact;                             // a row of G (not padding, not the right-hand side)
+            double v8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v8[c] = real ? l[c] * l[c] : 0.0;
+            double tot = warp_sum8(v8, lane);                       // lane 4 c holds the warp's share of |L(:, c)|^2
+            if ((lane & 3) == 0) s_part[(8 + (lane >> 2)) * kBCWarps + warp] = tot;
+            if (bmask) {                                            // rows below the panel: diagonal minus what the columns before c took
+                const bool below = real && tid >= 8;
+                const double dg = below ? *T.at(i, i) : 0.0;
+                double run = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    v8[c] = (below && ((bmask >> c) & 1u)) ? dg - run : 0.0;
+                    run = fma(l[c], l[c], run);
+                }
+                tot = warp_sum8(v8, lane);
+                if ((lane & 3) == 0) s_part[(lane >> 2) * kBCWarps + warp] = tot;
+            }
+        }
+        __syncthreads();
+        if (RANK) {
+            bool stop = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = 8 * J + c;
+                if (j >= nact || stop) continue;
+                const bool isb = (bmask >> c) & 1u;
+                double tau = 0, cn = 0;
+                if (isb) { tau = ptau[c]; for (int w = 0; w < kBCWarps; ++w) tau += s_part[c * kBCWarps + w]; }
+                for (int w = 0; w < kBCWarps; ++w) cn += s_part[(8 + c) * kBCWarps + w];
+                if (!on_column(j, !((okmask >> c) & 1u), isb, tau, cn)) stop = true;
+            }
+            if (stop) break;
+        }
+        // ---- trailing update on the tensor pipe: tile row I to warp (I - J - 1) mod 8, two tiles in flight
+        for (int I = J + 1 + warp; I < T.tr; I += kBCWarps) {
+            double2 a = *reinterpret_cast<const double2*>(T.tile(I, J) + g * 8 + 2 * t4);
+            a.x = -a.x; a.y = -a.y;
+            const int Kmax = min(I, T.tc - 1);
+            double* crow = T.tile(I, J + 1) + g * 8 + 2 * t4;       // tiles (I, J+1), (I, J+2), ... are consecutive
+            int K = J + 1;
+            for (; K + 1 <= Kmax; K += 2, crow += 128) {
+                const double2 b0 = *reinterpret_cast<const double2*>(T.tile(K, J) + g * 8 + 2 * t4);
+                const double2 b1 = *reinterpret_cast<const double2*>(T.tile(K + 1, J) + g * 8 + 2 * t4);
+                double2 c0 = *reinterpret_cast<double2*>(crow), c1 = *reinterpret_cast<double2*>(crow + 64);
+                dmma884(c0.x, c0.y, a.x, b0.x);
+                dmma884(c1.x, c1.y, a.x, b1.x);
+                dmma884(c0.x, c0.y, a.y, b0.y);
+                dmma884(c1.x, c1.y, a.y, b1.y);
+                *reinterpret_cast<double2*>(crow) = c0;
+                *reinterpret_cast<double2*>(crow + 64) = c1;
+            }
+            if (K <= Kmax) {
+                const double2 b0 = *reinterpret_cast<const double2*>(T.tile(K, J) + g * 8 + 2 * t4);
+                double2 c0 = *reinterpret_cast<double2*>(crow);
+                tile_mma(c0, a, b0);
+                *reinterpret_cast<double2*>(crow) = c0;
+            }
+        }
+    }
+    __syncthreads();
+    return J;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // k_rank_rule
@@ -87,13 +286,11 @@ constexpr int kSFMaxRows = 188;           // n + 1 <= 188 (31 clones)
 // With Q.emit_R the kept rows (scaled, zero padded to n x n) and y are also written out: the large-window EKF step works on
 // them (R-form: S = R Pcc R^T + s^2 I).
 // ------------------------------------------------------------------------------------------------
-// PACKED = false: rows of the factor in a rectangular shared-memory array (n <= 96), which the post-pass reads in place;
-// PACKED = true: rows packed (row i holds columns i .. N' and the right-hand side), written out to Q.L afterwards.
-template <bool PACKED>
-__global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
+__global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
 {
-    extern __shared__ __align__(16) double rsm[];            // the factor itself, one thread per row
+    extern __shared__ __align__(16) double rsm[];            // the tile-packed factor (lower: column j of L = row j of R), y in the extra row
     __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows];
+    __shared__ double s_part[16 * kBCWarps];
     __shared__ int s_np, s_k, s_smin, s_ncls;
     __shared__ double s_tau;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,17 +308,17 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
     if (!updating || (!rule && !Q.emit_R)) return;
     __syncthreads();
     // trailing all-zero columns (Updater.cc:480-489): column norm == 0  <=>  G(j,j) == 0
-    for (int j = tid; j < n; j += kSFThreads) {
-        const double g = G[(size_t)j * n + j];
-        s_gd[j] = g;
-        if (g != 0.0) atomicMax(&s_np, j + 1);
+    for (int j = tid; j < n; j += kBCThreads) {
+        const double gd = G[(size_t)j * n + j];
+        s_gd[j] = gd;
+        if (gd != 0.0) atomicMax(&s_np, j + 1);
     }
-    for (int c = tid; c <= n; c += kSFThreads)
+    for (int c = tid; c <= n; c += kBCThreads)
         if (cls[c] > 0.0) { atomicMin(&s_smin, c); atomicAdd(&s_ncls, 1); }
     __syncthreads();
     const int Np = s_np;
     PHASE_CLK(16);
-    for (int c = tid; c <= n; c += kSFThreads) s_nr2[c < kSFMaxRows ? c : kSFMaxRows - 1] = cls[c];      // staged: the suffix sum below must not walk global memory
+    for (int c = tid; c <= n; c += kBCThreads) s_nr2[c < kSFMaxRows ? c : kSFMaxRows - 1] = cls[c];      // staged: the suffix sum below must not walk global memory
     __syncthreads();
     if (tid == 0) {                                               // late[j] = information of the classes starting at column >= j
         double acc = 0;
@@ -135,103 +332,58 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
     const bool raw_top = rule && s_smin > 0 && s_ncls > 1;
     const bool boundaries = rule && s_smin == 0 && !raw_top;
 
-    const int ldl = PACKED ? (n + 1) : ((Np + 2) & ~1);      // even: thread i walks row i from column i, stride ldl + 1 doubles (odd) between lanes
-    double* L = PACKED ? Q.L : rsm;                               // rows of R (= columns of the lower factor), y at index Np
+    TileTri T;
+    T.t = rsm; T.tc = (Np + 7) >> 3; T.tr = T.tc + 1;
+    const int ncp = 8 * T.tc;                                     // padded column count; row ncp carries z, later y
     int q = 0, first_dep = Np;                                    // (thread-uniform copies)
     int mode = 1, kcut = 0;
     bool undecided = false;
-    auto after_pivot = [&](int j, bool dep) { if (!dep) q++; else if (first_dep == Np) first_dep = j; };
-    // class-boundary test (see above); tau = trace of the current Schur complement - information that has not started yet
-    auto boundary_decision = [&](int j, double tau) -> bool {
-        const int dd = j - q;
-        if (dd >= 1) {
-            if (tau < 1e-8) { mode = 2; kcut = j; return false; }                // exhausted: the reference cuts, later classes are discarded
-            if (tau < 1e-3 || dd >= 2) {                                        // only the reference's own sweep can tell
-                if (Q.world == 1) { mode = 3; return false; }
-                undecided = true;                                               // feature-sharded: keep everything, say so
-            }
-        }
-        return true;
-    };
     int jstop = Np;
     {
-        // ---- ONE THREAD PER ROW of the upper factor in shared memory.  Per step a thread walks its own row
-        //      (U(i,k) -= U(j,i) / p * U(j,k), k = i .. N', plus the right-hand side): the cost of a step is the length of the
-        //      remaining rows, and warps whose rows are finished only meet the barrier.  (A register-tiled block-wide scheme
-        //      was measured 5x slower here: every warp walks the whole step body, and instruction issue, not latency, bounds it.)
-        double* U = rsm;
-        auto row = [&](int i) -> double* { return PACKED ? (U + (size_t)i * (Np + 1) - (size_t)i * (i - 1) / 2 - i) : (U + (size_t)i * ldl); };   // row(i)[k], k >= i
-        for (int o = tid; o < Np * (Np + 1); o += kSFThreads) {
-            const int i = o / (Np + 1), k = o - i * (Np + 1);
-            if (k >= i) row(i)[k] = (k < Np) ? G[(size_t)i * n + k] : Q.red[(size_t)n * n + i];
-        }
+        const int ntile = tile_tri_count(T.tc, T.tr) * 64;
+        for (int o = tid; o < ntile; o += kBCThreads) rsm[o] = 0.0;
         __syncthreads();
+        for (int o = tid; o < Np * Np; o += kBCThreads) {
+            const int i = o / Np, j = o - i * Np;
+            if (j <= i) *T.at(i, j) = G[(size_t)i * n + j];
+        }
+        for (int j = tid; j < ncp; j += kBCThreads) {
+            if (j < Np) *T.at(ncp, j) = Q.red[(size_t)n * n + j];
+            else *T.at(j, j) = 1.0;                               // identity padding up to a multiple of 8 columns
+        }
         PHASE_CLK(17);
-        for (int j = 0; j < Np; ++j) {
-            if (boundaries && j > 0 && s_late[j] > s_late[j + 1]) {
-                if (warp == 0) {
-                    double t = 0;
-                    for (int k = j + lane; k < Np; k += 32) t += row(k)[k];
-                    t = warp_sum_d(t);
-                    if (lane == 0) s_tau = t - s_late[j];
+        // class-boundary test (see above); tau = trace of the current Schur complement - information that has not started yet
+        auto pivot_ok = [&](int j, double p) -> bool { return j >= Np || p >= fmax(1e-12, 1e-12 * s_gd[j]); };
+        auto is_boundary = [&](int j) -> bool { return boundaries && j > 0 && j < Np && s_late[j] > s_late[j + 1]; };
+        auto on_column = [&](int j, bool dep, bool isb, double tau, double cn) -> bool {
+            if (isb) {
+                const double tt = tau - s_late[j];
+                const int dd = j - q;
+                if (dd >= 1) {
+                    if (tt < 1e-8) { mode = 2; kcut = j; jstop = j; return false; }      // exhausted: the reference cuts, later classes are discarded
+                    if (tt < 1e-3 || dd >= 2) {                                          // only the reference's own sweep can tell
+                        if (Q.world == 1) { mode = 3; jstop = j; return false; }
+                        undecided = true;                                                // feature-sharded: keep everything, say so
+                    }
                 }
-                __syncthreads();
-                const double tau = s_tau;
-                __syncthreads();
-                if (!boundary_decision(j, tau)) { jstop = j; break; }
             }
-            const double* rj = row(j);
-            const double pj = rj[j];
-            const bool dep = !(pj >= fmax(1e-12, 1e-12 * s_gd[j]));
-            if (tid == 0) s_pv[j] = dep ? -1.0 : pj;
-            after_pivot(j, dep);
-            if (dep) continue;                                     // nothing changes: no barrier needed
-            const int i = j + 1 + tid;
-            if (i < Np) {
-                const double f = -rj[i] / pj;
-                double* __restrict__ ri = row(i);
-                const double* __restrict__ rjj = rj;
-                int k = i;
-                for (; k + 8 <= Np + 1; k += 8) {                  // 8 loads in flight, then 8 stores (the rows do not alias)
-                    double a[8], b[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { a[u] = rjj[k + u]; b[u] = ri[k + u]; }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
-                }
-                for (; k <= Np; ++k) ri[k] = fma(f, rjj[k], ri[k]);
-            }
-            __syncthreads();
-        }
-        __syncthreads();
-        PHASE_CLK(18);
-        // rows of R: U(j, j..) / sqrt(p_j); the right-hand side becomes y
-        for (int j = warp; j < jstop; j += kSFThreads / 32) {
-            if (s_pv[j] < 0.0) continue;
-            const double rs = rsqrt(s_pv[j]);
-            double* rj = row(j);
-            for (int k = j + lane; k <= Np; k += 32) {
-                const double v = rj[k] * rs;
-                if (PACKED) L[(size_t)j * ldl + k] = v; else rj[k] = v;
-            }
-        }
+            if (!dep) q++; else if (first_dep == Np) first_dep = j;
+            if (tid == 0) s_nr2[j] = dep ? 0.0 : cn;
+            return true;
+        };
+        if (Np > 0) tile_cholesky<true>(T, ncp + 1, Np, pivot_ok, is_boundary, on_column, s_pv, s_part);
+        else __syncthreads();
     }
+    PHASE_CLK(18);
     __syncthreads();
-    PHASE_CLK(19);
     if (raw_top) { if (Q.world == 1) mode = 3; else undecided = true; }
     const int jend = (mode == 2) ? kcut : jstop;                  // columns whose rows may be kept
     // the reference's own test on the rows that are unique (before the first dependent column): norm < 1e-4 (Updater.cc:519)
     const int ulim = rule ? min(first_dep, jend) : 0;
-    for (int j = warp; j < jend; j += kSFThreads / 32) {
-        if (s_pv[j] < 0.0) { if (lane == 0) s_nr2[j] = 0.0; continue; }
-        const double* cj = L + (size_t)j * ldl;
-        double sq = 0;
-        for (int i = j + lane; i < Np; i += 32) sq += cj[i] * cj[i];
-        sq = warp_sum_d(sq);
-        if (lane == 0) { s_nr2[j] = sq; if (j < ulim && sq < 1e-8) atomicMin(&s_k, j); }
-    }
+    for (int j = tid; j < ulim; j += kBCThreads)
+        if (s_pv[j] >= 0.0 && s_nr2[j] < 1e-8) atomicMin(&s_k, j);
     __syncthreads();
-    PHASE_CLK(20);
+    PHASE_CLK(19);
     int kept_rows = q;
     bool rebuild = false, discards = false, generic = false;
     int klim = jend;             // columns with index < klim (and a good pivot) are kept
@@ -258,121 +410,159 @@ __global__ void __launch_bounds__(kSFThreads, 1) k_rank_rule(RankRuleParams Q)
         cnt[6] = rule ? (double)kept_rows : (double)rows;
         cnt[7] = (rebuild ? 8.0 : 0.0) + (discards ? 1.0 : 0.0) + (mode == 4 ? 4.0 : 0.0) + (generic ? 16.0 : 0.0);
     }
+    PHASE_CLK(20);
     if (Q.emit_R && mode != 3) {
-        // kept rows of R (= columns of L with a good pivot below klim), zero padded to n x n, and y
+        // kept rows of R (= columns of L with a good pivot below klim), zero padded to n x n, and y.  Lane (a, b) of a warp
+        // takes R(j0 + b, i0 + a .. ): 8 columns j of one tile row (contiguous in shared memory), 4 consecutive i per row of R
         const int kl = klim;
-        for (int o = tid; o < n * n; o += kSFThreads) {
-            const int j = o / n, i = o - j * n;
-            double v = 0;
-            if (j < kl && j < Np && s_pv[j] >= 0.0 && i >= j && i < Np) v = L[(size_t)j * ldl + i];
-            Q.Rc[o] = v;
+        const int ib = (n + 3) >> 2, jb = (n + 7) >> 3;
+        for (int blk = warp; blk < ib * jb; blk += kBCWarps) {
+            const int j = 8 * (blk / ib) + (lane & 7), i = 4 * (blk % ib) + (lane >> 3);
+            if (i < n && j < n) {
+                double v = 0;
+                if (j < kl && j < Np && s_pv[j] >= 0.0 && i >= j && i < Np) v = *T.at(i, j);
+                Q.Rc[(size_t)j * n + i] = v;
+            }
         }
-        for (int j = tid; j < n; j += kSFThreads) Q.yc[j] = (j < kl && j < Np && s_pv[j] >= 0.0) ? L[(size_t)j * ldl + Np] : 0.0;
+        for (int j = tid; j < n; j += kBCThreads) Q.yc[j] = (j < kl && j < Np && s_pv[j] >= 0.0) ? *T.at(ncp, j) : 0.0;
     }
     PHASE_CLK(21);
     if (!rebuild) return;
     // G' = sum_{kept j} L_j L_j^T ,  z' = sum_{kept j} L_j y_j   (bitwise symmetric: products commute)
     double* Gw = Q.red; double* zw = Q.red + (size_t)n * n;
-    for (int o = tid; o < Np * Np; o += kSFThreads) {
+    for (int o = tid; o < Np * Np; o += kBCThreads) {
         const int r = o / Np, c = o - r * Np;
         const int lim = min(klim, min(r, c) + 1);
         double acc = 0;
         for (int j = 0; j < lim; ++j)
-            if (s_pv[j] >= 0.0) acc = fma(L[(size_t)j * ldl + r], L[(size_t)j * ldl + c], acc);
+            if (s_pv[j] >= 0.0) acc = fma(*T.at(r, j), *T.at(c, j), acc);
         Gw[(size_t)r * n + c] = acc;
     }
-    for (int r = tid; r < Np; r += kSFThreads) {
+    for (int r = tid; r < Np; r += kBCThreads) {
         const int lim = min(klim, r + 1);
         double acc = 0;
         for (int j = 0; j < lim; ++j)
-            if (s_pv[j] >= 0.0) acc = fma(L[(size_t)j * ldl + r], L[(size_t)j * ldl + Np], acc);
+            if (s_pv[j] >= 0.0) acc = fma(*T.at(r, j), *T.at(ncp, j), acc);
         zw[r] = acc;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, one thread per row, packed triangle in shared memory), then  Y = L^-1 [W | y]
-// (k_trsm, one CTA per 8 right-hand-side columns, L in shared memory).
+// Large-window EKF step, serial part:  S = L L^T (k_chol_S, one CTA, blocked / DMMA as above), then  Y = L^-1 [W | y]
+// (k_trsm: one warp per 8 right-hand-side columns, tile row by tile row on the tensor pipe; the diagonal blocks are applied
+// through their inverses, which k_chol_S leaves in the diagonal tiles of the factor it writes out).
+// Lt: tile-packed lower factor in global memory, tile (I, J) at (I (I + 1) / 2 + J) * 64; diagonal tiles = inv(L_II).
 // ------------------------------------------------------------------------------------------------
-constexpr int kCholThreads = 192;
-__global__ void __launch_bounds__(kCholThreads, 1) k_chol_S(const double* S, int m, double* Lp, double* invd, int* bad, const double* gate)
+__global__ void __launch_bounds__(kBCThreads, 1) k_chol_S(const double* S, int m, double* Lt, int* bad, const double* gate)
 {
-    extern __shared__ __align__(16) double csm[];                // lower triangle, row i at i (i + 1) / 2
-    __shared__ double s_rs[kSFMaxRows + 8];
+    extern __shared__ __align__(16) double csm[];                // tile-packed lower triangle, then tc tiles for the inverses
+    __shared__ double s_pv[kSFMaxRows];
     if (gate && !(gate[0] > 2.0)) return;
     const int tid = threadIdx.x;
-    double* A = csm;
-    for (int o = tid; o < m * m; o += kCholThreads) {
+    TileTri T;
+    T.t = csm; T.tc = (m + 7) >> 3; T.tr = T.tc;
+    const int ntile = tile_tri_count(T.tc, T.tc);
+    double* X = csm + (size_t)ntile * 64;
+    for (int o = tid; o < (ntile + T.tc) * 64; o += kBCThreads) csm[o] = 0.0;
+    __syncthreads();
+    for (int o = tid; o < m * m; o += kBCThreads) {
         const int r = o / m, c = o - r * m;
-        if (c <= r) A[r * (r + 1) / 2 + c] = S[(size_t)r * m + c];
+        if (c <= r) *T.at(r, c) = S[(size_t)r * m + c];
+    }
+    for (int j = m + tid; j < 8 * T.tc; j += kBCThreads) *T.at(j, j) = 1.0;
+    PHASE_CLK(32);
+    auto pivot_ok = [&](int j, double p) -> bool { const bool ok = p > 0.0; if (!ok && tid == 0) *bad = 1; return ok; };
+    auto no_boundary = [](int) -> bool { return false; };
+    auto no_column = [](int, bool, bool, double, double) -> bool { return true; };
+    tile_cholesky<false>(T, 8 * T.tc, 0, pivot_ok, no_boundary, no_column, s_pv, nullptr);
+    PHASE_CLK(33);
+    // inverses of the diagonal tiles: thread (J, c) solves L_JJ x = e_c
+    for (int w = tid; w < T.tc * 8; w += kBCThreads) {
+        const int J = w >> 3, c = w & 7;
+        const double* Lj = T.tile(J, J);
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double acc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < r; ++k) acc = fma(-Lj[r * 8 + k], (k >= c) ? x[k] : 0.0, acc);
+            const double dg = Lj[r * 8 + r];
+            x[r] = (r >= c && dg > 0.0) ? acc / dg : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) X[J * 64 + r * 8 + c] = x[r];
     }
     __syncthreads();
-    // right-looking Cholesky, one thread per row: A(i,k) -= A(i,j) / p * A(k,j), k = j+1 .. i; columns unscaled until the end
-    const int i = tid;
-    double* __restrict__ ri = A + i * (i + 1) / 2;
-    for (int j = 0; j < m; ++j) {
-        const double p = A[j * (j + 1) / 2 + j];
-        if (!(p > 0.0)) { if (tid == 0) *bad = 1; }
-        if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
-        if (i > j && i < m && p > 0.0) {
-            const double f = -ri[j] / p;
-            int offk = (j + 1) * (j + 2) / 2 + j;                  // A(k, j), k = j + 1
-            int k = j + 1;
-            for (; k + 8 <= i + 1; k += 8) {
-                double a[8], b[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { a[u] = A[offk]; offk += k + u + 1; b[u] = ri[k + u]; }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
-            }
-            for (; k <= i; ++k) { ri[k] = fma(f, A[offk], ri[k]); offk += k + 1; }
-        }
-        __syncthreads();
-    }
-    // the factor, column packed (what k_trsm reads): column j at j m - j (j-1) / 2, element i at + (i - j)
-    for (int o = tid; o < m * m; o += kCholThreads) {
-        const int r = o / m, c = o - r * m;
-        if (c <= r) Lp[((size_t)c * m - (size_t)c * (c - 1) / 2) + (r - c)] = A[r * (r + 1) / 2 + c] * s_rs[c];
-    }
-    for (int j = tid; j < m; j += kCholThreads) invd[j] = s_rs[j];
+    for (int o = tid; o < ntile * 64; o += kBCThreads) Lt[o] = csm[o];
+    __syncthreads();
+    for (int o = tid; o < T.tc * 64; o += kBCThreads) { const int J = o >> 6; Lt[((size_t)(J * (J + 1) / 2 + J) << 6) + (o & 63)] = X[o]; }
+    PHASE_CLK(34);
 }
 
-// B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  Lp: packed lower factor (column j
-// at j m - j (j-1) / 2), invd[j] = 1 / L(j,j).  One CTA per kTrsmCols columns, one thread per row, the factor in shared memory.
-constexpr int kTrsmCols = 8;
-__global__ void __launch_bounds__(192) k_trsm(const double* Lp, const double* invd, int m, double* B, int ldb, int nb, const double* gate)
+// B: m x nb row-major right-hand sides (leading dimension ldb); solves L Y = B in place.  One warp per 8 columns:
+//   for every tile row I:  C = B_I - sum_{K<I} L(I,K) Y_K   (DMMA, Y_K kept transposed in shared memory so that its fragment
+//   is one LDS.128),  Y_I = inv(L_II) C  (one more tile product through a transposed scratch tile).
+constexpr int kTrsmWarps = 4;
+__global__ void __launch_bounds__(kTrsmWarps * 32) k_trsm(const double* Lt, int m, double* B, int ldb, int nb, const double* gate)
 {
-    extern __shared__ __align__(16) double sL[];                 // packed lower triangle, then invd[m]
-    __shared__ double s_y[2][kTrsmCols];
+    extern __shared__ __align__(16) double sL[];                 // the factor's tiles, then per warp: tc transposed Y tiles + 1 scratch tile
     if (gate && !(gate[0] > 2.0)) return;
-    const int tid = threadIdx.x;
-    const int c0 = blockIdx.x * kTrsmCols;
-    const int np = m * (m + 1) / 2;
-    double* sI = sL + np;
-    for (int e = tid; e < np; e += 192) sL[e] = Lp[e];           // linear copy: many loads in flight
-    for (int e = tid; e < m; e += 192) sI[e] = invd[e];
-    double b[kTrsmCols];
-#pragma unroll
-    for (int c = 0; c < kTrsmCols; ++c) b[c] = (tid < m && c0 + c < nb) ? B[(size_t)tid * ldb + c0 + c] : 0.0;
-    __syncthreads();
-    int buf = 0;
-    for (int j = 0; j < m; ++j) {
-        const int off = j * m - j * (j - 1) / 2 - j;             // column j, element i at off + i
-        if (tid == j) {
-            const double inv = sI[j];
-#pragma unroll
-            for (int c = 0; c < kTrsmCols; ++c) { b[c] *= inv; s_y[buf][c] = b[c]; }
-        }
-        __syncthreads();
-        if (tid > j && tid < m) {
-            const double l = sL[off + tid];
-#pragma unroll
-            for (int c = 0; c < kTrsmCols; ++c) b[c] = fma(-l, s_y[buf][c], b[c]);
-        }
-        buf ^= 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int tc = (m + 7) >> 3;
+    const int ntile = tile_tri_count(tc, tc);
+    {
+        const double2* src = reinterpret_cast<const double2*>(Lt);
+        double2* dst = reinterpret_cast<double2*>(sL);
+        for (int e = tid; e < ntile * 32; e += kTrsmWarps * 32) dst[e] = src[e];      // linear copy: many loads in flight
     }
-#pragma unroll
-    for (int c = 0; c < kTrsmCols; ++c) if (tid < m && c0 + c < nb) B[(size_t)tid * ldb + c0 + c] = b[c];
+    double* YT = sL + (size_t)ntile * 64 + (size_t)warp * (tc + 1) * 64;
+    double* CT = YT + (size_t)tc * 64;
+    __syncthreads();
+    const int col0 = (blockIdx.x * kTrsmWarps + warp) * 8;
+    if (col0 >= nb) return;
+    const int cj = col0 + 2 * t4;
+    for (int I = 0; I < tc; ++I) {
+        const int row = 8 * I + g;
+        double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+        if (row < m) {
+            if (cj < nb) c0.x = B[(size_t)row * ldb + cj];
+            if (cj + 1 < nb) c0.y = B[(size_t)row * ldb + cj + 1];
+        }
+        const double* lrow = sL + ((size_t)(I * (I + 1) / 2) << 6) + g * 8 + 2 * t4;
+        int K = 0;
+        for (; K + 1 < I; K += 2) {                              // two accumulators: the chain of dependent DMMAs is halved
+            double2 a0 = *reinterpret_cast<const double2*>(lrow + K * 64), a1 = *reinterpret_cast<const double2*>(lrow + K * 64 + 64);
+            const double2 y0 = *reinterpret_cast<const double2*>(YT + K * 64 + g * 8 + 2 * t4);
+            const double2 y1 = *reinterpret_cast<const double2*>(YT + K * 64 + 64 + g * 8 + 2 * t4);
+            a0.x = -a0.x; a0.y = -a0.y; a1.x = -a1.x; a1.y = -a1.y;
+            dmma884(c0.x, c0.y, a0.x, y0.x);
+            dmma884(c1.x, c1.y, a1.x, y1.x);
+            dmma884(c0.x, c0.y, a0.y, y0.y);
+            dmma884(c1.x, c1.y, a1.y, y1.y);
+        }
+        if (K < I) {
+            double2 a0 = *reinterpret_cast<const double2*>(lrow + K * 64);
+            const double2 y0 = *reinterpret_cast<const double2*>(YT + K * 64 + g * 8 + 2 * t4);
+            a0.x = -a0.x; a0.y = -a0.y;
+            tile_mma(c0, a0, y0);
+        }
+        c0.x += c1.x; c0.y += c1.y;
+        // C (rows g, columns 2t, 2t+1) -> scratch, transposed: CT[column][row]
+        CT[(2 * t4) * 8 + g] = c0.x;
+        CT[(2 * t4 + 1) * 8 + g] = c0.y;
+        __syncwarp();
+        const double2 xi = *reinterpret_cast<const double2*>(lrow + I * 64);          // inv(L_II)[g][2t..]
+        const double2 ct = *reinterpret_cast<const double2*>(CT + g * 8 + 2 * t4);     // C[2t..][g]
+        double2 y = make_double2(0.0, 0.0);
+        tile_mma(y, xi, ct);
+        YT[I * 64 + (2 * t4) * 8 + g] = y.x;
+        YT[I * 64 + (2 * t4 + 1) * 8 + g] = y.y;
+        if (row < m) {
+            if (cj < nb) B[(size_t)row * ldb + cj] = y.x;
+            if (cj + 1 < nb) B[(size_t)row * ldb + cj + 1] = y.y;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,158 +599,147 @@ __device__ __forceinline__ void sr_apply_dq(const double* dth, const double* q, 
     sr_quat_mul(dq, q, out);
 }
 
-constexpr int kSRThreads = 256;
+constexpr int kSRThreads = kBCThreads;
+// shared-memory tiles of k_solve_small_R: T (S + extra rows), R (upper triangle by tile), Pc (extra tile rows x tile columns)
+__host__ __device__ inline int solve_small_tiles(int n, int d)
+{
+    const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
+    return tile_tri_count(tc, tc + tre) + tc * (tc + 1) / 2 + tre * tc;
+}
 __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRParams Q)
 {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double s_rs[kSFMaxRows];
+    __shared__ double s_pv[kSFMaxRows];
     __shared__ double s_dx[kSFMaxRows];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int N = Q.N, n = 6 * N, d = Q.d;
     if (!(Q.gate[0] > 2.0)) {                                      // Updater.cc:621-627: too few features, posterior = prior
         for (int o = tid; o < d * d; o += kSRThreads) Q.P_out[o] = Q.P[o];
         for (int o = tid; o < Q.xdim; o += kSRThreads) Q.x_out[o] = Q.x[o];
         return;
     }
-    // A: (n + d + 1) x lda.  Rows 0..n-1: lower triangle of S, then of its Cholesky factor.  Rows n + c: column c of [W | y],
-    // after the factorisation column c of Y = L^-1 [W | y] (the right-hand sides ride along as extra rows).
-    const int rows_total = n + d + 1;
-    const int lda = n + 1, ldp = d + 1;                            // both odd: rows of consecutive threads fall into different banks
-    double* A = sm;
-    double* sR = A + (size_t)rows_total * lda;                     // n x lda
-    double* sP = sR + (size_t)n * lda;                             // n x ldp: P[c,:]
+    // T: rows 0 .. 8 tc - 1: lower triangle of S, then of its Cholesky factor (columns n .. 8 tc - 1: s^2 I padding).  Row
+    // 8 tc + c: column c of [W | y], after the factorisation column c of Y = L^-1 [W | y] (the right-hand sides ride along).
+    TileTri T;
+    T.t = sm; T.tc = (n + 7) >> 3;
+    const int tc = T.tc, tre = (d + 1 + 7) >> 3, ncp = 8 * tc;
+    T.tr = tc + tre;
+    double* Rt = sm + (size_t)tile_tri_count(tc, T.tr) * 64;       // tile (Rj, Kb), Kb >= Rj, at (Rj tc - Rj (Rj - 1) / 2 + Kb - Rj) * 64: R(8 Rj + r, 8 Kb + k) at [r][k]
+    double* Pt = Rt + (size_t)(tc * (tc + 1) / 2) * 64;             // tile (Ci, Kb) at (Ci tc + Kb) * 64: Pc(8 Kb + k, 8 Ci + c) at [c][k]
+    auto rtile = [&](int Rj, int Kb) -> double* { return Rt + ((size_t)(Rj * tc - (Rj * (Rj - 1)) / 2 + Kb - Rj) << 6); };
     PHASE_CLK(0);
-    for (int o = tid; o < n * n; o += kSRThreads) { const int r = o / n, c = o - r * n; sR[r * lda + c] = Q.Rc[o]; }
-    for (int o = tid; o < n * d; o += kSRThreads) { const int j = o / n, k = o - j * n; sP[k * ldp + j] = Q.P[(size_t)j * d + 24 + k]; }   // P(24+k, j)
+    for (int o = tid; o < (tc * (tc + 1) / 2) * 64; o += kSRThreads) {
+        // decode (tile, r, k): tiles of row Rj are consecutive
+        const int tl = o >> 6, e = o & 63;
+        int Rj = 0, rem = tl;
+        while (rem >= tc - Rj) { rem -= tc - Rj; ++Rj; }
+        const int r = 8 * Rj + (e >> 3), k = 8 * (Rj + rem) + (e & 7);
+        Rt[o] = (r < n && k < n) ? Q.Rc[(size_t)r * n + k] : 0.0;
+    }
+    for (int o = tid; o < tre * tc * 64; o += kSRThreads) {
+        const int tl = o >> 6, e = o & 63;
+        const int Ci = tl / tc, Kb = tl - Ci * tc;
+        const int c = 8 * Ci + (e >> 3), k = 8 * Kb + (e & 7);
+        Pt[o] = (c < d && k < n) ? Q.P[(size_t)c * d + 24 + k] : 0.0;          // P(c, 24 + k) = Pc(k, c)
+    }
     __syncthreads();
     PHASE_CLK(1);
-    // ---- W = R P[c,:]  (R upper triangular), written transposed into the extra rows of A
-    {
-        const int tr_n = (n + 1) / 2, tc_n = (d + 3) / 4;
-        for (int t = tid; t < tr_n * tc_n; t += kSRThreads) {
-            const int r0 = 2 * (t / tc_n), j0 = 4 * (t % tc_n);
-            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-            const bool r1ok = r0 + 1 < n;
-            for (int k = r0; k < n; ++k) {
-                const double a0 = sR[r0 * lda + k], a1 = r1ok ? sR[(r0 + 1) * lda + k] : 0.0;
-                const double* pk = sP + k * ldp + j0;
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const double b = (j0 + y < d) ? pk[y] : 0.0;
-                    acc[0][y] = fma(a0, b, acc[0][y]);
-                    acc[1][y] = fma(a1, b, acc[1][y]);
-                }
-            }
-#pragma unroll
-            for (int y = 0; y < 4; ++y)
-                if (j0 + y < d) { A[(n + j0 + y) * lda + r0] = acc[0][y]; if (r1ok) A[(n + j0 + y) * lda + r0 + 1] = acc[1][y]; }
+    // ---- W^T tiles: Wt(Ci, Rj) = sum_{Kb >= Rj} Pt(Ci, Kb) Rt(Rj, Kb)^T   (R upper triangular)
+    for (int w = warp; w < tre * tc; w += kBCWarps) {
+        const int Ci = w / tc, Rj = w - Ci * tc;
+        double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+        int Kb = Rj;
+        for (; Kb + 1 < tc; Kb += 2) {
+            const double2 a0 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb) << 6) + g * 8 + 2 * t4);
+            const double2 a1 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb + 1) << 6) + g * 8 + 2 * t4);
+            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Rj, Kb) + g * 8 + 2 * t4);
+            const double2 b1 = *reinterpret_cast<const double2*>(rtile(Rj, Kb + 1) + g * 8 + 2 * t4);
+            dmma884(c0.x, c0.y, a0.x, b0.x);
+            dmma884(c1.x, c1.y, a1.x, b1.x);
+            dmma884(c0.x, c0.y, a0.y, b0.y);
+            dmma884(c1.x, c1.y, a1.y, b1.y);
         }
-        for (int r = tid; r < n; r += kSRThreads) A[(n + d) * lda + r] = Q.yc[r];
+        if (Kb < tc) {
+            const double2 a0 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb) << 6) + g * 8 + 2 * t4);
+            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Rj, Kb) + g * 8 + 2 * t4);
+            tile_mma(c0, a0, b0);
+        }
+        c0.x += c1.x; c0.y += c1.y;
+        // the row c = d of the extra rows is y, not a column of W
+        const int c = 8 * Ci + g, r = 8 * Rj + 2 * t4;
+        if (c == d) { c0.x = (r < n) ? Q.yc[r] : 0.0; c0.y = (r + 1 < n) ? Q.yc[r + 1] : 0.0; }
+        *reinterpret_cast<double2*>(T.tile(tc + Ci, Rj) + g * 8 + 2 * t4) = c0;
     }
     __syncthreads();
     PHASE_CLK(2);
-    // ---- S = W[:, 24:] R^T + s^2 I  (lower triangle; R[c][k] = 0 for k < c) into rows 0..n-1 of A
-    {
-        const int tn = (n + 1) / 2, tcn = (n + 3) / 4;
-        for (int t = tid; t < tn * tcn; t += kSRThreads) {
-            const int r0 = 2 * (t / tcn), c0 = 4 * (t % tcn);
-            if (c0 > r0 + 1) continue;                              // tile entirely above the diagonal
-            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-            const bool r1ok = r0 + 1 < n;
-            for (int k = c0; k < n; ++k) {
-                const double* wk = A + (n + 24 + k) * lda;          // W(:, 24 + k)
-                const double w0 = wk[r0], w1 = r1ok ? wk[r0 + 1] : 0.0;
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const double b = (c0 + y < n) ? sR[(c0 + y) * lda + k] : 0.0;
-                    acc[0][y] = fma(w0, b, acc[0][y]);
-                    acc[1][y] = fma(w1, b, acc[1][y]);
-                }
-            }
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int c = c0 + y;
-                if (c < n) {
-                    if (c <= r0) A[r0 * lda + c] = acc[0][y] + (c == r0 ? Q.sig2 : 0.0);
-                    if (r1ok && c <= r0 + 1) A[(r0 + 1) * lda + c] = acc[1][y] + (c == r0 + 1 ? Q.sig2 : 0.0);
-                }
-            }
+    // ---- S tiles (lower): S(Ri, Cj) = sum_{Kb >= Cj} Wc(Ri, Kb) Rt(Cj, Kb)^T + s^2 I ;  Wc(r, k) = W(r, 24 + k) = extra row 24 + k, column r
+    for (int w = warp; w < tc * (tc + 1) / 2; w += kBCWarps) {
+        int Ri = 0, rem = w;
+        while (rem > Ri) { rem -= Ri + 1; ++Ri; }
+        const int Cj = rem;
+        double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+        for (int Kb = Cj; Kb < tc; ++Kb) {
+            const double* wt = T.tile(tc + 3 + Kb, Ri);                                  // [k][r]
+            const double a0 = wt[(2 * t4) * 8 + g], a1 = wt[(2 * t4 + 1) * 8 + g];
+            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Cj, Kb) + g * 8 + 2 * t4);
+            if ((Kb - Cj) & 1) { dmma884(c1.x, c1.y, a0, b0.x); dmma884(c1.x, c1.y, a1, b0.y); }
+            else { dmma884(c0.x, c0.y, a0, b0.x); dmma884(c0.x, c0.y, a1, b0.y); }
         }
+        c0.x += c1.x; c0.y += c1.y;
+        if (Ri == Cj) { if (g == 2 * t4) c0.x += Q.sig2; if (g == 2 * t4 + 1) c0.y += Q.sig2; }
+        *reinterpret_cast<double2*>(T.tile(Ri, Cj) + g * 8 + 2 * t4) = c0;
     }
-    __syncthreads();
     PHASE_CLK(3);
-    // ---- right-looking Cholesky, ONE THREAD PER ROW (rows of S and the extra rows alike): at step j row i does
-    //      A(i,k) -= A(i,j) / p * A(k,j) for k = j+1 .. min(i, n-1).  Columns stay unscaled until the end (every thread reads
-    //      column j while its owners would be rescaling it).  One barrier per step; the work of a step is the remaining row.
+    // ---- blocked Cholesky; the extra rows become Y^T
     {
-        const int i = tid;
-        for (int j = 0; j < n; ++j) {
-            const double p = A[j * lda + j];
-            if (!(p > 0.0)) { if (tid == 0) *Q.bad = 1; }
-            if (tid == 0) s_rs[j] = (p > 0.0) ? rsqrt(p) : 0.0;
-            if (i > j && i < rows_total && p > 0.0) {
-                double* __restrict__ ri = A + i * lda;
-                const double f = -ri[j] / p;
-                const int kmax = min(i, n - 1);
-                const double* __restrict__ cj = A + j;             // column j: A(k, j) = cj[k * lda] (never written during step j)
-                int k = j + 1;
-                for (; k + 8 <= kmax + 1; k += 8) {
-                    double a[8], b[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { a[u] = cj[(k + u) * lda]; b[u] = ri[k + u]; }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) ri[k + u] = fma(f, a[u], b[u]);
-                }
-                for (; k <= kmax; ++k) ri[k] = fma(f, cj[k * lda], ri[k]);
-            }
-            __syncthreads();
+        auto pivot_ok = [&](int j, double p) -> bool { const bool ok = p > 0.0; if (!ok && tid == 0) *Q.bad = 1; return ok; };
+        auto no_boundary = [](int) -> bool { return false; };
+        auto no_column = [](int, bool, bool, double, double) -> bool { return true; };
+        tile_cholesky<false>(T, ncp + d + 1, 0, pivot_ok, no_boundary, no_column, s_pv, nullptr);
+    }
+    PHASE_CLK(4);
+    // ---- P+ = sym(P) - Y^T Y on the upper tile triangle (mirrored); the column j = d of Y^T Y is dx = Y^T y~
+    for (int w = warp; w < tre * (tre + 1) / 2; w += kBCWarps) {
+        int Jj = 0, rem = w;
+        while (rem > Jj) { rem -= Jj + 1; ++Jj; }
+        const int Ii = rem;                                                              // Ii <= Jj
+        const int i = 8 * Ii + g, j = 8 * Jj + 2 * t4;
+        double p00 = 0, p01 = 0, q0 = 0, q1 = 0;                                         // P(i, j), P(i, j+1), P(j, i), P(j+1, i): issued before the products
+        if (i < d && j < d) { p00 = Q.P[(size_t)i * d + j]; q0 = Q.P[(size_t)j * d + i]; }
+        if (i < d && j + 1 < d) { p01 = Q.P[(size_t)i * d + j + 1]; q1 = Q.P[(size_t)(j + 1) * d + i]; }
+        double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+        const double* ai = T.tile(tc + Ii, 0) + g * 8 + 2 * t4;
+        const double* bj = T.tile(tc + Jj, 0) + g * 8 + 2 * t4;
+        int Kb = 0;
+        for (; Kb + 1 < tc; Kb += 2) {
+            const double2 a0 = *reinterpret_cast<const double2*>(ai + Kb * 64), a1 = *reinterpret_cast<const double2*>(ai + Kb * 64 + 64);
+            const double2 b0 = *reinterpret_cast<const double2*>(bj + Kb * 64), b1 = *reinterpret_cast<const double2*>(bj + Kb * 64 + 64);
+            dmma884(c0.x, c0.y, a0.x, b0.x);
+            dmma884(c1.x, c1.y, a1.x, b1.x);
+            dmma884(c0.x, c0.y, a0.y, b0.y);
+            dmma884(c1.x, c1.y, a1.y, b1.y);
         }
-        PHASE_CLK(4);
-        for (int o = tid; o < rows_total * n; o += kSRThreads) {   // scale the columns: L(i,j) = A(i,j) / sqrt(p_j)
-            const int r = o / n, c = o - r * n;
-            if (c <= r) A[r * lda + c] *= s_rs[c];
+        if (Kb < tc) {
+            const double2 a0 = *reinterpret_cast<const double2*>(ai + Kb * 64);
+            const double2 b0 = *reinterpret_cast<const double2*>(bj + Kb * 64);
+            tile_mma(c0, a0, b0);
+        }
+        c0.x += c1.x; c0.y += c1.y;
+        if (i < d) {
+            if (j < d) {
+                const double v = .5 * (p00 + q0) - c0.x;
+                Q.P_out[(size_t)i * d + j] = v;
+                if (Ii != Jj) Q.P_out[(size_t)j * d + i] = v;
+            } else if (j == d) s_dx[i] = c0.x;
+            if (j + 1 < d) {
+                const double v = .5 * (p01 + q1) - c0.y;
+                Q.P_out[(size_t)i * d + j + 1] = v;
+                if (Ii != Jj) Q.P_out[(size_t)(j + 1) * d + i] = v;
+            } else if (j + 1 == d) s_dx[i] = c0.y;
         }
     }
     __syncthreads();
     PHASE_CLK(5);
-    // ---- dx = Y^T y~ ;  Y(j, c) = A(n + c, j)
-    for (int c = tid; c < d; c += kSRThreads) {
-        const double* yc_ = A + (n + c) * lda; const double* yd = A + (n + d) * lda;
-        double acc = 0;
-        for (int k = 0; k < n; ++k) acc = fma(yc_[k], yd[k], acc);
-        s_dx[c] = acc;
-    }
-    // ---- P+ = sym(P) - Y^T Y
-    {
-        const int tn = (d + 1) / 2, tcn = (d + 3) / 4;
-        for (int t = tid; t < tn * tcn; t += kSRThreads) {
-            const int i0 = 2 * (t / tcn), j0 = 4 * (t % tcn);
-            double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-            const bool i1ok = i0 + 1 < d;
-            const double* u0p = A + (n + i0) * lda; const double* u1p = i1ok ? u0p + lda : u0p;
-            const double* vp[4];
-#pragma unroll
-            for (int y = 0; y < 4; ++y) vp[y] = A + (n + min(j0 + y, d - 1)) * lda;
-            for (int k = 0; k < n; ++k) {
-                const double u0 = u0p[k], u1 = u1p[k];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const double b = vp[y][k];
-                    acc[0][y] = fma(u0, b, acc[0][y]);
-                    acc[1][y] = fma(u1, b, acc[1][y]);
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < 2; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int i = i0 + x, j = j0 + y;
-                    if (i < d && j < d) Q.P_out[(size_t)j * d + i] = .5 * (Q.P[(size_t)j * d + i] + Q.P[(size_t)i * d + j]) - acc[x][y];
-                }
-        }
-    }
-    __syncthreads();
-    PHASE_CLK(6);
     // ---- state correction (Updater.cc:546-613)
     const double* x = Q.x; double* xo = Q.x_out; const double* dx = s_dx;
     for (int bq = tid; bq < 2 + N; bq += kSRThreads) {
@@ -572,13 +751,15 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         if (bq >= 2) for (int k = 0; k < 3; ++k) xo[xq + 4 + k] = dx[eq + 3 + k] + x[xq + 4 + k];
     }
     if (tid == 64) {
-        double g[3];
+        double g3[3];
         for (int k = 0; k < 3; ++k) xo[4 + k] = dx[3 + k] + x[4 + k];
-        for (int k = 0; k < 3; ++k) g[k] = dx[6 + k] + x[7 + k];
-        const double nn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
-        for (int k = 0; k < 3; ++k) xo[7 + k] = g[k] / nn;
+        for (int k = 0; k < 3; ++k) g3[k] = dx[6 + k] + x[7 + k];
+        const double nn = sqrt(g3[0] * g3[0] + g3[1] * g3[1] + g3[2] * g3[2]);
+        for (int k = 0; k < 3; ++k) xo[7 + k] = g3[k] / nn;
+        for (int k = 0; k < 3; ++k) { }
         for (int k = 0; k < 12; ++k) xo[14 + k] = dx[12 + k] + x[14 + k];
     }
+    PHASE_CLK(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -764,24 +945,18 @@ size_t givens_smem_bytes(int n, bool* smem_window)
     return sizeof(double) * ((size_t)n + 8);
 }
 
-size_t solve_small_smem_bytes(int n, int d)
-{
-    return sizeof(double) * ((size_t)(n + d + 1) * (n + 1) + (size_t)n * (n + 1) + (size_t)n * (d + 1) + 16);
-}
+size_t solve_small_smem_bytes(int n, int d) { return sizeof(double) * 64 * (size_t)solve_small_tiles(n, d) + 64; }
+static size_t rank_rule_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)tile_tri_count(tc, tc + 1) + 64; }
+static size_t chol_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + tc) + 64; }
+static size_t trsm_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + kTrsmWarps * (tc + 1)) + 64; }
 
-constexpr int kRankSmallMaxN = 96;        // windows up to 16 clones: one thread per row of the factor in shared memory
-constexpr int kSolveSmallRMaxN = 72;      // windows up to 12 clones: the whole EKF step in one CTA (197 KB of shared memory)
+constexpr int kSolveSmallRMaxN = 72;      // windows up to 12 clones: the whole EKF step in one CTA (166 KB of shared memory)
 
 int compress_configure(int nmax)
 {
-    {
-        const int ns = nmax < kRankSmallMaxN ? nmax : kRankSmallMaxN;
-        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)ns * ((ns + 2) | 1) + 8))));
-        if (nmax > kRankSmallMaxN)
-            RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)(nmax + 1) * (nmax + 2) / 2 + 8))));
-    }
-    // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every variant is
+    // a handle sized for nmax also serves smaller windows (the filter's warm-up, other configurations): every kernel is
     // given the largest dynamic shared memory it can be launched with
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_rank_rule, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_rule_smem_bytes(nmax)));
     bool w;
     size_t gv = givens_smem_bytes(nmax, &w);
     if (!w) {
@@ -793,17 +968,16 @@ int compress_configure(int nmax)
         const int ns = nmax < kSolveSmallRMaxN ? nmax : kSolveSmallRMaxN;
         RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small_R, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem_bytes(ns, 24 + ns)));
     }
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_chol_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + 8))));
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)nmax * (nmax + 1) / 2 + nmax + 8))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_chol_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(nmax)));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(nmax)));
     return RVIO_OK;
 }
 
 // Enqueues the rank rule on [G | z | counters | classes] (after the all-reduce in the feature-sharded form).
 int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq_in, int n)
 {
-    if (n + 1 > kSFMaxRows) { set_error("enqueue_rank_rule", "window too large"); return RVIO_ERR_CAPACITY; }
-    if (n <= kRankSmallMaxN) RVIO_LAUNCH(k_rank_rule<false>, 1, kSFThreads, sizeof(double) * ((size_t)n * ((n + 2) | 1) + 8), s, rq);
-    else RVIO_LAUNCH(k_rank_rule<true>, 1, kSFThreads, sizeof(double) * ((size_t)(n + 1) * (n + 2) / 2 + 8), s, rq);
+    if (n + 9 > kSFMaxRows) { set_error("enqueue_rank_rule", "window too large"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_rank_rule, 1, kBCThreads, rank_rule_smem_bytes(n), s, rq);
     if (rq.world == 1) {
         bool w;
         const size_t gv = givens_smem_bytes(n, &w);
@@ -814,23 +988,23 @@ int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefP
     return RVIO_OK;
 }
 
-// Whole small-window EKF step in one CTA (n + d + 1 <= kSFMaxRows).
+// Whole small-window EKF step in one CTA.
 int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
 {
     const int n = 6 * q.N;
-    if (n > kSolveSmallRMaxN || n + q.d + 1 > kSRThreads) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
+    if (n > kSolveSmallRMaxN || 8 * ((n + 7) / 8) + q.d + 1 > kBCThreads) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
     RVIO_LAUNCH(k_solve_small_R, 1, kSRThreads, solve_small_smem_bytes(n, q.d), s, q);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }
 
-// Serial part of the large-window EKF step: S (n x n) -> L ; B (n x nb, leading dimension ldb) <- L^-1 B.
+// Serial part of the large-window EKF step: S (n x n) -> L (tile packed, needs tile_tri_count * 64 doubles of scratch: <= n x n + 64 n);
+// B (n x nb, leading dimension ldb) <- L^-1 B.
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate)
 {
-    if (n > kCholThreads) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
-    double* invd = L + (size_t)n * (n + 1) / 2;                 // the scratch is n x n: room for the packed factor and 1 / diag
-    RVIO_LAUNCH(k_chol_S, 1, kCholThreads, sizeof(double) * ((size_t)n * (n + 1) / 2 + 8), s, S, n, L, invd, bad, gate);
-    RVIO_LAUNCH(k_trsm, div_up(nb, kTrsmCols), 192, sizeof(double) * ((size_t)n * (n + 1) / 2 + n + 8), s, L, invd, n, B, ldb, nb, gate);
+    if (n + 8 > kBCThreads || n + 8 > kSFMaxRows) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_chol_S, 1, kBCThreads, chol_smem_bytes(n), s, S, n, L, bad, gate);
+    RVIO_LAUNCH(k_trsm, div_up(div_up(nb, 8), kTrsmWarps), kTrsmWarps * 32, trsm_smem_bytes(n), s, L, n, B, ldb, nb, gate);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

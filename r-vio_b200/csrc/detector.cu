@@ -459,7 +459,7 @@ int detector_create(Detector* D, int W, int H, int max_corners)
     RVIO_CUDA_TRY(cudaMalloc((void**)&D->mask, sizeof(float) * 31 * 31));
     RVIO_CUDA_TRY(cudaMemset(D->ctrl, 0, sizeof(DetCtrl)));
     RVIO_CUDA_TRY(cudaMallocHost((void**)&D->h_mask, sizeof(float) * 31 * 31));
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_det_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_det_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     D->mask_hw = -1;
     return RVIO_OK;
 }
@@ -484,7 +484,7 @@ int detector_enqueue(Detector* D, cudaStream_t st, const PyrLevel& level0, int s
     P.cell = (int)lrint(P.min_dist);
     P.gw = (D->W + P.cell - 1) / P.cell; P.gh = (D->H + P.cell - 1) / P.cell;
     const size_t smem = (size_t)kDetBlock * 16 + (((size_t)P.gw * P.gh + 15) & ~(size_t)15) + (size_t)P.gw * P.gh * kDetCellSlots * 4 + 64;
-    if (smem > 227 * 1024) { set_error("detector_enqueue", "minimum-distance grid does not fit in shared memory (Tracker.nMinDist too small for this image size)"); return RVIO_ERR_CAPACITY; }
+    if (smem > 200 * 1024) { set_error("detector_enqueue", "minimum-distance grid does not fit in shared memory (Tracker.nMinDist too small for this image size)"); return RVIO_ERR_CAPACITY; }
     if (D->mask_hw != P.hw) {                                        // cornerSubPix window weights (host libm, like OpenCV)
         const int ww = 2 * P.hw + 1;
         float mx[31];

@@ -1697,7 +1697,8 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     A(u->d_red, n * n + n + 8 + n + 1); A(u->d_M, n * n); A(u->d_R, n * (d + 1)); A(u->d_T, n * (n + d + 1)); A(u->d_Yt, n * (d + 1)); A(u->d_chi2, 500); A(u->d_sing, 1);
     A(u->d_tickets, (size_t)div_up((int)n, 32) * div_up((int)n, 32) + 64);
     A(u->d_rule, 4); A(u->d_rr, 8); A(u->d_L, n * (n + 1) + 8); A(u->d_gwin, givens_window_doubles((int)n));
-    A(u->d_Rc, n * n); A(u->d_yc, n); A(u->d_S, n * n); A(u->d_LS, n * n); A(u->d_W, n * (d + 1));
+    A(u->d_Rc, n * n); A(u->d_yc, n); A(u->d_S, n * n); A(u->d_LS, n * n + 64 * n + 64);      // d_LS: tile-packed factor (8 x 8 tiles of the padded lower triangle)
+    A(u->d_W, n * (d + 1));
 #undef A
 #define HA(p, cnt) if ((rc = uhalloc(u, &(p), (cnt))) != RVIO_OK) return rc
     HA(u->h_x, u->xmax); HA(u->h_P, d * d); HA(u->h_red, 16); HA(u->h_types, F + 1); HA(u->h_off, F + 2); HA(u->h_xy, 2 * (F * u->Lmax + 1)); HA(u->h_sing, 4); HA(u->h_rule, 4);

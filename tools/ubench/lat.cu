@@ -35,6 +35,10 @@ __global__ void k_chain(double* out, long long* cyc, double seed, int iseed)
         if (MODE == 12) x = 1.0 / x + 2.0;                       // DDIV + DADD
         if (MODE == 13) xu = max(xu + 1, (unsigned)xi) ^ 5u;     // IADD+MAX+LOP chain (3 dependent ALU)
         if (MODE == 14) { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+        if (MODE == 15) x = rsqrt(x) + 2.0;                      // rsqrt(double) + DADD
+        if (MODE == 16) { double c1 = y; asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(x), "+d"(c1) : "d"(y), "d"(y)); }   // dependent DMMA
+        if (MODE == 17) { double v = x; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); x = v * 1e-3; }   // warp sum of doubles
+        if (MODE == 18) x = sqrt(x) + 2.0;                       // sqrt(double) + DADD
     }
     long long t1 = clock64();
     if (threadIdx.x == 0) cyc[0] = t1 - t0;
@@ -62,12 +66,34 @@ __global__ void k_tp(double* out, long long* cyc, double seed)
     out[threadIdx.x] = s;
 }
 
+template <int K>
+__global__ void k_tp_dmma(double* out, long long* cyc, double seed)
+{
+    double x[K][2];
+    for (int k = 0; k < K; ++k) { x[k][0] = seed + k; x[k][1] = seed - k; }
+    const double y = seed * 0.5;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < N_IT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(x[k][0]), "+d"(x[k][1]) : "d"(y), "d"(y));
+    long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    double s = 0;
+    for (int k = 0; k < K; ++k) s += x[k][0] + x[k][1];
+    out[threadIdx.x] = s;
+}
+
 int main()
 {
     double* out; long long* cyc;
     cudaMalloc(&out, 8 * 1024); cudaMalloc(&cyc, 8);
     const char* names[] = {"DFMA", "DADD", "DMUL", "FFMA", "IMAD", "LDS chase", "REDUX", "SHFL", "F2F x2 + DADD", "MUFU.RCP", "bar.sync 0 (CTA)",
-                           "STS+LDS+DADD+2 syncwarp", "DDIV+DADD", "3 ALU", "bar.sync 1,96"};
+                           "STS+LDS+DADD+2 syncwarp", "DDIV+DADD", "3 ALU", "bar.sync 1,96",
+                           "rsqrt(double)+DADD", "DMMA m8n8k4 dependent", "warp_sum(double)", "sqrt(double)+DADD"};
     long long h;
 #define RUN(MODE, THREADS)                                                                  \
     for (int rep = 0; rep < 2; ++rep) k_chain<MODE><<<1, THREADS>>>(out, cyc, 1.000001, 3); \
@@ -75,12 +101,17 @@ int main()
     printf("%-28s threads %4d : %7.1f cycles / iteration\n", names[MODE], THREADS, (double)h / N_IT);
     RUN(0, 32) RUN(1, 32) RUN(2, 32) RUN(3, 32) RUN(4, 32) RUN(5, 32) RUN(6, 32) RUN(7, 32) RUN(8, 32) RUN(9, 32)
     RUN(10, 32) RUN(10, 96) RUN(10, 384) RUN(10, 1024) RUN(11, 32) RUN(12, 32) RUN(13, 32) RUN(14, 96)
-    RUN(0, 128) RUN(0, 384)
+    RUN(0, 128) RUN(0, 384) RUN(0, 256) RUN(15, 32) RUN(15, 256) RUN(16, 32) RUN(16, 256) RUN(17, 32) RUN(17, 256) RUN(18, 32) RUN(10, 256)
 #define TP(K, THREADS)                                                                      \
     for (int rep = 0; rep < 2; ++rep) k_tp<K><<<1, THREADS>>>(out, cyc, 1.000001);           \
     cudaDeviceSynchronize(); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);                \
     printf("DFMA throughput K=%2d threads %4d : %7.2f cycles / DFMA-per-thread, %6.1f DFMA/clk/SM\n", K, THREADS, (double)h / N_IT / K, (double)THREADS * K * N_IT / h);
     TP(1, 32) TP(8, 32) TP(16, 32) TP(8, 128) TP(8, 384) TP(8, 1024) TP(16, 384)
+#define TPM(K, THREADS)                                                                     \
+    for (int rep = 0; rep < 2; ++rep) k_tp_dmma<K><<<1, THREADS>>>(out, cyc, 1.000001);      \
+    cudaDeviceSynchronize(); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);                \
+    printf("DMMA throughput K=%2d threads %4d : %7.2f cycles / DMMA-per-warp, %6.1f FMA/clk/SM\n", K, THREADS, (double)h / N_IT / K, (double)(THREADS / 32) * K * N_IT * 256 / h);
+    TPM(1, 32) TPM(4, 32) TPM(8, 32) TPM(4, 128) TPM(4, 256) TPM(8, 256) TPM(4, 1024)
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
     return 0;
