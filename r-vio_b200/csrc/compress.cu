@@ -44,29 +44,6 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
-// Eight warp sums for the price of nine shuffles: after the call lane 4 m (m = 0 .. 7) holds the warp total of v[m]
-// (recursive halving over lane bits 4, 3, 2, then plain butterflies over bits 1, 0; fixed order -> deterministic).
-__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane)
-{
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-    double w[4], u[2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double send = h16 ? v[k] : v[k + 4], keep = h16 ? v[k + 4] : v[k];
-        w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const double send = h8 ? w[k] : w[k + 2], keep = h8 ? w[k + 2] : w[k];
-        u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const double send = h4 ? u[0] : u[1], keep = h4 ? u[1] : u[0];
-    double t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    return t;
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -90,9 +67,27 @@ __device__ long long g_phase_clk[64];
 #else
 #define PHASE_CLK(k) do { } while (0)
 #endif
-constexpr int kBCThreads = 256;           // threads of the blocked-Cholesky CTAs (8 warps; rows of the trapezoid <= 256)
+constexpr int kBCThreads = 512;           // threads of the blocked-Cholesky CTAs: 16 warps (a warp issues a dependent instruction every ~8 cycles:
+                                          // the tile products need 4 warps per scheduler to keep the FP64 tensor pipe busy)
 constexpr int kBCWarps = kBCThreads / 32;
 constexpr int kSFMaxRows = 200;           // padded columns + right-hand side row (31 clones: 186 -> 192 + 8)
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 16-byte copy of which only the first n_valid (0, 1, 2) doubles are read; the rest is zero filled.  `safe`: any valid
+// 16-byte aligned global address (used when nothing is read).
+__device__ __forceinline__ void cp_async16_zfill(double* dst_smem, const double* src, int n_valid, const double* safe)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const double* sp = n_valid > 0 ? src : safe;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(sp), "r"(8 * n_valid) : "memory");
+}
 
 struct TileTri {
     double* t; int tc, tr;                // tc tile columns (square lower triangle), tr >= tc tile rows
@@ -113,135 +108,272 @@ __device__ __forceinline__ void tile_mma(double2& c, const double2& a, const dou
     dmma884(c.x, c.y, a.y, b.y);
 }
 
-// Blocked Cholesky of the trapezoid T (rows 0 .. nrows-1; columns 0 .. 8 T.tc - 1), in place: L below and on the diagonal.
-//   pivot_ok(j, p)   thread-uniform: false -> column j is skipped (its column of L is zero)
-//   RANK only: nact = number of real columns (the rest is identity padding); is_boundary(j) says where a class test is due,
-//   on_column(j, dep, is_b, tau, colnorm2) is walked over the columns in order after each panel (thread-uniform) and returns
-//   false to stop (nothing after the current panel is touched then).  tau = trace of the Schur complement of the columns
-//   >= j restricted to real rows; colnorm2 = sum_i L(i,j)^2 over real rows.  s_part: 2 x 8 x kBCWarps doubles.
-// Returns the number of panels done.
-template <bool RANK, class OkFn, class BndFn, class ColFn>
-__device__ __forceinline__ int tile_cholesky(const TileTri& T, int nrows, int nact, OkFn pivot_ok, BndFn is_boundary, ColFn on_column,
-                                             double* s_pv, double* s_part)
+// What the factoring warp publishes about the diagonal tile of a panel.
+struct PanelPub {
+    double X[64];             // inv(L_JJ), row-major; rows / columns of skipped pivots are zero
+    double cin[8];            // RANK: the tile's own share of |L(:, c)|^2 (real rows)
+    double pv[8];             // pivots (as found, before the square root)
+    double below[9];          // RANK scratch of the walk
+    unsigned okmask;
+    int next_row;             // work counter of the trailing update (tile rows are handed out from the bottom up)
+    int stop;                 // RANK: the walk ended the factorisation in this panel
+};
+
+// Pivot rules (thread-uniform).  SPD: the matrix is S = W R^T + s^2 I; a non-positive pivot is reported.
+struct SpdPivot {
+    int* bad;
+    __device__ __forceinline__ bool ok(int, double p) const { const bool k = p > 0.0; if (!k) *bad = 1; return k; }
+};
+// Rank rule: a column whose pivot drowned in rounding (relative to its original diagonal) is dependent and skipped;
+// columns >= np are identity padding.
+struct RankPivot {
+    const double* gd; int np;
+    __device__ __forceinline__ bool ok(int j, double p) const { return j >= np || p >= fmax(1e-12, 1e-12 * gd[j]); }
+};
+
+// State of the reference's rule along the columns; lives in warp 0 (every lane holds the same values).
+struct RankWalk {
+    int q, first_dep, mode, kcut, jstop, undecided;
+    int np, world, boundaries;
+    const double* late;       // late[j] = information of the classes starting at column >= j
+    double* nr2;              // out: |row j of R|^2
+    __device__ __forceinline__ bool is_boundary(int j) const { return boundaries && j > 0 && j < np && late[j] > late[j + 1]; }
+};
+
+// One warp factors the diagonal tile (J, J): lane (g, t) owns L[g][2t], L[g][2t+1] (the fragment layout); per column one
+// broadcast of the pivot, one rsqrt, one broadcast of the scaled column, two FMAs -- ~30 instructions per column and lane
+// instead of the ~100 of a redundant per-lane factorisation (a single warp issues one dependent instruction every ~8 cycles,
+// so the instruction count of this chain IS the critical path of a small factorisation).  Then X = inv(L_JJ) (lanes 0..7,
+// one column each), the pivots and the column norms.  Returns the trace of the tile's real rows before the factorisation
+// when want_trace (RANK: only panels with a class boundary need it).
+template <bool RANK, class Pivot>
+__device__ __forceinline__ double factor_diag_tile(const TileTri& T, int J, int nact, const Pivot& piv, double* s_pv, PanelPub* pub,
+                                                   double* Xkeep, bool want_trace, unsigned& okmask_out)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-    int J = 0;
-    for (; J < T.tc; ++J) {
-        __syncthreads();
-        // ---- diagonal tile -> registers, factored redundantly by every thread
-        double D[8][8];
-        {
-            const double* dt = T.tile(J, J);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    double* dt = T.tile(J, J);
+    double2 e = *reinterpret_cast<const double2*>(dt + g * 8 + 2 * t4);
+    double tr0 = 0;
+    if (RANK && want_trace) {
+        double v = (lane < 8 && 8 * J + lane < nact) ? dt[lane * 9] : 0.0;
+        v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 4);
+        tr0 = __shfl_sync(FULL, v, 0);
+    }
+    if (J == 2) PHASE_CLK(RANK ? 56 : 60);
+    unsigned okmask = 0;
+    double pvc[8], rsv[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < 8; ++c) {
+        const double colv = (c & 1) ? e.y : e.x;                    // this lane's element of the column pair c belongs to (meaningful when t4 == c / 2)
+        const double p = __shfl_sync(FULL, colv, 4 * c + (c >> 1));
+        pvc[c] = p;
+        const bool ok = piv.ok(8 * J + c, p);
+        okmask |= (ok ? 1u : 0u) << c;
+        const double r_ = ok ? rsqrt(p) : 0.0;
+        rsv[c] = r_;
+        const double lc = (g >= c) ? colv * r_ : 0.0;               // L[g][c] in the lanes with t4 == c / 2 (rows above the diagonal: 0)
+        if (t4 == (c >> 1)) { if (c & 1) e.y = lc; else e.x = lc; }
+        const double lg = __shfl_sync(FULL, lc, 4 * g + (c >> 1));
+        const double la = __shfl_sync(FULL, lc, 4 * (2 * t4) + (c >> 1));
+        const double lb = __shfl_sync(FULL, lc, 4 * (2 * t4 + 1) + (c >> 1));
+        if (2 * t4 > c) e.x = fma(-lg, la, e.x);
+        if (2 * t4 + 1 > c) e.y = fma(-lg, lb, e.y);
+    }
+    if (J == 2) PHASE_CLK(RANK ? 57 : 61);
+    if (2 * t4 > g) e.x = 0.0;                                      // strictly upper part
+    if (2 * t4 + 1 > g) e.y = 0.0;
+    *reinterpret_cast<double2*>(dt + g * 8 + 2 * t4) = e;
+    if (RANK) {                                                     // column norms over the real rows: reduce over g
+        const bool real = 8 * J + g < nact;
+        double v0 = real ? e.x * e.x : 0.0, v1 = real ? e.y * e.y : 0.0;
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    if (c <= r) { const double2 v = *reinterpret_cast<const double2*>(dt + r * 8 + c); D[r][c] = v.x; D[r][c + 1] = v.y; }
-                    else { D[r][c] = 0.0; D[r][c + 1] = 0.0; }
-                }
-        }
-        double rs[8], ptau[8];
-        unsigned okmask = 0;
+        for (int o = 4; o <= 16; o <<= 1) { v0 += __shfl_xor_sync(FULL, v0, o); v1 += __shfl_xor_sync(FULL, v1, o); }
+        if (lane < 4) { pub->cin[2 * lane] = v0; pub->cin[2 * lane + 1] = v1; }
+    }
+    if (lane == 0) {                                                // (one lane, straight-line stores: a per-lane selection of pvc[lane] compiles to a jump table)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { s_pv[8 * J + c] = ((okmask >> c) & 1u) ? pvc[c] : -1.0; pub->pv[c] = pvc[c]; }
+        pub->okmask = okmask;
+    }
+    okmask_out = okmask;
+    __syncwarp();
+    if (J == 2) PHASE_CLK(RANK ? 58 : 62);
+    // X = inv(L_JJ): lane k < 8 runs the forward substitution on e_k against the rows of L_JJ just written (broadcast reads);
+    // a skipped pivot has a zero diagonal: its row of X is zero
+    {
+        const int k = lane & 7;
+        double x[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int j = 8 * J + c;
-            const double p = D[c][c];
-            if (RANK) {                                             // trace of the Schur complement at column j, rows of this panel
-                double a = 0;
+            double v = (k == c) ? 1.0 : 0.0;
 #pragma unroll
-                for (int r = c; r < 8; ++r) if (8 * J + r < nact) a += D[r][r];
-                ptau[c] = a;
-            }
-            const bool ok = pivot_ok(j, p);
-            okmask |= (ok ? 1u : 0u) << c;
-            const double r_ = ok ? rsqrt(p) : 0.0;
-            rs[c] = r_;
-            D[c][c] = p * r_;
-#pragma unroll
-            for (int r = c + 1; r < 8; ++r) D[r][c] *= r_;
-#pragma unroll
-            for (int r = c + 1; r < 8; ++r)
-#pragma unroll
-                for (int c2 = c + 1; c2 <= r; ++c2) D[r][c2] = fma(-D[r][c], D[c2][c], D[r][c2]);
-            if (tid == 0) s_pv[j] = ok ? p : -1.0;
+            for (int c1 = 0; c1 < c; ++c1) v = fma(-dt[c * 8 + c1], x[c1], v);
+            x[c] = v * rsv[c];                                      // 1 / L[c][c] = rsqrt(p); 0 for a skipped pivot
         }
-        // ---- my row of the panel: rows of the diagonal tile store the factor, rows below solve against it
-        const int i = 8 * J + tid;
-        double l[8];
+        if (lane < 8) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) l[c] = 0.0;
-        if (i < nrows) {
-            double2* rp = reinterpret_cast<double2*>(T.tile(i >> 3, J) + ((i & 7) << 3));
-            if (tid < 8) {
+            for (int c = 0; c < 8; ++c) { pub->X[c * 8 + lane] = x[c]; if (Xkeep) Xkeep[c * 8 + lane] = x[c]; }
+        }
+    }
+    if (J == 2) PHASE_CLK(RANK ? 59 : 63);
+    return tr0;
+}
+
+// The rule's bookkeeping for panel J (warp 0, after the panel's rows have been turned into L): column norms -> nr2, count of
+// independent columns, first dependent column, and the class-boundary tests (see k_rank_rule).  Returns true to stop.
+__device__ __forceinline__ bool rank_walk_panel(RankWalk& rw, int J, unsigned okmask, double tr0, PanelPub* pub, const double* s_part)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int j0 = 8 * J;
+    unsigned colmask = (j0 + 8 <= rw.np) ? 0xffu : ((1u << (rw.np - j0)) - 1u);       // real columns of this panel
+    double below = 0;                                                                  // lane c < 8: |L(rows below the tile, c)|^2 ; lane 8: their trace
+    if (lane < 9) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (tid == r) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) l[c] = (c <= r) ? D[r][c] : 0.0;
+        for (int w = 0; w < kBCWarps; ++w) below += s_part[w * 9 + lane];
+    }
+    if (lane < 8 && ((colmask >> lane) & 1u)) rw.nr2[j0 + lane] = ((okmask >> lane) & 1u) ? pub->cin[lane] + below : 0.0;
+    const unsigned bmask = __ballot_sync(FULL, lane < 8 && rw.is_boundary(j0 + lane)) & colmask;
+    bool stop = false;
+    if (bmask) {                                                                       // rare: a class of features starts inside this panel
+        if (lane < 9) pub->below[lane] = below;
+        __syncwarp();
+        unsigned bm = bmask;
+        while (bm) {
+            const int cb = __ffs(bm) - 1;
+            bm &= bm - 1;
+            // trace of the Schur complement at column j over the real rows: the tile's rows (recursively: every good pivot
+            // takes its column norm, a skipped one its pivot), the rows below (their trace minus what the columns took)
+            double tau = tr0 + pub->below[8];
+            for (int c = 0; c < cb; ++c) tau -= (((okmask >> c) & 1u) ? pub->cin[c] : pub->pv[c]) + pub->below[c];
+            const int j = j0 + cb;
+            const double tt = tau - rw.late[j];
+            const int dd = j - (rw.q + __popc(okmask & colmask & ((1u << cb) - 1u)));
+            if (dd >= 1) {
+                if (tt < 1e-8) { rw.mode = 2; rw.kcut = j; stop = true; }              // exhausted: the reference cuts, later classes are discarded
+                else if (tt < 1e-3 || dd >= 2) {                                       // only the reference's own sweep can tell
+                    if (rw.world == 1) { rw.mode = 3; stop = true; }
+                    else rw.undecided = 1;                                             // feature-sharded: keep everything, say so
+                }
+            }
+            if (stop) { rw.jstop = j; colmask &= (1u << cb) - 1u; break; }
+        }
+    }
+    rw.q += __popc(okmask & colmask);
+    const unsigned deps = ~okmask & colmask;
+    if (deps && rw.first_dep == rw.np) rw.first_dep = j0 + __ffs(deps) - 1;
+    return stop;
+}
+
+// Blocked Cholesky of the trapezoid T (T.tr tile rows, T.tc tile columns), in place: L below and on the diagonal.
+//   per panel J:  (A) every warp turns its tile rows of the panel into L(I,J) = A(I,J) inv(L_JJ)^T (two DMMAs per tile)
+//                 (B) trailing update C(I,K) -= L(I,J) L(K,J)^T on the tensor pipe, tile rows handed out dynamically;
+//                     warp 0 takes tile (J+1, J+1) first and factors it while the others are still updating (look-ahead:
+//                     the dependent chain of the 8 x 8 factorisation is off the critical path when there is enough
+//                     trailing work)
+//   RANK: rw carries the reference's rule (walked by warp 0 only, which publishes the verdict; the other warps never wait
+//   for it -- a trailing update past the cut is harmless, nothing behind the cut is read afterwards); nact = real columns.
+//   s_part: kBCWarps x 9 doubles.  Xall (optional): tc tiles, receives inv(L_JJ) of every panel.
+template <bool RANK, class Pivot>
+__device__ __forceinline__ void tile_cholesky(const TileTri& T, int nact, const Pivot& piv, RankWalk* rw, double* s_pv, PanelPub* pub,
+                                              double* s_part, double* Xall)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int fo = g * 8 + 2 * t4;                                  // this lane's pair inside a tile
+    double tr0 = 0;
+    unsigned okmask = 0;
+    if (tid == 0) pub->stop = 0;
+    __syncthreads();
+    if (warp == 0) {
+        bool wt = false;
+        if (RANK) { for (int c = 0; c < 8; ++c) wt = wt || rw->is_boundary(c); }
+        tr0 = factor_diag_tile<RANK>(T, 0, nact, piv, s_pv, pub, Xall, wt, okmask);
+    }
+    __syncthreads();
+    for (int J = 0; J < T.tc; ++J) {
+        if (J == 1) PHASE_CLK(RANK ? 48 : 40);
+        // ---- (A) the panel below the diagonal tile
+        double cn0 = 0, cn1 = 0, trp = 0;
+        {
+            const double2 xf = *reinterpret_cast<const double2*>(pub->X + fo);
+            for (int I = J + 1 + warp; I < T.tr; I += 2 * kBCWarps) {
+                const int I2 = I + kBCWarps;
+                const bool two = I2 < T.tr;
+                double* p0 = T.tile(I, J) + fo;
+                double* p1 = two ? T.tile(I2, J) + fo : p0;
+                const double2 a0 = *reinterpret_cast<const double2*>(p0), a1 = *reinterpret_cast<const double2*>(p1);
+                double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+                dmma884(c0.x, c0.y, a0.x, xf.x);
+                dmma884(c1.x, c1.y, a1.x, xf.x);
+                dmma884(c0.x, c0.y, a0.y, xf.y);
+                dmma884(c1.x, c1.y, a1.y, xf.y);
+                *reinterpret_cast<double2*>(p0) = c0;
+                if (two) *reinterpret_cast<double2*>(p1) = c1;
+                if (RANK) {
+                    if (8 * I + g < nact) { cn0 = fma(c0.x, c0.x, cn0); cn1 = fma(c0.y, c0.y, cn1); }
+                    if (two && 8 * I2 + g < nact) { cn0 = fma(c1.x, c1.x, cn0); cn1 = fma(c1.y, c1.y, cn1); }
+                    if (lane < 8) {
+                        if (I < T.tc && 8 * I + lane < nact) trp += T.tile(I, I)[lane * 9];
+                        if (two && I2 < T.tc && 8 * I2 + lane < nact) trp += T.tile(I2, I2)[lane * 9];
                     }
-            } else {
-                double a[8];
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) { const double2 v = rp[c >> 1]; a[c] = v.x; a[c + 1] = v.y; }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double v = a[c];
-#pragma unroll
-                    for (int c1 = 0; c1 < c; ++c1) v = fma(-l[c1], D[c][c1], v);
-                    l[c] = v * rs[c];
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) rp[c >> 1] = make_double2(l[c], l[c + 1]);
         }
-        unsigned bmask = 0;
         if (RANK) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) if (is_boundary(8 * J + c)) bmask |= 1u << c;
-            const bool real = i < nact;                             // a row of G (not padding, not the right-hand side)
-            double v8[8];
+            for (int o = 4; o <= 16; o <<= 1) { cn0 += __shfl_xor_sync(0xffffffffu, cn0, o); cn1 += __shfl_xor_sync(0xffffffffu, cn1, o); }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v8[c] = real ? l[c] * l[c] : 0.0;
-            double tot = warp_sum8(v8, lane);                       // lane 4 c holds the warp's share of |L(:, c)|^2
-            if ((lane & 3) == 0) s_part[(8 + (lane >> 2)) * kBCWarps + warp] = tot;
-            if (bmask) {                                            // rows below the panel: diagonal minus what the columns before c took
-                const bool below = real && tid >= 8;
-                const double dg = below ? *T.at(i, i) : 0.0;
-                double run = 0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    v8[c] = (below && ((bmask >> c) & 1u)) ? dg - run : 0.0;
-                    run = fma(l[c], l[c], run);
-                }
-                tot = warp_sum8(v8, lane);
-                if ((lane & 3) == 0) s_part[(lane >> 2) * kBCWarps + warp] = tot;
-            }
+            for (int o = 1; o <= 4; o <<= 1) trp += __shfl_xor_sync(0xffffffffu, trp, o);
+            if (lane < 4) { s_part[warp * 9 + 2 * lane] = cn0; s_part[warp * 9 + 2 * lane + 1] = cn1; }
+            if (lane == 0) s_part[warp * 9 + 8] = trp;
         }
+        if (J == 1) PHASE_CLK(RANK ? 49 : 41);
+        if (tid == 0) pub->next_row = T.tr - 1;
         __syncthreads();
-        if (RANK) {
+        if (J == 1) PHASE_CLK(RANK ? 50 : 42);
+        const bool last = J + 1 >= T.tc;                            // the last panel has nothing behind it
+        if (warp == 0) {
             bool stop = false;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int j = 8 * J + c;
-                if (j >= nact || stop) continue;
-                const bool isb = (bmask >> c) & 1u;
-                double tau = 0, cn = 0;
-                if (isb) { tau = ptau[c]; for (int w = 0; w < kBCWarps; ++w) tau += s_part[c * kBCWarps + w]; }
-                for (int w = 0; w < kBCWarps; ++w) cn += s_part[(8 + c) * kBCWarps + w];
-                if (!on_column(j, !((okmask >> c) & 1u), isb, tau, cn)) stop = true;
+            if (RANK) {
+                stop = rank_walk_panel(*rw, J, okmask, tr0, pub, s_part);
+                if (stop && lane == 0) pub->stop = 1;
             }
-            if (stop) break;
+            if (J == 1) PHASE_CLK(RANK ? 51 : 43);
+            if (!stop && !last) {                                   // look-ahead: the next diagonal tile first, then its factorisation
+                double2 a = *reinterpret_cast<const double2*>(T.tile(J + 1, J) + fo);
+                const double2 b = a;
+                a.x = -a.x; a.y = -a.y;
+                double* cp = T.tile(J + 1, J + 1) + fo;
+                double2 c = *reinterpret_cast<double2*>(cp);
+                tile_mma(c, a, b);
+                *reinterpret_cast<double2*>(cp) = c;
+                __syncwarp();
+                if (J == 1) PHASE_CLK(RANK ? 52 : 44);
+                bool wt = false;
+                if (RANK) { for (int c = 0; c < 8; ++c) wt = wt || rw->is_boundary(8 * (J + 1) + c); }
+                tr0 = factor_diag_tile<RANK>(T, J + 1, nact, piv, s_pv, pub, Xall ? Xall + (size_t)(J + 1) * 64 : nullptr, wt, okmask);
+            }
         }
-        // ---- trailing update on the tensor pipe: tile row I to warp (I - J - 1) mod 8, two tiles in flight
-        for (int I = J + 1 + warp; I < T.tr; I += kBCWarps) {
-            double2 a = *reinterpret_cast<const double2*>(T.tile(I, J) + g * 8 + 2 * t4);
+        if (last) break;
+        // ---- (B) trailing update
+        if (J == 1) PHASE_CLK(RANK ? 53 : 45);
+        while (true) {
+            int I = 0;
+            if (lane == 0) I = atomicSub(&pub->next_row, 1);
+            I = __shfl_sync(0xffffffffu, I, 0);
+            if (I < J + 2) break;
+            double2 a = *reinterpret_cast<const double2*>(T.tile(I, J) + fo);
             a.x = -a.x; a.y = -a.y;
             const int Kmax = min(I, T.tc - 1);
-            double* crow = T.tile(I, J + 1) + g * 8 + 2 * t4;       // tiles (I, J+1), (I, J+2), ... are consecutive
+            const double* brow = T.tile(J + 1, J) + fo;             // tiles (K, J): K (K + 1) / 2 + J -> stride grows by K + 1 tiles
+            double* crow = T.tile(I, J + 1) + fo;                   // tiles (I, J+1), (I, J+2), ... are consecutive
             int K = J + 1;
             for (; K + 1 <= Kmax; K += 2, crow += 128) {
-                const double2 b0 = *reinterpret_cast<const double2*>(T.tile(K, J) + g * 8 + 2 * t4);
-                const double2 b1 = *reinterpret_cast<const double2*>(T.tile(K + 1, J) + g * 8 + 2 * t4);
+                const double2 b0 = *reinterpret_cast<const double2*>(brow);
+                brow += (size_t)(K + 1) << 6;
+                const double2 b1 = *reinterpret_cast<const double2*>(brow);
+                brow += (size_t)(K + 2) << 6;
                 double2 c0 = *reinterpret_cast<double2*>(crow), c1 = *reinterpret_cast<double2*>(crow + 64);
                 dmma884(c0.x, c0.y, a.x, b0.x);
                 dmma884(c1.x, c1.y, a.x, b1.x);
@@ -251,17 +383,19 @@ __device__ __forceinline__ int tile_cholesky(const TileTri& T, int nrows, int na
                 *reinterpret_cast<double2*>(crow + 64) = c1;
             }
             if (K <= Kmax) {
-                const double2 b0 = *reinterpret_cast<const double2*>(T.tile(K, J) + g * 8 + 2 * t4);
+                const double2 b0 = *reinterpret_cast<const double2*>(brow);
                 double2 c0 = *reinterpret_cast<double2*>(crow);
                 tile_mma(c0, a, b0);
                 *reinterpret_cast<double2*>(crow) = c0;
             }
         }
+        if (J == 1) PHASE_CLK(RANK ? 54 : 46);
+        __syncthreads();
+        if (J == 1) PHASE_CLK(RANK ? 55 : 47);
+        if (RANK && pub->stop) break;
     }
     __syncthreads();
-    return J;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // k_rank_rule
@@ -290,8 +424,9 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
 {
     extern __shared__ __align__(16) double rsm[];            // the tile-packed factor (lower: column j of L = row j of R), y in the extra row
     __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows];
-    __shared__ double s_part[16 * kBCWarps];
-    __shared__ int s_np, s_k, s_smin, s_ncls;
+    __shared__ double s_part[9 * kBCWarps];
+    __shared__ PanelPub s_pub;
+    __shared__ int s_np, s_k, s_smin, s_ncls, s_verdict[6];
     __shared__ double s_tau;
     const int n = Q.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* cnt = Q.red + (size_t)n * n + n;
@@ -340,39 +475,37 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
     bool undecided = false;
     int jstop = Np;
     {
-        const int ntile = tile_tri_count(T.tc, T.tr) * 64;
-        for (int o = tid; o < ntile; o += kBCThreads) rsm[o] = 0.0;
+        // [G | z] -> tiles, asynchronously (every 16-byte piece of every tile is written: zero where there is no data)
+        const int nsq = T.tc * (T.tc + 1) / 2;
+        for (int o = tid; o < (nsq + T.tc) * 32; o += kBCThreads) {
+            const int tl = o >> 5, r = (o >> 2) & 7, q2 = 2 * (o & 3);
+            int I, J;
+            if (tl < nsq) {
+                I = (int)((sqrtf(8.f * (float)tl + 1.f) - 1.f) * .5f);
+                while (I * (I + 1) / 2 > tl) --I;
+                while ((I + 1) * (I + 2) / 2 <= tl) ++I;
+                J = tl - I * (I + 1) / 2;
+            } else { I = T.tc; J = tl - nsq; }
+            const int i = 8 * I + r, j = 8 * J + q2;
+            const double* src; int nv = 0;
+            if (I < T.tc) { src = G + (size_t)i * n + j; if (i < Np) nv = max(0, min(2, Np - j)); }
+            else { src = Q.red + (size_t)n * n + j; if (r == 0) nv = max(0, min(2, Np - j)); }
+            cp_async16_zfill(rsm + ((size_t)tl << 6) + r * 8 + q2, src, nv, G);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
-        for (int o = tid; o < Np * Np; o += kBCThreads) {
-            const int i = o / Np, j = o - i * Np;
-            if (j <= i) *T.at(i, j) = G[(size_t)i * n + j];
-        }
-        for (int j = tid; j < ncp; j += kBCThreads) {
-            if (j < Np) *T.at(ncp, j) = Q.red[(size_t)n * n + j];
-            else *T.at(j, j) = 1.0;                               // identity padding up to a multiple of 8 columns
-        }
+        for (int j = Np + tid; j < ncp; j += kBCThreads) *T.at(j, j) = 1.0;      // identity padding up to a multiple of 8 columns
         PHASE_CLK(17);
-        // class-boundary test (see above); tau = trace of the current Schur complement - information that has not started yet
-        auto pivot_ok = [&](int j, double p) -> bool { return j >= Np || p >= fmax(1e-12, 1e-12 * s_gd[j]); };
-        auto is_boundary = [&](int j) -> bool { return boundaries && j > 0 && j < Np && s_late[j] > s_late[j + 1]; };
-        auto on_column = [&](int j, bool dep, bool isb, double tau, double cn) -> bool {
-            if (isb) {
-                const double tt = tau - s_late[j];
-                const int dd = j - q;
-                if (dd >= 1) {
-                    if (tt < 1e-8) { mode = 2; kcut = j; jstop = j; return false; }      // exhausted: the reference cuts, later classes are discarded
-                    if (tt < 1e-3 || dd >= 2) {                                          // only the reference's own sweep can tell
-                        if (Q.world == 1) { mode = 3; jstop = j; return false; }
-                        undecided = true;                                                // feature-sharded: keep everything, say so
-                    }
-                }
-            }
-            if (!dep) q++; else if (first_dep == Np) first_dep = j;
-            if (tid == 0) s_nr2[j] = dep ? 0.0 : cn;
-            return true;
-        };
-        if (Np > 0) tile_cholesky<true>(T, ncp + 1, Np, pivot_ok, is_boundary, on_column, s_pv, s_part);
-        else __syncthreads();
+        // class-boundary test (see above), walked by warp 0 along the panels; the verdict comes back through shared memory
+        RankPivot piv; piv.gd = s_gd; piv.np = Np;
+        RankWalk rw;
+        rw.q = 0; rw.first_dep = Np; rw.mode = 1; rw.kcut = 0; rw.jstop = Np; rw.undecided = 0;
+        rw.np = Np; rw.world = Q.world; rw.boundaries = boundaries ? 1 : 0; rw.late = s_late; rw.nr2 = s_nr2;
+        if (Np > 0) tile_cholesky<true>(T, Np, piv, &rw, s_pv, &s_pub, s_part, nullptr);
+        if (tid == 0) { s_verdict[0] = rw.q; s_verdict[1] = rw.first_dep; s_verdict[2] = rw.mode; s_verdict[3] = rw.kcut; s_verdict[4] = rw.jstop; s_verdict[5] = rw.undecided; }
+        __syncthreads();
+        q = s_verdict[0]; first_dep = s_verdict[1]; mode = s_verdict[2]; kcut = s_verdict[3]; jstop = s_verdict[4]; undecided = s_verdict[5] != 0;
     }
     PHASE_CLK(18);
     __syncthreads();
@@ -457,42 +590,30 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_chol_S(const double* S, int m
 {
     extern __shared__ __align__(16) double csm[];                // tile-packed lower triangle, then tc tiles for the inverses
     __shared__ double s_pv[kSFMaxRows];
+    __shared__ PanelPub s_pub;
     if (gate && !(gate[0] > 2.0)) return;
     const int tid = threadIdx.x;
     TileTri T;
     T.t = csm; T.tc = (m + 7) >> 3; T.tr = T.tc;
     const int ntile = tile_tri_count(T.tc, T.tc);
     double* X = csm + (size_t)ntile * 64;
-    for (int o = tid; o < (ntile + T.tc) * 64; o += kBCThreads) csm[o] = 0.0;
-    __syncthreads();
-    for (int o = tid; o < m * m; o += kBCThreads) {
-        const int r = o / m, c = o - r * m;
-        if (c <= r) *T.at(r, c) = S[(size_t)r * m + c];
+    for (int o = tid; o < ntile * 32; o += kBCThreads) {           // S -> tiles, asynchronously, zero where there is no data
+        const int tl = o >> 5, r = (o >> 2) & 7, q2 = 2 * (o & 3);
+        int I = (int)((sqrtf(8.f * (float)tl + 1.f) - 1.f) * .5f);
+        while (I * (I + 1) / 2 > tl) --I;
+        while ((I + 1) * (I + 2) / 2 <= tl) ++I;
+        const int J = tl - I * (I + 1) / 2;
+        const int i = 8 * I + r, j = 8 * J + q2;
+        cp_async16_zfill(csm + ((size_t)tl << 6) + r * 8 + q2, S + (size_t)i * m + j, (i < m) ? max(0, min(2, m - j)) : 0, S);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     for (int j = m + tid; j < 8 * T.tc; j += kBCThreads) *T.at(j, j) = 1.0;
     PHASE_CLK(32);
-    auto pivot_ok = [&](int j, double p) -> bool { const bool ok = p > 0.0; if (!ok && tid == 0) *bad = 1; return ok; };
-    auto no_boundary = [](int) -> bool { return false; };
-    auto no_column = [](int, bool, bool, double, double) -> bool { return true; };
-    tile_cholesky<false>(T, 8 * T.tc, 0, pivot_ok, no_boundary, no_column, s_pv, nullptr);
+    SpdPivot piv; piv.bad = bad;
+    tile_cholesky<false>(T, 0, piv, nullptr, s_pv, &s_pub, nullptr, X);      // X: inv(L_JJ) of every panel
     PHASE_CLK(33);
-    // inverses of the diagonal tiles: thread (J, c) solves L_JJ x = e_c
-    for (int w = tid; w < T.tc * 8; w += kBCThreads) {
-        const int J = w >> 3, c = w & 7;
-        const double* Lj = T.tile(J, J);
-        double x[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double acc = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < r; ++k) acc = fma(-Lj[r * 8 + k], (k >= c) ? x[k] : 0.0, acc);
-            const double dg = Lj[r * 8 + r];
-            x[r] = (r >= c && dg > 0.0) ? acc / dg : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) X[J * 64 + r * 8 + c] = x[r];
-    }
-    __syncthreads();
     for (int o = tid; o < ntile * 64; o += kBCThreads) Lt[o] = csm[o];
     __syncthreads();
     for (int o = tid; o < T.tc * 64; o += kBCThreads) { const int J = o >> 6; Lt[((size_t)(J * (J + 1) / 2 + J) << 6) + (o & 63)] = X[o]; }
@@ -601,16 +722,24 @@ __device__ __forceinline__ void sr_apply_dq(const double* dth, const double* q, 
 
 constexpr int kSRThreads = kBCThreads;
 // shared-memory tiles of k_solve_small_R: T (S + extra rows), R (upper triangle by tile), Pc (extra tile rows x tile columns)
-__host__ __device__ inline int solve_small_tiles(int n, int d)
+// (the R / Pc region is reused for a copy of P during the factorisation: it is at least d x d doubles)
+__host__ __device__ inline int solve_small_stage_doubles(int n, int d)
 {
     const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
-    return tile_tri_count(tc, tc + tre) + tc * (tc + 1) / 2 + tre * tc;
+    const int a = (tc * (tc + 1) / 2 + tre * tc) * 64, b = d * d;
+    return a > b ? a : b;
+}
+__host__ __device__ inline size_t solve_small_doubles(int n, int d)
+{
+    const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
+    return (size_t)tile_tri_count(tc, tc + tre) * 64 + solve_small_stage_doubles(n, d);
 }
 __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRParams Q)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ double s_pv[kSFMaxRows];
     __shared__ double s_dx[kSFMaxRows];
+    __shared__ PanelPub s_pub;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int N = Q.N, n = 6 * N, d = Q.d;
     if (!(Q.gate[0] > 2.0)) {                                      // Updater.cc:621-627: too few features, posterior = prior
@@ -622,46 +751,47 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
     // 8 tc + c: column c of [W | y], after the factorisation column c of Y = L^-1 [W | y] (the right-hand sides ride along).
     TileTri T;
     T.t = sm; T.tc = (n + 7) >> 3;
-    const int tc = T.tc, tre = (d + 1 + 7) >> 3, ncp = 8 * tc;
+    const int tc = T.tc, tre = (d + 1 + 7) >> 3;
     T.tr = tc + tre;
     double* Rt = sm + (size_t)tile_tri_count(tc, T.tr) * 64;       // tile (Rj, Kb), Kb >= Rj, at (Rj tc - Rj (Rj - 1) / 2 + Kb - Rj) * 64: R(8 Rj + r, 8 Kb + k) at [r][k]
     double* Pt = Rt + (size_t)(tc * (tc + 1) / 2) * 64;             // tile (Ci, Kb) at (Ci tc + Kb) * 64: Pc(8 Kb + k, 8 Ci + c) at [c][k]
     auto rtile = [&](int Rj, int Kb) -> double* { return Rt + ((size_t)(Rj * tc - (Rj * (Rj - 1)) / 2 + Kb - Rj) << 6); };
     PHASE_CLK(0);
-    for (int o = tid; o < (tc * (tc + 1) / 2) * 64; o += kSRThreads) {
-        // decode (tile, r, k): tiles of row Rj are consecutive
-        const int tl = o >> 6, e = o & 63;
+    for (int o = tid; o < (tc * (tc + 1) / 2) * 32; o += kSRThreads) {          // R -> tiles (tiles of row Rj are consecutive)
+        const int tl = o >> 5, rr = (o >> 2) & 7, q2 = 2 * (o & 3);
         int Rj = 0, rem = tl;
         while (rem >= tc - Rj) { rem -= tc - Rj; ++Rj; }
-        const int r = 8 * Rj + (e >> 3), k = 8 * (Rj + rem) + (e & 7);
-        Rt[o] = (r < n && k < n) ? Q.Rc[(size_t)r * n + k] : 0.0;
+        const int r = 8 * Rj + rr, k = 8 * (Rj + rem) + q2;
+        cp_async16_zfill(Rt + ((size_t)tl << 6) + rr * 8 + q2, Q.Rc + (size_t)r * n + k, (r < n) ? max(0, min(2, n - k)) : 0, Q.Rc);
     }
-    for (int o = tid; o < tre * tc * 64; o += kSRThreads) {
-        const int tl = o >> 6, e = o & 63;
+    for (int o = tid; o < tre * tc * 32; o += kSRThreads) {                       // P(c, 24 + k) = Pc(k, c) -> tiles
+        const int tl = o >> 5, cc = (o >> 2) & 7, q2 = 2 * (o & 3);
         const int Ci = tl / tc, Kb = tl - Ci * tc;
-        const int c = 8 * Ci + (e >> 3), k = 8 * Kb + (e & 7);
-        Pt[o] = (c < d && k < n) ? Q.P[(size_t)c * d + 24 + k] : 0.0;          // P(c, 24 + k) = Pc(k, c)
+        const int c = 8 * Ci + cc, k = 8 * Kb + q2;
+        cp_async16_zfill(Pt + ((size_t)tl << 6) + cc * 8 + q2, Q.P + (size_t)c * d + 24 + k, (c < d) ? max(0, min(2, n - k)) : 0, Q.P);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     PHASE_CLK(1);
     // ---- W^T tiles: Wt(Ci, Rj) = sum_{Kb >= Rj} Pt(Ci, Kb) Rt(Rj, Kb)^T   (R upper triangular)
     for (int w = warp; w < tre * tc; w += kBCWarps) {
         const int Ci = w / tc, Rj = w - Ci * tc;
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
-        int Kb = Rj;
-        for (; Kb + 1 < tc; Kb += 2) {
-            const double2 a0 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb) << 6) + g * 8 + 2 * t4);
-            const double2 a1 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb + 1) << 6) + g * 8 + 2 * t4);
-            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Rj, Kb) + g * 8 + 2 * t4);
-            const double2 b1 = *reinterpret_cast<const double2*>(rtile(Rj, Kb + 1) + g * 8 + 2 * t4);
+        const double* ap = Pt + ((size_t)(Ci * tc + Rj) << 6) + g * 8 + 2 * t4;     // tiles (Ci, Kb), Kb = Rj .. : consecutive
+        const double* bp = rtile(Rj, Rj) + g * 8 + 2 * t4;                           // tiles (Rj, Kb), Kb = Rj .. : consecutive
+        int nk = tc - Rj;
+        for (; nk >= 2; nk -= 2, ap += 128, bp += 128) {
+            const double2 a0 = *reinterpret_cast<const double2*>(ap), a1 = *reinterpret_cast<const double2*>(ap + 64);
+            const double2 b0 = *reinterpret_cast<const double2*>(bp), b1 = *reinterpret_cast<const double2*>(bp + 64);
             dmma884(c0.x, c0.y, a0.x, b0.x);
             dmma884(c1.x, c1.y, a1.x, b1.x);
             dmma884(c0.x, c0.y, a0.y, b0.y);
             dmma884(c1.x, c1.y, a1.y, b1.y);
         }
-        if (Kb < tc) {
-            const double2 a0 = *reinterpret_cast<const double2*>(Pt + ((size_t)(Ci * tc + Kb) << 6) + g * 8 + 2 * t4);
-            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Rj, Kb) + g * 8 + 2 * t4);
+        if (nk) {
+            const double2 a0 = *reinterpret_cast<const double2*>(ap);
+            const double2 b0 = *reinterpret_cast<const double2*>(bp);
             tile_mma(c0, a0, b0);
         }
         c0.x += c1.x; c0.y += c1.y;
@@ -678,25 +808,32 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         while (rem > Ri) { rem -= Ri + 1; ++Ri; }
         const int Cj = rem;
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
-        for (int Kb = Cj; Kb < tc; ++Kb) {
-            const double* wt = T.tile(tc + 3 + Kb, Ri);                                  // [k][r]
-            const double a0 = wt[(2 * t4) * 8 + g], a1 = wt[(2 * t4 + 1) * 8 + g];
-            const double2 b0 = *reinterpret_cast<const double2*>(rtile(Cj, Kb) + g * 8 + 2 * t4);
-            if ((Kb - Cj) & 1) { dmma884(c1.x, c1.y, a0, b0.x); dmma884(c1.x, c1.y, a1, b0.y); }
+        const double* wt = T.tile(tc + 3 + Cj, Ri) + (2 * t4) * 8 + g;                  // extra tile rows: tc tiles each -> stride tc * 64
+        const double* bp = rtile(Cj, Cj) + g * 8 + 2 * t4;
+        for (int nk = tc - Cj, par = 0; nk > 0; --nk, par ^= 1, wt += (size_t)tc << 6, bp += 64) {
+            const double a0 = wt[0], a1 = wt[8];                                         // W(r, 24 + k) at [k][r]
+            const double2 b0 = *reinterpret_cast<const double2*>(bp);
+            if (par) { dmma884(c1.x, c1.y, a0, b0.x); dmma884(c1.x, c1.y, a1, b0.y); }
             else { dmma884(c0.x, c0.y, a0, b0.x); dmma884(c0.x, c0.y, a1, b0.y); }
         }
         c0.x += c1.x; c0.y += c1.y;
         if (Ri == Cj) { if (g == 2 * t4) c0.x += Q.sig2; if (g == 2 * t4 + 1) c0.y += Q.sig2; }
         *reinterpret_cast<double2*>(T.tile(Ri, Cj) + g * 8 + 2 * t4) = c0;
     }
+    __syncthreads();
     PHASE_CLK(3);
+    // R and Pc are dead: the region takes a copy of P (the epilogue of P+ reads P(i,j) and P(j,i)); the copy runs behind the
+    // factorisation
+    double* sPm = Rt;
+    for (int o = tid; o < (d * d) / 2; o += kSRThreads) cp_async16_zfill(sPm + 2 * o, Q.P + 2 * o, 2, Q.P);
+    cp_async_commit();
     // ---- blocked Cholesky; the extra rows become Y^T
     {
-        auto pivot_ok = [&](int j, double p) -> bool { const bool ok = p > 0.0; if (!ok && tid == 0) *Q.bad = 1; return ok; };
-        auto no_boundary = [](int) -> bool { return false; };
-        auto no_column = [](int, bool, bool, double, double) -> bool { return true; };
-        tile_cholesky<false>(T, ncp + d + 1, 0, pivot_ok, no_boundary, no_column, s_pv, nullptr);
+        SpdPivot piv; piv.bad = Q.bad;
+        tile_cholesky<false>(T, 0, piv, nullptr, s_pv, &s_pub, nullptr, nullptr);
     }
+    cp_async_wait<0>();
+    __syncthreads();
     PHASE_CLK(4);
     // ---- P+ = sym(P) - Y^T Y on the upper tile triangle (mirrored); the column j = d of Y^T Y is dx = Y^T y~
     for (int w = warp; w < tre * (tre + 1) / 2; w += kBCWarps) {
@@ -704,9 +841,9 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         while (rem > Jj) { rem -= Jj + 1; ++Jj; }
         const int Ii = rem;                                                              // Ii <= Jj
         const int i = 8 * Ii + g, j = 8 * Jj + 2 * t4;
-        double p00 = 0, p01 = 0, q0 = 0, q1 = 0;                                         // P(i, j), P(i, j+1), P(j, i), P(j+1, i): issued before the products
-        if (i < d && j < d) { p00 = Q.P[(size_t)i * d + j]; q0 = Q.P[(size_t)j * d + i]; }
-        if (i < d && j + 1 < d) { p01 = Q.P[(size_t)i * d + j + 1]; q1 = Q.P[(size_t)(j + 1) * d + i]; }
+        double p00 = 0, p01 = 0, q0 = 0, q1 = 0;                                         // P(i, j), P(i, j+1), P(j, i), P(j+1, i) from the shared copy
+        if (i < d && j < d) { p00 = sPm[i * d + j]; q0 = sPm[j * d + i]; }
+        if (i < d && j + 1 < d) { p01 = sPm[i * d + j + 1]; q1 = sPm[(j + 1) * d + i]; }
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
         const double* ai = T.tile(tc + Ii, 0) + g * 8 + 2 * t4;
         const double* bj = T.tile(tc + Jj, 0) + g * 8 + 2 * t4;
@@ -765,14 +902,6 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
 // ------------------------------------------------------------------------------------------------
 // k_givens_ref
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool SMEM>
 __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
@@ -945,7 +1074,7 @@ size_t givens_smem_bytes(int n, bool* smem_window)
     return sizeof(double) * ((size_t)n + 8);
 }
 
-size_t solve_small_smem_bytes(int n, int d) { return sizeof(double) * 64 * (size_t)solve_small_tiles(n, d) + 64; }
+size_t solve_small_smem_bytes(int n, int d) { return sizeof(double) * solve_small_doubles(n, d) + 64; }
 static size_t rank_rule_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)tile_tri_count(tc, tc + 1) + 64; }
 static size_t chol_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + tc) + 64; }
 static size_t trsm_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + kTrsmWarps * (tc + 1)) + 64; }
@@ -992,7 +1121,7 @@ int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefP
 int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
 {
     const int n = 6 * q.N;
-    if (n > kSolveSmallRMaxN || 8 * ((n + 7) / 8) + q.d + 1 > kBCThreads) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
+    if (n > kSolveSmallRMaxN) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
     RVIO_LAUNCH(k_solve_small_R, 1, kSRThreads, solve_small_smem_bytes(n, q.d), s, q);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
@@ -1002,7 +1131,7 @@ int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
 // B (n x nb, leading dimension ldb) <- L^-1 B.
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate)
 {
-    if (n + 8 > kBCThreads || n + 8 > kSFMaxRows) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
+    if (n + 8 > kSFMaxRows) { set_error("enqueue_chol_trsm", "window too large"); return RVIO_ERR_CAPACITY; }
     RVIO_LAUNCH(k_chol_S, 1, kBCThreads, chol_smem_bytes(n), s, S, n, L, bad, gate);
     RVIO_LAUNCH(k_trsm, div_up(div_up(nb, 8), kTrsmWarps), kTrsmWarps * 32, trsm_smem_bytes(n), s, L, n, B, ldb, nb, gate);
     RVIO_ENQ(cudaGetLastError());

@@ -250,10 +250,12 @@ __global__ void __launch_bounds__(576) k_propagate(PropagateParams Q)
 // k_augment_compose: P_in (d x d) -> P_out (d' x d'), x in place.  do_augment / slide decided on the host
 // (deterministic counters, System.cc:280-323), composition System.cc:326-365.
 // ------------------------------------------------------------------------------------------------
+constexpr int kCrossCols = 96, kCrossLd = kCrossCols + 1;          // clone columns staged per pass (+1: conflict-free column walks)
 __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
 {
     __shared__ double V[24][24], T1[24][24], P00[24][24];
     __shared__ double s_q[16];
+    __shared__ double s_cross[24 * kCrossLd];
     const int tid = threadIdx.x, i = tid / 24, j = tid % 24;
     const int d = Q.d, N = Q.N, W = Q.window;
     double* x = Q.x;
@@ -292,6 +294,8 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     double* P = Q.P_out;
     const int n = 6 * Nn;
     // ---- composition
+    V[i][j] = 0.0;
+    __syncthreads();
     if (tid == 0) {
         double qG[4], pG[3], gk[3], qk[4], pk[3], RG[9], Rk[9], t[3];
         for (int k = 0; k < 4; ++k) { qG[k] = x[k]; qk[k] = x[10 + k]; }
@@ -307,8 +311,6 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
         f_m3v(Rk, dv, pkG);
         for (int k = 0; k < 3; ++k) dv[k] = pk[k] - pG[k];
         for (int k = 0; k < 3; ++k) pGk[k] = RG[k] * dv[0] + RG[3 + k] * dv[1] + RG[6 + k] * dv[2];   // RG^T dv
-        for (int a = 0; a < 24; ++a)
-            for (int b = 0; b < 24; ++b) V[a][b] = 0;
         double S1[9], S2[9];
         f_skew(pkG, S1); f_skew(gk, S2);
         for (int a = 0; a < 3; ++a)
@@ -336,16 +338,21 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     }
     __syncthreads();
     PP(P, dn, i, j) = .5 * (P00[i][j] + P00[j][i]);
-    // cross terms: each thread owns whole columns of P0c (read 24 values, then write) -> no hazard
-    for (int c = tid; c < n; c += 576) {
-        double col[24];
-        for (int k = 0; k < 24; ++k) col[k] = PP(P, dn, k, 24 + c);
-        for (int r = 0; r < 24; ++r) {
+    // cross terms V P0c, kCrossCols columns per pass: the block P(0:24, 24 + c0 ..) is staged in shared memory (rows are
+    // contiguous in memory: coalesced), then one output element per thread (same summation order as before: k ascending)
+    for (int c0 = 0; c0 < n; c0 += kCrossCols) {
+        const int nc = min(kCrossCols, n - c0);
+        for (int o = tid; o < 24 * nc; o += 576) { const int k = o / nc, c = o - k * nc; s_cross[k * kCrossLd + c] = PP(P, dn, k, 24 + c0 + c); }
+        __syncthreads();
+        for (int o = tid; o < 24 * nc; o += 576) {
+            const int r = o / nc, c = o - r * nc;
             double acc = 0;
-            for (int k = 0; k < 24; ++k) acc += V[r][k] * col[k];
-            PP(P, dn, r, 24 + c) = acc;
-            PP(P, dn, 24 + c, r) = acc;
+#pragma unroll
+            for (int k = 0; k < 24; ++k) acc += V[r][k] * s_cross[k * kCrossLd + c];
+            PP(P, dn, r, 24 + c0 + c) = acc;
+            PP(P, dn, 24 + c0 + c, r) = acc;
         }
+        __syncthreads();
     }
     // clone-clone block is already symmetric (augmentation symmetrised it; propagate/update symmetrise their outputs)
     __syncthreads();

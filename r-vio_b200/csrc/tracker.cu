@@ -150,6 +150,55 @@ __global__ void __launch_bounds__(256) k_pyr_down(PyrLevel src, PyrLevel dst)
     store_with_border(dst, x, y, (uint8_t)((acc + 128) >> 8));
 }
 
+
+// Three pyrDown steps in ONE launch (levels 1, 2, 3 from level 0): each CTA owns an 8 x 8 tile of level 3 and everything
+// above it (16 x 16 of level 2, 32 x 32 of level 1), and recomputes the halo it needs (19 x 19 of level 2, 41 x 41 of level
+// 1, from 85 x 85 of level 0) in shared memory -- three dependent launches of a few microseconds each become one.
+// BORDER_REFLECT_101 is applied with the level's own size on every read; results are identical to k_pyr_down's.
+__device__ __forceinline__ int pyr_reflect(int c, int n) { return c < 0 ? -c : (c >= n ? 2 * (n - 1) - c : c); }
+template <int RS, int PS, int RD, int PD>
+__device__ __forceinline__ void pyr_down_region(const uint8_t* src, int sox, int soy, int sw, int sh,      // source region (origin, level size)
+                                                uint8_t* dst, int dox, int doy, const PyrLevel& L,          // destination region (origin), destination level
+                                                int own_x0, int own_y0, int own_n)                          // owned square of the destination level
+{
+    for (int o = threadIdx.x; o < RD * RD; o += 256) {
+        const int ry = o / RD, rx = o - ry * RD;
+        const int x = dox + rx, y = doy + ry;
+        if (x < 0 || y < 0 || x >= L.w || y >= L.h) continue;
+        int xi[5], acc = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) xi[k] = pyr_reflect(2 * x - 2 + k, sw) - sox;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint8_t* p = src + (pyr_reflect(2 * y - 2 + r, sh) - soy) * PS;
+            const int row = p[xi[2]] * 6 + (p[xi[1]] + p[xi[3]]) * 4 + p[xi[0]] + p[xi[4]];
+            acc += row * ((r == 0 || r == 4) ? 1 : ((r == 2) ? 6 : 4));
+        }
+        const uint8_t v = (uint8_t)((acc + 128) >> 8);
+        dst[ry * PD + rx] = v;
+        if (x >= own_x0 && x < own_x0 + own_n && y >= own_y0 && y < own_y0 + own_n) store_with_border(L, x, y, v);
+    }
+}
+__global__ void __launch_bounds__(256) k_pyr_down3(PyrLevel l0, PyrLevel l1, PyrLevel l2, PyrLevel l3)
+{
+    __shared__ uint8_t s0[85 * 88], s1[41 * 44], s2[19 * 20], s3[8 * 8];
+    const int X3 = 8 * blockIdx.x, Y3 = 8 * blockIdx.y;
+    const int o2x = 2 * X3 - 2, o2y = 2 * Y3 - 2, o1x = 2 * o2x - 2, o1y = 2 * o2y - 2, o0x = 2 * o1x - 2, o0y = 2 * o1y - 2;
+    for (int o = threadIdx.x; o < 85 * 85; o += 256) {
+        const int ry = o / 85, rx = o - ry * 85;
+        const int x = o0x + rx, y = o0y + ry;
+        uint8_t v = 0;
+        if (x >= 0 && y >= 0 && x < l0.w && y < l0.h) v = l0.base[(ptrdiff_t)y * l0.pitch + x];
+        s0[ry * 88 + rx] = v;
+    }
+    __syncthreads();
+    pyr_down_region<85, 88, 41, 44>(s0, o0x, o0y, l0.w, l0.h, s1, o1x, o1y, l1, 4 * X3, 4 * Y3, 32);
+    __syncthreads();
+    pyr_down_region<41, 44, 19, 20>(s1, o1x, o1y, l1.w, l1.h, s2, o2x, o2y, l2, 2 * X3, 2 * Y3, 16);
+    __syncthreads();
+    pyr_down_region<19, 20, 8, 8>(s2, o2x, o2y, l2.w, l2.h, s3, X3, Y3, l3, X3, Y3, 8);
+}
+
 // ================================================================================================
 // pyramidal Lucas-Kanade, one warp per feature
 // ================================================================================================
@@ -548,14 +597,17 @@ __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P, const __grid_c
 // ================================================================================================
 // RANSAC (single CTA)
 // ================================================================================================
-__device__ __forceinline__ int glibc_rand_next(TrackerScalars* sc)
+// glibc rand() state, staged in shared memory for the draw loop (the state lives in the tracker's device scalars: every
+// draw would otherwise be a dependent load-modify-store round trip to L2)
+struct RngLocal { int r[34]; int f, b; };
+__device__ __forceinline__ int glibc_rand_next(RngLocal* sc)
 {
     // glibc random_r.c TYPE_3: r[f] += r[b]; result = r[f] >> 1
-    unsigned v = (unsigned)sc->rng_r[sc->rng_f] + (unsigned)sc->rng_r[sc->rng_b];
-    sc->rng_r[sc->rng_f] = (int)v;
+    unsigned v = (unsigned)sc->r[sc->f] + (unsigned)sc->r[sc->b];
+    sc->r[sc->f] = (int)v;
     const int res = (int)(v >> 1);
-    if (++sc->rng_f >= 31) { sc->rng_f = 0; ++sc->rng_b; }
-    else if (++sc->rng_b >= 31) sc->rng_b = 0;
+    if (++sc->f >= 31) { sc->f = 0; ++sc->b; }
+    else if (++sc->b >= 31) sc->b = 0;
     return res;
 }
 
@@ -595,9 +647,14 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
     __shared__ int sCnt[kRansacIters];
     __shared__ int sWinner;
     __shared__ unsigned s_used[128];
+    __shared__ RngLocal s_rng;
+    __shared__ int s_pick[2 * kRansacIters];
     const int tid = threadIdx.x;
     const TrackerBuffers& B = P.B;
     TrackerScalars* sc = B.sc;
+    if (tid < 34) s_rng.r[tid] = sc->rng_r[tid];
+    if (tid == 34) { s_rng.f = sc->rng_f; s_rng.b = sc->rng_b; }
+    if (tid >= 64 && tid < 73) sR[tid - 64] = P.R[tid - 64];   // GetRotation: evaluated on the host, uploaded per frame (see tracker_enqueue)
 
     // flags start as the LK status (Tracker.cc:264 passes vInlierFlag in/out)
     for (int i = tid; i < n; i += 256) B.flags[i] = B.status[i];
@@ -621,24 +678,27 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
     // SetPointPair (Ransac.cc:57-82); defined here as "flags untouched", no rand() consumed.
     if (nc < 2 * kRansacIters) return;
 
+    if (tid < 128) s_used[tid] = 0u;
+    __syncthreads();
     if (tid == 0) {
-        // SetPointPair (Ransac.cc:50-83); "used" is a shared-memory bitmask (nc <= 4096)
-        for (int i = 0; i < 128; ++i) s_used[i] = 0u;
+        // SetPointPair (Ransac.cc:50-83); "used" is a shared-memory bitmask (nc <= 4096); the draws run on the staged state
         for (int it = 0; it < kRansacIters; ++it) {
             int a, b;
-            do { a = glibc_rand_next(sc) % nc; } while ((s_used[a >> 5] >> (a & 31)) & 1u);
-            do { b = glibc_rand_next(sc) % nc; } while (((s_used[b >> 5] >> (b & 31)) & 1u) || a == b);
-            B.two_points[2 * it] = B.cand[a];
-            B.two_points[2 * it + 1] = B.cand[b];
+            do { a = glibc_rand_next(&s_rng) % nc; } while ((s_used[a >> 5] >> (a & 31)) & 1u);
+            do { b = glibc_rand_next(&s_rng) % nc; } while (((s_used[b >> 5] >> (b & 31)) & 1u) || a == b);
+            s_pick[2 * it] = a; s_pick[2 * it + 1] = b;
             s_used[a >> 5] |= 1u << (a & 31); s_used[b >> 5] |= 1u << (b & 31);
         }
-        for (int i = 0; i < 9; ++i) sR[i] = P.R[i];        // GetRotation: evaluated on the host, uploaded per frame (see tracker_enqueue)
         sc->ransac_ran = 1;
     }
     __syncthreads();
+    if (tid < 34) sc->rng_r[tid] = s_rng.r[tid];
+    if (tid == 34) { sc->rng_f = s_rng.f; sc->rng_b = s_rng.b; }
+    if (tid >= 64 && tid < 64 + 2 * kRansacIters) { const int pi = B.cand[s_pick[tid - 64]]; s_pick[tid - 64] = pi; B.two_points[tid - 64] = pi; }
+    __syncthreads();
     if (tid < kRansacIters) {
         // SetRansacModel (Ransac.cc:86-117)
-        const int ia = B.two_points[2 * tid], ib = B.two_points[2 * tid + 1];
+        const int ia = s_pick[2 * tid], ib = s_pick[2 * tid + 1];
         const double A1[3] = {(double)B.pts1[ia].x, (double)B.pts1[ia].y, 1.0};
         const double A2[3] = {(double)B.un[ia].x, (double)B.un[ia].y, 1.0};
         const double B1[3] = {(double)B.pts1[ib].x, (double)B.pts1[ib].y, 1.0};
@@ -664,14 +724,23 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
     }
     __syncthreads();
     // CountInliers (Ransac.cc:158-177): 16 x nc Sampson tests
-    for (int it = 0; it < kRansacIters; ++it) {
-        int v = 0;
+    {
+        int v[kRansacIters];                               // point-major: every candidate is loaded once and tested against all hypotheses
+#pragma unroll
+        for (int it = 0; it < kRansacIters; ++it) v[it] = 0;
         for (int k = tid; k < nc; k += 256) {
             const int idx = B.cand[k];
-            if (epi_dist(&sE[9 * it], B.pts1[idx].x, B.pts1[idx].y, B.un[idx].x, B.un[idx].y, P.use_sampson) < P.thr) v++;
+            const float2 p1 = B.pts1[idx], p2 = B.un[idx];
+#pragma unroll
+            for (int it = 0; it < kRansacIters; ++it)
+                if (epi_dist(&sE[9 * it], p1.x, p1.y, p2.x, p2.y, P.use_sampson) < P.thr) v[it]++;
         }
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0 && v) atomicAdd(&sCnt[it], v);
+#pragma unroll
+        for (int it = 0; it < kRansacIters; ++it) {
+            int w = v[it];
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+            if ((tid & 31) == 0 && w) atomicAdd(&sCnt[it], w);
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -1153,9 +1222,14 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
         RVIO_LAUNCH(k_copy_level0, grd, blk, 0, s, gray_dev, gray_pitch, cur.lv[0]);
     }
     RVIO_ENQ(cudaEventRecord(t->ev_level0, s));            // what the detector needs (Tracker.cc:207,350 pass the equalised image)
-    for (int l = 1; l < cur.levels; ++l) {
-        const dim3 g(div_up(cur.lv[l].w, 256), cur.lv[l].h);
-        RVIO_LAUNCH(k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
+    if (cur.levels == 4) {
+        const dim3 g(div_up(cur.lv[3].w, 8), div_up(cur.lv[3].h, 8));
+        RVIO_LAUNCH(k_pyr_down3, g, blk, 0, s, cur.lv[0], cur.lv[1], cur.lv[2], cur.lv[3]);
+    } else {
+        for (int l = 1; l < cur.levels; ++l) {
+            const dim3 g(div_up(cur.lv[l].w, 256), cur.lv[l].h);
+            RVIO_LAUNCH(k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
+        }
     }
     t->frame_open = true;
     if (t->first) { RVIO_ENQ(cudaGetLastError()); return RVIO_FIRST_IMAGE; }

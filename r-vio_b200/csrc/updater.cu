@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     __shared__ int s_flag[4];           // [0] reject code, [1] Nc
     __shared__ double s_hh[4];          // householder: beta, alpha
     __shared__ double s_fro[kFeatThreads / 32];
+    __shared__ double s_lm[10][33];     // LM normal-equation terms per measurement lane (+ the totals in column 32)
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -268,9 +269,25 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
                     a11 += h01 * Hm[1] + h11 * Hm[4]; a12 += h01 * Hm[2] + h11 * Hm[5]; a22 += h02 * Hm[2] + h12 * Hm[5];
                     g0 += h00 * e0 + h10 * e1; g1 += h01 * e0 + h11 * e1; g2 += h02 * e0 + h12 * e1;
                 }
-                a00 = warp_sum(a00); a01 = warp_sum(a01); a02 = warp_sum(a02); a11 = warp_sum(a11);
-                a12 = warp_sum(a12); a22 = warp_sum(a22); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
-                cost = warp_sum(cost);
+                // ten sums over the measurements: through shared memory, lane v adds up quantity v over the (few) measurement
+                // lanes in index order -- one short dependent chain instead of ten 5-stage shuffle reductions
+                {
+                    const int nl = min(L, 32);
+                    __syncwarp();
+                    if (lane < nl) {
+                        s_lm[0][lane] = a00; s_lm[1][lane] = a01; s_lm[2][lane] = a02; s_lm[3][lane] = a11; s_lm[4][lane] = a12;
+                        s_lm[5][lane] = a22; s_lm[6][lane] = g0; s_lm[7][lane] = g1; s_lm[8][lane] = g2; s_lm[9][lane] = cost;
+                    }
+                    __syncwarp();
+                    if (lane < 10) {
+                        double acc = 0;
+                        for (int i = 0; i < nl; ++i) acc += s_lm[lane][i];
+                        s_lm[lane][32] = acc;
+                    }
+                    __syncwarp();
+                    a00 = s_lm[0][32]; a01 = s_lm[1][32]; a02 = s_lm[2][32]; a11 = s_lm[3][32]; a12 = s_lm[4][32];
+                    a22 = s_lm[5][32]; g0 = s_lm[6][32]; g1 = s_lm[7][32]; g2 = s_lm[8][32]; cost = s_lm[9][32];
+                }
                 if (cost <= lastCost) {
                     double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
                     const double g[3] = {g0, g1, g2};
@@ -495,15 +512,26 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         if (a > b) S[a * dof + b] = S[b * dof + a];
     }
     __syncthreads();
-    // Cholesky S = L L^T (lower), all threads
+    // Cholesky S = L L^T (lower), all threads; the forward substitution y = L^-1 r rides along (column j of L is applied to
+    // the right-hand side in the same step), gamma = y^T y
+    for (int i = tid; i < dof; i += kFeatThreads) vv[i] = rn[i];
+    double gamma = 0;                                  // (thread 0's copy is the one that counts)
+    __syncthreads();
     for (int j = 0; j < dof; ++j) {
         if (tid == 0) {
             const double dj = S[j * dof + j];
-            s_hh[1] = (dj > 0) ? sqrt(dj) : nan("");
+            const double sd = (dj > 0) ? sqrt(dj) : nan("");
+            const double yj = vv[j] / sd;
+            s_hh[1] = sd; s_hh[2] = yj;
+            gamma += yj * yj;
         }
         __syncthreads();
-        const double dj = s_hh[1];
-        for (int i = j + tid; i < dof; i += kFeatThreads) S[i * dof + j] = (i == j) ? dj : S[i * dof + j] / dj;
+        const double dj = s_hh[1], yj = s_hh[2];
+        for (int i = j + tid; i < dof; i += kFeatThreads) {
+            const double lij = (i == j) ? dj : S[i * dof + j] / dj;
+            S[i * dof + j] = lij;
+            if (i > j) vv[i] -= lij * yj;
+        }
         __syncthreads();
         const int rem = dof - j - 1;
         for (int o = tid; o < rem * rem; o += kFeatThreads) {
@@ -513,17 +541,6 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         __syncthreads();
     }
     if (warp == 0) {
-        // y = L^-1 r ; gamma = y^T y   (forward substitution: lanes split each dot product)
-        double gamma = 0;
-        for (int i = 0; i < dof; ++i) {
-            double part = 0;
-            for (int k = lane; k < i; k += 32) part += S[i * dof + k] * vv[k];
-            part = warp_sum(part);
-            const double y = (rn[i] - part) / S[i * dof + i];
-            if (lane == 0) vv[i] = y;
-            __syncwarp();
-            gamma += y * y;
-        }
         if (lane == 0) {
             gamma = fabs(gamma);
             P.f_gamma[f] = gamma;

@@ -29,6 +29,10 @@ for idx in [int(a) for a in sys.argv[1:]] or [1]:
         seg("k_rank_rule   [setup | fill | cholesky | test | verdict | emit]", [16, 17, 18, 19, 20, 21])
         if c[6] > c[0] > 0:
             seg("k_solve_small_R [stage | W | S | cholesky | P+ | correction]", [0, 1, 2, 3, 4, 5, 6])
+        seg("  panel 1 of the rank rule [A | barrier | walk | diag tile | factor | my rows | barrier]", [48, 49, 50, 51, 52, 53, 54, 55])
+        seg("  panel 1 of the other Cholesky [A | barrier | - | diag tile | factor | my rows | barrier]", [40, 41, 42, 43, 44, 45, 46, 47])
+        seg("    diagonal tile 2, rank rule [columns | norms + pivots | X]", [56, 57, 58, 59])
+        seg("    diagonal tile 2, other     [columns | norms + pivots | X]", [60, 61, 62, 63])
         if c[34] > c[32] > 0:
             seg("k_chol_S      [cholesky | inverses + write-out]", [32, 33, 34])
     upd.close()
