@@ -266,27 +266,39 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
         const bool slide = !(N < W);
         dn = slide ? d : d1;
         Nn = slide ? N : N + 1;
-        // element (a,b) of J P J^T, symmetrised, with the oldest clone removed when the window is full
-        for (int o = tid; o < dn * dn; o += 576) {
-            const int a = o % dn, b = o / dn;
-            int sa = a, sb = b;
-            if (slide) { if (a >= 24) sa = a + 6; if (b >= 24) sb = b + 6; }
-            // index in the (d+6) system -> source row/col of P
-            const int ra = sa < d ? sa : (sa - d < 3 ? 9 + (sa - d) : 12 + (sa - d - 3));
-            const int rb = sb < d ? sb : (sb - d < 3 ? 9 + (sb - d) : 12 + (sb - d - 3));
-            Q.P_out[(size_t)b * dn + a] = .5 * (PP(Q.P_in, d, ra, rb) + PP(Q.P_in, d, rb, ra));
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double clone[7];
-            for (int k = 0; k < 7; ++k) clone[k] = x[10 + k];
-            if (!slide) {
-                for (int k = 0; k < 7; ++k) x[26 + 7 * N + k] = clone[k];
-            } else {
-                for (int k = 0; k < 7 * (W - 1); ++k) x[26 + k] = x[33 + k];
-                for (int k = 0; k < 7; ++k) x[26 + 7 * (W - 1) + k] = clone[k];
+        // element (a,b) of J P J^T, symmetrised, with the oldest clone removed when the window is full; four elements per
+        // thread and pass (eight independent loads in flight: the loop is bound by the latency of the transposed reads)
+        for (int o0 = tid; o0 < dn * dn; o0 += 4 * 576) {
+            double u[4], w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int o = o0 + q * 576;
+                u[q] = 0; w[q] = 0;
+                if (o < dn * dn) {
+                    const int a = o % dn, b = o / dn;
+                    int sa = a, sb = b;
+                    if (slide) { if (a >= 24) sa = a + 6; if (b >= 24) sb = b + 6; }
+                    // index in the (d+6) system -> source row/col of P
+                    const int ra = sa < d ? sa : (sa - d < 3 ? 9 + (sa - d) : 12 + (sa - d - 3));
+                    const int rb = sb < d ? sb : (sb - d < 3 ? 9 + (sb - d) : 12 + (sb - d - 3));
+                    u[q] = PP(Q.P_in, d, ra, rb); w[q] = PP(Q.P_in, d, rb, ra);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int o = o0 + q * 576;
+                if (o < dn * dn) Q.P_out[o] = .5 * (u[q] + w[q]);
             }
         }
+        // state: the new clone is the current IMU pose (x[10..16]); a full window drops its oldest clone first.  One element
+        // per thread, loads before the barrier, stores after it
+        const int nshift = slide ? 7 * (W - 1) : 0;
+        double keep = 0, cl = 0;
+        if (tid < nshift) keep = x[33 + tid];
+        if (tid >= 576 - 7) cl = x[10 + tid - (576 - 7)];
+        __syncthreads();
+        if (tid < nshift) x[26 + tid] = keep;
+        if (tid >= 576 - 7) x[(slide ? 26 + 7 * (W - 1) : 26 + 7 * N) + tid - (576 - 7)] = cl;
     } else {
         for (int o = tid; o < d * d; o += 576) Q.P_out[o] = Q.P_in[o];
     }

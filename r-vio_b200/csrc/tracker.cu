@@ -639,6 +639,12 @@ __device__ __forceinline__ double epi_dist(const double* E, double x1, double y1
     return (num * num) / (Fx10 * Fx10 + Fx11 * Fx11 + Fx20 * Fx20 + Fx21 * Fx21);
 }
 
+#ifdef RVIO_B200_PHASE_CLOCKS
+__device__ long long g_trk_clk[32];
+#define TRK_CLK(k) do { if (threadIdx.x == 0) g_trk_clk[k] = clock64(); } while (0)
+#else
+#define TRK_CLK(k) do { } while (0)
+#endif
 __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
 {
     __shared__ int sh[34];
@@ -656,6 +662,7 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
     if (tid == 34) { s_rng.f = sc->rng_f; s_rng.b = sc->rng_b; }
     if (tid >= 64 && tid < 73) sR[tid - 64] = P.R[tid - 64];   // GetRotation: evaluated on the host, uploaded per frame (see tracker_enqueue)
 
+    TRK_CLK(0);
     // flags start as the LK status (Tracker.cc:264 passes vInlierFlag in/out)
     for (int i = tid; i < n; i += 256) B.flags[i] = B.status[i];
     // candidate compaction in index order (Ransac.cc:190-199)
@@ -680,6 +687,7 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
 
     if (tid < 128) s_used[tid] = 0u;
     __syncthreads();
+    TRK_CLK(1);
     if (tid == 0) {
         // SetPointPair (Ransac.cc:50-83); "used" is a shared-memory bitmask (nc <= 4096); the draws run on the staged state
         for (int it = 0; it < kRansacIters; ++it) {
@@ -692,6 +700,7 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
         sc->ransac_ran = 1;
     }
     __syncthreads();
+    TRK_CLK(2);
     if (tid < 34) sc->rng_r[tid] = s_rng.r[tid];
     if (tid == 34) { sc->rng_f = s_rng.f; sc->rng_b = s_rng.b; }
     if (tid >= 64 && tid < 64 + 2 * kRansacIters) { const int pi = B.cand[s_pick[tid - 64]]; s_pick[tid - 64] = pi; B.two_points[tid - 64] = pi; }
@@ -723,26 +732,34 @@ __device__ __forceinline__ void ransac_body(const RansacParams& P, const int n)
         for (int i = 0; i < 9; ++i) { sE[9 * tid + i] = E[i]; B.hyp[9 * tid + i] = E[i]; }
     }
     __syncthreads();
+    TRK_CLK(3);
     // CountInliers (Ransac.cc:158-177): 16 x nc Sampson tests
     {
-        int v[kRansacIters];                               // point-major: every candidate is loaded once and tested against all hypotheses
+        // point-major: every candidate is loaded once and tested against all hypotheses; the counts are formed with warp votes
+        // (one ballot per hypothesis) instead of sixteen shuffle reductions
+        int wcnt[kRansacIters];
 #pragma unroll
-        for (int it = 0; it < kRansacIters; ++it) v[it] = 0;
-        for (int k = tid; k < nc; k += 256) {
-            const int idx = B.cand[k];
-            const float2 p1 = B.pts1[idx], p2 = B.un[idx];
+        for (int it = 0; it < kRansacIters; ++it) wcnt[it] = 0;
+        for (int k0 = 0; k0 < nc; k0 += 256) {
+            const int k = k0 + tid;
+            unsigned msk = 0;
+            if (k < nc) {
+                const int idx = B.cand[k];
+                const float2 p1 = B.pts1[idx], p2 = B.un[idx];
 #pragma unroll
-            for (int it = 0; it < kRansacIters; ++it)
-                if (epi_dist(&sE[9 * it], p1.x, p1.y, p2.x, p2.y, P.use_sampson) < P.thr) v[it]++;
+                for (int it = 0; it < kRansacIters; ++it)
+                    if (epi_dist(&sE[9 * it], p1.x, p1.y, p2.x, p2.y, P.use_sampson) < P.thr) msk |= 1u << it;
+            }
+#pragma unroll
+            for (int it = 0; it < kRansacIters; ++it) wcnt[it] += __popc(__ballot_sync(0xffffffffu, (msk >> it) & 1u));
         }
+        if ((tid & 31) == 0) {
 #pragma unroll
-        for (int it = 0; it < kRansacIters; ++it) {
-            int w = v[it];
-            for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
-            if ((tid & 31) == 0 && w) atomicAdd(&sCnt[it], w);
+            for (int it = 0; it < kRansacIters; ++it) if (wcnt[it]) atomicAdd(&sCnt[it], wcnt[it]);
         }
     }
     __syncthreads();
+    TRK_CLK(4);
     if (tid == 0) {
         int best = 0, bi = 0;
         for (int it = 0; it < kRansacIters; ++it) {
@@ -815,6 +832,7 @@ __device__ __forceinline__ void bookkeep_body(const TrackerBuffers& B, int n)
         n_up += emitted;
         n_meas += tot_m;
     }
+    TRK_CLK(6);
     // ---- pass 2: tracked features (Tracker.cc:305-342)
     int n_in = 0;
     for (int start = 0; start < n; start += 256) {
@@ -857,6 +875,7 @@ __device__ __forceinline__ void bookkeep_body(const TrackerBuffers& B, int n)
         n_up += emitted;
         n_meas += tot_m;
     }
+    TRK_CLK(7);
     if (tid == 0) {
         B.up_off[n_up] = n_meas;
         sc->fq_n = fq_n0 + n_lost;
@@ -872,8 +891,10 @@ __global__ void __launch_bounds__(256) k_ransac_bookkeep(RansacParams P)
     const int n = P.n_dev ? *P.n_dev : P.n;       // read before anything below rewrites the scalars
     ransac_body(P, n);
     __syncthreads();
+    TRK_CLK(5);
     __threadfence_block();
     bookkeep_body(P.B, n);
+    TRK_CLK(8);
 }
 
 // First image (Tracker.cc:215-233): slot i <- corner i, free list = n..F-1.
@@ -1597,3 +1618,11 @@ int tracker_update_counts(const rvio_tracker* t, int* n_meas) { if (n_meas) *n_m
 int tracker_device(const rvio_tracker* t) { return t->device; }
 cudaStream_t tracker_stream(const rvio_tracker* t) { return t->stream; }
 }
+
+#ifdef RVIO_B200_PHASE_CLOCKS
+extern "C" int rvio_b200_trk_clocks(long long* out, int n)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, rvio::g_trk_clk, sizeof(long long) * (n < 32 ? n : 32));
+}
+#endif

@@ -802,56 +802,112 @@ struct GramParams {
 // of z) over the features of its group into a partial buffer; the LAST CTA of a tile to finish (atomic ticket) sums the
 // partials in fixed group order (deterministic) into the reduce buffer; the last CTA of tile 0 also writes the counters.
 // reduce buffer layout: [G (n*n) | z (n) | counters (8) | cls (n+1)]; counters: n_good, rows, rej_init, rej_lm, rej_gate, n_local
+#ifdef RVIO_B200_PHASE_CLOCKS
+// (profiling build only) wall-clock (globaltimer, ns) span of k_gram over all CTAs and the phases of tile 0's reducing CTA
+__device__ unsigned long long g_gram_ns[16];
+__device__ __forceinline__ unsigned long long gram_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GRAM_T(k) do { if (threadIdx.x == 0) g_gram_ns[k] = gram_now(); } while (0)
+#else
+#define GRAM_T(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
-    __shared__ double sA[8][33], sB[8][33];
-    __shared__ int s_last;
+#ifdef RVIO_B200_PHASE_CLOCKS
+    const unsigned long long t_in = gram_now();
+    if (threadIdx.x == 0) { atomicMin(&g_gram_ns[0], t_in); }
+#endif
+    __shared__ double sA[2][8][33], sB[2][8][33], s_r[2][8];      // double-buffered 8-row chunks of the two column ranges (+ residuals)
+    __shared__ int s_list[256], s_ldof[256];                      // features of this group that touch the tile, in index order
+    __shared__ int s_wsum[8], s_last, s_cnt[6];
     __shared__ double s_cls[192];
+    __shared__ int s_fd[512], s_fc[512];                          // (tail) dof / first column of every feature
+    __shared__ double s_ff[512];
     const int ti = blockIdx.x / P.nt, tj = blockIdx.x % P.nt, g = blockIdx.y;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
     const int n = P.n;
     const int i0 = ti * 32, j0 = tj * 32;
+    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
+    // ---- which of this group's features (f = g, g + groups, ...) touch the tile: one feature per thread, order-preserving
+    //      compaction (the accumulation order over the features is part of the deterministic result)
+    int n_act = 0;
+    for (int base = 0; base * P.groups + g < n_feat; base += 256) {
+        const int f = g + (base + tid) * P.groups;
+        int dof = 0;
+        bool act = false;
+        if (f < n_feat) {
+            dof = P.f_dof[f];
+            if (dof > 0) {
+                const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
+                act = !(i0 >= c1 || i0 + 32 <= c0 || j0 >= c1 || j0 + 32 <= c0);     // block is zero on this tile otherwise
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = n_act;
+        for (int w = 0; w < warp; ++w) off += s_wsum[w];
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_wsum[w];
+        if (act) { const int pos = off + __popc(m & ((1u << lane) - 1u)); if (pos < 256) { s_list[pos] = f; s_ldof[pos] = dof; } }
+        n_act += tot;
+        __syncthreads();
+    }
+    if (n_act > 256) n_act = 256;                                  // (cannot happen: <= 4096 features over 16 groups)
     double acc[2][2] = {{0, 0}, {0, 0}};
     double zacc = 0;
-    const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
-    for (int f = g; f < n_feat; f += P.groups) {
-        const int dof = P.f_dof[f];
-        if (dof <= 0) continue;
-        const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
-        if (i0 >= c1 || i0 + 32 <= c0 || j0 >= c1 || j0 + 32 <= c0) continue;     // block is zero on this tile
-        const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
-        const double* rv = P.rblk + (size_t)f * P.blk_rows;
-        for (int a0 = 0; a0 < dof; a0 += 8) {
-            {
-                const int r = threadIdx.x >> 5, c = threadIdx.x & 31;      // 8 rows x 32 cols
-                const int a = a0 + r;
-                sA[r][c] = (a < dof && i0 + c < n) ? H[(size_t)a * n + i0 + c] : 0.0;
-                sB[r][c] = (a < dof && j0 + c < n) ? H[(size_t)a * n + j0 + c] : 0.0;
-            }
+    {
+        // chunk stream (feature li, rows a0 .. a0 + 7): the loads of chunk t + 1 are in flight while chunk t is multiplied
+        const int r = tid >> 5, c = tid & 31;                      // 8 rows x 32 columns
+        int li = 0, a0 = 0;
+        double ra = 0, rb = 0, rr = 0;
+        auto fetch = [&](int li_, int a0_) {
+            const int f = s_list[li_], dof = s_ldof[li_];
+            const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+            const int a = a0_ + r;
+            ra = (a < dof && i0 + c < n) ? H[(size_t)a * n + i0 + c] : 0.0;
+            rb = (a < dof && j0 + c < n) ? H[(size_t)a * n + j0 + c] : 0.0;
+            rr = (c == 0 && a < dof && ti == tj) ? P.rblk[(size_t)f * P.blk_rows + a] : 0.0;
+        };
+        if (n_act > 0) fetch(0, 0);
+        int buf = 0;
+        while (li < n_act) {
+            sA[buf][r][c] = ra; sB[buf][r][c] = rb;
+            if (c == 0) s_r[buf][r] = rr;
             __syncthreads();
+            int nli = li, na0 = a0 + 8;
+            if (na0 >= s_ldof[li]) { nli = li + 1; na0 = 0; }
+            if (nli < n_act) fetch(nli, na0);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double a0v = sA[r][2 * ty], a1v = sA[r][2 * ty + 1];
-                const double b0v = sB[r][2 * tx], b1v = sB[r][2 * tx + 1];
+            for (int q = 0; q < 8; ++q) {
+                const double a0v = sA[buf][q][2 * ty], a1v = sA[buf][q][2 * ty + 1];
+                const double b0v = sB[buf][q][2 * tx], b1v = sB[buf][q][2 * tx + 1];
                 acc[0][0] += a0v * b0v; acc[0][1] += a0v * b1v; acc[1][0] += a1v * b0v; acc[1][1] += a1v * b1v;
             }
-            if (ti == tj && threadIdx.x < 32) {
-                // z rows of this tile (a diagonal tile sees every feature that touches these columns)
-                for (int r = 0; r < 8; ++r) { const int a = a0 + r; if (a < dof) zacc += sA[r][threadIdx.x] * rv[a]; }
+            if (ti == tj && tid < 32) {
+                // z rows of this tile (a diagonal tile sees every feature that touches these columns); rows past dof are zero
+#pragma unroll
+                for (int q = 0; q < 8; ++q) zacc += sA[buf][q][tid] * s_r[buf][q];
             }
-            __syncthreads();
+            li = nli; a0 = na0; buf ^= 1;
         }
     }
+#ifdef RVIO_B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) { atomicMax(&g_gram_ns[1], gram_now()); }       // products done (latest CTA)
+#endif
     double* Gp = P.Gpart + (size_t)g * n * n;
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
             const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
             if (i < n && j < n) Gp[(size_t)i * n + j] = acc[a][b];
         }
-    if (ti == tj && threadIdx.x < 32 && i0 + threadIdx.x < n) P.zpart[(size_t)g * n + i0 + threadIdx.x] = zacc;
+    if (ti == tj && tid < 32 && i0 + tid < n) P.zpart[(size_t)g * n + i0 + tid] = zacc;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
+#ifdef RVIO_B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) { atomicMax(&g_gram_ns[2], gram_now()); }       // partials written + fence (latest CTA)
+#endif
+    if (tid == 0) {
         const int t = atomicAdd(&tickets[blockIdx.x], 1);
         s_last = (t == P.groups - 1) ? 1 : 0;
         if (s_last) tickets[blockIdx.x] = 0;           // self-reset for the next launch
@@ -859,24 +915,48 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-            const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + b;
+    {
+        // every partial of this thread's four elements (and its z entry) is requested before the first sum: one round trip to
+        // L2 instead of one per element (the stores into `red` would otherwise fence the next element's loads)
+        const int ng = P.groups;                                   // <= 16 on this path
+        const double* __restrict__ Gpart = P.Gpart;
+        const double* __restrict__ zpart = P.zpart;
+        double v[4][16], vz[16];
+        const bool zrow = ti == tj && tid < 32 && i0 + tid < n;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + 2 * ty + (e >> 1), j = j0 + 2 * tx + (e & 1);
+            const bool ok = i < n && j < n;
+#pragma unroll
+            for (int gg = 0; gg < 16; ++gg) v[e][gg] = (ok && gg < ng) ? Gpart[(size_t)gg * n * n + (size_t)i * n + j] : 0.0;
+        }
+#pragma unroll
+        for (int gg = 0; gg < 16; ++gg) vz[gg] = (zrow && gg < ng) ? zpart[(size_t)gg * n + i0 + tid] : 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + 2 * ty + (e >> 1), j = j0 + 2 * tx + (e & 1);
             if (i < n && j < n) {
                 double sum = 0;
-#pragma unroll 8
-                for (int gg = 0; gg < P.groups; ++gg) sum += P.Gpart[(size_t)gg * n * n + (size_t)i * n + j];
+#pragma unroll
+                for (int gg = 0; gg < 16; ++gg) if (gg < ng) sum += v[e][gg];
                 red[(size_t)i * n + j] = sum;
             }
         }
-    if (ti == tj && threadIdx.x < 32 && i0 + threadIdx.x < n) {
-        double sum = 0;
-        for (int gg = 0; gg < P.groups; ++gg) sum += P.zpart[(size_t)gg * n + i0 + threadIdx.x];
-        red[(size_t)n * n + i0 + threadIdx.x] = sum;
+        if (zrow) {
+            double sum = 0;
+#pragma unroll
+            for (int gg = 0; gg < 16; ++gg) if (gg < ng) sum += vz[gg];
+            red[(size_t)n * n + i0 + tid] = sum;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 64) {
+    if (blockIdx.x != 0) return;
+    GRAM_T(3);
+    // ---- (tile 0 only) counters and the information per column-support class
+    if (tid < 6) s_cnt[tid] = 0;
+    __syncthreads();
+    {
         int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
-        for (int f = rank; f < n_feat; f += world) {
+        for (int f = rank + tid * world; f < n_feat; f += 256 * world) {
             loc++;
             const int st = f_status[f];
             if (st == 0) { good++; rows += P.f_dof[f]; }
@@ -884,22 +964,43 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
             else if (st == 2) r2++;
             else r3++;
         }
+        if (good) atomicAdd(&s_cnt[0], good);
+        if (rows) atomicAdd(&s_cnt[1], rows);
+        if (r1) atomicAdd(&s_cnt[2], r1);
+        if (r2) atomicAdd(&s_cnt[3], r2);
+        if (r3) atomicAdd(&s_cnt[4], r3);
+        if (loc) atomicAdd(&s_cnt[5], loc);
+    }
+    const bool staged = n_feat <= 512;
+    if (staged)
+        for (int f = tid; f < n_feat; f += 256) { s_fd[f] = P.f_dof[f]; s_fc[f] = P.f_c0[f]; s_ff[f] = P.f_fro2[f]; }
+    __syncthreads();
+    if (tid == 0) {
         double* c = red + (size_t)n * n + n;
-        c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
+        c[0] = s_cnt[0]; c[1] = s_cnt[1]; c[2] = s_cnt[2]; c[3] = s_cnt[3]; c[4] = s_cnt[4]; c[5] = s_cnt[5]; c[6] = 0; c[7] = 0;
     }
-    if (blockIdx.x == 0) {
-        // information per column-support class: cls[c] = sum of ||H_f||_F^2 over the accepted features whose first non-zero
-        // column is c (c = 0 for '2' features, 6 (N - (L-1)) for '1' features), in feature order (deterministic)
-        for (int c = threadIdx.x; c <= n; c += 256) {
-            double acc = 0;
-            for (int f = rank; f < n_feat; f += world)
-                if (P.f_dof[f] > 0 && P.f_c0[f] == c) acc += P.f_fro2[f];
-            s_cls[c] = acc;
+    // cls[c] = sum of ||H_f||_F^2 over the accepted features whose first non-zero column is c (c = 0 for '2' features,
+    // 6 (N - (L-1)) for '1' features: multiples of 6).  One warp per class, lanes stride over the features, fixed butterfly:
+    // deterministic
+    for (int c = tid; c <= n; c += 256) s_cls[c] = 0.0;
+    __syncthreads();
+    for (int c = 6 * warp; c <= n; c += 6 * 8) {
+        double a2 = 0;
+        if (staged) {
+            for (int f = rank + lane * world; f < n_feat; f += 32 * world)
+                if (s_fd[f] > 0 && s_fc[f] == c) a2 += s_ff[f];
+        } else {
+            for (int f = rank + lane * world; f < n_feat; f += 32 * world)
+                if (P.f_dof[f] > 0 && P.f_c0[f] == c) a2 += P.f_fro2[f];
         }
-        __syncthreads();
-        double* cls = red + (size_t)n * n + n + 8;
-        for (int c = threadIdx.x; c <= n; c += 256) cls[c] = s_cls[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        if (lane == 0) s_cls[c] = a2;
     }
+    __syncthreads();
+    double* cls = red + (size_t)n * n + n + 8;
+    for (int c = tid; c <= n; c += 256) cls[c] = s_cls[c];
+    GRAM_T(4);
 }
 
 // Normal terms on the tensor cores (large windows): the same two-stage deterministic reduction as k_gram, 64 x 64 tiles of
@@ -2081,3 +2182,13 @@ extern "C" int rvio_updater_set_rank_rule(rvio_updater* u, int mode)
     RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
     return RVIO_OK;
 }
+
+#ifdef RVIO_B200_PHASE_CLOCKS
+extern "C" int rvio_b200_gram_ns(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    int rc = (int)cudaMemcpyFromSymbol(out, rvio::g_gram_ns, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = 0; z[0] = ~0ull; cudaMemcpyToSymbol(rvio::g_gram_ns, z, sizeof z); }
+    return rc;
+}
+#endif
