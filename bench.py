@@ -390,12 +390,12 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         tl = np.zeros(8, np.float32)
         L.rvio_vio_timeline(vio.h, 1, None)
         acc = []
-        for i in range(used, min(used + 12, n_frames)):
+        for i in range(used, min(used + 24, n_frames)):
             vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
             L.rvio_vio_timeline(vio.h, 1, tl.ctypes.data)
             acc.append(tl.copy())
         L.rvio_vio_timeline(vio.h, 0, None)
-        used = min(used + 12, n_frames)
+        used = min(used + 24, n_frames)
         timeline = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail",
                              "host_enqueue", "host_blocked_in_sync"],
                             [round(float(v) * 1e3, 1) for v in np.median(np.array(acc), 0)]))

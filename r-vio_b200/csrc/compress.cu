@@ -109,7 +109,7 @@ __device__ __forceinline__ void tile_mma(double2& c, const double2& a, const dou
 }
 
 // What the factoring warp publishes about the diagonal tile of a panel.
-struct PanelPub {
+struct __align__(16) PanelPub {
     double X[64];             // inv(L_JJ), row-major; rows / columns of skipped pivots are zero
     double cin[8];            // RANK: the tile's own share of |L(:, c)|^2 (real rows)
     double pv[8];             // pivots (as found, before the square root)
@@ -420,9 +420,11 @@ __device__ __forceinline__ void tile_cholesky(const TileTri& T, int nact, const 
 // With Q.emit_R the kept rows (scaled, zero padded to n x n) and y are also written out: the large-window EKF step works on
 // them (R-form: S = R Pcc R^T + s^2 I).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
+// rsm: the tile-packed factor (lower: column j of L = row j of R), y in the extra row.  Rt_smem (optional, fused small-window
+// step): the kept rows go straight into the EKF step's shared-memory tiles of R (upper triangle by tile, rt_tc tile columns)
+// and yc_smem instead of global memory.
+__device__ __forceinline__ void rank_rule_body(const RankRuleParams& Q, double* rsm, double* Rt_smem, int rt_tc, double* yc_smem)
 {
-    extern __shared__ __align__(16) double rsm[];            // the tile-packed factor (lower: column j of L = row j of R), y in the extra row
     __shared__ double s_pv[kSFMaxRows], s_gd[kSFMaxRows], s_late[kSFMaxRows + 2], s_nr2[kSFMaxRows];
     __shared__ double s_part[9 * kBCWarps];
     __shared__ PanelPub s_pub;
@@ -544,7 +546,19 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
         cnt[7] = (rebuild ? 8.0 : 0.0) + (discards ? 1.0 : 0.0) + (mode == 4 ? 4.0 : 0.0) + (generic ? 16.0 : 0.0);
     }
     PHASE_CLK(20);
-    if (Q.emit_R && mode != 3) {
+    if (Q.emit_R && mode != 3 && Rt_smem) {
+        const int kl = klim, ntl = rt_tc * (rt_tc + 1) / 2;
+        for (int o = tid; o < ntl * 64; o += kBCThreads) {       // tile (Rj, Kb >= Rj) at Rj rt_tc - Rj (Rj - 1) / 2 + Kb - Rj
+            const int tl = o >> 6, e = o & 63;
+            int Rj = 0, rem = tl;
+            while (rem >= rt_tc - Rj) { rem -= rt_tc - Rj; ++Rj; }
+            const int r = 8 * Rj + (e >> 3), k = 8 * (Rj + rem) + (e & 7);
+            double v = 0;
+            if (r < kl && r < Np && s_pv[r] >= 0.0 && k >= r && k < Np) v = *T.at(k, r);     // R(r, k) = L(k, r)
+            Rt_smem[o] = v;
+        }
+        for (int j = tid; j < 8 * rt_tc; j += kBCThreads) yc_smem[j] = (j < kl && j < Np && s_pv[j] >= 0.0) ? *T.at(ncp, j) : 0.0;
+    } else if (Q.emit_R && mode != 3) {
         // kept rows of R (= columns of L with a good pivot below klim), zero padded to n x n, and y.  Lane (a, b) of a warp
         // takes R(j0 + b, i0 + a .. ): 8 columns j of one tile row (contiguous in shared memory), 4 consecutive i per row of R
         const int kl = klim;
@@ -578,6 +592,12 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
             if (s_pv[j] >= 0.0) acc = fma(*T.at(r, j), *T.at(ncp, j), acc);
         zw[r] = acc;
     }
+}
+
+__global__ void __launch_bounds__(kBCThreads, 1) k_rank_rule(RankRuleParams Q)
+{
+    extern __shared__ __align__(16) double rsm_dyn[];
+    rank_rule_body(Q, rsm_dyn, nullptr, 0, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -734,9 +754,9 @@ __host__ __device__ inline size_t solve_small_doubles(int n, int d)
     const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
     return (size_t)tile_tri_count(tc, tc + tre) * 64 + solve_small_stage_doubles(n, d);
 }
-__global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRParams Q)
+// r_staged: the tiles of R are already in place (written by rank_rule_body in the same CTA) and y is in yc_smem.
+__device__ __forceinline__ void solve_small_body(const SolveSmallRParams& Q, double* sm, bool r_staged, const double* yc_smem)
 {
-    extern __shared__ __align__(16) double sm[];
     __shared__ double s_pv[kSFMaxRows];
     __shared__ double s_dx[kSFMaxRows];
     __shared__ PanelPub s_pub;
@@ -757,6 +777,7 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
     double* Pt = Rt + (size_t)(tc * (tc + 1) / 2) * 64;             // tile (Ci, Kb) at (Ci tc + Kb) * 64: Pc(8 Kb + k, 8 Ci + c) at [c][k]
     auto rtile = [&](int Rj, int Kb) -> double* { return Rt + ((size_t)(Rj * tc - (Rj * (Rj - 1)) / 2 + Kb - Rj) << 6); };
     PHASE_CLK(0);
+    if (!r_staged)
     for (int o = tid; o < (tc * (tc + 1) / 2) * 32; o += kSRThreads) {          // R -> tiles (tiles of row Rj are consecutive)
         const int tl = o >> 5, rr = (o >> 2) & 7, q2 = 2 * (o & 3);
         int Rj = 0, rem = tl;
@@ -797,7 +818,7 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
         c0.x += c1.x; c0.y += c1.y;
         // the row c = d of the extra rows is y, not a column of W
         const int c = 8 * Ci + g, r = 8 * Rj + 2 * t4;
-        if (c == d) { c0.x = (r < n) ? Q.yc[r] : 0.0; c0.y = (r + 1 < n) ? Q.yc[r + 1] : 0.0; }
+        if (c == d) { const double* ycv = r_staged ? yc_smem : Q.yc; c0.x = (r < n) ? ycv[r] : 0.0; c0.y = (r + 1 < n) ? ycv[r + 1] : 0.0; }
         *reinterpret_cast<double2*>(T.tile(tc + Ci, Rj) + g * 8 + 2 * t4) = c0;
     }
     __syncthreads();
@@ -899,14 +920,19 @@ __global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRPara
     PHASE_CLK(6);
 }
 
+__global__ void __launch_bounds__(kSRThreads, 1) k_solve_small_R(SolveSmallRParams Q)
+{
+    extern __shared__ __align__(16) double sm_dyn[];
+    solve_small_body(Q, sm_dyn, false, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_givens_ref
 // ------------------------------------------------------------------------------------------------
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
+__device__ __forceinline__ void givens_ref_body(const GivensRefParams& Q, double* sm)
 {
-    extern __shared__ __align__(16) double sm[];
     __shared__ short s_accf[kGVMaxFeat], s_accd[kGVMaxFeat];
     __shared__ int s_nacc, s_k, s_full;
     __shared__ double s_tr[2];
@@ -1061,6 +1087,42 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
     }
 }
 
+template <bool SMEM>
+__global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
+{
+    extern __shared__ __align__(16) double gsm_dyn[];
+    givens_ref_body<SMEM>(Q, gsm_dyn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_update_small -- small windows (N <= 12): rank rule, (rarely) the reference's sweep, and the whole EKF step in ONE launch.
+// The kept rows of R never leave shared memory (the rule writes them straight into the EKF step's tiles), the sweep's
+// no-op launch between the two and a memset node disappear, and so do two kernel boundaries of the frame's critical path.
+// Dynamic shared memory: [EKF step: T | R / Pc (later P)] [rank rule's factor]; the sweep (when it runs, the rule's factor is
+// dead and the step has not started) takes the front of the same buffer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBCThreads, 1) k_update_small(RankRuleParams rq, GivensRefParams gq, SolveSmallRParams sq)
+{
+    extern __shared__ __align__(16) double usm[];
+    __shared__ double s_yc[kSFMaxRows];
+    static_assert(kGVThreads == kBCThreads, "the fused step runs the sweep with the CTA it has");
+    const int n = rq.n, d = sq.d;
+    const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
+    if (threadIdx.x == 0) *sq.bad = 0;
+    double* Rt = usm + (size_t)tile_tri_count(tc, tc + tre) * 64;
+    double* rank_tiles = usm + solve_small_doubles(n, d);
+    rank_rule_body(rq, rank_tiles, Rt, tc, s_yc);
+    __syncthreads();
+    const bool updating = sq.gate[0] > 2.0;
+    const bool sweep = updating && rq.rr[3] != 0;                  // (written by thread 0 of this CTA before the barrier)
+    if (sweep) {
+        givens_ref_body<true>(gq, usm);
+        __threadfence_block();
+        __syncthreads();
+    }
+    solve_small_body(sq, usm, updating && !sweep, s_yc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1079,6 +1141,12 @@ static size_t rank_rule_smem_bytes(int n) { const int tc = (n + 7) / 8; return s
 static size_t chol_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + tc) + 64; }
 static size_t trsm_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof(double) * 64 * (size_t)(tile_tri_count(tc, tc) + kTrsmWarps * (tc + 1)) + 64; }
 
+static size_t update_small_smem_bytes(int n, int d)
+{
+    bool w;
+    const size_t a = solve_small_smem_bytes(n, d) + rank_rule_smem_bytes(n), b = givens_smem_bytes(n, &w);
+    return a > b ? a : b;
+}
 constexpr int kSolveSmallRMaxN = 72;      // windows up to 12 clones: the whole EKF step in one CTA (166 KB of shared memory)
 
 int compress_configure(int nmax)
@@ -1096,6 +1164,10 @@ int compress_configure(int nmax)
     {
         const int ns = nmax < kSolveSmallRMaxN ? nmax : kSolveSmallRMaxN;
         RVIO_CUDA_TRY(cudaFuncSetAttribute(k_solve_small_R, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_small_smem_bytes(ns, 24 + ns)));
+    }
+    {
+        const int ns = nmax < kSolveSmallRMaxN ? nmax : kSolveSmallRMaxN;
+        RVIO_CUDA_TRY(cudaFuncSetAttribute(k_update_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_small_smem_bytes(ns, 24 + ns)));
     }
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_chol_S, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(nmax)));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(nmax)));
@@ -1123,6 +1195,18 @@ int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q)
     const int n = 6 * q.N;
     if (n > kSolveSmallRMaxN) { set_error("enqueue_solve_small_R", "window too large for the single-CTA solve"); return RVIO_ERR_CAPACITY; }
     RVIO_LAUNCH(k_solve_small_R, 1, kSRThreads, solve_small_smem_bytes(n, q.d), s, q);
+    RVIO_ENQ(cudaGetLastError());
+    return RVIO_OK;
+}
+
+// Small windows: rank rule + (rare) sweep + EKF step in one launch.
+int enqueue_update_small(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq, const SolveSmallRParams& q)
+{
+    const int n = 6 * q.N;
+    bool w;
+    givens_smem_bytes(n, &w);
+    if (n > kSolveSmallRMaxN || n + 9 > kSFMaxRows || !w) { set_error("enqueue_update_small", "window too large for the single-CTA step"); return RVIO_ERR_CAPACITY; }
+    RVIO_LAUNCH(k_update_small, 1, kBCThreads, update_small_smem_bytes(n, q.d), s, rq, gq, q);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

@@ -35,6 +35,7 @@ struct SolveSmallRParams {
 
 int compress_configure(int nmax);
 int enqueue_solve_small_R(cudaStream_t s, const SolveSmallRParams& q);
+int enqueue_update_small(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq, const SolveSmallRParams& q);
 size_t givens_window_doubles(int n);
 int enqueue_rank_rule(cudaStream_t s, const RankRuleParams& rq, const GivensRefParams& gq, int n);
 int enqueue_chol_trsm(cudaStream_t s, const double* S, int n, double* L, double* B, int ldb, int nb, int* bad, const double* gate);

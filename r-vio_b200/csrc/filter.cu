@@ -250,6 +250,12 @@ __global__ void __launch_bounds__(576) k_propagate(PropagateParams Q)
 // k_augment_compose: P_in (d x d) -> P_out (d' x d'), x in place.  do_augment / slide decided on the host
 // (deterministic counters, System.cc:280-323), composition System.cc:326-365.
 // ------------------------------------------------------------------------------------------------
+#ifdef RVIO_B200_PHASE_CLOCKS
+__device__ long long g_aug_clk[16];
+#define AUG_CLK(k) do { if (threadIdx.x == 0) g_aug_clk[k] = clock64(); } while (0)
+#else
+#define AUG_CLK(k) do { } while (0)
+#endif
 constexpr int kCrossCols = 96, kCrossLd = kCrossCols + 1;          // clone columns staged per pass (+1: conflict-free column walks)
 __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
 {
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     const int d = Q.d, N = Q.N, W = Q.window;
     double* x = Q.x;
     int dn = d, Nn = N;                      // new dimension / clone count
+    AUG_CLK(0);
     // ---- augmentation
     if (Q.do_augment) {
         const int d1 = d + 6;
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
         }
         // state: the new clone is the current IMU pose (x[10..16]); a full window drops its oldest clone first.  One element
         // per thread, loads before the barrier, stores after it
+        AUG_CLK(1);
         const int nshift = slide ? 7 * (W - 1) : 0;
         double keep = 0, cl = 0;
         if (tid < nshift) keep = x[33 + tid];
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     __syncthreads();
     double* P = Q.P_out;
     const int n = 6 * Nn;
+    AUG_CLK(2);
     // ---- composition
     V[i][j] = 0.0;
     __syncthreads();
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     }
     P00[i][j] = PP(P, dn, i, j);
     __syncthreads();
+    AUG_CLK(3);
     {
         double acc = 0;
         for (int k = 0; k < 24; ++k) acc += V[i][k] * P00[k][j];
@@ -350,6 +360,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
     }
     __syncthreads();
     PP(P, dn, i, j) = .5 * (P00[i][j] + P00[j][i]);
+    AUG_CLK(4);
     // cross terms V P0c, kCrossCols columns per pass: the block P(0:24, 24 + c0 ..) is staged in shared memory (rows are
     // contiguous in memory: coalesced), then one output element per thread (same summation order as before: k ascending)
     for (int c0 = 0; c0 < n; c0 += kCrossCols) {
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
         }
         __syncthreads();
     }
+    AUG_CLK(5);
     // clone-clone block is already symmetric (augmentation symmetrised it; propagate/update symmetrise their outputs)
     __syncthreads();
     if (tid == 0) {
@@ -376,6 +388,7 @@ __global__ void __launch_bounds__(576) k_augment_compose(AugmentParams Q)
         for (int k = 0; k < 3; ++k) Q.pose_out[k] = s_q[10 + k];
         for (int k = 0; k < 4; ++k) Q.pose_out[3 + k] = s_q[k];
     }
+    AUG_CLK(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,3 +526,11 @@ int launch_find_newer_refill(cudaStream_t s, const FindNewerParams& p)
 }
 
 }  // namespace rvio
+
+#ifdef RVIO_B200_PHASE_CLOCKS
+extern "C" int rvio_b200_aug_clocks(long long* out)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, rvio::g_aug_clk, sizeof(long long) * 16);
+}
+#endif

@@ -142,6 +142,13 @@ __device__ __forceinline__ void d_solve3(const double* A_, const double* b_, dou
 // ================================================================================================
 // k_feature: one CTA (128 threads) per feature
 // ================================================================================================
+#ifdef RVIO_B200_PHASE_CLOCKS
+// (profiling build only) phase clocks of the k_feature CTA with the longest track of the launch
+__device__ long long g_feat_clk[16];
+#define FEAT_CLK(k) do { if (threadIdx.x == 0) fclk[k] = clock64(); } while (0)
+#else
+#define FEAT_CLK(k) do { } while (0)
+#endif
 constexpr int kFeatThreads = 256;
 constexpr int kSolveSmallMaxClones = 12;     // n = 72: the single-CTA EKF step (k_solve_small_R) fits in 227 KB of shared memory
 
@@ -156,6 +163,11 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef RVIO_B200_PHASE_CLOCKS
+    long long fclk[12];
+    for (int k = 0; k < 12; ++k) fclk[k] = 0;
+#endif
+    FEAT_CLK(0);
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
     if (f >= n_feat) return;
     if (f % P.world != P.rank) return;   // feature sharding: this rank owns f % world == rank
@@ -188,21 +200,40 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 
     // ---- relative-pose chain, Updater.cc:118-132 (serial in i)
     const double* rel = (type == '1') ? (P.x + P.xdim - 7 * phases_full) : (P.x + 26);
-    if (tid == 0) {
-        double R0[9], t[3];
-        d_quat_to_rot(rel, R0);
-        d_m3v(R0, rel + 4, t);
-        for (int k = 0; k < 4; ++k) relI[k] = rel[k];
-        relI[4] = -t[0]; relI[5] = -t[1]; relI[6] = -t[2];
-        for (int i = 1; i < phases_full; ++i) {
-            double Ri[9], dv[3];
-            d_quat_mul(rel + 7 * i, relI + 7 * (i - 1), relI + 7 * i);
-            d_quat_to_rot(rel + 7 * i, Ri);
-            for (int k = 0; k < 3; ++k) dv[k] = relI[7 * (i - 1) + 4 + k] - rel[7 * i + 4 + k];
-            d_m3v(Ri, dv, relI + 7 * i + 4);
+    if (warp == 0) {
+        // relI_i = A_i o A_(i-1) o ... o A_0 with A_i = (q_i, -R(q_i) p_i) and (q, t) o (q', t') = (q q', R(q) t' + t): rigid
+        // transforms compose associatively, so the chain is an inclusive scan over the lanes (log2 steps instead of L - 1)
+        const bool act = lane < phases_full;
+        double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+        if (act) {
+            double R0[9], tt[3];
+            for (int k = 0; k < 4; ++k) q[k] = rel[7 * lane + k];
+            d_quat_to_rot(q, R0);
+            d_m3v(R0, rel + 7 * lane + 4, tt);
+            t[0] = -tt[0]; t[1] = -tt[1]; t[2] = -tt[2];
+        }
+        for (int sft = 1; sft < phases_full; sft <<= 1) {
+            double q2[4], t2[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q2[k] = __shfl_up_sync(0xffffffffu, q[k], sft);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t2[k] = __shfl_up_sync(0xffffffffu, t[k], sft);
+            if (act && lane >= sft) {
+                double R[9], r[3], qn[4];
+                d_quat_to_rot(q, R);
+                d_m3v(R, t2, r);
+                t[0] += r[0]; t[1] += r[1]; t[2] += r[2];
+                d_quat_mul(q, q2, qn);
+                for (int k = 0; k < 4; ++k) q[k] = qn[k];
+            }
+        }
+        if (act) {
+            for (int k = 0; k < 4; ++k) relI[7 * lane + k] = q[k];
+            for (int k = 0; k < 3; ++k) relI[7 * lane + 4 + k] = t[k];
         }
     }
     __syncthreads();
+    FEAT_CLK(1);
     // ---- camera poses, Updater.cc:134-141 (parallel in i)
     for (int i = tid; i < phases_full; i += kFeatThreads) {
         double R[9], T[9], M[9], qC[4], a[3], b[3];
@@ -219,6 +250,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     }
     __syncthreads();
 
+    FEAT_CLK(2);
     // ---- inverse-depth initialisation + LM (warp 0), Updater.cc:143-269
     if (warp == 0) {
         const float2 m0 = meas[0];
@@ -316,6 +348,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     __syncthreads();
     if (s_flag[0]) return;
 
+    FEAT_CLK(3);
     const double phi = s_pf[0], psi = s_pf[1], rho = s_pf[2];
     double e[3], J[6];
     d_set_dir(phi, psi, e, J);
@@ -404,6 +437,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
     }
     __syncthreads();
 
+    FEAT_CLK(4);
     // ---- left-nullspace projection (Updater.cc:370-402) by Householder reflections on H_f
     if (tid == 0) {
         double s = 0;
@@ -440,6 +474,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         }
         __syncthreads();
     }
+    FEAT_CLK(5);
     const int dof = Mr - Nc;
     const double* Hn = Hx + Nc * ld;       // projected block, dof x wc (row stride ld)
     const double* rn = rr + Nc;
@@ -497,6 +532,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         }
         __syncthreads();
     }
+    FEAT_CLK(6);
     // symmetrise + noise
     for (int o = tid; o < dof * dof; o += kFeatThreads) {
         const int a = o / dof, b = o - a * dof;
@@ -512,20 +548,21 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         if (a > b) S[a * dof + b] = S[b * dof + a];
     }
     __syncthreads();
+    FEAT_CLK(7);
     // Cholesky S = L L^T (lower), all threads; the forward substitution y = L^-1 r rides along (column j of L is applied to
     // the right-hand side in the same step), gamma = y^T y
     for (int i = tid; i < dof; i += kFeatThreads) vv[i] = rn[i];
     double gamma = 0;                                  // (thread 0's copy is the one that counts)
     __syncthreads();
+    if (tid == 0) {
+        const double dj = S[0];
+        const double sd = (dj > 0) ? sqrt(dj) : nan("");
+        const double yj = vv[0] / sd;
+        s_hh[1] = sd; s_hh[2] = yj;
+        gamma += yj * yj;
+    }
+    __syncthreads();
     for (int j = 0; j < dof; ++j) {
-        if (tid == 0) {
-            const double dj = S[j * dof + j];
-            const double sd = (dj > 0) ? sqrt(dj) : nan("");
-            const double yj = vv[j] / sd;
-            s_hh[1] = sd; s_hh[2] = yj;
-            gamma += yj * yj;
-        }
-        __syncthreads();
         const double dj = s_hh[1], yj = s_hh[2];
         for (int i = j + tid; i < dof; i += kFeatThreads) {
             const double lij = (i == j) ? dj : S[i * dof + j] / dj;
@@ -537,6 +574,13 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         for (int o = tid; o < rem * rem; o += kFeatThreads) {
             const int a = j + 1 + o / rem, b = j + 1 + o % rem;
             if (b <= a) S[a * dof + b] -= S[a * dof + j] * S[b * dof + j];
+        }
+        if (tid == 0 && rem > 0) {                     // thread 0 has just finished the next pivot: prepare the next column here
+            const double dn = S[(j + 1) * dof + j + 1];
+            const double sd = (dn > 0) ? sqrt(dn) : nan("");
+            const double yn = vv[j + 1] / sd;
+            s_hh[1] = sd; s_hh[2] = yn;
+            gamma += yn * yn;
         }
         __syncthreads();
     }
@@ -552,6 +596,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         }
     }
     __syncthreads();
+    FEAT_CLK(8);
     if (!s_flag[2]) return;
     // ---- accepted: publish the projected block (full width n, zero outside [c0, c0+wc))
     double* Hout = P.Hblk + (size_t)f * P.blk_rows * n;
@@ -574,6 +619,12 @@ __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
         for (int w = 0; w < kFeatThreads / 32; ++w) t += s_fro[w];
         P.f_fro2[f] = t;
     }
+#ifdef RVIO_B200_PHASE_CLOCKS
+    FEAT_CLK(9);
+    if (tid == 0 && (P.offsets[f + 1] - P.offsets[f]) >= 11 && type == '2') {      // a full-length track: the slow kind
+        for (int k = 0; k < 10; ++k) g_feat_clk[k] = fclk[k];
+    }
+#endif
 }
 
 // ================================================================================================
@@ -1717,6 +1768,7 @@ struct rvio_updater {
     int* d_sing; int* d_tickets;
     int* d_rule; int32_t* d_rr; double *d_L, *d_gwin, *d_Rc, *d_yc, *d_S, *d_LS, *d_W;      // reference compression rule + R-form EKF step (compress.cu)
     int rank_rule;
+    bool split_small_solve;     // RVIO_B200_SPLIT_SOLVE=1: rank rule / sweep / EKF step as three launches instead of k_update_small, for A/B timing
     bool legacy_small_solve;    // RVIO_B200_LEGACY_SOLVE=1: the round-1 G-form solve (k_wgemm + k_gj_block + k_pout_finalize), for A/B timing
     int groups_cap;
     // pinned
@@ -1824,6 +1876,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     RVIO_CUDA_TRY(cudaMemcpyAsync(u->d_chi2, RVIO_CHI2_95_HOST, sizeof(double) * 500, cudaMemcpyHostToDevice, u->stream));
     u->rank_rule = 0;                                    // the reference's rule (d_rule is zero-initialised)
     { const char* e = getenv("RVIO_B200_LEGACY_SOLVE"); u->legacy_small_solve = e && e[0] == '1'; }
+    { const char* e = getenv("RVIO_B200_SPLIT_SOLVE"); u->split_small_solve = e && e[0] == '1'; }
     if ((rc = compress_configure(u->nmax)) != RVIO_OK) return rc;
     RVIO_CUDA_TRY(cudaStreamSynchronize(u->stream));
     *out = u;
@@ -1914,21 +1967,30 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         return RVIO_OK;
     }
     const bool small = N <= kSolveSmallMaxClones;
+    RankRuleParams rq;
+    GivensRefParams gq;
     {
-        // which rows the reference's compression keeps (Updater.cc:474-536): may rewrite [G | z] in place; for the
-        // large-window path it also hands over the kept rows R (G = R^T R) and y (R^T y = z)
-        RankRuleParams rq;
+        // which rows the reference's compression keeps (Updater.cc:474-536): may rewrite [G | z] in place; it also hands over
+        // the kept rows R (G = R^T R) and y (R^T y = z) to the EKF step
         rq.red = u->d_red; rq.n = n; rq.world = u->cur_world; rq.rule_dev = u->d_rule; rq.L = u->d_L; rq.rr = u->d_rr;
         rq.emit_R = 1; rq.Rc = u->d_Rc; rq.yc = u->d_yc;
-        GivensRefParams gq;
         gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.f_dof = u->d_fdof; gq.n_feat = u->cur_nfeat; gq.n_feat_dev = u->cur_nfeat_dev;
         gq.n = n; gq.blk_rows = u->lay.Mc; gq.red = u->d_red; gq.rr = u->d_rr; gq.win = u->d_gwin;
         gq.emit_R = rq.emit_R; gq.Rc = u->d_Rc; gq.yc = u->d_yc;
+    }
+    if (small && !u->legacy_small_solve && !u->split_small_solve) {
+        // rank rule, (rare) sweep and the whole EKF step in ONE single-CTA launch (compress.cu: k_update_small)
+        SolveSmallRParams q;
+        q.Rc = u->d_Rc; q.yc = u->d_yc; q.x = x_dev; q.P = P_dev; q.xdim = xdim; q.N = N; q.d = d; q.sig2 = u->consts.sig2;
+        q.gate = u->d_red + (size_t)n * n + n; q.x_out = x_out_dev; q.P_out = P_out_dev; q.bad = u->d_sing;
+        return enqueue_update_small(s, rq, gq, q);
+    }
+    {
         const int r2 = enqueue_rank_rule(s, rq, gq, n);
         if (r2 != RVIO_OK) return r2;
     }
     if (small && !u->legacy_small_solve) {
-        // the whole EKF step in one CTA, R-form (compress.cu: k_solve_small_R)
+        // (RVIO_B200_SPLIT_SOLVE=1: the three launches of the un-fused form, kept for A/B timing)
         SolveSmallRParams q;
         q.Rc = u->d_Rc; q.yc = u->d_yc; q.x = x_dev; q.P = P_dev; q.xdim = xdim; q.N = N; q.d = d; q.sig2 = u->consts.sig2;
         q.gate = u->d_red + (size_t)n * n + n; q.x_out = x_out_dev; q.P_out = P_out_dev; q.bad = u->d_sing;
@@ -2190,5 +2252,13 @@ extern "C" int rvio_b200_gram_ns(unsigned long long* out, int reset)
     int rc = (int)cudaMemcpyFromSymbol(out, rvio::g_gram_ns, sizeof(unsigned long long) * 16);
     if (reset) { unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = 0; z[0] = ~0ull; cudaMemcpyToSymbol(rvio::g_gram_ns, z, sizeof z); }
     return rc;
+}
+#endif
+
+#ifdef RVIO_B200_PHASE_CLOCKS
+extern "C" int rvio_b200_feat_clocks(long long* out)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, rvio::g_feat_clk, sizeof(long long) * 16);
 }
 #endif

@@ -424,7 +424,9 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     RVIO_ENQ(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
     if (use_det && rc != RVIO_NO_FEATURES && (rc == RVIO_FIRST_IMAGE || side_refill))     // main stream is ordered after the detector here
         RVIO_ENQ(cudaMemcpyAsync(v->h_detctrl, tracker_detector(v->trk)->ctrl, sizeof(DetCtrl), cudaMemcpyDeviceToHost, s));
-    return tracker_enqueue_scalars(v->trk);                  // tracker counters follow everything else on the main stream
+    const int rsc = tracker_enqueue_scalars(v->trk);         // tracker counters follow everything else on the main stream
+    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[6], s));          // end of the frame's device work (inside the frame graph when one is replayed)
+    return rsc;
 }
 
 static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int height, int stride, int channels,
@@ -465,7 +467,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
 
     const bool was_first = tracker_is_first(v->trk);
     // ---- a steady-state frame (window full, features being tracked) is replayed as a CUDA graph
-    const bool steady = v->use_graphs && !v->timeline && g_profile_on.load(std::memory_order_relaxed) == 0 &&
+    const bool steady = v->use_graphs && g_profile_on.load(std::memory_order_relaxed) == 0 &&
                         !tracker_is_first(v->trk) && tracker_n_track(v->trk) > 0 && v->n_clones == v->window &&
                         v->n_clones > v->min_clones && v->n_img_after_init > 1;
     FrameOutcome fo;
@@ -494,7 +496,8 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         if (n_cand > 0 && cand_dev_in)
             RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, cand_dev_in, sizeof(float) * 2 * n_cand, cudaMemcpyDeviceToDevice, s));
         const bool staged_in = img_dev != nullptr || host_pinned;
-        const uint64_t key = (uint64_t)use_det << 20 |
+        const uint64_t key = (uint64_t)use_det << 20 | (uint64_t)(v->timeline ? 1 : 0) << 40 |     // (the stage events are graph nodes of their own variant)
+                            
                              (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
                              (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)staged_in << 5 | (uint64_t)(channels & 7) << 6 |
                              (uint64_t)(cand_dev_in != nullptr) << 9 | (uint64_t)imu16 << 10;
@@ -536,7 +539,6 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     v->tl_ms[6] = (float)((h1.tv_sec - h0.tv_sec) * 1e3 + (h1.tv_nsec - h0.tv_nsec) * 1e-6);   // host: enqueue
     v->tl_ms[7] = (float)((h2.tv_sec - h1.tv_sec) * 1e3 + (h2.tv_nsec - h1.tv_nsec) * 1e-6);   // host: blocked in the sync
     if (v->timeline) {
-        cudaEventRecord(v->tl[6], s);
         cudaEventSynchronize(v->tl[6]);
         for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, v->tl[k], v->tl[k + 1]) == cudaSuccess) v->tl_ms[k] = ms; else v->tl_ms[k] = -1.f; }
     }

@@ -40,6 +40,18 @@ for i in range(n):
             if b == 0 and c[44] > c[40] > 0:
                 print(f"   first settle iteration: masks {c[41] - c[40]}, rounds {c[42] - c[41]}, emit {c[43] - c[42]}, filter + compact {c[44] - c[43]} -> {c[45]} alive")
             print(f"   block {b}: {c[34 + b]} keys: filter+histogram {s[0] - prev}, gather {s[1] - s[0]}, sort {s[2] - s[1]}, settle {s[3] - s[2]}")
+if hasattr(L, "rvio_b200_aug_clocks"):
+    buf = (ctypes.c_longlong * 16)()
+    L.rvio_b200_aug_clocks(buf)
+    c = list(buf)
+    names = ["augmentation copy", "state shift", "V + P00 (thread 0's pose algebra)", "24x24 products", "cross terms", "final"]
+    print("k_augment_compose (cycles): " + ", ".join(f"{nm} {c[k + 1] - c[k]}" for k, nm in enumerate(names)) + f"; total {c[6] - c[0]}")
+if hasattr(L, "rvio_b200_feat_clocks"):
+    buf = (ctypes.c_longlong * 16)()
+    L.rvio_b200_feat_clocks(buf)
+    c = list(buf)
+    names = ["setup + pose chain", "camera poses", "LM", "Jacobians", "nullspace", "gate product", "symmetrise", "Cholesky + gamma", "publish"]
+    print("k_feature, a full-length type-2 track (cycles): " + ", ".join(f"{nm} {c[k + 1] - c[k]}" for k, nm in enumerate(names)) + f"; total {c[9] - c[0]}")
 if hasattr(L, "rvio_b200_trk_clocks"):
     buf = (ctypes.c_longlong * 32)()
     L.rvio_b200_trk_clocks(buf, 32)
