@@ -66,7 +66,8 @@ struct rvio_vio {
     bool use_graphs;
     std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
     uint64_t graph_launches;
-    bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage events on the main stream
+    bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage stamps on the main stream
+    unsigned long long* d_stamps; unsigned long long h_stamps[8];
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
@@ -234,6 +235,8 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     v->timeline = false;
     v->use_graphs = true; v->graph_launches = 0;
     for (int k = 0; k < 8; ++k) { RVIO_CUDA_TRY(cudaEventCreate(&v->tl[k])); v->tl_ms[k] = 0.f; }
+    RVIO_CUDA_TRY(cudaMalloc((void**)&v->d_stamps, sizeof(unsigned long long) * 8));
+    RVIO_CUDA_TRY(cudaMemset(v->d_stamps, 0, sizeof(unsigned long long) * 8));
     v->window = cfg->tracker.max_track_len - 1;             // System.cc:71-72
     v->min_clones = cfg->tracker.min_track_len - 1;         // System.cc:74-75
     v->F = cfg->tracker.n_features; v->Fu = (v->F + 1) / 2;
@@ -289,6 +292,10 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     delete v;
 }
 
+// (stage timeline) one-thread kernel that writes the GPU's global timer: unlike event-record nodes, it can be read back
+// when the frame is replayed as a graph
+__global__ void k_stamp(unsigned long long* out) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *out = t; }
+
 struct FrameOutcome { bool committable, ran_update; };
 
 // Everything one frame puts on the two streams, from the IMU upload to the device->host copies of the results; no
@@ -323,7 +330,7 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     }
 
     // ---- visual tracking (System.cc:258) on the main stream
-    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[0], s));
+    if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 0);
     int rc;
     const int world = v->shard.world, srank = v->shard.rank;
     if (world > 1) {
@@ -342,7 +349,7 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     else if (img_dev) rc = tracker_enqueue_frame_dev(v->trk, img_dev, pitch, imu, n_imu);
     else rc = tracker_enqueue_frame_host(v->trk, img_host, width, height, stride, channels, imu, n_imu);
     if (rc < 0) return rc;
-    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[1], s));          // tracker kernels enqueued (upload .. bookkeeping)
+    if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 1);          // tracker kernels enqueued (upload .. bookkeeping)
     const int* n_cand_dev = hdr + 1;
     if (use_det && rc != RVIO_NO_FEATURES) {
         // FeatureDetector::DetectWithSubPix on its own stream: it only needs the equalised level 0, so it runs beside
@@ -394,14 +401,14 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
             r2 = shard_allreduce_terms(&v->shard, s, red, cnt);
             if (r2 != RVIO_OK) return r2;
         }
-        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[2], s));      // per-feature + normal terms done
+        if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 2);      // per-feature + normal terms done
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
-        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[3], s));      // (waited for propagation)
+        if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 3);      // (waited for propagation)
         r2 = updater_enqueue_solve_on(v->upd, s, v->d_x[v->xi], v->d_P[v->pi], v->d_x[1 - v->xi], v->d_P[1 - v->pi]);
         if (r2 != RVIO_OK) return r2;
         v->xi = 1 - v->xi; v->pi = 1 - v->pi;
         out->ran_update = true;
-        if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[4], s));      // solve done
+        if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 4);      // solve done
         RVIO_ENQ(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
     } else {
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
@@ -416,7 +423,7 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
         v->pi = 1 - v->pi;
         if (ap.do_augment && N < v->window) v->n_clones = N + 1;
     }
-    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[5], s));          // augmentation + composition done
+    if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 5);          // augmentation + composition done
     if (side_refill) {
         RVIO_ENQ(cudaEventRecord(v->ev_side_done, side));
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_side_done, 0));
@@ -425,7 +432,7 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     if (use_det && rc != RVIO_NO_FEATURES && (rc == RVIO_FIRST_IMAGE || side_refill))     // main stream is ordered after the detector here
         RVIO_ENQ(cudaMemcpyAsync(v->h_detctrl, tracker_detector(v->trk)->ctrl, sizeof(DetCtrl), cudaMemcpyDeviceToHost, s));
     const int rsc = tracker_enqueue_scalars(v->trk);         // tracker counters follow everything else on the main stream
-    if (v->timeline) RVIO_ENQ(cudaEventRecord(v->tl[6], s));          // end of the frame's device work (inside the frame graph when one is replayed)
+    if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 6);          // end of the frame's device work (inside the frame graph when one is replayed)
     return rsc;
 }
 
@@ -539,8 +546,9 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     v->tl_ms[6] = (float)((h1.tv_sec - h0.tv_sec) * 1e3 + (h1.tv_nsec - h0.tv_nsec) * 1e-6);   // host: enqueue
     v->tl_ms[7] = (float)((h2.tv_sec - h1.tv_sec) * 1e3 + (h2.tv_nsec - h1.tv_nsec) * 1e-6);   // host: blocked in the sync
     if (v->timeline) {
-        cudaEventSynchronize(v->tl[6]);
-        for (int k = 0; k < 6; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, v->tl[k], v->tl[k + 1]) == cudaSuccess) v->tl_ms[k] = ms; else v->tl_ms[k] = -1.f; }
+        if (cudaMemcpy(v->h_stamps, v->d_stamps, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int k = 0; k < 6; ++k) v->tl_ms[k] = (float)((double)(long long)(v->h_stamps[k + 1] - v->h_stamps[k]) * 1e-6);
+        else cudaGetLastError();
     }
     if (use_det && was_first && tracker_host_scalars(v->trk)->n_new == 0) {     // Tracker.cc:209-213: nothing detected, still "first image"
         tracker_set_first(v->trk, true);
