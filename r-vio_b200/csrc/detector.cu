@@ -113,28 +113,31 @@ __global__ void __launch_bounds__(1024) k_det_nms(DetParams P)
 // (measured on B200, 18.8 k candidates, 200 corners: the previous shared-memory bitonic sort took 52 us and the warp-serial
 //  settling 85 us of the kernel's 148 us.)
 
-// true when (x, y) lies closer than sqrt(md2) to a corner kept in one of the 3 x 3 cells around (xc, yc): the nine cell
-// counts are loaded first (independent loads), then only the occupied slots are visited
-__device__ __forceinline__ bool det_near_kept(const unsigned char* cnt, const unsigned* slots, int gw, int gh, int xc, int yc,
-                                              int x, int y, double md2)
+// Shadow bitmap: bit (x, y) is set when the pixel lies closer than the minimum distance to a corner kept so far -- the test a
+// candidate has to pass is then one bit.  A kept corner paints its disc { dx^2 + dy^2 < d^2 } (one warp per corner, one row
+// per lane, word-wise atomicOr).
+__device__ __forceinline__ bool det_shadowed(const unsigned* sb, int wpr, int x, int y)
 {
-    int cidx[9], m[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int yy = yc + k / 3 - 1, xx = xc + k % 3 - 1;
-        const bool in = yy >= 0 && yy < gh && xx >= 0 && xx < gw;
-        cidx[k] = in ? yy * gw + xx : 0;
-        m[k] = in ? (int)cnt[cidx[k]] : 0;
-    }
-    bool near = false;
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-        for (int q = 0; q < m[k]; ++q) {
-            const unsigned pq = slots[cidx[k] * kDetCellSlots + q];
-            const int dx = x - (int)(pq & 0xffffu), dy = y - (int)(pq >> 16);
-            near = near || ((double)(dx * dx + dy * dy) < md2);
+    return (sb[y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+}
+__device__ __forceinline__ void det_paint(unsigned* sb, int wpr, int W, int H, int kx, int ky, double md2, int R, int lane)
+{
+    for (int r = lane; r <= 2 * R; r += 32) {
+        const int dy = r - R, y = ky + dy;
+        if (y < 0 || y >= H) continue;
+        const double rem = md2 - (double)(dy * dy);
+        if (!(rem > 0.0)) continue;
+        int dxm = (int)sqrt(rem);
+        while ((double)((dxm + 1) * (dxm + 1) + dy * dy) < md2) ++dxm;
+        while (dxm >= 0 && !((double)(dxm * dxm + dy * dy) < md2)) --dxm;
+        if (dxm < 0) continue;
+        const int x0 = max(kx - dxm, 0), x1 = min(kx + dxm, W - 1);
+        for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+            const int lo = max(x0 - 32 * w, 0), hi = min(x1 - 32 * w, 31);
+            const unsigned m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(&sb[y * wpr + w], m);
         }
-    return near;
+    }
 }
 
 #ifdef RVIO_B200_PHASE_CLOCKS
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
     __shared__ int s_lo, s_take, s_count, s_nout, s_stop;
     __shared__ int s_warp[32];
     __shared__ unsigned s_M[32 * kDetWarpBatch][kDetWarpBatch + 1], s_A[kDetWarpBatch], s_U[kDetWarpBatch];      // (+1: rows of consecutive lanes in different banks)
+    __shared__ unsigned s_new[32 * kDetWarpBatch];         // corners kept in the current batch (y << 16 | x)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(dsm);
     const int tid = threadIdx.x, lane = tid & 31;
     int nc = P.ctrl->n_cand;
@@ -168,11 +172,11 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
     const unsigned base = thr_bits >> shift;
     const int nbins = (int)((max_bits >> shift) - base) + 1;
     for (int i = tid; i < kDetBins; i += 1024) s_hist[i] = 0;
-    const int cell = P.cell, gw = P.gw, gh = P.gh;
-    unsigned char* cnt = dsm + (size_t)kDetBlock * 16;
-    unsigned* slots = reinterpret_cast<unsigned*>(cnt + ((gw * gh + 15) & ~15));
+    const int IW = P.img.w, IH = P.img.h, wpr = P.wpr;
+    unsigned* sb = P.shadow_in_smem ? reinterpret_cast<unsigned*>(dsm + (size_t)kDetBlock * 16) : P.shadow;
+    const int paintR = (int)ceil(P.min_dist);
     unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(dsm + (size_t)kDetBlock * 8);     // second buffer of the compaction
-    for (int i = tid; i < gw * gh; i += 1024) cnt[i] = 0;
+    for (int i = tid; i < wpr * IH; i += 1024) sb[i] = 0u;
     if (tid == 0) { s_nout = 0; s_stop = 0; }
     __syncthreads();
     const double md2 = P.min_dist * P.min_dist;
@@ -190,8 +194,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
             if (!first_round) {
                 const unsigned lo32 = (unsigned)kk;
                 const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-                const int xc = x / cell, yc = y / cell;
-                const bool alive = !det_near_kept(cnt, slots, gw, gh, xc, yc, x, y, md2);
+                const bool alive = !det_shadowed(sb, wpr, x, y);
                 if (!alive) { P.keys[i] = 0ull; continue; }
             }
             atomicAdd(&s_hist[(int)(((unsigned)(kk >> 32) >> shift) - base)], 1);
@@ -199,28 +202,55 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
         first_round = false;
         __syncthreads();
         DET_CLK(1 + 4 * dbg_blocks);
-        if (tid == 0) {                                   // next block of bins from the top, at most kDetBlock candidates
-            int hi = nbins;
-            while (hi > 0 && s_hist[hi - 1] == 0) --hi;
-            int lo = hi, acc = 0;
-            while (lo > 0 && acc + s_hist[lo - 1] <= kDetBlock) { acc += s_hist[lo - 1]; --lo; }
-            if (hi > 0 && lo == hi) { P.ctrl->overflow = 1; s_stop = 1; }    // one bin alone exceeds the block
-            if (hi == 0) s_stop = 1;                      // nothing left
-            s_lo = lo; s_take = acc; s_count = 0;
+        {
+            // next block of bins from the top, at most kDetBlock candidates: suffix sums of the histogram (thread t = bin t; warp
+            // shuffles + one pass over the 32 warp totals), lo = first bin whose suffix still fits, instead of a serial walk
+            const int h = (tid < nbins) ? s_hist[tid] : 0;
+            int suf = h;                                      // inclusive suffix sum inside the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t2; }
+            if (lane == 0) s_warp[tid >> 5] = suf;
+            __syncthreads();
+            int above = 0;                                    // everything in the warps above mine
+            for (int w = (tid >> 5) + 1; w < 32; ++w) above += s_warp[w];
+            suf += above;                                     // = number of candidates in bins >= tid
+            const unsigned fits = __ballot_sync(0xffffffffu, tid < nbins && suf <= kDetBlock);
+            const unsigned nz = __ballot_sync(0xffffffffu, h > 0);
+            __syncthreads();
+            unsigned* scratch = &s_M[0][0];
+            if (lane == 0) { s_warp[tid >> 5] = __popc(fits); scratch[tid >> 5] = nz; }
+            __syncthreads();
+            if (tid == 0) {
+                int nfit = 0, hi = 0;
+                for (int w = 0; w < 32; ++w) { nfit += s_warp[w]; if (scratch[w]) hi = 32 * w + (32 - __clz(scratch[w])); }
+                const int lo = nbins - nfit;                  // suffix sums are non-increasing in the bin index: the fitting bins are the top nfit ones
+                s_lo = lo; s_count = 0;
+                s_take = -1;                                  // filled in below by the thread that owns bin lo
+                if (hi > 0 && lo >= hi) { P.ctrl->overflow = 1; s_stop = 1; }    // one bin alone exceeds the block
+                if (hi == 0) s_stop = 1;                      // nothing left
+            }
+            __syncthreads();
+            if (tid == s_lo && tid < nbins) s_take = suf;
+            if (tid == 0 && s_lo >= nbins) s_take = 0;
         }
         __syncthreads();
         if (s_stop) break;
         const int lo = s_lo, take = s_take;
-        for (int i0 = 0; i0 < nc; i0 += 1024) {                 // (one shared-memory atomic per warp and pass, not per key)
-            const int i = i0 + tid;
-            unsigned long long kk = (i < nc) ? P.keys[i] : 0ull;
-            bool hit = false;
-            if (kk != 0ull) hit = (int)(((unsigned)(kk >> 32) >> shift) - base) >= lo;
-            const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            int wbase = 0;
-            if (lane == 0 && hm) wbase = atomicAdd(&s_count, __popc(hm));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (hit) { keys[wbase + __popc(hm & ((1u << lane) - 1u))] = kk; P.keys[i] = 0ull; }      // consumed by this round
+        for (int i0 = 0; i0 < nc; i0 += 4 * 1024) {             // four keys per thread in flight; one shared-memory atomic per warp and key slot
+            unsigned long long kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * 1024 + tid; kk[q] = (i < nc) ? P.keys[i] : 0ull; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * 1024 + tid;
+                bool hit = false;
+                if (kk[q] != 0ull) hit = (int)(((unsigned)(kk[q] >> 32) >> shift) - base) >= lo;
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                int wbase = 0;
+                if (lane == 0 && hm) wbase = atomicAdd(&s_count, __popc(hm));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (hit) { keys[wbase + __popc(hm & ((1u << lane) - 1u))] = kk[q]; P.keys[i] = 0ull; }      // consumed by this round
+            }
         }
         __syncthreads();
         for (int i = take + tid; i < kDetBlock; i += 1024) keys[i] = 0ull;
@@ -321,49 +351,50 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                 __syncthreads();
                 if (dbg_blocks == 0 && dbg_iters == 1) DET_CLK(41);
                 if (tid < 32) {
-                    // (2) a candidate is kept iff no stronger kept candidate lies within the distance: decided in rounds -- rejected as
-                    //     soon as a stronger neighbour is kept, kept as soon as every stronger neighbour is decided (and none kept).
-                    //     Words are walked in rank order with fresh masks, so most of a batch settles in the first round.
-                    bool any_u = true;
-                    while (any_u) {
-                        any_u = false;
-                        for (int k = 0; k < kDetWarpBatch && 32 * k < B; ++k) {
-                            const int i = 32 * k + lane;
-                            const unsigned uk = s_U[k];
-                            bool acc = false, rej = false;
-                            if ((uk >> lane) & 1u) {
-                                bool a = false, u = false;
-                                for (int w = 0; w <= k; ++w) { const unsigned m = s_M[i][w]; a = a || (m & s_A[w]); u = u || (m & s_U[w]); }
-                                if (a) rej = true; else if (!u) acc = true;
-                            }
+                    // (2) a candidate is kept iff no stronger kept candidate lies within the distance.  The batch is in rank order,
+                    //     so word k (32 candidates) depends only on the words before it, which are final, and on itself: first the
+                    //     candidates shadowed by a kept member of an earlier word drop out, then the word settles in rounds held in
+                    //     registers (rejected as soon as a stronger neighbour is kept, kept as soon as every stronger neighbour
+                    //     inside the word is decided and none is kept).
+                    for (int k = 0; k < kDetWarpBatch && 32 * k < B; ++k) {
+                        const int i = 32 * k + lane;
+                        bool dead = !((s_U[k] >> lane) & 1u);                 // (beyond the batch)
+                        for (int w = 0; w < k; ++w) dead = dead || (s_M[i][w] & s_A[w]);
+                        const unsigned mk = s_M[i][k];
+                        unsigned U = __ballot_sync(0xffffffffu, !dead), A = 0u;
+                        while (U) {
+                            const bool und = (U >> lane) & 1u;
+                            const bool rej = und && (mk & A);
+                            const bool acc = und && !rej && !(mk & U);
                             const unsigned am = __ballot_sync(0xffffffffu, acc), rm = __ballot_sync(0xffffffffu, rej);
-                            const unsigned left = uk & ~(am | rm);
-                            if (lane == 0) { s_A[k] |= am; s_U[k] = left; }
-                            __syncwarp();
-                            if (left) any_u = true;
+                            A |= am; U &= ~(am | rm);
                         }
+                        if (lane == 0) { s_A[k] = A; s_U[k] = 0u; }
+                        __syncwarp();
                     }
-                    if (dbg_blocks == 0 && dbg_iters == 1) DET_CLK(42);
-                    // (3) the kept ones in rank order: output + minimum-distance grid (byte counters, bumped through their 32-bit word)
+                    // (3) the kept ones in rank order: output, and their coordinates for the painters
                     int no = n_out;
                     for (int k = 0; k < kDetWarpBatch && 32 * k < B; ++k) {
                         const unsigned am = s_A[k];
                         const int pos = no + __popc(am & ((1u << lane) - 1u));
                         if (((am >> lane) & 1u) && pos < P.max_corners) {
                             const unsigned lo32 = (unsigned)cur[32 * k + lane];
-                            const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-                            P.out[pos] = make_float2((float)x, (float)y);
-                            const int c = (y / cell) * gw + (x / cell);
-                            const unsigned sh = 8u * (unsigned)(c & 3);
-                            const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(cnt) + (c >> 2), 1u << sh);
-                            const int m = (int)((old >> sh) & 0xffu);
-                            if (m < kDetCellSlots) slots[c * kDetCellSlots + m] = lo32;
-                            else P.ctrl->overflow = 1;
+                            P.out[pos] = make_float2((float)(lo32 & 0xffffu), (float)(lo32 >> 16));
+                            s_new[pos - n_out] = lo32;
                         }
                         no += __popc(am);
                     }
                     if (no > P.max_corners) no = P.max_corners;
                     if (lane == 0) s_nout = no;
+                }
+                __syncthreads();
+                {
+                    // (3b) every corner kept in this batch paints its disc into the shadow bitmap: one warp per corner
+                    const int n_new = s_nout - n_out;
+                    for (int c = (tid >> 5); c < n_new; c += 32) {
+                        const unsigned lo32 = s_new[c];
+                        det_paint(sb, wpr, IW, IH, (int)(lo32 & 0xffffu), (int)(lo32 >> 16), md2, paintR, lane);
+                    }
                 }
                 __syncthreads();
                 if (dbg_blocks == 0 && dbg_iters == 1) DET_CLK(43);
@@ -384,7 +415,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
                         kk = cur[k];
                         const unsigned lo32 = (unsigned)kk;
                         const int y = (int)(lo32 >> 16), x = (int)(lo32 & 0xffffu);
-                        if (det_near_kept(cnt, slots, gw, gh, x / cell, y / cell, x, y, md2)) kk = 0ull;
+                        if (det_shadowed(sb, wpr, x, y)) kk = 0ull;
                     }
                     mine[u] = kk;
                     local += kk != 0ull;
@@ -422,7 +453,7 @@ __global__ void __launch_bounds__(1024) k_det_select(DetParams P)
 __global__ void __launch_bounds__(128) k_det_subpix(DetParams P)
 {
     __shared__ float s_patch[4][33 * 33];
-    __shared__ unsigned char s_px[4][34 * 36];                       // (pw + 1)^2 source pixels of the current patch
+    __shared__ unsigned char s_px[4][34 * 36];                       // large windows: (pw + 1)^2 source pixels of the current patch; small: a 32 x 32 tile
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int k = blockIdx.x * 4 + wib;
     if (k >= P.ctrl->n_out) return;
@@ -435,17 +466,17 @@ __global__ void __launch_bounds__(128) k_det_subpix(DetParams P)
     int iter = 0;
     double err = 0;
     const double eps = P.subpix_eps * P.subpix_eps;
+    int tx0 = 0, ty0 = 0;
+    bool have_tile = false;
     // per-lane element tables, fixed for the whole refinement (window sizes up to 15 x 15 take the register path)
-    constexpr int kSrcPer = 11, kPatPer = 10, kWinPer = 8;            // ceil(18*18/32), ceil(17*17/32), ceil(15*15/32)
+    constexpr int kPatPer = 10, kWinPer = 8;                          // ceil(17*17/32), ceil(15*15/32)
     const bool small = hw <= 7;
-    short src_i[kSrcPer], src_j[kSrcPer], pat_o[kPatPer], win_o[kWinPer];
+    short pat_o[kPatPer], win_o[kWinPer];
     signed char win_x[kWinPer], win_y[kWinPer];
     float win_m[kWinPer];
     if (small) {
 #pragma unroll
-        for (int u = 0; u < kSrcPer; ++u) { const int o = u * 32 + lane; src_i[u] = (short)(o / sw); src_j[u] = (short)(o - (o / sw) * sw); }
-#pragma unroll
-        for (int u = 0; u < kPatPer; ++u) { const int o = u * 32 + lane; pat_o[u] = (short)((o / pw) * sw + (o - (o / pw) * pw)); }
+        for (int u = 0; u < kPatPer; ++u) { const int o = u * 32 + lane; pat_o[u] = (short)((o / pw) * 32 + (o - (o / pw) * pw)); }      // (row stride of the staged tile)
 #pragma unroll
         for (int u = 0; u < kWinPer; ++u) {
             const int q = u * 32 + lane, i = q / ww, j = q - i * ww;
@@ -462,26 +493,33 @@ __global__ void __launch_bounds__(128) k_det_subpix(DetParams P)
         const float a21 = __fmul_rn(__fsub_rn(1.f, a), b), a22 = __fmul_rn(a, b);
         double sa = 0, sb = 0, sc = 0, s1 = 0, s2 = 0;
         if (small) {
-            // one round trip to global memory: the (pw+1)^2 source pixels (coordinates clamped to the image); the
-            // bilinear taps then come from shared memory
-            unsigned char v[kSrcPer];
+            // the (pw+1)^2 source pixels come from a 32 x 32 tile of the image (coordinates clamped to the image) staged in
+            // shared memory: the refinement moves the window by fractions of a pixel, so the tile is fetched once and only
+            // re-fetched if the window leaves it (one global round trip per corner instead of one per iteration)
+            if (!have_tile || ix < tx0 || iy < ty0 || ix + sw > tx0 + 32 || iy + sw > ty0 + 32) {
+                tx0 = ix - (32 - sw) / 2; ty0 = iy - (32 - sw) / 2;
+                unsigned char v[32];
+                const int yy = min(max(ty0 + lane, 0), H - 1);
+                const unsigned char* row = P.img.base + (ptrdiff_t)yy * P.img.pitch;
 #pragma unroll
-            for (int u = 0; u < kSrcPer; ++u) {
-                const int yy = min(max(iy + src_i[u], 0), H - 1), xx = min(max(ix + src_j[u], 0), W - 1);
-                v[u] = (u * 32 + lane < sw * sw) ? P.img.base[(ptrdiff_t)yy * P.img.pitch + xx] : (unsigned char)0;
+                for (int u = 0; u < 32; ++u) v[u] = row[min(max(tx0 + u, 0), W - 1)];
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 32; u += 4)
+                    *reinterpret_cast<unsigned*>(px + lane * 32 + u) = (unsigned)v[u] | ((unsigned)v[u + 1] << 8) | ((unsigned)v[u + 2] << 16) | ((unsigned)v[u + 3] << 24);
+                have_tile = true;
+                __syncwarp();
             }
-#pragma unroll
-            for (int u = 0; u < kSrcPer; ++u) if (u * 32 + lane < sw * sw) px[u * 32 + lane] = v[u];
-            __syncwarp();
+            const unsigned char* pxo = px + (iy - ty0) * 32 + (ix - tx0);
 #pragma unroll
             for (int u = 0; u < kPatPer; ++u) {
                 const int o = u * 32 + lane;
                 if (o < pw * pw) {
-                    const unsigned char* q = px + pat_o[u];
+                    const unsigned char* q = pxo + pat_o[u];
                     float t = __fmul_rn((float)q[0], a11);
                     t = __fadd_rn(t, __fmul_rn((float)q[1], a12));
-                    t = __fadd_rn(t, __fmul_rn((float)q[sw], a21));
-                    t = __fadd_rn(t, __fmul_rn((float)q[sw + 1], a22));
+                    t = __fadd_rn(t, __fmul_rn((float)q[32], a21));
+                    t = __fadd_rn(t, __fmul_rn((float)q[33], a22));
                     patch[o] = t;
                 }
             }
@@ -560,6 +598,7 @@ int detector_create(Detector* D, int W, int H, int max_corners)
     RVIO_CUDA_TRY(cudaMalloc((void**)&D->ctrl, sizeof(DetCtrl)));
     RVIO_CUDA_TRY(cudaMalloc((void**)&D->out, sizeof(float2) * ((size_t)max_corners + 1)));
     RVIO_CUDA_TRY(cudaMalloc((void**)&D->mask, sizeof(float) * 31 * 31));
+    RVIO_CUDA_TRY(cudaMalloc((void**)&D->shadow, sizeof(unsigned) * (size_t)((W + 31) / 32) * H));
     RVIO_CUDA_TRY(cudaMemset(D->ctrl, 0, sizeof(DetCtrl)));
     RVIO_CUDA_TRY(cudaMallocHost((void**)&D->h_mask, sizeof(float) * 31 * 31));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_det_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -569,7 +608,7 @@ int detector_create(Detector* D, int W, int H, int max_corners)
 
 void detector_destroy(Detector* D)
 {
-    cudaFree(D->eig); cudaFree(D->keys); cudaFree(D->ctrl); cudaFree(D->out); cudaFree(D->mask);
+    cudaFree(D->eig); cudaFree(D->keys); cudaFree(D->ctrl); cudaFree(D->out); cudaFree(D->mask); cudaFree(D->shadow);
     cudaFreeHost(D->h_mask);
 }
 
@@ -584,9 +623,12 @@ int detector_enqueue(Detector* D, cudaStream_t st, const PyrLevel& level0, int s
     P.hw = (int)floor(.5 * min_dist_f);                               // FeatureDetector.cc:68
     if (P.hw < 1 || P.hw > 15 || P.min_dist < 1) { set_error("detector_enqueue", "Tracker.nMinDist outside the supported range [2, 31]"); return RVIO_ERR_ARG; }
     P.subpix_iters = 30; P.subpix_eps = 1e-2;                        // FeatureDetector.cc:70
-    P.cell = (int)lrint(P.min_dist);
-    P.gw = (D->W + P.cell - 1) / P.cell; P.gh = (D->H + P.cell - 1) / P.cell;
-    const size_t smem = (size_t)kDetBlock * 16 + (((size_t)P.gw * P.gh + 15) & ~(size_t)15) + (size_t)P.gw * P.gh * kDetCellSlots * 4 + 64;
+    P.cell = P.gw = P.gh = 0;
+    P.wpr = (D->W + 31) / 32;
+    const size_t bitmap = sizeof(unsigned) * (size_t)P.wpr * D->H;
+    P.shadow_in_smem = ((size_t)kDetBlock * 16 + bitmap + 64 <= 200 * 1024) ? 1 : 0;      // 752x480: 45 KB, 1280x720: 115 KB; larger: the global copy
+    P.shadow = D->shadow;
+    const size_t smem = (size_t)kDetBlock * 16 + (P.shadow_in_smem ? bitmap : 0) + 64;
     if (smem > 200 * 1024) { set_error("detector_enqueue", "minimum-distance grid does not fit in shared memory (Tracker.nMinDist too small for this image size)"); return RVIO_ERR_CAPACITY; }
     if (D->mask_hw != P.hw) {                                        // cornerSubPix window weights (host libm, like OpenCV)
         const int ww = 2 * P.hw + 1;

@@ -18,7 +18,9 @@ struct DetParams {
     unsigned long long* keys; int key_cap;
     float2* out; int max_corners;
     double quality, min_dist;
-    int cell, gw, gh;
+    int cell, gw, gh;                   // (unused since the shadow bitmap replaced the minimum-distance grid)
+    unsigned* shadow;                   // W x H bit map of the pixels closer than min_dist to a kept corner (global copy: images too large for shared memory)
+    int shadow_in_smem, wpr;            // words per bitmap row
     int hw, subpix_iters; double subpix_eps;
     const float* mask;
 };
@@ -26,6 +28,7 @@ struct DetParams {
 struct Detector {
     int W, H, max_corners;
     float* eig; unsigned long long* keys; DetCtrl* ctrl; float2* out; float* mask; float* h_mask; int mask_hw;
+    unsigned* shadow;
 };
 
 int detector_create(Detector* D, int W, int H, int max_corners);

@@ -68,6 +68,7 @@ struct rvio_vio {
     uint64_t graph_launches;
     bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage stamps on the main stream
     unsigned long long* d_stamps; unsigned long long h_stamps[8];
+    std::unordered_map<const void*, bool> pin_cache;   // is this host frame buffer pinned? (cudaPointerGetAttributes, asked once per address)
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
@@ -298,6 +299,20 @@ __global__ void k_stamp(unsigned long long* out) { unsigned long long t; asm vol
 
 struct FrameOutcome { bool committable, ran_update; };
 
+// The frame's results (pose, update counters, detector control block, tracker scalars) go to the host in ONE step: a small
+// kernel stores them into the pinned host buffers directly (pinned memory is device-addressable under unified addressing),
+// instead of four dependent D2H copy nodes at the end of the frame's critical path.
+__global__ void k_results(const double* pose, double* h_pose, const double* cnt, double* h_cnt, const int* det, int* h_det,
+                          const int* sc, int* h_sc, int sc_words)
+{
+    const int t = threadIdx.x;
+    if (t < 7) h_pose[t] = pose[t];
+    if (cnt && t >= 8 && t < 16) h_cnt[t - 8] = cnt[t - 8];
+    if (det && t >= 16 && t < 20) h_det[t - 16] = det[t - 16];
+    for (int i = t; i < sc_words; i += blockDim.x) h_sc[i] = sc[i];
+    __threadfence_system();
+}
+
 // Everything one frame puts on the two streams, from the IMU upload to the device->host copies of the results; no
 // synchronisation and no host-visible result is touched here, so the sequence can be captured into a CUDA graph and
 // replayed (with rvio::t_replay set the stream operations are skipped and only the host-side bookkeeping advances).
@@ -409,7 +424,6 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
         v->xi = 1 - v->xi; v->pi = 1 - v->pi;
         out->ran_update = true;
         if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 4);      // solve done
-        RVIO_ENQ(cudaMemcpyAsync(v->h_cnt, updater_counters_dev(v->upd), sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
     } else {
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_prop_done, 0));
     }
@@ -428,10 +442,14 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
         RVIO_ENQ(cudaEventRecord(v->ev_side_done, side));
         RVIO_ENQ(cudaStreamWaitEvent(s, v->ev_side_done, 0));
     }
-    RVIO_ENQ(cudaMemcpyAsync(v->h_pose, v->d_pose, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
-    if (use_det && rc != RVIO_NO_FEATURES && (rc == RVIO_FIRST_IMAGE || side_refill))     // main stream is ordered after the detector here
-        RVIO_ENQ(cudaMemcpyAsync(v->h_detctrl, tracker_detector(v->trk)->ctrl, sizeof(DetCtrl), cudaMemcpyDeviceToHost, s));
-    const int rsc = tracker_enqueue_scalars(v->trk);         // tracker counters follow everything else on the main stream
+    {
+        const bool det_out = use_det && rc != RVIO_NO_FEATURES && (rc == RVIO_FIRST_IMAGE || side_refill);      // main stream is ordered after the detector here
+        RVIO_LAUNCH(k_results, 1, 64, 0, s, v->d_pose, v->h_pose, out->ran_update ? updater_counters_dev(v->upd) : nullptr, v->h_cnt,
+                    det_out ? reinterpret_cast<const int*>(tracker_detector(v->trk)->ctrl) : nullptr, reinterpret_cast<int*>(v->h_detctrl),
+                    reinterpret_cast<const int*>(tracker_buffers(v->trk)->sc), reinterpret_cast<int*>(const_cast<TrackerScalars*>(tracker_host_scalars(v->trk))),
+                    (int)(sizeof(TrackerScalars) / sizeof(int)));
+    }
+    const int rsc = RVIO_OK;
     if (v->timeline) RVIO_LAUNCH(k_stamp, 1, 1, 0, s, v->d_stamps + 6);          // end of the frame's device work (inside the frame graph when one is replayed)
     return rsc;
 }
@@ -491,13 +509,24 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         } else if (channels == 1) {
             // a single-channel frame in PINNED host memory (cudaHostAlloc / cudaHostRegister by the caller) is DMA'd straight
             // into the pipeline's gray buffer: no staging copy on the host; the frame graph then runs its "staged" variant
-            cudaPointerAttributes pa;
-            if (cudaPointerGetAttributes(&pa, img_host) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            // (the attribute query is a driver call: its answer is remembered per buffer address)
+            bool pinned;
+            auto pc = v->pin_cache.find(img_host);
+            if (pc != v->pin_cache.end()) pinned = pc->second;
+            else {
+                cudaPointerAttributes pa;
+                pinned = cudaPointerGetAttributes(&pa, img_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+                if (!pinned) cudaGetLastError();
+                if (v->pin_cache.size() < 4096) v->pin_cache.emplace(img_host, pinned);
+            }
+            if (pinned) {
                 size_t gp; uint8_t* g = tracker_gray(v->trk, &gp);
-                RVIO_CUDA_TRY(cudaMemcpy2DAsync(g, gp, img_host, stride, v->cfg.tracker.width, v->cfg.tracker.height, cudaMemcpyHostToDevice, s));
+                const size_t wbytes = (size_t)v->cfg.tracker.width;
+                if ((size_t)stride == wbytes && gp == wbytes)
+                    RVIO_CUDA_TRY(cudaMemcpyAsync(g, img_host, wbytes * v->cfg.tracker.height, cudaMemcpyHostToDevice, s));
+                else
+                    RVIO_CUDA_TRY(cudaMemcpy2DAsync(g, gp, img_host, stride, wbytes, v->cfg.tracker.height, cudaMemcpyHostToDevice, s));
                 host_pinned = true;
-            } else {
-                cudaGetLastError();
             }
         }
         if (n_cand > 0 && cand_dev_in)
