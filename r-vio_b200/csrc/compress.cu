@@ -743,10 +743,14 @@ __device__ __forceinline__ void sr_apply_dq(const double* dth, const double* q, 
 constexpr int kSRThreads = kBCThreads;
 // shared-memory tiles of k_solve_small_R: T (S + extra rows), R (upper triangle by tile), Pc (extra tile rows x tile columns)
 // (the R / Pc region is reused for a copy of P during the factorisation: it is at least d x d doubles)
+// Windows up to kPtStagedMaxN columns also stage P[c,:] as tiles next to R (all operands of W = R P[c,:] in shared memory);
+// above that (13, 14 clones: the EuRoC default) the fragments of P come straight from global memory so that the step still
+// fits in one CTA.
+constexpr int kPtStagedMaxN = 72;
 __host__ __device__ inline int solve_small_stage_doubles(int n, int d)
 {
     const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
-    const int a = (tc * (tc + 1) / 2 + tre * tc) * 64, b = d * d;
+    const int a = (tc * (tc + 1) / 2 + (n <= kPtStagedMaxN ? tre * tc : 0)) * 64, b = d * d;
     return a > b ? a : b;
 }
 __host__ __device__ inline size_t solve_small_doubles(int n, int d)
@@ -785,6 +789,8 @@ __device__ __forceinline__ void solve_small_body(const SolveSmallRParams& Q, dou
         const int r = 8 * Rj + rr, k = 8 * (Rj + rem) + q2;
         cp_async16_zfill(Rt + ((size_t)tl << 6) + rr * 8 + q2, Q.Rc + (size_t)r * n + k, (r < n) ? max(0, min(2, n - k)) : 0, Q.Rc);
     }
+    const bool pt_staged = n <= kPtStagedMaxN;
+    if (pt_staged)
     for (int o = tid; o < tre * tc * 32; o += kSRThreads) {                       // P(c, 24 + k) = Pc(k, c) -> tiles
         const int tl = o >> 5, cc = (o >> 2) & 7, q2 = 2 * (o & 3);
         const int Ci = tl / tc, Kb = tl - Ci * tc;
@@ -799,21 +805,42 @@ __device__ __forceinline__ void solve_small_body(const SolveSmallRParams& Q, dou
     for (int w = warp; w < tre * tc; w += kBCWarps) {
         const int Ci = w / tc, Rj = w - Ci * tc;
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
-        const double* ap = Pt + ((size_t)(Ci * tc + Rj) << 6) + g * 8 + 2 * t4;     // tiles (Ci, Kb), Kb = Rj .. : consecutive
         const double* bp = rtile(Rj, Rj) + g * 8 + 2 * t4;                           // tiles (Rj, Kb), Kb = Rj .. : consecutive
         int nk = tc - Rj;
-        for (; nk >= 2; nk -= 2, ap += 128, bp += 128) {
-            const double2 a0 = *reinterpret_cast<const double2*>(ap), a1 = *reinterpret_cast<const double2*>(ap + 64);
-            const double2 b0 = *reinterpret_cast<const double2*>(bp), b1 = *reinterpret_cast<const double2*>(bp + 64);
-            dmma884(c0.x, c0.y, a0.x, b0.x);
-            dmma884(c1.x, c1.y, a1.x, b1.x);
-            dmma884(c0.x, c0.y, a0.y, b0.y);
-            dmma884(c1.x, c1.y, a1.y, b1.y);
-        }
-        if (nk) {
-            const double2 a0 = *reinterpret_cast<const double2*>(ap);
-            const double2 b0 = *reinterpret_cast<const double2*>(bp);
-            tile_mma(c0, a0, b0);
+        if (pt_staged) {
+            const double* ap = Pt + ((size_t)(Ci * tc + Rj) << 6) + g * 8 + 2 * t4;  // tiles (Ci, Kb), Kb = Rj .. : consecutive
+            for (; nk >= 2; nk -= 2, ap += 128, bp += 128) {
+                const double2 a0 = *reinterpret_cast<const double2*>(ap), a1 = *reinterpret_cast<const double2*>(ap + 64);
+                const double2 b0 = *reinterpret_cast<const double2*>(bp), b1 = *reinterpret_cast<const double2*>(bp + 64);
+                dmma884(c0.x, c0.y, a0.x, b0.x);
+                dmma884(c1.x, c1.y, a1.x, b1.x);
+                dmma884(c0.x, c0.y, a0.y, b0.y);
+                dmma884(c1.x, c1.y, a1.y, b1.y);
+            }
+            if (nk) {
+                const double2 a0 = *reinterpret_cast<const double2*>(ap);
+                const double2 b0 = *reinterpret_cast<const double2*>(bp);
+                tile_mma(c0, a0, b0);
+            }
+        } else {
+            // the fragments of P (row c of P, columns 24 + k: P is symmetric) straight from global memory, all of a tile's
+            // requests issued before its first product
+            constexpr int kMaxKb = 11;                                               // ceil(84 / 8)
+            const int cP = 8 * Ci + g;
+            const double* pg = Q.P + (size_t)cP * d + 24 + 8 * Rj + 2 * t4;
+            double2 av[kMaxKb];
+#pragma unroll
+            for (int q = 0; q < kMaxKb; ++q) {
+                const int k = 8 * (Rj + q) + 2 * t4;
+                av[q] = (q < nk && cP < d && k < n) ? *reinterpret_cast<const double2*>(pg + 8 * q) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < kMaxKb; ++q) {
+                if (q < nk) {
+                    const double2 b0 = *reinterpret_cast<const double2*>(bp + 64 * q);
+                    if (q & 1) tile_mma(c1, av[q], b0); else tile_mma(c0, av[q], b0);
+                }
+            }
         }
         c0.x += c1.x; c0.y += c1.y;
         // the row c = d of the extra rows is y, not a column of W
@@ -1110,7 +1137,7 @@ __global__ void __launch_bounds__(kBCThreads, 1) k_update_small(RankRuleParams r
     const int tc = (n + 7) >> 3, tre = (d + 1 + 7) >> 3;
     if (threadIdx.x == 0) *sq.bad = 0;
     double* Rt = usm + (size_t)tile_tri_count(tc, tc + tre) * 64;
-    double* rank_tiles = usm + solve_small_doubles(n, d);
+    double* rank_tiles = usm;                                       // (inside the step's T region, which is written only after the rule has emitted R)
     rank_rule_body(rq, rank_tiles, Rt, tc, s_yc);
     __syncthreads();
     const bool updating = sq.gate[0] > 2.0;
@@ -1144,10 +1171,12 @@ static size_t trsm_smem_bytes(int n) { const int tc = (n + 7) / 8; return sizeof
 static size_t update_small_smem_bytes(int n, int d)
 {
     bool w;
-    const size_t a = solve_small_smem_bytes(n, d) + rank_rule_smem_bytes(n), b = givens_smem_bytes(n, &w);
+    size_t a = solve_small_smem_bytes(n, d);
+    const size_t r = rank_rule_smem_bytes(n), b = givens_smem_bytes(n, &w);
+    if (r > a) a = r;
     return a > b ? a : b;
 }
-constexpr int kSolveSmallRMaxN = 72;      // windows up to 12 clones: the whole EKF step in one CTA (166 KB of shared memory)
+constexpr int kSolveSmallRMaxN = 84;      // windows up to 14 clones (the EuRoC default): the whole EKF step in one CTA (206 KB of shared memory)
 
 int compress_configure(int nmax)
 {

@@ -1231,9 +1231,9 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     const dim3 blk(256), grd(div_up(t->W, 256), t->H);
     const bool will_track = !t->first && t->n_track > 0;
     if (will_track) {
-        // Ransac::GetRotation on the host (libm), uploaded ahead of the image kernels so that it is off the critical path
+        // Ransac::GetRotation on the host (libm) into a pinned block that k_ransac_bookkeep reads directly (nine doubles over
+        // PCIe at the start of the kernel, behind its candidate compaction): no copy node on the frame's critical path
         host_gyro_rotation(t->Ric, imu, n_imu, t->cfg.small_angle, t->h_R);
-        RVIO_ENQ(cudaMemcpyAsync(t->d_R, t->h_R, sizeof(double) * 9, cudaMemcpyHostToDevice, s));
     }
     // Tracker.cc:198-202
     if (t->cfg.enable_equalizer) {
@@ -1274,7 +1274,7 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     if (!finish) { RVIO_ENQ(cudaGetLastError()); return RVIO_OK; }
     RansacParams rp;
     rp.B = t->B; rp.n = n; rp.n_dev = lp.n_dev; rp.use_sampson = t->cfg.use_sampson;
-    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->h_R;
     RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, s, rp);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
@@ -1363,7 +1363,7 @@ extern "C" int rvio_tracker_track_finish(rvio_tracker* t)
     RVIO_CUDA_TRY(cudaSetDevice(t->device));
     RansacParams rp;
     rp.B = t->B; rp.n = t->last_n; rp.n_dev = nullptr; rp.use_sampson = t->cfg.use_sampson;
-    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->h_R;
     RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, t->stream, rp);
     RVIO_CUDA_TRY(cudaGetLastError());
     return sync_scalars(t);
@@ -1576,7 +1576,7 @@ int tracker_enqueue_ransac(rvio_tracker* t)
 {
     RansacParams rp;
     rp.B = t->B; rp.n = t->last_n; rp.n_dev = &t->B.sc->n_new; rp.use_sampson = t->cfg.use_sampson;
-    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->d_R;
+    rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->h_R;
     RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, t->stream, rp);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;

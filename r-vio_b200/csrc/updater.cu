@@ -150,7 +150,7 @@ __device__ long long g_feat_clk[16];
 #define FEAT_CLK(k) do { } while (0)
 #endif
 constexpr int kFeatThreads = 256;
-constexpr int kSolveSmallMaxClones = 12;     // n = 72: the single-CTA EKF step (k_solve_small_R) fits in 227 KB of shared memory
+constexpr int kSolveSmallMaxClones = 14;     // n = 84 (the EuRoC default window): the single-CTA step (k_update_small) fits in 227 KB of shared memory
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
@@ -739,7 +739,7 @@ constexpr int kGateThreads = 256;
 __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
 {
     extern __shared__ __align__(16) double sg[];                  // S[dof*dof], v[dof], chunk T[dof][33], chunk H[dof][33]
-    __shared__ double s_piv;
+    __shared__ double s_piv, s_y;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
     if (f >= n_feat || f % P.world != P.rank) return;
@@ -803,31 +803,46 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
         if (a > b) S[a * dof + b] = S[b * dof + a];
     }
     __syncthreads();
-    for (int j = 0; j < dof; ++j) {                                // Cholesky S = L L^T (lower)
-        if (tid == 0) { const double dj = S[j * dof + j]; s_piv = (dj > 0) ? sqrt(dj) : nan(""); }
-        __syncthreads();
-        const double dj = s_piv;
-        for (int i = j + tid; i < dof; i += kGateThreads) S[i * dof + j] = (i == j) ? dj : S[i * dof + j] / dj;
+    // Cholesky S = L L^T (lower); the forward substitution y = L^-1 r rides along (column j of L is applied to the right-hand
+    // side in the same step), gamma = y^T y.  Two barriers per column: thread 0, which finishes the next pivot in the trailing
+    // update, prepares the next column right there.
+    {
+        const double* rn = P.rblk + (size_t)f * P.blk_rows;
+        for (int i = tid; i < dof; i += kGateThreads) vv[i] = rn[i];
+    }
+    double gamma = 0;                                              // (thread 0's copy is the one that counts)
+    __syncthreads();
+    if (tid == 0) {
+        const double d0 = S[0];
+        const double sd = (d0 > 0) ? sqrt(d0) : nan("");
+        const double y0 = vv[0] / sd;
+        s_piv = sd; s_y = y0;
+        gamma += y0 * y0;
+    }
+    __syncthreads();
+    for (int j = 0; j < dof; ++j) {
+        const double dj = s_piv, yj = s_y;
+        for (int i = j + tid; i < dof; i += kGateThreads) {
+            const double lij = (i == j) ? dj : S[i * dof + j] / dj;
+            S[i * dof + j] = lij;
+            if (i > j) vv[i] -= lij * yj;
+        }
         __syncthreads();
         const int rem = dof - j - 1;
         for (int o = tid; o < rem * rem; o += kGateThreads) {
             const int a = j + 1 + o / rem, b = j + 1 + o % rem;
             if (b <= a) S[a * dof + b] -= S[a * dof + j] * S[b * dof + j];
         }
+        if (tid == 0 && rem > 0) {
+            const double dn = S[(j + 1) * dof + j + 1];
+            const double sd = (dn > 0) ? sqrt(dn) : nan("");
+            const double yn = vv[j + 1] / sd;
+            s_piv = sd; s_y = yn;
+            gamma += yn * yn;
+        }
         __syncthreads();
     }
-    if (warp == 0) {                                               // gamma = |L^-1 r|^2
-        const double* rn = P.rblk + (size_t)f * P.blk_rows;
-        double gamma = 0;
-        for (int i = 0; i < dof; ++i) {
-            double part = 0;
-            for (int k = lane; k < i; k += 32) part += S[i * dof + k] * vv[k];
-            part = warp_sum(part);
-            const double y = (rn[i] - part) / S[i * dof + i];
-            if (lane == 0) vv[i] = y;
-            __syncwarp();
-            gamma += y * y;
-        }
+    if (warp == 0) {
         if (lane == 0) {
             gamma = fabs(gamma);
             P.f_gamma[f] = gamma;
