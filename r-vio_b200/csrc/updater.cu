@@ -738,7 +738,7 @@ struct GateParams {
 constexpr int kGateThreads = 256;
 __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
 {
-    extern __shared__ __align__(16) double sg[];                  // S[dof*dof], v[dof], chunk T[dof][33], chunk H[dof][33]
+    extern __shared__ __align__(16) double sg[];                  // S[dof*dof], v[dof], chunk T[64][34], chunk H[64][34]
     __shared__ double s_piv, s_y;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
@@ -746,47 +746,69 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
     const int dof = P.f_pend[f];
     if (dof <= 0) return;
     const int n = P.n, c0 = P.f_c0[f], wc = P.f_wc[f];
-    double* S = sg; double* vv = S + dof * dof; double* cT = vv + dof; double* cH = cT + dof * 33;
+    constexpr int kCLd = 34;                                       // chunk row stride (even: 16-byte fragment loads)
+    double* S = sg; double* vv = S + dof * dof;
+    double* cT = vv + dof;                                         // 64 x kCLd: rows of T_f, 32 columns at a time (dof^2 + dof is even: 16-byte aligned)
+    double* cH = cT + 64 * kCLd;                                   // 64 x kCLd: rows of H_f
     const double* Hf = P.Hblk + (size_t)f * P.blk_rows * n;
     const double* Tf = P.T + (size_t)f * P.blk_rows * n;
-    const int na = (dof + 1) / 2;
-    // S = T_f H_f^T over the feature's column range, 2 x 2 register tiles, 32-column chunks staged in shared memory
-    double acc[4][4];
-    int ta[4], tb[4], nt = 0;
-    for (int o = tid; o < na * na && nt < 4; o += kGateThreads) { ta[nt] = 2 * (o / na); tb[nt] = 2 * (o % na); ++nt; }
+    // S = T_f H_f^T over the feature's column range on the FP64 tensor pipe: 8 x 8 output tiles (all of them: the symmetrisation
+    // below needs S(a,b) and S(b,a)), warp w owns tiles w, w + 8, ...; 32-column chunks of T_f and H_f staged in shared memory,
+    // both fragments of a tile product are one 16-byte load (columns 2t, 2t+1 of row g: the k index is permuted identically)
+    const int TR = (dof + 7) >> 3;                                 // <= 8 (dof <= 64)
+    const int gq = lane >> 2, t4 = lane & 3;
+    double acc[8][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0; }
+    for (int u = 0; u < 8; ++u) { acc[u][0] = 0; acc[u][1] = 0; }
+    for (int o = tid; o < 64 * kCLd; o += kGateThreads) { cT[o] = 0.0; cH[o] = 0.0; }      // rows >= dof stay zero
+    __syncthreads();
     for (int j0 = 0; j0 < wc; j0 += 32) {
         const int jw = min(32, wc - j0);
-        for (int o = tid; o < dof * 32; o += kGateThreads) {
-            const int a = o >> 5, jj = o & 31;
-            const bool ok = jj < jw;
-            cT[a * 33 + jj] = ok ? Tf[(size_t)a * n + c0 + j0 + jj] : 0.0;
-            cH[a * 33 + jj] = ok ? Hf[(size_t)a * n + c0 + j0 + jj] : 0.0;
+        {
+            // all of a thread's loads of the chunk are requested before the first store (dof <= 64: at most 8 elements per thread)
+            double vt[8], vh[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int o = tid + q * kGateThreads;
+                const int a = o >> 5, jj = o & 31;
+                const bool ok = o < dof * 32 && jj < jw;
+                vt[q] = ok ? Tf[(size_t)a * n + c0 + j0 + jj] : 0.0;
+                vh[q] = ok ? Hf[(size_t)a * n + c0 + j0 + jj] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int o = tid + q * kGateThreads;
+                if (o < dof * 32) { cT[(o >> 5) * kCLd + (o & 31)] = vt[q]; cH[(o >> 5) * kCLd + (o & 31)] = vh[q]; }
+            }
         }
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (u < nt) {
-                const double* t0 = cT + ta[u] * 33; const double* t1 = (ta[u] + 1 < dof) ? t0 + 33 : t0;
-                const double* h0 = cH + tb[u] * 33; const double* h1 = (tb[u] + 1 < dof) ? h0 + 33 : h0;
-                for (int jj = 0; jj < 32; ++jj) {
-                    const double x0 = t0[jj], x1 = t1[jj], y0 = h0[jj], y1 = h1[jj];
-                    acc[u][0] = fma(x0, y0, acc[u][0]); acc[u][1] = fma(x0, y1, acc[u][1]);
-                    acc[u][2] = fma(x1, y0, acc[u][2]); acc[u][3] = fma(x1, y1, acc[u][3]);
+        for (int u = 0; u < 8; ++u) {
+            const int tl = warp + 8 * u;
+            if (tl < TR * TR) {
+                const int I = tl / TR, J = tl - I * TR;
+                const double* ap = cT + (8 * I + gq) * kCLd + 2 * t4;
+                const double* bp = cH + (8 * J + gq) * kCLd + 2 * t4;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const double2 av = *reinterpret_cast<const double2*>(ap + 8 * ks), bv = *reinterpret_cast<const double2*>(bp + 8 * ks);
+                    dmma_8x8x4(acc[u], av.x, bv.x);
+                    dmma_8x8x4(acc[u], av.y, bv.y);
                 }
             }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-        if (u < nt) {
-            const int a = ta[u], b = tb[u];
-            S[a * dof + b] = acc[u][0];
-            if (b + 1 < dof) S[a * dof + b + 1] = acc[u][1];
-            if (a + 1 < dof) { S[(a + 1) * dof + b] = acc[u][2]; if (b + 1 < dof) S[(a + 1) * dof + b + 1] = acc[u][3]; }
+    for (int u = 0; u < 8; ++u) {
+        const int tl = warp + 8 * u;
+        if (tl < TR * TR) {
+            const int I = tl / TR, J = tl - I * TR;
+            const int a = 8 * I + gq, b = 8 * J + 2 * t4;
+            if (a < dof && b < dof) S[a * dof + b] = acc[u][0];
+            if (a < dof && b + 1 < dof) S[a * dof + b + 1] = acc[u][1];
         }
+    }
     __syncthreads();
     // symmetrise + noise (Updater.cc:417-418)
     for (int o = tid; o < dof * dof; o += kGateThreads) {
@@ -1073,6 +1095,13 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
 // the UPPER triangle of G (mirrored by the reducing CTA), the products through FP64 DMMA (A(i,k) = H(k,i), B(k,j) = H(k,j):
 // both fragments come from the same k-major row chunk in shared memory).  128 threads = 4 warps x (32 x 32).
 constexpr int kGramT = 64, kGramLd = kGramT + 8, kGramRows = 32;
+// 16-byte asynchronous copy of which only the first n_valid (0, 1, 2) doubles are read; the rest is zero filled
+__device__ __forceinline__ void gram_cp16(double* dst_smem, const double* src, int n_valid, const double* safe)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const double* sp = n_valid > 0 ? src : safe;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(sp), "r"(8 * n_valid) : "memory");
+}
 __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
     __shared__ __align__(16) double sI[kGramRows][kGramLd], sJ[kGramRows][kGramLd];
@@ -1102,14 +1131,19 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
         const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
         const double* rv = P.rblk + (size_t)f * P.blk_rows;
         for (int a0 = 0; a0 < dof; a0 += kGramRows) {
-            for (int o = tid; o < kGramRows * kGramT; o += 128) {
-                const int r = o / kGramT, c = o - r * kGramT;
+            // the chunk's rows through cp.async (16-byte pieces, zero filled past the block's rows / the matrix' columns): all of a
+            // thread's requests are in flight together -- the scalar loop it replaces paid one L2 round trip per element
+            for (int o = tid; o < kGramRows * (kGramT / 2); o += 128) {
+                const int r = o / (kGramT / 2), c = 2 * (o - r * (kGramT / 2));
                 const int a = a0 + r;
                 const bool rok = a < dof;
-                sI[r][c] = (rok && i0 + c < n) ? H[(size_t)a * n + i0 + c] : 0.0;
-                sJ[r][c] = (rok && j0 + c < n) ? H[(size_t)a * n + j0 + c] : 0.0;
+                const double* src = H + (size_t)(rok ? a : 0) * n;
+                gram_cp16(&sI[r][c], src + i0 + c, rok ? max(0, min(2, n - (i0 + c))) : 0, H);
+                if (ti != tj) gram_cp16(&sJ[r][c], src + j0 + c, rok ? max(0, min(2, n - (j0 + c))) : 0, H);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             if (ti == tj && tid < kGramRows) s_r[tid] = (a0 + tid < dof) ? rv[a0 + tid] : 0.0;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < kGramRows; kk += 4) {
@@ -1117,7 +1151,7 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
 #pragma unroll
                 for (int a = 0; a < 4; ++a) af[a] = sI[kk + t][wm * 32 + a * 8 + gq];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) bf[b] = sJ[kk + t][wn * 32 + b * 8 + gq];
+                for (int b = 0; b < 4; ++b) bf[b] = (ti == tj) ? sI[kk + t][wn * 32 + b * 8 + gq] : sJ[kk + t][wn * 32 + b * 8 + gq];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1867,7 +1901,7 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_dmma_hp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * kGM * kGLdA + 2 * kGK * kGLdB))));
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)u->lay.Dc * u->lay.Dc + u->lay.Dc + 66 * u->lay.Dc + 8))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)u->lay.Dc * u->lay.Dc + u->lay.Dc + 2 * 64 * 34 + 16))));
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
     u->groups_cap = cfg->max_clones * 6 >= 96 ? 48 : 16;      // partial normal terms per tile (the tensor-core variant spreads wider)
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
@@ -1950,7 +1984,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
             gq.n_feat = n_feat_cap; gq.n_feat_dev = n_feat_dev; gq.n = n; gq.blk_rows = u->lay.Mc; gq.rank = rank; gq.world = world;
             gq.sig2 = u->consts.sig2; gq.chi2 = u->d_chi2; gq.f_status = u->d_fstatus; gq.f_gamma = u->d_fgamma; gq.f_dof = u->d_fdof;
             const int Dc = u->lay.Dc;
-            RVIO_LAUNCH(k_gate, n_feat_cap, kGateThreads, sizeof(double) * ((size_t)Dc * Dc + Dc + 66 * Dc + 8), s, gq);
+            RVIO_LAUNCH(k_gate, n_feat_cap, kGateThreads, sizeof(double) * ((size_t)Dc * Dc + Dc + 2 * 64 * 34 + 16), s, gq);
         }
         GramParams gp;
         gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc; gp.f_fro2 = u->d_ffro2;
