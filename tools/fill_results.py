@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Fills the measured numbers of DESIGN.md / BASELINE.md / README.md (fields marked <!--KEY-->...<!--/KEY-->) from the committed
+bench lines under profiles/; re-runnable."""
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def last_json(path):
+    return json.loads([l for l in open(os.path.join(ROOT, path)) if l.startswith("{")][-1])
+
+
+def fmt(v, nd=0):
+    if nd == 0:
+        s = f"{v:,.0f}".replace(",", " ")
+    else:
+        s = f"{v:,.{nd}f}".replace(",", " ")
+    return s
+
+
+b = last_json("profiles/bench_r02.json")
+r = last_json("profiles/bench_r02_reference.json")
+g2 = last_json("profiles/bench_r02_gpus2.json")
+tl = b["stage_us_per_step"]
+wc = b["update_worstcase"]
+fp64_peak = 64 * 2 * 148 * 1.965e9 / 1e12          # TFLOP/s: 64 FMA/clk/SM (tools/ubench/lat.cu)
+vals = {
+    "VALUE": fmt(b["value"]), "VALUE_MS": fmt(b["ms_per_step"], 3),
+    "E2E": fmt(b["e2e"]["value"]), "E2E_MS": fmt(b["e2e"]["ms_per_step"], 3),
+    "BATCH": fmt(b["batch"]["value"]),
+    "REF": fmt(r["value"]), "REF_MS": fmt(r["ms_per_step"], 2),
+    "STRESS": fmt(b["stress"]["value"]), "STRESS_MS": fmt(b["stress"]["ms_per_step"], 3),
+    "G2": fmt(g2["value"]), "G2RANKS": " / ".join(f"{x:.3f}" for x in g2["per_rank_ms_per_step"]["device"]),
+    "G2BATCH": fmt(g2["batch"]["value"]),
+    "G2SH": fmt(g2["sharded"]["value"]), "G2SH1": fmt(g2["sharded"]["unsharded_same_stream"]["value"]),
+    "G2EFF": f"{g2['value'] / (2 * b['value']):.2f}",
+    "SPEEDUP": f"{b['e2e']['value'] / r['value']:.1f}", "SPEEDUPV": f"{b['value'] / r['value']:.1f}",
+    "T_TR": fmt(tl["tracker"]), "T_FE": fmt(tl["feature+normal_terms"]), "T_SO": fmt(tl["solve"]),
+    "T_AU": fmt(tl["augment_compose"]), "T_TA": fmt(tl["tail"]),
+}
+for key, tag in (("configs[2]", "WC2"), ("configs[4]", "WC4")):
+    w = wc[key]; ro = w["roofline_update"]
+    vals[tag] = fmt(w["ms_update_kernels"], 3)
+    vals[tag + "TF"] = fmt(ro["tflops"], 1)
+    vals[tag + "FR"] = f"{100 * ro['tflops'] / fp64_peak:.0f} %"
+    vals[tag + "FRAC"] = vals[tag + "FR"]
+    vals[tag + "GB"] = fmt(ro["achieved"])
+    vals[tag + "HB"] = f"{100 * ro['frac']:.1f} %"
+for name in sys.argv[1:] or ["DESIGN.md", "BASELINE.md", "README.md"]:
+    p = os.path.join(ROOT, name)
+    s = open(p).read()
+    # first pass: turn @KEY@ into a re-fillable marker pair; then (re)fill every marker pair
+    s = re.sub(r"@([A-Z0-9_]+)@", lambda m: f"<!--{m.group(1)}--><!--/{m.group(1)}-->", s)
+    missing = set(re.findall(r"<!--([A-Z0-9_]+)-->", s)) - set(vals)
+    if missing:
+        print(name, "unknown placeholders:", missing)
+    for k, v in vals.items():
+        s = re.sub(rf"<!--{k}-->.*?<!--/{k}-->", f"<!--{k}-->{v}<!--/{k}-->", s, flags=re.S)
+    open(p, "w").write(s)
+    print("filled", name)
