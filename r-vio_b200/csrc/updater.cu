@@ -4,6 +4,7 @@
 #include "tracker_kernels.cuh"
 #include "updater_kernels.cuh"
 #include "compress_kernels.cuh"
+#include "tile_cholesky.cuh"
 #include "chi2_table.h"
 
 #include <math.h>
@@ -735,11 +736,15 @@ struct GateParams {
     uint8_t* f_status; double* f_gamma; int32_t* f_dof;
 };
 
-constexpr int kGateThreads = 256;
-__global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
+constexpr int kGateThreads = kBCThreads;      // the blocked Cholesky's CTA shape (tile_cholesky.cuh)
+__global__ void __launch_bounds__(kGateThreads, 1) k_gate(GateParams P)
 {
-    extern __shared__ __align__(16) double sg[];                  // S[dof*dof], v[dof], chunk T[64][34], chunk H[64][34]
-    __shared__ double s_piv, s_y;
+    // dynamic shared memory: [tile-packed S (+ one extra tile row for r): 44 tiles][chunk T[64][34]][chunk H[64][34]]; after the
+    // product the two chunk buffers hold the full 64 x 64 S (both triangles: the symmetrisation needs S(a,b) and S(b,a))
+    extern __shared__ __align__(16) double sg[];
+    __shared__ double s_pv[72];
+    __shared__ PanelPub s_pub;
+    __shared__ int s_bad;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
     if (f >= n_feat || f % P.world != P.rank) return;
@@ -747,28 +752,31 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
     if (dof <= 0) return;
     const int n = P.n, c0 = P.f_c0[f], wc = P.f_wc[f];
     constexpr int kCLd = 34;                                       // chunk row stride (even: 16-byte fragment loads)
-    double* S = sg; double* vv = S + dof * dof;
-    double* cT = vv + dof;                                         // 64 x kCLd: rows of T_f, 32 columns at a time (dof^2 + dof is even: 16-byte aligned)
+    constexpr int kTileDoubles = 44 * 64;                          // 8 tile rows of the lower triangle + the row of r
+    double* Tt = sg;
+    double* cT = sg + kTileDoubles;                                // 64 x kCLd: rows of T_f, 32 columns at a time
     double* cH = cT + 64 * kCLd;                                   // 64 x kCLd: rows of H_f
     const double* Hf = P.Hblk + (size_t)f * P.blk_rows * n;
     const double* Tf = P.T + (size_t)f * P.blk_rows * n;
-    // S = T_f H_f^T over the feature's column range on the FP64 tensor pipe: 8 x 8 output tiles (all of them: the symmetrisation
-    // below needs S(a,b) and S(b,a)), warp w owns tiles w, w + 8, ...; 32-column chunks of T_f and H_f staged in shared memory,
-    // both fragments of a tile product are one 16-byte load (columns 2t, 2t+1 of row g: the k index is permuted identically)
+    // S = T_f H_f^T over the feature's column range on the FP64 tensor pipe: 8 x 8 output tiles, warp w owns tiles w, w + 16, ...;
+    // 32-column chunks of T_f and H_f staged in shared memory, both fragments of a tile product are one 16-byte load
+    // (columns 2t, 2t+1 of row g: the k index is permuted identically)
     const int TR = (dof + 7) >> 3;                                 // <= 8 (dof <= 64)
+    constexpr int kW = kGateThreads / 32;
     const int gq = lane >> 2, t4 = lane & 3;
-    double acc[8][2];
+    double acc[4][2];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { acc[u][0] = 0; acc[u][1] = 0; }
-    for (int o = tid; o < 64 * kCLd; o += kGateThreads) { cT[o] = 0.0; cH[o] = 0.0; }      // rows >= dof stay zero
+    for (int u = 0; u < 4; ++u) { acc[u][0] = 0; acc[u][1] = 0; }
+    for (int o = tid; o < 2 * 64 * kCLd; o += kGateThreads) cT[o] = 0.0;                    // rows >= dof stay zero
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     for (int j0 = 0; j0 < wc; j0 += 32) {
         const int jw = min(32, wc - j0);
         {
-            // all of a thread's loads of the chunk are requested before the first store (dof <= 64: at most 8 elements per thread)
-            double vt[8], vh[8];
+            // all of a thread's loads of the chunk are requested before the first store (dof <= 64: at most 4 elements per thread)
+            double vt[4], vh[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const int o = tid + q * kGateThreads;
                 const int a = o >> 5, jj = o & 31;
                 const bool ok = o < dof * 32 && jj < jw;
@@ -776,15 +784,15 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
                 vh[q] = ok ? Hf[(size_t)a * n + c0 + j0 + jj] : 0.0;
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const int o = tid + q * kGateThreads;
                 if (o < dof * 32) { cT[(o >> 5) * kCLd + (o & 31)] = vt[q]; cH[(o >> 5) * kCLd + (o & 31)] = vh[q]; }
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int tl = warp + 8 * u;
+        for (int u = 0; u < 4; ++u) {
+            const int tl = warp + kW * u;
             if (tl < TR * TR) {
                 const int I = tl / TR, J = tl - I * TR;
                 const double* ap = cT + (8 * I + gq) * kCLd + 2 * t4;
@@ -799,74 +807,45 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(GateParams P)
         }
         __syncthreads();
     }
+    // the full S into the (now dead) chunk buffers, row stride 64
+    double* Sf = cT;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int tl = warp + 8 * u;
+    for (int u = 0; u < 4; ++u) {
+        const int tl = warp + kW * u;
         if (tl < TR * TR) {
             const int I = tl / TR, J = tl - I * TR;
-            const int a = 8 * I + gq, b = 8 * J + 2 * t4;
-            if (a < dof && b < dof) S[a * dof + b] = acc[u][0];
-            if (a < dof && b + 1 < dof) S[a * dof + b + 1] = acc[u][1];
+            *reinterpret_cast<double2*>(Sf + (8 * I + gq) * 64 + 8 * J + 2 * t4) = make_double2(acc[u][0], acc[u][1]);
         }
     }
     __syncthreads();
-    // symmetrise + noise (Updater.cc:417-418)
-    for (int o = tid; o < dof * dof; o += kGateThreads) {
-        const int a = o / dof, b = o - a * dof;
-        if (a <= b) {
-            double v = .5 * (S[a * dof + b] + S[b * dof + a]);
-            if (a == b) v = S[a * dof + a] + P.sig2;
-            S[a * dof + b] = v;
-        }
-    }
+    // symmetrise + noise (Updater.cc:417-418) into the tile-packed lower triangle; identity padding; r as the extra row
+    TileTri T;
+    T.t = Tt; T.tc = TR; T.tr = TR + 1;
+    const int ncp = 8 * TR;
+    for (int o = tid; o < tile_tri_count(TR, TR + 1) * 64; o += kGateThreads) Tt[o] = 0.0;
     __syncthreads();
-    for (int o = tid; o < dof * dof; o += kGateThreads) {
-        const int a = o / dof, b = o - a * dof;
-        if (a > b) S[a * dof + b] = S[b * dof + a];
+    for (int o = tid; o < ncp * ncp; o += kGateThreads) {
+        const int a = o / ncp, b = o - a * ncp;
+        if (b > a) continue;
+        double v;
+        if (a < dof) v = (a == b) ? Sf[a * 64 + a] + P.sig2 : .5 * (Sf[b * 64 + a] + Sf[a * 64 + b]);
+        else v = (a == b) ? 1.0 : 0.0;
+        *T.at(a, b) = v;
     }
-    __syncthreads();
-    // Cholesky S = L L^T (lower); the forward substitution y = L^-1 r rides along (column j of L is applied to the right-hand
-    // side in the same step), gamma = y^T y.  Two barriers per column: thread 0, which finishes the next pivot in the trailing
-    // update, prepares the next column right there.
     {
         const double* rn = P.rblk + (size_t)f * P.blk_rows;
-        for (int i = tid; i < dof; i += kGateThreads) vv[i] = rn[i];
+        for (int j = tid; j < dof; j += kGateThreads) *T.at(ncp, j) = rn[j];
     }
-    double gamma = 0;                                              // (thread 0's copy is the one that counts)
-    __syncthreads();
-    if (tid == 0) {
-        const double d0 = S[0];
-        const double sd = (d0 > 0) ? sqrt(d0) : nan("");
-        const double y0 = vv[0] / sd;
-        s_piv = sd; s_y = y0;
-        gamma += y0 * y0;
-    }
-    __syncthreads();
-    for (int j = 0; j < dof; ++j) {
-        const double dj = s_piv, yj = s_y;
-        for (int i = j + tid; i < dof; i += kGateThreads) {
-            const double lij = (i == j) ? dj : S[i * dof + j] / dj;
-            S[i * dof + j] = lij;
-            if (i > j) vv[i] -= lij * yj;
-        }
-        __syncthreads();
-        const int rem = dof - j - 1;
-        for (int o = tid; o < rem * rem; o += kGateThreads) {
-            const int a = j + 1 + o / rem, b = j + 1 + o % rem;
-            if (b <= a) S[a * dof + b] -= S[a * dof + j] * S[b * dof + j];
-        }
-        if (tid == 0 && rem > 0) {
-            const double dn = S[(j + 1) * dof + j + 1];
-            const double sd = (dn > 0) ? sqrt(dn) : nan("");
-            const double yn = vv[j + 1] / sd;
-            s_piv = sd; s_y = yn;
-            gamma += yn * yn;
-        }
-        __syncthreads();
-    }
-    if (warp == 0) {
+    // Cholesky S = L L^T with r riding along as an extra row (-> y = L^-1 r): blocked, look-ahead, DMMA trailing updates
+    SpdPivot piv; piv.bad = &s_bad;
+    tile_cholesky<false>(T, 0, piv, nullptr, s_pv, &s_pub, nullptr, nullptr);
+    if (warp == 0) {                                               // gamma = |L^-1 r|^2
+        double g2 = 0;
+        for (int j = lane; j < dof; j += 32) { const double y = *T.at(ncp, j); g2 += y * y; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g2 += __shfl_xor_sync(0xffffffffu, g2, o);
         if (lane == 0) {
-            gamma = fabs(gamma);
+            double gamma = s_bad ? nan("") : fabs(g2);             // a non-positive pivot: not a valid innovation covariance -> rejected
             P.f_gamma[f] = gamma;
             const bool ok = gamma < P.chi2[dof - 1];
             if (!ok) P.f_status[f] = 3;
@@ -1095,6 +1074,13 @@ __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_sta
 // the UPPER triangle of G (mirrored by the reducing CTA), the products through FP64 DMMA (A(i,k) = H(k,i), B(k,j) = H(k,j):
 // both fragments come from the same k-major row chunk in shared memory).  128 threads = 4 warps x (32 x 32).
 constexpr int kGramT = 64, kGramLd = kGramT + 8, kGramRows = 32;
+constexpr size_t kGramDmmaSmem = sizeof(double) * (2 * 2 * kGramRows * kGramLd + 2 * kGramRows);      // two [sI | sJ] buffers + residuals
+// 8-byte asynchronous copy (zero when !valid)
+__device__ __forceinline__ void gram_cp8(double* dst_smem, const double* src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
 // 16-byte asynchronous copy of which only the first n_valid (0, 1, 2) doubles are read; the rest is zero filled
 __device__ __forceinline__ void gram_cp16(double* dst_smem, const double* src, int n_valid, const double* safe)
 {
@@ -1104,10 +1090,10 @@ __device__ __forceinline__ void gram_cp16(double* dst_smem, const double* src, i
 }
 __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
-    __shared__ __align__(16) double sI[kGramRows][kGramLd], sJ[kGramRows][kGramLd];
-    __shared__ double s_r[kGramRows];
+    extern __shared__ __align__(16) double gsm[];                  // two buffers of [sI | sJ] (kGramRows x kGramLd each) + residuals
     __shared__ int s_last;
     __shared__ double s_cls[192];
+    __shared__ int s_list[256], s_ldof[256], s_wsum[4];
     const int n = P.n, nt = P.nt, g = blockIdx.y;
     // upper-triangle tile pair from the linear index
     int ti = 0, rem = blockIdx.x;
@@ -1116,6 +1102,8 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
     const int i0 = ti * kGramT, j0 = tj * kGramT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1, gq = lane >> 2, t = lane & 3;
+    constexpr int kBuf = 2 * kGramRows * kGramLd;                  // doubles per buffer
+    double* s_r = gsm + 2 * kBuf;                                  // [2][kGramRows]
     double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -1123,46 +1111,77 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
         for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0; acc[a][b][1] = 0; }
     double zacc = 0;
     const int n_feat = P.n_feat_dev ? *P.n_feat_dev : P.n_feat;
-    for (int f = g; f < n_feat; f += P.groups) {
-        const int dof = P.f_dof[f];
-        if (dof <= 0) continue;
-        const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
-        if (i0 >= c1 || i0 + kGramT <= c0 || j0 >= c1 || j0 + kGramT <= c0) continue;     // block is zero on this tile
-        const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
-        const double* rv = P.rblk + (size_t)f * P.blk_rows;
-        for (int a0 = 0; a0 < dof; a0 += kGramRows) {
-            // the chunk's rows through cp.async (16-byte pieces, zero filled past the block's rows / the matrix' columns): all of a
-            // thread's requests are in flight together -- the scalar loop it replaces paid one L2 round trip per element
-            for (int o = tid; o < kGramRows * (kGramT / 2); o += 128) {
-                const int r = o / (kGramT / 2), c = 2 * (o - r * (kGramT / 2));
-                const int a = a0 + r;
-                const bool rok = a < dof;
-                const double* src = H + (size_t)(rok ? a : 0) * n;
-                gram_cp16(&sI[r][c], src + i0 + c, rok ? max(0, min(2, n - (i0 + c))) : 0, H);
-                if (ti != tj) gram_cp16(&sJ[r][c], src + j0 + c, rok ? max(0, min(2, n - (j0 + c))) : 0, H);
+    // ---- this group's features that touch the tile, in index order (the accumulation order is part of the deterministic result)
+    int n_act = 0;
+    for (int base = 0; base * P.groups + g < n_feat; base += 128) {
+        const int f = g + (base + tid) * P.groups;
+        int dof = 0;
+        bool act = false;
+        if (f < n_feat) {
+            dof = P.f_dof[f];
+            if (dof > 0) {
+                const int c0 = P.f_c0[f], c1 = c0 + P.f_wc[f];
+                act = !(i0 >= c1 || i0 + kGramT <= c0 || j0 >= c1 || j0 + kGramT <= c0);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (ti == tj && tid < kGramRows) s_r[tid] = (a0 + tid < dof) ? rv[a0 + tid] : 0.0;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < kGramRows; kk += 4) {
-                double af[4], bf[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) af[a] = sI[kk + t][wm * 32 + a * 8 + gq];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) bf[b] = (ti == tj) ? sI[kk + t][wn * 32 + b * 8 + gq] : sJ[kk + t][wn * 32 + b * 8 + gq];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) dmma_8x8x4(acc[a][b], af[a], bf[b]);
-            }
-            if (ti == tj && tid < kGramT) {
-#pragma unroll 8
-                for (int r = 0; r < kGramRows; ++r) zacc = fma(sI[r][tid], s_r[r], zacc);
-            }
-            __syncthreads();
         }
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = n_act, tot = 0;
+        for (int w = 0; w < 4; ++w) { if (w < warp) off += s_wsum[w]; tot += s_wsum[w]; }
+        if (act) { const int pos = off + __popc(m & ((1u << lane) - 1u)); if (pos < 256) { s_list[pos] = f; s_ldof[pos] = dof; } }
+        n_act += tot;
+        __syncthreads();
+    }
+    if (n_act > 256) n_act = 256;                                  // (cannot happen: <= 4096 features over >= 16 groups)
+    // ---- chunk stream (feature li, rows a0 .. a0 + 31): chunk t + 1 is on its way (cp.async, 16-byte pieces, zero filled past
+    //      the block's rows / the matrix' columns) while chunk t is multiplied
+    auto issue = [&](int li_, int a0_, int buf) {
+        const int f = s_list[li_], dof = s_ldof[li_];
+        const double* H = P.Hblk + (size_t)f * P.blk_rows * n;
+        double* bI = gsm + buf * kBuf; double* bJ = bI + kGramRows * kGramLd;
+        for (int o = tid; o < kGramRows * (kGramT / 2); o += 128) {
+            const int r = o / (kGramT / 2), c = 2 * (o - r * (kGramT / 2));
+            const int a = a0_ + r;
+            const bool rok = a < dof;
+            const double* src = H + (size_t)(rok ? a : 0) * n;
+            gram_cp16(bI + r * kGramLd + c, src + i0 + c, rok ? max(0, min(2, n - (i0 + c))) : 0, H);
+            if (ti != tj) gram_cp16(bJ + r * kGramLd + c, src + j0 + c, rok ? max(0, min(2, n - (j0 + c))) : 0, H);
+        }
+        if (ti == tj && tid < kGramRows) {
+            const int a = a0_ + tid;
+            gram_cp8(s_r + buf * kGramRows + tid, P.rblk + (size_t)f * P.blk_rows + (a < dof ? a : 0), a < dof);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int li = 0, a0 = 0, buf = 0;
+    if (n_act > 0) issue(0, 0, 0);
+    while (li < n_act) {
+        int nli = li, na0 = a0 + kGramRows;
+        if (na0 >= s_ldof[li]) { nli = li + 1; na0 = 0; }
+        if (nli < n_act) { issue(nli, na0, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double* bI = gsm + buf * kBuf; const double* bJ = (ti == tj) ? bI : bI + kGramRows * kGramLd;
+#pragma unroll
+        for (int kk = 0; kk < kGramRows; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = bI[(kk + t) * kGramLd + wm * 32 + a * 8 + gq];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = bJ[(kk + t) * kGramLd + wn * 32 + b * 8 + gq];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma_8x8x4(acc[a][b], af[a], bf[b]);
+        }
+        if (ti == tj && tid < kGramT) {
+            const double* rr = s_r + buf * kGramRows;
+#pragma unroll 8
+            for (int r = 0; r < kGramRows; ++r) zacc = fma(bI[r * kGramLd + tid], rr[r], zacc);
+        }
+        __syncthreads();                                           // everyone is done with this buffer before the chunk after next lands in it
+        li = nli; a0 = na0; buf ^= 1;
     }
     double* Gp = P.Gpart + (size_t)g * n * n;
 #pragma unroll
@@ -1901,7 +1920,8 @@ extern "C" int rvio_updater_create(const rvio_updater_cfg* cfg, int device, rvio
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, u->lay.total_bytes));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gauss_jordan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (u->nmax + 2))));
     RVIO_CUDA_TRY(cudaFuncSetAttribute(k_dmma_hp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * kGM * kGLdA + 2 * kGK * kGLdB))));
-    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)u->lay.Dc * u->lay.Dc + u->lay.Dc + 2 * 64 * 34 + 16))));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramDmmaSmem));
+    RVIO_CUDA_TRY(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (44 * 64 + 2 * 64 * 34 + 16))));
     const size_t F = u->Fmax, n = u->nmax, d = u->dmax, Mc = u->lay.Mc;
     u->groups_cap = cfg->max_clones * 6 >= 96 ? 48 : 16;      // partial normal terms per tile (the tensor-core variant spreads wider)
 #define A(p, cnt) if ((rc = ualloc(u, &(p), (cnt))) != RVIO_OK) return rc
@@ -1983,8 +2003,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
             gq.Hblk = u->d_Hblk; gq.rblk = u->d_rblk; gq.T = u->d_Tg; gq.f_pend = u->d_fpend; gq.f_c0 = u->d_fc0; gq.f_wc = u->d_fwc;
             gq.n_feat = n_feat_cap; gq.n_feat_dev = n_feat_dev; gq.n = n; gq.blk_rows = u->lay.Mc; gq.rank = rank; gq.world = world;
             gq.sig2 = u->consts.sig2; gq.chi2 = u->d_chi2; gq.f_status = u->d_fstatus; gq.f_gamma = u->d_fgamma; gq.f_dof = u->d_fdof;
-            const int Dc = u->lay.Dc;
-            RVIO_LAUNCH(k_gate, n_feat_cap, kGateThreads, sizeof(double) * ((size_t)Dc * Dc + Dc + 2 * 64 * 34 + 16), s, gq);
+            RVIO_LAUNCH(k_gate, n_feat_cap, kGateThreads, sizeof(double) * (44 * 64 + 2 * 64 * 34 + 16), s, gq);
         }
         GramParams gp;
         gp.Hblk = u->d_Hblk; gp.rblk = u->d_rblk; gp.f_dof = u->d_fdof; gp.f_c0 = u->d_fc0; gp.f_wc = u->d_fwc; gp.f_fro2 = u->d_ffro2;
@@ -1994,7 +2013,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         if (tensor_gate) {
             gp.groups = n_feat_cap < u->groups_cap ? n_feat_cap : u->groups_cap;
             gp.nt = div_up(n, kGramT);
-            RVIO_LAUNCH(k_gram_dmma, dim3(gp.nt * (gp.nt + 1) / 2, gp.groups), 128, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
+            RVIO_LAUNCH(k_gram_dmma, dim3(gp.nt * (gp.nt + 1) / 2, gp.groups), 128, kGramDmmaSmem, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
         } else {
             RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
         }
