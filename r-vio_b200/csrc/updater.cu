@@ -1090,6 +1090,9 @@ __device__ __forceinline__ void gram_cp16(double* dst_smem, const double* src, i
 }
 __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
+#ifdef RVIO_B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicMin(&g_gram_ns[8], gram_now());
+#endif
     extern __shared__ __align__(16) double gsm[];                  // two buffers of [sI | sJ] (kGramRows x kGramLd each) + residuals
     __shared__ int s_last;
     __shared__ double s_cls[192];
@@ -1133,6 +1136,9 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
         n_act += tot;
         __syncthreads();
     }
+#ifdef RVIO_B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicMax(&g_gram_ns[9], gram_now());
+#endif
     if (n_act > 256) n_act = 256;                                  // (cannot happen: <= 4096 features over >= 16 groups)
     // ---- chunk stream (feature li, rows a0 .. a0 + 31): chunk t + 1 is on its way (cp.async, 16-byte pieces, zero filled past
     //      the block's rows / the matrix' columns) while chunk t is multiplied
@@ -1183,6 +1189,9 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
         __syncthreads();                                           // everyone is done with this buffer before the chunk after next lands in it
         li = nli; a0 = na0; buf ^= 1;
     }
+#ifdef RVIO_B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicMax(&g_gram_ns[10], gram_now());
+#endif
     double* Gp = P.Gpart + (size_t)g * n * n;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -1203,24 +1212,52 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = tid; e < kGramT * kGramT; e += 128) {
-        const int i = i0 + e / kGramT, j = j0 + e % kGramT;
-        if (i < n && j < n && (ti != tj || j >= i)) {           // diagonal tiles: the DMMA order of (i,j) and (j,i) differs -> take the upper part
-            double sum = 0;
-#pragma unroll 8
-            for (int gg = 0; gg < P.groups; ++gg) sum += P.Gpart[(size_t)gg * n * n + (size_t)i * n + j];
-            red[(size_t)i * n + j] = sum;
-            red[(size_t)j * n + i] = sum;                        // mirror: G bitwise symmetric
+    {
+        // all partials of two elements are requested before the first sum (one L2 round trip per pair of elements; the
+        // stores into `red` would otherwise fence the next element's loads); sums in group order: deterministic
+        const int ng = P.groups;                                   // <= 48
+        const double* __restrict__ Gpart = P.Gpart;
+        for (int e0 = tid; e0 < kGramT * kGramT; e0 += 2 * 128) {
+            double v[2][48];
+            int ii[2], jj[2];
+            bool ok[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = e0 + q * 128;
+                ii[q] = i0 + e / kGramT; jj[q] = j0 + e % kGramT;
+                ok[q] = e < kGramT * kGramT && ii[q] < n && jj[q] < n && (ti != tj || jj[q] >= ii[q]);      // diagonal tiles: the upper part, mirrored
+#pragma unroll
+                for (int gg = 0; gg < 48; ++gg) v[q][gg] = (ok[q] && gg < ng) ? Gpart[(size_t)gg * n * n + (size_t)ii[q] * n + jj[q]] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (ok[q]) {
+                    double sum = 0;
+#pragma unroll
+                    for (int gg = 0; gg < 48; ++gg) if (gg < ng) sum += v[q][gg];
+                    red[(size_t)ii[q] * n + jj[q]] = sum;
+                    red[(size_t)jj[q] * n + ii[q]] = sum;        // mirror: G bitwise symmetric
+                }
+            }
         }
     }
     if (ti == tj && tid < kGramT && i0 + tid < n) {
+        double vz[48];
+#pragma unroll
+        for (int gg = 0; gg < 48; ++gg) vz[gg] = (gg < P.groups) ? P.zpart[(size_t)gg * n + i0 + tid] : 0.0;
         double sum = 0;
-        for (int gg = 0; gg < P.groups; ++gg) sum += P.zpart[(size_t)gg * n + i0 + tid];
+#pragma unroll
+        for (int gg = 0; gg < 48; ++gg) if (gg < P.groups) sum += vz[gg];
         red[(size_t)n * n + i0 + tid] = sum;
     }
-    if (blockIdx.x == 0 && tid == 64) {
+    if (blockIdx.x != 0) return;
+    // ---- (tile 0 only) counters and the information per column-support class
+    __shared__ int s_cnt[6];
+    if (tid < 6) s_cnt[tid] = 0;
+    __syncthreads();
+    {
         int good = 0, rows = 0, r1 = 0, r2 = 0, r3 = 0, loc = 0;
-        for (int f = rank; f < n_feat; f += world) {
+        for (int f = rank + tid * world; f < n_feat; f += 128 * world) {
             loc++;
             const int st = f_status[f];
             if (st == 0) { good++; rows += P.f_dof[f]; }
@@ -1228,20 +1265,44 @@ __global__ void __launch_bounds__(128) k_gram_dmma(GramParams P, const uint8_t* 
             else if (st == 2) r2++;
             else r3++;
         }
+        if (good) atomicAdd(&s_cnt[0], good);
+        if (rows) atomicAdd(&s_cnt[1], rows);
+        if (r1) atomicAdd(&s_cnt[2], r1);
+        if (r2) atomicAdd(&s_cnt[3], r2);
+        if (r3) atomicAdd(&s_cnt[4], r3);
+        if (loc) atomicAdd(&s_cnt[5], loc);
+    }
+    // feature tables staged in the (now dead) chunk buffers: dof, first column, ||H_f||_F^2
+    const bool staged = n_feat <= 4096;                            // 4096 x 16 B = 64 KB <= the two chunk buffers
+    int* s_fd = reinterpret_cast<int*>(gsm);
+    int* s_fc = s_fd + 4096;
+    double* s_ff = gsm + 4096;                                     // (after the two int tables)
+    if (staged)
+        for (int f = tid; f < n_feat; f += 128) { s_fd[f] = P.f_dof[f]; s_fc[f] = P.f_c0[f]; s_ff[f] = P.f_fro2[f]; }
+    for (int c = tid; c <= n; c += 128) s_cls[c] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
         double* c = red + (size_t)n * n + n;
-        c[0] = good; c[1] = rows; c[2] = r1; c[3] = r2; c[4] = r3; c[5] = loc; c[6] = 0; c[7] = 0;
+        c[0] = s_cnt[0]; c[1] = s_cnt[1]; c[2] = s_cnt[2]; c[3] = s_cnt[3]; c[4] = s_cnt[4]; c[5] = s_cnt[5]; c[6] = 0; c[7] = 0;
     }
-    if (blockIdx.x == 0) {
-        for (int c = tid; c <= n; c += 128) {
-            double a2 = 0;
-            for (int f = rank; f < n_feat; f += world)
+    // cls[c] = sum of ||H_f||_F^2 over the accepted features whose first non-zero column is c (multiples of 6): one warp per
+    // class, lanes stride over the features, fixed butterfly -> deterministic
+    for (int c = 6 * warp; c <= n; c += 6 * 4) {
+        double a2 = 0;
+        if (staged) {
+            for (int f = rank + lane * world; f < n_feat; f += 32 * world)
+                if (s_fd[f] > 0 && s_fc[f] == c) a2 += s_ff[f];
+        } else {
+            for (int f = rank + lane * world; f < n_feat; f += 32 * world)
                 if (P.f_dof[f] > 0 && P.f_c0[f] == c) a2 += P.f_fro2[f];
-            s_cls[c] = a2;
         }
-        __syncthreads();
-        double* cls = red + (size_t)n * n + n + 8;
-        for (int c = tid; c <= n; c += 128) cls[c] = s_cls[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        if (lane == 0) s_cls[c] = a2;
     }
+    __syncthreads();
+    double* cls = red + (size_t)n * n + n + 8;
+    for (int c = tid; c <= n; c += 128) cls[c] = s_cls[c];
 }
 
 // ================================================================================================
