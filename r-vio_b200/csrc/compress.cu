@@ -6,7 +6,7 @@
 // the kept rows Hn, rn only through  G = Hn^T Hn,  z = Hn^T rn, so the product path keeps its normal-term form
 // (k_gram -> solve) and this file only decides WHICH rows the reference keeps and rewrites [G | z] accordingly:
 //
-//   k_rank_rule   (every updating frame, one CTA)   pivot-free Cholesky of G = R^T R (one thread per row, shared memory),
+//   k_rank_rule   (every updating frame, one CTA)   pivot-free blocked Cholesky of G = R^T R (tile_cholesky.cuh),
 //                 which yields the rows of the reference's trapezoid as long as the leading columns are independent (R is
 //                 unique up to row signs for ANY orthogonal triangularisation) -- the reference's own test (norm < 1e-4)
 //                 applies to them.  At a dependent column the reference's row is a unit combination of the rows still
@@ -22,7 +22,8 @@
 //                 exactly once, by cp.async, a few steps ahead).  Special cases of Eigen's makeGivens (q == 0 -> identity,
 //                 p == 0 -> row swap) are kept exactly: they are what moves the exact zeros around and make the reference's
 //                 outcome deterministic.  Then the first-small-row cut, and [G | z] := kept rows.
-//   k_solve_small_R / k_chol_S + k_trsm   the EKF step itself on the kept rows (Updater.cc:540-619), see below.
+//   k_update_small (<= 14 clones: rule + sweep + EKF step in one launch) / k_chol_S + k_trsm   the EKF step itself on the kept
+//                 rows (Updater.cc:540-619), see below.
 //
 // Both kernels read the mode from device memory (0 = reference rule, 1 = full information: keep [G | z] of all rows), so
 // captured frame graphs stay valid when the mode is switched.
@@ -368,13 +369,14 @@ __global__ void __launch_bounds__(kTrsmWarps * 32) k_trsm(const double* Lt, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_solve_small_R -- the whole EKF step of a small window (n + d + 1 <= 188, i.e. N <= 13) in ONE CTA, R-form
+// k_solve_small_R -- the whole EKF step of a small window (N <= 14 clones) in ONE CTA, R-form
 // (Updater.cc:540-619 with Hn = R, the kept rows handed over by the rank rule, zero rows where a column was dropped):
-//     W = R P[c,:]            (n x d, shared memory, 2 x 4 register tiles)
-//     S = W[:,c] R^T + s^2 I  (n x n, SPD)
-//     [ S ; W^T ; y^T ]  ->  register-resident Cholesky with the d + 1 right-hand sides as extra rows: the extra rows of the
-//                            factor are Y^T = (L^-1 [W | y])^T, i.e. factorisation and triangular solves in the same sweep
-//     dx = Y^T y~ ,  P+ = sym(P) - Y^T Y ,  state correction (quaternions multiplicative, Updater.cc:546-613)
+//     W = R P[c,:]            (n x d: FP64 DMMA tile products, operands as 8 x 8 tiles in shared memory)
+//     S = W[:,c] R^T + s^2 I  (n x n, SPD; DMMA)
+//     [ S ; W^T ; y^T ]  ->  blocked Cholesky (tile_cholesky.cuh) with the d + 1 right-hand sides as extra tile rows: the extra
+//                            rows of the factor are Y^T = (L^-1 [W | y])^T, i.e. factorisation and triangular solves in one sweep
+//     dx = Y^T y~ ,  P+ = sym(P) - Y^T Y (DMMA; P copied into shared memory behind the factorisation),
+//     state correction (quaternions multiplicative, Updater.cc:546-613)
 // Replaces k_wgemm + k_gj_block + k_pout_finalize (three launches, a pivoted Gauss-Jordan on the non-symmetric G Pcc + s^2 I).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sr_quat_mul(const double* q1, const double* q2, double* out)      // Numerics.h:30-63
@@ -783,7 +785,7 @@ __global__ void __launch_bounds__(kGVThreads) k_givens_ref(GivensRefParams Q)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_update_small -- small windows (N <= 12): rank rule, (rarely) the reference's sweep, and the whole EKF step in ONE launch.
+// k_update_small -- small windows (N <= 14 clones): rank rule, (rarely) the reference's sweep, and the whole EKF step in ONE launch.
 // The kept rows of R never leave shared memory (the rule writes them straight into the EKF step's tiles), the sweep's
 // no-op launch between the two and a memset node disappear, and so do two kernel boundaries of the frame's critical path.
 // Dynamic shared memory: [EKF step: T | R / Pc (later P)] [rank rule's factor]; the sweep (when it runs, the rule's factor is

@@ -2140,7 +2140,7 @@ int updater_enqueue_solve(rvio_updater* u, cudaStream_t s, double* x_out_dev, do
         RVIO_ENQ(cudaGetLastError());
         return RVIO_OK;
     }
-    // ---- large windows (N > 13, e.g. the EuRoC default of 14 clones, configs[2] / [4]): the EKF step in the reference's own
+    // ---- large windows (N > 14: configs[2] / [4]): the EKF step in the reference's own
     //      form on the kept rows R (n x n, zero padded; Updater.cc:540-619 with Hn = R):
     //          W = R P[c,:]        S = W[:,c] R^T + s^2 I  (SPD)        S = L L^T        Y = L^-1 [W | y]
     //          dx = Y^T y~         P+ = P - Y^T Y                       (y~ = L^-1 y = last column of Y)
