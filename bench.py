@@ -204,7 +204,7 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
-def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush):
+def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
     """pre-roll until the first valid pose, W warm-up steps, K timed steps (per-step CUDA events on the library's own stream,
     L2 flush between timed steps outside the event pair).  Returns (per-step ms list, wall seconds, launches, frames used)."""
     import torch
@@ -250,9 +250,15 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush):
                 pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
                                     dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
         else:
+            if prefetch and i + 1 < n_frames:
+                # the host announces frame i+1 when it arrives (System::PushImageData), i.e. while frame i is processed: its H2D
+                # copy runs on the library's copy stream inside THIS step's timed region (fenced before the end event below)
+                vio.prefetch(frames[i + 1])
             pose = vio.step(frames[i], imus[i], cands[i], device_detector=inloop)
         if timing:
             wall += time.perf_counter() - t0
+            if prefetch:
+                vio.prefetch_fence()
             ev1[timed].record(stream)
             timed += 1
             ui = vio.update_info()
@@ -288,10 +294,18 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         torch.cuda.synchronize()
 
     with ClockSampler(local_rank) as clk:
-        # ---- e2e leg (host buffers through the public C ABI)
+        # ---- e2e legs (host buffers in pinned memory through the public C ABI).  `e2e`: the host announces frame k+1 while frame
+        #      k is processed (rvio_vio_prefetch: the reference's System::PushImageData moment), so its upload overlaps frame k;
+        #      `e2e.sync`: no announcement, every step uploads its own frame before it can start.
         vio = host.Vio(cfg, local_rank)
         barrier()
-        e2e_ms, e2e_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush)
+        e2s_ms, e2s_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush)
+        barrier()
+        vio.close()
+        vio = host.Vio(cfg, local_rank)
+        barrier()
+        e2e_ms, e2e_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush, prefetch=True)
+        pref_hits = vio.prefetch_fence()
         barrier()
         vio.close()
         # ---- device-resident leg (headline `value`)
@@ -299,6 +313,68 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         barrier()
         dev_ms, dev_wall, launches, used, infos = drive(L, vio, wl, K, W, dev, inloop, True, flush)
         barrier()
+    # ---- bare H2D copy of one frame from pinned memory (what `e2e.sync` adds in front of every step)
+    pin = torch.from_numpy(frames[0]).pin_memory(); dst = torch.empty_like(pin, device=dev)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        dst.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    h0.record()
+    for _ in range(20):
+        dst.copy_(pin, non_blocking=True)
+    h1.record(); torch.cuda.synchronize()
+    h2d_frame_us = 1e3 * h0.elapsed_time(h1) / 20
+    del pin, dst
+
+    # ---- the headline numbers are complete here: reduce them over the ranks NOW, so that nothing an extra leg does can lose them
+    t_dev = float(np.sum(dev_ms)) / 1e3
+    t_e2e = float(np.sum(e2e_ms)) / 1e3
+    t_e2s = float(np.sum(e2s_ms)) / 1e3
+    t_dev_rank, t_e2e_rank = [t_dev], [t_e2e]
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, t_e2s], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)                                           # per-rank times: the slow rank is named in the JSON line
+        t_dev_rank = [float(e[0]) for e in every]; t_e2e_rank = [float(e[1]) for e in every]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_e2s = float(t[0]), float(t[1]), float(t[2])
+    res = dict(t_dev=t_dev, t_e2e=t_e2e, t_e2s=t_e2s, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
+               prof={}, dev_wall=dev_wall, e2e_wall=e2e_wall, e2s_wall=e2s_wall, timeline=None, batch=None, infos=infos,
+               affinity=affinity, sharded=None, t_dev_rank=t_dev_rank, t_e2e_rank=t_e2e_rank, pref_hits=int(pref_hits),
+               h2d_frame_us=h2d_frame_us)
+    _arm_legs_deadline(res, rank)
+
+    # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
+    if rank == 0:
+        tl = np.zeros(8, np.float32)
+        L.rvio_vio_timeline(vio.h, 1, None)
+        acc = []
+        for i in range(used, min(used + 24, n_frames)):
+            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
+            L.rvio_vio_timeline(vio.h, 1, tl.ctypes.data)
+            acc.append(tl.copy())
+        L.rvio_vio_timeline(vio.h, 0, None)
+        used = min(used + 24, n_frames)
+        res["timeline"] = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail",
+                                    "host_enqueue", "host_blocked_in_sync"],
+                                   [round(float(v) * 1e3, 1) for v in np.median(np.array(acc), 0)]))
+    # ---- per-kernel events over a few more steps (roofline leg)
+    if rank == 0:
+        prof = {}
+        L.rvio_b200_profile(1)
+        n_prof = 0
+        for i in range(used, min(used + 24, n_frames)):
+            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
+            n_prof += 1
+        L.rvio_b200_profile(0)
+        buf = C.create_string_buffer(1 << 16)
+        nbytes = L.rvio_b200_profile_report(buf, len(buf))
+        for line in buf.raw[:nbytes].decode().splitlines():
+            name, cnt, tot = line.split()
+            prof[name] = (int(cnt), float(tot), n_prof)
+        res["prof"] = prof
+    vio.close()
+    barrier()
     # ---- batch leg (BASELINE configs[3]: independent streams, several per GPU, no communication): S handles driven by
     #      S host threads on the same device-resident frames; aggregate frames/s over the slowest stream (wall clock
     #      between device synchronisations; the single-stream `value` above is the CUDA-event number).
@@ -333,7 +409,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                     got = True
                 i += 1
             starts.append(i)
-        torch.cuda.synchronize()
+        barrier()                                             # all ranks replay their streams at the same time
         start_bar = threading.Barrier(S + 1); end_bar = threading.Barrier(S + 1)
         errs = []
 
@@ -375,141 +451,26 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                      "timing": "wall clock between device synchronisations, all streams concurrent (graphs captured beforehand, one stream at a time)"}
         else:
             batch = None
-    # ---- feature-sharded single stream (BASELINE configs[4]: 2048 features, 30-clone window): every rank is fed the same
-    #      frames; LK all-gather + normal-term all-reduce are enqueued by the library on its own stream (in the frame graph)
-    sharded = None
-    if world > 1 and not args.no_sharded:
-        try:
-            sharded = sharded_leg(args, L, dev, flush, rank, world, local_rank)
-        except Exception as e:          # pragma: no cover
-            sharded = {"error": repr(e)[:300]}
-        barrier()
-    # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
-    timeline = None
-    if rank == 0:
-        tl = np.zeros(8, np.float32)
-        L.rvio_vio_timeline(vio.h, 1, None)
-        acc = []
-        for i in range(used, min(used + 24, n_frames)):
-            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
-            L.rvio_vio_timeline(vio.h, 1, tl.ctypes.data)
-            acc.append(tl.copy())
-        L.rvio_vio_timeline(vio.h, 0, None)
-        used = min(used + 24, n_frames)
-        timeline = dict(zip(["tracker", "feature+normal_terms", "wait_propagate", "solve", "augment_compose", "tail",
-                             "host_enqueue", "host_blocked_in_sync"],
-                            [round(float(v) * 1e3, 1) for v in np.median(np.array(acc), 0)]))
-    # ---- per-kernel events over a few more steps (roofline leg)
-    prof = {}
-    if rank == 0:
-        L.rvio_b200_profile(1)
-        n_prof = 0
-        for i in range(used, min(used + 24, n_frames)):
-            vio.step(frames[i], imus[i], wl["cand2"][i], device_detector=inloop)
-            n_prof += 1
-        L.rvio_b200_profile(0)
-        buf = C.create_string_buffer(1 << 16)
-        nbytes = L.rvio_b200_profile_report(buf, len(buf))
-        for line in buf.raw[:nbytes].decode().splitlines():
-            name, cnt, tot = line.split()
-            prof[name] = (int(cnt), float(tot), n_prof)
-    vio.close()
-
-    t_dev = float(np.sum(dev_ms)) / 1e3
-    t_e2e = float(np.sum(e2e_ms)) / 1e3
-    t_dev_rank, t_e2e_rank = [t_dev], [t_e2e]
+    res["batch"] = batch
     if world > 1:
-        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-        every = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(every, t)                                           # per-rank times: the slow rank is named in the JSON line
-        t_dev_rank = [float(e[0]) for e in every]; t_e2e_rank = [float(e[1]) for e in every]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(t[0]), float(t[1])
         # every rank takes part in the same collectives, whatever happened to its own batch leg (a rank that skipped one
         # would leave the others waiting in NCCL for ever)
-        b = torch.tensor([batch["value"] if batch is not None else 0.0, 1.0 if batch is not None else 0.0],
-                         dtype=torch.float64, device=dev)
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        if S > 1 and int(round(float(b[1]))) == world and batch is not None:
-            batch["value"] = float(b[0]); batch["n_gpus"] = world
+        bt = torch.tensor([batch["value"] if batch is not None else 0.0, 1.0 if batch is not None else 0.0],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(bt, op=dist.ReduceOp.SUM)
+        if S > 1 and int(round(float(bt[1]))) == world and batch is not None:
+            batch["value"] = float(bt[0]); batch["n_gpus"] = world
         else:
-            batch = None
-    return dict(t_dev=t_dev, t_e2e=t_e2e, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
-                prof=prof, dev_wall=dev_wall, e2e_wall=e2e_wall, timeline=timeline, batch=batch, infos=infos, affinity=affinity, sharded=sharded,
-                t_dev_rank=t_dev_rank, t_e2e_rank=t_e2e_rank)
-
-
-def update_cost_model(rows_per_feat, n, d):
-    """SURVEY 8(d) accounting for one Updater::update: fp32-equivalent flops (Householder accounting for the compression)
-    and algorithmic bytes (float64 here: H written once, read by the gate and by the compression; P in + out)."""
-    r = np.asarray(rows_per_feat, np.float64)
-    R = float(r.sum())
-    f_gate = float((2 * r * n * n + 2 * r * r * n).sum())
-    f_qr = max(0.0, 2 * R * n * n - (2.0 / 3.0) * n ** 3) if R > n else 0.0
-    rk = min(R, n)
-    f_ekf = 4 * d ** 3 + 2 * d * d * rk + 2 * rk ** 3 + 4 * d * n * rk + 2 * d * rk * rk + 2 * rk * n * n + 2 * rk * rk * n
-    return dict(R=int(R), flops=f_gate + f_qr + f_ekf, f_gate=f_gate, f_qr=f_qr, f_ekf=f_ekf,
-                bytes=8.0 * R * n * 3 + 16.0 * d * d)
-
-
-UPDATE_KERNELS = ("k_feature", "k_gate", "k_gram", "k_rank_rule", "k_givens_ref", "k_wgemm", "k_gj_block", "k_pout_finalize", "k_dgemm",
-                  "k_gauss_jordan", "k_finalize", "k_chol", "k_tsqr")
-
-
-def _profile_report(L):
-    import ctypes as C
-    buf = C.create_string_buffer(1 << 16)
-    nbytes = L.rvio_b200_profile_report(buf, len(buf))
-    out = {}
-    for line in buf.raw[:nbytes].decode().splitlines():
-        name, cnt, tot = line.split()
-        out[name] = (int(cnt), float(tot))
-    return out
-
-
-def update_worstcase_leg(L, dev, flush, peaks, idx, reps=4):
-    """SURVEY 8(d) updater micro-benchmark: F_u maximum-length type-'1' tracks (the tallest stacked H of the config):
-    14 700 x 150 (configs[2]) and 60 416 x 180 (configs[4]).  Per-kernel CUDA events inside the library; the update-kernel
-    roofline is algorithmic bytes / flops of the whole update over the summed kernel time."""
-    import torch
-    from rvio_b200 import synth, host
-    cfg = synth.baseline_config(idx)
-    Fu = (cfg.n_features + 1) // 2
-    x, P, types, off, xy = synth.make_update_case(cfg, Fu, 900 + idx, mix_types=False)
-    N = cfg.max_track_len - 1; n = 6 * N; d = 24 + n
-    upd = host.Updater(cfg, dev.index)
-    for _ in range(2):
-        upd.update(x, P, types, (off, xy))
-    info = upd.info
-    dof = upd.debug(len(types))["dof"]
-    L.rvio_b200_profile(1)
-    wall = []
-    for r in range(reps):
-        flush.fill_(r); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        upd.update(x, P, types, (off, xy))
-        wall.append(time.perf_counter() - t0)
-    L.rvio_b200_profile(0)
-    prof = _profile_report(L)
-    upd.close()
-    per = {k: v[1] / reps for k, v in prof.items()}                        # ms per update
-    t_upd = sum(v for k, v in per.items() if any(k.startswith(u) for u in UPDATE_KERNELS)) / 1e3
-    cm = update_cost_model(dof[dof > 0], n, d)
-    gbs = cm["bytes"] / t_upd / 1e9
-    tfl = cm["flops"] / t_upd / 1e12
-    top = max(per, key=per.get)
-    return {"workload": f"BASELINE configs[{idx}] worst-case update: {Fu} type-'1' tracks of length {cfg.max_track_len}, N={N} clones, "
-                        f"stacked H {cm['R']} x {n}, float64", "n_good": int(info.n_good), "rows": int(info.rows_stacked),
-            "rank": int(info.rank), "rank_flags": int(info.rank_flags),
-            "ms_update_kernels": 1e3 * t_upd, "ms_through_c_abi": 1e3 * float(np.median(wall)),
-            "updates_per_s": 1.0 / t_upd,
-            "roofline_update": {"bound": "hbm", "algorithmic_bytes": cm["bytes"], "flops": cm["flops"],
-                                "flops_split": {"gate": cm["f_gate"], "compression_householder": cm["f_qr"], "ekf": cm["f_ekf"]},
-                                "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                                "tflops": tfl, "tensor_peak_tflops_bf16": peaks.get("bf16_tflops"),
-                                "frac_of_tensor_peak": tfl / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
-                                "top_kernel": top},
-            "kernel_us_per_update": {k: round(v * 1e3, 1) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
+            res["batch"] = None
+    # ---- feature-sharded single stream (BASELINE configs[4]: 2048 features, 30-clone window): every rank is fed the same
+    #      frames; LK all-gather + normal-term all-reduce are enqueued by the library on its own stream (in the frame graph)
+    if world > 1 and not args.no_sharded:
+        try:
+            res["sharded"] = sharded_leg(args, L, dev, flush, rank, world, local_rank)
+        except Exception as e:          # pragma: no cover
+            res["sharded"] = {"error": repr(e)[:300]}
+        barrier()
+    return res
 
 
 def sharded_leg(args, L, dev, flush, rank, world, local_rank):
@@ -719,9 +680,87 @@ def _watchdog(seconds):
     faulthandler.dump_traceback_later(seconds, exit=True)
 
 
+# The headline numbers (value, e2e) are complete before any extra leg (timeline, per-kernel profile, batch, sharded stream,
+# stress stream, worst-case updates, CPU baseline) starts.  Should one of those legs wedge (a collective that never returns on
+# some box), the JSON line is still printed from what exists, with the unfinished legs named, and every rank exits 0.
+_LINE_CTX = {}
+_DEADLINE = {"timer": None, "res": None}
+
+
+def _arm_legs_deadline(res, rank):
+    seconds = float(os.environ.get("RVIO_BENCH_LEGS_DEADLINE_S", "420"))
+    _DEADLINE["res"] = res
+
+    def fire():                                               # pragma: no cover
+        import faulthandler
+        faulthandler.dump_traceback(file=sys.stderr)
+        if rank == 0:
+            try:
+                out = build_line(_DEADLINE["res"])
+                out["legs_deadline"] = f"extra legs did not finish within {seconds:.0f} s: line printed from the completed legs"
+                print(json.dumps(out), flush=True)
+            finally:
+                os._exit(0)
+        time.sleep(3.0)
+        os._exit(0)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    _DEADLINE["timer"] = t
+
+
+def _disarm_legs_deadline():
+    if _DEADLINE["timer"] is not None:
+        _DEADLINE["timer"].cancel()
+        _DEADLINE["timer"] = None
+
+
+def build_line(res):
+    """The JSON line from whatever legs have completed (`res` is filled leg by leg)."""
+    c = _LINE_CTX
+    cfg, wl, world, K, W, peaks = c["cfg"], c["wl"], c["world"], c["K"], c["W"], c["peaks"]
+    rf, per_kernel_us = roofline_from_profile(res["prof"], cfg, peaks)
+    n_imu = int(np.median([len(x) for x in wl["imus"][-K:]]))
+    n_cand = int(np.median([len(x) for x in wl["cand2"][-K:]]))
+    h2d = cfg.width * cfg.height + n_imu * 64 + n_cand * 8
+    d2h = 56 + 4 * 46 + 64
+    value = world * K / res["t_dev"]
+    e2e = world * K / res["t_e2e"]
+    out = {"metric": "vio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": 1e3 * res["t_dev"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": c["workload"],
+           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K,
+                   "upload": "host frames in pinned memory; frame k+1 is announced to the library at the start of step k "
+                             "(rvio_vio_prefetch = the host's System::PushImageData moment) and its H2D copy runs on the copy stream "
+                             "inside step k's timed region (the end event is recorded after rvio_vio_prefetch_fence); IMU rows up and "
+                             "pose / counters down inside every step",
+                   "steps_fed_by_prefetch": res["pref_hits"],
+                   "sync": {"value": world * K / res["t_e2s"], "unit": "frames/s", "ms_per_step": 1e3 * res["t_e2s"] / K,
+                            "wall_ms_per_step": 1e3 * res["e2s_wall"] / K,
+                            "what": "no announcement: every step uploads its own frame (pinned, DMA straight into the gray buffer) "
+                                    "before its first kernel can start"},
+                   "h2d_frame_us": round(res["h2d_frame_us"], 2)},
+           "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
+           "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
+           "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"], "sharded": res["sharded"]}
+    out["parallelism"] = f"{world} independent stream(s), one per GPU (no collective on the data path)"
+    out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
+                                   "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}
+    out["cpu_affinity"] = res["affinity"]
+    out["update_frames"] = {"rows_kept_flags": [list(t) for t in res["infos"][:32]],
+                            "note": "(n_feat, accepted, stacked rows, rows kept by the reference's rank rule, flags) per timed step; the "
+                                    "device runs the reference rule (RVIO_RANK_RULE_REFERENCE), the mode the parity tests cover"}
+    for k in ("stress", "update_worstcase", "cpu_baseline"):
+        if k in res:
+            out[k] = res[k]
+    return out
+
+
 def main():
     args = parse()
-    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "900")))
+    _watchdog(int(os.environ.get("RVIO_BENCH_WATCHDOG_S", "780")))
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import rvio_b200  # noqa: F401
@@ -768,39 +807,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = make_workload(cfg, n_frames, SEED + args.config + 1000 * rank + int(os.environ.get("RVIO_BENCH_SEED_OFFSET", "0")),
                        args.detector == "precomputed")
-    res = run_b200(args, cfg, wl, rank, world, local_rank)
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peaks["_measured"] = True
     except Exception:
         peaks = {"hbm_gbs": 6650.0, "_measured": False}
-    rf, per_kernel_us = roofline_from_profile(res["prof"], cfg, peaks)
-    n_imu = int(np.median([len(x) for x in wl["imus"][-K:]]))
-    n_cand = int(np.median([len(x) for x in wl["cand2"][-K:]]))
-    h2d = cfg.width * cfg.height + n_imu * 64 + n_cand * 8
-    d2h = 56 + 4 * 46 + 64
-    value = world * K / res["t_dev"]
-    e2e = world * K / res["t_e2e"]
-    out = {"metric": "vio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-           "ms_per_step": 1e3 * res["t_dev"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": workload,
-           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K},
-           "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
-           "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
-           "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"], "sharded": res["sharded"]}
-    out["parallelism"] = f"{world} independent stream(s), one per GPU (no collective on the data path)"
-    out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
-                                   "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}
-    out["cpu_affinity"] = res["affinity"]
-    out["update_frames"] = {"rows_kept_flags": [list(t) for t in res["infos"][:32]],
-                            "note": "(n_feat, accepted, stacked rows, rows kept by the reference's rank rule, flags) per timed step; the "
-                                    "device runs the reference rule (RVIO_RANK_RULE_REFERENCE), the mode the parity tests cover"}
+    _LINE_CTX.update(cfg=cfg, wl=wl, world=world, K=K, W=W, peaks=peaks, workload=workload)
+    res = run_b200(args, cfg, wl, rank, world, local_rank)
+    if rank != 0:
+        _disarm_legs_deadline()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     if world == 1 and not args.no_extra_legs:
         import torch as _t
         from rvio_b200 import capi as _capi
@@ -808,25 +827,26 @@ def main():
         fl = _t.empty(384 << 20, dtype=_t.uint8, device=dev)
         Lb = _capi.lib()
         try:
-            out["stress"] = stress_leg(args, Lb, dev, fl, peaks, rank)
+            res["stress"] = stress_leg(args, Lb, dev, fl, peaks, rank)
         except Exception as e:          # pragma: no cover
-            out["stress"] = {"error": repr(e)[:200]}
-        out["update_worstcase"] = {}
+            res["stress"] = {"error": repr(e)[:200]}
+        res["update_worstcase"] = {}
         for idx in (2, 4):
             try:
-                out["update_worstcase"][f"configs[{idx}]"] = update_worstcase_leg(Lb, dev, fl, peaks, idx)
+                res["update_worstcase"][f"configs[{idx}]"] = update_worstcase_leg(Lb, dev, fl, peaks, idx)
             except Exception as e:      # pragma: no cover
-                out["update_worstcase"][f"configs[{idx}]"] = {"error": repr(e)[:200]}
+                res["update_worstcase"][f"configs[{idx}]"] = {"error": repr(e)[:200]}
         del fl
     if not args.no_cpu_baseline and world == 1:
         steps = 60
         wl2 = {k: (v[:int(T_STATIC * cfg.fps) + 4 + W + steps + 4] if isinstance(v, list) else v) for k, v in wl.items()}
         r = run_reference(cfg, wl2, steps, min(W, 10), ncores, args.detector == "inloop")
         import cv2
-        out["cpu_baseline"] = {"value": r["steps"] / r["t"], "unit": "frames/s", "cores": ncores, "kind": "port",
+        res["cpu_baseline"] = {"value": r["steps"] / r["t"], "unit": "frames/s", "cores": ncores, "kind": "port",
                                "sample": f"{r['steps']} frames of the same stream; OpenCV stages via cv2 {cv2.__version__} ({ncores} threads), "
                                          f"Eigen stages via oracle C port (1 thread); median tracker {r['tracker_ms']:.3f} ms, filter {r['filter_ms']:.3f} ms"}
-    print(json.dumps(out))
+    _disarm_legs_deadline()
+    print(json.dumps(build_line(res)), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

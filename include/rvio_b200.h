@@ -228,6 +228,16 @@ int rvio_vio_step(rvio_vio* vio, const uint8_t* img, int width, int height, int 
 /* Same with the (single-channel) image and the candidate list already in device memory. */
 int rvio_vio_step_dev(rvio_vio* vio, const uint8_t* img_dev, int pitch_bytes, const double* imu, int n_imu,
                       const float* cand_px_dev, int n_cand, int cand_filtered, double* pose_out, int* pose_valid);
+/* Optional: announce a frame ahead of its step -- the moment the reference's host receives it (System::PushImageData,
+ * src/rvio/System.h:50, InputBuffer.cc:42), one or two frames before System::MonoVIO pops it (System.cc:176-181).  A
+ * single-channel frame in PINNED host memory is uploaded at once on a copy stream, beside the frame being processed; the
+ * rvio_vio_step that is later handed the same buffer (within the next two steps, contents unchanged) takes the uploaded copy
+ * instead of uploading inside the step.  Any other frame (colour, pageable) is left to the step: the call does nothing.
+ * Results are identical with or without the announcement. */
+int rvio_vio_prefetch(rvio_vio* vio, const uint8_t* img, int width, int height, int stride_bytes, int channels);
+/* Measurement aid: orders the pipeline's stream after the most recent rvio_vio_prefetch upload (no host blocking), so that an
+ * event recorded on rvio_tracker_stream afterwards bounds the upload; *hits (optional) = steps that consumed a prefetched frame. */
+int rvio_vio_prefetch_fence(rvio_vio* vio, uint64_t* hits);
 /* Filter state after the last step: x (26+7N), P (d x d column-major). */
 int rvio_vio_get_state(rvio_vio* vio, double* x, int* xdim, double* P, int* d);
 /* Update counters of the last step (n_feat = 0 when no update ran). */

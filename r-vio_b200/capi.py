@@ -52,7 +52,7 @@ SYMBOLS = [
     "rvio_updater_create", "rvio_updater_destroy", "rvio_updater_update", "rvio_updater_update_from_tracker",
     "rvio_updater_get_debug", "rvio_updater_get_normal_terms", "rvio_updater_update_begin",
     "rvio_updater_reduce_buffer", "rvio_updater_update_finish", "rvio_updater_set_rank_rule",
-    "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_get_state",
+    "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_prefetch", "rvio_vio_prefetch_fence", "rvio_vio_get_state",
     "rvio_vio_get_update_info", "rvio_vio_shard_init", "rvio_vio_shard_probe", "rvio_b200_nccl_unique_id", "rvio_vio_tracker", "rvio_vio_updater", "rvio_vio_timeline", "rvio_vio_graphs",
     "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
     "rvio_tracker_stream", "rvio_updater_stream", "rvio_b200_profile", "rvio_b200_profile_report",
@@ -111,6 +111,8 @@ def lib():
     L.rvio_vio_destroy.restype = None
     L.rvio_vio_step.argtypes = [vp, u8, ci, ci, ci, ci, vp, ci, vp, ci, ci, f64, pi]
     L.rvio_vio_step_dev.argtypes = [vp, vp, ci, vp, ci, vp, ci, ci, f64, pi]
+    L.rvio_vio_prefetch.argtypes = [vp, u8, ci, ci, ci, ci]
+    L.rvio_vio_prefetch_fence.argtypes = [vp, vp]
     L.rvio_vio_get_state.argtypes = [vp, vp, pi, vp, pi]
     L.rvio_vio_get_update_info.argtypes = [vp, C.POINTER(UpdateInfo)]
     L.rvio_vio_shard_init.argtypes = [vp, ci, ci, vp]

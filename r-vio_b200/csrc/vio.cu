@@ -69,6 +69,11 @@ struct rvio_vio {
     bool timeline; cudaEvent_t tl[8]; float tl_ms[8];   // optional per-stage stamps on the main stream
     unsigned long long* d_stamps; unsigned long long h_stamps[8];
     std::unordered_map<const void*, bool> pin_cache;   // is this host frame buffer pinned? (cudaPointerGetAttributes, asked once per address)
+    // rvio_vio_prefetch: a frame announced ahead of its step (System::PushImageData time) is uploaded on a copy stream into one
+    // of two device slots while the previous frame is still being processed; the step that is later handed the same host
+    // buffer takes the slot instead of uploading
+    cudaStream_t copys; cudaEvent_t ev_pref[2]; uint8_t* d_pref[2]; const uint8_t* pref_src[2]; int pref_next, pref_last;
+    uint64_t pref_hits, pref_step[2], n_steps;    // a slot is honoured by the next two steps only (a forgotten announcement expires)
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
@@ -235,6 +240,8 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_side_done, cudaEventDisableTiming));
     v->timeline = false;
     v->use_graphs = true; v->graph_launches = 0;
+    v->copys = nullptr; v->pref_next = 0; v->pref_last = -1; v->pref_hits = 0; v->n_steps = 0; v->pref_step[0] = v->pref_step[1] = 0;
+    for (int k = 0; k < 2; ++k) { v->ev_pref[k] = nullptr; v->d_pref[k] = nullptr; v->pref_src[k] = nullptr; }
     for (int k = 0; k < 8; ++k) { RVIO_CUDA_TRY(cudaEventCreate(&v->tl[k])); v->tl_ms[k] = 0.f; }
     RVIO_CUDA_TRY(cudaMalloc((void**)&v->d_stamps, sizeof(unsigned long long) * 8));
     RVIO_CUDA_TRY(cudaMemset(v->d_stamps, 0, sizeof(unsigned long long) * 8));
@@ -282,6 +289,11 @@ extern "C" void rvio_vio_destroy(rvio_vio* v)
     cudaSetDevice(v->device);
     cudaStreamSynchronize(v->stream);
     cudaStreamSynchronize(v->side);
+    if (v->copys) {
+        cudaStreamSynchronize(v->copys);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(v->ev_pref[k]); cudaFree(v->d_pref[k]); }
+        cudaStreamDestroy(v->copys);
+    }
     for (auto& kv : v->graphs) cudaGraphExecDestroy(kv.second);
     cudaEventDestroy(v->ev_frame_in); cudaEventDestroy(v->ev_prop_done); cudaEventDestroy(v->ev_bookkeep_done); cudaEventDestroy(v->ev_side_done);
     cudaStreamDestroy(v->side); cudaStreamDestroy(v->dets); cudaEventDestroy(v->ev_det_done);
@@ -454,6 +466,18 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     return rsc;
 }
 
+// a driver call: its answer is remembered per buffer address
+static bool host_buffer_is_pinned(rvio_vio* v, const uint8_t* p)
+{
+    auto pc = v->pin_cache.find(p);
+    if (pc != v->pin_cache.end()) return pc->second;
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    if (v->pin_cache.size() < 4096) v->pin_cache.emplace(p, pinned);
+    return pinned;
+}
+
 static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int height, int stride, int channels,
                          const uint8_t* img_dev, int pitch, const double* imu, int n_imu,
                          const float* cand_host, const float* cand_dev_in, int n_cand, int cand_filtered,
@@ -510,15 +534,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
             // a single-channel frame in PINNED host memory (cudaHostAlloc / cudaHostRegister by the caller) is DMA'd straight
             // into the pipeline's gray buffer: no staging copy on the host; the frame graph then runs its "staged" variant
             // (the attribute query is a driver call: its answer is remembered per buffer address)
-            bool pinned;
-            auto pc = v->pin_cache.find(img_host);
-            if (pc != v->pin_cache.end()) pinned = pc->second;
-            else {
-                cudaPointerAttributes pa;
-                pinned = cudaPointerGetAttributes(&pa, img_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-                if (!pinned) cudaGetLastError();
-                if (v->pin_cache.size() < 4096) v->pin_cache.emplace(img_host, pinned);
-            }
+            const bool pinned = host_buffer_is_pinned(v, img_host);
             if (pinned) {
                 size_t gp; uint8_t* g = tracker_gray(v->trk, &gp);
                 const size_t wbytes = (size_t)v->cfg.tracker.width;
@@ -605,11 +621,64 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
     return RVIO_OK;
 }
 
+// Upload of a frame ahead of its step (the host's System::PushImageData moment, System.h:50 / InputBuffer.cc:42): the H2D copy
+// runs on a copy stream beside the frame that is being processed.  Only for single-channel frames in pinned host memory
+// (anything else is left to the step itself and the call is a no-op); at most two frames are kept.
+extern "C" int rvio_vio_prefetch(rvio_vio* v, const uint8_t* img, int width, int height, int stride_bytes, int channels)
+{
+    RVIO_ARG_CHECK(v && img && width == v->cfg.tracker.width && height == v->cfg.tracker.height && stride_bytes >= width);
+    if (channels != 1) return RVIO_OK;
+    RVIO_CUDA_TRY(cudaSetDevice(v->device));
+    if (!host_buffer_is_pinned(v, img)) return RVIO_OK;
+    const size_t W = (size_t)width, H = (size_t)height;
+    if (!v->copys) {
+        RVIO_CUDA_TRY(cudaStreamCreateWithFlags(&v->copys, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RVIO_CUDA_TRY(cudaEventCreateWithFlags(&v->ev_pref[k], cudaEventDisableTiming));
+            RVIO_CUDA_TRY(cudaMalloc((void**)&v->d_pref[k], W * H));
+        }
+    }
+    int slot = v->pref_next;
+    for (int k = 0; k < 2; ++k) if (v->pref_src[k] == img) slot = k;      // announced twice: refresh the same slot
+    v->pref_next = 1 - slot;
+    // (the slot's previous reader, a step's device-to-device copy on the main stream, has completed: steps are synchronous)
+    RVIO_CUDA_TRY(cudaMemcpy2DAsync(v->d_pref[slot], W, img, (size_t)stride_bytes, W, H, cudaMemcpyHostToDevice, v->copys));
+    RVIO_CUDA_TRY(cudaEventRecord(v->ev_pref[slot], v->copys));
+    v->pref_src[slot] = img; v->pref_last = slot; v->pref_step[slot] = v->n_steps;
+    return RVIO_OK;
+}
+
+// Orders the pipeline's stream after the most recent prefetch (no host blocking): measurement code records its end-of-step
+// event after this so that the upload provably lies inside the timed region.
+extern "C" int rvio_vio_prefetch_fence(rvio_vio* v, uint64_t* hits)
+{
+    RVIO_ARG_CHECK(v);
+    if (hits) *hits = v->pref_hits;
+    if (v->copys && v->pref_last >= 0) {
+        RVIO_CUDA_TRY(cudaSetDevice(v->device));
+        RVIO_CUDA_TRY(cudaStreamWaitEvent(v->stream, v->ev_pref[v->pref_last], 0));
+    }
+    return RVIO_OK;
+}
+
 extern "C" int rvio_vio_step(rvio_vio* v, const uint8_t* img, int width, int height, int stride_bytes, int channels,
                              const double* imu, int n_imu, const float* cand_px, int n_cand, int cand_filtered,
                              double* pose_out, int* pose_valid)
 {
     RVIO_ARG_CHECK(v && img && (n_cand <= 0 || cand_px));
+    const uint64_t step_no = v->n_steps++;
+    if (v->copys && channels == 1 && n_imu >= 2)
+        for (int k = 0; k < 2; ++k)
+            if (v->pref_src[k] && step_no - v->pref_step[k] > 1) v->pref_src[k] = nullptr;      // expired
+            else if (v->pref_src[k] == img) {             // uploaded ahead of time by rvio_vio_prefetch: take the device slot
+                v->pref_src[k] = nullptr;
+                RVIO_ARG_CHECK(width == v->cfg.tracker.width && height == v->cfg.tracker.height);
+                RVIO_CUDA_TRY(cudaSetDevice(v->device));
+                RVIO_CUDA_TRY(cudaStreamWaitEvent(v->stream, v->ev_pref[k], 0));
+                v->pref_hits++;
+                return vio_step_impl(v, nullptr, width, height, stride_bytes, 1, v->d_pref[k], width, imu, n_imu, cand_px, nullptr,
+                                     n_cand, cand_filtered, pose_out, pose_valid);
+            }
     return vio_step_impl(v, img, width, height, stride_bytes, channels, nullptr, 0, imu, n_imu, cand_px, nullptr, n_cand,
                          cand_filtered, pose_out, pose_valid);
 }

@@ -318,6 +318,17 @@ class Vio:
                                                        1 if cand_filtered else 0, self._pose, C.byref(self._valid)), "rvio_vio_step")
         return self._pose.copy() if self._valid.value else None
 
+    def prefetch(self, im):
+        """Announce a frame ahead of its step (System::PushImageData time): a pinned single-channel frame is uploaded beside the
+        frame being processed; `step` with the same buffer then skips its own upload (rvio_vio_prefetch)."""
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        capi.check(self.L.rvio_vio_prefetch(self.h, im.reshape(-1), im.shape[1], im.shape[0], im.strides[0], ch), "rvio_vio_prefetch")
+
+    def prefetch_fence(self) -> int:
+        n = C.c_uint64()
+        capi.check(self.L.rvio_vio_prefetch_fence(self.h, C.byref(n)), "rvio_vio_prefetch_fence")
+        return int(n.value)
+
     def step_dev(self, img_dev_ptr, pitch, imu, cand_dev_ptr=None, n_cand=0, cand_filtered=False):
         imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 8)
         capi.check(self.L.rvio_vio_step_dev(self.h, img_dev_ptr, pitch, imu.ctypes.data, len(imu), cand_dev_ptr, n_cand,

@@ -143,3 +143,65 @@ def test_run_asl_tool_matches_oracle_loop(tmp_path):
     assert np.array_equal(got[:, 0], want[:, 0])                      # stamps
     assert np.abs(got[:, 1:4] - want[:, 1:4]).max() < 1e-7            # positions
     assert np.abs(np.abs(np.sum(got[:, 4:] * want[:, 4:], axis=1)) - 1).max() < 1e-12     # quaternions (sign-free)
+
+
+def test_prefetch_gives_identical_poses():
+    """rvio_vio_prefetch (frame announced one step ahead, uploaded on the copy stream) must not change a single bit of the
+    pose stream; steady frames must actually consume the uploaded copies; an announcement that is not used within two
+    steps expires (the buffer may have been recycled by the host)."""
+    import torch
+    cfg = synth.baseline_config(1)
+    st = synth.Stream(cfg, 70, 20260925, t_static=0.5)
+    consumed, imus = 0, []
+    for i in range(st.n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        imus.append(imu)
+    keep = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory() for f in st.frames]
+    frames = [k.numpy() for k in keep]
+
+    def run(prefetch):
+        g = host.Vio(cfg)
+        out = []
+        if prefetch:
+            g.prefetch(frames[0])
+        for i in range(st.n_frames):
+            if prefetch and i + 1 < st.n_frames:
+                g.prefetch(frames[i + 1])
+            out.append(g.step(frames[i], imus[i], None, device_detector=True))
+        hits = g.prefetch_fence()
+        x, P = g.state()
+        g.close()
+        return out, hits, x, P
+
+    p0, h0, x0, P0 = run(False)
+    p1, h1, x1, P1 = run(True)
+    assert h0 == 0 and h1 >= st.n_frames - 12, (h0, h1)          # frames before the IMU has two samples are not steps
+    assert sum(p is not None for p in p0) > 40
+    for a, b in zip(p0, p1):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b)
+    assert np.array_equal(x0, x1) and np.array_equal(P0, P1)
+
+    # expiry: announce a buffer, step three OTHER frames, then hand the announced buffer in with new contents
+    g = host.Vio(cfg)
+    ref = host.Vio(cfg)
+    for i in range(40):
+        g.step(frames[i], imus[i], None, device_detector=True)
+        ref.step(frames[i], imus[i], None, device_detector=True)
+    scratch = torch.from_numpy(frames[5].copy()).pin_memory()
+    sbuf = scratch.numpy()
+    g.prefetch(sbuf)
+    for i in range(40, 43):
+        g.step(frames[i], imus[i], None, device_detector=True)
+        ref.step(frames[i], imus[i], None, device_detector=True)
+    sbuf[:] = frames[43]
+    a = g.step(sbuf, imus[43], None, device_detector=True)
+    b = ref.step(frames[43], imus[43], None, device_detector=True)
+    assert a is not None and np.array_equal(a, b)
+    for i in range(44, 50):
+        a = g.step(frames[i], imus[i], None, device_detector=True)
+        b = ref.step(frames[i], imus[i], None, device_detector=True)
+        assert np.array_equal(a, b)
+    assert g.prefetch_fence() == 0
+    g.close(); ref.close()
