@@ -33,6 +33,12 @@ if ROOT not in sys.path:
 
 SEED = 20260922
 T_STATIC = 0.5
+# Seed of the configs[4] stream of the `sharded` leg.  The reference's motion detector (System.cc:203-214: 0.005 rad or 1 cm inside ONE
+# frame interval) fires late on these gently ramped trajectories, and the filter then starts from "at rest" with whatever velocity the
+# trajectory already has; with SEED + 4 that is 1.1 m/s at frame 28: the filter never recovers, LM / the gate reject every track (in the
+# CPU oracle alike) and the update is a pass-through.  20260953 is detected at frame 20 with 0.07 m/s: every track is accepted and the
+# window-full frames carry 500-1000 features (stacked H up to 60 000 x 180) -- the update the sharding is meant for.
+SHARDED_SEED = 20260953
 
 
 def parse():
@@ -314,7 +320,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         dev_ms, dev_wall, launches, used, infos = drive(L, vio, wl, K, W, dev, inloop, True, flush)
         barrier()
     # ---- bare H2D copy of one frame from pinned memory (what `e2e.sync` adds in front of every step)
-    pin = torch.from_numpy(frames[0]).pin_memory(); dst = torch.empty_like(pin, device=dev)
+    pin = torch.from_numpy(frames[0]).pin_memory(); dst = torch.empty(pin.shape, dtype=pin.dtype, device=dev)
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         dst.copy_(pin, non_blocking=True)
@@ -482,7 +488,7 @@ def sharded_leg(args, L, dev, flush, rank, world, local_rank):
     from rvio_b200 import synth, host
     cfg = synth.baseline_config(4)
     Ks, Ws = min(args.steps, 20), cfg.max_track_len + 6
-    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 20, SEED + 4, False)      # same seed on every rank: same frames
+    wl = make_workload(cfg, int(T_STATIC * cfg.fps) + 4 + Ws + Ks + 20, SHARDED_SEED, False)  # same seed on every rank: same frames
     uid = torch.zeros(128, dtype=torch.uint8, device=dev)
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=torch.uint8))
@@ -749,6 +755,11 @@ def build_line(res):
     out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
                                    "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}
     out["cpu_affinity"] = res["affinity"]
+    try:
+        from rvio_b200 import capi as _capi
+        out["pdl"] = bool(_capi.lib().rvio_b200_pdl(-1))      # programmatic dependent launch between the frame's short dependent kernels
+    except Exception:                                          # pragma: no cover
+        out["pdl"] = None
     out["update_frames"] = {"rows_kept_flags": [list(t) for t in res["infos"][:32]],
                             "note": "(n_feat, accepted, stacked rows, rows kept by the reference's rank rule, flags) per timed step; the "
                                     "device runs the reference rule (RVIO_RANK_RULE_REFERENCE), the mode the parity tests cover"}
@@ -768,7 +779,7 @@ def main():
     cfg = synth.baseline_config(args.config)
     K, W = args.steps, max(args.warmup, 3)
     args.warmup = W
-    n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 40
+    n_frames = int(T_STATIC * cfg.fps) + 4 + W + K + 80        # pre-roll (first pose ~ frame 21), warm-up, timed steps, 2 x 24 steps of the timeline / profile legs
     workload = {"workload": f"BASELINE configs[{args.config}]: synthetic EuRoC-shaped {cfg.width}x{cfg.height} mono + 200 Hz IMU stream, "
                             f"{cfg.n_features} features, {cfg.max_track_len - 1}-clone window, 1 frame per step",
                 "detector": ("FeatureDetector::DetectWithSubPix inside every timed step (whole Tracker::track): device kernels in this arm, "

@@ -278,6 +278,11 @@ uint64_t rvio_b200_kernel_launches(void);
 /* Per-kernel CUDA-event timing (bench.py roofline leg): enable, run some steps, then read "kernel count total_ms" lines. */
 void rvio_b200_profile(int enable);
 int rvio_b200_profile_report(char* buf, int cap);
+/* Programmatic dependent launch between the short dependent kernels of a frame (CLAHE -> pyramid -> LK -> RANSAC -> per-feature
+ * -> normal terms): each of them becomes resident behind its predecessor and blocks in griddepcontrol.wait until that has
+ * completed; results are unchanged, the launch gaps go.  enable: 1 / 0, negative = query; returns the previous setting.
+ * Process-wide; the environment variable RVIO_B200_PDL sets the initial value. */
+int rvio_b200_pdl(int enable);
 /* Raw CUDA stream used by a handle (so a host can order its own work / events against it). */
 void* rvio_tracker_stream(rvio_tracker* trk);
 void* rvio_updater_stream(rvio_updater* upd);

@@ -54,7 +54,7 @@ SYMBOLS = [
     "rvio_updater_reduce_buffer", "rvio_updater_update_finish", "rvio_updater_set_rank_rule",
     "rvio_vio_create", "rvio_vio_destroy", "rvio_vio_step", "rvio_vio_step_dev", "rvio_vio_prefetch", "rvio_vio_prefetch_fence", "rvio_vio_get_state",
     "rvio_vio_get_update_info", "rvio_vio_shard_init", "rvio_vio_shard_probe", "rvio_b200_nccl_unique_id", "rvio_vio_tracker", "rvio_vio_updater", "rvio_vio_timeline", "rvio_vio_graphs",
-    "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches",
+    "rvio_b200_version", "rvio_b200_last_error", "rvio_b200_kernel_launches", "rvio_b200_pdl",
     "rvio_tracker_stream", "rvio_updater_stream", "rvio_b200_profile", "rvio_b200_profile_report",
 ]
 
@@ -127,6 +127,7 @@ def lib():
     L.rvio_b200_version.restype = C.c_char_p
     L.rvio_b200_last_error.restype = C.c_char_p
     L.rvio_b200_kernel_launches.restype = C.c_uint64
+    L.rvio_b200_pdl.argtypes = [ci]
     L.rvio_b200_profile.argtypes = [ci]
     L.rvio_b200_profile.restype = None
     L.rvio_b200_profile_report.argtypes = [C.c_char_p, ci]

@@ -1,5 +1,6 @@
 // api_misc.cu -- library-wide state: error text, launch counter, device check, version.
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -13,6 +14,8 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 std::atomic<int> g_profile_on{0};
 thread_local bool t_replay = false;
+static int pdl_default() { const char* e = getenv("RVIO_B200_PDL"); return e ? (atoi(e) != 0) : 0; }
+std::atomic<int> g_pdl_on{pdl_default()};
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
@@ -58,6 +61,12 @@ int require_b200(int device)
 extern "C" const char* rvio_b200_version(void) { return "rvio_b200 0.1 (sm_100a)"; }
 extern "C" const char* rvio_b200_last_error(void) { return rvio::g_last_error; }
 extern "C" uint64_t rvio_b200_kernel_launches(void) { return rvio::g_kernel_launches.load(); }
+
+extern "C" int rvio_b200_pdl(int enable)
+{
+    if (enable < 0) return rvio::g_pdl_on.load();
+    return rvio::g_pdl_on.exchange(enable ? 1 : 0);
+}
 
 extern "C" void rvio_b200_profile(int enable)
 {

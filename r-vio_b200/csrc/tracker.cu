@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(1024) k_clahe_lut(const uint8_t* __restrict__ 
                                                     int tw, int th, int clip, float lut_scale,
                                                     uint8_t* __restrict__ lut /* 25 x 256 */)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     __shared__ int hist[256];
     __shared__ int sh[34];
     const int tid = threadIdx.x;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__
                                                      const uint8_t* __restrict__ lut, float inv_tw, float inv_th,
                                                      PyrLevel dst)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     __shared__ uint8_t slut[25 * 256];
     for (int i = threadIdx.x; i < 25 * 256 / 4; i += blockDim.x)
         reinterpret_cast<uint32_t*>(slut)[i] = reinterpret_cast<const uint32_t*>(lut)[i];
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__
 // Equalizer off: plain copy into level 0 (with border).
 __global__ void k_copy_level0(const uint8_t* __restrict__ src, int pitch, PyrLevel dst)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dst.w) return;
     store_with_border(dst, x, y, src[(size_t)y * pitch + x]);
@@ -136,6 +139,7 @@ __global__ void k_copy_level0(const uint8_t* __restrict__ src, int pitch, PyrLev
 // cv::pyrDown: separable [1 4 6 4 1], BORDER_REFLECT_101 (read from the source border), (sum+128)>>8.
 __global__ void __launch_bounds__(256) k_pyr_down(PyrLevel src, PyrLevel dst)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dst.w) return;
     const uint8_t* s = src.base + (ptrdiff_t)(2 * y - 2) * src.pitch + (2 * x - 2);
@@ -181,6 +185,7 @@ __device__ __forceinline__ void pyr_down_region(const uint8_t* src, int sox, int
 }
 __global__ void __launch_bounds__(256) k_pyr_down3(PyrLevel l0, PyrLevel l1, PyrLevel l2, PyrLevel l3)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     __shared__ uint8_t s0[85 * 88], s1[41 * 44], s2[19 * 20], s3[8 * 8];
     const int X3 = 8 * blockIdx.x, Y3 = 8 * blockIdx.y;
     const int o2x = 2 * X3 - 2, o2y = 2 * Y3 - 2, o1x = 2 * o2x - 2, o1y = 2 * o2y - 2, o0x = 2 * o1x - 2, o0y = 2 * o1y - 2;
@@ -301,6 +306,7 @@ __device__ __forceinline__ void lk_stage_tile(const PyrLevel& J, int tx0, int ty
 
 __global__ void __launch_bounds__(kLKWarps * 32) k_lk(LKParams P, const __grid_constant__ LKTmaps M)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     __shared__ LKWarpSmem smem_all[kLKWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pt = P.first + blockIdx.x * kLKWarps + wib;
@@ -888,6 +894,7 @@ __device__ __forceinline__ void bookkeep_body(const TrackerBuffers& B, int n)
 // RANSAC followed by the bookkeeping in ONE single-CTA launch (Tracker.cc:264-342).
 __global__ void __launch_bounds__(256) k_ransac_bookkeep(RansacParams P)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     const int n = P.n_dev ? *P.n_dev : P.n;       // read before anything below rewrites the scalars
     ransac_body(P, n);
     __syncthreads();
@@ -1238,18 +1245,18 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
     // Tracker.cc:198-202
     if (t->cfg.enable_equalizer) {
         RVIO_LAUNCH(k_clahe_lut, 25, 1024, 0, s, gray_dev, gray_pitch, t->W, t->H, t->tw, t->th, t->clip, t->lut_scale, t->d_lut);
-        RVIO_LAUNCH(k_clahe_apply, grd, blk, 0, s, gray_dev, gray_pitch, t->d_lut, t->inv_tw, t->inv_th, cur.lv[0]);
+        RVIO_LAUNCH_PDL(true, k_clahe_apply, grd, blk, 0, s, gray_dev, gray_pitch, t->d_lut, t->inv_tw, t->inv_th, cur.lv[0]);
     } else {
         RVIO_LAUNCH(k_copy_level0, grd, blk, 0, s, gray_dev, gray_pitch, cur.lv[0]);
     }
     RVIO_ENQ(cudaEventRecord(t->ev_level0, s));            // what the detector needs (Tracker.cc:207,350 pass the equalised image)
     if (cur.levels == 4) {
         const dim3 g(div_up(cur.lv[3].w, 8), div_up(cur.lv[3].h, 8));
-        RVIO_LAUNCH(k_pyr_down3, g, blk, 0, s, cur.lv[0], cur.lv[1], cur.lv[2], cur.lv[3]);
+        RVIO_LAUNCH_PDL(true, k_pyr_down3, g, blk, 0, s, cur.lv[0], cur.lv[1], cur.lv[2], cur.lv[3]);
     } else {
         for (int l = 1; l < cur.levels; ++l) {
             const dim3 g(div_up(cur.lv[l].w, 256), cur.lv[l].h);
-            RVIO_LAUNCH(k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
+            RVIO_LAUNCH_PDL(true, k_pyr_down, g, blk, 0, s, cur.lv[l - 1], cur.lv[l]);
         }
     }
     t->frame_open = true;
@@ -1270,12 +1277,12 @@ static int tracker_enqueue(rvio_tracker* t, const uint8_t* gray_dev, int gray_pi
         lp.first = shard_rank * S; lp.last = lp.first + S;
         n_lk = S;
     }
-    RVIO_LAUNCH(k_lk, div_up(n_lk, kLKWarps), kLKWarps * 32, 0, s, lp, t->tmaps[t->cur_idx]);
+    RVIO_LAUNCH_PDL(true, k_lk, div_up(n_lk, kLKWarps), kLKWarps * 32, 0, s, lp, t->tmaps[t->cur_idx]);
     if (!finish) { RVIO_ENQ(cudaGetLastError()); return RVIO_OK; }
     RansacParams rp;
     rp.B = t->B; rp.n = n; rp.n_dev = lp.n_dev; rp.use_sampson = t->cfg.use_sampson;
     rp.thr = t->cfg.inlier_thr; rp.small_angle = t->cfg.small_angle; rp.R = t->h_R;
-    RVIO_LAUNCH(k_ransac_bookkeep, 1, 256, 0, s, rp);
+    RVIO_LAUNCH_PDL(true, k_ransac_bookkeep, 1, 256, 0, s, rp);
     RVIO_ENQ(cudaGetLastError());
     return RVIO_OK;
 }

@@ -155,6 +155,7 @@ constexpr int kSolveSmallMaxClones = 14;     // n = 84 (the EuRoC default window
 
 __global__ void __launch_bounds__(kFeatThreads) k_feature(FeatureParams P)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
     extern __shared__ __align__(16) double sm[];
     __shared__ double s_pf[4];          // phi, psi, rho, (unused)
     __shared__ int s_flag[4];           // [0] reject code, [1] Nc
@@ -879,6 +880,7 @@ __device__ __forceinline__ unsigned long long gram_now() { unsigned long long t;
 #endif
 __global__ void __launch_bounds__(256) k_gram(GramParams P, const uint8_t* f_status, int rank, int world, double* red, int* tickets)
 {
+    rvio::pdl_wait(); rvio::pdl_trigger();      // programmatic dependent launch (common.cuh): nothing above touches memory
 #ifdef RVIO_B200_PHASE_CLOCKS
     const unsigned long long t_in = gram_now();
     if (threadIdx.x == 0) { atomicMin(&g_gram_ns[0], t_in); }
@@ -1904,6 +1906,7 @@ struct rvio_updater {
     double *h_x, *h_P, *h_red; uint8_t* h_types; int32_t* h_off; float* h_xy; int* h_sing; int* h_rule;
     // state of an open begin/finish pair
     int cur_N, cur_xdim, cur_d, cur_nfeat, cur_rank, cur_world; bool open; const int* cur_nfeat_dev;
+    bool pred_is_kernel = false;     // the next updater_enqueue_normal_terms directly follows a kernel on its stream (PDL allowed)
     const double* cur_x_dev; const double* cur_P_dev;
     std::vector<void*> allocs, hallocs;
 };
@@ -2030,6 +2033,8 @@ extern "C" void rvio_updater_destroy(rvio_updater* u)
 // ------------------------------------------------------------------------------------------------
 namespace rvio {
 
+void updater_hint_kernel_predecessor(rvio_updater* u, bool yes) { u->pred_is_kernel = yes; }
+
 int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* x_dev, int xdim, const double* P_dev, int d,
                                  const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev,
                                  int n_feat_cap, const int* n_feat_dev, int rank, int world)
@@ -2053,7 +2058,9 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
         }
         const bool tensor_gate = u->d_Tg != nullptr && n >= u->gate_tensor_min_n;
         fp.gate_mode = tensor_gate ? 1 : 0; fp.f_pend = u->d_fpend;
-        RVIO_LAUNCH(k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
+        // (behind k_ransac_bookkeep in the fused frame: vio.cu says so through updater_hint_kernel_predecessor)
+        RVIO_LAUNCH_PDL(world == 1 && u->pred_is_kernel, k_feature, n_feat_cap, kFeatThreads, u->lay.total_bytes, s, fp);
+        u->pred_is_kernel = false;
         if (tensor_gate) {
             // Updater.cc:416: the per-feature products H~ Pcc as ONE tall GEMM on the tensor cores, then the per-feature gate
             DmmaParams dq;
@@ -2076,7 +2083,7 @@ int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* 
             gp.nt = div_up(n, kGramT);
             RVIO_LAUNCH(k_gram_dmma, dim3(gp.nt * (gp.nt + 1) / 2, gp.groups), 128, kGramDmmaSmem, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
         } else {
-            RVIO_LAUNCH(k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
+            RVIO_LAUNCH_PDL(true, k_gram, dim3(gp.nt * gp.nt, gp.groups), 256, 0, s, gp, u->d_fstatus, rank, world, u->d_red, u->d_tickets);
         }
     } else {
         RVIO_ENQ(cudaMemsetAsync(u->d_red, 0, sizeof(double) * ((size_t)n * n + n + 8 + n + 1), s));

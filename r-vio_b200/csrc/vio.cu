@@ -36,6 +36,7 @@ const TrackerBuffers* tracker_buffers(const rvio_tracker* t);
 cudaStream_t tracker_stream(const rvio_tracker* t);
 const TrackerScalars* tracker_host_scalars(const rvio_tracker* t);
 // updater.cu
+void updater_hint_kernel_predecessor(rvio_updater* u, bool yes);
 int updater_enqueue_normal_terms(rvio_updater* u, cudaStream_t s, const double* x_dev, int xdim, const double* P_dev, int d,
                                  const uint8_t* types_dev, const int32_t* off_dev, const float2* xy_dev,
                                  int n_feat_cap, const int* n_feat_dev, int rank, int world);
@@ -419,6 +420,8 @@ static int enqueue_frame(rvio_vio* v, bool staged, const uint8_t* img_host, int 
     //      IMU block and the cross terms only): they run on the prior buffers, concurrently with k_propagate.
     if (N > v->min_clones) {
         const TrackerBuffers* B = tracker_buffers(v->trk);
+        // k_feature directly follows k_ransac_bookkeep on the main stream unless a candidate upload or a stage stamp sits between
+        updater_hint_kernel_predecessor(v->upd, rc == RVIO_OK && world == 1 && !(n_cand > 0 && cand_upload && !use_det));
         int r2 = updater_enqueue_normal_terms(v->upd, s, v->d_x[xi0], xdim, v->d_P[pi0], d, B->up_types, B->up_off, B->up_xy,
                                               v->Fu, &B->sc->n_up, srank, world);
         if (r2 != RVIO_OK) return r2;
@@ -548,7 +551,7 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
         if (n_cand > 0 && cand_dev_in)
             RVIO_CUDA_TRY(cudaMemcpyAsync(v->d_cand, cand_dev_in, sizeof(float) * 2 * n_cand, cudaMemcpyDeviceToDevice, s));
         const bool staged_in = img_dev != nullptr || host_pinned;
-        const uint64_t key = (uint64_t)use_det << 20 | (uint64_t)(v->timeline ? 1 : 0) << 40 |     // (the stage events are graph nodes of their own variant)
+        const uint64_t key = (uint64_t)use_det << 20 | (uint64_t)(v->timeline ? 1 : 0) << 40 | (uint64_t)(g_pdl_on.load(std::memory_order_relaxed) != 0) << 41 |     // (the stage events are graph nodes of their own variant)
                             
                              (uint64_t)tracker_parity(v->trk) | (uint64_t)v->xi << 1 | (uint64_t)v->pi << 2 | (uint64_t)(n_cand > 0) << 3 |
                              (uint64_t)(cand_filtered != 0) << 4 | (uint64_t)staged_in << 5 | (uint64_t)(channels & 7) << 6 |

@@ -205,3 +205,42 @@ def test_prefetch_gives_identical_poses():
         assert np.array_equal(a, b)
     assert g.prefetch_fence() == 0
     g.close(); ref.close()
+
+
+def test_programmatic_dependent_launch_gives_identical_poses():
+    """rvio_b200_pdl: the short dependent kernels of a frame (CLAHE -> pyramid -> LK -> RANSAC -> per-feature -> normal terms) launched
+    as programmatic dependents (resident early, blocked in griddepcontrol.wait until the predecessor completed) must reproduce the
+    plain stream order bit for bit, eagerly and as replayed frame graphs."""
+    from rvio_b200 import capi
+    L = capi.lib()
+    cfg = synth.baseline_config(1)
+    st = synth.Stream(cfg, 80, 20260923, t_static=0.5)
+    consumed, imus = 0, []
+    for i in range(st.n_frames):
+        imu, consumed = st.imu_for_frame(i, consumed)
+        imus.append(imu)
+
+    def run(pdl, graphs):
+        prev = L.rvio_b200_pdl(1 if pdl else 0)
+        try:
+            g = host.Vio(cfg)
+            if not graphs:
+                capi.check(L.rvio_vio_graphs(g.h, 0, None))
+            out = [g.step(st.frames[i], imus[i], None, device_detector=True) for i in range(st.n_frames)]
+            n_graph = g.graph_launches()
+            x, P = g.state()
+            g.close()
+        finally:
+            L.rvio_b200_pdl(prev)
+        return out, x, P, n_graph
+
+    base, x0, P0, _ = run(False, True)
+    assert sum(p is not None for p in base) > 50
+    for pdl, graphs in ((True, True), (True, False)):
+        out, x, P, n_graph = run(pdl, graphs)
+        assert (n_graph > 30) == graphs
+        for a, b in zip(base, out):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert np.array_equal(a, b), (pdl, graphs)
+        assert np.array_equal(x0, x) and np.array_equal(P0, P)
