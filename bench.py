@@ -210,6 +210,9 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
+_LAST_DRIVE = {}
+
+
 def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
     """pre-roll until the first valid pose, W warm-up steps, K timed steps (per-step CUDA events on the library's own stream,
     L2 flush between timed steps outside the event pair).  Returns (per-step ms list, wall seconds, launches, frames used)."""
@@ -235,6 +238,7 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
     launches0 = None
     wall = 0.0
     infos = []
+    host_tl = np.zeros(8, np.float32); host_us = []
     while timed < K:
         if i >= n_frames:
             raise RuntimeError("stream too short for the requested steps")
@@ -267,6 +271,8 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
                 vio.prefetch_fence()
             ev1[timed].record(stream)
             timed += 1
+            L.rvio_vio_timeline(vio.h, 0, host_tl.ctypes.data)         # host wall clock of the step just finished: [6] enqueue, [7] blocked in the sync
+            host_us.append((1e3 * float(host_tl[6]), 1e3 * float(host_tl[7])))
             ui = vio.update_info()
             infos.append((int(ui.n_feat), int(ui.n_good), int(ui.rows_stacked), int(ui.rank), int(ui.rank_flags)))
         elif got_pose:
@@ -276,6 +282,11 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
         i += 1
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    # where a step's wall time goes on the host: inside the C call, enqueueing (image copy + graph launch) and blocked in its one
+    # synchronisation; what is left of the wall time per step is the Python / ctypes layer around the call
+    _LAST_DRIVE.update(host_enqueue_us=round(float(np.median([h[0] for h in host_us])), 1),
+                       host_blocked_in_sync_us=round(float(np.median([h[1] for h in host_us])), 1),
+                       wall_us=round(1e6 * wall / max(1, K), 1))
     return step_ms, wall, L.rvio_b200_kernel_launches() - launches0, i, infos
 
 
@@ -301,16 +312,18 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
 
     with ClockSampler(local_rank) as clk:
         # ---- e2e legs (host buffers in pinned memory through the public C ABI).  `e2e`: the host announces frame k+1 while frame
-        #      k is processed (rvio_vio_prefetch: the reference's System::PushImageData moment), so its upload overlaps frame k;
-        #      `e2e.sync`: no announcement, every step uploads its own frame before it can start.
+        #      k is processed (rvio_vio_prefetch: the reference's System::PushImageData moment), so its upload overlaps frame k
+        #      (`e2e.announced`); headline `e2e`: no announcement, every step uploads its own frame before it can start.
         vio = host.Vio(cfg, local_rank)
         barrier()
         e2s_ms, e2s_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush)
+        host_e2s = dict(_LAST_DRIVE)
         barrier()
         vio.close()
         vio = host.Vio(cfg, local_rank)
         barrier()
         e2e_ms, e2e_wall, _, _, _ = drive(L, vio, wl, K, W, dev, inloop, False, flush, prefetch=True)
+        host_e2e = dict(_LAST_DRIVE)
         pref_hits = vio.prefetch_fence()
         barrier()
         vio.close()
@@ -318,6 +331,7 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
         vio = host.Vio(cfg, local_rank)
         barrier()
         dev_ms, dev_wall, launches, used, infos = drive(L, vio, wl, K, W, dev, inloop, True, flush)
+        host_dev = dict(_LAST_DRIVE)
         barrier()
     # ---- bare H2D copy of one frame from pinned memory (what `e2e.sync` adds in front of every step)
     pin = torch.from_numpy(frames[0]).pin_memory(); dst = torch.empty(pin.shape, dtype=pin.dtype, device=dev)
@@ -336,18 +350,18 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     t_dev = float(np.sum(dev_ms)) / 1e3
     t_e2e = float(np.sum(e2e_ms)) / 1e3
     t_e2s = float(np.sum(e2s_ms)) / 1e3
-    t_dev_rank, t_e2e_rank = [t_dev], [t_e2e]
+    t_dev_rank, t_e2s_rank = [t_dev], [t_e2s]
     if world > 1:
         t = torch.tensor([t_dev, t_e2e, t_e2s], dtype=torch.float64, device=dev)
         every = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(every, t)                                           # per-rank times: the slow rank is named in the JSON line
-        t_dev_rank = [float(e[0]) for e in every]; t_e2e_rank = [float(e[1]) for e in every]
+        t_dev_rank = [float(e[0]) for e in every]; t_e2s_rank = [float(e[2]) for e in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, t_e2s = float(t[0]), float(t[1]), float(t[2])
     res = dict(t_dev=t_dev, t_e2e=t_e2e, t_e2s=t_e2s, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk.summary(),
                prof={}, dev_wall=dev_wall, e2e_wall=e2e_wall, e2s_wall=e2s_wall, timeline=None, batch=None, infos=infos,
-               affinity=affinity, sharded=None, t_dev_rank=t_dev_rank, t_e2e_rank=t_e2e_rank, pref_hits=int(pref_hits),
-               h2d_frame_us=h2d_frame_us)
+               affinity=affinity, sharded=None, t_dev_rank=t_dev_rank, t_e2s_rank=t_e2s_rank, pref_hits=int(pref_hits),
+               h2d_frame_us=h2d_frame_us, host_us={"value": host_dev, "e2e": host_e2e, "e2e.sync": host_e2s})
     _arm_legs_deadline(res, rank)
 
     # ---- per-stage timeline of the main stream (CUDA events inside the library), a few steps
@@ -477,6 +491,79 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
             res["sharded"] = {"error": repr(e)[:300]}
         barrier()
     return res
+
+
+def update_cost_model(rows_per_feat, n, d):
+    """SURVEY 8(d) accounting for one Updater::update: fp32-equivalent flops (Householder accounting for the compression)
+    and algorithmic bytes (float64 here: H written once, read by the gate and by the compression; P in + out)."""
+    r = np.asarray(rows_per_feat, np.float64)
+    R = float(r.sum())
+    f_gate = float((2 * r * n * n + 2 * r * r * n).sum())
+    f_qr = max(0.0, 2 * R * n * n - (2.0 / 3.0) * n ** 3) if R > n else 0.0
+    rk = min(R, n)
+    f_ekf = 4 * d ** 3 + 2 * d * d * rk + 2 * rk ** 3 + 4 * d * n * rk + 2 * d * rk * rk + 2 * rk * n * n + 2 * rk * rk * n
+    return dict(R=int(R), flops=f_gate + f_qr + f_ekf, f_gate=f_gate, f_qr=f_qr, f_ekf=f_ekf,
+                bytes=8.0 * R * n * 3 + 16.0 * d * d)
+
+
+UPDATE_KERNELS = ("k_feature", "k_gate", "k_gram", "k_rank_rule", "k_givens_ref", "k_wgemm", "k_gj_block", "k_pout_finalize", "k_dgemm",
+                  "k_gauss_jordan", "k_finalize", "k_chol", "k_tsqr")
+
+
+def _profile_report(L):
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    nbytes = L.rvio_b200_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.raw[:nbytes].decode().splitlines():
+        name, cnt, tot = line.split()
+        out[name] = (int(cnt), float(tot))
+    return out
+
+
+def update_worstcase_leg(L, dev, flush, peaks, idx, reps=4):
+    """SURVEY 8(d) updater micro-benchmark: F_u maximum-length type-'1' tracks (the tallest stacked H of the config):
+    14 700 x 150 (configs[2]) and 60 416 x 180 (configs[4]).  Per-kernel CUDA events inside the library; the update-kernel
+    roofline is algorithmic bytes / flops of the whole update over the summed kernel time."""
+    import torch
+    from rvio_b200 import synth, host
+    cfg = synth.baseline_config(idx)
+    Fu = (cfg.n_features + 1) // 2
+    x, P, types, off, xy = synth.make_update_case(cfg, Fu, 900 + idx, mix_types=False)
+    N = cfg.max_track_len - 1; n = 6 * N; d = 24 + n
+    upd = host.Updater(cfg, dev.index)
+    for _ in range(2):
+        upd.update(x, P, types, (off, xy))
+    info = upd.info
+    dof = upd.debug(len(types))["dof"]
+    L.rvio_b200_profile(1)
+    wall = []
+    for r in range(reps):
+        flush.fill_(r); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        upd.update(x, P, types, (off, xy))
+        wall.append(time.perf_counter() - t0)
+    L.rvio_b200_profile(0)
+    prof = _profile_report(L)
+    upd.close()
+    per = {k: v[1] / reps for k, v in prof.items()}                        # ms per update
+    t_upd = sum(v for k, v in per.items() if any(k.startswith(u) for u in UPDATE_KERNELS)) / 1e3
+    cm = update_cost_model(dof[dof > 0], n, d)
+    gbs = cm["bytes"] / t_upd / 1e9
+    tfl = cm["flops"] / t_upd / 1e12
+    top = max(per, key=per.get)
+    return {"workload": f"BASELINE configs[{idx}] worst-case update: {Fu} type-'1' tracks of length {cfg.max_track_len}, N={N} clones, "
+                        f"stacked H {cm['R']} x {n}, float64", "n_good": int(info.n_good), "rows": int(info.rows_stacked),
+            "rank": int(info.rank), "rank_flags": int(info.rank_flags),
+            "ms_update_kernels": 1e3 * t_upd, "ms_through_c_abi": 1e3 * float(np.median(wall)),
+            "updates_per_s": 1.0 / t_upd,
+            "roofline_update": {"bound": "hbm", "algorithmic_bytes": cm["bytes"], "flops": cm["flops"],
+                                "flops_split": {"gate": cm["f_gate"], "compression_householder": cm["f_qr"], "ekf": cm["f_ekf"]},
+                                "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                "tflops": tfl, "tensor_peak_tflops_bf16": peaks.get("bf16_tflops"),
+                                "frac_of_tensor_peak": tfl / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
+                                "top_kernel": top},
+            "kernel_us_per_update": {k: round(v * 1e3, 1) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
 
 
 def sharded_leg(args, L, dev, flush, rank, world, local_rank):
@@ -732,29 +819,28 @@ def build_line(res):
     h2d = cfg.width * cfg.height + n_imu * 64 + n_cand * 8
     d2h = 56 + 4 * 46 + 64
     value = world * K / res["t_dev"]
-    e2e = world * K / res["t_e2e"]
+    e2e = world * K / res["t_e2s"]                            # headline e2e: the strict form (no announcement)
     out = {"metric": "vio_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": 1e3 * res["t_dev"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": c["workload"],
            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": 1e3 * res["t_e2e"] / K, "wall_ms_per_step": 1e3 * res["e2e_wall"] / K,
-                   "upload": "host frames in pinned memory; frame k+1 is announced to the library at the start of step k "
-                             "(rvio_vio_prefetch = the host's System::PushImageData moment) and its H2D copy runs on the copy stream "
-                             "inside step k's timed region (the end event is recorded after rvio_vio_prefetch_fence); IMU rows up and "
-                             "pose / counters down inside every step",
-                   "steps_fed_by_prefetch": res["pref_hits"],
-                   "sync": {"value": world * K / res["t_e2s"], "unit": "frames/s", "ms_per_step": 1e3 * res["t_e2s"] / K,
-                            "wall_ms_per_step": 1e3 * res["e2s_wall"] / K,
-                            "what": "no announcement: every step uploads its own frame (pinned, DMA straight into the gray buffer) "
-                                    "before its first kernel can start"},
+                   "ms_per_step": 1e3 * res["t_e2s"] / K, "wall_ms_per_step": 1e3 * res["e2s_wall"] / K,
+                   "upload": "host frames in pinned memory; every step uploads its own frame (DMA straight into the pipeline's gray buffer) "
+                             "before its first kernel can start; IMU rows up and pose / counters down inside every step",
+                   "announced": {"value": world * K / res["t_e2e"], "unit": "frames/s", "ms_per_step": 1e3 * res["t_e2e"] / K,
+                                 "wall_ms_per_step": 1e3 * res["e2e_wall"] / K, "steps_fed_by_prefetch": res["pref_hits"],
+                                 "what": "frame k+1 announced at the start of step k (rvio_vio_prefetch = the host's System::PushImageData "
+                                         "moment): its H2D copy runs on the copy stream inside step k's timed region (end event recorded after "
+                                         "rvio_vio_prefetch_fence)"},
                    "h2d_frame_us": round(res["h2d_frame_us"], 2)},
            "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": rf,
            "kernel_us_per_step": per_kernel_us, "stage_us_per_step": res["timeline"],
            "wall_ms_per_step": 1e3 * res["dev_wall"] / K, "batch": res["batch"], "sharded": res["sharded"]}
     out["parallelism"] = f"{world} independent stream(s), one per GPU (no collective on the data path)"
     out["per_rank_ms_per_step"] = {"device": [round(1e3 * t / K, 4) for t in res["t_dev_rank"]],
-                                   "e2e": [round(1e3 * t / K, 4) for t in res["t_e2e_rank"]]}
+                                   "e2e": [round(1e3 * t / K, 4) for t in res["t_e2s_rank"]]}
     out["cpu_affinity"] = res["affinity"]
+    out["host_us_per_step"] = res.get("host_us")              # per leg: C-call enqueue / blocked-in-sync / whole Python-level wall time
     try:
         from rvio_b200 import capi as _capi
         out["pdl"] = bool(_capi.lib().rvio_b200_pdl(-1))      # programmatic dependent launch between the frame's short dependent kernels

@@ -281,7 +281,7 @@ int rvio_b200_profile_report(char* buf, int cap);
 /* Programmatic dependent launch between the short dependent kernels of a frame (CLAHE -> pyramid -> LK -> RANSAC -> per-feature
  * -> normal terms): each of them becomes resident behind its predecessor and blocks in griddepcontrol.wait until that has
  * completed; results are unchanged, the launch gaps go.  enable: 1 / 0, negative = query; returns the previous setting.
- * Process-wide; the environment variable RVIO_B200_PDL sets the initial value. */
+ * Process-wide; on by default (measured +3.4 % frames/s at configs[1]), RVIO_B200_PDL=0 in the environment switches it off. */
 int rvio_b200_pdl(int enable);
 /* Raw CUDA stream used by a handle (so a host can order its own work / events against it). */
 void* rvio_tracker_stream(rvio_tracker* trk);

@@ -14,7 +14,7 @@ std::atomic<uint64_t> g_kernel_launches{0};
 
 std::atomic<int> g_profile_on{0};
 thread_local bool t_replay = false;
-static int pdl_default() { const char* e = getenv("RVIO_B200_PDL"); return e ? (atoi(e) != 0) : 0; }
+static int pdl_default() { const char* e = getenv("RVIO_B200_PDL"); return e ? (atoi(e) != 0) : 1; }
 std::atomic<int> g_pdl_on{pdl_default()};
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };

@@ -259,6 +259,14 @@ public:
         return mLastStatus >= 0 && valid != 0;
     }
 
+    // System::PushImageData (System.h:50, called from the image callback rvio_mono.cc:76): the frame is known to the host one
+    // or two iterations before MonoVIO pops it.  Announcing it here lets the library upload a pinned mono8 frame beside the
+    // frame in flight (rvio_vio_prefetch); MonoVIO on the same buffer then starts without its own upload.  Optional.
+    void PushImageData(const uint8_t* im, int width, int height, int stride_bytes, int channels)
+    {
+        mLastStatus = rvio_vio_prefetch(mHandle, im, width, height, stride_bytes, channels);
+    }
+
     int last_status() const { return mLastStatus; }
     rvio_vio* handle() { return mHandle; }
 
