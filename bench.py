@@ -398,16 +398,17 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
     # ---- batch leg (BASELINE configs[3]: independent streams, several per GPU, no communication): S handles driven by
     #      S host threads on the same device-resident frames; aggregate frames/s over the slowest stream (wall clock
     #      between device synchronisations; the single-stream `value` above is the CUDA-event number).
-    batch = None
     S = args.batch_streams
+    batch = None
     if S > 1:
-        # Round 1 saw this leg stall under torchrun: eight host threads were CAPTURING frame graphs concurrently while an NCCL
-        # process group (its watchdog / proxy threads) was alive.  Pre-roll and warm-up (which is where every frame graph of a
-        # stream is captured) now run one stream after the other on the main thread; the worker threads only replay.
-        import threading
         d_frames = [torch.from_numpy(f).to(dev) for f in frames]
         d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
         d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
+
+    def run_batch():
+        # Round 1 saw this leg stall under torchrun: eight host threads were CAPTURING frame graphs concurrently while an NCCL
+        # process group (its watchdog / proxy threads) was alive.  Pre-roll and warm-up (which is where every frame graph of a
+        # stream is captured) now run one stream after the other on the main thread; the worker threads only replay.
         vios = [host.Vio(cfg, local_rank) for _ in range(S)]
         Kb = min(K, 100)
 
@@ -466,22 +467,41 @@ def run_b200(args, cfg, wl, rank, world, local_rank):
                 t.join(timeout=60)
         for v in vios:
             v.close()
-        if not errs:
-            batch = {"streams_per_gpu": S, "steps_per_stream": Kb, "value": S * Kb / (t1 - t0), "unit": "frames/s",
+        if errs:
+            return None
+        return S * Kb / (t1 - t0), Kb
+
+    # Programmatic dependent launch keeps the NEXT kernel of a stream resident (and its shared memory / registers taken) while the
+    # current one runs: a gain for one stream that leaves most of the GPU idle, a cost when eight streams compete for the SMs.  The leg
+    # is therefore run in both settings (rvio_b200_pdl is a process-wide switch a multi-stream host would set) and reports both.
+    if S > 1:
+        pdl0 = L.rvio_b200_pdl(-1)
+        both = {}
+        for setting in (pdl0, 1 - pdl0):
+            L.rvio_b200_pdl(setting)
+            try:
+                r = run_batch()
+            except Exception:          # pragma: no cover
+                r = None
+            both["on" if setting else "off"] = r
+        L.rvio_b200_pdl(pdl0)
+        vals = {k: (v[0] if v else 0.0) for k, v in both.items()}
+        oks = {k: (1.0 if v else 0.0) for k, v in both.items()}
+        if world > 1:
+            # every rank takes part in the same collectives, whatever happened to its own batch leg (a rank that skipped one
+            # would leave the others waiting in NCCL for ever)
+            bt = torch.tensor([vals["on"], vals["off"], oks["on"], oks["off"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(bt, op=dist.ReduceOp.SUM)
+            vals = {"on": float(bt[0]), "off": float(bt[1])}
+            oks = {"on": float(bt[2]) / world, "off": float(bt[3]) / world}
+        good = {k: v for k, v in vals.items() if oks[k] == 1.0}
+        if good:
+            best = max(good, key=good.get)
+            Kb = next(v[1] for v in both.values() if v) if any(both.values()) else min(K, 100)
+            batch = {"streams_per_gpu": S, "steps_per_stream": Kb, "value": good[best], "unit": "frames/s", "n_gpus": world, "pdl": best,
+                     "by_pdl_setting": {k: round(v, 1) for k, v in good.items()},
                      "timing": "wall clock between device synchronisations, all streams concurrent (graphs captured beforehand, one stream at a time)"}
-        else:
-            batch = None
     res["batch"] = batch
-    if world > 1:
-        # every rank takes part in the same collectives, whatever happened to its own batch leg (a rank that skipped one
-        # would leave the others waiting in NCCL for ever)
-        bt = torch.tensor([batch["value"] if batch is not None else 0.0, 1.0 if batch is not None else 0.0],
-                          dtype=torch.float64, device=dev)
-        dist.all_reduce(bt, op=dist.ReduceOp.SUM)
-        if S > 1 and int(round(float(bt[1]))) == world and batch is not None:
-            batch["value"] = float(bt[0]); batch["n_gpus"] = world
-        else:
-            res["batch"] = None
     # ---- feature-sharded single stream (BASELINE configs[4]: 2048 features, 30-clone window): every rank is fed the same
     #      frames; LK all-gather + normal-term all-reduce are enqueued by the library on its own stream (in the frame graph)
     if world > 1 and not args.no_sharded:
