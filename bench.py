@@ -239,6 +239,10 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
     wall = 0.0
     infos = []
     host_tl = np.zeros(8, np.float32); host_us = []
+    stage_diag = bool(os.environ.get("RVIO_BENCH_STAGES_IN_LEGS"))        # diagnostic: stage stamps inside the measured legs (adds ~7 us / step)
+    if stage_diag:
+        L.rvio_vio_timeline(vio.h, 1, None)
+    stages = []
     while timed < K:
         if i >= n_frames:
             raise RuntimeError("stream too short for the requested steps")
@@ -271,8 +275,10 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
                 vio.prefetch_fence()
             ev1[timed].record(stream)
             timed += 1
-            L.rvio_vio_timeline(vio.h, 0, host_tl.ctypes.data)         # host wall clock of the step just finished: [6] enqueue, [7] blocked in the sync
+            L.rvio_vio_timeline(vio.h, 1 if stage_diag else 0, host_tl.ctypes.data)   # host wall clock of the step just finished: [6] enqueue, [7] blocked in the sync
             host_us.append((1e3 * float(host_tl[6]), 1e3 * float(host_tl[7])))
+            if stage_diag:
+                stages.append([1e3 * float(x) for x in host_tl[:6]])
             ui = vio.update_info()
             infos.append((int(ui.n_feat), int(ui.n_good), int(ui.rows_stacked), int(ui.rank), int(ui.rank_flags)))
         elif got_pose:
@@ -287,6 +293,8 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
     _LAST_DRIVE.update(host_enqueue_us=round(float(np.median([h[0] for h in host_us])), 1),
                        host_blocked_in_sync_us=round(float(np.median([h[1] for h in host_us])), 1),
                        wall_us=round(1e6 * wall / max(1, K), 1))
+    if stage_diag:
+        _LAST_DRIVE["stage_us"] = [round(float(v), 1) for v in np.median(np.array(stages), 0)]
     return step_ms, wall, L.rvio_b200_kernel_launches() - launches0, i, infos
 
 

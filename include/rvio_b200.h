@@ -230,7 +230,8 @@ int rvio_vio_step_dev(rvio_vio* vio, const uint8_t* img_dev, int pitch_bytes, co
                       const float* cand_px_dev, int n_cand, int cand_filtered, double* pose_out, int* pose_valid);
 /* Optional: announce a frame ahead of its step -- the moment the reference's host receives it (System::PushImageData,
  * src/rvio/System.h:50, InputBuffer.cc:42), one or two frames before System::MonoVIO pops it (System.cc:176-181).  A
- * single-channel frame in PINNED host memory is uploaded at once on a copy stream, beside the frame being processed; the
+ * single-channel frame in PINNED host memory is uploaded on a copy stream beside the frame being processed (the copy is enqueued
+ * as soon as the next rvio_vio_step has launched its own frame, so that it never sits in front of that step's image copy); the
  * rvio_vio_step that is later handed the same buffer (within the next two steps, contents unchanged) takes the uploaded copy
  * instead of uploading inside the step.  Any other frame (colour, pageable) is left to the step: the call does nothing.
  * Results are identical with or without the announcement. */

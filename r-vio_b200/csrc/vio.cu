@@ -75,6 +75,10 @@ struct rvio_vio {
     // buffer takes the slot instead of uploading
     cudaStream_t copys; cudaEvent_t ev_pref[2]; uint8_t* d_pref[2]; const uint8_t* pref_src[2]; int pref_next, pref_last;
     uint64_t pref_hits, pref_step[2], n_steps;    // a slot is honoured by the next two steps only (a forgotten announcement expires)
+    // An announcement is only NOTED by rvio_vio_prefetch; its H2D copy is enqueued right after the next step has launched its frame
+    // (or at once when that step is the announced frame's own): a copy enqueued BEFORE the step would sit on the copy engine in front
+    // of the step's own image copy, and one isolated H2D transfer has ~50 us of latency on the measured boxes.
+    const uint8_t* pend_src; int pend_stride; uint64_t pend_step;
     int window, min_clones, Fu, F;
     // device state (ping-pong)
     double* d_x[2]; double* d_P[2]; int xi, pi;
@@ -242,6 +246,7 @@ extern "C" int rvio_vio_create(const rvio_vio_cfg* cfg, int device, rvio_vio** o
     v->timeline = false;
     v->use_graphs = true; v->graph_launches = 0;
     v->copys = nullptr; v->pref_next = 0; v->pref_last = -1; v->pref_hits = 0; v->n_steps = 0; v->pref_step[0] = v->pref_step[1] = 0;
+    v->pend_src = nullptr; v->pend_stride = 0; v->pend_step = 0;
     for (int k = 0; k < 2; ++k) { v->ev_pref[k] = nullptr; v->d_pref[k] = nullptr; v->pref_src[k] = nullptr; }
     for (int k = 0; k < 8; ++k) { RVIO_CUDA_TRY(cudaEventCreate(&v->tl[k])); v->tl_ms[k] = 0.f; }
     RVIO_CUDA_TRY(cudaMalloc((void**)&v->d_stamps, sizeof(unsigned long long) * 8));
@@ -481,6 +486,24 @@ static bool host_buffer_is_pinned(rvio_vio* v, const uint8_t* p)
     return pinned;
 }
 
+// Enqueues the H2D copy of the noted announcement on the copy stream (rvio_vio_prefetch has created the stream, events and slots).
+static int issue_pending_prefetch(rvio_vio* v)
+{
+    const uint8_t* img = v->pend_src;
+    if (!img) return RVIO_OK;
+    v->pend_src = nullptr;
+    const size_t W = (size_t)v->cfg.tracker.width, H = (size_t)v->cfg.tracker.height;
+    int slot = v->pref_next;
+    for (int k = 0; k < 2; ++k) if (v->pref_src[k] == img) slot = k;      // announced twice: refresh the same slot
+    v->pref_next = 1 - slot;
+    // (the slot's previous reader, a step's device-to-device copy on the main stream, has completed: steps are synchronous, and the
+    // step in flight reads the OTHER slot)
+    RVIO_CUDA_TRY(cudaMemcpy2DAsync(v->d_pref[slot], W, img, (size_t)v->pend_stride, W, H, cudaMemcpyHostToDevice, v->copys));
+    RVIO_CUDA_TRY(cudaEventRecord(v->ev_pref[slot], v->copys));
+    v->pref_src[slot] = img; v->pref_last = slot; v->pref_step[slot] = v->pend_step;
+    return RVIO_OK;
+}
+
 static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int height, int stride, int channels,
                          const uint8_t* img_dev, int pitch, const double* imu, int n_imu,
                          const float* cand_host, const float* cand_dev_in, int n_cand, int cand_filtered,
@@ -587,6 +610,10 @@ static int vio_step_impl(rvio_vio* v, const uint8_t* img_host, int width, int he
                            16 + sizeof(double) * 8 * (size_t)n_imu, cand_dev, n_cand > 0 && !cand_dev_in, n_cand, n_cand, cand_filtered, use_det, &fo);
         if (rc != RVIO_OK) return rc;
     }
+    if (v->pend_src) {                                      // an announced frame: its upload starts now, beside this frame's work
+        const int rp = issue_pending_prefetch(v);
+        if (rp != RVIO_OK) return rp;
+    }
     clock_gettime(CLOCK_MONOTONIC, &h1);
     int r3 = tracker_wait(v->trk);                          // the one synchronisation of the frame
     if (r3 != RVIO_OK) return r3;
@@ -641,13 +668,11 @@ extern "C" int rvio_vio_prefetch(rvio_vio* v, const uint8_t* img, int width, int
             RVIO_CUDA_TRY(cudaMalloc((void**)&v->d_pref[k], W * H));
         }
     }
-    int slot = v->pref_next;
-    for (int k = 0; k < 2; ++k) if (v->pref_src[k] == img) slot = k;      // announced twice: refresh the same slot
-    v->pref_next = 1 - slot;
-    // (the slot's previous reader, a step's device-to-device copy on the main stream, has completed: steps are synchronous)
-    RVIO_CUDA_TRY(cudaMemcpy2DAsync(v->d_pref[slot], W, img, (size_t)stride_bytes, W, H, cudaMemcpyHostToDevice, v->copys));
-    RVIO_CUDA_TRY(cudaEventRecord(v->ev_pref[slot], v->copys));
-    v->pref_src[slot] = img; v->pref_last = slot; v->pref_step[slot] = v->n_steps;
+    if (v->pend_src && v->pend_src != img) {               // two announcements without a step in between: the older one goes up now
+        const int rc = issue_pending_prefetch(v);
+        if (rc != RVIO_OK) return rc;
+    }
+    v->pend_src = img; v->pend_stride = stride_bytes; v->pend_step = v->n_steps;
     return RVIO_OK;
 }
 
@@ -657,6 +682,7 @@ extern "C" int rvio_vio_prefetch_fence(rvio_vio* v, uint64_t* hits)
 {
     RVIO_ARG_CHECK(v);
     if (hits) *hits = v->pref_hits;
+    if (v->pend_src) { const int rp = issue_pending_prefetch(v); if (rp != RVIO_OK) return rp; }
     if (v->copys && v->pref_last >= 0) {
         RVIO_CUDA_TRY(cudaSetDevice(v->device));
         RVIO_CUDA_TRY(cudaStreamWaitEvent(v->stream, v->ev_pref[v->pref_last], 0));
@@ -670,6 +696,11 @@ extern "C" int rvio_vio_step(rvio_vio* v, const uint8_t* img, int width, int hei
 {
     RVIO_ARG_CHECK(v && img && (n_cand <= 0 || cand_px));
     const uint64_t step_no = v->n_steps++;
+    if (v->pend_src == img && channels == 1 && n_imu >= 2) {      // announced and stepped back to back: the upload cannot wait
+        RVIO_CUDA_TRY(cudaSetDevice(v->device));
+        const int rp = issue_pending_prefetch(v);
+        if (rp != RVIO_OK) return rp;
+    }
     if (v->copys && channels == 1 && n_imu >= 2)
         for (int k = 0; k < 2; ++k)
             if (v->pref_src[k] && step_no - v->pref_step[k] > 1) v->pref_src[k] = nullptr;      // expired
