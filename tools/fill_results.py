@@ -36,6 +36,9 @@ vals = {
     "G2": fmt(g2["value"]), "G2RANKS": " / ".join(f"{x:.3f}" for x in g2["per_rank_ms_per_step"]["device"]),
     "G2BATCH": fmt(g2["batch"]["value"]),
     "G2SH": fmt(g2["sharded"]["value"]), "G2SH1": fmt(g2["sharded"]["unsharded_same_stream"]["value"]),
+    "G2SHMS": fmt(g2["sharded"]["ms_per_step"], 3),
+    "G2AG": fmt(g2["sharded"]["collectives_us_per_frame"]["allgather_lk"], 1),
+    "G2AR": fmt(g2["sharded"]["collectives_us_per_frame"]["allreduce_normal_terms"], 1),
     "G2EFF": f"{g2['value'] / (2 * b['value']):.2f}",
     "SPEEDUP": f"{b['e2e']['value'] / r['value']:.1f}", "SPEEDUPV": f"{b['value'] / r['value']:.1f}",
     "T_TR": fmt(tl["tracker"]), "T_FE": fmt(tl["feature+normal_terms"]), "T_SO": fmt(tl["solve"]),
