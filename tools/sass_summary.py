@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel SASS summary of librvio_b200.so (runs without a GPU): instruction counts of the mnemonics that matter for
 the Blackwell-evidence table of /opt/skills/guides/B200_PROFILING.md (UTMALDG = TMA, DMMA/HMMA/UTC*MMA = tensor cores,
-LDGSTS = cp.async, SYNCS = mbarrier, DFMA = FP64 SIMT ...).
+LDGSTS = cp.async, SYNCS = mbarrier, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents of programmatic dependent
+launch, DFMA = FP64 SIMT ...).
 
     python tools/sass_summary.py > profiles/sass_r02.md
 """
@@ -13,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "r-vio_b200", "librvio_b200.so")
-KEYS = ["DMMA", "HMMA", "UTC", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "LDTM", "DFMA", "DMUL", "DADD", "FFMA", "IMAD", "LDG", "STG", "LDS", "STS",
+KEYS = ["DMMA", "HMMA", "UTC", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "LDTM", "ACQBULK", "PREEXIT", "DFMA", "DMUL", "DADD", "FFMA", "IMAD", "LDG", "STG", "LDS", "STS",
         "BAR", "SHFL", "REDUX", "ATOM", "MUFU", "LDL", "STL"]
 
 
@@ -40,8 +41,9 @@ def main():
     names = demangle(list(funcs))
     print("# SASS summary of `r-vio_b200/librvio_b200.so` (sm_100a), `cuobjdump -sass`, instruction counts per kernel\n")
     print("Tensor-core / TMA evidence: `DMMA` = FP64 tensor-core MMA (`mma.sync.m8n8k4.f64`), `UTMALDG` = TMA tensor load "
-          "(`cp.async.bulk.tensor`), `SYNCS` = mbarrier operations, `LDGSTS` = `cp.async`.\n")
-    cols = ["DMMA", "UTMALDG", "SYNCS", "LDGSTS", "DFMA", "DMUL", "FFMA", "LDG", "STG", "LDS", "STS", "BAR", "SHFL", "REDUX", "ATOM", "LDL", "STL"]
+          "(`cp.async.bulk.tensor`), `SYNCS` = mbarrier operations, `LDGSTS` = `cp.async`, `ACQBULK` / `PREEXIT` = `griddepcontrol.wait` / "
+          "`griddepcontrol.launch_dependents` (programmatic dependent launch, DESIGN.md section 5).\n")
+    cols = ["DMMA", "UTMALDG", "SYNCS", "LDGSTS", "ACQBULK", "PREEXIT", "DFMA", "DMUL", "FFMA", "LDG", "STG", "LDS", "STS", "BAR", "SHFL", "REDUX", "ATOM", "LDL", "STL"]
     print("| kernel | instr | " + " | ".join(cols) + " |")
     print("|---|---|" + "---|" * len(cols))
     tot = collections.Counter()
