@@ -56,7 +56,7 @@ wl = dict(imus=[np.zeros((10, 8))] * 8, cand2=[np.zeros((5, 2), np.float32)] * 8
 bench._LINE_CTX.update(cfg=cfg, wl=wl, world=2, K=4, W=3, peaks=dict(hbm_gbs=6564.2, _measured=True), workload=dict(workload="test"))
 res = dict(t_dev=0.002, t_e2e=0.004, t_e2s=0.005, dev_ms=[0.5] * 4, e2e_ms=[1.0] * 4, launches=80, clocks=dict(sm_mhz=1965.0),
            prof=dict(), dev_wall=0.002, e2e_wall=0.004, e2s_wall=0.005, timeline=None, batch=None, infos=[(1, 1, 9, 9, 0)],
-           affinity=None, sharded=None, t_dev_rank=[0.002, 0.0019], t_e2s_rank=[0.005, 0.0048], pref_hits=4, h2d_frame_us=12.0)
+           affinity=None, sharded=None, t_dev_rank=[0.002, 0.0019], t_e2e_rank=[0.004, 0.0038], pref_hits=4, h2d_frame_us=12.0)
 bench._arm_legs_deadline(res, int(sys.argv[1]))
 time.sleep(30)            # "an extra leg that never returns"
 print("not reached")
@@ -75,8 +75,8 @@ def test_legs_deadline_prints_the_line_from_completed_legs(tmp_path):
     assert out0.returncode == 0, out0.stderr[-800:]
     line = json.loads(out0.stdout.strip().splitlines()[-1])
     assert line["metric"] == "vio_frames_per_sec" and line["n_gpus"] == 2 and line["steps"] == 4
-    assert abs(line["value"] - 2 * 4 / 0.002) < 1e-6 and abs(line["e2e"]["value"] - 2 * 4 / 0.005) < 1e-6
-    assert abs(line["e2e"]["announced"]["value"] - 2 * 4 / 0.004) < 1e-6
+    assert abs(line["value"] - 2 * 4 / 0.002) < 1e-6 and abs(line["e2e"]["value"] - 2 * 4 / 0.004) < 1e-6
+    assert abs(line["e2e"]["strict"]["value"] - 2 * 4 / 0.005) < 1e-6
     assert "legs_deadline" in line and line["sharded"] is None and line["roofline"] is None
     out1 = subprocess.run([sys.executable, str(script), "1"], capture_output=True, text=True, env=env, timeout=120)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
