@@ -650,17 +650,20 @@ def sharded_leg(args, L, dev, flush, rank, world, local_rank):
         # x+ / P+ whenever the reference's cut would not have discarded anything, which tests/dist_sharded_vio.py checks on this stream).
         # (b) With every row kept on every frame (RVIO_RANK_RULE_FULL_INFORMATION): the same arithmetic per frame as the sharded run, so
         # THIS ratio is what the sharding itself buys; (a) additionally contains the cost of the sweep.
-        for key, full in (("unsharded_same_stream", False), ("unsharded_all_rows_kept", True)):
-            ref = host.Vio(cfg, local_rank)
-            if full:
-                ref.set_rank_rule(True)
-            ms1, _, _, _, inf1 = drive(L, ref, wl, Ks, Ws, dev, True, True, flush)
-            ref.close()
-            out[key] = {"value": Ks / (float(np.sum(ms1)) / 1e3), "ms_per_step": float(np.mean(ms1)),
-                        "undecided_rank_rule_frames": int(sum(1 for x in inf1 if x[4] & 4)),
-                        "frames_resolved_by_givens_sweep": int(sum(1 for x in inf1 if x[4] & 2))}
-        out["speedup_vs_1gpu"] = (float(np.sum(out["unsharded_same_stream"]["ms_per_step"])) * Ks / 1e3) / tmax
-        out["speedup_vs_1gpu_same_rows_kept"] = (out["unsharded_all_rows_kept"]["ms_per_step"] * Ks / 1e3) / tmax
+        for key, full, ratio in (("unsharded_same_stream", False, "speedup_vs_1gpu"),
+                                 ("unsharded_all_rows_kept", True, "speedup_vs_1gpu_same_rows_kept")):
+            try:                                           # a failure here must not cost the sharded numbers above
+                ref = host.Vio(cfg, local_rank)
+                if full:
+                    ref.set_rank_rule(True)
+                ms1, _, _, _, inf1 = drive(L, ref, wl, Ks, Ws, dev, True, True, flush)
+                ref.close()
+                out[key] = {"value": Ks / (float(np.sum(ms1)) / 1e3), "ms_per_step": float(np.mean(ms1)),
+                            "undecided_rank_rule_frames": int(sum(1 for x in inf1 if x[4] & 4)),
+                            "frames_resolved_by_givens_sweep": int(sum(1 for x in inf1 if x[4] & 2))}
+                out[ratio] = (float(np.sum(ms1)) / 1e3) / tmax
+            except Exception as e:                         # pragma: no cover
+                out[key] = {"error": repr(e)[:200]}
     return out
 
 
