@@ -211,6 +211,25 @@ def bind_to_gpu_numa_node(local_rank):
 
 # ----------------------------------------------------------------------------------------- B200 arm
 _LAST_DRIVE = {}
+_RAW = {}
+
+
+def raw_abi(L):
+    """The four per-frame entry points with plain-pointer prototypes (what a C / C++ host hands to the C ABI): the timed loop passes
+    addresses computed beforehand instead of going through the NumPy-checking Python adaptor (r-vio_b200/host.py: ~15 us per step of
+    ndpointer validation and array normalisation that a compiled host does not have)."""
+    import ctypes as C
+    if not _RAW:
+        vp, ci = C.c_void_p, C.c_int
+        for name, args in (("rvio_vio_step", [vp, vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp, vp]),
+                           ("rvio_vio_step_dev", [vp, vp, ci, vp, ci, vp, ci, ci, vp, vp]),
+                           ("rvio_vio_prefetch", [vp, vp, ci, ci, ci, ci]),
+                           ("rvio_vio_prefetch_fence", [vp, vp])):
+            f = L[name]                                    # a fresh function object: the adaptor's own prototypes stay as they are
+            f.argtypes = args
+            f.restype = ci
+            _RAW[name] = f
+    return _RAW
 
 
 def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
@@ -230,6 +249,26 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
         d_c1 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand1"]]
         d_c2 = [torch.from_numpy(c).to(dev) if len(c) else None for c in wl["cand2"]]
         torch.cuda.synchronize()
+    # ---- everything the per-frame calls need, as plain addresses (device detector mode; the precomputed-candidates protocol keeps the
+    #      Python adaptor)
+    import ctypes as C
+    from rvio_b200 import capi
+    raw = raw_abi(L) if inloop else None
+    if raw:
+        Wpx, Hpx = int(frames[0].shape[1]), int(frames[0].shape[0])
+        imu_ptr = [int(a.ctypes.data) for a in imus]
+        imu_n = [int(a.shape[0]) for a in imus]
+        assert all(a.dtype == np.float64 and a.flags.c_contiguous and (a.ndim == 2 and a.shape[1] == 8 or a.size == 0) for a in imus)
+        if dev_inputs:
+            img_ptr = [int(t.data_ptr()) for t in d_frames]
+        else:
+            assert all(f.dtype == np.uint8 and f.flags.c_contiguous and f.shape == (Hpx, Wpx) for f in frames)
+            img_ptr = [int(f.ctypes.data) for f in frames]
+        pose_buf = np.zeros(7); pose_ptr = int(pose_buf.ctypes.data)
+        valid = C.c_int(0); valid_ptr = C.addressof(valid)
+        r_step, r_step_dev, r_pref, r_fence = (raw["rvio_vio_step"], raw["rvio_vio_step_dev"], raw["rvio_vio_prefetch"],
+                                               raw["rvio_vio_prefetch_fence"])
+        hnd = vio.h
     got_pose = False
     i = 0
     timed, warm = 0, 0
@@ -256,13 +295,22 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
                 launches0 = L.rvio_b200_kernel_launches()
             ev0[timed].record(stream)
             t0 = time.perf_counter()
-        if dev_inputs:
-            if inloop:
-                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i], None, -1)
+        if raw:
+            if dev_inputs:
+                rc = r_step_dev(hnd, img_ptr[i], Wpx, imu_ptr[i], imu_n[i], None, -1, 0, pose_ptr, valid_ptr)
             else:
-                dc = (d_c2 if got_pose else d_c1)[i]
-                pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
-                                    dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
+                if prefetch and i + 1 < n_frames:
+                    # the host announces frame i+1 when it arrives (System::PushImageData), i.e. while frame i is processed: its H2D
+                    # copy runs on the library's copy stream inside THIS step's timed region (fenced before the end event below)
+                    r_pref(hnd, img_ptr[i + 1], Wpx, Hpx, Wpx, 1)
+                rc = r_step(hnd, img_ptr[i], Wpx, Hpx, Wpx, 1, imu_ptr[i], imu_n[i], None, -1, 0, pose_ptr, valid_ptr)
+            if rc < 0:
+                capi.check(rc, "rvio_vio_step")
+            pose = pose_buf if valid.value else None
+        elif dev_inputs:
+            dc = (d_c2 if got_pose else d_c1)[i]
+            pose = vio.step_dev(d_frames[i].data_ptr(), frames[i].shape[1], imus[i],
+                                dc.data_ptr() if dc is not None else None, 0 if dc is None else dc.shape[0])
         else:
             if prefetch and i + 1 < n_frames:
                 # the host announces frame i+1 when it arrives (System::PushImageData), i.e. while frame i is processed: its H2D
@@ -272,7 +320,10 @@ def drive(L, vio, wl, K, W, dev, inloop, dev_inputs, flush, prefetch=False):
         if timing:
             wall += time.perf_counter() - t0
             if prefetch:
-                vio.prefetch_fence()
+                if raw:
+                    r_fence(hnd, None)
+                else:
+                    vio.prefetch_fence()
             ev1[timed].record(stream)
             timed += 1
             L.rvio_vio_timeline(vio.h, 1 if stage_diag else 0, host_tl.ctypes.data)   # host wall clock of the step just finished: [6] enqueue, [7] blocked in the sync
