@@ -17,7 +17,7 @@ r = {0: [], 1: []}
 for f in sorted(glob.glob('gpurun_out/ab_pdl*_*.json')):
     try:
         j = json.loads(open(f).read().strip().splitlines()[-1])
-        r[int(j['pdl'])].append((j['value'], j['e2e']['value'], j['e2e']['sync']['value'], j['e2e'].get('h2d_frame_us')))
+        r[int(j['pdl'])].append((j['value'], j['e2e']['value'], j['e2e']['strict']['value'], j['e2e'].get('h2d_frame_us')))
     except Exception as e:
         print('bad', f, e)
 print(r)
