@@ -3,15 +3,18 @@
 
 Contract (see task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
   step      = one frame of the hot path on a seeded synthetic EuRoC-shaped stream (BASELINE.json configs[1] by default:
-              752x480 mono + 200 Hz IMU, 200 features, 11-clone window), i.e. one System::MonoVIO iteration.
-  value     = frames/s with the frames (and the detector's corner candidates) already resident in HBM (rvio_vio_step_dev).
-  e2e       = frames/s through the public C ABI with HOST buffers (rvio_vio_step): per frame the image + IMU go up and
-              the pose comes back inside the timed region.
-  roofline  = dominant kernel of a step (per-kernel CUDA events recorded by the library on its own stream).
+              752x480 mono + 200 Hz IMU, 200 features, 11-clone window), i.e. one System::MonoVIO iteration, the corner detector
+              (FeatureDetector::DetectWithSubPix) included in every step of both arms (--detector inloop, the default).
+  value     = frames/s with the frames already resident in HBM (rvio_vio_step_dev).
+  e2e       = frames/s through the public C ABI with HOST buffers in pinned memory: per timed step one frame upload (frame k+1,
+              announced while frame k is processed: rvio_vio_prefetch), the IMU rows up, the pose back; e2e.strict = the same
+              without the announcement (every step uploads its own frame before its first kernel can start).
+  roofline  = dominant kernel of a step's critical path (per-kernel CUDA events recorded by the library on its own stream).
   cpu_baseline / --impl reference = the same loop on the host cores: OpenCV stages through the real OpenCV (cv2, all
               threads), Eigen stages through the single-threaded C restatement in oracle/ (the reference is single threaded).
-The corner detector is NOT on the hot path: both arms are fed the same pre-computed corner candidates
-(cv2.goodFeaturesToTrack on the equalised frame); FindNewer + refill run inside both arms.
+Order of a run: untimed settling passes, the three measured legs (e2e.strict, e2e, value), their reduction over the ranks, then the
+extra legs under a deadline (stage timeline, per-kernel profile, 8 streams per GPU, N > 1: the configs[4] stream feature-sharded
+over the N GPUs, N = 1: configs[2] stream, worst-case updates, CPU baseline).
 N > 1: one process per GPU, each rank runs an independent stream (BASELINE configs[3] style replicas, no collective on the
 data path); value = total frames / max-over-ranks time ("scaling": "weak").
 """
